@@ -1,0 +1,164 @@
+/*
+ * lpgnn.h -- C ABI of liblpgnn.so: the B200 (sm_100a) kernels behind the lp-gnn hot path.
+ *
+ * This is the drop-in boundary.  The reference (vbdai/lp-gnn) is pure Python and reaches its
+ * numerics through torch_geometric / torch_sparse / ATen; each entry point below replaces one
+ * of those third-party calls AT THE REFERENCE CALL SITE cited next to it, so a maintainer of
+ * the reference binds this library with ctypes and keeps arch.py's module
+ * classes, forward(batch) and state_dict keys unchanged.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer unless the name ends in _host.  The library never
+ *    allocates user-visible memory: outputs and workspaces are caller-allocated (sizes from the
+ *    *_workspace_bytes queries).  All work is enqueued on `stream` (a cudaStream_t); nothing
+ *    synchronises unless stated.
+ *  - Row-major dense matrices, leading dimension = number of columns.  Feature matrices are
+ *    float32 (LPGNN_F32) or bfloat16 (LPGNN_BF16); accumulation is always float32.
+ *  - Graph indices are int32 (max(m, n, nnz) < 2^31; BASELINE C4 has nnz = 1e7).
+ *  - Return value: 0 on success, a negative LPGNN_E* code otherwise; lpgnn_last_error() gives a
+ *    thread-local message.  There is no CPU fallback anywhere: without an sm_100 device every
+ *    call fails with LPGNN_ENODEVICE.
+ */
+#ifndef LPGNN_H_
+#define LPGNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPGNN_VERSION 100 /* 0.1.0 */
+
+#define LPGNN_OK 0
+#define LPGNN_EINVAL (-1)    /* bad argument (shape, alignment, null pointer) */
+#define LPGNN_ECUDA (-2)     /* CUDA runtime / driver error, see lpgnn_last_error() */
+#define LPGNN_ENODEVICE (-3) /* no CUDA device, or device is not sm_100 */
+#define LPGNN_EWORKSPACE (-4)/* workspace too small */
+
+#define LPGNN_F32 0
+#define LPGNN_BF16 1
+
+/* epilogue flags of the node transforms */
+#define LPGNN_EPI_NONE 0
+#define LPGNN_EPI_RELU 1
+
+typedef void* lpgnn_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define LPGNN_API __attribute__((visibility("default")))
+#else
+#define LPGNN_API
+#endif
+
+LPGNN_API int lpgnn_version(void);
+LPGNN_API const char* lpgnn_last_error(void);
+/* Fills SM count and compute capability of the current device. */
+LPGNN_API int lpgnn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a1) Graph construction.  Replaces torch_sparse.SparseTensor.from_edge_index
+ * (reference dataset.py:301-304) and SparseTensor.t() (reference arch.py:71).
+ *
+ * Input: COO of the m x n LP matrix A in any order (coo_row[e] in [0,m), coo_col[e] in [0,n),
+ * int64 if idx_is_i64 else int32).  Output: canonical CSR (stable sort by row, then column:
+ * row-major, ascending column inside a row, duplicates kept in input order) and the CSC view
+ * (stable sort of the CSR entries by column: column-major, ascending row inside a column) with
+ * the permutation csr2csc (val_csc[k] = val[csr2csc[k]]).  Bit-exact with the reference's
+ * ordering; all integer work, deterministic (no atomics on ordered data).
+ * ------------------------------------------------------------------------------------------- */
+LPGNN_API size_t lpgnn_graph_build_workspace_bytes(int64_t nnz, int32_t m, int32_t n);
+LPGNN_API int lpgnn_graph_build(const void* coo_row, const void* coo_col, int idx_is_i64,
+                      const float* coo_val, int64_t nnz, int32_t m, int32_t n,
+                      int32_t* rowptr /*[m+1]*/, int32_t* col /*[nnz]*/, float* val /*[nnz]*/,
+                      int32_t* colptr /*[n+1]*/, int32_t* row_csc /*[nnz]*/, float* val_csc /*[nnz]*/,
+                      int32_t* csr2csc /*[nnz]*/,
+                      void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a2) Aggregation.  Replaces torch_sparse.matmul(adj_t, x, reduce='add') == spmm_sum, reached
+ * from PyG GraphConv.message_and_aggregate (reference arch.py:75-80), forward AND backward
+ * (backward wrt the dense operand is the same call on the other orientation).
+ *
+ *   Y[i, :] = sum_{e in [ptr[i], ptr[i+1])} val[e] * X[idx[e], :]     (e ascending, fp32 accumulate)
+ *
+ * X is [n_src, F], Y is [rows, F], both of `dtype`.  F * sizeof(elem) must be a multiple of 16.
+ * Atomics-free and deterministic: one warp (or sub-warp) owns an output row.
+ * ------------------------------------------------------------------------------------------- */
+LPGNN_API int lpgnn_spmm(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,
+               const void* X, void* Y, int32_t F, int dtype, lpgnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a2+a3, input layer) Fused aggregation + node transform for narrow inputs (conv1 of GCN_FC:
+ * in = p or q = 8).  Replaces GraphConv.forward = lin_rel(spmm(adj_t, x_src)) + lin_root(x_dst)
+ * (reference arch.py:75-80 with the (p,q)->hids layer built at arch.py:170) and the relu_ at
+ * arch.py:182:
+ *
+ *   out[i,:] = epi( (sum_e val[e]*Xsrc[idx[e],:]) * W_rel^T + b_rel + Xdst[i,:] * W_root^T )
+ *
+ * Xsrc [n_src,k_src] f32, Xdst [rows,k_dst] f32, W_rel [N,k_src] f32, W_root [N,k_dst] f32,
+ * b_rel [N] f32; k_src,k_dst <= 64; out [rows,N] of out_dtype.  If agg_out != NULL the fp32
+ * aggregate [rows,k_src] is also written (needed by the weight gradient).
+ * ------------------------------------------------------------------------------------------- */
+LPGNN_API int lpgnn_conv_in_fused(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,
+                        const float* Xsrc, int32_t k_src, const float* Xdst, int32_t k_dst,
+                        const float* W_rel, const float* b_rel, const float* W_root, int32_t N,
+                        void* out, int out_dtype, int epilogue, float* agg_out,
+                        lpgnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a3) Dense node transform of a hidden GraphConv layer.  Replaces lin_rel(agg) + lin_root(x_dst)
+ * (two torch Linear / cuBLAS sgemm calls + bias + add, PyG GraphConv.forward reached from
+ * reference arch.py:75-80) and the following relu_ (arch.py:188) with ONE GEMM over the
+ * concatenated reduction dimension:
+ *
+ *   out[M,N] = epi( A1[M,K1] * W1[N,K1]^T + A2[M,K2] * W2[N,K2]^T + bias[N] )
+ *
+ * dtype LPGNN_BF16: tcgen05 tensor-core kernel (TMA-fed, TMEM accumulators, fp32 accumulate);
+ * operands and out are bf16, bias f32; K1,K2 multiples of 64, N multiple of 64 (A2/W2 may be
+ * NULL with K2 = 0).  dtype LPGNN_F32: fp32 CUDA-core kernel (the 1e-4 parity mode); operands,
+ * bias and out are f32 (K1,K2 multiples of 4).
+ * ------------------------------------------------------------------------------------------- */
+LPGNN_API int lpgnn_node_transform(const void* A1, int32_t K1, const void* W1,
+                         const void* A2, int32_t K2, const void* W2,
+                         const float* bias, int32_t M, int32_t N,
+                         void* out, int dtype, int epilogue, lpgnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a4+a5) Basis-status head + knowledge masking.  Replaces torch.nn.Linear(H,3) (reference
+ * arch.py:190) and add_knowledge (reference arch.py:129-141):
+ *
+ *   raw[i,:]    = H[i,:] * W^T + b                       (W [3,Hdim] f32, b [3] f32)
+ *   logits[i,:] = 10 * raw / max(||raw||_2, 1e-12)
+ *   logits[i,0] -= 10 where feas[i, q-3] != 0 ;  logits[i,2] -= 10 where feas[i, q-1] != 0
+ *
+ * H [rows,Hdim] of h_dtype; feas [rows,q] f32 (the node features x_s / x_t); logits [rows,3] f32.
+ * raw_out (optional, [rows,3] f32) keeps the un-normalised logits for the backward pass.
+ * ------------------------------------------------------------------------------------------- */
+LPGNN_API int lpgnn_head_mask(const void* H, int h_dtype, int32_t rows, int32_t Hdim,
+                    const float* W, const float* b, const float* feas, int32_t q,
+                    float* logits, float* raw_out, lpgnn_stream_t stream);
+
+/* add_knowledge alone on given logits (reference arch.py:129-141; used by callers that own the
+ * head GEMM, e.g. GCNRand-style baselines). in/out [rows,3] f32, may alias. */
+LPGNN_API int lpgnn_add_knowledge(const float* logits_in, int32_t rows, const float* feas, int32_t q,
+                        float* logits_out, lpgnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a6) Basis decision.  Replaces val.inference_gnn (reference val.py:106-124): softmax over the
+ * 3 classes, NaN -> 0, the m largest P(basic) over all m+n nodes get status 1 (ties at the
+ * threshold go to the lower node index), the others get 0 if p0 >= p2 else 2.
+ * logits_cons [m,3] f32, logits_vars [n,3] f32 -> status [m+n] (int64 if status_is_i64 else
+ * uint8), constraints first.  counts_out (optional, int32[4] device): number of nodes with
+ * status 0,1,2 and number of basic variables (the two invariants asserted at val.py:118-122).
+ * ------------------------------------------------------------------------------------------- */
+LPGNN_API size_t lpgnn_basis_select_workspace_bytes(int64_t total_nodes);
+LPGNN_API int lpgnn_basis_select(const float* logits_cons, int32_t m, const float* logits_vars, int32_t n,
+                       int32_t k_basic, void* status, int status_is_i64, int32_t* counts_out,
+                       void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPGNN_H_ */

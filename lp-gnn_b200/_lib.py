@@ -1,0 +1,89 @@
+"""ctypes binding of ``liblpgnn.so`` (C ABI: ``include/lpgnn.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C lp-gnn_b200/csrc`` and
+loaded lazily on first use.  There is NO fallback: if the shared object is missing, or no sm_100
+device is present, every op raises ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch  # noqa: F401  (loads libcudart.so.12 into the process before liblpgnn.so is opened)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblpgnn.so")
+
+F32, BF16 = 0, 1
+EPI_NONE, EPI_RELU = 0, 1
+
+_p = C.c_void_p
+_i32, _i64, _sz, _int = C.c_int32, C.c_int64, C.c_size_t, C.c_int
+
+# name -> (restype, argtypes); must list every symbol include/lpgnn.h declares
+SIGNATURES = {
+    "lpgnn_version": (_int, []),
+    "lpgnn_last_error": (C.c_char_p, []),
+    "lpgnn_device_info": (_int, [C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)]),
+    "lpgnn_graph_build_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "lpgnn_graph_build": (_int, [_p, _p, _int, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "lpgnn_spmm": (_int, [_p, _p, _p, _i32, _p, _p, _i32, _int, _p]),
+    "lpgnn_conv_in_fused": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p, _i32, _p, _int, _int, _p, _p]),
+    "lpgnn_node_transform": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _int, _p]),
+    "lpgnn_head_mask": (_int, [_p, _int, _i32, _i32, _p, _p, _p, _i32, _p, _p, _p]),
+    "lpgnn_add_knowledge": (_int, [_p, _i32, _p, _i32, _p, _p]),
+    "lpgnn_basis_select_workspace_bytes": (_sz, [_i64]),
+    "lpgnn_basis_select": (_int, [_p, _i32, _p, _i32, _i32, _p, _int, _p, _p, _sz, _p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Opens liblpgnn.so and binds every entry point.  Raises if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"liblpgnn.so not found at {LIB_PATH}: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C lp-gnn_b200/csrc`. There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().lpgnn_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return F32
+    if dt == torch.bfloat16:
+        return BF16
+    raise TypeError(f"lpgnn kernels take float32 or bfloat16 features, got {dt}")
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("lpgnn ops run on a CUDA (sm_100) device only; got a CPU tensor. "
+                               "There is no CPU fallback.")

@@ -1,0 +1,163 @@
+"""Drop-in for the reference ``arch.py`` (GCN_FC stack): same class names, constructor signatures,
+``forward(batch) -> (logit_cons[m,3], logit_vars[n,3])`` and state_dict keys, so
+``model = eval(args.arch)`` after ``from arch import *`` (reference train.py:9,79; val.py:6,266;
+scripts/pred_basis.py:5,128) and an existing ``mdl.pth`` keep working -- but every numeric step runs
+in the hand-written sm_100a kernels of ``liblpgnn.so``:
+
+    reference (arch.py)                                   here
+    --------------------------------------------------    ------------------------------------------
+    GraphConvTwoDirection.forward, conv1   (65-81, 181)   ops.conv_in_fused  x2   (aggregate+transform+relu)
+    GraphConvTwoDirection.forward, hidden  (65-81, 185)   ops.spmm x2 + ops.node_transform x2 (tcgen05 / fp32)
+    F.dropout + relu_                      (186-188)      fused into the transform epilogue (relu) + mask
+    lin_left / lin_right + add_knowledge   (190-191)      ops.head_mask x2
+
+Precision: ``model.precision = 'fp32'`` (default; logits within 1e-4 of the reference) or
+``'bf16'`` (bf16 activations / tensor-core GEMMs, fp32 accumulate; within 2e-2).  ``.half()`` /
+``.bfloat16()`` select the bf16 mode (the reference's ``--fp16`` inference switch, val.py:269,
+pred_basis.py:146) while the parameters stay fp32 master copies.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from . import ops
+from .graph import BipartiteCSR
+
+__all__ = ["GraphConv", "GraphConvTwoDirection", "GCNBase", "GCN_FC", "add_knowledge"]
+
+
+class _Linear(nn.Module):
+    """Parameter container with torch_geometric ``Linear``'s layout and default init
+    (weight [out,in] kaiming_uniform(a=sqrt 5); bias U(+-1/sqrt(in)))."""
+
+    def __init__(self, in_features, out_features, bias=True):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.weight = nn.Parameter(torch.empty(out_features, in_features))
+        self.bias = nn.Parameter(torch.empty(out_features)) if bias else None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            bound = 1.0 / math.sqrt(self.in_features) if self.in_features > 0 else 0.0
+            nn.init.uniform_(self.bias, -bound, bound)
+
+
+class GraphConv(nn.Module):
+    """PyG ``GraphConv((in_src, in_dst), out, aggr='add')`` parameter layout: ``lin_rel`` (with
+    bias) acts on the aggregated source features, ``lin_root`` (no bias) on the destination's own."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        if isinstance(in_channels, int):
+            in_channels = (in_channels, in_channels)
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin_rel = _Linear(in_channels[0], out_channels, bias=True)
+        self.lin_root = _Linear(in_channels[1], out_channels, bias=False)
+
+
+class _CastCache:
+    """bf16 copies of fp32 master weights, refreshed when the parameter changes (version counter)."""
+
+    def __init__(self):
+        self._c = {}
+
+    def get(self, p: torch.Tensor, dtype):
+        if p.dtype == dtype:
+            return p.detach()
+        key = id(p)
+        hit = self._c.get(key)
+        if hit is not None and hit[0] == p._version and hit[1].device == p.device and hit[1].dtype == dtype:
+            return hit[1]
+        c = p.detach().to(dtype).contiguous()
+        self._c[key] = (p._version, c)
+        return c
+
+
+class GraphConvTwoDirection(nn.Module):
+    """Reference arch.py:51-81.  ``left`` = constraints, ``right`` = variables; both directions read
+    the OLD features (synchronous update):
+        right' = lin_rel_l2r(A^T left) + lin_root_l2r(right)
+        left'  = lin_rel_r2l(A  right) + lin_root_r2l(left)
+    """
+
+    def __init__(self, left_dim, right_dim, out_dim):
+        super().__init__()
+        self.left2right = GraphConv((left_dim, right_dim), out_dim)
+        self.right2left = GraphConv((right_dim, left_dim), out_dim)
+        self._cache = _CastCache()
+
+    def forward(self, left_feas, right_feas, edge_index: BipartiteCSR, edge_weight=None, relu=False):
+        from .autograd import two_direction_forward
+        return two_direction_forward(self, left_feas, right_feas, edge_index, relu)
+
+
+class GCNBase(nn.Module):
+    """Reference arch.py:107-114: weights-only checkpointing."""
+
+    def save(self, pn):
+        torch.save(self.state_dict(), pn)
+
+    def load(self, pn):
+        st = torch.load(pn, map_location=torch.device("cpu"))
+        self.load_state_dict(st)
+
+
+def add_knowledge(left_logit, right_logit, left_feas, right_feas, bound=10):
+    """Reference arch.py:129-141 on the device: row L2-normalise x10, then -10 on class 0 / class 2
+    where the lower / upper bound tag of the node is non-zero."""
+    if bound != 10:
+        raise ValueError("the masking kernel implements the reference's bound=10")
+    from .autograd import add_knowledge_fn
+    return add_knowledge_fn(left_logit, left_feas), add_knowledge_fn(right_logit, right_feas)
+
+
+class GCN_FC(GCNBase):
+    """Reference arch.py:167-193: conv1 (p,q -> hids) + (depth-2) hidden convs + two Linear(hids,3)
+    heads + knowledge masking.  Same constructor argument order as the reference, so a seeded
+    construction draws the same initial weights."""
+
+    def __init__(self, p, q, hids=128, depth=3, dp=.1, *args, **kwargs):
+        super().__init__()
+        self.conv1 = GraphConvTwoDirection(p, q, hids)
+        self.layers = nn.ModuleList()
+        for _ in range(depth - 2):
+            self.layers.append(GraphConvTwoDirection(hids, hids, hids))
+        self.lin_left = nn.Linear(hids, 3)
+        self.lin_right = nn.Linear(hids, 3)
+        self.dp = dp
+        self.hids = hids
+        self.precision = "fp32"
+
+    # -- precision switches ----------------------------------------------------------------
+    def set_precision(self, precision: str):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if precision == "bf16" and self.hids % 64 != 0:
+            raise ValueError("bf16 mode needs hids to be a multiple of 64 (tensor-core tile)")
+        self.precision = precision
+        return self
+
+    def half(self):       # reference `--fp16`: model.half() (val.py:269, pred_basis.py:146)
+        return self.set_precision("bf16")
+
+    def bfloat16(self):
+        return self.set_precision("bf16")
+
+    def float(self):
+        return self.set_precision("fp32")
+
+    def forward(self, batch):
+        from .autograd import gcn_fc_forward
+        return gcn_fc_forward(self, batch.x_s, batch.x_t, batch.edge_index)
+
+    @torch.no_grad()
+    def predict_basis(self, batch, int64=True):
+        """forward + ``val.inference_gnn`` without leaving the device (reference
+        scripts/pred_basis.py:113-118 ``inference_only``)."""
+        lc, lv = self.forward(batch)
+        return ops.basis_select(lc, lv, k_basic=lc.shape[0], int64=int64)

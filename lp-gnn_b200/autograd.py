@@ -1,0 +1,89 @@
+"""Forward / backward orchestration of the GCN_FC hot path over the CUDA kernels.
+
+Inference (no grad) goes straight through ``ops``.  Training wraps the same kernels in
+``torch.autograd.Function``s whose backward passes are again kernels of liblpgnn (the transposed
+SpMM orientation, the data/weight-gradient GEMMs, the head/mask backward) -- never PyTorch-eager
+math on the activations.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .graph import BipartiteCSR
+
+
+def _act_dtype(model) -> torch.dtype:
+    return torch.bfloat16 if getattr(model, "precision", "fp32") == "bf16" else torch.float32
+
+
+def _needs_grad(module) -> bool:
+    return torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters())
+
+
+def _check_graph(g):
+    if not isinstance(g, BipartiteCSR):
+        raise TypeError(f"batch.edge_index must be a BipartiteCSR (got {type(g).__name__}); build it with "
+                        "BipartiteCSR.from_edge_index(...).to('cuda')")
+    return g.views()
+
+
+# --------------------------------------------------------------------------------------------------
+# inference path
+# --------------------------------------------------------------------------------------------------
+def _conv_hidden_infer(conv, left, right, csr, csc, relu):
+    dt = left.dtype
+    cast = conv._cache.get
+    l2r, r2l = conv.left2right, conv.right2left
+    agg_t = ops.spmm(csc, left)     # [n,H]  A^T . left
+    agg_s = ops.spmm(csr, right)    # [m,H]  A   . right
+    right_new = ops.node_transform(agg_t, cast(l2r.lin_rel.weight, dt), right, cast(l2r.lin_root.weight, dt),
+                                   l2r.lin_rel.bias.detach(), relu=relu)
+    left_new = ops.node_transform(agg_s, cast(r2l.lin_rel.weight, dt), left, cast(r2l.lin_root.weight, dt),
+                                  r2l.lin_rel.bias.detach(), relu=relu)
+    return left_new, right_new
+
+
+def _conv_in_infer(conv, x_left, x_right, csr, csc, dt, relu):
+    l2r, r2l = conv.left2right, conv.right2left
+    right_new, _ = ops.conv_in_fused(csc, x_left, x_right, l2r.lin_rel.weight.detach(), l2r.lin_rel.bias.detach(),
+                                     l2r.lin_root.weight.detach(), dt, relu=relu)
+    left_new, _ = ops.conv_in_fused(csr, x_right, x_left, r2l.lin_rel.weight.detach(), r2l.lin_rel.bias.detach(),
+                                    r2l.lin_root.weight.detach(), dt, relu=relu)
+    return left_new, right_new
+
+
+def two_direction_forward(conv, left, right, graph, relu=False):
+    """GraphConvTwoDirection.forward (reference arch.py:65-81) for callers that use the layer
+    on its own."""
+    csr, csc = _check_graph(graph)
+    if _needs_grad(conv) or left.requires_grad or right.requires_grad:
+        from .training import conv_train
+        return conv_train(conv, left, right, csr, csc, relu, dropout_p=0.0, training=False)
+    narrow = conv.left2right.in_channels[0] + conv.left2right.in_channels[1] <= 64
+    if narrow and left.dtype == torch.float32:
+        return _conv_in_infer(conv, left, right, csr, csc, torch.float32, relu)
+    return _conv_hidden_infer(conv, left, right, csr, csc, relu)
+
+
+def gcn_fc_forward(model, x_s, x_t, graph):
+    """GCN_FC.forward (reference arch.py:179-193)."""
+    csr, csc = _check_graph(graph)
+    if _needs_grad(model):
+        from .training import gcn_fc_train
+        return gcn_fc_train(model, x_s, x_t, csr, csc)
+    dt = _act_dtype(model)
+    left, right = _conv_in_infer(model.conv1, x_s, x_t, csr, csc, dt, relu=True)
+    for conv in model.layers:
+        # eval mode: dropout is the identity; relu is fused into the transform epilogue
+        left, right = _conv_hidden_infer(conv, left, right, csr, csc, relu=True)
+    logit_s, _ = ops.head_mask(left, model.lin_left.weight.detach(), model.lin_left.bias.detach(), x_s)
+    logit_t, _ = ops.head_mask(right, model.lin_right.weight.detach(), model.lin_right.bias.detach(), x_t)
+    return logit_s, logit_t
+
+
+def add_knowledge_fn(logits, feas):
+    if torch.is_grad_enabled() and logits.requires_grad:
+        from .training import AddKnowledgeFn
+        return AddKnowledgeFn.apply(logits, feas)
+    return ops.add_knowledge_kernel(logits, feas)

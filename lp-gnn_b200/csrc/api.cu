@@ -1,0 +1,87 @@
+// C-ABI plumbing: error state, device checks, dtype dispatch of the node transform.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace lpgnn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int g_sm_count = 0;
+static int g_cc_major = 0, g_cc_minor = 0;
+static int g_dev_checked = -1;
+
+int check_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available: liblpgnn has no CPU fallback");
+    return LPGNN_ENODEVICE;
+  }
+  if (dev != g_dev_checked) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cudaGetDeviceProperties failed");
+      return LPGNN_ENODEVICE;
+    }
+    g_sm_count = p.multiProcessorCount;
+    g_cc_major = p.major;
+    g_cc_minor = p.minor;
+    g_dev_checked = dev;
+  }
+  if (g_cc_major != 10) {
+    set_error("device compute capability %d.%d is not sm_100 (Blackwell B200); liblpgnn is sm_100a-only", g_cc_major,
+              g_cc_minor);
+    return LPGNN_ENODEVICE;
+  }
+  return LPGNN_OK;
+}
+
+int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
+
+int node_transform_f32(const float* A1, int K1, const float* W1, const float* A2, int K2, const float* W2,
+                       const float* bias, int M, int N, float* out, int relu, cudaStream_t st);
+int node_transform_bf16(const void* A1, int K1, const void* W1, const void* A2, int K2, const void* W2,
+                        const float* bias, int M, int N, void* out, int relu, cudaStream_t st);
+
+}  // namespace lpgnn
+
+using namespace lpgnn;
+
+extern "C" int lpgnn_version(void) { return LPGNN_VERSION; }
+extern "C" const char* lpgnn_last_error(void) { return g_err; }
+
+extern "C" int lpgnn_device_info(int* sm, int* major, int* minor) {
+  if (int rc = check_device()) return rc;
+  if (sm) *sm = g_sm_count;
+  if (major) *major = g_cc_major;
+  if (minor) *minor = g_cc_minor;
+  return LPGNN_OK;
+}
+
+extern "C" int lpgnn_node_transform(const void* A1, int32_t K1, const void* W1, const void* A2, int32_t K2,
+                                    const void* W2, const float* bias, int32_t M, int32_t N, void* out, int dtype,
+                                    int epilogue, lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(M >= 0 && N > 0 && K1 > 0 && K2 >= 0, "node_transform: bad shape M=%d N=%d K1=%d K2=%d", M, N, K1, K2);
+  LPGNN_REQUIRE(dtype == LPGNN_F32 || dtype == LPGNN_BF16, "node_transform: bad dtype %d", dtype);
+  if (M == 0) return LPGNN_OK;
+  LPGNN_REQUIRE(A1 && W1 && out, "node_transform: null pointer");
+  LPGNN_REQUIRE(K2 == 0 || (A2 && W2), "node_transform: K2=%d but A2/W2 is null", K2);
+  const int relu = (epilogue & LPGNN_EPI_RELU) ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (K2 == 0) { A2 = nullptr; W2 = nullptr; }
+  if (dtype == LPGNN_F32)
+    return node_transform_f32((const float*)A1, K1, (const float*)W1, (const float*)A2, K2, (const float*)W2, bias, M,
+                              N, (float*)out, relu, st);
+  return node_transform_bf16(A1, K1, W1, A2, K2, W2, bias, M, N, out, relu, st);
+}

@@ -1,0 +1,59 @@
+// Shared helpers for liblpgnn (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/lpgnn.h"
+
+namespace lpgnn {
+
+// thread-local error string behind lpgnn_last_error()
+void set_error(const char* fmt, ...);
+int check_device();  // LPGNN_OK or LPGNN_ENODEVICE
+int sm_count();
+
+#define LPGNN_CUDA_OK(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      ::lpgnn::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return LPGNN_ECUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+#define LPGNN_LAUNCH_OK()                                                                \
+  do {                                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) {                                                             \
+      ::lpgnn::set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return LPGNN_ECUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+#define LPGNN_REQUIRE(cond, ...)                                                         \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      ::lpgnn::set_error(__VA_ARGS__);                                                   \
+      return LPGNN_EINVAL;                                                               \
+    }                                                                                    \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);  // .x = a (low half), .y = b
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// 128-bit read-only streaming load / store
+__device__ __forceinline__ uint4 ldg128(const void* p) {
+  return __ldg(reinterpret_cast<const uint4*>(p));
+}
+
+}  // namespace lpgnn

@@ -1,0 +1,254 @@
+// (a3, bf16 fast path) Node transform of a hidden GraphConv layer on the 5th-gen tensor cores:
+//   out[M,N] = epi( A1[M,K1]*W1[N,K1]^T + A2[M,K2]*W2[N,K2]^T + bias[N] )     bf16 in/out, fp32 accumulate
+//
+// Replaces lin_rel(agg) + lin_root(x_dst) + relu_ of PyG GraphConv (reference arch.py:75-80, 188:
+// two cuBLAS GEMMs, a bias add, an add and an elementwise kernel) with one persistent,
+// warp-specialised tcgen05 kernel; the two (A,W) pairs are walked as ONE concatenated reduction so
+// the accumulator never leaves TMEM between them.
+//
+//   warp 0      TMA producer: cp.async.bulk.tensor tiles of A (128 x 64) and W (BN x 64), 128-byte
+//               swizzle, into a kStages-deep shared-memory ring (full/empty mbarriers)
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (UMMA 128 x BN x 16, kind::f16),
+//               accumulators in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i
+//               overlaps the main loop of tile i+1; tcgen05.commit releases ring slots
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue: tcgen05.ld (32 lanes x 32 columns), + bias, ReLU, pack to bf16, 64-byte
+//               row segments to global
+// Tiles are ordered n-fastest so CTAs resident together share the same A row block through L2.
+// Bound: tensor pipe (2*M*N*(K1+K2) flops against the measured bf16 peak); see DESIGN.md.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace lpgnn {
+namespace {
+
+constexpr int BM = 128;          // UMMA M (cta_group::1)
+constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UK = 16;           // UMMA K for 16-bit inputs
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+template <int BN> struct Cfg {
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;  // power of two >= 32 for BN in {64,128,256}
+  static constexpr int kBarBytes = 2048;  // mbarriers + tmem ptr + bias slice (BN floats)
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024 /*align slack*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2, int kblocks1,
+               int kblocks2, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int M, int N,
+               int relu) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128-byte swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::kStages * C::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full_bar = bars;                       // [kStages]
+  uint64_t* empty_bar = bars + C::kStages;         // [kStages]
+  uint64_t* tmem_full = bars + 2 * C::kStages;     // [2]
+  uint64_t* tmem_empty = bars + 2 * C::kStages + 2;// [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * C::kStages + 6);  // [BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_n = N / BN;
+  const int num_m = (M + BM - 1) / BM;
+  const int num_tiles = num_m * num_n;
+  const int kblocks = kblocks1 + kblocks2;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA1);
+    ptx::prefetch_tensormap(&tmW1);
+    if (kblocks2 > 0) { ptx::prefetch_tensormap(&tmA2); ptx::prefetch_tensormap(&tmW2); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tmem_full[b], 1); ptx::mbar_init(&tmem_empty[b], 128); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_ptr, C::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+          const bool first = kb < kblocks1;
+          const int kc = (first ? kb : kb - kblocks1) * BK;
+          ptx::tma_load_2d(smem_a + stage * C::kABytes, first ? &tmA1 : &tmA2, &full_bar[stage], kc, m_blk * BM);
+          ptx::tma_load_2d(smem_b + stage * C::kBBytes, first ? &tmW1 : &tmW2, &full_bar[stage], kc, n_blk * BN);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int t = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const int buf = t & 1;
+        const uint32_t use_phase = (t >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty[buf], use_phase ^ 1);  // epilogue has drained this accumulator
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t adesc = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_a + stage * C::kABytes));
+          const uint64_t bdesc = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_b + stage * C::kBBytes));
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            // advance 16 elements = 32 bytes along K inside the swizzle row: +2 in 16-byte units
+            ptx::umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // slot free once these MMAs have read it
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full[buf]);      // accumulator complete
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp - kEpiWarp0;               // TMEM lane quarter of this warp (== warp % 4)
+    const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..127
+    int t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int buf = t & 1;
+      const uint32_t use_phase = (t >> 1) & 1;
+      // stage the bias slice of this tile
+      for (int j = et; j < BN; j += 128) bias_s[j] = bias ? __ldg(bias + n_blk * BN + j) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      ptx::mbar_wait(&tmem_full[buf], use_phase);
+      ptx::tc_fence_after();
+      const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
+      __nv_bfloat16* orow = out + row * N + (int64_t)n_blk * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(taddr + c * 32, r);
+        ptx::tmem_ld_wait();
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float v0 = __uint_as_float(r[2 * j]) + bias_s[c * 32 + 2 * j];
+          float v1 = __uint_as_float(r[2 * j + 1]) + bias_s[c * 32 + 2 * j + 1];
+          if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+          packed[j] = pack_bf16(v0, v1);
+        }
+        if (row < M) {
+          uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty[buf]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // bias_s may be overwritten for the next tile
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+// ---------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// [rows, K] bf16 row-major, box = [box_rows, 64], 128-byte swizzle, OOB rows read as zero.
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("node_transform(bf16): cuTensorMapEncodeTiled unavailable"); return LPGNN_ECUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("node_transform(bf16): cuTensorMapEncodeTiled failed (%d)", (int)r); return LPGNN_ECUDA; }
+  return LPGNN_OK;
+}
+
+template <int BN>
+int launch(const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& a2, const CUtensorMap& w2, int kb1, int kb2,
+           const float* bias, __nv_bfloat16* out, int M, int N, int relu, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LPGNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = ceil_div(M, BM) * (N / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu);
+  LPGNN_LAUNCH_OK();
+  return LPGNN_OK;
+}
+
+}  // namespace
+
+int node_transform_bf16(const void* A1, int K1, const void* W1, const void* A2, int K2, const void* W2,
+                        const float* bias, int M, int N, void* out, int relu, cudaStream_t st) {
+  LPGNN_REQUIRE(K1 > 0 && K1 % BK == 0 && K2 % BK == 0, "node_transform(bf16): K1=%d, K2=%d must be multiples of 64", K1, K2);
+  LPGNN_REQUIRE(N % 64 == 0, "node_transform(bf16): N=%d must be a multiple of 64", N);
+  LPGNN_REQUIRE((uintptr_t)A1 % 16 == 0 && (uintptr_t)W1 % 16 == 0 && (uintptr_t)A2 % 16 == 0 &&
+                    (uintptr_t)W2 % 16 == 0 && (uintptr_t)out % 16 == 0,
+                "node_transform(bf16): operands must be 16-byte aligned");
+  const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
+  const bool two = A2 != nullptr && K2 > 0;
+  CUtensorMap a1, w1, a2, w2;
+  if (int rc = make_map(&a1, A1, M, K1, BM)) return rc;
+  if (int rc = make_map(&w1, W1, N, K1, BN)) return rc;
+  if (two) {
+    if (int rc = make_map(&a2, A2, M, K2, BM)) return rc;
+    if (int rc = make_map(&w2, W2, N, K2, BN)) return rc;
+  } else {
+    a2 = a1; w2 = w1;
+  }
+  const int kb1 = K1 / BK, kb2 = two ? K2 / BK : 0;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (BN == 256) return launch<256>(a1, w1, a2, w2, kb1, kb2, bias, o, M, N, relu, st);
+  if (BN == 128) return launch<128>(a1, w1, a2, w2, kb1, kb2, bias, o, M, N, relu, st);
+  return launch<64>(a1, w1, a2, w2, kb1, kb2, bias, o, M, N, relu, st);
+}
+
+}  // namespace lpgnn

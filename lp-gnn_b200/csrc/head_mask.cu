@@ -1,0 +1,125 @@
+// (a4+a5) Basis-status head + knowledge masking in one pass over the hidden activations.
+//
+// Replaces torch.nn.Linear(hids,3) (reference arch.py:190: cuBLAS skinny GEMM + bias) and
+// add_knowledge (reference arch.py:129-141: F.normalize, *10 and four boolean index_put_) -- ~12
+// library kernels -- with one kernel: a warp reads one H-wide row with 128-bit loads, forms the 3
+// dot products (weights staged in shared memory), reduces with shuffles, then normalises, scales
+// by 10 and applies the +-inf-bound mask read from the node features.
+// HBM-bound: rows * (Hdim*sizeof(h) + 4*q + 12) bytes.
+#include "common.cuh"
+
+namespace lpgnn {
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ void finish_row(float r0, float r1, float r2, const float* __restrict__ feas, int q,
+                                           int64_t row, float* __restrict__ logits) {
+  // F.normalize: x / max(||x||_2, eps), eps = 1e-12 ; then * 10 (arch.py:134-135)
+  const float nrm = sqrtf(r0 * r0 + r1 * r1 + r2 * r2);
+  const float den = fmaxf(nrm, 1e-12f);
+  float y0 = (r0 / den) * 10.f, y1 = (r1 / den) * 10.f, y2 = (r2 / den) * 10.f;
+  // mask: tag columns q-3 (lower bound) and q-1 (upper bound) are non-zero for +-inf (arch.py:130-140)
+  if (__ldg(feas + row * q + (q - 3)) != 0.f) y0 -= 10.f;
+  if (__ldg(feas + row * q + (q - 1)) != 0.f) y2 -= 10.f;
+  logits[row * 3 + 0] = y0;
+  logits[row * 3 + 1] = y1;
+  logits[row * 3 + 2] = y2;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+head_mask_kernel(const T* __restrict__ H, int32_t rows, int32_t Hdim, const float* __restrict__ W,
+                 const float* __restrict__ b, const float* __restrict__ feas, int q, float* __restrict__ logits,
+                 float* __restrict__ raw_out) {
+  extern __shared__ __align__(16) float w_s[];  // [3][Hdim]
+  for (int i = threadIdx.x; i < 3 * Hdim; i += kThreads) w_s[i] = __ldg(W + i);
+  __syncthreads();
+  constexpr int E = 16 / sizeof(T);
+  const int lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * (kThreads / 32);
+  const int chunks = Hdim / E;
+  const float b0 = __ldg(b), b1 = __ldg(b + 1), b2 = __ldg(b + 2);
+  for (int64_t row = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); row < rows; row += warps_total) {
+    const uint4* hrow = reinterpret_cast<const uint4*>(H + row * Hdim);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int c = lane; c < chunks; c += 32) {
+      const uint4 v = __ldg(hrow + c);
+      float x[E];
+      if constexpr (sizeof(T) == 4) {
+        x[0] = __uint_as_float(v.x); x[1] = __uint_as_float(v.y); x[2] = __uint_as_float(v.z); x[3] = __uint_as_float(v.w);
+      } else {
+        x[0] = bf16_lo(v.x); x[1] = bf16_hi(v.x); x[2] = bf16_lo(v.y); x[3] = bf16_hi(v.y);
+        x[4] = bf16_lo(v.z); x[5] = bf16_hi(v.z); x[6] = bf16_lo(v.w); x[7] = bf16_hi(v.w);
+      }
+      const float* w0 = w_s + c * E;
+#pragma unroll
+      for (int k = 0; k < E; ++k) {
+        a0 = fmaf(x[k], w0[k], a0);
+        a1 = fmaf(x[k], w0[Hdim + k], a1);
+        a2 = fmaf(x[k], w0[2 * Hdim + k], a2);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+    }
+    if (lane == 0) {
+      a0 += b0; a1 += b1; a2 += b2;
+      if (raw_out) { raw_out[row * 3] = a0; raw_out[row * 3 + 1] = a1; raw_out[row * 3 + 2] = a2; }
+      finish_row(a0, a1, a2, feas, q, row, logits);
+    }
+  }
+}
+
+__global__ void add_knowledge_kernel(const float* __restrict__ in, int32_t rows, const float* __restrict__ feas,
+                                     int q, float* __restrict__ out) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  finish_row(in[row * 3], in[row * 3 + 1], in[row * 3 + 2], feas, q, row, out);
+}
+
+}  // namespace
+}  // namespace lpgnn
+
+using namespace lpgnn;
+
+extern "C" int lpgnn_head_mask(const void* H, int h_dtype, int32_t rows, int32_t Hdim, const float* W, const float* b,
+                               const float* feas, int32_t q, float* logits, float* raw_out, lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(rows >= 0 && Hdim > 0 && q >= 3, "head_mask: bad shape rows=%d Hdim=%d q=%d", rows, Hdim, q);
+  LPGNN_REQUIRE(h_dtype == LPGNN_F32 || h_dtype == LPGNN_BF16, "head_mask: bad dtype %d", h_dtype);
+  if (rows == 0) return LPGNN_OK;
+  LPGNN_REQUIRE(H && W && b && feas && logits, "head_mask: null pointer");
+  const int esz = h_dtype == LPGNN_F32 ? 4 : 2;
+  LPGNN_REQUIRE((Hdim * esz) % 16 == 0 && (uintptr_t)H % 16 == 0, "head_mask: H rows must be 16-byte multiples/aligned");
+  LPGNN_REQUIRE(3 * Hdim * 4 <= 96 * 1024, "head_mask: Hdim=%d too large for the shared-memory weight stage", Hdim);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = min(ceil_div(rows, kThreads / 32), sm_count() * 8);
+  const size_t smem = (size_t)3 * Hdim * sizeof(float);
+  if (h_dtype == LPGNN_F32) {
+    LPGNN_CUDA_OK(cudaFuncSetAttribute(head_mask_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    head_mask_kernel<float><<<grid, kThreads, smem, st>>>(reinterpret_cast<const float*>(H), rows, Hdim, W, b, feas, q,
+                                                          logits, raw_out);
+  } else {
+    LPGNN_CUDA_OK(cudaFuncSetAttribute(head_mask_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       96 * 1024));
+    head_mask_kernel<__nv_bfloat16><<<grid, kThreads, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(H), rows, Hdim,
+                                                                  W, b, feas, q, logits, raw_out);
+  }
+  LPGNN_LAUNCH_OK();
+  return LPGNN_OK;
+}
+
+extern "C" int lpgnn_add_knowledge(const float* logits_in, int32_t rows, const float* feas, int32_t q,
+                                   float* logits_out, lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(rows >= 0 && q >= 3, "add_knowledge: bad shape rows=%d q=%d", rows, q);
+  if (rows == 0) return LPGNN_OK;
+  LPGNN_REQUIRE(logits_in && feas && logits_out, "add_knowledge: null pointer");
+  add_knowledge_kernel<<<ceil_div(rows, 256), 256, 0, (cudaStream_t)stream>>>(logits_in, rows, feas, q, logits_out);
+  LPGNN_LAUNCH_OK();
+  return LPGNN_OK;
+}

@@ -1,0 +1,226 @@
+"""``BipartiteCSR``: the LP coefficient matrix A (m constraints x n variables) in HBM.
+
+Drop-in for the ``torch_sparse.SparseTensor`` that the reference stores in ``batch.edge_index``
+(built at reference dataset.py:301-304, transposed at arch.py:71, queried at dataset.py:133-144,
+moved at train.py:118 / utils.py:909-915).  It keeps BOTH orientations resident --
+
+    CSR  rowptr[m+1], col[z], val[z]          (row-major, ascending column inside a row)
+    CSC  colptr[n+1], row_csc[z], val_csc[z]  (column-major, ascending row inside a column)
+    csr2csc[z]                                (val_csc = val[csr2csc])
+
+-- as int32 / float32, because the forward pass of one direction and the backward pass of the other
+use the same view.  Construction happens on the device (``lpgnn_graph_build``); a graph created in
+a DataLoader worker stays a host COO until ``.to(cuda)`` is called in the main process, so CUDA is
+never initialised in forked workers ("CUDA in DataLoader workers").
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+class _StorageView:
+    """``edge_index.storage.value()`` etc. (reference arch.py:21)."""
+
+    def __init__(self, g):
+        self._g = g
+
+    def value(self):
+        return self._g.values()
+
+    def row(self):
+        return self._g.coo()[0]
+
+    def col(self):
+        return self._g.coo()[1]
+
+    def rowptr(self):
+        g = self._g
+        g._require_built()
+        return (g.colptr if g._transposed else g.rowptr).long()
+
+
+class BipartiteCSR:
+    def __init__(self):
+        self.m = self.n = 0
+        self._coo = None            # (row, col, val) host/device tensors before the build
+        self.rowptr = self.col = self.val = None
+        self.colptr = self.row_csc = self.val_csc = self.csr2csc = None
+        self._transposed = False    # True: this object presents A^T (shares buffers with its parent)
+        self.storage = _StorageView(self)
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_edge_index(cls, edge_index, edge_attr=None, sparse_sizes=None, is_sorted=False):
+        """Same signature as ``SparseTensor.from_edge_index`` (reference dataset.py:301-304).
+        ``edge_index`` [2,z] integer (any order), ``edge_attr`` [z] float (default: ones)."""
+        if sparse_sizes is None:
+            raise ValueError("sparse_sizes=(m, n) is required")
+        g = cls()
+        g.m, g.n = int(sparse_sizes[0]), int(sparse_sizes[1])
+        row, col = edge_index[0], edge_index[1]
+        if edge_attr is None:
+            edge_attr = torch.ones(row.shape[0], dtype=torch.float32, device=row.device)
+        if row.numel() and (int(row.max()) >= g.m or int(col.max()) >= g.n or int(row.min()) < 0 or int(col.min()) < 0):
+            raise ValueError("edge_index out of range for sparse_sizes")
+        g._coo = (row.to(torch.int32).contiguous(), col.to(torch.int32).contiguous(),
+                  edge_attr.to(torch.float32).contiguous())
+        if row.is_cuda:
+            g._build()
+        return g
+
+    @classmethod
+    def from_coo_arrays(cls, row, col, val, m, n, device):
+        """numpy / tensor COO -> built graph on ``device`` (one H2D copy per array)."""
+        ei = torch.stack([torch.as_tensor(row), torch.as_tensor(col)])
+        g = cls.from_edge_index(ei, torch.as_tensor(val), (m, n))
+        return g.to(device)
+
+    def _build(self):
+        row, col, val = self._coo
+        dev = row.device
+        z = int(row.shape[0])
+        lib = _lib.load()
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.rowptr = torch.empty(self.m + 1, **i32)
+        self.colptr = torch.empty(self.n + 1, **i32)
+        self.col = torch.empty(z, **i32)
+        self.row_csc = torch.empty(z, **i32)
+        self.csr2csc = torch.empty(z, **i32)
+        self.val = torch.empty(z, dtype=torch.float32, device=dev)
+        self.val_csc = torch.empty(z, dtype=torch.float32, device=dev)
+        ws_bytes = lib.lpgnn_graph_build_workspace_bytes(z, self.m, self.n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.lpgnn_graph_build(row.data_ptr(), col.data_ptr(), 0, val.data_ptr(), z, self.m, self.n,
+                                       self.rowptr.data_ptr(), self.col.data_ptr(), self.val.data_ptr(),
+                                       self.colptr.data_ptr(), self.row_csc.data_ptr(), self.val_csc.data_ptr(),
+                                       self.csr2csc.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr())
+        _lib.check(rc, "lpgnn_graph_build")
+        # the caching allocator keeps `ws` / the COO alive until the stream has consumed them
+        ws.record_stream(torch.cuda.current_stream(dev))
+        self._coo = None
+
+    def _require_built(self):
+        if self.rowptr is None:
+            raise RuntimeError("BipartiteCSR is still a host COO: call .to('cuda') first "
+                               "(graphs are built on the device; there is no CPU path)")
+
+    # ------------------------------------------------------------------ movement
+    @property
+    def is_cuda(self):
+        return self.rowptr is not None
+
+    @property
+    def device(self):
+        return self.rowptr.device if self.rowptr is not None else self._coo[0].device
+
+    def pin_memory(self):
+        if self._coo is not None and not self._coo[0].is_cuda:
+            self._coo = tuple(t.pin_memory() for t in self._coo)
+        return self
+
+    def to(self, device=None, *args, non_blocking=False, **kwargs):
+        if device is None or isinstance(device, torch.dtype):
+            return self
+        device = torch.device(device)
+        if device.type != "cuda":
+            if self.rowptr is not None:
+                raise RuntimeError("a built BipartiteCSR lives on the GPU; use .coo() to read it back")
+            return self
+        if self.rowptr is not None:
+            if self.rowptr.device != device and device.index is not None:
+                raise RuntimeError("moving a built BipartiteCSR between GPUs is not supported")
+            return self
+        self._coo = tuple(t.to(device, non_blocking=non_blocking) for t in self._coo)
+        self._build()
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", torch.cuda.current_device() if device is None else device))
+
+    def half(self):       # reference utils.py:913 (`batch[nm].half()`): values stay fp32, features carry the dtype
+        return self
+
+    def float(self):
+        return self
+
+    # ------------------------------------------------------------------ SparseTensor API subset
+    def t(self):
+        """A^T as a view sharing the same buffers (reference arch.py:71)."""
+        v = BipartiteCSR.__new__(BipartiteCSR)
+        v.__dict__.update(self.__dict__)
+        v._transposed = not self._transposed
+        v.storage = _StorageView(v)
+        return v
+
+    def sparse_sizes(self):
+        return (self.n, self.m) if self._transposed else (self.m, self.n)
+
+    def size(self, dim):
+        return self.sparse_sizes()[dim]
+
+    def nnz(self):
+        return int(self.col.shape[0]) if self.col is not None else int(self._coo[0].shape[0])
+
+    def density(self):
+        return self.nnz() / float(self.m * self.n)
+
+    def views(self):
+        """(ptr, idx, val, n_dst) of the presented matrix and of its transpose."""
+        self._require_built()
+        csr = (self.rowptr, self.col, self.val, self.m)
+        csc = (self.colptr, self.row_csc, self.val_csc, self.n)
+        return (csc, csr) if self._transposed else (csr, csc)
+
+    def values(self):
+        self._require_built()
+        return self.val_csc if self._transposed else self.val
+
+    def coo(self):
+        """(row, col, value) int64/int64/float32 in the presented orientation's canonical order."""
+        (ptr, idx, val, rows), _ = self.views()
+        counts = (ptr[1:] - ptr[:-1]).long()
+        row = torch.repeat_interleave(torch.arange(rows, device=ptr.device), counts)
+        return row, idx.long(), val
+
+    def clone(self):
+        g = BipartiteCSR.__new__(BipartiteCSR)
+        g.__dict__.update(self.__dict__)
+        for k in ("rowptr", "col", "val", "colptr", "row_csc", "val_csc", "csr2csc"):
+            if getattr(self, k) is not None:
+                setattr(g, k, getattr(self, k).clone())
+        if self._coo is not None:
+            g._coo = tuple(t.clone() for t in self._coo)
+        g.storage = _StorageView(g)
+        return g
+
+    def set_value(self, value, layout="coo"):
+        """New graph with the same structure and ``value`` given in the presented orientation's
+        canonical (coo/csr) order (reference dataset.py:136)."""
+        self._require_built()
+        g = self.clone()
+        value = value.to(device=self.val.device, dtype=torch.float32)
+        perm = self.csr2csc.long()
+        if self._transposed:
+            g.val_csc = value.contiguous()
+            g.val = torch.empty_like(value)
+            g.val[perm] = value
+        else:
+            g.val = value.contiguous()
+            g.val_csc = value[perm].contiguous()
+        return g
+
+    def sum(self, dim):
+        """Column sums (dim=0) or row sums (dim=1) of the presented matrix (dataset.py:137-138)."""
+        (ptr, idx, val, rows), (ptr_t, _, val_t, rows_t) = self.views()
+        src_ptr, src_val, n_out = (ptr, val, rows) if dim == 1 else (ptr_t, val_t, rows_t)
+        csum = torch.zeros(src_val.shape[0] + 1, dtype=torch.float64, device=src_val.device)
+        csum[1:] = torch.cumsum(src_val.double(), 0)
+        return (csum[src_ptr[1:].long()] - csum[src_ptr[:-1].long()]).float()
+
+    def __repr__(self):
+        r, c = self.sparse_sizes()
+        where = self.device if (self.rowptr is not None or self._coo is not None) else "?"
+        return f"BipartiteCSR({r}x{c}, nnz={self.nnz()}, device={where}, built={self.rowptr is not None})"

@@ -1,0 +1,126 @@
+"""Python entry points of the CUDA kernels (thin wrappers over the C ABI, ``include/lpgnn.h``).
+
+Each function validates shapes/dtypes, allocates outputs with torch (the library never allocates
+user-visible memory), and enqueues the kernel on torch's CURRENT stream.  No function here has a
+CPU or PyTorch-eager fallback.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import EPI_NONE, EPI_RELU, check, dtype_code, ptr, require_cuda, stream_ptr  # noqa: F401
+
+
+def _contig(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def spmm(view, x: torch.Tensor) -> torch.Tensor:
+    """``Y[i] = sum_e val[e] * X[idx[e]]`` for one orientation ``view = (ptr, idx, val, rows)``
+    (``BipartiteCSR.views()``).  Replaces ``torch_sparse.matmul(adj_t, x, reduce='add')``
+    (reference arch.py:75-80 through PyG GraphConv)."""
+    ptr_, idx, val, rows = view
+    require_cuda(ptr_, x)
+    x = _contig(x)
+    F = x.shape[1]
+    y = torch.empty((rows, F), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().lpgnn_spmm(ptr_.data_ptr(), idx.data_ptr(), val.data_ptr(), rows, x.data_ptr(), y.data_ptr(), F,
+                                    dtype_code(x.dtype), stream_ptr())
+    check(rc, "lpgnn_spmm")
+    return y
+
+
+def conv_in_fused(view, x_src, x_dst, w_rel, b_rel, w_root, out_dtype, relu=True, want_agg=False):
+    """conv1 of GCN_FC for one direction: ``relu(lin_rel(A_view @ x_src) + lin_root(x_dst))`` in one
+    kernel (reference arch.py:75-80, 181-182).  Returns ``(out[rows,N], agg[rows,k_src] | None)``."""
+    ptr_, idx, val, rows = view
+    require_cuda(ptr_, x_src, x_dst, w_rel, w_root)
+    x_src, x_dst = _contig(x_src.float()), _contig(x_dst.float())
+    w_rel, w_root, b_rel = _contig(w_rel.float()), _contig(w_root.float()), _contig(b_rel.float())
+    N = w_rel.shape[0]
+    out = torch.empty((rows, N), dtype=out_dtype, device=x_src.device)
+    agg = torch.empty((rows, x_src.shape[1]), dtype=torch.float32, device=x_src.device) if want_agg else None
+    with torch.cuda.device(x_src.device):
+        rc = _lib.load().lpgnn_conv_in_fused(ptr_.data_ptr(), idx.data_ptr(), val.data_ptr(), rows, x_src.data_ptr(),
+                                             x_src.shape[1], x_dst.data_ptr(), x_dst.shape[1], w_rel.data_ptr(),
+                                             b_rel.data_ptr(), w_root.data_ptr(), N, out.data_ptr(), dtype_code(out_dtype),
+                                             EPI_RELU if relu else EPI_NONE, ptr(agg), stream_ptr())
+    check(rc, "lpgnn_conv_in_fused")
+    return out, agg
+
+
+def node_transform(a1, w1, a2=None, w2=None, bias=None, relu=False) -> torch.Tensor:
+    """``epi(a1 @ w1.T + a2 @ w2.T + bias)``: bf16 operands -> tcgen05 kernel, fp32 -> CUDA-core
+    kernel.  Replaces ``lin_rel(agg) + lin_root(x_dst)`` (+ relu_) (reference arch.py:75-80, 188)."""
+    require_cuda(a1, w1, a2, w2, bias)
+    dt = a1.dtype
+    a1, w1 = _contig(a1), _contig(w1)
+    if w1.dtype != dt:
+        raise TypeError(f"node_transform: weight dtype {w1.dtype} != activation dtype {dt}")
+    M, K1 = a1.shape
+    N = w1.shape[0]
+    K2 = 0
+    if a2 is not None:
+        a2, w2 = _contig(a2), _contig(w2)
+        K2 = a2.shape[1]
+        if a2.dtype != dt or w2.dtype != dt:
+            raise TypeError("node_transform: all operands must share one dtype")
+    if bias is not None:
+        bias = _contig(bias.float())
+    out = torch.empty((M, N), dtype=dt, device=a1.device)
+    with torch.cuda.device(a1.device):
+        rc = _lib.load().lpgnn_node_transform(a1.data_ptr(), K1, w1.data_ptr(), ptr(a2), K2, ptr(w2), ptr(bias), M, N,
+                                              out.data_ptr(), dtype_code(dt), EPI_RELU if relu else EPI_NONE,
+                                              stream_ptr())
+    check(rc, "lpgnn_node_transform")
+    return out
+
+
+def head_mask(h, w, b, feas, want_raw=False):
+    """Linear(H,3) + add_knowledge in one pass (reference arch.py:190-191, 129-141).
+    Returns ``(logits[rows,3] f32, raw[rows,3] f32 | None)``."""
+    require_cuda(h, w, b, feas)
+    h, feas = _contig(h), _contig(feas.float())
+    w, b = _contig(w.float()), _contig(b.float())
+    rows, H = h.shape
+    logits = torch.empty((rows, 3), dtype=torch.float32, device=h.device)
+    raw = torch.empty((rows, 3), dtype=torch.float32, device=h.device) if want_raw else None
+    with torch.cuda.device(h.device):
+        rc = _lib.load().lpgnn_head_mask(h.data_ptr(), dtype_code(h.dtype), rows, H, w.data_ptr(), b.data_ptr(),
+                                         feas.data_ptr(), feas.shape[1], logits.data_ptr(), ptr(raw), stream_ptr())
+    check(rc, "lpgnn_head_mask")
+    return logits, raw
+
+
+def add_knowledge_kernel(logits, feas):
+    """add_knowledge on given logits (reference arch.py:129-141)."""
+    require_cuda(logits, feas)
+    logits, feas = _contig(logits.float()), _contig(feas.float())
+    out = torch.empty_like(logits)
+    with torch.cuda.device(logits.device):
+        rc = _lib.load().lpgnn_add_knowledge(logits.data_ptr(), logits.shape[0], feas.data_ptr(), feas.shape[1],
+                                             out.data_ptr(), stream_ptr())
+    check(rc, "lpgnn_add_knowledge")
+    return out
+
+
+def basis_select(logits_cons, logits_vars, k_basic=None, int64=True, want_counts=False):
+    """``val.inference_gnn`` on the device (reference val.py:106-124): status per node, constraints
+    first.  ``k_basic`` defaults to m (the reference's top-m rule)."""
+    require_cuda(logits_cons, logits_vars)
+    lc, lv = _contig(logits_cons.float()), _contig(logits_vars.float())
+    m, n = lc.shape[0], lv.shape[0]
+    k = m if k_basic is None else int(k_basic)
+    dev = lc.device
+    status = torch.empty(m + n, dtype=torch.int64 if int64 else torch.uint8, device=dev)
+    counts = torch.empty(4, dtype=torch.int32, device=dev) if want_counts else None
+    lib = _lib.load()
+    ws_bytes = lib.lpgnn_basis_select_workspace_bytes(m + n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.lpgnn_basis_select(lc.data_ptr(), m, lv.data_ptr(), n, k, status.data_ptr(), 1 if int64 else 0,
+                                    ptr(counts), ws.data_ptr(), ws_bytes, stream_ptr())
+    check(rc, "lpgnn_basis_select")
+    return (status, counts) if want_counts else status

@@ -1,0 +1,103 @@
+"""(a1) graph construction on the device must be BIT-EXACT with the oracle's ordering
+(oracle.port.graph_from_coo restates reference dataset.py:301-304 + arch.py:71)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_graph_arrays
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(row, col, val, m, n, dev, i64=False):
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200.graph import BipartiteCSR
+    ei = torch.stack([torch.from_numpy(row), torch.from_numpy(col)])
+    g = BipartiteCSR.from_edge_index(ei, torch.from_numpy(val), (m, n)).to(dev)
+    torch.cuda.synchronize()
+    return g
+
+
+def _assert_equal(g, ref):
+    c = lambda t: t.cpu().numpy()
+    np.testing.assert_array_equal(c(g.rowptr), ref.rowptr.astype(np.int32))
+    np.testing.assert_array_equal(c(g.col), ref.col.astype(np.int32))
+    np.testing.assert_array_equal(c(g.val).view(np.uint32), ref.val.view(np.uint32))
+    np.testing.assert_array_equal(c(g.colptr), ref.colptr.astype(np.int32))
+    np.testing.assert_array_equal(c(g.row_csc), ref.row_csc.astype(np.int32))
+    np.testing.assert_array_equal(c(g.val_csc).view(np.uint32), ref.val_csc.view(np.uint32))
+    np.testing.assert_array_equal(c(g.csr2csc), ref.csr2csc.astype(np.int32))
+
+
+@pytest.mark.parametrize("m,n,z,seed", [
+    (5, 7, 12, 0), (1, 1, 1, 1), (1000, 2000, 10_000, 2), (300, 70_000, 40_000, 3),
+    (70_000, 300, 40_000, 4), (50_000, 100_000, 500_000, 5), (4097, 4097, 4096 * 3 + 1, 6)])
+def test_build_matches_oracle(cuda, m, n, z, seed):
+    row, col, val = make_graph_arrays(m, n, z, seed)
+    g = _build(row, col, val, m, n, cuda)
+    _assert_equal(g, port.graph_from_coo(row, col, val, m, n))
+
+
+def test_build_sorted_input_and_empty_rows(cuda):
+    m, n = 2000, 3000
+    row, col, val = make_graph_arrays(m, n, 5000, 7, sort=True)
+    keep = (row % 3 != 0) & (col % 5 != 0)          # whole rows / columns without entries
+    row, col, val = row[keep], col[keep], val[keep]
+    g = _build(row, col, val, m, n, cuda)
+    _assert_equal(g, port.graph_from_coo(row, col, val, m, n))
+
+
+def test_build_duplicates_keep_input_order(cuda):
+    m, n = 50, 60
+    row, col, val = make_graph_arrays(m, n, 4000, 8, dup=True)
+    g = _build(row, col, val, m, n, cuda)
+    _assert_equal(g, port.graph_from_coo(row, col, val, m, n))
+
+
+def test_build_empty_graph(cuda):
+    m, n = 10, 20
+    e = np.zeros(0, dtype=np.int64)
+    g = _build(e, e, np.zeros(0, dtype=np.float32), m, n, cuda)
+    assert g.nnz() == 0
+    assert g.rowptr.cpu().tolist() == [0] * (m + 1)
+    assert g.colptr.cpu().tolist() == [0] * (n + 1)
+
+
+def test_build_dense_row_and_column(cuda):
+    m, n = 3000, 5000
+    row = np.concatenate([np.full(n, 7), np.arange(m)]).astype(np.int64)      # row 7 dense, column 11 dense
+    col = np.concatenate([np.arange(n), np.full(m, 11)]).astype(np.int64)
+    key, first = np.unique(row * n + col, return_index=True)
+    row, col = row[first], col[first]
+    val = np.random.default_rng(9).uniform(-1, 1, row.shape[0]).astype(np.float32)
+    perm = np.random.default_rng(10).permutation(row.shape[0])
+    row, col, val = row[perm], col[perm], val[perm]
+    g = _build(row, col, val, m, n, cuda)
+    _assert_equal(g, port.graph_from_coo(row, col, val, m, n))
+
+
+def test_full_size_properties_c4_shape(cuda):
+    """BASELINE C4 shape (1M x 2M, ~1e7 nnz): size-independent properties instead of the oracle."""
+    m, n, z = 1_000_000, 2_000_000, 10_000_000
+    rng = np.random.default_rng(11)
+    row = rng.integers(0, m, size=z)
+    col = rng.integers(0, n, size=z)
+    val = rng.uniform(-1, 1, size=z).astype(np.float32)
+    g = _build(row.astype(np.int64), col.astype(np.int64), val, m, n, cuda)
+    rowptr, colptr = g.rowptr.long(), g.colptr.long()
+    assert int(rowptr[0]) == 0 and int(rowptr[-1]) == z and int(colptr[-1]) == z
+    assert bool((rowptr[1:] >= rowptr[:-1]).all()) and bool((colptr[1:] >= colptr[:-1]).all())
+    r, c, v = g.coo()
+    key = r * n + c
+    assert bool((key[1:] >= key[:-1]).all())                       # CSR canonical order
+    rt, ct, vt = g.t().coo()                                       # rows of A^T = columns of A
+    keyt = rt * m + ct
+    assert bool((keyt[1:] >= keyt[:-1]).all())                     # CSC canonical order
+    assert torch.equal(g.val[g.csr2csc.long()], g.val_csc)         # permutation consistency
+    assert torch.equal(torch.sort(g.csr2csc)[0], torch.arange(z, device=cuda, dtype=torch.int32))
+    # multiset of entries preserved: checksums of (row,col,val-bits) triples
+    bits = torch.from_numpy(val.view(np.int32).astype(np.int64)).to(cuda)
+    chk_in = (torch.from_numpy(row).to(cuda) * 1_000_003 + torch.from_numpy(col).to(cuda) * 7919 + bits).sum()
+    chk_out = (r * 1_000_003 + c * 7919 + g.val.view(torch.int32).long()).sum()
+    assert int(chk_in) == int(chk_out)

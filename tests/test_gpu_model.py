@@ -1,0 +1,84 @@
+"""End-to-end GCN_FC forward through the drop-in arch module vs the oracle port (same weights, same
+inputs): fp32 logits within 1e-4 relative to the row norm 10, bf16 within 2e-2, status agreement >= 99.9 %."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(cfg, hids, depth, dev, structure="staircase"):
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import arch, synth
+    from lpgnn_b200.graph import BipartiteCSR
+    lp = synth.processed_lp(cfg[0], cfg[1], cfg[2], seed=cfg[3], structure=structure)
+    torch.manual_seed(0)
+    model = arch.GCN_FC(8, 8, hids=hids, depth=depth)
+    torch.manual_seed(0)
+    ref = port.PortGCN_FC(8, 8, hids=hids, depth=depth)
+    sd = model.state_dict()
+    for k, v in ref.state_dict().items():                    # same constructor order => same init
+        assert torch.equal(v, sd[k]), k
+    g_ref = port.graph_from_coo(lp.row, lp.col, lp.a_data.astype(np.float32), lp.m, lp.n)
+    batch = types.SimpleNamespace(
+        x_s=torch.from_numpy(lp.c_feas).to(dev), x_t=torch.from_numpy(lp.v_feas).to(dev),
+        edge_index=BipartiteCSR.from_coo_arrays(lp.row, lp.col, lp.a_data.astype(np.float32), lp.m, lp.n, dev))
+    return lp, model.to(dev).eval(), ref.eval(), g_ref, batch
+
+
+@pytest.mark.parametrize("cfg,hids,depth", [((1000, 2000, 10_000, 1235), 64, 2), ((1000, 2000, 10_000, 1235), 128, 3),
+                                              ((3000, 6000, 30_000, 77), 1024, 3), ((500, 1000, 5000, 5), 128, 5)])
+def test_gcn_fc_forward_fp32(cuda, cfg, hids, depth):
+    lp, model, ref, g_ref, batch = _setup(cfg, hids, depth, cuda)
+    with torch.no_grad():
+        lc, lv = model(batch)
+        ec, ev = ref(torch.from_numpy(lp.c_feas), torch.from_numpy(lp.v_feas), port.TorchGraph(g_ref))
+    # float64 model of the same network bounds what fp32 rounding alone can do
+    e64c, e64v = port.gcn_fc_forward_np(ref.state_dict(), lp.c_feas, lp.v_feas, g_ref, depth, acc_dtype=np.float64)
+    for got, exp, e64 in ((lc, ec, e64c), (lv, ev, e64v)):
+        got = got.cpu().numpy()
+        err_ref = np.abs(got - exp.numpy()).max() / 10.0          # relative to the row norm 10
+        err_64 = np.abs(got - e64).max() / 10.0
+        assert err_ref < 1e-4, (err_ref, err_64)
+        assert err_64 < 1e-4
+    status = model.predict_basis(batch).cpu().numpy()
+    exp = port.inference_gnn_np(np.concatenate([ec.numpy(), ev.numpy()]), lp.m)
+    assert np.mean(status == exp) >= 0.999
+    assert int((status == 1).sum()) == lp.m
+
+
+@pytest.mark.parametrize("cfg,hids,depth", [((1000, 2000, 10_000, 1235), 64, 2), ((3000, 6000, 30_000, 77), 1024, 3),
+                                              ((2000, 4000, 20_000, 9), 128, 3)])
+def test_gcn_fc_forward_bf16(cuda, cfg, hids, depth):
+    lp, model, ref, g_ref, batch = _setup(cfg, hids, depth, cuda)
+    model.half()                                                   # the reference's --fp16 switch
+    assert model.precision == "bf16"
+    with torch.no_grad():
+        lc, lv = model(batch)
+        ec, ev = ref(torch.from_numpy(lp.c_feas), torch.from_numpy(lp.v_feas), port.TorchGraph(g_ref))
+    for got, exp in ((lc, ec), (lv, ev)):
+        err = np.abs(got.cpu().numpy() - exp.numpy()).max() / 10.0
+        assert err < 2e-2, err
+    status = model.predict_basis(batch).cpu().numpy()
+    exp = port.inference_gnn_np(np.concatenate([ec.numpy(), ev.numpy()]), lp.m)
+    assert int((status == 1).sum()) == lp.m
+    assert np.mean(status == exp) >= 0.98          # bf16 logits move near-ties; the 99.9 % bar applies to fp32
+
+
+def test_state_dict_keys_and_checkpoint_roundtrip(cuda, tmp_path):
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import arch
+    model = arch.GCN_FC(8, 8, hids=1024, depth=3)
+    keys = list(model.state_dict().keys())
+    assert sum(p.numel() for p in model.parameters()) == 4_237_318
+    assert keys[:3] == ["conv1.left2right.lin_rel.weight", "conv1.left2right.lin_rel.bias",
+                        "conv1.left2right.lin_root.weight"]
+    model.save(tmp_path / "mdl.pth")
+    other = arch.GCN_FC(8, 8, hids=1024, depth=3)
+    other.load(tmp_path / "mdl.pth")
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, other.state_dict()[k])

@@ -1,0 +1,87 @@
+"""(a2) SpMM parity: CUDA kernel vs the oracle's sequential CSR-order accumulation."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_graph_arrays
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+def _graph(m, n, z, seed, dev):
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200.graph import BipartiteCSR
+    row, col, val = make_graph_arrays(m, n, z, seed)
+    g = BipartiteCSR.from_coo_arrays(row, col, val, m, n, dev)
+    return g, port.graph_from_coo(row, col, val, m, n)
+
+
+@pytest.mark.parametrize("F", [4, 8, 16, 64, 100, 128, 1024])
+@pytest.mark.parametrize("m,n,z", [(37, 53, 400), (1000, 2000, 10_000)])
+def test_spmm_fp32_both_orientations(cuda, m, n, z, F):
+    from lpgnn_b200 import ops
+    g, ref = _graph(m, n, z, 100 + F, cuda)
+    rng = np.random.default_rng(F)
+    xr = rng.standard_normal((n, F)).astype(np.float32)
+    xl = rng.standard_normal((m, F)).astype(np.float32)
+    csr, csc = g.views()
+    ys = ops.spmm(csr, torch.from_numpy(xr).to(cuda)).cpu().numpy()
+    yt = ops.spmm(csc, torch.from_numpy(xl).to(cuda)).cpu().numpy()
+    es = port.spmm_sequential(ref.rowptr, ref.col, ref.val, xr)
+    et = port.spmm_sequential(ref.colptr, ref.row_csc, ref.val_csc, xl)
+    # same accumulation order; only fma contraction may differ from the CPU -> a few ulp
+    np.testing.assert_allclose(ys, es, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(yt, et, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("F", [8, 64, 128, 1024])
+def test_spmm_bf16(cuda, F):
+    from lpgnn_b200 import ops
+    m, n, z = 500, 900, 6000
+    g, ref = _graph(m, n, z, 7, cuda)
+    x = torch.randn(n, F, generator=torch.Generator().manual_seed(F)).to(torch.bfloat16)
+    csr, _ = g.views()
+    y = ops.spmm(csr, x.to(cuda)).float().cpu().numpy()
+    e = port.spmm_sequential(ref.rowptr, ref.col, ref.val, x.float().numpy())   # fp32 accumulate of bf16 inputs
+    np.testing.assert_allclose(y, e, rtol=1e-2, atol=1e-2)                       # output rounding to bf16
+    # and the rounding is the ONLY difference: re-round the oracle
+    e_bf = torch.from_numpy(e).to(torch.bfloat16).float().numpy()
+    assert np.mean(y == e_bf) > 0.99
+
+
+def test_spmm_empty_rows_and_dense_row(cuda):
+    from lpgnn_b200 import ops
+    from lpgnn_b200.graph import BipartiteCSR
+    m, n, F = 64, 3000, 128
+    row = np.concatenate([np.full(n, 5), np.array([9, 9, 63])]).astype(np.int64)   # rows 0-4 etc. empty, row 5 dense
+    col = np.concatenate([np.arange(n), np.array([1, 2, 2999])]).astype(np.int64)
+    val = np.random.default_rng(3).uniform(-1, 1, row.shape[0]).astype(np.float32)
+    g = BipartiteCSR.from_coo_arrays(row, col, val, m, n, cuda)
+    ref = port.graph_from_coo(row, col, val, m, n)
+    x = np.random.default_rng(4).standard_normal((n, F)).astype(np.float32)
+    y = ops.spmm(g.views()[0], torch.from_numpy(x).to(cuda)).cpu().numpy()
+    e = port.spmm_sequential(ref.rowptr, ref.col, ref.val, x)
+    np.testing.assert_allclose(y, e, rtol=1e-5, atol=1e-4)
+    assert not y[0].any() and not y[10].any()
+
+
+def test_spmm_linearity_full_size_c2(cuda):
+    """C2 shape, H=1024: linearity A(x+y) = Ax + Ay and agreement with a float64 torch model on a sample of rows."""
+    from lpgnn_b200 import ops
+    m, n, z, F = 50_000, 100_000, 500_000, 1024
+    g, ref = _graph(m, n, z, 21, cuda)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(n, F, device=cuda, generator=gen)
+    y = torch.randn(n, F, device=cuda, generator=gen)
+    csr, _ = g.views()
+    a, b, c = ops.spmm(csr, x), ops.spmm(csr, y), ops.spmm(csr, x + y)
+    assert float((a + b - c).abs().max()) < 1e-4
+    rows = np.random.default_rng(1).integers(0, m, 64)
+    xc = x.double()
+    for r in rows:
+        lo, hi = int(ref.rowptr[r]), int(ref.rowptr[r + 1])
+        cols = torch.from_numpy(ref.col[lo:hi]).to(cuda)
+        w = torch.from_numpy(ref.val[lo:hi]).to(cuda).double()
+        e = (w[:, None] * xc[cols]).sum(0)
+        assert float((a[r].double() - e).abs().max()) < 1e-4

@@ -1,0 +1,94 @@
+"""(a3) node transforms: fp32 CUDA-core kernel and bf16 tcgen05 kernel vs float64 / fp32 torch math on
+the same inputs; (a2+a3) fused input layer vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_graph_arrays
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a1, w1, a2, w2, b, relu):
+    y = a1.double() @ w1.double().T
+    if a2 is not None:
+        y = y + a2.double() @ w2.double().T
+    if b is not None:
+        y = y + b.double()
+    return y.relu() if relu else y
+
+
+@pytest.mark.parametrize("M,N,K1,K2", [(1, 64, 64, 0), (129, 64, 64, 64), (1000, 128, 128, 128),
+                                        (777, 1024, 1024, 1024), (300, 72, 20, 8), (4096, 256, 512, 0)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_transform_fp32(cuda, M, N, K1, K2, relu):
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    a1 = torch.randn(M, K1, device=cuda, generator=g)
+    w1 = torch.randn(N, K1, device=cuda, generator=g) / K1 ** 0.5
+    a2 = torch.randn(M, K2, device=cuda, generator=g) if K2 else None
+    w2 = torch.randn(N, K2, device=cuda, generator=g) / K2 ** 0.5 if K2 else None
+    b = torch.randn(N, device=cuda, generator=g)
+    y = ops.node_transform(a1, w1, a2, w2, b, relu=relu)
+    e = _ref(a1, w1, a2, w2, b, relu)
+    # fp32 accumulate over K <= 2048: relative error ~ sqrt(K) * 2^-24 of the row scale
+    assert float((y.double() - e).abs().max()) < 2e-5 * max(1.0, float(e.abs().max()))
+
+
+@pytest.mark.parametrize("M,N,K1,K2", [(128, 256, 64, 0), (128, 256, 128, 0), (128, 256, 256, 256),
+                                        (1, 64, 64, 64), (129, 64, 64, 64), (1000, 128, 128, 128),
+                                        (5000, 1024, 1024, 1024), (50_000, 1024, 1024, 1024), (333, 512, 192, 64)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_transform_bf16_tcgen05(cuda, M, N, K1, K2, relu):
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    bf = torch.bfloat16
+    a1 = torch.randn(M, K1, device=cuda, generator=g).to(bf)
+    w1 = (torch.randn(N, K1, device=cuda, generator=g) / K1 ** 0.5).to(bf)
+    a2 = torch.randn(M, K2, device=cuda, generator=g).to(bf) if K2 else None
+    w2 = (torch.randn(N, K2, device=cuda, generator=g) / K2 ** 0.5).to(bf) if K2 else None
+    b = torch.randn(N, device=cuda, generator=g)
+    y = ops.node_transform(a1, w1, a2, w2, b, relu=relu)
+    torch.cuda.synchronize()
+    assert y.dtype == bf and y.shape == (M, N)
+    e = _ref(a1, w1, a2, w2, b, relu)           # exact products of the bf16 inputs, float64 accumulate
+    err = (y.double() - e).abs()
+    scale = max(1.0, float(e.abs().max()))
+    # inputs are identical bf16 values; the only errors are fp32 accumulation and the final bf16 rounding (2^-9 relative)
+    assert float(err.max()) < 8e-3 * scale, f"max err {float(err.max())} scale {scale}"
+    assert float(err.mean()) < 2e-3
+
+
+@pytest.mark.parametrize("hids,out_dtype", [(64, torch.float32), (128, torch.float32), (1024, torch.float32),
+                                             (1024, torch.bfloat16), (96, torch.float32)])
+def test_conv_in_fused_vs_oracle(cuda, hids, out_dtype):
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    from lpgnn_b200.graph import BipartiteCSR
+    m, n, z = 700, 1300, 6000
+    row, col, val = make_graph_arrays(m, n, z, 5)
+    g = BipartiteCSR.from_coo_arrays(row, col, val, m, n, cuda)
+    ref = port.graph_from_coo(row, col, val, m, n)
+    rng = np.random.default_rng(hids)
+    x_s = rng.standard_normal((m, 8)).astype(np.float32)
+    x_t = rng.standard_normal((n, 8)).astype(np.float32)
+    w_rel = (rng.standard_normal((hids, 8)) / 3).astype(np.float32)
+    w_root = (rng.standard_normal((hids, 8)) / 3).astype(np.float32)
+    b = rng.standard_normal(hids).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    csr, csc = g.views()
+    # variables side: dst = vars, src = cons, orientation = CSC
+    out, agg = ops.conv_in_fused(csc, t(x_s), t(x_t), t(w_rel), t(b), t(w_root), out_dtype, relu=True, want_agg=True)
+    agg_e = port.spmm_sequential(ref.colptr, ref.row_csc, ref.val_csc, x_s)
+    np.testing.assert_allclose(agg.cpu().numpy(), agg_e, rtol=1e-5, atol=1e-5)
+    e = np.maximum(agg_e.astype(np.float64) @ w_rel.T.astype(np.float64) + b + x_t.astype(np.float64) @ w_root.T, 0)
+    tol = 1e-4 if out_dtype == torch.float32 else 3e-2
+    np.testing.assert_allclose(out.float().cpu().numpy(), e, rtol=tol, atol=tol)
+    # constraints side, no relu
+    out2, _ = ops.conv_in_fused(csr, t(x_t), t(x_s), t(w_rel), t(b), t(w_root), out_dtype, relu=False)
+    agg2 = port.spmm_sequential(ref.rowptr, ref.col, ref.val, x_t)
+    e2 = agg2.astype(np.float64) @ w_rel.T.astype(np.float64) + b + x_s.astype(np.float64) @ w_root.T
+    np.testing.assert_allclose(out2.float().cpu().numpy(), e2, rtol=tol, atol=tol)
