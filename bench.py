@@ -1,0 +1,462 @@
+#!/usr/bin/env python
+"""bench.py -- the lp-gnn hot path on B200 (contract: see the task prompt / DESIGN.md section 6).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+
+A *step* is one pass of the hot path over one synthetic LP of the named workload (default: C2 of
+BASELINE.json, GCN_FC(8,8,hids=1024,depth=3) inference on a 50K x 100K LP with ~500K nonzeros):
+
+    graph build (COO -> CSR+CSC)  ->  GCN_FC forward (conv1, SpMM, node transforms, head+mask)
+    ->  basis selection (softmax / top-m / status)
+
+* ``value``  LPs/s with the step's inputs (COO, node features) already resident in HBM.
+* ``e2e``    the same metric through the public API with HOST (pinned) inputs: H2D copies of the COO
+             and the features, the step, and a D2H copy of the status vector inside the timed region.
+* ``roofline``      dominant kernel (tcgen05 node transform) against the measured bf16 peak, timed
+                    live with CUDA events; ``kernels`` lists every kernel of the step the same way
+                    (HBM-bound ones against the measured copy bandwidth).
+* ``cpu_baseline``  the oracle port of the reference's CPU path, timed on this box's host cores on a
+                    bounded sample (rank 0, N=1 only).
+With N > 1 (torchrun, one rank per GPU) every rank runs its own LPs (independent units, no data-path
+collective): weak scaling, value = N * K LPs / max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+# ----------------------------------------------------------------------------------------------- utils
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", local) if torch.cuda.is_available() else None)
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def max_over_ranks(x, world, dev):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def workload_spec(name):
+    from lpgnn_b200 import synth
+    cfg = dict(synth.CONFIGS[name])
+    cfg["name"] = name
+    return cfg
+
+
+def mp_edges(nnz, depth, fwd_bwd=False):
+    # z * 2 directions * (D-1) conv layers * (1 fwd | 2 fwd+bwd)
+    return nnz * 2 * (depth - 1) * (2 if fwd_bwd else 1)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def time_kernel(fn, reps, flush=None):
+    """Average duration (ms) of ``fn`` over ``reps`` launches, CUDA events on the current stream."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()                      # > L2-sized write between timed launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / reps
+
+
+def run_gpu(args):
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import _lib, arch, ops, synth
+    from lpgnn_b200.graph import BipartiteCSR
+
+    rank, world, local = dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    peaks = load_peaks()
+    cfg = workload_spec(args.workload)
+    bf16 = args.precision == "bf16"
+
+    # every rank draws its own LP of the workload's shape (independent units)
+    lp = synth.processed_lp(cfg["m"], cfg["n"], cfg["nnz"], seed=cfg["seed"] + 1000 * rank, structure=args.structure)
+    m, n, z, H, D = lp.m, lp.n, lp.nnz, cfg["hids"], cfg["depth"]
+    torch.manual_seed(0)
+    model = arch.GCN_FC(8, 8, hids=H, depth=D).to(dev).eval()
+    model.set_precision(args.precision)
+
+    # host (pinned) inputs of one step
+    h_row = torch.from_numpy(lp.row.astype(np.int32)).pin_memory()
+    h_col = torch.from_numpy(lp.col.astype(np.int32)).pin_memory()
+    h_val = torch.from_numpy(lp.a_data.astype(np.float32)).pin_memory()
+    h_xs = torch.from_numpy(lp.c_feas).pin_memory()
+    h_xt = torch.from_numpy(lp.v_feas).pin_memory()
+    h_status = torch.empty(m + n, dtype=torch.uint8).pin_memory()
+    h2d_bytes = sum(t.numel() * t.element_size() for t in (h_row, h_col, h_val, h_xs, h_xt))
+    d2h_bytes = h_status.numel()
+
+    # device-resident copies for the HBM-resident arm
+    d_row, d_col, d_val = h_row.to(dev), h_col.to(dev), h_val.to(dev)
+    d_xs, d_xt = h_xs.to(dev), h_xt.to(dev)
+
+    def step_resident():
+        g = BipartiteCSR.from_edge_index(torch.stack([d_row, d_col]), d_val, (m, n))   # builds on the device
+        batch = types.SimpleNamespace(x_s=d_xs, x_t=d_xt, edge_index=g)
+        with torch.no_grad():
+            return model.predict_basis(batch, int64=False)
+
+    def step_e2e():
+        row = h_row.to(dev, non_blocking=True)
+        col = h_col.to(dev, non_blocking=True)
+        val = h_val.to(dev, non_blocking=True)
+        xs = h_xs.to(dev, non_blocking=True)
+        xt = h_xt.to(dev, non_blocking=True)
+        g = BipartiteCSR.from_edge_index(torch.stack([row, col]), val, (m, n))
+        batch = types.SimpleNamespace(x_s=xs, x_t=xt, edge_index=g)
+        with torch.no_grad():
+            st = model.predict_basis(batch, int64=False)
+        h_status.copy_(st, non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # the caller needs the statuses on the host
+        return h_status
+
+    # ---- warm-up, then EXACTLY K timed steps between barrier + synchronize
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier(world)
+    torch.cuda.synchronize()
+    launches0 = lib.lpgnn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        status = step_resident()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = lib.lpgnn_launch_count() - launches0
+    barrier(world)
+    t_ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    n_basic = int((status == 1).sum().item())
+    assert n_basic == m, f"basis invariant violated: {n_basic} basic nodes for m={m}"
+
+    # ---- end-to-end arm (host buffers, H2D + D2H inside the timed region)
+    for _ in range(3):
+        step_e2e()
+    barrier(world)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
+    barrier(world)
+    clocks = sampler.stop() if rank == 0 else None
+
+    lps = world * args.steps / (t_ms / 1e3)
+    lps_e2e = world * args.steps / (t_e2e / 1e3)
+    out = {
+        "metric": "LPs/sec (basis prediction: graph build + GCN_FC forward + basis selection)",
+        "value": lps, "unit": "LPs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if bf16 else "f32", "data": "synthetic",
+        "config": {"workload": f"{cfg['name']}: GCN_FC(8,8,hids={H},depth={D}) inference, synthetic {args.structure} LP "
+                               f"{m}x{n}, nnz={z}, one LP per step per GPU",
+                   "l2": "activations per layer (>=300 MB) exceed the 126 MB L2; no explicit flush in the step loop",
+                   "precision": args.precision, "structure": args.structure},
+        "mp_edges_per_sec": mp_edges(z, D) * lps,
+        "e2e": {"value": lps_e2e, "unit": "LPs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": t_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+
+    if rank == 0 and not args.no_kernels:
+        out.update(kernel_rooflines(model, lp, dev, peaks, bf16, args))
+    if rank == 0 and world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(cfg, lp, args, sample_budget_s=args.cpu_seconds)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def kernel_rooflines(model, lp, dev, peaks, bf16, args):
+    """Per-kernel durations (CUDA events, live) and roofline fractions with the algorithmic bytes /
+    flops of SURVEY 8d (stated in DESIGN.md section 4)."""
+    from lpgnn_b200 import ops
+    from lpgnn_b200.graph import BipartiteCSR
+    m, n, z = lp.m, lp.n, lp.nnz
+    H = model.hids
+    dt = torch.bfloat16 if bf16 else torch.float32
+    s = 2 if bf16 else 4
+    g = BipartiteCSR.from_coo_arrays(lp.row, lp.col, lp.a_data.astype(np.float32), m, n, dev)
+    csr, csc = g.views()
+    xs, xt = torch.from_numpy(lp.c_feas).to(dev), torch.from_numpy(lp.v_feas).to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    reps = args.kernel_reps
+    kernels = []
+
+    def add(name, bound, t_ms, alg, launches_per_step):
+        if bound == "hbm":
+            ach = alg / (t_ms * 1e-3) / 1e9
+            peak, unit = peaks["hbm_gbs"], "GB/s"
+        else:
+            ach = alg / (t_ms * 1e-3) / 1e12
+            peak, unit = peaks["bf16_burst"], "TFLOP/s"
+        kernels.append({"kernel": name, "bound": bound, "ms": t_ms, "algorithmic": alg, "achieved": ach, "peak": peak,
+                        "unit": unit, "frac": ach / peak, "launches_per_step": launches_per_step})
+
+    c1 = model.conv1
+    w = lambda p: p.detach()
+    # input layer (fused aggregate+transform), variables side: rows = n
+    f_in = lambda: ops.conv_in_fused(csc, xs, xt, w(c1.left2right.lin_rel.weight), w(c1.left2right.lin_rel.bias),
+                                     w(c1.left2right.lin_root.weight), dt, relu=True)
+    t = time_kernel(f_in, reps, flush)
+    add("conv_in_fused (vars side)", "hbm", t, n * H * s + (m + n) * 8 * 4 + z * 8 + (n + 1) * 4, 1)
+    right, _ = f_in()
+    left, _ = ops.conv_in_fused(csr, xt, xs, w(c1.right2left.lin_rel.weight), w(c1.right2left.lin_rel.bias),
+                                w(c1.right2left.lin_root.weight), dt, relu=True)
+    if len(model.layers):
+        conv = model.layers[0]
+        cast = conv._cache.get
+        # SpMM pair of one hidden layer: compulsory bytes 2(m+n)Hs + 16z + 4(m+n+2)   
+        t_s = time_kernel(lambda: ops.spmm(csr, right), reps, flush)
+        t_t = time_kernel(lambda: ops.spmm(csc, left), reps, flush)
+        add("spmm pair (A.R and A^T.L)", "hbm", t_s + t_t, 2 * (m + n) * H * s + 16 * z + 4 * (m + n + 2), 2)
+        kernels[-1]["gather_model_bytes"] = 2 * z * H * s + (m + n) * H * s + 16 * z
+        agg_t, agg_s = ops.spmm(csc, left), ops.spmm(csr, right)
+        l2r, r2l = conv.left2right, conv.right2left
+        f_t = lambda: ops.node_transform(agg_t, cast(l2r.lin_rel.weight, dt), right, cast(l2r.lin_root.weight, dt),
+                                         w(l2r.lin_rel.bias), relu=True)
+        f_s = lambda: ops.node_transform(agg_s, cast(r2l.lin_rel.weight, dt), left, cast(r2l.lin_root.weight, dt),
+                                         w(r2l.lin_rel.bias), relu=True)
+        t_g = time_kernel(f_t, reps, flush) + time_kernel(f_s, reps, flush)
+        add("node_transform pair (tcgen05)" if bf16 else "node_transform pair (fp32 CUDA cores)", "tensor", t_g,
+            4 * (m + n) * H * H, 2)
+        right2 = f_t()
+    else:
+        right2 = right
+    t_h = time_kernel(lambda: ops.head_mask(right2, w(model.lin_right.weight), w(model.lin_right.bias), xt), reps, flush)
+    add("head_mask (vars side)", "hbm", t_h, n * (H * s + 8 * 4 + 3 * 4), 1)
+    lc = torch.randn(m, 3, device=dev)
+    lv = torch.randn(n, 3, device=dev)
+    t_sel = time_kernel(lambda: ops.basis_select(lc, lv, int64=False), reps, flush)
+    add("basis_select (12 launches)", "hbm", t_sel, (m + n) * (12 + 4 + 1 + 4 * 4 + 4 + 1), 12)
+    h_row = torch.from_numpy(lp.row.astype(np.int32)).to(dev)
+    h_col = torch.from_numpy(lp.col.astype(np.int32)).to(dev)
+    h_val = torch.from_numpy(lp.a_data.astype(np.float32)).to(dev)
+    ei = torch.stack([h_row, h_col])
+    t_b = time_kernel(lambda: BipartiteCSR.from_edge_index(ei, h_val, (m, n)), reps, flush)
+    add("graph_build (COO->CSR+CSC)", "hbm", t_b, z * 12 * 2 * 2, -1)
+    dom = max(kernels, key=lambda k: k["ms"])
+    roof = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
+            "frac": dom["frac"], "traffic": None, "kernel": dom["kernel"], "peak_source": peaks["source"] +
+            (" (burst bf16 figure: kernel timed alone)" if dom["bound"] == "tensor" else " (copy bandwidth)")}
+    return {"roofline": roof, "kernels": kernels}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arms
+def _port_setup(cfg, lp):
+    from oracle import port        # the one place bench.py executes oracle/: the timed CPU baseline
+    torch.manual_seed(0)
+    model = port.PortGCN_FC(8, 8, hids=cfg["hids"], depth=cfg["depth"]).eval()
+    g = port.graph_from_coo(lp.row, lp.col, lp.a_data.astype(np.float32), lp.m, lp.n)
+    return port, model, g
+
+
+def cpu_step(port, model, lp):
+    """One LP through the reference's CPU path: graph construction (MyToBipartite equivalent), GCN_FC
+    forward, inference_gnn -- all on the host cores."""
+    g = port.graph_from_coo(lp.row, lp.col, lp.a_data.astype(np.float32), lp.m, lp.n)
+    tg = port.TorchGraph(g)
+    with torch.no_grad():
+        lc, lv = model(torch.from_numpy(lp.c_feas), torch.from_numpy(lp.v_feas), tg)
+        return port.inference_gnn_t(torch.cat((lc, lv), 0), lp.m)
+
+
+def cpu_baseline(cfg, lp, args, sample_budget_s=20.0):
+    import warnings
+    warnings.filterwarnings("ignore")
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    port, model, _ = _port_setup(cfg, lp)
+    cpu_step(port, model, lp)                      # warm-up
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        cpu_step(port, model, lp)
+        reps += 1
+        if time.perf_counter() - t0 > sample_budget_s or reps >= 20:
+            break
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": 1.0 / dt, "unit": "LPs/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} LPs of the same workload ({cfg['name']}, fp32), {dt * 1e3:.0f} ms/LP; oracle port of the "
+                      f"reference CPU path (PyG-equivalent restatement, not the PyG binary); torch threads={cores}",
+            "mp_edges_per_sec": mp_edges(lp.nnz, cfg["depth"]) / dt}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the Python
+    reference cannot travel to the GPU box), all host threads, same config / metric / unit."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import synth
+    cfg = workload_spec(args.workload)
+    lp = synth.processed_lp(cfg["m"], cfg["n"], cfg["nnz"], seed=cfg["seed"], structure=args.structure)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    port, model, _ = _port_setup(cfg, lp)
+    for _ in range(max(1, min(args.warmup, 3))):
+        cpu_step(port, model, lp)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        status = cpu_step(port, model, lp)
+    dt = time.perf_counter() - t0
+    assert int((status == 1).sum()) == lp.m
+    lps = args.steps / dt
+    print(json.dumps({
+        "impl": "reference",
+        "metric": "LPs/sec (basis prediction: graph build + GCN_FC forward + basis selection)",
+        "value": lps, "unit": "LPs/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{cfg['name']}: GCN_FC(8,8,hids={cfg['hids']},depth={cfg['depth']}) inference, synthetic "
+                               f"{args.structure} LP {lp.m}x{lp.n}, nnz={lp.nnz}, one LP per step",
+                   "precision": "fp32", "structure": args.structure},
+        "mp_edges_per_sec": mp_edges(lp.nnz, cfg["depth"]) * lps,
+        "cpu_baseline": {"value": lps, "unit": "LPs/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} LPs, one per step; oracle port of the reference CPU path "
+                                   f"(reference arch.py/val.py restated with torch CPU ops; PyG/torch_sparse are not "
+                                   f"installable here), torch threads={cores}"},
+        "e2e": {"value": lps, "unit": "LPs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--structure", default="staircase", choices=["staircase", "uniform"])
+    ap.add_argument("--kernel-reps", type=int, default=10)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-kernels", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 3
+        args.warmup = args.warmup if args.warmup is not None else 1
+        run_reference(args)
+    else:
+        args.steps = args.steps if args.steps is not None else 50
+        args.warmup = args.warmup if args.warmup is not None else 5
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -54,6 +54,8 @@ typedef void* lpgnn_stream_t; /* cudaStream_t */
 
 LPGNN_API int lpgnn_version(void);
 LPGNN_API const char* lpgnn_last_error(void);
+/* Number of CUDA kernels this library has enqueued so far in this process (all streams). */
+LPGNN_API uint64_t lpgnn_launch_count(void);
 /* Fills SM count and compute capability of the current device. */
 LPGNN_API int lpgnn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

@@ -24,6 +24,7 @@ _i32, _i64, _sz, _int = C.c_int32, C.c_int64, C.c_size_t, C.c_int
 SIGNATURES = {
     "lpgnn_version": (_int, []),
     "lpgnn_last_error": (C.c_char_p, []),
+    "lpgnn_launch_count": (C.c_uint64, []),
     "lpgnn_device_info": (_int, [C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)]),
     "lpgnn_graph_build_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "lpgnn_graph_build": (_int, [_p, _p, _int, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),

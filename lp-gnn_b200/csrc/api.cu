@@ -15,6 +15,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
 static int g_sm_count = 0;
 static int g_cc_major = 0, g_cc_minor = 0;
 static int g_dev_checked = -1;
@@ -59,6 +62,7 @@ using namespace lpgnn;
 
 extern "C" int lpgnn_version(void) { return LPGNN_VERSION; }
 extern "C" const char* lpgnn_last_error(void) { return g_err; }
+extern "C" uint64_t lpgnn_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 extern "C" int lpgnn_device_info(int* sm, int* major, int* minor) {
   if (int rc = check_device()) return rc;

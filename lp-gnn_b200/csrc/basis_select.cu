@@ -252,5 +252,6 @@ extern "C" int lpgnn_basis_select(const float* logits_cons, int32_t m, const flo
     status_kernel<uint8_t><<<ntiles, kThreads, 0, st>>>(keys, side, total, m, state, ties,
                                                         reinterpret_cast<uint8_t*>(status), counts_out);
   LPGNN_LAUNCH_OK();
+  count_launches(12);
   return LPGNN_OK;
 }

@@ -14,6 +14,7 @@ namespace lpgnn {
 void set_error(const char* fmt, ...);
 int check_device();  // LPGNN_OK or LPGNN_ENODEVICE
 int sm_count();
+void count_launches(int n);  // kernels enqueued by the library (lpgnn_launch_count)
 
 #define LPGNN_CUDA_OK(expr)                                                              \
   do {                                                                                   \

@@ -88,6 +88,7 @@ int launch(const int32_t* ptr, const int32_t* idx, const float* val, int32_t row
                                                                  b_rel, W_root, N,
                                                                  reinterpret_cast<__nv_bfloat16*>(out), relu, agg_out);
   LPGNN_LAUNCH_OK();
+  count_launches(1);
   return LPGNN_OK;
 }
 

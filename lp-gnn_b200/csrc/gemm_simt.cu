@@ -119,6 +119,7 @@ int node_transform_f32(const float* A1, int K1, const float* W1, const float* A2
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
   sgemm_cat_kernel<<<grid, kThreads, 0, st>>>(s0, s1, bias, M, N, out, relu);
   LPGNN_LAUNCH_OK();
+  count_launches(1);
   return LPGNN_OK;
 }
 

@@ -221,6 +221,7 @@ int launch(const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& a2, 
   const int grid = tiles < sm_count() ? tiles : sm_count();
   gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu);
   LPGNN_LAUNCH_OK();
+  count_launches(1);
   return LPGNN_OK;
 }
 

@@ -160,6 +160,7 @@ int radix_sort(SortBufs& b, int64_t n, int bits, cudaStream_t st) {
     radix_scatter_kernel<<<nblocks, kSortThreads, 0, st>>>(b.k[cur], b.v[cur], b.k[cur ^ 1], b.v[cur ^ 1], n,
                                                            shift, b.counts, nblocks);
     cur ^= 1;
+    count_launches(3);
   }
   return cur;
 }
@@ -240,5 +241,6 @@ extern "C" int lpgnn_graph_build(const void* coo_row, const void* coo_col, int i
   gather_f32_kernel<<<gb, tb, 0, st>>>(val, b.v[cur], val_csc, z);
   fill_ptr_kernel<<<ceil_div(z + 1, tb), tb, 0, st>>>(b.k[cur], z, n, colptr);
   LPGNN_LAUNCH_OK();
+  count_launches(idx_is_i64 ? 12 : 10);  // + 3 per radix pass, counted in radix_sort
   return LPGNN_OK;
 }

@@ -110,6 +110,7 @@ extern "C" int lpgnn_head_mask(const void* H, int h_dtype, int32_t rows, int32_t
                                                                   W, b, feas, q, logits, raw_out);
   }
   LPGNN_LAUNCH_OK();
+  count_launches(1);
   return LPGNN_OK;
 }
 
@@ -121,5 +122,6 @@ extern "C" int lpgnn_add_knowledge(const float* logits_in, int32_t rows, const f
   LPGNN_REQUIRE(logits_in && feas && logits_out, "add_knowledge: null pointer");
   add_knowledge_kernel<<<ceil_div(rows, 256), 256, 0, (cudaStream_t)stream>>>(logits_in, rows, feas, q, logits_out);
   LPGNN_LAUNCH_OK();
+  count_launches(1);
   return LPGNN_OK;
 }

@@ -119,6 +119,7 @@ int launch(const int32_t* ptr, const int32_t* idx, const float* val, int32_t row
   spmm_rows_kernel<T, G, CH><<<grid, kThreads, 0, st>>>(ptr, idx, val, rows, reinterpret_cast<const uint4*>(X),
                                                         reinterpret_cast<uint4*>(Y), chunks);
   LPGNN_LAUNCH_OK();
+  count_launches(1);
   return LPGNN_OK;
 }
 

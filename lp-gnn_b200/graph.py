@@ -62,7 +62,9 @@ class BipartiteCSR:
         row, col = edge_index[0], edge_index[1]
         if edge_attr is None:
             edge_attr = torch.ones(row.shape[0], dtype=torch.float32, device=row.device)
-        if row.numel() and (int(row.max()) >= g.m or int(col.max()) >= g.n or int(row.min()) < 0 or int(col.min()) < 0):
+        # range check only for host inputs (a device-side check would force a stream sync in the hot loop)
+        if not row.is_cuda and row.numel() and (
+                int(row.max()) >= g.m or int(col.max()) >= g.n or int(row.min()) < 0 or int(col.min()) < 0):
             raise ValueError("edge_index out of range for sparse_sizes")
         g._coo = (row.to(torch.int32).contiguous(), col.to(torch.int32).contiguous(),
                   edge_attr.to(torch.float32).contiguous())

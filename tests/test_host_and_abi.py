@@ -1,0 +1,106 @@
+"""Host-side logic and the C-ABI surface, no GPU: the library loads, exports every symbol that
+include/lpgnn.h declares, and refuses to compute without a device (no CPU fallback)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "lpgnn.h")).read()
+    return sorted(set(re.findall(r"LPGNN_API\s+[\w\s\*]+?(lpgnn_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import _lib
+    syms = _header_symbols()
+    assert len(syms) >= 12
+    assert sorted(_lib.SIGNATURES.keys()) == syms                   # ctypes table == header
+    lib = _lib.load()
+    for s in syms:
+        assert hasattr(lib, s), s
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (lpgnn_\w+)", out))
+    assert exported == set(syms)                                    # nothing undeclared leaks out either
+    assert lib.lpgnn_version() == 100
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device behaviour")
+def test_no_cpu_fallback_without_device():
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import _lib, ops
+    from lpgnn_b200.graph import BipartiteCSR
+    lib = _lib.load()
+    assert lib.lpgnn_device_info(None, None, None) == -3            # LPGNN_ENODEVICE
+    assert "no CPU fallback" in _lib.last_error()
+    x = torch.zeros(4, 8)
+    ptr = torch.zeros(5, dtype=torch.int32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.spmm((ptr, ptr, x, 4), x)
+    g = BipartiteCSR.from_edge_index(torch.tensor([[0, 1], [1, 0]]), torch.tensor([1.0, 2.0]), (2, 2))
+    assert not g.is_cuda and g.nnz() == 2 and g.t().sparse_sizes() == (2, 2)
+    with pytest.raises(RuntimeError, match="host COO"):
+        g.views()
+
+
+def test_sass_contains_blackwell_tensor_and_tma_instructions():
+    """The node transform must be a tcgen05/TMA kernel, not mma.sync (B200_PROFILING.md mnemonics)."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import _lib
+    exe = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([exe, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
+    assert "HMMA." not in sass.replace("UTCHMMA", "")
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "lp-gnn_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+
+
+def test_synthetic_lp_layout_and_invariants():
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import synth
+    lp = synth.config_lp("C1")
+    assert lp.c_feas.shape == (1000, 8) and lp.v_feas.shape == (2000, 8)
+    assert lp.c_feas.dtype == np.float32 and 9000 < lp.nnz <= 10_500
+    assert np.abs(lp.a_data).max() <= 1 and np.abs(lp.c_feas).max() <= 1       # dataset.py:235-238
+    key = lp.row * lp.n + lp.col
+    assert (np.diff(key) > 0).all()                                            # row-major, no duplicates
+    for feas, y in ((lp.c_feas, lp.y_s), (lp.v_feas, lp.y_t)):                 # dataset.py:203-207
+        assert set(np.unique(feas[:, 5])) <= {-1.0, 0.0, 1.0}
+        assert (y[feas[:, 5] != 0] != 0).all() and (y[feas[:, 7] != 0] != 2).all()
+    again = synth.config_lp("C1")
+    assert np.array_equal(again.row, lp.row) and np.array_equal(again.v_feas, lp.v_feas)   # seeded
+    pop = synth.lp_population(50)
+    assert len(pop) == 50 and all(n == 2 * m for m, n, _, _ in pop)
+
+
+def test_features_against_golden():
+    import scipy.sparse as sp
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import features
+    gold = os.path.join(ROOT, "tests", "golden")
+    for name in ("tiny_5x7", "small_300x600", "bounds_40x90"):
+        z = np.load(os.path.join(gold, f"lp_features_{name}.npz"))
+        m, n = z["in_shape"]
+        A = sp.csr_matrix((z["in_A_data"], z["in_A_indices"], z["in_A_indptr"]), shape=(m, n))
+        c, b_l, A2, b_u, l, u = features.scale_lp(z["in_c"], z["in_b_l"], A, z["in_b_u"], z["in_l"], z["in_u"])
+        np.testing.assert_array_equal(A2.data, z["out_A_data"])
+        np.testing.assert_array_equal(c, z["out_c"])
+        v, cf = features.node_features(c, b_l, A2, b_u, l, u)
+        np.testing.assert_allclose(v, z["out_v_feas"], rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(cf, z["out_c_feas"], rtol=1e-12, atol=1e-14)
+        np.testing.assert_array_equal(v[:, [5, 7]], z["out_v_feas"][:, [5, 7]])

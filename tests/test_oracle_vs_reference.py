@@ -1,0 +1,70 @@
+"""The oracle port against the reference's own Python imported verbatim (only where /root/reference
+exists, i.e. the build container; skipped on the GPU box)."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+from oracle.ref_import import load_reference, reference_available
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="/root/reference not present")
+
+
+@pytest.fixture(scope="module")
+def R():
+    return load_reference()
+
+
+def test_state_dict_keys_and_param_count(R):
+    torch.manual_seed(0)
+    ref = R.arch.GCN_FC(8, 8, hids=1024, depth=3)
+    torch.manual_seed(0)
+    mine = port.PortGCN_FC(8, 8, hids=1024, depth=3)
+    assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
+    assert sum(p.numel() for p in ref.parameters()) == 4_237_318
+    for k, v in ref.state_dict().items():
+        assert torch.equal(v, mine.state_dict()[k]), k               # same init draw order
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_generator_features_match_reference(R, seed):
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import features, synth
+    c, b_l, A, b_u, l, u = synth.raw_lp(200, 400, 2000, seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        rc, rbl, rA, rbu, rl, ru = R.dataset.scaling(c.copy(), b_l.copy(), A.copy(), b_u.copy(), l.copy(), u.copy())
+    rv, rcf = R.dataset.cvt_to_features(rc, rbl, rA, rbu, rl, ru)
+    for impl in (port.scaling, features.scale_lp):
+        c2, bl2, A2, bu2, l2, u2 = impl(c, b_l, A, b_u, l, u)
+        np.testing.assert_array_equal(c2, rc)
+        np.testing.assert_array_equal(A2.toarray(), rA.toarray())
+        np.testing.assert_array_equal(bl2, rbl)
+        np.testing.assert_array_equal(u2, ru)
+    for impl in (port.cvt_to_features, features.node_features):
+        v, cf = impl(rc, rbl, rA, rbu, rl, ru)
+        np.testing.assert_allclose(v, rv, rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(cf, rcf, rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("logit_scale", [1.0, 8.0])
+def test_inference_gnn_matches_reference(R, logit_scale):
+    rng = np.random.default_rng(3)
+    m, n = 700, 1500
+    logits = (rng.standard_normal((m + n, 3)) * logit_scale).astype(np.float32)
+    ref = R.val.inference_gnn(torch.from_numpy(logits), m).numpy()
+    np.testing.assert_array_equal(port.inference_gnn_np(logits, m), ref)
+
+
+def test_add_knowledge_matches_reference(R):
+    rng = np.random.default_rng(4)
+    l, r = rng.standard_normal((50, 3)).astype(np.float32), rng.standard_normal((80, 3)).astype(np.float32)
+    fl, fr = rng.integers(-1, 2, (50, 8)).astype(np.float32), rng.integers(-1, 2, (80, 8)).astype(np.float32)
+    a, b = R.arch.add_knowledge(torch.from_numpy(l), torch.from_numpy(r), torch.from_numpy(fl), torch.from_numpy(fr))
+    c, d = port.add_knowledge_np(l, r, fl, fr)
+    np.testing.assert_allclose(c, a.numpy(), rtol=0, atol=2e-6)
+    np.testing.assert_allclose(d, b.numpy(), rtol=0, atol=2e-6)
+    e, f = port.add_knowledge_t(torch.from_numpy(l), torch.from_numpy(r), torch.from_numpy(fl), torch.from_numpy(fr))
+    assert torch.equal(e, a) and torch.equal(f, b)
