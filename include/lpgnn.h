@@ -41,6 +41,9 @@ extern "C" {
 #define LPGNN_BF16 1
 
 /* epilogue flags of the node transforms */
+/* lpgnn_graph_build flags */
+#define LPGNN_COO_SORTED 1
+
 #define LPGNN_EPI_NONE 0
 #define LPGNN_EPI_RELU 1
 
@@ -69,13 +72,19 @@ LPGNN_API int lpgnn_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * (stable sort of the CSR entries by column: column-major, ascending row inside a column) with
  * the permutation csr2csc (val_csc[k] = val[csr2csc[k]]).  Bit-exact with the reference's
  * ordering; all integer work, deterministic (no atomics on ordered data).
+ *
+ * flags: LPGNN_COO_SORTED = the caller asserts the COO is already in canonical (row, col) order
+ * (torch_sparse's `is_sorted=True`; true for everything LPDataset.get produces, dataset.py:251-252),
+ * which skips the COO sort.  status (device int32, optional) receives a bit mask after the call:
+ * bit 0 = the SORTED claim was false (outputs are then NOT canonical), bit 1 = an index was out of
+ * range.  It is written asynchronously; read it after synchronising the stream.
  * ------------------------------------------------------------------------------------------- */
 LPGNN_API size_t lpgnn_graph_build_workspace_bytes(int64_t nnz, int32_t m, int32_t n);
 LPGNN_API int lpgnn_graph_build(const void* coo_row, const void* coo_col, int idx_is_i64,
-                      const float* coo_val, int64_t nnz, int32_t m, int32_t n,
+                      const float* coo_val, int64_t nnz, int32_t m, int32_t n, int flags,
                       int32_t* rowptr /*[m+1]*/, int32_t* col /*[nnz]*/, float* val /*[nnz]*/,
                       int32_t* colptr /*[n+1]*/, int32_t* row_csc /*[nnz]*/, float* val_csc /*[nnz]*/,
-                      int32_t* csr2csc /*[nnz]*/,
+                      int32_t* csr2csc /*[nnz]*/, int32_t* status /*[1] device, optional*/,
                       void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------

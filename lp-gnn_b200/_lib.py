@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "liblpgnn.so")
 
 F32, BF16 = 0, 1
 EPI_NONE, EPI_RELU = 0, 1
+COO_SORTED = 1
 
 _p = C.c_void_p
 _i32, _i64, _sz, _int = C.c_int32, C.c_int64, C.c_size_t, C.c_int
@@ -27,7 +28,7 @@ SIGNATURES = {
     "lpgnn_launch_count": (C.c_uint64, []),
     "lpgnn_device_info": (_int, [C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)]),
     "lpgnn_graph_build_workspace_bytes": (_sz, [_i64, _i32, _i32]),
-    "lpgnn_graph_build": (_int, [_p, _p, _int, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "lpgnn_graph_build": (_int, [_p, _p, _int, _p, _i64, _i32, _i32, _int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "lpgnn_spmm": (_int, [_p, _p, _p, _i32, _p, _p, _i32, _int, _p]),
     "lpgnn_conv_in_fused": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p, _i32, _p, _int, _int, _p, _p]),
     "lpgnn_node_transform": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _int, _p]),

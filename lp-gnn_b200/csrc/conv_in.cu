@@ -16,7 +16,7 @@ namespace lpgnn {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kRows = 64;
+constexpr int kRows = 32;
 
 template <int KT, typename OutT>
 __global__ void __launch_bounds__(kThreads)
@@ -29,22 +29,32 @@ conv_in_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
   const int64_t row0 = (int64_t)blockIdx.x * kRows;
   const int nrows = (int)min((int64_t)kRows, rows - row0);
 
-  // ---- phase 1: aggregate + stage x_dst
-  for (int p = threadIdx.x; p < kRows * KT; p += kThreads) {
-    const int r = p / KT, k = p % KT;
-    float v = 0.f;
+  // ---- phase 1: aggregate + stage x_dst.  8 adjacent lanes share a row (they read the same (idx,val) pair
+  // through one broadcast transaction and 32 contiguous bytes of the source row); four neighbours in flight.
+  for (int p = threadIdx.x; p < kRows * 8; p += kThreads) {
+    const int r = p >> 3, f0 = p & 7;
     if (r < nrows) {
       const int64_t row = row0 + r;
-      if (k < k_src) {
-        const int32_t beg = ptr[row], end = ptr[row + 1];
-        for (int32_t e = beg; e < end; ++e)
-          v = fmaf(__ldg(val + e), __ldg(Xsrc + (int64_t)__ldg(idx + e) * k_src + k), v);
+      const int32_t beg = ptr[row], end = ptr[row + 1];
+      for (int k = f0; k < k_src; k += 8) {
+        float v = 0.f;
+        int32_t e = beg;
+        for (; e + 4 <= end; e += 4) {
+          const int32_t i0 = __ldg(idx + e), i1 = __ldg(idx + e + 1), i2 = __ldg(idx + e + 2), i3 = __ldg(idx + e + 3);
+          const float w0 = __ldg(val + e), w1 = __ldg(val + e + 1), w2 = __ldg(val + e + 2), w3 = __ldg(val + e + 3);
+          const float x0 = __ldg(Xsrc + (int64_t)i0 * k_src + k), x1 = __ldg(Xsrc + (int64_t)i1 * k_src + k);
+          const float x2 = __ldg(Xsrc + (int64_t)i2 * k_src + k), x3 = __ldg(Xsrc + (int64_t)i3 * k_src + k);
+          v = fmaf(w0, x0, v); v = fmaf(w1, x1, v); v = fmaf(w2, x2, v); v = fmaf(w3, x3, v);   // CSR order
+        }
+        for (; e < end; ++e) v = fmaf(__ldg(val + e), __ldg(Xsrc + (int64_t)__ldg(idx + e) * k_src + k), v);
         if (agg_out) agg_out[row * k_src + k] = v;
-      } else if (k < K) {
-        v = __ldg(Xdst + row * k_dst + (k - k_src));
+        z[r][k] = v;
       }
+      for (int k = f0; k < k_dst; k += 8) z[r][k_src + k] = __ldg(Xdst + row * k_dst + k);
+      for (int k = K + f0; k < KT; k += 8) z[r][k] = 0.f;
+    } else {
+      for (int k = f0; k < KT; k += 8) z[r][k] = 0.f;
     }
-    z[r][k] = v;
   }
   __syncthreads();
 

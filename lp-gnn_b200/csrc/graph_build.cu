@@ -19,9 +19,10 @@ namespace lpgnn {
 namespace {
 
 constexpr int kSortThreads = 256;
-constexpr int kSortRounds = 16;
-constexpr int kSortTile = kSortThreads * kSortRounds;  // items per block
-constexpr int kRadix = 256;
+constexpr int kSortRounds = 8;                          // items per thread, held in registers
+constexpr int kSortTile = kSortThreads * kSortRounds;   // items per block
+constexpr int kMaxRadixBits = 9;
+constexpr int kMaxRadix = 1 << kMaxRadixBits;
 
 __global__ void iota_kernel(uint32_t* out, int64_t n) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -39,26 +40,65 @@ __global__ void gather_u32_kernel(const uint32_t* __restrict__ src, const uint32
   if (i < n) out[i] = src[idx[i]];
 }
 
-__global__ void gather_f32_kernel(const float* __restrict__ src, const uint32_t* __restrict__ idx,
-                                  float* __restrict__ out, int64_t n) {
+// CSR payload gather: col[e] = coo_col[perm[e]], val[e] = coo_val[perm[e]]
+__global__ void gather_entry_kernel(const uint32_t* __restrict__ col_src, const float* __restrict__ val_src,
+                                    const uint32_t* __restrict__ perm, uint32_t* __restrict__ col_out,
+                                    float* __restrict__ val_out, int64_t n) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n) out[i] = src[idx[i]];
+  if (i < n) { const uint32_t p = perm[i]; col_out[i] = col_src[p]; val_out[i] = val_src[p]; }
+}
+
+// CSC payload: csr2csc[k] = perm[k], row_csc[k] = rows[perm[k]], val_csc[k] = val[perm[k]]
+__global__ void gather_csc_kernel(const uint32_t* __restrict__ rows, const float* __restrict__ val,
+                                  const uint32_t* __restrict__ perm, uint32_t* __restrict__ csr2csc,
+                                  uint32_t* __restrict__ row_csc, float* __restrict__ val_csc, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) { const uint32_t p = perm[i]; csr2csc[i] = p; row_csc[i] = rows[p]; val_csc[i] = val[p]; }
+}
+
+// keys[i] = key_src[i], vals[i] = i   (start of a sort)
+__global__ void init_pairs_kernel(const uint32_t* __restrict__ key_src, uint32_t* __restrict__ keys,
+                                  uint32_t* __restrict__ vals, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) { keys[i] = key_src[i]; vals[i] = (uint32_t)i; }
+}
+
+// flag[0] |= 1 if the COO is NOT sorted by (row, col) (strictly non-decreasing linear index)
+__global__ void check_sorted_kernel(const uint32_t* __restrict__ row, const uint32_t* __restrict__ col, int64_t n,
+                                    uint32_t* __restrict__ flag) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i + 1 < n) {
+    const uint32_t r0 = row[i], r1 = row[i + 1];
+    if (r1 < r0 || (r1 == r0 && col[i + 1] < col[i])) atomicOr(flag, 1u);
+  }
+}
+__global__ void expand_check_range_kernel(const uint32_t* __restrict__ row, const uint32_t* __restrict__ col, int64_t n,
+                                          uint32_t m, uint32_t ncols, uint32_t* __restrict__ flag) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && (row[i] >= m || col[i] >= ncols)) atomicOr(flag, 2u);
 }
 
 __global__ void __launch_bounds__(kSortThreads)
-radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, uint32_t* __restrict__ counts,
-                  int nblocks) {
-  __shared__ uint32_t h[kRadix];
-  h[threadIdx.x] = 0;
+radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int radix_bits,
+                  uint32_t* __restrict__ counts, int nblocks) {
+  __shared__ uint32_t h[kMaxRadix];
+  const int radix = 1 << radix_bits;
+  for (int d = threadIdx.x; d < radix; d += kSortThreads) h[d] = 0;
   __syncthreads();
-  int64_t base = (int64_t)blockIdx.x * kSortTile;
-#pragma unroll 4
+  const int64_t base = (int64_t)blockIdx.x * kSortTile;
+  uint32_t k[kSortRounds];
+#pragma unroll
   for (int r = 0; r < kSortRounds; ++r) {
-    int64_t i = base + r * kSortThreads + threadIdx.x;
-    if (i < n) atomicAdd(&h[(keys[i] >> shift) & (kRadix - 1)], 1u);  // integer counts: order-free
+    const int64_t i = base + r * kSortThreads + threadIdx.x;
+    k[r] = (i < n) ? keys[i] : 0xffffffffu;
+  }
+#pragma unroll
+  for (int r = 0; r < kSortRounds; ++r) {
+    const int64_t i = base + r * kSortThreads + threadIdx.x;
+    if (i < n) atomicAdd(&h[(k[r] >> shift) & (radix - 1)], 1u);  // integer counts: order-free
   }
   __syncthreads();
-  counts[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+  for (int d = threadIdx.x; d < radix; d += kSortThreads) counts[(size_t)d * nblocks + blockIdx.x] = h[d];
 }
 
 // exclusive scan of `counts` (length len) in place; single block.
@@ -86,46 +126,62 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* __restrict__ count
   }
 }
 
+// Stable scatter.  Warp w owns the contiguous slice [base + w*256, base + (w+1)*256) of the tile and
+// walks it in 8 rounds of 32 consecutive items, keeping a private per-digit counter row in shared
+// memory: the rank of an item inside its digit = (items of that digit in earlier rounds of the warp)
+// + (match-any rank inside the round).  One block-wide exclusive prefix over the 8 warp rows then
+// gives every item its global slot.  No atomics on ordered data -> deterministic and stable.
 __global__ void __launch_bounds__(kSortThreads)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
-                     const uint32_t* __restrict__ offsets, int nblocks) {
+                     int radix_bits, const uint32_t* __restrict__ offsets, int nblocks) {
   constexpr int kWarps = kSortThreads / 32;
-  __shared__ uint32_t goff[kRadix];          // global start of (digit, this block)
-  __shared__ uint32_t run[kRadix];           // items of this digit already placed by earlier rounds
-  __shared__ uint32_t wcnt[kWarps][kRadix];  // per-warp digit counts of the current round
+  __shared__ uint32_t goff[kMaxRadix];          // global start of (digit, this block)
+  __shared__ uint32_t wcnt[kWarps][kMaxRadix];  // per-warp digit counters -> exclusive prefix over warps
+  const int radix = 1 << radix_bits;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  goff[t] = offsets[(size_t)t * nblocks + blockIdx.x];
-  run[t] = 0;
+  for (int d = t; d < radix; d += kSortThreads) {
+    goff[d] = offsets[(size_t)d * nblocks + blockIdx.x];
 #pragma unroll
-  for (int w = 0; w < kWarps; ++w) wcnt[w][t] = 0;
-  __syncthreads();
-  const int64_t base = (int64_t)blockIdx.x * kSortTile;
+    for (int w = 0; w < kWarps; ++w) wcnt[w][d] = 0;
+  }
+  const int64_t base = (int64_t)blockIdx.x * kSortTile + warp * (32 * kSortRounds);
+  uint32_t key[kSortRounds], val[kSortRounds], rank[kSortRounds];
+#pragma unroll
   for (int r = 0; r < kSortRounds; ++r) {
-    const int64_t i = base + r * kSortThreads + t;
-    const bool valid = i < n;
-    uint32_t key = 0, val = 0;
-    if (valid) { key = keys_in[i]; val = vals_in[i]; }
-    const uint32_t digit = valid ? ((key >> shift) & (kRadix - 1)) : kRadix;  // invalid lanes: own class
-    const uint32_t peers = __match_any_sync(0xffffffffu, digit);
-    const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1));
-    if (valid && rank_in_warp == 0) wcnt[warp][digit] = __popc(peers);
-    __syncthreads();
-    uint32_t pos = 0;
-    if (valid) {
-      uint32_t before = run[digit];
-      for (int w = 0; w < warp; ++w) before += wcnt[w][digit];
-      pos = goff[digit] + before + rank_in_warp;
-    }
-    __syncthreads();
-    {
-      uint32_t s = 0;
+    const int64_t i = base + r * 32 + lane;
+    key[r] = 0; val[r] = 0;
+    if (i < n) { key[r] = keys_in[i]; val[r] = vals_in[i]; }
+  }
+  __syncthreads();
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) { s += wcnt[w][t]; wcnt[w][t] = 0; }
-      run[t] += s;
+  for (int r = 0; r < kSortRounds; ++r) {
+    const bool valid = base + r * 32 + lane < n;
+    const uint32_t digit = valid ? ((key[r] >> shift) & (radix - 1)) : (uint32_t)radix;  // invalid lanes: own class
+    const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+    const uint32_t in_round = __popc(peers & ((1u << lane) - 1));
+    uint32_t before = 0;
+    if (valid) before = wcnt[warp][digit];
+    __syncwarp();
+    if (valid && in_round == 0) wcnt[warp][digit] = before + __popc(peers);
+    __syncwarp();
+    rank[r] = before + in_round;
+  }
+  __syncthreads();
+  for (int d = t; d < radix; d += kSortThreads) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) { const uint32_t c = wcnt[w][d]; wcnt[w][d] = acc; acc += c; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kSortRounds; ++r) {
+    if (base + r * 32 + lane < n) {
+      const uint32_t digit = (key[r] >> shift) & (radix - 1);
+      const uint32_t pos = goff[digit] + wcnt[warp][digit] + rank[r];
+      keys_out[pos] = key[r];
+      vals_out[pos] = val[r];
     }
-    __syncthreads();
-    if (valid) { keys_out[pos] = key; vals_out[pos] = val; }
   }
 }
 
@@ -153,12 +209,15 @@ struct SortBufs {
 // Sorts (k[0], v[0]) by key bits [0, bits); returns the index (0/1) of the buffer holding the result.
 int radix_sort(SortBufs& b, int64_t n, int bits, cudaStream_t st) {
   const int nblocks = ceil_div(n, kSortTile);
+  const int passes = (bits + kMaxRadixBits - 1) / kMaxRadixBits;
+  const int digit_bits = (bits + passes - 1) / passes;  // <= 9
   int cur = 0;
-  for (int shift = 0; shift < bits; shift += 8) {
-    radix_hist_kernel<<<nblocks, kSortThreads, 0, st>>>(b.k[cur], n, shift, b.counts, nblocks);
-    scan_kernel<<<1, 1024, 0, st>>>(b.counts, (int64_t)kRadix * nblocks);
+  for (int p = 0; p < passes; ++p) {
+    const int shift = p * digit_bits;
+    radix_hist_kernel<<<nblocks, kSortThreads, 0, st>>>(b.k[cur], n, shift, digit_bits, b.counts, nblocks);
+    scan_kernel<<<1, 1024, 0, st>>>(b.counts, (int64_t)(1 << digit_bits) * nblocks);
     radix_scatter_kernel<<<nblocks, kSortThreads, 0, st>>>(b.k[cur], b.v[cur], b.k[cur ^ 1], b.v[cur ^ 1], n,
-                                                           shift, b.counts, nblocks);
+                                                           shift, digit_bits, b.counts, nblocks);
     cur ^= 1;
     count_launches(3);
   }
@@ -175,14 +234,14 @@ extern "C" size_t lpgnn_graph_build_workspace_bytes(int64_t nnz, int32_t m, int3
   const size_t z = (size_t)(nnz > 0 ? nnz : 1);
   const size_t words = align_up(z, 64);
   const size_t nblocks = (z + kSortTile - 1) / kSortTile;
-  // k0,k1,v0,v1,r32,c32,rows_sorted + counts
-  return (7 * words + align_up(kRadix * nblocks, 64)) * sizeof(uint32_t) + 256;
+  // k0,k1,v0,v1,r32,c32,rows_sorted + counts + flag word
+  return (7 * words + align_up(kMaxRadix * nblocks, 64) + 64) * sizeof(uint32_t) + 256;
 }
 
 extern "C" int lpgnn_graph_build(const void* coo_row, const void* coo_col, int idx_is_i64, const float* coo_val,
-                                 int64_t nnz, int32_t m, int32_t n, int32_t* rowptr, int32_t* col, float* val,
-                                 int32_t* colptr, int32_t* row_csc, float* val_csc, int32_t* csr2csc,
-                                 void* workspace, size_t workspace_bytes, lpgnn_stream_t stream) {
+                                 int64_t nnz, int32_t m, int32_t n, int flags, int32_t* rowptr, int32_t* col,
+                                 float* val, int32_t* colptr, int32_t* row_csc, float* val_csc, int32_t* csr2csc,
+                                 int32_t* status, void* workspace, size_t workspace_bytes, lpgnn_stream_t stream) {
   if (int rc = check_device()) return rc;
   LPGNN_REQUIRE(m >= 0 && n >= 0 && nnz >= 0, "graph_build: negative size");
   LPGNN_REQUIRE(nnz < ((int64_t)1 << 31), "graph_build: nnz must be < 2^31");
@@ -193,6 +252,7 @@ extern "C" int lpgnn_graph_build(const void* coo_row, const void* coo_col, int i
     return LPGNN_EWORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (status) LPGNN_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
   if (nnz == 0) {
     LPGNN_CUDA_OK(cudaMemsetAsync(rowptr, 0, sizeof(int32_t) * ((size_t)m + 1), st));
     LPGNN_CUDA_OK(cudaMemsetAsync(colptr, 0, sizeof(int32_t) * ((size_t)n + 1), st));
@@ -210,37 +270,57 @@ extern "C" int lpgnn_graph_build(const void* coo_row, const void* coo_col, int i
   uint32_t* rows_sorted = w + 6 * words;
   b.counts = w + 7 * words;
   const int tb = 256, gb = ceil_div(z, tb);
+  int launches = 0;
 
   const uint32_t *rsrc, *csrc;
   if (idx_is_i64) {
     narrow_i64_kernel<<<gb, tb, 0, st>>>(reinterpret_cast<const int64_t*>(coo_row), r32, z);
     narrow_i64_kernel<<<gb, tb, 0, st>>>(reinterpret_cast<const int64_t*>(coo_col), c32, z);
     rsrc = r32; csrc = c32;
+    launches += 2;
   } else {
     rsrc = reinterpret_cast<const uint32_t*>(coo_row);
     csrc = reinterpret_cast<const uint32_t*>(coo_col);
   }
-  // ---- CSR: LSD over (row, col): column digits first, then row digits
-  LPGNN_CUDA_OK(cudaMemcpyAsync(b.k[0], csrc, sizeof(uint32_t) * z, cudaMemcpyDeviceToDevice, st));
-  iota_kernel<<<gb, tb, 0, st>>>(b.v[0], z);
-  int cur = radix_sort(b, z, bits_for(n), st);
-  if (cur != 0) std::swap(b.k[0], b.k[1]), std::swap(b.v[0], b.v[1]);
-  gather_u32_kernel<<<gb, tb, 0, st>>>(rsrc, b.v[0], b.k[0], z);  // keys := row of each (col-sorted) entry
-  cur = radix_sort(b, z, bits_for(m), st);
-  // b.k[cur] = rows of the CSR entries (sorted), b.v[cur] = original COO index of each CSR entry
-  LPGNN_CUDA_OK(cudaMemcpyAsync(rows_sorted, b.k[cur], sizeof(uint32_t) * z, cudaMemcpyDeviceToDevice, st));
-  gather_u32_kernel<<<gb, tb, 0, st>>>(csrc, b.v[cur], reinterpret_cast<uint32_t*>(col), z);
-  gather_f32_kernel<<<gb, tb, 0, st>>>(coo_val, b.v[cur], val, z);
-  fill_ptr_kernel<<<ceil_div(z + 1, tb), tb, 0, st>>>(rows_sorted, z, m, rowptr);
+  uint32_t* u_col = reinterpret_cast<uint32_t*>(col);
+  const uint32_t* csr_rows;  // row of every CSR entry
+  if (flags & LPGNN_COO_SORTED) {
+    // Caller asserts row-major order (what the reference's pipeline produces, dataset.py:251-252):
+    // the CSR arrays are the input; the claim is verified on the device and reported in *status.
+    if (status) {
+      check_sorted_kernel<<<gb, tb, 0, st>>>(rsrc, csrc, z, reinterpret_cast<uint32_t*>(status));
+      ++launches;
+    }
+    LPGNN_CUDA_OK(cudaMemcpyAsync(col, csrc, sizeof(uint32_t) * z, cudaMemcpyDeviceToDevice, st));
+    LPGNN_CUDA_OK(cudaMemcpyAsync(val, coo_val, sizeof(float) * z, cudaMemcpyDeviceToDevice, st));
+    csr_rows = rsrc;
+  } else {
+    // ---- CSR: LSD over (row, col): column digits first, then row digits
+    init_pairs_kernel<<<gb, tb, 0, st>>>(csrc, b.k[0], b.v[0], z);
+    int cur = radix_sort(b, z, bits_for(n), st);
+    if (cur != 0) std::swap(b.k[0], b.k[1]), std::swap(b.v[0], b.v[1]);
+    gather_u32_kernel<<<gb, tb, 0, st>>>(rsrc, b.v[0], b.k[0], z);  // keys := row of each (col-sorted) entry
+    cur = radix_sort(b, z, bits_for(m), st);
+    // b.k[cur] = rows of the CSR entries (sorted), b.v[cur] = original COO index of each CSR entry
+    LPGNN_CUDA_OK(cudaMemcpyAsync(rows_sorted, b.k[cur], sizeof(uint32_t) * z, cudaMemcpyDeviceToDevice, st));
+    gather_entry_kernel<<<gb, tb, 0, st>>>(csrc, coo_val, b.v[cur], u_col, val, z);
+    csr_rows = rows_sorted;
+    launches += 3;
+  }
+  if (status) {
+    expand_check_range_kernel<<<gb, tb, 0, st>>>(rsrc, csrc, z, (uint32_t)m, (uint32_t)n,
+                                                 reinterpret_cast<uint32_t*>(status));
+    ++launches;
+  }
+  fill_ptr_kernel<<<ceil_div(z + 1, tb), tb, 0, st>>>(csr_rows, z, m, rowptr);
   // ---- CSC view: stable sort of CSR entries by column
-  LPGNN_CUDA_OK(cudaMemcpyAsync(b.k[0], col, sizeof(uint32_t) * z, cudaMemcpyDeviceToDevice, st));
-  iota_kernel<<<gb, tb, 0, st>>>(b.v[0], z);
-  cur = radix_sort(b, z, bits_for(n), st);
-  LPGNN_CUDA_OK(cudaMemcpyAsync(csr2csc, b.v[cur], sizeof(uint32_t) * z, cudaMemcpyDeviceToDevice, st));
-  gather_u32_kernel<<<gb, tb, 0, st>>>(rows_sorted, b.v[cur], reinterpret_cast<uint32_t*>(row_csc), z);
-  gather_f32_kernel<<<gb, tb, 0, st>>>(val, b.v[cur], val_csc, z);
+  init_pairs_kernel<<<gb, tb, 0, st>>>(u_col, b.k[0], b.v[0], z);
+  const int cur = radix_sort(b, z, bits_for(n), st);
+  gather_csc_kernel<<<gb, tb, 0, st>>>(csr_rows, val, b.v[cur], reinterpret_cast<uint32_t*>(csr2csc),
+                                       reinterpret_cast<uint32_t*>(row_csc), val_csc, z);
   fill_ptr_kernel<<<ceil_div(z + 1, tb), tb, 0, st>>>(b.k[cur], z, n, colptr);
+  launches += 4;
   LPGNN_LAUNCH_OK();
-  count_launches(idx_is_i64 ? 12 : 10);  // + 3 per radix pass, counted in radix_sort
+  count_launches(launches);
   return LPGNN_OK;
 }

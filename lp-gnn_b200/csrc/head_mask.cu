@@ -12,6 +12,19 @@ namespace lpgnn {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kRegThreads = 128;  // register-resident variant: smaller blocks for register-file granularity
+
+__device__ __forceinline__ void finish_row_tags(float r0, float r1, float r2, float tag_lo, float tag_up, int64_t row,
+                                                float* __restrict__ logits) {
+  const float nrm = sqrtf(r0 * r0 + r1 * r1 + r2 * r2);
+  const float den = fmaxf(nrm, 1e-12f);
+  float y0 = (r0 / den) * 10.f, y1 = (r1 / den) * 10.f, y2 = (r2 / den) * 10.f;
+  if (tag_lo != 0.f) y0 -= 10.f;
+  if (tag_up != 0.f) y2 -= 10.f;
+  logits[row * 3 + 0] = y0;
+  logits[row * 3 + 1] = y1;
+  logits[row * 3 + 2] = y2;
+}
 
 __device__ __forceinline__ void finish_row(float r0, float r1, float r2, const float* __restrict__ feas, int q,
                                            int64_t row, float* __restrict__ logits) {
@@ -74,6 +87,81 @@ head_mask_kernel(const T* __restrict__ H, int32_t rows, int32_t Hdim, const floa
   }
 }
 
+// Fast path: the three weight rows live in REGISTERS (lane l owns 16-byte chunks l, l+32, ...), so the
+// inner loop is one 128-bit load per chunk plus FMAs -- no shared-memory traffic (the shared-memory
+// version above is bank-conflict bound: every lane reads a different 32-byte slice of the weights).
+template <typename T, int CH>
+__global__ void __launch_bounds__(kRegThreads)
+head_mask_reg_kernel(const T* __restrict__ H, int32_t rows, int32_t Hdim, const float* __restrict__ W,
+                     const float* __restrict__ b, const float* __restrict__ feas, int q, float* __restrict__ logits,
+                     float* __restrict__ raw_out) {
+  constexpr int E = 16 / sizeof(T);
+  const int lane = threadIdx.x & 31;
+  const int chunks = Hdim / E;
+  float w[3][CH][E];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int ch = lane + 32 * c;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int k = 0; k < E; ++k) w[j][c][k] = (ch < chunks) ? __ldg(W + (int64_t)j * Hdim + ch * E + k) : 0.f;
+  }
+  const float b0 = __ldg(b), b1 = __ldg(b + 1), b2 = __ldg(b + 2);
+  const int warps_total = gridDim.x * (kRegThreads / 32);
+  for (int64_t row = blockIdx.x * (kRegThreads / 32) + (threadIdx.x >> 5); row < rows; row += warps_total) {
+    const uint4* hrow = reinterpret_cast<const uint4*>(H + row * Hdim);
+    uint4 v[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int ch = lane + 32 * c;
+      v[c] = (ch < chunks) ? __ldg(hrow + ch) : make_uint4(0, 0, 0, 0);
+    }
+    // the two mask tags are fetched by lanes 0/1 alongside the row, not after the reduction
+    float tag = 0.f;
+    if (lane == 0) tag = __ldg(feas + row * q + (q - 3));
+    if (lane == 1) tag = __ldg(feas + row * q + (q - 1));
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      float x[E];
+      if constexpr (sizeof(T) == 4) {
+        x[0] = __uint_as_float(v[c].x); x[1] = __uint_as_float(v[c].y);
+        x[2] = __uint_as_float(v[c].z); x[3] = __uint_as_float(v[c].w);
+      } else {
+        x[0] = bf16_lo(v[c].x); x[1] = bf16_hi(v[c].x); x[2] = bf16_lo(v[c].y); x[3] = bf16_hi(v[c].y);
+        x[4] = bf16_lo(v[c].z); x[5] = bf16_hi(v[c].z); x[6] = bf16_lo(v[c].w); x[7] = bf16_hi(v[c].w);
+      }
+#pragma unroll
+      for (int k = 0; k < E; ++k) {
+        a0 = fmaf(x[k], w[0][c][k], a0);
+        a1 = fmaf(x[k], w[1][c][k], a1);
+        a2 = fmaf(x[k], w[2][c][k], a2);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+    }
+    const float tag_up = __shfl_sync(0xffffffffu, tag, 1);
+    if (lane == 0) {
+      a0 += b0; a1 += b1; a2 += b2;
+      if (raw_out) { raw_out[row * 3] = a0; raw_out[row * 3 + 1] = a1; raw_out[row * 3 + 2] = a2; }
+      finish_row_tags(a0, a1, a2, tag, tag_up, row, logits);
+    }
+  }
+}
+
+template <typename T, int CH>
+void launch_reg(const void* H, int32_t rows, int32_t Hdim, const float* W, const float* b, const float* feas, int q,
+                float* logits, float* raw_out, cudaStream_t st) {
+  const int grid = min(ceil_div(rows, kRegThreads / 32), sm_count() * 16);
+  head_mask_reg_kernel<T, CH><<<grid, kRegThreads, 0, st>>>(reinterpret_cast<const T*>(H), rows, Hdim, W, b, feas, q,
+                                                         logits, raw_out);
+}
+
 __global__ void add_knowledge_kernel(const float* __restrict__ in, int32_t rows, const float* __restrict__ feas,
                                      int q, float* __restrict__ out) {
   const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -97,17 +185,28 @@ extern "C" int lpgnn_head_mask(const void* H, int h_dtype, int32_t rows, int32_t
   LPGNN_REQUIRE((Hdim * esz) % 16 == 0 && (uintptr_t)H % 16 == 0, "head_mask: H rows must be 16-byte multiples/aligned");
   LPGNN_REQUIRE(3 * Hdim * 4 <= 96 * 1024, "head_mask: Hdim=%d too large for the shared-memory weight stage", Hdim);
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = min(ceil_div(rows, kThreads / 32), sm_count() * 8);
-  const size_t smem = (size_t)3 * Hdim * sizeof(float);
-  if (h_dtype == LPGNN_F32) {
-    LPGNN_CUDA_OK(cudaFuncSetAttribute(head_mask_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    head_mask_kernel<float><<<grid, kThreads, smem, st>>>(reinterpret_cast<const float*>(H), rows, Hdim, W, b, feas, q,
-                                                          logits, raw_out);
+  const int chunks = Hdim * esz / 16;
+  const int ch = (chunks + 31) / 32;
+  const bool f32 = h_dtype == LPGNN_F32;
+  if (ch <= 8) {
+#define LPGNN_HEAD(CHV)                                                                                   \
+  (f32 ? launch_reg<float, CHV>(H, rows, Hdim, W, b, feas, q, logits, raw_out, st)                        \
+       : launch_reg<__nv_bfloat16, CHV>(H, rows, Hdim, W, b, feas, q, logits, raw_out, st))
+    if (ch <= 1) LPGNN_HEAD(1); else if (ch <= 2) LPGNN_HEAD(2); else if (ch <= 4) LPGNN_HEAD(4); else LPGNN_HEAD(8);
+#undef LPGNN_HEAD
   } else {
-    LPGNN_CUDA_OK(cudaFuncSetAttribute(head_mask_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       96 * 1024));
-    head_mask_kernel<__nv_bfloat16><<<grid, kThreads, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(H), rows, Hdim,
-                                                                  W, b, feas, q, logits, raw_out);
+    const int grid = min(ceil_div(rows, kThreads / 32), sm_count() * 8);
+    const size_t smem = (size_t)3 * Hdim * sizeof(float);
+    if (f32) {
+      LPGNN_CUDA_OK(cudaFuncSetAttribute(head_mask_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      head_mask_kernel<float><<<grid, kThreads, smem, st>>>(reinterpret_cast<const float*>(H), rows, Hdim, W, b, feas,
+                                                            q, logits, raw_out);
+    } else {
+      LPGNN_CUDA_OK(cudaFuncSetAttribute(head_mask_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         96 * 1024));
+      head_mask_kernel<__nv_bfloat16><<<grid, kThreads, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(H), rows,
+                                                                    Hdim, W, b, feas, q, logits, raw_out);
+    }
   }
   LPGNN_LAUNCH_OK();
   count_launches(1);

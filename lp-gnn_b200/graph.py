@@ -48,6 +48,8 @@ class BipartiteCSR:
         self.rowptr = self.col = self.val = None
         self.colptr = self.row_csc = self.val_csc = self.csr2csc = None
         self._transposed = False    # True: this object presents A^T (shares buffers with its parent)
+        self._sorted_hint = False   # caller's is_sorted=True: skip the COO sort (verified on the device)
+        self._status = None         # device int32: bit0 = sorted claim false, bit1 = index out of range
         self.storage = _StorageView(self)
 
     # ------------------------------------------------------------------ construction
@@ -57,26 +59,33 @@ class BipartiteCSR:
         ``edge_index`` [2,z] integer (any order), ``edge_attr`` [z] float (default: ones)."""
         if sparse_sizes is None:
             raise ValueError("sparse_sizes=(m, n) is required")
+        return cls.from_coo(edge_index[0], edge_index[1], edge_attr, int(sparse_sizes[0]), int(sparse_sizes[1]),
+                            is_sorted=is_sorted)
+
+    @classmethod
+    def from_coo(cls, row, col, val, m, n, is_sorted=False):
+        """COO given as separate tensors (host or device, any integer dtype).  Device inputs are built
+        immediately on the current stream; host inputs are kept until ``.to(cuda)``."""
         g = cls()
-        g.m, g.n = int(sparse_sizes[0]), int(sparse_sizes[1])
-        row, col = edge_index[0], edge_index[1]
-        if edge_attr is None:
-            edge_attr = torch.ones(row.shape[0], dtype=torch.float32, device=row.device)
-        # range check only for host inputs (a device-side check would force a stream sync in the hot loop)
+        g.m, g.n = int(m), int(n)
+        if val is None:
+            val = torch.ones(row.shape[0], dtype=torch.float32, device=row.device)
+        # range check only for host inputs (a device-side check would force a stream sync in the hot loop;
+        # the build kernel reports out-of-range indices in its status word, see check())
         if not row.is_cuda and row.numel() and (
                 int(row.max()) >= g.m or int(col.max()) >= g.n or int(row.min()) < 0 or int(col.min()) < 0):
             raise ValueError("edge_index out of range for sparse_sizes")
         g._coo = (row.to(torch.int32).contiguous(), col.to(torch.int32).contiguous(),
-                  edge_attr.to(torch.float32).contiguous())
+                  val.to(torch.float32).contiguous())
+        g._sorted_hint = bool(is_sorted)
         if row.is_cuda:
             g._build()
         return g
 
     @classmethod
-    def from_coo_arrays(cls, row, col, val, m, n, device):
+    def from_coo_arrays(cls, row, col, val, m, n, device, is_sorted=False):
         """numpy / tensor COO -> built graph on ``device`` (one H2D copy per array)."""
-        ei = torch.stack([torch.as_tensor(row), torch.as_tensor(col)])
-        g = cls.from_edge_index(ei, torch.as_tensor(val), (m, n))
+        g = cls.from_coo(torch.as_tensor(row), torch.as_tensor(col), torch.as_tensor(val), m, n, is_sorted=is_sorted)
         return g.to(device)
 
     def _build(self):
@@ -92,17 +101,31 @@ class BipartiteCSR:
         self.csr2csc = torch.empty(z, **i32)
         self.val = torch.empty(z, dtype=torch.float32, device=dev)
         self.val_csc = torch.empty(z, dtype=torch.float32, device=dev)
+        self._status = torch.empty(1, **i32)
         ws_bytes = lib.lpgnn_graph_build_workspace_bytes(z, self.m, self.n)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             rc = lib.lpgnn_graph_build(row.data_ptr(), col.data_ptr(), 0, val.data_ptr(), z, self.m, self.n,
+                                       _lib.COO_SORTED if self._sorted_hint else 0,
                                        self.rowptr.data_ptr(), self.col.data_ptr(), self.val.data_ptr(),
                                        self.colptr.data_ptr(), self.row_csc.data_ptr(), self.val_csc.data_ptr(),
-                                       self.csr2csc.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr())
+                                       self.csr2csc.data_ptr(), self._status.data_ptr(), ws.data_ptr(), ws_bytes,
+                                       _lib.stream_ptr())
         _lib.check(rc, "lpgnn_graph_build")
         # the caching allocator keeps `ws` / the COO alive until the stream has consumed them
         ws.record_stream(torch.cuda.current_stream(dev))
         self._coo = None
+
+    def check(self):
+        """Synchronising validation of the device-side build status: raises if an ``is_sorted=True`` claim
+        was false or an index was out of range.  (The hot loop never calls this; tests and loaders do.)"""
+        self._require_built()
+        st = int(self._status.item())
+        if st & 1:
+            raise ValueError("BipartiteCSR: is_sorted=True was passed but the COO is not in (row, col) order")
+        if st & 2:
+            raise ValueError("BipartiteCSR: edge index out of range for sparse_sizes")
+        return self
 
     def _require_built(self):
         if self.rowptr is None:

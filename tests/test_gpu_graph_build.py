@@ -101,3 +101,43 @@ def test_full_size_properties_c4_shape(cuda):
     chk_in = (torch.from_numpy(row).to(cuda) * 1_000_003 + torch.from_numpy(col).to(cuda) * 7919 + bits).sum()
     chk_out = (r * 1_000_003 + c * 7919 + g.val.view(torch.int32).long()).sum()
     assert int(chk_in) == int(chk_out)
+
+
+def test_build_sorted_hint_matches_and_is_verified(cuda):
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200.graph import BipartiteCSR
+    m, n = 3000, 7000
+    row, col, val = make_graph_arrays(m, n, 30_000, 12, sort=True)
+    g = BipartiteCSR.from_coo_arrays(row, col, val, m, n, cuda, is_sorted=True).check()
+    _assert_equal(g, port.graph_from_coo(row, col, val, m, n))
+    # a false claim is detected on the device and reported by check()
+    perm = np.random.default_rng(0).permutation(row.shape[0])
+    bad = BipartiteCSR.from_coo_arrays(row[perm], col[perm], val[perm], m, n, cuda, is_sorted=True)
+    with pytest.raises(ValueError, match="not in"):
+        bad.check()
+    # out-of-range indices given on the device are reported too
+    r = torch.tensor([0, 1, m], dtype=torch.int32, device=cuda)
+    c = torch.tensor([0, 1, 2], dtype=torch.int32, device=cuda)
+    with pytest.raises(ValueError, match="out of range"):
+        BipartiteCSR.from_coo(r, c, torch.ones(3, device=cuda), m, n).check()
+
+
+def test_sparse_tensor_api_subset(cuda):
+    """The SparseTensor methods the reference calls on batch.edge_index."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200.graph import BipartiteCSR
+    m, n = 40, 70
+    row, col, val = make_graph_arrays(m, n, 500, 13)
+    g = BipartiteCSR.from_coo_arrays(row, col, val, m, n, cuda)
+    dense = np.zeros((m, n), dtype=np.float64)
+    dense[row, col] = val
+    assert g.nnz() == row.shape[0] and g.sparse_sizes() == (m, n) and g.t().sparse_sizes() == (n, m)
+    assert abs(g.density() - row.shape[0] / (m * n)) < 1e-12
+    np.testing.assert_allclose(g.sum(1).cpu().numpy(), dense.sum(1), atol=1e-5)
+    np.testing.assert_allclose(g.sum(0).cpu().numpy(), dense.sum(0), atol=1e-5)
+    ones = g.clone().set_value(torch.ones(g.nnz()), layout="coo")       # dataset.py:135-138
+    np.testing.assert_array_equal(ones.sum(0).cpu().numpy(), (dense != 0).sum(0))
+    np.testing.assert_array_equal(ones.sum(1).cpu().numpy(), (dense != 0).sum(1))
+    assert torch.equal(g.storage.value(), g.val) and torch.equal(g.t().storage.value(), g.val_csc)
+    r, c, v = g.t().coo()
+    np.testing.assert_array_equal(dense.T[r.cpu().numpy(), c.cpu().numpy()].astype(np.float32), v.cpu().numpy())
