@@ -109,13 +109,16 @@ LPGNN_API int lpgnn_spmm(const int32_t* ptr, const int32_t* idx, const float* va
  *   out[i,:] = epi( (sum_e val[e]*Xsrc[idx[e],:]) * W_rel^T + b_rel + Xdst[i,:] * W_root^T )
  *
  * Xsrc [n_src,k_src] f32, Xdst [rows,k_dst] f32, W_rel [N,k_src] f32, W_root [N,k_dst] f32,
- * b_rel [N] f32; k_src,k_dst <= 64; out [rows,N] of out_dtype.  If agg_out != NULL the fp32
- * aggregate [rows,k_src] is also written (needed by the weight gradient).
+ * b_rel [N] f32; k_src+k_dst <= 64; N even; out [rows,N] of out_dtype.  z_cat (required, f32
+ * [rows, KT], KT = lpgnn_conv_in_zcat_width(k_src,k_dst) in {16,32,64}) receives the concatenated
+ * transform input [aggregate | Xdst | 0-pad]: scratch for the forward pass, and exactly the operand
+ * the weight gradient of this layer needs (lpgnn_small_wgrad).
  * ------------------------------------------------------------------------------------------- */
+LPGNN_API int32_t lpgnn_conv_in_zcat_width(int32_t k_src, int32_t k_dst);
 LPGNN_API int lpgnn_conv_in_fused(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,
                         const float* Xsrc, int32_t k_src, const float* Xdst, int32_t k_dst,
                         const float* W_rel, const float* b_rel, const float* W_root, int32_t N,
-                        void* out, int out_dtype, int epilogue, float* agg_out,
+                        void* out, int out_dtype, int epilogue, float* z_cat,
                         lpgnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -127,14 +130,14 @@ LPGNN_API int lpgnn_conv_in_fused(const int32_t* ptr, const int32_t* idx, const 
  *   out[M,N] = epi( A1[M,K1] * W1[N,K1]^T + A2[M,K2] * W2[N,K2]^T + bias[N] )
  *
  * dtype LPGNN_BF16: tcgen05 tensor-core kernel (TMA-fed, TMEM accumulators, fp32 accumulate);
- * operands and out are bf16, bias f32; K1,K2 multiples of 64, N multiple of 64 (A2/W2 may be
- * NULL with K2 = 0).  dtype LPGNN_F32: fp32 CUDA-core kernel (the 1e-4 parity mode); operands,
+ * operands are bf16, out is bf16 or f32 (out_dtype; f32 is used by the weight-gradient GEMMs),
+ * bias f32; K1,K2 multiples of 64, N multiple of 64 (A2/W2 may be NULL with K2 = 0).  dtype LPGNN_F32: fp32 CUDA-core kernel (the 1e-4 parity mode); operands,
  * bias and out are f32 (K1,K2 multiples of 4).
  * ------------------------------------------------------------------------------------------- */
 LPGNN_API int lpgnn_node_transform(const void* A1, int32_t K1, const void* W1,
                          const void* A2, int32_t K2, const void* W2,
                          const float* bias, int32_t M, int32_t N,
-                         void* out, int dtype, int epilogue, lpgnn_stream_t stream);
+                         void* out, int dtype, int out_dtype, int epilogue, lpgnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a4+a5) Basis-status head + knowledge masking.  Replaces torch.nn.Linear(H,3) (reference
@@ -168,6 +171,52 @@ LPGNN_API size_t lpgnn_basis_select_workspace_bytes(int64_t total_nodes);
 LPGNN_API int lpgnn_basis_select(const float* logits_cons, int32_t m, const float* logits_vars, int32_t n,
                        int32_t k_basic, void* status, int status_is_i64, int32_t* counts_out,
                        void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
+
+/* =============================================================================================
+ * Backward pass (training step: reference train.py:121-129 calls loss.backward(), which runs the
+ * autograd formulas of PyG GraphConv / torch_sparse spmm_sum / F.normalize / relu_ / dropout).
+ * The data-gradient GEMMs are lpgnn_node_transform with transposed weights, the aggregation
+ * backward is lpgnn_spmm on the other orientation; the entry points below are the rest.
+ * ============================================================================================= */
+
+/* Backward of lpgnn_head_mask wrt the hidden activation (reference arch.py:186-191, 129-141), fused with
+ * the ReLU / inverted-dropout mask of that activation:
+ *   draw[i,:] = d(10*raw/max(|raw|,1e-12))^T dlogits[i,:]        (mask offsets are constants)
+ *   dH[i,:]   = (draw[i,:] * W) * scale * (Hact[i,:] > 0)
+ * dlogits, raw, draw [rows,3] f32; Hact, dH [rows,Hdim] of h_dtype; W [3,Hdim] f32.  draw (optional
+ * output) feeds the head's weight / bias gradients (lpgnn_small_wgrad, lpgnn_colsum). */
+LPGNN_API int lpgnn_head_mask_bwd(const float* dlogits, const float* raw, const void* Hact, int h_dtype,
+                        int32_t rows, int32_t Hdim, const float* W, float scale, void* dH, float* draw,
+                        lpgnn_stream_t stream);
+
+/* out = (a [+ b]) * scale * (act > 0), elementwise; b may be NULL; out may alias a.  Backward of
+ * relu_ (reference arch.py:182,188) and of dropout followed by relu_ (arch.py:186-188: `act` is the
+ * post-dropout activation, scale = 1/(1-p)); the optional b fuses the sum of the two gradient paths
+ * of a node feature (root path + aggregated path).  count multiple of 16 bytes / sizeof(elem). */
+LPGNN_API int lpgnn_relu_bwd(const void* a, const void* b, const void* act, int64_t count, int dtype,
+                   float scale, void* out, lpgnn_stream_t stream);
+
+/* In-place inverted dropout, x = keep ? x/(1-p) : 0 with keep drawn from a counter-based hash of
+ * (seed, element index) (reference arch.py:186-187 F.dropout; the RNG stream necessarily differs). */
+LPGNN_API int lpgnn_dropout(void* x, int64_t count, int dtype, float p, uint64_t seed, lpgnn_stream_t stream);
+
+/* out[N, ld_out] = X[M,N]^T with the columns [M, ld_out) zero-filled (ld_out >= M; the weight-gradient
+ * GEMM wants a reduction length that is a multiple of its K tile). */
+LPGNN_API int lpgnn_transpose(const void* X, int dtype, int64_t M, int64_t N, void* out, int64_t ld_out,
+                    lpgnn_stream_t stream);
+
+/* out[c] = sum_r X[r,c] (bias gradients), two-stage with a fixed summation order. */
+LPGNN_API size_t lpgnn_colsum_workspace_bytes(int64_t M, int32_t N);
+LPGNN_API int lpgnn_colsum(const void* X, int dtype, int64_t M, int32_t N, float* out,
+                 void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
+
+/* dW[N,K] = dY[M,N]^T * Z[M,K] for narrow Z (K <= 64; Z f32 with row stride ldz) and optionally
+ * dB[N] = column sums of dY: weight gradients of the input layer (Z = z_cat of lpgnn_conv_in_fused)
+ * and of the head (dY = hidden activation, Z = draw).  Two-stage, fixed order (deterministic). */
+LPGNN_API size_t lpgnn_small_wgrad_workspace_bytes(int64_t M, int32_t N, int32_t K);
+LPGNN_API int lpgnn_small_wgrad(const void* dY, int dtype, const float* Z, int32_t ldz, int32_t K,
+                      int64_t M, int32_t N, float* dW, float* dB,
+                      void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -30,10 +30,19 @@ SIGNATURES = {
     "lpgnn_graph_build_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "lpgnn_graph_build": (_int, [_p, _p, _int, _p, _i64, _i32, _i32, _int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "lpgnn_spmm": (_int, [_p, _p, _p, _i32, _p, _p, _i32, _int, _p]),
+    "lpgnn_conv_in_zcat_width": (_i32, [_i32, _i32]),
     "lpgnn_conv_in_fused": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p, _i32, _p, _int, _int, _p, _p]),
-    "lpgnn_node_transform": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _int, _p]),
+    "lpgnn_node_transform": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _int, _int, _p]),
     "lpgnn_head_mask": (_int, [_p, _int, _i32, _i32, _p, _p, _p, _i32, _p, _p, _p]),
     "lpgnn_add_knowledge": (_int, [_p, _i32, _p, _i32, _p, _p]),
+    "lpgnn_head_mask_bwd": (_int, [_p, _p, _p, _int, _i32, _i32, _p, C.c_float, _p, _p, _p]),
+    "lpgnn_relu_bwd": (_int, [_p, _p, _p, _i64, _int, C.c_float, _p, _p]),
+    "lpgnn_dropout": (_int, [_p, _i64, _int, C.c_float, C.c_uint64, _p]),
+    "lpgnn_transpose": (_int, [_p, _int, _i64, _i64, _p, _i64, _p]),
+    "lpgnn_colsum_workspace_bytes": (_sz, [_i64, _i32]),
+    "lpgnn_colsum": (_int, [_p, _int, _i64, _i32, _p, _p, _sz, _p]),
+    "lpgnn_small_wgrad_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "lpgnn_small_wgrad": (_int, [_p, _int, _p, _i32, _i32, _i64, _i32, _p, _p, _p, _sz, _p]),
     "lpgnn_basis_select_workspace_bytes": (_sz, [_i64]),
     "lpgnn_basis_select": (_int, [_p, _i32, _p, _i32, _i32, _p, _int, _p, _p, _sz, _p]),
 }

@@ -54,7 +54,7 @@ int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
 int node_transform_f32(const float* A1, int K1, const float* W1, const float* A2, int K2, const float* W2,
                        const float* bias, int M, int N, float* out, int relu, cudaStream_t st);
 int node_transform_bf16(const void* A1, int K1, const void* W1, const void* A2, int K2, const void* W2,
-                        const float* bias, int M, int N, void* out, int relu, cudaStream_t st);
+                        const float* bias, int M, int N, void* out, int out_f32, int relu, cudaStream_t st);
 
 }  // namespace lpgnn
 
@@ -74,10 +74,12 @@ extern "C" int lpgnn_device_info(int* sm, int* major, int* minor) {
 
 extern "C" int lpgnn_node_transform(const void* A1, int32_t K1, const void* W1, const void* A2, int32_t K2,
                                     const void* W2, const float* bias, int32_t M, int32_t N, void* out, int dtype,
-                                    int epilogue, lpgnn_stream_t stream) {
+                                    int out_dtype, int epilogue, lpgnn_stream_t stream) {
   if (int rc = check_device()) return rc;
   LPGNN_REQUIRE(M >= 0 && N > 0 && K1 > 0 && K2 >= 0, "node_transform: bad shape M=%d N=%d K1=%d K2=%d", M, N, K1, K2);
   LPGNN_REQUIRE(dtype == LPGNN_F32 || dtype == LPGNN_BF16, "node_transform: bad dtype %d", dtype);
+  LPGNN_REQUIRE(out_dtype == LPGNN_F32 || (out_dtype == LPGNN_BF16 && dtype == LPGNN_BF16),
+                "node_transform: out_dtype %d not available for operand dtype %d", out_dtype, dtype);
   if (M == 0) return LPGNN_OK;
   LPGNN_REQUIRE(A1 && W1 && out, "node_transform: null pointer");
   LPGNN_REQUIRE(K2 == 0 || (A2 && W2), "node_transform: K2=%d but A2/W2 is null", K2);
@@ -87,5 +89,5 @@ extern "C" int lpgnn_node_transform(const void* A1, int32_t K1, const void* W1, 
   if (dtype == LPGNN_F32)
     return node_transform_f32((const float*)A1, K1, (const float*)W1, (const float*)A2, K2, (const float*)W2, bias, M,
                               N, (float*)out, relu, st);
-  return node_transform_bf16(A1, K1, W1, A2, K2, W2, bias, M, N, out, relu, st);
+  return node_transform_bf16(A1, K1, W1, A2, K2, W2, bias, M, N, out, out_dtype == LPGNN_F32 ? 1 : 0, relu, st);
 }

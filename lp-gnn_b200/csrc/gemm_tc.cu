@@ -38,11 +38,11 @@ template <int BN> struct Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024 /*align slack*/;
 };
 
-template <int BN>
+template <int BN, typename OutT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2, int kblocks1,
-               int kblocks2, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int M, int N,
+               int kblocks2, const float* __restrict__ bias, OutT* __restrict__ out, int M, int N,
                int relu) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -143,26 +143,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       ptx::mbar_wait(&tmem_full[buf], use_phase);
       ptx::tc_fence_after();
       const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
-      __nv_bfloat16* orow = out + row * N + (int64_t)n_blk * BN;
+      OutT* orow = out + row * N + (int64_t)n_blk * BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         ptx::tmem_ld_32x32(taddr + c * 32, r);
         ptx::tmem_ld_wait();
-        uint32_t packed[16];
+        if constexpr (sizeof(OutT) == 2) {
+          uint32_t packed[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float v0 = __uint_as_float(r[2 * j]) + bias_s[c * 32 + 2 * j];
-          float v1 = __uint_as_float(r[2 * j + 1]) + bias_s[c * 32 + 2 * j + 1];
-          if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-          packed[j] = pack_bf16(v0, v1);
-        }
-        if (row < M) {
-          uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+          for (int j = 0; j < 16; ++j) {
+            float v0 = __uint_as_float(r[2 * j]) + bias_s[c * 32 + 2 * j];
+            float v1 = __uint_as_float(r[2 * j + 1]) + bias_s[c * 32 + 2 * j + 1];
+            if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            packed[j] = pack_bf16(v0, v1);
+          }
+          if (row < M) {
+            uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          }
+        } else {  // fp32 output (weight gradients)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = __uint_as_float(r[j]) + bias_s[c * 32 + j];
+            if (relu) v = fmaxf(v, 0.f);
+            r[j] = __float_as_uint(v);
+          }
+          if (row < M) {
+            uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          }
         }
       }
       ptx::tc_fence_before();
@@ -208,18 +222,20 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int bo
   return LPGNN_OK;
 }
 
-template <int BN>
+template <int BN, typename OutT>
 int launch(const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& a2, const CUtensorMap& w2, int kb1, int kb2,
-           const float* bias, __nv_bfloat16* out, int M, int N, int relu, cudaStream_t st) {
+           const float* bias, void* out, int M, int N, int relu, cudaStream_t st) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    LPGNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    LPGNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       C::kSmemBytes));
     attr_set = true;
   }
   const int tiles = ceil_div(M, BM) * (N / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu);
+  gemm_tc_kernel<BN, OutT><<<grid, kThreads, C::kSmemBytes, st>>>(a1, w1, a2, w2, kb1, kb2, bias,
+                                                                  reinterpret_cast<OutT*>(out), M, N, relu);
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;
@@ -228,7 +244,7 @@ int launch(const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& a2, 
 }  // namespace
 
 int node_transform_bf16(const void* A1, int K1, const void* W1, const void* A2, int K2, const void* W2,
-                        const float* bias, int M, int N, void* out, int relu, cudaStream_t st) {
+                        const float* bias, int M, int N, void* out, int out_f32, int relu, cudaStream_t st) {
   LPGNN_REQUIRE(K1 > 0 && K1 % BK == 0 && K2 % BK == 0, "node_transform(bf16): K1=%d, K2=%d must be multiples of 64", K1, K2);
   LPGNN_REQUIRE(N % 64 == 0, "node_transform(bf16): N=%d must be a multiple of 64", N);
   LPGNN_REQUIRE((uintptr_t)A1 % 16 == 0 && (uintptr_t)W1 % 16 == 0 && (uintptr_t)A2 % 16 == 0 &&
@@ -246,10 +262,14 @@ int node_transform_bf16(const void* A1, int K1, const void* W1, const void* A2, 
     a2 = a1; w2 = w1;
   }
   const int kb1 = K1 / BK, kb2 = two ? K2 / BK : 0;
-  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-  if (BN == 256) return launch<256>(a1, w1, a2, w2, kb1, kb2, bias, o, M, N, relu, st);
-  if (BN == 128) return launch<128>(a1, w1, a2, w2, kb1, kb2, bias, o, M, N, relu, st);
-  return launch<64>(a1, w1, a2, w2, kb1, kb2, bias, o, M, N, relu, st);
+  if (out_f32) {
+    if (BN == 256) return launch<256, float>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, st);
+    if (BN == 128) return launch<128, float>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, st);
+    return launch<64, float>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, st);
+  }
+  if (BN == 256) return launch<256, __nv_bfloat16>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, st);
+  if (BN == 128) return launch<128, __nv_bfloat16>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, st);
+  return launch<64, __nv_bfloat16>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, st);
 }
 
 }  // namespace lpgnn

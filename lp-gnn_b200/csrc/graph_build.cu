@@ -4,9 +4,9 @@
 // sorted by row*ncols+col) and SparseTensor.t() (reference arch.py:71: csr2csc =
 // argsort(col*nrows+row)).  All integer work; bit-exact with the reference ordering.
 //
-// Method: stable LSD radix sort (8-bit digits) of (key, payload) pairs, hand-written:
+// Method: stable LSD radix sort (up to 9-bit digits) of (key, payload) pairs, hand-written:
 //   histogram kernel  -> per-block digit counts, laid out digit-major
-//   scan kernel       -> exclusive scan over [256 x nblocks]  (global digit offsets per block)
+//   scan kernel       -> one block per digit: exclusive scan over the tile counts + digit total
 //   scatter kernel    -> stable scatter; the rank of an item inside its digit is computed
 //                        with warp match + an in-order cross-warp prefix, no atomics on
 //                        ordered data, so the result is deterministic.
@@ -56,6 +56,19 @@ __global__ void gather_csc_kernel(const uint32_t* __restrict__ rows, const float
   if (i < n) { const uint32_t p = perm[i]; csr2csc[i] = p; row_csc[i] = rows[p]; val_csc[i] = val[p]; }
 }
 
+// plain copies as kernels (a cudaMemcpyAsync D2D costs ~10x a small kernel on the launch path)
+__global__ void copy_entry_kernel(const uint32_t* __restrict__ col_src, const float* __restrict__ val_src,
+                                  uint32_t* __restrict__ col_out, float* __restrict__ val_out, int64_t n,
+                                  uint32_t* __restrict__ status) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) { col_out[i] = col_src[i]; val_out[i] = val_src[i]; }
+}
+__global__ void copy_u32_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+__global__ void reset_status_kernel(uint32_t* status) { *status = 0u; }
+
 // keys[i] = key_src[i], vals[i] = i   (start of a sort)
 __global__ void init_pairs_kernel(const uint32_t* __restrict__ key_src, uint32_t* __restrict__ keys,
                                   uint32_t* __restrict__ vals, int64_t n) {
@@ -101,29 +114,35 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int r
   for (int d = threadIdx.x; d < radix; d += kSortThreads) counts[(size_t)d * nblocks + blockIdx.x] = h[d];
 }
 
-// exclusive scan of `counts` (length len) in place; single block.
-__global__ void __launch_bounds__(1024) scan_kernel(uint32_t* __restrict__ counts, int64_t len) {
-  __shared__ uint32_t part[1024];
-  const int t = threadIdx.x;
-  const int64_t per = (len + 1023) / 1024;
-  const int64_t lo = t * per, hi = min(lo + per, len);
-  uint32_t s = 0;
-  for (int64_t i = lo; i < hi; ++i) s += counts[i];
-  part[t] = s;
+// One block per digit d: exclusive scan of counts[d][0..nblocks) in place (coalesced) and the digit's
+// total into totals[d].  The scatter kernel turns the totals into digit bases itself.
+__global__ void __launch_bounds__(kSortThreads)
+scan_digit_rows_kernel(uint32_t* __restrict__ counts, int nblocks, uint32_t* __restrict__ totals) {
+  __shared__ uint32_t warp_sum[kSortThreads / 32];
+  __shared__ uint32_t carry_s;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  uint32_t* row = counts + (size_t)blockIdx.x * nblocks;
+  if (t == 0) carry_s = 0;
   __syncthreads();
-  // Hillis-Steele inclusive scan over 1024 partials
-  for (int off = 1; off < 1024; off <<= 1) {
-    uint32_t v = (t >= off) ? part[t - off] : 0;
+  for (int base = 0; base < nblocks; base += kSortThreads) {
+    const int i = base + t;
+    const uint32_t c = (i < nblocks) ? row[i] : 0u;
+    uint32_t incl = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
     __syncthreads();
-    part[t] += v;
+    uint32_t before = carry_s;
+    for (int w = 0; w < warp; ++w) before += warp_sum[w];
+    if (i < nblocks) row[i] = before + incl - c;
+    __syncthreads();
+    if (t == kSortThreads - 1) carry_s = before + incl;
     __syncthreads();
   }
-  uint32_t run = (t == 0) ? 0 : part[t - 1];
-  for (int64_t i = lo; i < hi; ++i) {
-    uint32_t c = counts[i];
-    counts[i] = run;
-    run += c;
-  }
+  if (t == 0) totals[blockIdx.x] = carry_s;
 }
 
 // Stable scatter.  Warp w owns the contiguous slice [base + w*256, base + (w+1)*256) of the tile and
@@ -134,17 +153,38 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* __restrict__ count
 __global__ void __launch_bounds__(kSortThreads)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
-                     int radix_bits, const uint32_t* __restrict__ offsets, int nblocks) {
+                     int radix_bits, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ totals,
+                     int nblocks) {
   constexpr int kWarps = kSortThreads / 32;
   __shared__ uint32_t goff[kMaxRadix];          // global start of (digit, this block)
+  __shared__ uint32_t dbase[kMaxRadix];         // exclusive scan of the digit totals
   __shared__ uint32_t wcnt[kWarps][kMaxRadix];  // per-warp digit counters -> exclusive prefix over warps
   const int radix = 1 << radix_bits;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   for (int d = t; d < radix; d += kSortThreads) {
-    goff[d] = offsets[(size_t)d * nblocks + blockIdx.x];
+    dbase[d] = totals[d];
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) wcnt[w][d] = 0;
   }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of <= 512 totals by one warp, 16 per lane
+    constexpr int kPer = kMaxRadix / 32;
+    uint32_t loc[kPer];
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) { const int d = lane * kPer + j; loc[j] = (d < radix) ? dbase[d] : 0u; s += loc[j]; }
+    uint32_t incl = s;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    uint32_t run = incl - s;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) { const int d = lane * kPer + j; if (d < radix) dbase[d] = run; run += loc[j]; }
+  }
+  __syncthreads();
+  for (int d = t; d < radix; d += kSortThreads) goff[d] = dbase[d] + offsets[(size_t)d * nblocks + blockIdx.x];
   const int64_t base = (int64_t)blockIdx.x * kSortTile + warp * (32 * kSortRounds);
   uint32_t key[kSortRounds], val[kSortRounds], rank[kSortRounds];
 #pragma unroll
@@ -204,6 +244,7 @@ int bits_for(int64_t extent) {  // bits needed for values in [0, extent)
 struct SortBufs {
   uint32_t *k[2], *v[2];
   uint32_t* counts;
+  uint32_t* totals;  // [kMaxRadix]
 };
 
 // Sorts (k[0], v[0]) by key bits [0, bits); returns the index (0/1) of the buffer holding the result.
@@ -215,9 +256,9 @@ int radix_sort(SortBufs& b, int64_t n, int bits, cudaStream_t st) {
   for (int p = 0; p < passes; ++p) {
     const int shift = p * digit_bits;
     radix_hist_kernel<<<nblocks, kSortThreads, 0, st>>>(b.k[cur], n, shift, digit_bits, b.counts, nblocks);
-    scan_kernel<<<1, 1024, 0, st>>>(b.counts, (int64_t)(1 << digit_bits) * nblocks);
+    scan_digit_rows_kernel<<<1 << digit_bits, kSortThreads, 0, st>>>(b.counts, nblocks, b.totals);
     radix_scatter_kernel<<<nblocks, kSortThreads, 0, st>>>(b.k[cur], b.v[cur], b.k[cur ^ 1], b.v[cur ^ 1], n,
-                                                           shift, digit_bits, b.counts, nblocks);
+                                                           shift, digit_bits, b.counts, b.totals, nblocks);
     cur ^= 1;
     count_launches(3);
   }
@@ -234,8 +275,8 @@ extern "C" size_t lpgnn_graph_build_workspace_bytes(int64_t nnz, int32_t m, int3
   const size_t z = (size_t)(nnz > 0 ? nnz : 1);
   const size_t words = align_up(z, 64);
   const size_t nblocks = (z + kSortTile - 1) / kSortTile;
-  // k0,k1,v0,v1,r32,c32,rows_sorted + counts + flag word
-  return (7 * words + align_up(kMaxRadix * nblocks, 64) + 64) * sizeof(uint32_t) + 256;
+  // k0,k1,v0,v1,r32,c32,rows_sorted + counts + digit totals
+  return (7 * words + align_up(kMaxRadix * nblocks, 64) + kMaxRadix + 64) * sizeof(uint32_t) + 256;
 }
 
 extern "C" int lpgnn_graph_build(const void* coo_row, const void* coo_col, int idx_is_i64, const float* coo_val,
@@ -252,7 +293,7 @@ extern "C" int lpgnn_graph_build(const void* coo_row, const void* coo_col, int i
     return LPGNN_EWORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (status) LPGNN_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+  if (status) reset_status_kernel<<<1, 1, 0, st>>>(reinterpret_cast<uint32_t*>(status));
   if (nnz == 0) {
     LPGNN_CUDA_OK(cudaMemsetAsync(rowptr, 0, sizeof(int32_t) * ((size_t)m + 1), st));
     LPGNN_CUDA_OK(cudaMemsetAsync(colptr, 0, sizeof(int32_t) * ((size_t)n + 1), st));
@@ -269,6 +310,7 @@ extern "C" int lpgnn_graph_build(const void* coo_row, const void* coo_col, int i
   uint32_t* c32 = w + 5 * words;
   uint32_t* rows_sorted = w + 6 * words;
   b.counts = w + 7 * words;
+  b.totals = b.counts + align_up((size_t)kMaxRadix * ceil_div(z, kSortTile), 64);
   const int tb = 256, gb = ceil_div(z, tb);
   int launches = 0;
 
@@ -291,8 +333,8 @@ extern "C" int lpgnn_graph_build(const void* coo_row, const void* coo_col, int i
       check_sorted_kernel<<<gb, tb, 0, st>>>(rsrc, csrc, z, reinterpret_cast<uint32_t*>(status));
       ++launches;
     }
-    LPGNN_CUDA_OK(cudaMemcpyAsync(col, csrc, sizeof(uint32_t) * z, cudaMemcpyDeviceToDevice, st));
-    LPGNN_CUDA_OK(cudaMemcpyAsync(val, coo_val, sizeof(float) * z, cudaMemcpyDeviceToDevice, st));
+    copy_entry_kernel<<<gb, tb, 0, st>>>(csrc, coo_val, u_col, val, z, nullptr);
+    ++launches;
     csr_rows = rsrc;
   } else {
     // ---- CSR: LSD over (row, col): column digits first, then row digits
@@ -302,10 +344,10 @@ extern "C" int lpgnn_graph_build(const void* coo_row, const void* coo_col, int i
     gather_u32_kernel<<<gb, tb, 0, st>>>(rsrc, b.v[0], b.k[0], z);  // keys := row of each (col-sorted) entry
     cur = radix_sort(b, z, bits_for(m), st);
     // b.k[cur] = rows of the CSR entries (sorted), b.v[cur] = original COO index of each CSR entry
-    LPGNN_CUDA_OK(cudaMemcpyAsync(rows_sorted, b.k[cur], sizeof(uint32_t) * z, cudaMemcpyDeviceToDevice, st));
+    copy_u32_kernel<<<gb, tb, 0, st>>>(b.k[cur], rows_sorted, z);
     gather_entry_kernel<<<gb, tb, 0, st>>>(csrc, coo_val, b.v[cur], u_col, val, z);
     csr_rows = rows_sorted;
-    launches += 3;
+    launches += 4;
   }
   if (status) {
     expand_check_range_kernel<<<gb, tb, 0, st>>>(rsrc, csrc, z, (uint32_t)m, (uint32_t)n,
@@ -319,7 +361,7 @@ extern "C" int lpgnn_graph_build(const void* coo_row, const void* coo_col, int i
   gather_csc_kernel<<<gb, tb, 0, st>>>(csr_rows, val, b.v[cur], reinterpret_cast<uint32_t*>(csr2csc),
                                        reinterpret_cast<uint32_t*>(row_csc), val_csc, z);
   fill_ptr_kernel<<<ceil_div(z + 1, tb), tb, 0, st>>>(b.k[cur], z, n, colptr);
-  launches += 4;
+  launches += 4 + (status ? 1 : 0);
   LPGNN_LAUNCH_OK();
   count_launches(launches);
   return LPGNN_OK;

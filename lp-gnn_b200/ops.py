@@ -32,26 +32,29 @@ def spmm(view, x: torch.Tensor) -> torch.Tensor:
     return y
 
 
-def conv_in_fused(view, x_src, x_dst, w_rel, b_rel, w_root, out_dtype, relu=True, want_agg=False):
-    """conv1 of GCN_FC for one direction: ``relu(lin_rel(A_view @ x_src) + lin_root(x_dst))`` in one
-    kernel (reference arch.py:75-80, 181-182).  Returns ``(out[rows,N], agg[rows,k_src] | None)``."""
+def conv_in_fused(view, x_src, x_dst, w_rel, b_rel, w_root, out_dtype, relu=True):
+    """conv1 of GCN_FC for one direction: ``relu(lin_rel(A_view @ x_src) + lin_root(x_dst))`` (reference
+    arch.py:75-80, 181-182).  Returns ``(out[rows,N], z_cat[rows,KT])`` where ``z_cat = [A_view@x_src | x_dst | 0]``
+    (fp32) is the transform input, kept for the weight gradient."""
     ptr_, idx, val, rows = view
     require_cuda(ptr_, x_src, x_dst, w_rel, w_root)
     x_src, x_dst = _contig(x_src.float()), _contig(x_dst.float())
     w_rel, w_root, b_rel = _contig(w_rel.float()), _contig(w_root.float()), _contig(b_rel.float())
     N = w_rel.shape[0]
+    lib = _lib.load()
+    kt = lib.lpgnn_conv_in_zcat_width(x_src.shape[1], x_dst.shape[1])
     out = torch.empty((rows, N), dtype=out_dtype, device=x_src.device)
-    agg = torch.empty((rows, x_src.shape[1]), dtype=torch.float32, device=x_src.device) if want_agg else None
+    z_cat = torch.empty((rows, kt), dtype=torch.float32, device=x_src.device)
     with torch.cuda.device(x_src.device):
-        rc = _lib.load().lpgnn_conv_in_fused(ptr_.data_ptr(), idx.data_ptr(), val.data_ptr(), rows, x_src.data_ptr(),
-                                             x_src.shape[1], x_dst.data_ptr(), x_dst.shape[1], w_rel.data_ptr(),
-                                             b_rel.data_ptr(), w_root.data_ptr(), N, out.data_ptr(), dtype_code(out_dtype),
-                                             EPI_RELU if relu else EPI_NONE, ptr(agg), stream_ptr())
+        rc = lib.lpgnn_conv_in_fused(ptr_.data_ptr(), idx.data_ptr(), val.data_ptr(), rows, x_src.data_ptr(),
+                                     x_src.shape[1], x_dst.data_ptr(), x_dst.shape[1], w_rel.data_ptr(),
+                                     b_rel.data_ptr(), w_root.data_ptr(), N, out.data_ptr(), dtype_code(out_dtype),
+                                     EPI_RELU if relu else EPI_NONE, z_cat.data_ptr(), stream_ptr())
     check(rc, "lpgnn_conv_in_fused")
-    return out, agg
+    return out, z_cat
 
 
-def node_transform(a1, w1, a2=None, w2=None, bias=None, relu=False) -> torch.Tensor:
+def node_transform(a1, w1, a2=None, w2=None, bias=None, relu=False, out_dtype=None) -> torch.Tensor:
     """``epi(a1 @ w1.T + a2 @ w2.T + bias)``: bf16 operands -> tcgen05 kernel, fp32 -> CUDA-core
     kernel.  Replaces ``lin_rel(agg) + lin_root(x_dst)`` (+ relu_) (reference arch.py:75-80, 188)."""
     require_cuda(a1, w1, a2, w2, bias)
@@ -69,11 +72,12 @@ def node_transform(a1, w1, a2=None, w2=None, bias=None, relu=False) -> torch.Ten
             raise TypeError("node_transform: all operands must share one dtype")
     if bias is not None:
         bias = _contig(bias.float())
-    out = torch.empty((M, N), dtype=dt, device=a1.device)
+    out_dtype = dt if out_dtype is None else out_dtype
+    out = torch.empty((M, N), dtype=out_dtype, device=a1.device)
     with torch.cuda.device(a1.device):
         rc = _lib.load().lpgnn_node_transform(a1.data_ptr(), K1, w1.data_ptr(), ptr(a2), K2, ptr(w2), ptr(bias), M, N,
-                                              out.data_ptr(), dtype_code(dt), EPI_RELU if relu else EPI_NONE,
-                                              stream_ptr())
+                                              out.data_ptr(), dtype_code(dt), dtype_code(out_dtype),
+                                              EPI_RELU if relu else EPI_NONE, stream_ptr())
     check(rc, "lpgnn_node_transform")
     return out
 
@@ -124,3 +128,90 @@ def basis_select(logits_cons, logits_vars, k_basic=None, int64=True, want_counts
                                     ptr(counts), ws.data_ptr(), ws_bytes, stream_ptr())
     check(rc, "lpgnn_basis_select")
     return (status, counts) if want_counts else status
+
+
+# ------------------------------------------------------------------------------------------------ backward ops
+def head_mask_bwd(dlogits, raw, h_act, w, scale=1.0):
+    """Backward of ``head_mask`` wrt the hidden activation, fused with its ReLU/dropout mask.
+    Returns ``(dH[rows,H], draw[rows,3])``."""
+    require_cuda(dlogits, raw, h_act, w)
+    dlogits, raw, h_act, w = _contig(dlogits.float()), _contig(raw), _contig(h_act), _contig(w.float())
+    rows, H = h_act.shape
+    dH = torch.empty_like(h_act)
+    draw = torch.empty((rows, 3), dtype=torch.float32, device=h_act.device)
+    with torch.cuda.device(h_act.device):
+        rc = _lib.load().lpgnn_head_mask_bwd(dlogits.data_ptr(), raw.data_ptr(), h_act.data_ptr(), dtype_code(h_act.dtype),
+                                             rows, H, w.data_ptr(), float(scale), dH.data_ptr(), draw.data_ptr(),
+                                             stream_ptr())
+    check(rc, "lpgnn_head_mask_bwd")
+    return dH, draw
+
+
+def relu_bwd(a, b, act, scale=1.0, out=None):
+    """``(a [+ b]) * scale * (act > 0)``; ``out`` may alias ``a``."""
+    require_cuda(a, b, act)
+    a, act = _contig(a), _contig(act)
+    if b is not None:
+        b = _contig(b)
+    out = torch.empty_like(a) if out is None else out
+    with torch.cuda.device(a.device):
+        rc = _lib.load().lpgnn_relu_bwd(a.data_ptr(), ptr(b), act.data_ptr(), a.numel(), dtype_code(a.dtype), float(scale),
+                                        out.data_ptr(), stream_ptr())
+    check(rc, "lpgnn_relu_bwd")
+    return out
+
+
+def dropout_(x, p, seed):
+    """In-place inverted dropout (training only)."""
+    require_cuda(x)
+    if p <= 0.0:
+        return x
+    with torch.cuda.device(x.device):
+        rc = _lib.load().lpgnn_dropout(x.data_ptr(), x.numel(), dtype_code(x.dtype), float(p), int(seed) & (2 ** 64 - 1),
+                                       stream_ptr())
+    check(rc, "lpgnn_dropout")
+    return x
+
+
+def transpose(x, pad_to=64):
+    """``x^T`` as ``[N, ld]`` with ``ld = M`` rounded up to ``pad_to`` and zero-filled padding columns."""
+    require_cuda(x)
+    x = _contig(x)
+    M, N = x.shape
+    ld = (M + pad_to - 1) // pad_to * pad_to
+    out = torch.empty((N, ld), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().lpgnn_transpose(x.data_ptr(), dtype_code(x.dtype), M, N, out.data_ptr(), ld, stream_ptr())
+    check(rc, "lpgnn_transpose")
+    return out
+
+
+def colsum(x):
+    require_cuda(x)
+    x = _contig(x)
+    M, N = x.shape
+    lib = _lib.load()
+    out = torch.empty(N, dtype=torch.float32, device=x.device)
+    ws_bytes = lib.lpgnn_colsum_workspace_bytes(M, N)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.lpgnn_colsum(x.data_ptr(), dtype_code(x.dtype), M, N, out.data_ptr(), ws.data_ptr(), ws_bytes, stream_ptr())
+    check(rc, "lpgnn_colsum")
+    return out
+
+
+def small_wgrad(dy, z, k, want_bias=False):
+    """``dW[N,k] = dy^T z[:, :k]`` (z fp32, any row stride) and optionally ``dB[N] = colsum(dy)``."""
+    require_cuda(dy, z)
+    dy, z = _contig(dy), _contig(z.float())
+    M, N = dy.shape
+    lib = _lib.load()
+    dW = torch.empty((N, k), dtype=torch.float32, device=dy.device)
+    dB = torch.empty(N, dtype=torch.float32, device=dy.device) if want_bias else None
+    ws_bytes = lib.lpgnn_small_wgrad_workspace_bytes(M, N, k)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dy.device)
+    with torch.cuda.device(dy.device):
+        rc = lib.lpgnn_small_wgrad(dy.data_ptr(), dtype_code(dy.dtype), z.data_ptr(), z.shape[1], k, M, N, dW.data_ptr(),
+                                   ptr(dB), ws.data_ptr(), ws_bytes, stream_ptr())
+    check(rc, "lpgnn_small_wgrad")
+    return dW, dB

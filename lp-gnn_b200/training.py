@@ -1,0 +1,191 @@
+"""Training path: GCN_FC forward + hand-derived backward over the CUDA kernels.
+
+One ``torch.autograd.Function`` covers the whole network (reference arch.py:179-193), so autograd sees
+the parameters and the two logit tensors only; every activation-sized step of the backward pass is a
+kernel of liblpgnn (``ops``).  The loss (reference train.py:32-53) and the optimiser (train.py:85-89)
+stay in PyTorch, as in the reference.
+
+Backward algebra for one GraphConvTwoDirection layer (reference arch.py:65-81; A is m x n):
+    R' = relu(drop(T W_rel^{l2r T} + R W_root^{l2r T} + b)),  T = A^T L        (variables)
+    L' = relu(drop(S W_rel^{r2l T} + L W_root^{r2l T} + b)),  S = A  R        (constraints)
+    dPre_t = dR' * mask(R'), dPre_s = dL' * mask(L')                         -> ops.relu_bwd / head_mask_bwd
+    dW_rel^{l2r} = dPre_t^T T, dW_root^{l2r} = dPre_t^T R, db = colsum(dPre_t)   -> transposes + GEMM / colsum
+    dL = dPre_s W_root^{r2l} + A   (dPre_t W_rel^{l2r})                       -> GEMM + ops.spmm(csr)
+    dR = dPre_t W_root^{l2r} + A^T (dPre_s W_rel^{r2l})                       -> GEMM + ops.spmm(csc)
+Everything is atomics-free, so a step is bit-reproducible.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def _param_list(model):
+    """Flat parameter order shared by forward() and backward()."""
+    out = []
+    for conv in [model.conv1, *model.layers]:
+        for gc in (conv.left2right, conv.right2left):
+            out += [gc.lin_rel.weight, gc.lin_rel.bias, gc.lin_root.weight]
+    out += [model.lin_left.weight, model.lin_left.bias, model.lin_right.weight, model.lin_right.bias]
+    return out
+
+
+def _wgrad(d_pre, d_pre_t, x):
+    """dW[N,K] = d_pre^T x via the TN GEMM on transposed copies (reduction over the node dimension)."""
+    xt = ops.transpose(x)                                   # [K, M]
+    return ops.node_transform(d_pre_t, xt, out_dtype=torch.float32)
+
+
+class _GCNFCFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_s, x_t, csr, csc, cfg, *params):
+        dt, dp, training, seed = cfg["dtype"], cfg["dp"], cfg["training"], cfg["seed"]
+        n_layers = cfg["n_hidden"]
+        P = [p.detach() for p in params]
+        cast = (lambda w: w.to(dt)) if dt != torch.float32 else (lambda w: w)
+        x_s, x_t = x_s.float().contiguous(), x_t.float().contiguous()
+        # conv1 (p,q -> H), relu fused
+        right, z_t = ops.conv_in_fused(csc, x_s, x_t, P[0], P[1], P[2], dt, relu=True)
+        left, z_s = ops.conv_in_fused(csr, x_t, x_s, P[3], P[4], P[5], dt, relu=True)
+        saved = [z_s, z_t, left, right]
+        scale = 1.0
+        for i in range(n_layers):
+            w = P[6 + 6 * i: 12 + 6 * i]
+            agg_t, agg_s = ops.spmm(csc, left), ops.spmm(csr, right)
+            right_new = ops.node_transform(agg_t, cast(w[0]), right, cast(w[2]), w[1], relu=True)
+            left_new = ops.node_transform(agg_s, cast(w[3]), left, cast(w[5]), w[4], relu=True)
+            if training and dp > 0:
+                # reference order is dropout then relu_ (arch.py:186-188); relu(drop(x)) == drop(relu(x))
+                ops.dropout_(right_new, dp, seed + 2 * i)
+                ops.dropout_(left_new, dp, seed + 2 * i + 1)
+                scale = 1.0 / (1.0 - dp)
+            saved += [agg_s, agg_t, left_new, right_new]
+            left, right = left_new, right_new
+        hw = P[6 + 6 * n_layers:]
+        logit_s, raw_s = ops.head_mask(left, hw[0], hw[1], x_s, want_raw=True)
+        logit_t, raw_t = ops.head_mask(right, hw[2], hw[3], x_t, want_raw=True)
+        ctx.csr, ctx.csc, ctx.cfg = csr, csc, cfg
+        ctx.scale = scale if (training and dp > 0) else 1.0
+        ctx.save_for_backward(x_s, x_t, raw_s, raw_t, *saved, *P)
+        ctx.n_saved_act = len(saved)
+        return logit_s, logit_t
+
+    @staticmethod
+    def backward(ctx, d_logit_s, d_logit_t):
+        cfg = ctx.cfg
+        dt, n_layers = cfg["dtype"], cfg["n_hidden"]
+        csr, csc = ctx.csr, ctx.csc
+        t = ctx.saved_tensors
+        x_s, x_t, raw_s, raw_t = t[:4]
+        acts = t[4:4 + ctx.n_saved_act]
+        P = t[4 + ctx.n_saved_act:]
+        z_s, z_t = acts[0], acts[1]
+        cast = (lambda w: w.to(dt)) if dt != torch.float32 else (lambda w: w)
+        grads = [None] * len(P)
+        hbase = 6 + 6 * n_layers
+        # ---- heads: dPre of the last layer's activations (relu/dropout mask fused)
+        left, right = acts[2 + 4 * n_layers], acts[3 + 4 * n_layers]
+        last_scale = ctx.scale if n_layers > 0 else 1.0
+        d_pre_s, draw_s = ops.head_mask_bwd(d_logit_s.contiguous(), raw_s, left, P[hbase], last_scale)
+        d_pre_t, draw_t = ops.head_mask_bwd(d_logit_t.contiguous(), raw_t, right, P[hbase + 2], last_scale)
+        gw, _ = ops.small_wgrad(left, draw_s, 3)            # [H,3] = left^T draw
+        grads[hbase] = gw.t().contiguous()
+        grads[hbase + 1] = ops.colsum(draw_s)
+        gw, _ = ops.small_wgrad(right, draw_t, 3)
+        grads[hbase + 2] = gw.t().contiguous()
+        grads[hbase + 3] = ops.colsum(draw_t)
+        # ---- hidden layers, last to first
+        for i in reversed(range(n_layers)):
+            w = P[6 + 6 * i: 12 + 6 * i]
+            agg_s, agg_t = acts[4 + 4 * i], acts[5 + 4 * i]
+            left_in, right_in = acts[2 + 4 * i], acts[3 + 4 * i]       # inputs of this layer (outputs of the previous)
+            dps_t, dpt_t = ops.transpose(d_pre_s), ops.transpose(d_pre_t)
+            g = 6 + 6 * i
+            grads[g + 0] = _wgrad(d_pre_t, dpt_t, agg_t)               # l2r lin_rel.weight
+            grads[g + 1] = ops.colsum(d_pre_t)
+            grads[g + 2] = _wgrad(d_pre_t, dpt_t, right_in)            # l2r lin_root.weight
+            grads[g + 3] = _wgrad(d_pre_s, dps_t, agg_s)               # r2l lin_rel.weight
+            grads[g + 4] = ops.colsum(d_pre_s)
+            grads[g + 5] = _wgrad(d_pre_s, dps_t, left_in)             # r2l lin_root.weight
+            del dps_t, dpt_t
+            # data gradients (weights transposed once per step: [K,N] K-major for the TN kernel)
+            w_rel_l2r_t, w_root_l2r_t = cast(w[0]).t().contiguous(), cast(w[2]).t().contiguous()
+            w_rel_r2l_t, w_root_r2l_t = cast(w[3]).t().contiguous(), cast(w[5]).t().contiguous()
+            d_agg_t = ops.node_transform(d_pre_t, w_rel_l2r_t)          # [n,H]
+            d_right_root = ops.node_transform(d_pre_t, w_root_l2r_t)    # [n,H]
+            d_agg_s = ops.node_transform(d_pre_s, w_rel_r2l_t)          # [m,H]
+            d_left_root = ops.node_transform(d_pre_s, w_root_r2l_t)     # [m,H]
+            d_left_agg = ops.spmm(csr, d_agg_t)                         # A   . dAgg_t  [m,H]
+            d_right_agg = ops.spmm(csc, d_agg_s)                        # A^T . dAgg_s  [n,H]
+            prev_scale = ctx.scale if i > 0 else 1.0                    # conv1 output has no dropout
+            d_pre_s = ops.relu_bwd(d_left_root, d_left_agg, left_in, prev_scale, out=d_left_root)
+            d_pre_t = ops.relu_bwd(d_right_root, d_right_agg, right_in, prev_scale, out=d_right_root)
+        # ---- conv1: weight gradients only (inputs are data)
+        k_s, k_t = x_s.shape[1], x_t.shape[1]
+        gw, gb = ops.small_wgrad(d_pre_t, z_t, k_s + k_t, want_bias=True)   # z_t = [A^T x_s | x_t]
+        grads[0], grads[1], grads[2] = gw[:, :k_s].contiguous(), gb, gw[:, k_s:].contiguous()
+        gw, gb = ops.small_wgrad(d_pre_s, z_s, k_s + k_t, want_bias=True)   # z_s = [A x_t | x_s]
+        grads[3], grads[4], grads[5] = gw[:, :k_t].contiguous(), gb, gw[:, k_t:].contiguous()
+        return (None, None, None, None, None, *grads)
+
+
+_step_counter = [0]
+
+
+def gcn_fc_train(model, x_s, x_t, csr, csc):
+    dt = torch.bfloat16 if model.precision == "bf16" else torch.float32
+    _step_counter[0] += 1
+    cfg = dict(dtype=dt, dp=float(model.dp), training=bool(model.training), n_hidden=len(model.layers),
+               seed=(int(torch.initial_seed()) * 1_000_003 + _step_counter[0] * 7919) & (2 ** 62 - 1))
+    return _GCNFCFunction.apply(x_s, x_t, csr, csc, cfg, *_param_list(model))
+
+
+def conv_train(conv, left, right, csr, csc, relu, dropout_p=0.0, training=False):
+    raise NotImplementedError("stand-alone GraphConvTwoDirection training is not wired up; train through GCN_FC")
+
+
+class AddKnowledgeFn(torch.autograd.Function):
+    """add_knowledge with gradient (reference arch.py:129-141) for callers that own the head."""
+
+    @staticmethod
+    def forward(ctx, logits, feas):
+        ctx.save_for_backward(logits)
+        return ops.add_knowledge_kernel(logits, feas)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        x = x.float()
+        nrm = x.norm(dim=1, keepdim=True).clamp_min(1e-12)      # [rows,3]: tiny, not an activation-sized tensor
+        u = x / nrm
+        return (10.0 / nrm) * (g - u * (u * g).sum(1, keepdim=True)), None
+
+
+def smoke_step(dev):
+    """One training step on a small LP (forward, balanced loss, backward, Adam) -- used by smoke()."""
+    import types
+
+    import numpy as np
+
+    from . import arch, synth
+    from .graph import BipartiteCSR
+    from .losses import balanced
+    lp = synth.processed_lp(400, 800, 4000, seed=5)
+    torch.manual_seed(0)
+    model = arch.GCN_FC(8, 8, hids=64, depth=3).to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4)
+    batch = types.SimpleNamespace(
+        x_s=torch.from_numpy(lp.c_feas).to(dev), x_t=torch.from_numpy(lp.v_feas).to(dev),
+        edge_index=BipartiteCSR.from_coo_arrays(lp.row, lp.col, lp.a_data.astype(np.float32), lp.m, lp.n, dev, is_sorted=True))
+    y_s, y_t = torch.from_numpy(lp.y_s).to(dev), torch.from_numpy(lp.y_t).to(dev)
+    losses = []
+    for _ in range(3):
+        lc, lv = model(batch)
+        loss = balanced(lc, lv, y_s, y_t)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)), losses
+    print(f"smoke[train]: losses {losses}")

@@ -1,0 +1,169 @@
+"""Training step parity: gradients of every parameter through the CUDA backward kernels vs the gradients
+the REFERENCE computed (golden vectors produced by /root/reference's own autograd, oracle/make_golden.py),
+plus unit checks of each backward kernel against torch autograd on the same inputs."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _golden_setup(name, dev, precision):
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import arch
+    from lpgnn_b200.graph import BipartiteCSR
+    zg = np.load(os.path.join(GOLD, f"graph_{name}.npz"))
+    zm = np.load(os.path.join(GOLD, f"model_{name}.npz"))
+    model = arch.GCN_FC(8, 8, hids=int(zm["hids"]), depth=int(zm["depth"]))
+    model.load_state_dict({k[3:]: torch.from_numpy(zm[k]) for k in zm.files if k.startswith("w::")})
+    model = model.to(dev).eval().set_precision(precision)          # eval: the golden gradients were taken without dropout
+    m, n = int(zg["m"]), int(zg["n"])
+    row = np.repeat(np.arange(m), np.diff(zg["rowptr"]))
+    g = BipartiteCSR.from_coo_arrays(row, zg["col"], zg["val"], m, n, dev, is_sorted=True).check()
+    batch = types.SimpleNamespace(x_s=torch.from_numpy(zg["x_s"]).to(dev), x_t=torch.from_numpy(zg["x_t"]).to(dev),
+                                  edge_index=g)
+    y_s, y_t = torch.from_numpy(zg["y_s"]).to(dev), torch.from_numpy(zg["y_t"]).to(dev)
+    return model, batch, y_s, y_t, zm
+
+
+@pytest.mark.parametrize("name", ["tiny_5x7", "small_300x600", "c1_1000x2000"])
+def test_loss_and_gradients_match_reference_fp32(cuda, name):
+    from lpgnn_b200.losses import balanced
+    model, batch, y_s, y_t, zm = _golden_setup(name, cuda, "fp32")
+    lc, lv = model(batch)                                           # grad enabled -> autograd.Function path
+    assert lc.requires_grad
+    np.testing.assert_allclose(lc.detach().cpu().numpy(), zm["logits_cons"], atol=1e-3)
+    assert np.abs(lv.detach().cpu().numpy() - zm["logits_vars"]).max() / 10 < 1e-4
+    loss = balanced(lc, lv, y_s, y_t)
+    assert abs(float(loss) - float(zm["loss"])) < 1e-4 * max(1.0, abs(float(zm["loss"])))
+    loss.backward()
+    for k, p in model.named_parameters():
+        ref = zm[f"g::{k}"]
+        got = p.grad.cpu().numpy()
+        assert got.shape == ref.shape, k
+        scale = max(np.abs(ref).max(), 1e-6)
+        assert np.abs(got - ref).max() / scale < 2e-3, (k, np.abs(got - ref).max() / scale)
+
+
+@pytest.mark.parametrize("name", ["small_300x600", "c1_1000x2000"])
+def test_gradients_bf16_close_to_reference(cuda, name):
+    from lpgnn_b200.losses import balanced
+    model, batch, y_s, y_t, zm = _golden_setup(name, cuda, "bf16")
+    lc, lv = model(batch)
+    loss = balanced(lc, lv, y_s, y_t)
+    assert abs(float(loss) - float(zm["loss"])) < 2e-2 * max(1.0, abs(float(zm["loss"])))
+    loss.backward()
+    for k, p in model.named_parameters():
+        ref = zm[f"g::{k}"]
+        got = p.grad.cpu().numpy()
+        rel = np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-9)
+        assert rel < 8e-2, (k, rel)                                 # bf16 activations + bf16 tensor-core GEMMs
+
+
+def test_backward_is_bit_reproducible(cuda):
+    from lpgnn_b200.losses import balanced
+    grads = []
+    for _ in range(2):
+        model, batch, y_s, y_t, _ = _golden_setup("small_300x600", cuda, "fp32")
+        lc, lv = model(batch)
+        balanced(lc, lv, y_s, y_t).backward()
+        grads.append([p.grad.clone() for p in model.parameters()])
+    for a, b in zip(*grads):
+        assert torch.equal(a, b)                                    # atomics-free: identical bits run to run
+
+
+def test_training_reduces_loss_with_dropout(cuda):
+    from lpgnn_b200.losses import balanced
+    model, batch, y_s, y_t, _ = _golden_setup("small_300x600", cuda, "fp32")
+    model.train()
+    model.dp = 0.1
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4)
+    losses = []
+    for _ in range(30):
+        lc, lv = model(batch)
+        loss = balanced(lc, lv, y_s, y_t)
+        assert not torch.isnan(loss).item()                          # train.py:126
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert min(losses[-5:]) < losses[0]
+
+
+# ------------------------------------------------------------------------------------------- kernel units
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_relu_bwd_and_transpose_and_colsum(cuda, dtype):
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    M, N = 1000, 192
+    a = torch.randn(M, N, device=cuda, generator=g).to(dtype)
+    b = torch.randn(M, N, device=cuda, generator=g).to(dtype)
+    act = torch.randn(M, N, device=cuda, generator=g).relu().to(dtype)
+    out = ops.relu_bwd(a, b, act, scale=1.25)
+    exp = ((a.float() + b.float()) * 1.25 * (act > 0)).to(dtype)
+    assert torch.equal(out, exp)
+    assert torch.equal(ops.relu_bwd(a, None, act), (a.float() * (act > 0)).to(dtype))
+    t = ops.transpose(a)
+    assert t.shape == (N, 1024) and torch.equal(t[:, :M], a.t()) and not t[:, M:].any()
+    cs = ops.colsum(a)
+    assert float((cs - a.float().sum(0)).abs().max()) < 1e-2
+    assert torch.equal(cs, ops.colsum(a))                           # deterministic
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("K,ldz", [(3, 3), (16, 16), (12, 16), (40, 64)])
+def test_small_wgrad(cuda, dtype, K, ldz):
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(K)
+    M, N = 3000, 320
+    dy = torch.randn(M, N, device=cuda, generator=g).to(dtype)
+    z = torch.randn(M, ldz, device=cuda, generator=g)
+    dW, dB = ops.small_wgrad(dy, z, K, want_bias=True)
+    exp = dy.double().t() @ z[:, :K].double()
+    assert float((dW.double() - exp).abs().max()) < 2e-3
+    assert float((dB.double() - dy.double().sum(0)).abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("dtype,H", [(torch.float32, 64), (torch.float32, 1024), (torch.bfloat16, 1024), (torch.bfloat16, 128)])
+def test_head_mask_bwd_vs_autograd(cuda, dtype, H):
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(H)
+    rows = 2000
+    h = torch.randn(rows, H, device=cuda, generator=g).relu().to(dtype)
+    w = torch.randn(3, H, device=cuda, generator=g) / H ** 0.5
+    b = torch.randn(3, device=cuda, generator=g)
+    feas = torch.randint(-1, 2, (rows, 8), device=cuda, generator=g).float()
+    dl = torch.randn(rows, 3, device=cuda, generator=g)
+    logits, raw = ops.head_mask(h, w, b, feas, want_raw=True)
+    dH, draw = ops.head_mask_bwd(dl, raw, h, w, scale=1.0)
+    hh = h.float().clone().requires_grad_(True)
+    ww = w.clone().requires_grad_(True)
+    r = hh @ ww.t() + b
+    y = torch.nn.functional.normalize(r) * 10
+    (y * dl).sum().backward()
+    exp_dH = hh.grad * (h.float() > 0)
+    tol = 1e-4 if dtype == torch.float32 else 3e-2
+    assert float((dH.float() - exp_dH).abs().max()) < tol * max(1.0, float(exp_dH.abs().max()))
+    gw, _ = ops.small_wgrad(h, draw, 3)
+    assert float((gw.t() - ww.grad).abs().max()) < 1e-2 * max(1.0, float(ww.grad.abs().max()))
+
+
+def test_dropout_statistics_and_determinism(cuda):
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    x = torch.ones(4096, 1024, device=cuda)
+    a = ops.dropout_(x.clone(), 0.1, seed=123)
+    b = ops.dropout_(x.clone(), 0.1, seed=123)
+    c = ops.dropout_(x.clone(), 0.1, seed=124)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    keep = float((a > 0).float().mean())
+    assert abs(keep - 0.9) < 2e-3
+    assert abs(float(a.mean()) - 1.0) < 3e-3                        # inverted scaling keeps the mean
+    assert set(torch.unique(a).cpu().tolist()) == {0.0, float(torch.tensor(1.0 / 0.9, dtype=torch.float32))}

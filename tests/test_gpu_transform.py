@@ -81,9 +81,10 @@ def test_conv_in_fused_vs_oracle(cuda, hids, out_dtype):
     t = lambda a: torch.from_numpy(a).to(cuda)
     csr, csc = g.views()
     # variables side: dst = vars, src = cons, orientation = CSC
-    out, agg = ops.conv_in_fused(csc, t(x_s), t(x_t), t(w_rel), t(b), t(w_root), out_dtype, relu=True, want_agg=True)
+    out, zc = ops.conv_in_fused(csc, t(x_s), t(x_t), t(w_rel), t(b), t(w_root), out_dtype, relu=True)
     agg_e = port.spmm_sequential(ref.colptr, ref.row_csc, ref.val_csc, x_s)
-    np.testing.assert_allclose(agg.cpu().numpy(), agg_e, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(zc[:, :8].cpu().numpy(), agg_e, rtol=1e-5, atol=1e-5)
+    np.testing.assert_array_equal(zc[:, 8:16].cpu().numpy(), x_t)
     e = np.maximum(agg_e.astype(np.float64) @ w_rel.T.astype(np.float64) + b + x_t.astype(np.float64) @ w_root.T, 0)
     tol = 1e-4 if out_dtype == torch.float32 else 3e-2
     np.testing.assert_allclose(out.float().cpu().numpy(), e, rtol=tol, atol=tol)
