@@ -1,0 +1,169 @@
+"""Drop-in for the reference ``dataset.py``: same processed-file layout, same ``LPDataset.get`` ->
+``UnipartiteData`` -> ``MyToBipartite`` flow and the same batch fields (``x_s, x_t, y_s, y_t, edge_index, bs,
+s_bs, t_bs, processed_path[, con_nms, var_nms]``; reference dataset.py:229-332), but ``batch.edge_index`` is a
+``BipartiteCSR`` (host COO until ``.to(cuda)``; built on the device) instead of a torch_sparse ``SparseTensor``.
+
+Host code: runs in DataLoader worker processes and never touches CUDA.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import os.path as osp
+
+import numpy as np
+import torch
+from scipy.sparse import coo_matrix
+
+from .data import Data, Dataset
+from .features import node_features, scale_lp
+from .graph import BipartiteCSR
+from .io_utils import msgpack_dump, msgpack_load
+
+
+class UnipartiteData(Data):
+    def __init__(self, x, y, edge_index, edge_weight=None, **kwargs):
+        super().__init__(x=x, y=y, edge_index=edge_index, edge_weight=edge_weight, **kwargs)
+
+
+scaling = scale_lp                 # reference names (dataset.py:23, 79)
+cvt_to_features = node_features
+
+
+def to_undirected_sorted(row, col_shifted, attr, num_nodes):
+    """``torch_geometric.utils.to_undirected`` for a bipartite edge list (dataset.py:252): both directions,
+    attributes duplicated, sorted by ``src * N + dst`` (no duplicates can occur)."""
+    src = np.concatenate([row, col_shifted])
+    dst = np.concatenate([col_shifted, row])
+    att = np.concatenate([attr, attr])
+    order = np.argsort(src * np.int64(num_nodes) + dst, kind="stable")
+    return np.stack([src[order], dst[order]]), att[order]
+
+
+class LPDataset(Dataset):
+    def __init__(self, root, transform=None, pre_transform=None, pre_filter=None, load_meta=False, chunk=None):
+        self.load_meta = load_meta
+        self.chunk = chunk
+        self.p = self.q = 8
+        super().__init__(root, transform, pre_transform, pre_filter)
+
+    @property
+    def raw_file_names(self):
+        fns = []
+        for folder in [self.raw_dir, self.processed_dir]:
+            if not osp.exists(folder):
+                continue
+            now = sorted((f for f in os.listdir(folder) if f.endswith(".pk")), key=lambda nm: (len(nm), nm))
+            if len(now) > len(fns):
+                fns = now
+        if len(fns) == 0:
+            raise ValueError("not found pk")
+        return fns
+
+    @property
+    def processed_file_names(self):
+        return self.raw_file_names
+
+    def len(self):
+        return len(self.processed_file_names)
+
+    def process(self):
+        """raw ``.pk`` -> processed ``.pk`` + ``.meta`` (dataset.py:178-224)."""
+        os.makedirs(self.processed_dir, exist_ok=True)
+        for raw_path in self.raw_paths:
+            processed_path = osp.join(self.processed_dir, osp.basename(raw_path))
+            if osp.exists(processed_path) and osp.exists(processed_path + ".meta"):
+                continue
+            [c, b_l, (row, col, data), b_u, l, u, con_lbls, var_lbls, con_nms, var_nms] = msgpack_load(raw_path)
+            ncons, nvars = len(con_nms), len(var_nms)
+            A = coo_matrix((np.asarray(data), (np.asarray(row), np.asarray(col))), shape=(ncons, nvars)).tocsr()
+            c, b_l, A, b_u, l, u = scale_lp(np.asarray(c), np.asarray(b_l), A, np.asarray(b_u), np.asarray(l), np.asarray(u))
+            v_feas, c_feas = node_features(c, b_l, A, b_u, l, u)
+            v_feas, c_feas = v_feas.astype(np.float32), c_feas.astype(np.float32)
+            y_s, y_t = np.asarray(con_lbls, dtype=np.int64), np.asarray(var_lbls, dtype=np.int64)
+            # labels never contradict the +-inf tags (dataset.py:201-207)
+            assert (y_s[c_feas[:, -3] != 0] != 0).all() and (y_s[c_feas[:, -1] != 0] != 2).all()
+            violates = int((y_t[v_feas[:, -3] != 0] == 0).sum())
+            if violates:
+                logging.warning(f"violate {violates}")
+            assert (y_t[v_feas[:, -1] != 0] != 2).all()
+            A = A.tocoo()
+            msgpack_dump([A.row, A.col, A.data, c_feas, v_feas, y_s, y_t, ncons + nvars], processed_path)
+            msgpack_dump(dict(num_cons=ncons, num_vars=nvars, raw_path=raw_path, processed_path=processed_path,
+                              con_nms=list(con_nms), var_nms=list(var_nms)), processed_path + ".meta")
+
+    def get(self, idx):
+        """dataset.py:229-264: unipartite graph with cons first, undirected sorted edges."""
+        fn = osp.join(self.processed_dir, self.processed_file_names[idx])
+        [row, col, A_data, c_feas, v_feas, y_s, y_t, nnodes] = msgpack_load(fn)
+        row, col, A_data = np.asarray(row), np.asarray(col), np.asarray(A_data)
+        c_feas, v_feas = np.asarray(c_feas), np.asarray(v_feas)
+        ncons = c_feas.shape[0]
+        assert A_data.max() <= 1 and A_data.min() >= -1
+        assert c_feas.max() <= 1 and c_feas.min() >= -1
+        aux = dict(processed_path=fn)
+        if self.load_meta:
+            meta = msgpack_load(fn + ".meta")
+            aux.update(con_nms=meta["con_nms"], var_nms=meta["var_nms"])
+        nnodes = int(nnodes)
+        ei, ea = to_undirected_sorted(row.astype(np.int64), col.astype(np.int64) + ncons, A_data.astype(np.float32), nnodes)
+        is_vars = torch.zeros(nnodes, dtype=torch.long)
+        is_vars[ncons:] = 1
+        return UnipartiteData(
+            x=torch.cat((torch.from_numpy(c_feas), torch.from_numpy(v_feas)), dim=0),
+            y=torch.cat((torch.from_numpy(np.asarray(y_s)), torch.from_numpy(np.asarray(y_t))), dim=0),
+            is_vars=is_vars, edge_index=torch.from_numpy(ei), edge_attr=torch.from_numpy(ea), num_nodes=nnodes, **aux)
+
+
+class MyToBipartite:
+    """dataset.py:268-332.  Output graph: ``BipartiteCSR`` host COO (cons -> var half of the edges, already in
+    canonical (row, col) order because the undirected list is sorted by ``src*N+dst``), built on the device when
+    the batch is moved with ``batch.to(dev)`` / ``batch_to``."""
+
+    def __init__(self, dev="cpu", phase="train", thresh_num=np.inf):
+        self.dev, self.phase, self.thresh_num = dev, phase, thresh_num
+
+    def __call__(self, batch):
+        if hasattr(batch, "x_s"):
+            return batch
+        if batch.edge_index.shape[-1] // 2 > self.thresh_num:
+            return batch
+        is_vars = batch.is_vars.bool()
+        is_cons = ~is_vars
+        nnodes = batch.num_nodes
+        nvars = int(is_vars.sum())
+        ncons = nnodes - nvars
+        mapping = torch.empty(nnodes, dtype=torch.long)
+        mapping[is_cons] = torch.arange(ncons)
+        mapping[is_vars] = torch.arange(nvars) + ncons
+        src, dst = mapping[batch.edge_index[0]], mapping[batch.edge_index[1]]
+        mask = src < ncons
+        assert int(mask.sum()) * 2 == mask.shape[0]                               # dataset.py:297
+        batch.edge_index = BipartiteCSR.from_coo(src[mask], dst[mask] - ncons, batch.edge_attr[mask], ncons, nvars,
+                                                 is_sorted=bool(is_cons[:ncons].all()))
+        del batch.edge_attr
+        batch.x_s, batch.x_t = batch.x[is_cons, :], batch.x[is_vars, :]
+        batch.y_s, batch.y_t = batch.y[is_cons], batch.y[is_vars]
+        del batch.x, batch.y
+        batch.bs = batch.batch_size if hasattr(batch, "batch_size") else batch.num_nodes
+        t_bs = int(batch.is_vars[:batch.bs].sum())
+        batch.s_bs, batch.t_bs = batch.bs - t_bs, t_bs
+        del batch.is_vars
+        if self.phase == "train" and hasattr(batch, "batch"):
+            del batch.batch
+        return batch
+
+
+def write_synthetic_dataset(root, sizes, seed=0, structure="staircase"):
+    """Materialises processed ``.pk`` files of synthetic LPs (``synth.processed_lp``) so that the loaders,
+    train.py and pred_basis.py can run end to end without the MIRP data.  ``sizes`` = [(m, n, nnz), ...]."""
+    from . import synth
+    pdir = osp.join(root, "processed")
+    os.makedirs(pdir, exist_ok=True)
+    for i, (m, n, z) in enumerate(sizes):
+        lp = synth.processed_lp(m, n, z, seed=seed * 100_003 + i, structure=structure)
+        fn = osp.join(pdir, f"lp{i}.pk")
+        msgpack_dump([lp.row, lp.col, lp.a_data, lp.c_feas, lp.v_feas, lp.y_s, lp.y_t, lp.m + lp.n], fn)
+        msgpack_dump(dict(num_cons=lp.m, num_vars=lp.n, raw_path="", processed_path=fn,
+                          con_nms=[f"c{j}" for j in range(lp.m)], var_nms=[f"x{j}" for j in range(lp.n)]), fn + ".meta")
+    return pdir

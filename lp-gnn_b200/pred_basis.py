@@ -1,0 +1,125 @@
+"""Drop-in for the reference ``scripts/pred_basis.py``: for every LP run the model, decide the basis
+(``inference_gnn``) and write a HiGHS ``.bas`` file plus the ``.bas.sort`` probability file
+(pred_basis.py:14-23, 57-67, 70-111); then the per-LP inference timing loop (157-178).
+
+Differences in mechanism, not in outputs: the basis decision runs on the device (no logits round trip), the
+statuses come back as one uint8 D2H copy per LP, files are written by a small thread pool instead of a thread
+per file, and under ``torchrun`` the LPs are sharded over the ranks (independent units, no collective).
+"""
+from __future__ import annotations
+
+import json
+import logging
+import os
+import os.path as osp
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import torch
+
+from . import ops
+from .arch import *  # noqa: F401,F403
+from .data import DataLoader
+from .dataset import LPDataset, MyToBipartite
+from .io_utils import batch_to, extract_fn, mkdir_p, shard_indices, split_train_val
+from .train import init_distributed, parse_args
+from .val import InferenceManager  # noqa: F401  (eval(args.inference_manager))
+
+
+def enc_vec(v):
+    return " ".join(str(x) for x in v)
+
+
+def write_bas_highs(fn, vnms=None, cnms=None, vbas=None, cbas=None):
+    """HiGHS basis file (pred_basis.py:14-23): ``HIGHS v1 / Valid / # Columns n / <n ints> / # Rows m / <m ints>``."""
+    assert vbas is not None
+    mkdir_p(osp.dirname(fn))
+    with open(fn, "w") as f:
+        f.write("HIGHS v1\nValid\n")
+        f.write(f"# Columns {len(vbas)}\n")
+        f.write(enc_vec(np.asarray(vbas).tolist()) + "\n")
+        f.write(f"# Rows {len(cbas)}\n")
+        f.write(enc_vec(np.asarray(cbas).tolist()) + "\n")
+
+
+def write_sort_vars(fn, p_basic_vars, p_basic_cons):
+    """``.bas.sort`` file (pred_basis.py:57-67): P(basic) of the variables, then of the constraints."""
+    with open(fn, "w") as f:
+        f.write(f"{len(p_basic_vars)} \n")
+        f.write(enc_vec(p_basic_vars) + "\n")
+        f.write(f"{len(p_basic_cons)} \n")
+        f.write(enc_vec(p_basic_cons) + "\n")
+
+
+@torch.no_grad()
+def predict_one(model, batch, dev, fp16=False):
+    """model -> logits -> (status uint8 [m+n], P(basic) [m+n]) on the host (pred_basis.py:70-85)."""
+    batch = batch_to(batch, dev, fp16)
+    lc, lv = model(batch)
+    lc, lv = lc[:batch.s_bs], lv[:batch.t_bs]
+    status = ops.basis_select(lc, lv, k_basic=lc.shape[0], int64=False)
+    p1 = torch.softmax(torch.cat((lc, lv), 0), dim=-1)[:, 1]      # [m+n] values for the .sort file (tiny)
+    return status.cpu().numpy(), p1.cpu().numpy(), lc.shape[0]
+
+
+@torch.no_grad()
+def inference_only(model, batch):
+    """pred_basis.py:113-118: the timed region of the per-LP benchmark."""
+    lc, lv = model(batch)
+    return ops.basis_select(lc, lv, k_basic=lc.shape[0], int64=False)
+
+
+def run(args):
+    rank, world, local = init_distributed()
+    if not torch.cuda.is_available():
+        raise RuntimeError("pred_basis needs a CUDA device: the lp-gnn hot path has no CPU fallback")
+    dev = torch.device("cuda", local if world > 1 else args.dev)
+    torch.cuda.set_device(dev)
+    inf_mng = eval(args.inference_manager)           # noqa: S307
+    folder = inf_mng.get_basis_folder()
+    model = eval(args.arch).to(dev)                  # noqa: S307
+    if args.load_from.lower() != "none":
+        model.load(args.load_from)
+    if args.fp16:
+        model.half()
+    model.eval()
+    out_dir = f"{args.log_dir}/{folder}/"
+    mkdir_p(out_dir)
+    ds = LPDataset(args.dataset_processed_prefix, MyToBipartite(thresh_num=args.edge_num_thresh), load_meta=True)
+    train_ds, val_ds = split_train_val(ds, args.seed)
+    idxs = list(val_ds.indices()) if args.split == "val" else list(val_ds.indices()) + list(train_ds.indices())
+    mine = [idxs[i] for i in shard_indices(len(idxs), rank, world)]
+    sub = ds[np.asarray(mine, dtype=np.int64)] if mine else None
+    times = {}
+    pool = ThreadPoolExecutor(max_workers=4)
+    futures = []
+    if sub is not None:
+        loader = DataLoader(sub, batch_size=1, shuffle=False, num_workers=args.num_workers)
+        for batch in loader:
+            fn = extract_fn(batch.processed_path[0])
+            status, p1, m = predict_one(model, batch, dev, bool(args.fp16))
+            futures.append(pool.submit(write_bas_highs, f"{out_dir}/{fn}.bas", None, None, status[m:], status[:m]))
+            futures.append(pool.submit(write_sort_vars, f"{out_dir}/{fn}.bas.sort", p1[m:], p1[:m]))
+        # timing pass (pred_basis.py:157-178): model + basis decision per LP, inputs already on the device
+        loader = DataLoader(sub, batch_size=1, shuffle=False, num_workers=args.num_workers)
+        for batch in loader:
+            batch = batch_to(batch, dev, bool(args.fp16))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            inference_only(model, batch)
+            torch.cuda.synchronize()
+            times[extract_fn(batch.processed_path[0])] = time.perf_counter() - t0
+    for f in futures:
+        f.result()
+    pool.shutdown()
+    with open(f"{args.log_dir}/inf_time.rank{rank}.json", "w") as f:
+        json.dump(times, f)
+    if world > 1:
+        torch.distributed.barrier()
+    return times
+
+
+if __name__ == "__main__":
+    logging.basicConfig(level=logging.INFO)
+    run(parse_args())

@@ -1,0 +1,175 @@
+"""Drop-in for the reference ``train.py`` (run_exp, 55-157) with data-parallel training added:
+
+* same loop: one LP graph per step (``DataLoader(batch_size=1)``, train.py:70), ``model(batch)``, loss from
+  ``--loss`` (balanced / unbalanced / focal), Adam/SGD with weight decay 5e-4 and StepLR(epochs//4, 0.1),
+  weights saved to ``{log_dir}/mdl.pth`` every epoch;
+* launched under ``torchrun`` (one process per GPU) every rank trains on its own shard of the LP graphs and the
+  gradients are averaged with ONE NCCL all-reduce of the flattened 16.9 MB gradient bucket per step (the whole
+  model is one bucket) -- effective batch = WORLD_SIZE graphs per optimiser step.
+
+The per-step host syncs of the reference (``isnan(loss).item()``, ``loss.item()``, sklearn accuracy every step,
+train.py:126-137) are reduced to one ``.item()`` every ``--log_every`` steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import logging
+import os
+import time
+
+import numpy as np
+import torch
+from torch.optim.lr_scheduler import StepLR
+
+from .arch import *  # noqa: F401,F403  (``eval(args.arch)`` resolves GCN_FC(...) like the reference, train.py:79)
+from .data import DataLoader
+from .dataset import LPDataset, MyToBipartite
+from .io_utils import shard_indices, split_train_val
+from .losses import LOSSES
+
+
+def dist_info():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init_distributed(backend=None):
+    rank, world, local = dist_info()
+    if world > 1 and not torch.distributed.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29512")
+        backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        torch.distributed.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def broadcast_parameters(model, world):
+    if world > 1:
+        for p in model.parameters():
+            torch.distributed.broadcast(p.data, src=0)
+
+
+def allreduce_gradients(params, world):
+    """Mean of the gradients over ranks with one collective: flatten -> all_reduce(SUM) -> scale -> unflatten.
+    NCCL over NVLink/NVSwitch on the GPU box; gloo in the CPU tests.  Deterministic (fixed bucket layout)."""
+    if world == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM)
+    flat.mul_(1.0 / world)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+def parse_args(argv=None, **defaults):
+    """The flags of ``utils.Environment`` that the training / prediction entry points read (utils.py:743-770)."""
+    ap = argparse.ArgumentParser(conflict_handler="resolve")
+    ap.add_argument("--dev", type=int, default=0)
+    ap.add_argument("--exp_nm", type=str, default="tmp")
+    ap.add_argument("--opt", type=str, default="adam")
+    ap.add_argument("--lr", type=float, default=1e-3)
+    ap.add_argument("--epochs", type=int, default=30)
+    ap.add_argument("--arch", type=str, default="GCN_FC(8,8,hids=128)")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--num_workers", type=int, default=0)
+    ap.add_argument("--load_from", type=str, default="None")
+    ap.add_argument("--dataset", type=str, default="None")
+    ap.add_argument("--solver_prefix", type=str, default="highs-")
+    ap.add_argument("--data_prefix", type=str, default="./lp-dataset/")
+    ap.add_argument("--log_prefix", type=str, default="./runs/")
+    ap.add_argument("--edge_num_thresh", type=float, default=4e6 * 3)
+    ap.add_argument("--loss", type=str, default="balanced")
+    ap.add_argument("--inference_manager", type=str, default="InferenceManager(0,)")
+    ap.add_argument("--split", type=str, default="val")
+    ap.add_argument("--fp16", type=int, default=0)
+    ap.add_argument("--log_every", type=int, default=9)
+    ap.add_argument("--dataset_processed_prefix", type=str, default=None)
+    ap.add_argument("--log_dir", type=str, default=None)
+    ap.set_defaults(**defaults)
+    args, _ = ap.parse_known_args(argv)
+    if args.dataset_processed_prefix is None:       # utils.py:835-836
+        args.dataset_processed_prefix = f"{args.data_prefix}/{args.dataset}/{args.solver_prefix}inp_tgt/"
+    if args.log_dir is None:
+        args.log_dir = f"{args.log_prefix}/{args.exp_nm}/"
+    return args
+
+
+def run_exp(args):
+    rank, world, local = init_distributed()
+    if not torch.cuda.is_available():
+        raise RuntimeError("training needs CUDA devices: the lp-gnn hot path has no CPU fallback")
+    dev = torch.device("cuda", local if world > 1 else args.dev)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(args.seed)
+    np.random.seed(args.seed)
+    os.makedirs(args.log_dir, exist_ok=True)
+    ds = LPDataset(args.dataset_processed_prefix, transform=MyToBipartite(thresh_num=args.edge_num_thresh))
+    train_ds, _ = split_train_val(ds, args.seed)
+    if world > 1:                                    # one shard of LP graphs per GPU
+        train_ds = train_ds[np.asarray(shard_indices(len(train_ds), rank, world))]
+    loader = DataLoader(train_ds, batch_size=1, shuffle=True, drop_last=True, num_workers=args.num_workers,
+                        persistent_workers=args.num_workers > 0, pin_memory=False)
+    model = eval(args.arch)                          # noqa: S307  (the reference's plugin mechanism, train.py:79)
+    if args.load_from.lower() != "none":
+        model.load(args.load_from)
+    model = model.to(dev)
+    if args.fp16:
+        model.half()
+    broadcast_parameters(model, world)
+    params = list(model.parameters())
+    if args.opt == "adam":
+        opt = torch.optim.Adam(params, lr=args.lr, weight_decay=5e-4)
+    else:
+        opt = torch.optim.SGD(params, lr=args.lr, weight_decay=5e-4)
+    scheduler = StepLR(opt, step_size=max(args.epochs // 4, 1), gamma=0.1)
+    loss_fn = LOSSES[args.loss]
+    glstep, history = 0, []
+    steps_per_epoch = len(loader)
+    if world > 1:                                    # every rank must take the same number of optimiser steps
+        t = torch.tensor([steps_per_epoch], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
+        steps_per_epoch = int(t.item())
+    t0 = time.time()
+    for epoch in range(args.epochs):
+        model.train()
+        for it, batch in enumerate(loader):
+            if it >= steps_per_epoch:
+                break
+            if not hasattr(batch, "x_s"):
+                raise NotImplementedError("graphs above edge_num_thresh need the sampled path (SURVEY 8 f-4)")
+            batch.to(dev, non_blocking=True)
+            glstep += 1
+            logit_cons, logit_vars = model(batch)
+            logit_cons, logit_vars = logit_cons[:batch.s_bs], logit_vars[:batch.t_bs]
+            y_s, y_t = batch.y_s[:batch.s_bs], batch.y_t[:batch.t_bs]
+            loss = loss_fn(logit_cons, logit_vars, y_s, y_t)
+            opt.zero_grad()
+            loss.backward()
+            allreduce_gradients(params, world)
+            opt.step()
+            if glstep % args.log_every == 1:
+                lv = float(loss.item())
+                assert not np.isnan(lv)              # train.py:126
+                history.append(dict(epoch=epoch, step=glstep, loss=lv, lr=scheduler.get_last_lr()[0]))
+                if rank == 0:
+                    logging.info(f"{epoch} {it}/{steps_per_epoch} step {glstep} loss {lv:.4f}")
+        scheduler.step()
+        if rank == 0:
+            model.save(f"{args.log_dir}/mdl.pth")
+    torch.cuda.synchronize()
+    if rank == 0:
+        model.save(f"{args.log_dir}/mdl.pth")
+        with open(f"{args.log_dir}/train_log.json", "w") as f:
+            json.dump(dict(history=history, seconds=time.time() - t0, steps=glstep, world=world), f)
+    if world > 1:
+        torch.distributed.barrier()
+    return model, history
+
+
+if __name__ == "__main__":
+    logging.basicConfig(level=logging.INFO)
+    run_exp(parse_args())

@@ -1,0 +1,91 @@
+"""Drop-in for the hot-path parts of the reference ``val.py``: ``inference_gnn`` (106-124),
+``model_inference_with_batch`` (12-36), ``accuracy`` (199-237), ``InferenceManager`` naming (167-197)."""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import torch
+
+from . import ops
+from .io_utils import batch_to
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("inference needs a CUDA (sm_100) device: the lp-gnn hot path has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+@torch.no_grad()
+def inference_gnn(logits, m, **kwargs):
+    """Reference val.py:106-124 on the device: softmax, NaN -> 0, global top-m on P(basic) -> status 1, the rest
+    argmax over {0, 2}.  ``logits`` [m+n,3] (constraints first); CPU inputs are moved to the GPU and the result
+    is returned on the input's device, int64 like the reference."""
+    src_dev = logits.device
+    lg = logits.float()
+    if not lg.is_cuda:
+        lg = lg.to(_device())
+    pred, counts = ops.basis_select(lg[:m], lg[m:], k_basic=m, int64=True, want_counts=True)
+    c = counts.tolist()                                   # one host sync, as the reference's asserts (val.py:118-122)
+    n = logits.shape[0] - m
+    assert c[1] == m, (c, m)                              # #basic == number of rows
+    assert c[3] == m - (c[1] - c[3]), c                   # basic structurals == non-basic rows
+    return pred.to(src_dev)
+
+
+@torch.no_grad()
+def model_inference_with_batch(model, batched_graphs, args=None):
+    """Reference val.py:12-36 for graphs that fit the bipartite full-graph path (every LP below
+    ``edge_num_thresh``); returns CPU logits like the reference."""
+    if not hasattr(batched_graphs, "x_s"):
+        raise NotImplementedError("sampled-subgraph inference (NeighborLoader, reference val.py:22-27) is the f-4 "
+                                  "follow-up row of SURVEY.md section 8; transform the graph with MyToBipartite first")
+    dev = _device()
+    model.eval()
+    batch = batch_to(batched_graphs, dev, bool(getattr(args, "fp16", 0)))
+    logit_cons, logit_vars = model(batch)
+    return logit_cons[:batch.s_bs].cpu(), logit_vars[:batch.t_bs].cpu()
+
+
+@torch.no_grad()
+def accuracy(logits, gt, num_cons, return_pr=False, dataset_name=""):
+    """Reference val.py:199-237: mean of constraint / variable accuracy, macro precision / recall of class 1."""
+    from sklearn import metrics
+    pred = inference_gnn(logits, num_cons)
+    pred_np, gt_np = pred.cpu().numpy(), gt.cpu().numpy()
+    if (pred_np[:num_cons] == 1).all():
+        logging.warning("warning: may collapse, basis==all slacks")
+    acc1 = (gt_np[:num_cons] == pred_np[:num_cons]).mean()
+    acc2 = (gt_np[num_cons:] == pred_np[num_cons:]).mean()
+    stoch = bool(dataset_name) and "stoch" in dataset_name
+    if stoch:
+        acc1 = acc2
+    acc = (acc1 + acc2) / 2.
+    if not return_pr:
+        return acc
+    kw = dict(labels=[1], average="macro", zero_division=0)
+    p1 = metrics.precision_score(gt_np[:num_cons], pred_np[:num_cons], **kw)
+    p2 = metrics.precision_score(gt_np[num_cons:], pred_np[num_cons:], **kw)
+    r1 = metrics.recall_score(gt_np[:num_cons], pred_np[:num_cons], **kw)
+    r2 = metrics.recall_score(gt_np[num_cons:], pred_np[num_cons:], **kw)
+    if stoch:
+        p1, r1 = p2, r2
+    return acc, (p1 + p2) / 2., (r1 + r2) / 2.
+
+
+class InferenceManager:
+    """Reference val.py:167-197 (only ``inference_gnn`` is on the hot path; the other two are marked deprecated
+    upstream, val.py:126)."""
+
+    def __init__(self, which_func=0, mode=None, gnn_wei=None, run=0):
+        self.which_func = ["inference_gnn", "inference_all_slacks", "inference_gnn_sparsity"][which_func]
+        if self.which_func != "inference_gnn":
+            raise NotImplementedError("only InferenceManager(0, ...) (inference_gnn) is supported")
+        self.mode, self.gnn_wei, self.run = mode, gnn_wei, run
+
+    def get_log_folder(self):
+        return f"gnn-bas-{self.run}"
+
+    def get_basis_folder(self):
+        return "pred-basis" + (f"-{self.run}" if self.run != 0 else "")

@@ -1,0 +1,55 @@
+"""N > 1 host logic on CPU: world_size-2 gloo processes run the gradient all-reduce and the LP sharding that the
+multi-GPU training / prediction entry points use (the NCCL path is the same code with another backend)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import arch, io_utils, train
+    r, w, _ = train.init_distributed(backend="gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(100 + rank)                                   # different initial weights per rank
+    model = arch.GCN_FC(8, 8, hids=64, depth=3)
+    train.broadcast_parameters(model, world)                        # -> rank 0's weights everywhere
+    torch.manual_seed(7 + rank)
+    for p in model.parameters():
+        p.grad = torch.randn_like(p)
+    local = [p.grad.clone() for p in model.parameters()]
+    train.allreduce_gradients(list(model.parameters()), world)
+    torch.save(dict(w=[p.detach().clone() for p in model.parameters()], g=[p.grad.clone() for p in model.parameters()],
+                    local=local, shard=io_utils.shard_indices(11, rank, world)), os.path.join(out_dir, f"r{rank}.pt"))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_gloo_broadcast_allreduce_and_sharding(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = (torch.load(tmp_path / f"r{i}.pt") for i in range(world))
+    for a, b in zip(r0["w"], r1["w"]):
+        assert torch.equal(a, b)                                    # broadcast made the replicas identical
+    for g0, g1, l0, l1 in zip(r0["g"], r1["g"], r0["local"], r1["local"]):
+        assert torch.equal(g0, g1)                                  # every rank holds the same averaged gradient
+        assert torch.allclose(g0, (l0 + l1) / 2, atol=1e-6)
+    assert sorted(r0["shard"] + r1["shard"]) == list(range(11)) and not set(r0["shard"]) & set(r1["shard"])

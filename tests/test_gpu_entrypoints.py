@@ -1,0 +1,107 @@
+"""The reference's entry points end to end on the GPU: dataset files -> train.run_exp -> mdl.pth ->
+pred_basis.run -> HiGHS .bas files, and val.inference_gnn / accuracy on CPU-resident logits like the callers use."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dataset_root(tmp_path_factory):
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import dataset
+    root = str(tmp_path_factory.mktemp("lpds"))
+    dataset.write_synthetic_dataset(root, [(150 + 10 * i, 320 + 20 * i, 1500 + 100 * i) for i in range(8)], seed=2)
+    return root
+
+
+def test_train_then_predict_basis_files(cuda, dataset_root, tmp_path):
+    from lpgnn_b200 import arch, dataset, pred_basis, train
+    from lpgnn_b200.io_utils import split_train_val
+    log_dir = str(tmp_path / "run") + "/"
+    args = train.parse_args([], arch="GCN_FC(8,8,hids=64,depth=3)", epochs=3, lr=1e-3, loss="balanced",
+                            dataset_processed_prefix=dataset_root, log_dir=log_dir, num_workers=0, log_every=1)
+    model, history = train.run_exp(args)
+    assert os.path.exists(log_dir + "mdl.pth") and len(history) >= 10
+    assert all(np.isfinite(h["loss"]) for h in history)
+    assert np.mean([h["loss"] for h in history[-5:]]) < np.mean([h["loss"] for h in history[:5]])
+    # prediction sweep with the saved weights
+    args2 = train.parse_args([], arch="GCN_FC(8,8,hids=64,depth=3)", load_from=log_dir + "mdl.pth",
+                             dataset_processed_prefix=dataset_root, log_dir=log_dir, split="val", num_workers=0)
+    times = pred_basis.run(args2)
+    ds = dataset.LPDataset(dataset_root, dataset.MyToBipartite(), load_meta=True)
+    _, val_ds = split_train_val(ds, 0)
+    assert len(times) == len(val_ds) == 3 and all(t > 0 for t in times.values())
+    # check every .bas file against the oracle run with the same weights
+    ref = port.PortGCN_FC(8, 8, hids=64, depth=3).eval()
+    ref.load_state_dict(torch.load(log_dir + "mdl.pth"))
+    for i in val_ds.indices():
+        uni = ds.get(i)
+        fn = os.path.basename(uni.processed_path).replace(".pk", "")
+        lines = open(f"{log_dir}/pred-basis/{fn}.bas").read().splitlines()
+        g = port.to_bipartite(uni.edge_index.numpy(), uni.edge_attr.numpy(), uni.is_vars.numpy())
+        m, n = g.m, g.n
+        assert lines[:3] == ["HIGHS v1", "Valid", f"# Columns {n}"] and lines[4] == f"# Rows {m}"
+        vbas = np.array(lines[3].split(), dtype=np.int64)
+        cbas = np.array(lines[5].split(), dtype=np.int64)
+        assert vbas.shape == (n,) and cbas.shape == (m,) and int((vbas == 1).sum() + (cbas == 1).sum()) == m
+        with torch.no_grad():
+            lc, lv = ref(uni.x[:m], uni.x[m:], port.TorchGraph(g))
+        exp = port.inference_gnn_np(torch.cat((lc, lv)).numpy(), m)
+        agree = np.mean(np.concatenate([cbas, vbas]) == exp)
+        assert agree >= 0.995, agree
+        assert os.path.exists(f"{log_dir}/pred-basis/{fn}.bas.sort")
+
+
+def test_val_inference_gnn_and_accuracy_accept_cpu_logits(cuda):
+    """pred_basis.py:81-85 and train.py:132-137 hand CPU / detached logits to inference_gnn / accuracy."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import val
+    rng = np.random.default_rng(0)
+    m, n = 300, 700
+    logits = torch.from_numpy((rng.standard_normal((m + n, 3)) * 3).astype(np.float32))
+    pred = val.inference_gnn(logits, m)
+    assert pred.device.type == "cpu" and pred.dtype == torch.int64
+    np.testing.assert_array_equal(pred.numpy(), port.inference_gnn_np(logits.numpy(), m))
+    gt = torch.from_numpy(rng.integers(0, 3, m + n))
+    acc, prec, recl = val.accuracy(logits, gt, m, return_pr=True)
+    exp = port.inference_gnn_np(logits.numpy(), m)
+    exp_acc = ((exp[:m] == gt.numpy()[:m]).mean() + (exp[m:] == gt.numpy()[m:]).mean()) / 2
+    assert abs(acc - exp_acc) < 1e-12 and 0 <= prec <= 1 and 0 <= recl <= 1
+
+
+def test_model_inference_with_batch_and_half_switch(cuda, dataset_root):
+    from lpgnn_b200 import arch, dataset, val
+    ds = dataset.LPDataset(dataset_root, dataset.MyToBipartite())
+    batch = ds[0]
+    torch.manual_seed(0)
+    model = arch.GCN_FC(8, 8, hids=128, depth=3).to(cuda)
+    lc, lv = val.model_inference_with_batch(model, batch, types.SimpleNamespace(fp16=0, arch="GCN_FC(8,8,hids=128,depth=3)"))
+    assert lc.device.type == "cpu" and lc.shape == (batch.s_bs, 3) and lv.shape == (batch.t_bs, 3)
+    batch.edge_index.check()
+    model.half()
+    lc2, lv2 = val.model_inference_with_batch(model, ds[0], types.SimpleNamespace(fp16=1))
+    assert float((lc2 - lc).norm() / lc.norm()) < 2e-2
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_data_parallel_training_matches_single_process(cuda, dataset_root, tmp_path):
+    """torchrun-style 2-rank NCCL training: replicas stay identical and the loss goes down."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    log_dir = str(tmp_path / "ddp") + "/"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tests", "ddp_train_entry.py"), dataset_root, log_dir]
+    out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert os.path.exists(log_dir + "mdl.pth")
+    import json
+    log = json.load(open(log_dir + "train_log.json"))
+    assert log["world"] == 2 and log["history"][-1]["loss"] < log["history"][0]["loss"]

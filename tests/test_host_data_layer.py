@@ -1,0 +1,128 @@
+"""Host-side data layer (no GPU): processed-file format, LPDataset.get / MyToBipartite against the oracle's
+restatement of reference dataset.py:229-332, loaders, split, writers, sharding."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import data, dataset, io_utils, pred_basis, synth, train
+    return dict(data=data, dataset=dataset, io=io_utils, pred=pred_basis, synth=synth, train=train)
+
+
+def test_msgpack_numpy_roundtrip(pkg, tmp_path):
+    io = pkg["io"]
+    obj = [np.arange(5, dtype=np.int64), np.linspace(0, 1, 7).astype(np.float32).reshape(7, 1), 12, "name",
+           {"k": np.float64(3.5)}, [np.array([True, False])]]
+    fn = tmp_path / "x.pk"
+    io.msgpack_dump(obj, fn)
+    back = io.msgpack_load(fn)
+    np.testing.assert_array_equal(back[0], obj[0])
+    assert back[0].dtype == np.int64 and back[1].dtype == np.float32 and back[1].shape == (7, 1)
+    assert back[2] == 12 and back[3] == "name" and float(back[4]["k"]) == 3.5
+    # the msgpack_numpy wire format: a map with nd/type/shape/data keys
+    import msgpack
+    raw = msgpack.unpackb(open(fn, "rb").read(), raw=True, strict_map_key=False)
+    assert set(raw[0].keys()) == {b"nd", b"type", b"kind", b"shape", b"data"} and raw[0][b"nd"] is True
+
+
+def test_dataset_get_and_to_bipartite_match_oracle(pkg, tmp_path):
+    ds_mod, synth = pkg["dataset"], pkg["synth"]
+    root = str(tmp_path / "ds")
+    ds_mod.write_synthetic_dataset(root, [(60, 130, 500), (200, 350, 1500), (5, 9, 20)], seed=3)
+    ds = ds_mod.LPDataset(root, transform=ds_mod.MyToBipartite(thresh_num=np.inf), load_meta=True)
+    assert len(ds) == 3 and ds.processed_file_names == ["lp0.pk", "lp1.pk", "lp2.pk"]
+    for i in range(3):
+        uni = ds.get(i)
+        lp = synth.processed_lp(*[(60, 130, 500), (200, 350, 1500), (5, 9, 20)][i], seed=3 * 100_003 + i)
+        ei, ea = port.unipartite_edges(lp.row, lp.col, lp.a_data, lp.m)            # dataset.py:250-252
+        np.testing.assert_array_equal(uni.edge_index.numpy(), ei)
+        np.testing.assert_array_equal(uni.edge_attr.numpy(), ea)
+        assert uni.num_nodes == lp.m + lp.n and int(uni.is_vars.sum()) == lp.n
+        ref = port.to_bipartite(ei, ea, uni.is_vars.numpy())                        # dataset.py:283-304
+        batch = ds[i]
+        g = batch.edge_index
+        assert g.sparse_sizes() == (lp.m, lp.n) and g.nnz() == lp.nnz and not g.is_cuda and g._sorted_hint
+        r, c, v = g._coo
+        np.testing.assert_array_equal(c.numpy(), ref.col.astype(np.int32))
+        np.testing.assert_array_equal(v.numpy(), ref.val)
+        np.testing.assert_array_equal(r.numpy(), np.repeat(np.arange(lp.m), np.diff(ref.rowptr)).astype(np.int32))
+        np.testing.assert_array_equal(batch.x_s.numpy(), lp.c_feas)
+        np.testing.assert_array_equal(batch.x_t.numpy(), lp.v_feas)
+        np.testing.assert_array_equal(batch.y_t.numpy(), lp.y_t)
+        assert (batch.s_bs, batch.t_bs, batch.bs) == (lp.m, lp.n, lp.m + lp.n)
+        assert not hasattr(batch, "x") and not hasattr(batch, "is_vars") and not hasattr(batch, "edge_attr")
+        assert batch.con_nms[:2] == ["c0", "c1"]
+
+
+def test_golden_unipartite_graph_through_product_transform(pkg):
+    """The reference's own unipartite tensors (golden) through the product's MyToBipartite."""
+    ds_mod, data = pkg["dataset"], pkg["data"]
+    z = np.load(os.path.join(GOLD, "graph_small_300x600.npz"))
+    m, n = int(z["m"]), int(z["n"])
+    uni = data.Data(x=torch.zeros(m + n, 8), y=torch.zeros(m + n, dtype=torch.long), is_vars=torch.from_numpy(z["is_vars"]),
+                    edge_index=torch.from_numpy(z["uni_edge_index"]), edge_attr=torch.from_numpy(z["uni_edge_attr"]),
+                    num_nodes=m + n)
+    batch = ds_mod.MyToBipartite()(uni)
+    r, c, v = batch.edge_index._coo
+    np.testing.assert_array_equal(c.numpy(), z["col"].astype(np.int32))
+    np.testing.assert_array_equal(v.numpy().view(np.uint32), z["val"].view(np.uint32))
+    assert (batch.s_bs, batch.t_bs) == (int(z["s_bs"]), int(z["t_bs"]))
+
+
+def test_loader_split_and_process(pkg, tmp_path):
+    ds_mod, data, io = pkg["dataset"], pkg["data"], pkg["io"]
+    root = str(tmp_path / "ds")
+    ds_mod.write_synthetic_dataset(root, [(20 + i, 50 + i, 120) for i in range(10)], seed=1)
+    ds = ds_mod.LPDataset(root, transform=ds_mod.MyToBipartite())
+    tr, va = io.split_train_val(ds, seed=0)
+    assert len(tr) == 7 and len(va) == 3 and sorted(list(tr.indices()) + list(va.indices())) == list(range(10))
+    np.random.seed(0)
+    perm = np.random.permutation(10)                                   # utils.py:259-262 semantics
+    assert list(tr.indices()) == sorted(perm[:7].tolist())
+    loader = data.DataLoader(va, batch_size=1, shuffle=False, num_workers=0)
+    names = [b.processed_path[0] for b in loader]
+    assert len(names) == 3 and all(isinstance(b, str) for b in names)
+    # raw -> processed (LPDataset.process) on a raw LP with names/labels
+    synth = pkg["synth"]
+    raw_root = str(tmp_path / "raw_ds")
+    os.makedirs(os.path.join(raw_root, "raw"))
+    c, b_l, A, b_u, l, u = synth.raw_lp(30, 70, 200, seed=4)
+    coo = A.tocoo()
+    io.msgpack_dump([c, b_l, (coo.row, coo.col, coo.data), b_u, l, u, np.ones(30, dtype=np.int64), np.ones(70, dtype=np.int64),
+                     [f"r{i}" for i in range(30)], [f"v{i}" for i in range(70)]], os.path.join(raw_root, "raw", "a.pk"))
+    ds2 = ds_mod.LPDataset(raw_root, transform=ds_mod.MyToBipartite(), load_meta=True)
+    ds2.process()
+    b = ds2[0]
+    assert b.x_s.shape == (30, 8) and b.x_t.shape == (70, 8) and b.var_nms[0] == "v0"
+    assert float(b.x_s.abs().max()) <= 1.0
+
+
+def test_bas_writers_and_extract_fn(pkg, tmp_path):
+    pred, io = pkg["pred"], pkg["io"]
+    fn = tmp_path / "out" / "lp7.bas"
+    pred.write_bas_highs(str(fn), None, None, np.array([1, 0, 2, 1], dtype=np.uint8), np.array([0, 1], dtype=np.uint8))
+    assert open(fn).read() == "HIGHS v1\nValid\n# Columns 4\n1 0 2 1\n# Rows 2\n0 1\n"     # pred_basis.py:19-23
+    pred.write_sort_vars(str(fn) + ".sort", np.array([0.5, 0.25], dtype=np.float32), np.array([0.125], dtype=np.float32))
+    assert open(str(fn) + ".sort").read().splitlines()[0] == "2 "
+    assert io.extract_fn("/a/b/lp7.mps.gz") == "lp7" and io.extract_fn("x.y.pk") == "x.y"
+
+
+def test_shard_indices_partition(pkg):
+    io = pkg["io"]
+    for world in (1, 2, 3, 8):
+        parts = [io.shard_indices(37, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(37))
+        w = np.random.default_rng(0).integers(1, 1000, 37)
+        parts = [io.shard_indices(37, r, world, weights=w) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(37))
+        loads = [w[p].sum() for p in parts]
+        assert max(loads) - min(loads) <= w.max()                       # LPT balance
