@@ -115,6 +115,13 @@ LPGNN_API int lpgnn_spmm(const int32_t* ptr, const int32_t* idx, const float* va
  * the weight gradient of this layer needs (lpgnn_small_wgrad).
  * ------------------------------------------------------------------------------------------- */
 LPGNN_API int32_t lpgnn_conv_in_zcat_width(int32_t k_src, int32_t k_dst);
+/* The gather half alone: z_cat (f32 [rows,KT], optional) and/or z_bf16 (bf16 [rows,64], zero-padded,
+ * optional).  In bf16 mode the input layer is gather_cat -> lpgnn_node_transform(z_bf16, [W_rel|W_root|0]
+ * as bf16 [N,64]): the tensor-core kernel with a single K block, bound by its epilogue (the output
+ * write), which is ~4x faster than the CUDA-core transform. */
+LPGNN_API int lpgnn_gather_cat(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,
+                     const float* Xsrc, int32_t k_src, const float* Xdst, int32_t k_dst,
+                     float* z_cat, void* z_bf16, lpgnn_stream_t stream);
 LPGNN_API int lpgnn_conv_in_fused(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,
                         const float* Xsrc, int32_t k_src, const float* Xdst, int32_t k_dst,
                         const float* W_rel, const float* b_rel, const float* W_root, int32_t N,

@@ -44,8 +44,37 @@ def _conv_hidden_infer(conv, left, right, csr, csc, relu):
     return left_new, right_new
 
 
+def wcat_bf16(conv_cache, gc):
+    """[W_rel | W_root | 0] as bf16 [N,64] (cached per parameter version): B operand of the bf16 input layer."""
+    key = ("wcat", id(gc))
+    ver = (gc.lin_rel.weight._version, gc.lin_root.weight._version, gc.lin_rel.weight.device)
+    hit = conv_cache._c.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    w_rel, w_root = gc.lin_rel.weight.detach(), gc.lin_root.weight.detach()
+    w = torch.zeros((w_rel.shape[0], 64), dtype=torch.bfloat16, device=w_rel.device)
+    w[:, :w_rel.shape[1]] = w_rel
+    w[:, w_rel.shape[1]:w_rel.shape[1] + w_root.shape[1]] = w_root
+    conv_cache._c[key] = (ver, w)
+    return w
+
+
+def conv_in_bf16(conv, x_left, x_right, csr, csc, relu, want_f32=False):
+    """bf16 input layer: gather_cat (fp32 accumulate, bf16 out) -> tensor-core transform with one K block."""
+    l2r, r2l = conv.left2right, conv.right2left
+    z32_t, zb_t = ops.gather_cat(csc, x_left, x_right, want_f32=want_f32, want_bf16=True)
+    z32_s, zb_s = ops.gather_cat(csr, x_right, x_left, want_f32=want_f32, want_bf16=True)
+    right_new = ops.node_transform(zb_t, wcat_bf16(conv._cache, l2r), bias=l2r.lin_rel.bias.detach(), relu=relu)
+    left_new = ops.node_transform(zb_s, wcat_bf16(conv._cache, r2l), bias=r2l.lin_rel.bias.detach(), relu=relu)
+    return left_new, right_new, z32_s, z32_t
+
+
 def _conv_in_infer(conv, x_left, x_right, csr, csc, dt, relu):
     l2r, r2l = conv.left2right, conv.right2left
+    k_tot = l2r.in_channels[0] + l2r.in_channels[1]
+    if dt == torch.bfloat16 and k_tot <= 64 and l2r.out_channels % 64 == 0:
+        left_new, right_new, _, _ = conv_in_bf16(conv, x_left, x_right, csr, csc, relu)
+        return left_new, right_new
     right_new, _ = ops.conv_in_fused(csc, x_left, x_right, l2r.lin_rel.weight.detach(), l2r.lin_rel.bias.detach(),
                                      l2r.lin_root.weight.detach(), dt, relu=relu)
     left_new, _ = ops.conv_in_fused(csr, x_right, x_left, r2l.lin_rel.weight.detach(), r2l.lin_rel.bias.detach(),

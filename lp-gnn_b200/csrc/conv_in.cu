@@ -27,14 +27,15 @@ template <int KT>
 __global__ void __launch_bounds__(kThreads)
 gather_cat_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ val,
                   int32_t rows, const float* __restrict__ Xsrc, int k_src, const float* __restrict__ Xdst, int k_dst,
-                  float* __restrict__ z) {
+                  float* __restrict__ z, __nv_bfloat16* __restrict__ zb /*[rows,64] or null*/) {
   const int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const int64_t row = p >> 3;
   const int f0 = (int)(p & 7);
   if (row >= rows) return;
   const int K = k_src + k_dst;
   const int32_t beg = ptr[row], end = ptr[row + 1];
-  float* zr = z + row * KT;
+  float* zr = z ? z + row * KT : nullptr;
+  __nv_bfloat16* zbr = zb ? zb + row * 64 : nullptr;
   for (int k = f0; k < k_src; k += 8) {
     float v = 0.f;
     int32_t e = beg;
@@ -46,10 +47,16 @@ gather_cat_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ i
       v = fmaf(w0, x0, v); v = fmaf(w1, x1, v); v = fmaf(w2, x2, v); v = fmaf(w3, x3, v);   // CSR order
     }
     for (; e < end; ++e) v = fmaf(__ldg(val + e), __ldg(Xsrc + (int64_t)__ldg(idx + e) * k_src + k), v);
-    zr[k] = v;
+    if (zr) zr[k] = v;
+    if (zbr) zbr[k] = __float2bfloat16_rn(v);
   }
-  for (int k = f0; k < k_dst; k += 8) zr[k_src + k] = __ldg(Xdst + row * k_dst + k);
-  for (int k = K + f0; k < KT; k += 8) zr[k] = 0.f;
+  for (int k = f0; k < k_dst; k += 8) {
+    const float v = __ldg(Xdst + row * k_dst + k);
+    if (zr) zr[k_src + k] = v;
+    if (zbr) zbr[k_src + k] = __float2bfloat16_rn(v);
+  }
+  if (zr) for (int k = K + f0; k < KT; k += 8) zr[k] = 0.f;
+  if (zbr) for (int k = K + f0; k < 64; k += 8) zbr[k] = __float2bfloat16_rn(0.f);
 }
 
 // ---- kernel 2: out[r, c] = epi(b[c] + sum_k z[r][k] * Wcat[c][k]).  Block = 64 rows x 512 columns; a thread
@@ -109,7 +116,7 @@ int launch(const int32_t* ptr, const int32_t* idx, const float* val, int32_t row
            const float* Xdst, int k_dst, const float* W_rel, const float* b_rel, const float* W_root, int N,
            void* out, int out_dtype, int relu, float* z, cudaStream_t st) {
   gather_cat_kernel<KT><<<ceil_div((int64_t)rows * 8, kThreads), kThreads, 0, st>>>(ptr, idx, val, rows, Xsrc, k_src,
-                                                                                   Xdst, k_dst, z);
+                                                                                   Xdst, k_dst, z, nullptr);
   dim3 grid(ceil_div(N, kColsPerBlock), ceil_div(rows, kRows));
   if (out_dtype == LPGNN_F32)
     small_k_transform_kernel<KT, float><<<grid, kThreads, 0, st>>>(z, rows, W_rel, k_src, W_root, k_dst, b_rel, N,
@@ -130,6 +137,25 @@ using namespace lpgnn;
 extern "C" int32_t lpgnn_conv_in_zcat_width(int32_t k_src, int32_t k_dst) {
   const int K = k_src + k_dst;
   return K <= 16 ? 16 : (K <= 32 ? 32 : 64);
+}
+
+extern "C" int lpgnn_gather_cat(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,
+                                const float* Xsrc, int32_t k_src, const float* Xdst, int32_t k_dst, float* z_cat,
+                                void* z_bf16, lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(rows >= 0 && k_src >= 1 && k_dst >= 0 && k_src + k_dst <= 64, "gather_cat: bad shape");
+  if (rows == 0) return LPGNN_OK;
+  LPGNN_REQUIRE(ptr && Xsrc && (z_cat || z_bf16) && (k_dst == 0 || Xdst), "gather_cat: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int KT = lpgnn_conv_in_zcat_width(k_src, k_dst);
+  const int grid = ceil_div((int64_t)rows * 8, kThreads);
+  __nv_bfloat16* zb = reinterpret_cast<__nv_bfloat16*>(z_bf16);
+  if (KT == 16) gather_cat_kernel<16><<<grid, kThreads, 0, st>>>(ptr, idx, val, rows, Xsrc, k_src, Xdst, k_dst, z_cat, zb);
+  else if (KT == 32) gather_cat_kernel<32><<<grid, kThreads, 0, st>>>(ptr, idx, val, rows, Xsrc, k_src, Xdst, k_dst, z_cat, zb);
+  else gather_cat_kernel<64><<<grid, kThreads, 0, st>>>(ptr, idx, val, rows, Xsrc, k_src, Xdst, k_dst, z_cat, zb);
+  LPGNN_LAUNCH_OK();
+  count_launches(1);
+  return LPGNN_OK;
 }
 
 extern "C" int lpgnn_conv_in_fused(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,

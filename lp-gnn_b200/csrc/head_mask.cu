@@ -87,69 +87,86 @@ head_mask_kernel(const T* __restrict__ H, int32_t rows, int32_t Hdim, const floa
   }
 }
 
-// Fast path: the three weight rows live in REGISTERS (lane l owns 16-byte chunks l, l+32, ...), so the
-// inner loop is one 128-bit load per chunk plus FMAs -- no shared-memory traffic (the shared-memory
-// version above is bank-conflict bound: every lane reads a different 32-byte slice of the weights).
+// Fast path.  Weights are staged in shared memory in a lane-major layout
+//   ws[((j*CH + c)*E + k)*32 + lane] = W[j][(lane + 32*c)*E + k]
+// so every weight read is a conflict-free LDS (the row-major layout of the generic kernel above is
+// bank-conflict bound: lanes read 32-byte-strided slices).  A warp handles TWO adjacent rows per
+// iteration, sharing each weight read between them and keeping 2*CH 128-bit loads in flight per lane;
+// registers stay low enough for 24+ resident warps per SM.
 template <typename T, int CH>
-__global__ void __launch_bounds__(kRegThreads)
-head_mask_reg_kernel(const T* __restrict__ H, int32_t rows, int32_t Hdim, const float* __restrict__ W,
-                     const float* __restrict__ b, const float* __restrict__ feas, int q, float* __restrict__ logits,
-                     float* __restrict__ raw_out) {
+__global__ void __launch_bounds__(kThreads)
+head_mask_fast_kernel(const T* __restrict__ H, int32_t rows, int32_t Hdim, const float* __restrict__ W,
+                      const float* __restrict__ b, const float* __restrict__ feas, int q, float* __restrict__ logits,
+                      float* __restrict__ raw_out) {
   constexpr int E = 16 / sizeof(T);
+  __shared__ float ws[3 * CH * E * 32];
   const int lane = threadIdx.x & 31;
   const int chunks = Hdim / E;
-  float w[3][CH][E];
-#pragma unroll
-  for (int c = 0; c < CH; ++c) {
-    const int ch = lane + 32 * c;
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-#pragma unroll
-      for (int k = 0; k < E; ++k) w[j][c][k] = (ch < chunks) ? __ldg(W + (int64_t)j * Hdim + ch * E + k) : 0.f;
+  for (int i = threadIdx.x; i < 3 * CH * E * 32; i += kThreads) {
+    const int l = i & 31, k = (i >> 5) % E, c = ((i >> 5) / E) % CH, j = (i >> 5) / (E * CH);
+    const int ch = l + 32 * c;
+    ws[i] = (ch < chunks) ? __ldg(W + (int64_t)j * Hdim + ch * E + k) : 0.f;
   }
+  __syncthreads();
   const float b0 = __ldg(b), b1 = __ldg(b + 1), b2 = __ldg(b + 2);
-  const int warps_total = gridDim.x * (kRegThreads / 32);
-  for (int64_t row = blockIdx.x * (kRegThreads / 32) + (threadIdx.x >> 5); row < rows; row += warps_total) {
-    const uint4* hrow = reinterpret_cast<const uint4*>(H + row * Hdim);
-    uint4 v[CH];
+  const int warps_total = gridDim.x * (kThreads / 32);
+  for (int64_t row = 2 * (blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)); row < rows; row += 2 * warps_total) {
+    const bool has1 = row + 1 < rows;
+    const uint4* hrow0 = reinterpret_cast<const uint4*>(H + row * Hdim);
+    const uint4* hrow1 = reinterpret_cast<const uint4*>(H + (row + (has1 ? 1 : 0)) * Hdim);
+    uint4 v0[CH], v1[CH];
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int ch = lane + 32 * c;
-      v[c] = (ch < chunks) ? __ldg(hrow + ch) : make_uint4(0, 0, 0, 0);
+      v0[c] = (ch < chunks) ? __ldg(hrow0 + ch) : make_uint4(0, 0, 0, 0);
+      v1[c] = (ch < chunks) ? __ldg(hrow1 + ch) : make_uint4(0, 0, 0, 0);
     }
-    // the two mask tags are fetched by lanes 0/1 alongside the row, not after the reduction
+    // the mask tags are fetched by lanes 0..3 alongside the rows, not after the reduction
     float tag = 0.f;
-    if (lane == 0) tag = __ldg(feas + row * q + (q - 3));
-    if (lane == 1) tag = __ldg(feas + row * q + (q - 1));
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (lane < 4) {
+      const int64_t r = row + (((lane >> 1) && has1) ? 1 : 0);
+      tag = __ldg(feas + r * q + ((lane & 1) ? (q - 1) : (q - 3)));
+    }
+    float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-      float x[E];
+      float x[E], y[E];
       if constexpr (sizeof(T) == 4) {
-        x[0] = __uint_as_float(v[c].x); x[1] = __uint_as_float(v[c].y);
-        x[2] = __uint_as_float(v[c].z); x[3] = __uint_as_float(v[c].w);
+        x[0] = __uint_as_float(v0[c].x); x[1] = __uint_as_float(v0[c].y);
+        x[2] = __uint_as_float(v0[c].z); x[3] = __uint_as_float(v0[c].w);
+        y[0] = __uint_as_float(v1[c].x); y[1] = __uint_as_float(v1[c].y);
+        y[2] = __uint_as_float(v1[c].z); y[3] = __uint_as_float(v1[c].w);
       } else {
-        x[0] = bf16_lo(v[c].x); x[1] = bf16_hi(v[c].x); x[2] = bf16_lo(v[c].y); x[3] = bf16_hi(v[c].y);
-        x[4] = bf16_lo(v[c].z); x[5] = bf16_hi(v[c].z); x[6] = bf16_lo(v[c].w); x[7] = bf16_hi(v[c].w);
+        x[0] = bf16_lo(v0[c].x); x[1] = bf16_hi(v0[c].x); x[2] = bf16_lo(v0[c].y); x[3] = bf16_hi(v0[c].y);
+        x[4] = bf16_lo(v0[c].z); x[5] = bf16_hi(v0[c].z); x[6] = bf16_lo(v0[c].w); x[7] = bf16_hi(v0[c].w);
+        y[0] = bf16_lo(v1[c].x); y[1] = bf16_hi(v1[c].x); y[2] = bf16_lo(v1[c].y); y[3] = bf16_hi(v1[c].y);
+        y[4] = bf16_lo(v1[c].z); y[5] = bf16_hi(v1[c].z); y[6] = bf16_lo(v1[c].w); y[7] = bf16_hi(v1[c].w);
       }
 #pragma unroll
       for (int k = 0; k < E; ++k) {
-        a0 = fmaf(x[k], w[0][c][k], a0);
-        a1 = fmaf(x[k], w[1][c][k], a1);
-        a2 = fmaf(x[k], w[2][c][k], a2);
+        const float w0 = ws[((0 * CH + c) * E + k) * 32 + lane];
+        const float w1 = ws[((1 * CH + c) * E + k) * 32 + lane];
+        const float w2 = ws[((2 * CH + c) * E + k) * 32 + lane];
+        a[0] = fmaf(x[k], w0, a[0]); a[1] = fmaf(x[k], w1, a[1]); a[2] = fmaf(x[k], w2, a[2]);
+        a[3] = fmaf(y[k], w0, a[3]); a[4] = fmaf(y[k], w1, a[4]); a[5] = fmaf(y[k], w2, a[5]);
       }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, off);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, off);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, off);
-    }
-    const float tag_up = __shfl_sync(0xffffffffu, tag, 1);
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int j = 0; j < 6; ++j) a[j] += __shfl_xor_sync(0xffffffffu, a[j], off);
+    const float t_up0 = __shfl_sync(0xffffffffu, tag, 1);
+    const float t_lo1 = __shfl_sync(0xffffffffu, tag, 2);
+    const float t_up1 = __shfl_sync(0xffffffffu, tag, 3);
     if (lane == 0) {
-      a0 += b0; a1 += b1; a2 += b2;
-      if (raw_out) { raw_out[row * 3] = a0; raw_out[row * 3 + 1] = a1; raw_out[row * 3 + 2] = a2; }
-      finish_row_tags(a0, a1, a2, tag, tag_up, row, logits);
+      const float r0 = a[0] + b0, r1 = a[1] + b1, r2 = a[2] + b2;
+      if (raw_out) { raw_out[row * 3] = r0; raw_out[row * 3 + 1] = r1; raw_out[row * 3 + 2] = r2; }
+      finish_row_tags(r0, r1, r2, tag, t_up0, row, logits);
+    }
+    if (lane == 1 && has1) {
+      const float r0 = a[3] + b0, r1 = a[4] + b1, r2 = a[5] + b2;
+      if (raw_out) { raw_out[(row + 1) * 3] = r0; raw_out[(row + 1) * 3 + 1] = r1; raw_out[(row + 1) * 3 + 2] = r2; }
+      finish_row_tags(r0, r1, r2, t_lo1, t_up1, row + 1, logits);
     }
   }
 }
@@ -157,9 +174,9 @@ head_mask_reg_kernel(const T* __restrict__ H, int32_t rows, int32_t Hdim, const 
 template <typename T, int CH>
 void launch_reg(const void* H, int32_t rows, int32_t Hdim, const float* W, const float* b, const float* feas, int q,
                 float* logits, float* raw_out, cudaStream_t st) {
-  const int grid = min(ceil_div(rows, kRegThreads / 32), sm_count() * 16);
-  head_mask_reg_kernel<T, CH><<<grid, kRegThreads, 0, st>>>(reinterpret_cast<const T*>(H), rows, Hdim, W, b, feas, q,
-                                                         logits, raw_out);
+  const int grid = min(ceil_div(rows, 2 * (kThreads / 32)), sm_count() * 4);
+  head_mask_fast_kernel<T, CH><<<grid, kThreads, 0, st>>>(reinterpret_cast<const T*>(H), rows, Hdim, W, b, feas, q,
+                                                          logits, raw_out);
 }
 
 __global__ void add_knowledge_kernel(const float* __restrict__ in, int32_t rows, const float* __restrict__ feas,

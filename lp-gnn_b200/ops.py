@@ -54,6 +54,23 @@ def conv_in_fused(view, x_src, x_dst, w_rel, b_rel, w_root, out_dtype, relu=True
     return out, z_cat
 
 
+def gather_cat(view, x_src, x_dst, want_f32=True, want_bf16=False):
+    """``z = [A_view @ x_src | x_dst | 0]``: fp32 ``[rows,KT]`` and/or bf16 ``[rows,64]`` (input of the
+    tensor-core transform in bf16 mode)."""
+    ptr_, idx, val, rows = view
+    require_cuda(ptr_, x_src, x_dst)
+    x_src, x_dst = _contig(x_src.float()), _contig(x_dst.float())
+    lib = _lib.load()
+    kt = lib.lpgnn_conv_in_zcat_width(x_src.shape[1], x_dst.shape[1])
+    z32 = torch.empty((rows, kt), dtype=torch.float32, device=x_src.device) if want_f32 else None
+    zb = torch.empty((rows, 64), dtype=torch.bfloat16, device=x_src.device) if want_bf16 else None
+    with torch.cuda.device(x_src.device):
+        rc = lib.lpgnn_gather_cat(ptr_.data_ptr(), idx.data_ptr(), val.data_ptr(), rows, x_src.data_ptr(), x_src.shape[1],
+                                  x_dst.data_ptr(), x_dst.shape[1], ptr(z32), ptr(zb), stream_ptr())
+    check(rc, "lpgnn_gather_cat")
+    return z32, zb
+
+
 def node_transform(a1, w1, a2=None, w2=None, bias=None, relu=False, out_dtype=None) -> torch.Tensor:
     """``epi(a1 @ w1.T + a2 @ w2.T + bias)``: bf16 operands -> tcgen05 kernel, fp32 -> CUDA-core
     kernel.  Replaces ``lin_rel(agg) + lin_root(x_dst)`` (+ relu_) (reference arch.py:75-80, 188)."""

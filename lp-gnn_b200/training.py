@@ -45,9 +45,22 @@ class _GCNFCFunction(torch.autograd.Function):
         P = [p.detach() for p in params]
         cast = (lambda w: w.to(dt)) if dt != torch.float32 else (lambda w: w)
         x_s, x_t = x_s.float().contiguous(), x_t.float().contiguous()
-        # conv1 (p,q -> H), relu fused
-        right, z_t = ops.conv_in_fused(csc, x_s, x_t, P[0], P[1], P[2], dt, relu=True)
-        left, z_s = ops.conv_in_fused(csr, x_t, x_s, P[3], P[4], P[5], dt, relu=True)
+        # conv1 (p,q -> H), relu fused.  bf16 mode: gather -> tensor-core transform over one zero-padded K block
+        # (same arithmetic as the inference path); fp32 mode: CUDA-core fused kernel.
+        if dt == torch.bfloat16 and x_s.shape[1] + x_t.shape[1] <= 64 and P[0].shape[0] % 64 == 0:
+            def wcat(w_rel, w_root):
+                w = torch.zeros((w_rel.shape[0], 64), dtype=dt, device=w_rel.device)
+                w[:, :w_rel.shape[1]] = w_rel
+                w[:, w_rel.shape[1]:w_rel.shape[1] + w_root.shape[1]] = w_root
+                return w
+            z_t, zb_t = ops.gather_cat(csc, x_s, x_t, want_f32=True, want_bf16=True)
+            z_s, zb_s = ops.gather_cat(csr, x_t, x_s, want_f32=True, want_bf16=True)
+            right = ops.node_transform(zb_t, wcat(P[0], P[2]), bias=P[1], relu=True)
+            left = ops.node_transform(zb_s, wcat(P[3], P[5]), bias=P[4], relu=True)
+            del zb_t, zb_s
+        else:
+            right, z_t = ops.conv_in_fused(csc, x_s, x_t, P[0], P[1], P[2], dt, relu=True)
+            left, z_s = ops.conv_in_fused(csr, x_t, x_s, P[3], P[4], P[5], dt, relu=True)
         saved = [z_s, z_t, left, right]
         scale = 1.0
         for i in range(n_layers):
