@@ -151,7 +151,7 @@ def run_exp(args):
             loss.backward()
             allreduce_gradients(params, world)
             opt.step()
-            if glstep % args.log_every == 1:
+            if (glstep - 1) % max(args.log_every, 1) == 0:
                 lv = float(loss.item())
                 assert not np.isnan(lv)              # train.py:126
                 history.append(dict(epoch=epoch, step=glstep, loss=lv, lr=scheduler.get_last_lr()[0]))
