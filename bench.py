@@ -104,6 +104,7 @@ def dist_setup(n_gpus):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
         dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world,

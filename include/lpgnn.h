@@ -146,6 +146,21 @@ LPGNN_API int lpgnn_node_transform(const void* A1, int32_t K1, const void* W1,
                          const float* bias, int32_t M, int32_t N,
                          void* out, int dtype, int out_dtype, int epilogue, lpgnn_stream_t stream);
 
+/* (a3+a4, inference) The LAST hidden transform fused with the basis-status head (reference
+ * arch.py:185-190): the epilogue also forms, per row, the three dot products of the ReLU'd fp32
+ * accumulator row with head_w [3,N] f32 over the tile's columns and writes them to
+ * head_partial [nparts][M][3] f32 (nparts = lpgnn_node_transform_head_parts(N), one slice per column
+ * tile; summed in a fixed order by lpgnn_head_finish).  out (bf16 [M,N]) may be NULL: inference
+ * never needs the last hidden activation in HBM.  bf16 operands only. */
+LPGNN_API int32_t lpgnn_node_transform_head_parts(int32_t N);
+LPGNN_API int lpgnn_node_transform_head(const void* A1, int32_t K1, const void* W1,
+                              const void* A2, int32_t K2, const void* W2,
+                              const float* bias, int32_t M, int32_t N, void* out, int epilogue,
+                              const float* head_w, float* head_partial, lpgnn_stream_t stream);
+/* logits = add_knowledge(sum_p head_partial[p] + b): finishes the fused head (arch.py:190-191). */
+LPGNN_API int lpgnn_head_finish(const float* head_partial, int32_t nparts, int32_t rows, const float* b,
+                      const float* feas, int32_t q, float* logits, lpgnn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (a4+a5) Basis-status head + knowledge masking.  Replaces torch.nn.Linear(H,3) (reference
  * arch.py:190) and add_knowledge (reference arch.py:129-141):

@@ -34,6 +34,9 @@ SIGNATURES = {
     "lpgnn_gather_cat": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p]),
     "lpgnn_conv_in_fused": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p, _i32, _p, _int, _int, _p, _p]),
     "lpgnn_node_transform": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _int, _int, _p]),
+    "lpgnn_node_transform_head_parts": (_i32, [_i32]),
+    "lpgnn_node_transform_head": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _p, _p, _p]),
+    "lpgnn_head_finish": (_int, [_p, _i32, _i32, _p, _p, _i32, _p, _p]),
     "lpgnn_head_mask": (_int, [_p, _int, _i32, _i32, _p, _p, _p, _i32, _p, _p, _p]),
     "lpgnn_add_knowledge": (_int, [_p, _i32, _p, _i32, _p, _p]),
     "lpgnn_head_mask_bwd": (_int, [_p, _p, _p, _int, _i32, _i32, _p, C.c_float, _p, _p, _p]),

@@ -103,8 +103,21 @@ def gcn_fc_forward(model, x_s, x_t, graph):
         return gcn_fc_train(model, x_s, x_t, csr, csc)
     dt = _act_dtype(model)
     left, right = _conv_in_infer(model.conv1, x_s, x_t, csr, csc, dt, relu=True)
-    for conv in model.layers:
+    n_layers = len(model.layers)
+    for li, conv in enumerate(model.layers):
         # eval mode: dropout is the identity; relu is fused into the transform epilogue
+        if li == n_layers - 1 and dt == torch.bfloat16:
+            # last layer: the head is fused into the transform epilogue; the hidden activation never reaches HBM
+            cast = conv._cache.get
+            l2r, r2l = conv.left2right, conv.right2left
+            agg_t, agg_s = ops.spmm(csc, left), ops.spmm(csr, right)
+            logit_t, _ = ops.node_transform_head(agg_t, cast(l2r.lin_rel.weight, dt), right, cast(l2r.lin_root.weight, dt),
+                                                 l2r.lin_rel.bias.detach(), model.lin_right.weight.detach(),
+                                                 model.lin_right.bias.detach(), x_t)
+            logit_s, _ = ops.node_transform_head(agg_s, cast(r2l.lin_rel.weight, dt), left, cast(r2l.lin_root.weight, dt),
+                                                 r2l.lin_rel.bias.detach(), model.lin_left.weight.detach(),
+                                                 model.lin_left.bias.detach(), x_s)
+            return logit_s, logit_t
         left, right = _conv_hidden_infer(conv, left, right, csr, csc, relu=True)
     logit_s, _ = ops.head_mask(left, model.lin_left.weight.detach(), model.lin_left.bias.detach(), x_s)
     logit_t, _ = ops.head_mask(right, model.lin_right.weight.detach(), model.lin_right.bias.detach(), x_t)

@@ -54,7 +54,8 @@ int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
 int node_transform_f32(const float* A1, int K1, const float* W1, const float* A2, int K2, const float* W2,
                        const float* bias, int M, int N, float* out, int relu, cudaStream_t st);
 int node_transform_bf16(const void* A1, int K1, const void* W1, const void* A2, int K2, const void* W2,
-                        const float* bias, int M, int N, void* out, int out_f32, int relu, cudaStream_t st);
+                        const float* bias, int M, int N, void* out, int out_f32, int relu, const float* head_w,
+                        float* head_partial, cudaStream_t st);
 
 }  // namespace lpgnn
 
@@ -89,5 +90,22 @@ extern "C" int lpgnn_node_transform(const void* A1, int32_t K1, const void* W1, 
   if (dtype == LPGNN_F32)
     return node_transform_f32((const float*)A1, K1, (const float*)W1, (const float*)A2, K2, (const float*)W2, bias, M,
                               N, (float*)out, relu, st);
-  return node_transform_bf16(A1, K1, W1, A2, K2, W2, bias, M, N, out, out_dtype == LPGNN_F32 ? 1 : 0, relu, st);
+  return node_transform_bf16(A1, K1, W1, A2, K2, W2, bias, M, N, out, out_dtype == LPGNN_F32 ? 1 : 0, relu, nullptr,
+                             nullptr, st);
+}
+
+extern "C" int32_t lpgnn_node_transform_head_parts(int32_t N) { return N % 256 == 0 ? N / 256 : (N % 128 == 0 ? N / 128 : N / 64); }
+
+extern "C" int lpgnn_node_transform_head(const void* A1, int32_t K1, const void* W1, const void* A2, int32_t K2,
+                                         const void* W2, const float* bias, int32_t M, int32_t N, void* out,
+                                         int epilogue, const float* head_w, float* head_partial,
+                                         lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(M >= 0 && N > 0 && K1 > 0 && K2 >= 0, "node_transform_head: bad shape M=%d N=%d K1=%d K2=%d", M, N, K1, K2);
+  if (M == 0) return LPGNN_OK;
+  LPGNN_REQUIRE(A1 && W1 && head_w && head_partial, "node_transform_head: null pointer");
+  LPGNN_REQUIRE(K2 == 0 || (A2 && W2), "node_transform_head: K2=%d but A2/W2 is null", K2);
+  if (K2 == 0) { A2 = nullptr; W2 = nullptr; }
+  return node_transform_bf16(A1, K1, W1, A2, K2, W2, bias, M, N, out, 0, (epilogue & LPGNN_EPI_RELU) ? 1 : 0, head_w,
+                             head_partial, (cudaStream_t)stream);
 }

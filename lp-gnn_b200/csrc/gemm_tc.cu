@@ -34,8 +34,12 @@ template <int BN> struct Cfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;  // power of two >= 32 for BN in {64,128,256}
-  static constexpr int kBarBytes = 2048;  // mbarriers + tmem ptr + bias slice (BN floats)
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024 /*align slack*/;
+  static constexpr int kBarBytes = 5120;  // mbarriers + tmem ptr + bias slice (BN floats) + head weight slice (3*BN floats)
+  // epilogue staging: per epilogue warp 32 rows x (128 B payload + 16 B pad); the pad makes both the
+  // row-wise 16-byte writes and the 4-rows-per-instruction read-back bank-conflict free
+  static constexpr int kStagePitch = 144;
+  static constexpr int kStagingBytes = 4 * 32 * kStagePitch;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kStagingBytes + 1024 /*align slack*/;
 };
 
 template <int BN, typename OutT>
@@ -43,7 +47,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2, int kblocks1,
                int kblocks2, const float* __restrict__ bias, OutT* __restrict__ out, int M, int N,
-               int relu) {
+               int relu, const float* __restrict__ head_w /*[3,N] or null*/,
+               float* __restrict__ head_partial /*[N/BN][M][3] or null*/) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle atoms
@@ -57,6 +62,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   uint64_t* tmem_empty = bars + 2 * C::kStages + 2;// [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
   float* bias_s = reinterpret_cast<float*>(bars + 2 * C::kStages + 6);  // [BN]
+  float* headw_s = bias_s + BN;                                         // [3][BN]
+  uint8_t* staging = smem + C::kStages * C::kStageBytes + C::kBarBytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_n = N / BN;
@@ -139,44 +146,82 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const uint32_t use_phase = (t >> 1) & 1;
       // stage the bias slice of this tile
       for (int j = et; j < BN; j += 128) bias_s[j] = bias ? __ldg(bias + n_blk * BN + j) : 0.f;
+      if (head_w)
+        for (int j = et; j < 3 * BN; j += 128) headw_s[j] = __ldg(head_w + (int64_t)(j / BN) * N + n_blk * BN + (j % BN));
       asm volatile("bar.sync 1, 128;" ::: "memory");
       ptx::mbar_wait(&tmem_full[buf], use_phase);
       ptx::tc_fence_after();
-      const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
-      OutT* orow = out + row * N + (int64_t)n_blk * BN;
+      // Each lane owns accumulator row (q*32 + lane).  128 payload bytes per row (64 bf16 / 32 fp32 columns) are
+      // staged through shared memory so that one warp-wide 16-byte store covers 4 rows x 128 contiguous bytes
+      // instead of 32 rows x 16 bytes (32 cache lines per instruction).
+      constexpr int kColsPerPiece = 128 / (int)sizeof(OutT);       // 64 (bf16) or 32 (fp32)
+      uint8_t* my_stage = staging + q * (32 * C::kStagePitch);
+      const int64_t row_base = (int64_t)m_blk * BM + q * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+      float hd0 = 0.f, hd1 = 0.f, hd2 = 0.f;   // fused basis-status head: partial dot products of this row
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(taddr + c * 32, r);
-        ptx::tmem_ld_wait();
+      for (int pc = 0; pc < BN / kColsPerPiece; ++pc) {
+        uint4* srow = reinterpret_cast<uint4*>(my_stage + lane * C::kStagePitch);
         if constexpr (sizeof(OutT) == 2) {
-          uint32_t packed[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float v0 = __uint_as_float(r[2 * j]) + bias_s[c * 32 + 2 * j];
-            float v1 = __uint_as_float(r[2 * j + 1]) + bias_s[c * 32 + 2 * j + 1];
-            if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-            packed[j] = pack_bf16(v0, v1);
-          }
-          if (row < M) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(taddr + pc * 64 + h * 32, r);
+            ptx::tmem_ld_wait();
+            uint32_t packed[16];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            for (int j = 0; j < 16; ++j) {
+              float v0 = __uint_as_float(r[2 * j]) + bias_s[pc * 64 + h * 32 + 2 * j];
+              float v1 = __uint_as_float(r[2 * j + 1]) + bias_s[pc * 64 + h * 32 + 2 * j + 1];
+              if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+              packed[j] = pack_bf16(v0, v1);
+              if (head_w) {
+                const int col = pc * 64 + h * 32 + 2 * j;
+                hd0 = fmaf(v0, headw_s[col], hd0);          hd0 = fmaf(v1, headw_s[col + 1], hd0);
+                hd1 = fmaf(v0, headw_s[BN + col], hd1);     hd1 = fmaf(v1, headw_s[BN + col + 1], hd1);
+                hd2 = fmaf(v0, headw_s[2 * BN + col], hd2); hd2 = fmaf(v1, headw_s[2 * BN + col + 1], hd2);
+              }
+            }
+            if (out) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                srow[h * 4 + j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            }
           }
-        } else {  // fp32 output (weight gradients)
+        } else {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr + pc * 32, r);
+          ptx::tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float v = __uint_as_float(r[j]) + bias_s[c * 32 + j];
+            float v = __uint_as_float(r[j]) + bias_s[pc * 32 + j];
             if (relu) v = fmaxf(v, 0.f);
             r[j] = __float_as_uint(v);
           }
-          if (row < M) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          for (int j = 0; j < 8; ++j) srow[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        }
+        if (!out) continue;                       // head-only mode: the activation tile is never written
+        __syncwarp();
+        // read back: instruction i covers rows 4i..4i+3, lane -> (row 4i + lane/8, 16-byte piece lane%8)
+        const int sub_row = lane >> 3, piece = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + sub_row;
+          const uint4 v = *reinterpret_cast<const uint4*>(my_stage + rr * C::kStagePitch + piece * 16);
+          const int64_t grow = row_base + rr;
+          if (grow < M) {
+            uint8_t* dst = reinterpret_cast<uint8_t*>(out + grow * N + (int64_t)n_blk * BN + pc * kColsPerPiece);
+            *reinterpret_cast<uint4*>(dst + piece * 16) = v;
           }
+        }
+        __syncwarp();
+      }
+      if (head_partial) {
+        const int64_t grow = row_base + lane;
+        if (grow < M) {
+          float* hp = head_partial + ((int64_t)n_blk * M + grow) * 3;
+          hp[0] = hd0; hp[1] = hd1; hp[2] = hd2;
         }
       }
       ptx::tc_fence_before();
@@ -224,7 +269,8 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int bo
 
 template <int BN, typename OutT>
 int launch(const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& a2, const CUtensorMap& w2, int kb1, int kb2,
-           const float* bias, void* out, int M, int N, int relu, cudaStream_t st) {
+           const float* bias, void* out, int M, int N, int relu, const float* head_w, float* head_partial,
+           cudaStream_t st) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -235,7 +281,8 @@ int launch(const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& a2, 
   const int tiles = ceil_div(M, BM) * (N / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   gemm_tc_kernel<BN, OutT><<<grid, kThreads, C::kSmemBytes, st>>>(a1, w1, a2, w2, kb1, kb2, bias,
-                                                                  reinterpret_cast<OutT*>(out), M, N, relu);
+                                                                  reinterpret_cast<OutT*>(out), M, N, relu, head_w,
+                                                                  head_partial);
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;
@@ -244,12 +291,15 @@ int launch(const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& a2, 
 }  // namespace
 
 int node_transform_bf16(const void* A1, int K1, const void* W1, const void* A2, int K2, const void* W2,
-                        const float* bias, int M, int N, void* out, int out_f32, int relu, cudaStream_t st) {
+                        const float* bias, int M, int N, void* out, int out_f32, int relu, const float* head_w,
+                        float* head_partial, cudaStream_t st) {
   LPGNN_REQUIRE(K1 > 0 && K1 % BK == 0 && K2 % BK == 0, "node_transform(bf16): K1=%d, K2=%d must be multiples of 64", K1, K2);
   LPGNN_REQUIRE(N % 64 == 0, "node_transform(bf16): N=%d must be a multiple of 64", N);
   LPGNN_REQUIRE((uintptr_t)A1 % 16 == 0 && (uintptr_t)W1 % 16 == 0 && (uintptr_t)A2 % 16 == 0 &&
                     (uintptr_t)W2 % 16 == 0 && (uintptr_t)out % 16 == 0,
                 "node_transform(bf16): operands must be 16-byte aligned");
+  LPGNN_REQUIRE(out || (head_w && head_partial), "node_transform(bf16): no output requested");
+  LPGNN_REQUIRE(!head_w || (head_partial && !out_f32), "node_transform(bf16): fused head needs head_partial and bf16 mode");
   const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
   const bool two = A2 != nullptr && K2 > 0;
   CUtensorMap a1, w1, a2, w2;
@@ -263,13 +313,13 @@ int node_transform_bf16(const void* A1, int K1, const void* W1, const void* A2, 
   }
   const int kb1 = K1 / BK, kb2 = two ? K2 / BK : 0;
   if (out_f32) {
-    if (BN == 256) return launch<256, float>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, st);
-    if (BN == 128) return launch<128, float>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, st);
-    return launch<64, float>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, st);
+    if (BN == 256) return launch<256, float>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, st);
+    if (BN == 128) return launch<128, float>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, st);
+    return launch<64, float>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, st);
   }
-  if (BN == 256) return launch<256, __nv_bfloat16>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, st);
-  if (BN == 128) return launch<128, __nv_bfloat16>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, st);
-  return launch<64, __nv_bfloat16>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, st);
+  if (BN == 256) return launch<256, __nv_bfloat16>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, st);
+  if (BN == 128) return launch<128, __nv_bfloat16>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, st);
+  return launch<64, __nv_bfloat16>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, st);
 }
 
 }  // namespace lpgnn

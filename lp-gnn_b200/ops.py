@@ -99,6 +99,31 @@ def node_transform(a1, w1, a2=None, w2=None, bias=None, relu=False, out_dtype=No
     return out
 
 
+def node_transform_head(a1, w1, a2, w2, bias, head_w, head_b, feas, relu=True, want_out=False):
+    """Last hidden transform fused with the basis-status head and knowledge masking (bf16 tensor-core kernel):
+    ``logits = add_knowledge(relu(a1 w1^T + a2 w2^T + bias) head_w^T + head_b)`` without writing the hidden
+    activation (unless ``want_out``).  Returns ``(logits[M,3] f32, out | None)``."""
+    require_cuda(a1, w1, a2, w2, bias, head_w, head_b, feas)
+    a1, w1, a2, w2 = _contig(a1), _contig(w1), _contig(a2), _contig(w2)
+    bias, head_w, head_b, feas = _contig(bias.float()), _contig(head_w.float()), _contig(head_b.float()), _contig(feas.float())
+    M, K1 = a1.shape
+    N, K2 = w1.shape[0], a2.shape[1]
+    lib = _lib.load()
+    nparts = lib.lpgnn_node_transform_head_parts(N)
+    partial = torch.empty((nparts, M, 3), dtype=torch.float32, device=a1.device)
+    out = torch.empty((M, N), dtype=a1.dtype, device=a1.device) if want_out else None
+    logits = torch.empty((M, 3), dtype=torch.float32, device=a1.device)
+    with torch.cuda.device(a1.device):
+        rc = lib.lpgnn_node_transform_head(a1.data_ptr(), K1, w1.data_ptr(), a2.data_ptr(), K2, w2.data_ptr(), bias.data_ptr(),
+                                           M, N, ptr(out), EPI_RELU if relu else EPI_NONE, head_w.data_ptr(),
+                                           partial.data_ptr(), stream_ptr())
+        check(rc, "lpgnn_node_transform_head")
+        rc = lib.lpgnn_head_finish(partial.data_ptr(), nparts, M, head_b.data_ptr(), feas.data_ptr(), feas.shape[1],
+                                   logits.data_ptr(), stream_ptr())
+    check(rc, "lpgnn_head_finish")
+    return logits, out
+
+
 def head_mask(h, w, b, feas, want_raw=False):
     """Linear(H,3) + add_knowledge in one pass (reference arch.py:190-191, 129-141).
     Returns ``(logits[rows,3] f32, raw[rows,3] f32 | None)``."""

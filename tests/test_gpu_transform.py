@@ -93,3 +93,34 @@ def test_conv_in_fused_vs_oracle(cuda, hids, out_dtype):
     agg2 = port.spmm_sequential(ref.rowptr, ref.col, ref.val, x_t)
     e2 = agg2.astype(np.float64) @ w_rel.T.astype(np.float64) + b + x_s.astype(np.float64) @ w_root.T
     np.testing.assert_allclose(out2.float().cpu().numpy(), e2, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 1024, 1024), (129, 128, 128), (5000, 64, 64), (300, 512, 256)])
+@pytest.mark.parametrize("want_out", [False, True])
+def test_transform_with_fused_head(cuda, M, N, K, want_out):
+    """Last-layer transform with the basis-status head + knowledge masking fused into the epilogue vs the
+    unfused kernels (same bf16 inputs; the fused path keeps the ReLU'd activation in fp32)."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    bf = torch.bfloat16
+    a1 = torch.randn(M, K, device=cuda, generator=g).to(bf)
+    a2 = torch.randn(M, K, device=cuda, generator=g).to(bf)
+    w1 = (torch.randn(N, K, device=cuda, generator=g) / K ** 0.5).to(bf)
+    w2 = (torch.randn(N, K, device=cuda, generator=g) / K ** 0.5).to(bf)
+    b = torch.randn(N, device=cuda, generator=g)
+    hw = torch.randn(3, N, device=cuda, generator=g) / N ** 0.5
+    hb = torch.randn(3, device=cuda, generator=g)
+    feas = torch.randint(-1, 2, (M, 8), device=cuda, generator=g).float()
+    logits, out = ops.node_transform_head(a1, w1, a2, w2, b, hw, hb, feas, relu=True, want_out=want_out)
+    act = (a1.double() @ w1.double().T + a2.double() @ w2.double().T + b.double()).relu()
+    raw = act @ hw.double().T + hb.double()
+    exp = torch.nn.functional.normalize(raw) * 10
+    exp[:, 0] -= 10 * (feas[:, 5] != 0)
+    exp[:, 2] -= 10 * (feas[:, 7] != 0)
+    err = (logits.double() - exp).abs()
+    assert float(err.max()) < 5e-3, float(err.max())              # fp32 accumulate of exact bf16 products
+    assert (out is None) == (not want_out)
+    if want_out:
+        ref = ops.node_transform(a1, w1, a2, w2, b, relu=True)
+        assert torch.equal(out, ref)
