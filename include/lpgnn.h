@@ -75,9 +75,9 @@ LPGNN_API int lpgnn_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *
  * flags: LPGNN_COO_SORTED = the caller asserts the COO is already in canonical (row, col) order
  * (torch_sparse's `is_sorted=True`; true for everything LPDataset.get produces, dataset.py:251-252),
- * which skips the COO sort.  status (device int32, optional) receives a bit mask after the call:
- * bit 0 = the SORTED claim was false (outputs are then NOT canonical), bit 1 = an index was out of
- * range.  It is written asynchronously; read it after synchronising the stream.
+ * which skips the COO sort.  status (device int32, optional, ZERO-INITIALISED BY THE CALLER) gets bits
+ * OR-ed in by the kernels: bit 0 = the SORTED claim was false (outputs are then NOT canonical),
+ * bit 1 = an index was out of range.  Written asynchronously; read it after synchronising the stream.
  * ------------------------------------------------------------------------------------------- */
 LPGNN_API size_t lpgnn_graph_build_workspace_bytes(int64_t nnz, int32_t m, int32_t n);
 LPGNN_API int lpgnn_graph_build(const void* coo_row, const void* coo_col, int idx_is_i64,

@@ -6,7 +6,8 @@
 //   1. softmax per node (fp32) -> key = bit pattern of p1 (p1 >= 0, so unsigned order == float
 //      order), side = 0 if p0 >= p2 else 2 (argmax over {0,2} picks the first maximum);
 //      fused with the histogram of the top radix digit
-//   2. 4-pass MSB radix select of the k-th largest key (256-bin histograms, integer atomics only)
+//   2. 4-pass MSB radix select of the k-th largest key (256-bin histograms, integer atomics only); every kernel
+//      re-derives the threshold state from the histograms with one warp, so there are no state-advancing launches
 //   3. ties at the threshold are taken in ascending node index (block counts + scan + in-block
 //      ranks: deterministic; torch.topk leaves the tie order implementation-defined)
 //   4. status = 1 if selected else side.
@@ -20,14 +21,73 @@ constexpr int kThreads = 256;
 constexpr int kItems = 8;                     // nodes per thread in the ordered passes
 constexpr int kTile = kThreads * kItems;      // nodes per block in the ordered passes
 
-struct SelectState {
-  uint32_t prefix;    // decided high bits of the threshold key
-  uint32_t mask;      // which bits are decided
-  uint32_t k_rem;     // how many still to take among keys matching the prefix
-  uint32_t pad;
+// Threshold search state.  Every kernel re-derives it from the per-pass histograms (a chain of up to four
+// 256-bin picks done by one warp), so no kernel exists only to advance the state and there is no host sync.
+struct Threshold {
+  uint32_t prefix;  // decided high bits of the k-th largest key
+  uint32_t mask;    // which bits are decided
+  uint32_t k_rem;   // how many keys are still to be taken among those matching the prefix
 };
 
 __device__ __forceinline__ float nan_to_zero(float v) { return (v != v) ? 0.f : v; }
+
+// Executed by ONE warp.  hist: [npass][256].  Picks, pass by pass, the digit d with
+// count(digit > d) < k_rem <= count(digit >= d) among the keys that match the prefix so far.
+__device__ Threshold pick_chain(const uint32_t* __restrict__ hist, int npass, uint32_t k) {
+  Threshold t{0u, 0u, k};
+  const int lane = threadIdx.x & 31;
+  if (k == 0) { t.prefix = 0xffffffffu; t.mask = 0xffffffffu; return t; }  // threshold above every key
+  for (int p = 0; p < npass; ++p) {
+    const uint32_t* h = hist + p * 256;
+    const int shift = 24 - 8 * p;
+    // lane l owns the 8 bins 255-8l .. 248-8l (descending digit order)
+    uint32_t c[8], s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c[j] = h[255 - 8 * lane - j]; s += c[j]; }
+    uint32_t incl = s;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    const uint32_t before = incl - s;                       // keys with a larger digit owned by lower lanes
+    const bool mine = before < t.k_rem && t.k_rem <= incl;
+    const uint32_t who = __ballot_sync(0xffffffffu, mine);
+    uint32_t digit = 0, above = 0;
+    if (who) {
+      const int src = __ffs(who) - 1;
+      if (lane == src) {
+        uint32_t acc = before;
+        int j = 0;
+        for (; j < 7; ++j) { if (acc + c[j] >= t.k_rem) break; acc += c[j]; }
+        digit = 255 - 8 * lane - j;
+        above = acc;
+      }
+      digit = __shfl_sync(0xffffffffu, digit, src);
+      above = __shfl_sync(0xffffffffu, above, src);
+    } else {                                                 // k exceeds the population: take everything
+      above = __shfl_sync(0xffffffffu, incl, 31) - h[0];
+    }
+    t.prefix |= digit << shift;
+    t.mask |= 0xffu << shift;
+    t.k_rem -= above;
+  }
+  return t;
+}
+
+__device__ __forceinline__ Threshold block_threshold(const uint32_t* hist, int npass, uint32_t k, Threshold* smem_t) {
+  if (threadIdx.x < 32) {
+    const Threshold t = pick_chain(hist, npass, k);
+    if (threadIdx.x == 0) *smem_t = t;
+  }
+  __syncthreads();
+  return *smem_t;
+}
+
+__global__ void init_hist_kernel(uint32_t* hist /*[4][256]*/, int32_t* counts) {
+  for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) hist[i] = 0;
+  if (counts && threadIdx.x < 4) counts[threadIdx.x] = 0;
+}
 
 __global__ void __launch_bounds__(kThreads)
 softmax_key_kernel(const float* __restrict__ lc, int32_t m, const float* __restrict__ lv, int32_t n,
@@ -52,99 +112,59 @@ softmax_key_kernel(const float* __restrict__ lc, int32_t m, const float* __restr
   if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
 }
 
-// One block.  Chooses the digit of the k-th largest key from hist, updates the state, clears hist.
-__global__ void __launch_bounds__(256) pick_digit_kernel(uint32_t* __restrict__ hist, SelectState* __restrict__ st,
-                                                         int shift) {
-  __shared__ uint32_t h[256];
-  h[threadIdx.x] = hist[threadIdx.x];
-  hist[threadIdx.x] = 0;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t k = st->k_rem;
-    if (k == 0) {  // nothing to select: threshold above every key
-      st->prefix = 0xffffffffu; st->mask = 0xffffffffu;
-    } else {
-      uint32_t above = 0;
-      int d = 255;
-      for (; d > 0; --d) {
-        if (above + h[d] >= k) break;
-        above += h[d];
-      }
-      st->prefix |= ((uint32_t)d) << shift;
-      st->mask |= 0xffu << shift;
-      st->k_rem = k - above;
-    }
-  }
-}
-
+// histogram of digit `pass` (bits [24-8*pass, 32-8*pass)) over the keys matching the threshold prefix so far
 __global__ void __launch_bounds__(kThreads)
-digit_hist_kernel(const uint32_t* __restrict__ keys, int64_t total, const SelectState* __restrict__ st, int shift,
-                  uint32_t* __restrict__ hist) {
+digit_hist_kernel(const uint32_t* __restrict__ keys, int64_t total, uint32_t* __restrict__ hist, int pass, uint32_t k) {
   __shared__ uint32_t h[256];
+  __shared__ Threshold ts;
   h[threadIdx.x] = 0;
-  __syncthreads();
-  const uint32_t prefix = st->prefix, mask = st->mask;
+  const Threshold t = block_threshold(hist, pass, k, &ts);   // includes a __syncthreads()
+  const int shift = 24 - 8 * pass;
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
     const uint32_t key = keys[i];
-    if ((key & mask) == prefix) atomicAdd(&h[(key >> shift) & 0xff], 1u);
+    if ((key & t.mask) == t.prefix) atomicAdd(&h[(key >> shift) & 0xff], 1u);
   }
   __syncthreads();
-  if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
-}
-
-__global__ void init_state_kernel(SelectState* st, uint32_t k, uint32_t* hist, int32_t* counts) {
-  if (threadIdx.x == 0) { st->prefix = 0; st->mask = 0; st->k_rem = k; st->pad = 0; }
-  hist[threadIdx.x] = 0;
-  if (counts && threadIdx.x < 4) counts[threadIdx.x] = 0;
+  if (h[threadIdx.x]) atomicAdd(&hist[pass * 256 + threadIdx.x], h[threadIdx.x]);
 }
 
 // number of keys equal to the threshold in each tile
 __global__ void __launch_bounds__(kThreads)
-tie_count_kernel(const uint32_t* __restrict__ keys, int64_t total, const SelectState* __restrict__ st,
+tie_count_kernel(const uint32_t* __restrict__ keys, int64_t total, const uint32_t* __restrict__ hist, uint32_t k,
                  uint32_t* __restrict__ tile_ties) {
   __shared__ uint32_t cnt;
+  __shared__ Threshold ts;
   if (threadIdx.x == 0) cnt = 0;
-  __syncthreads();
-  const uint32_t thr = st->prefix;
+  const Threshold t = block_threshold(hist, 4, k, &ts);
   const int64_t base = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kItems;
   uint32_t c = 0;
 #pragma unroll
   for (int j = 0; j < kItems; ++j)
-    if (base + j < total && keys[base + j] == thr) ++c;
+    if (base + j < total && keys[base + j] == t.prefix) ++c;
   if (c) atomicAdd(&cnt, c);
   __syncthreads();
   if (threadIdx.x == 0) tile_ties[blockIdx.x] = cnt;
 }
 
-__global__ void __launch_bounds__(1024) tie_scan_kernel(uint32_t* __restrict__ tile_ties, int ntiles) {
-  // exclusive scan, single block, sequential chunks (ntiles is small: total/2048)
-  __shared__ uint32_t part[1024];
-  const int t = threadIdx.x;
-  const int per = (ntiles + 1023) / 1024;
-  const int lo = t * per, hi = min(lo + per, ntiles);
-  uint32_t s = 0;
-  for (int i = lo; i < hi; ++i) s += tile_ties[i];
-  part[t] = s;
-  __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    uint32_t v = (t >= off) ? part[t - off] : 0;
-    __syncthreads();
-    part[t] += v;
-    __syncthreads();
-  }
-  uint32_t run = (t == 0) ? 0 : part[t - 1];
-  for (int i = lo; i < hi; ++i) { uint32_t c = tile_ties[i]; tile_ties[i] = run; run += c; }
-}
-
 template <typename OutT>
 __global__ void __launch_bounds__(kThreads)
 status_kernel(const uint32_t* __restrict__ keys, const uint8_t* __restrict__ side, int64_t total, int32_t m,
-              const SelectState* __restrict__ st, const uint32_t* __restrict__ tile_tie_offset,
+              const uint32_t* __restrict__ hist, uint32_t k, const uint32_t* __restrict__ tile_ties,
               OutT* __restrict__ status, int32_t* __restrict__ counts) {
   __shared__ uint32_t warp_ties[kThreads / 32];
+  __shared__ uint32_t red[kThreads / 32];
   __shared__ int32_t c_s[4];
+  __shared__ Threshold ts;
   if (threadIdx.x < 4) c_s[threadIdx.x] = 0;
-  const uint32_t thr = st->prefix, k_rem = st->k_rem;
+  const Threshold t = block_threshold(hist, 4, k, &ts);
+  const uint32_t thr = t.prefix, k_rem = t.k_rem;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // ties in the tiles before this one (fixed order -> lowest node index first)
+  uint32_t part = 0;
+  for (int i = threadIdx.x; i < (int)blockIdx.x; i += kThreads) part += tile_ties[i];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+  if (lane == 0) red[warp] = part;
   const int64_t base = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kItems;
   uint32_t key[kItems];
   uint32_t my_ties = 0;
@@ -154,7 +174,6 @@ status_kernel(const uint32_t* __restrict__ keys, const uint8_t* __restrict__ sid
     if (base + j < total && key[j] == thr) ++my_ties;
   }
   // exclusive prefix of my_ties over the block, in thread order (== node order)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t incl = my_ties;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
@@ -163,8 +182,9 @@ status_kernel(const uint32_t* __restrict__ keys, const uint8_t* __restrict__ sid
   }
   if (lane == 31) warp_ties[warp] = incl;
   __syncthreads();
-  uint32_t before = tile_tie_offset[blockIdx.x] + incl - my_ties;
-  for (int w = 0; w < warp; ++w) before += warp_ties[w];
+  uint32_t before = incl - my_ties;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) { before += red[w]; if (w < warp) before += warp_ties[w]; }
   int32_t n0 = 0, n1 = 0, n2 = 0, nbv = 0;
 #pragma unroll
   for (int j = 0; j < kItems; ++j) {
@@ -195,7 +215,7 @@ Layout layout(int64_t total_nodes) {
   size_t off = 0;
   L.keys = off; off += align_up(t * 4, 256);
   L.side = off; off += align_up(t, 256);
-  L.hist = off; off += 256 * 4;
+  L.hist = off; off += 4 * 256 * 4;
   L.state = off; off += 256;
   L.ties = off; off += align_up(((t + kTile - 1) / kTile + 1) * 4, 256);
   L.total = off;
@@ -231,27 +251,25 @@ extern "C" int lpgnn_basis_select(const float* logits_cons, int32_t m, const flo
   uint32_t* keys = reinterpret_cast<uint32_t*>(w + L.keys);
   uint8_t* side = reinterpret_cast<uint8_t*>(w + L.side);
   uint32_t* hist = reinterpret_cast<uint32_t*>(w + L.hist);
-  SelectState* state = reinterpret_cast<SelectState*>(w + L.state);
+  void* state = w + L.state;
   uint32_t* ties = reinterpret_cast<uint32_t*>(w + L.ties);
 
   const int grid_stride = min(ceil_div(total, kThreads), sm_count() * 8);
   const int ntiles = ceil_div(total, kTile);
-  init_state_kernel<<<1, 256, 0, st>>>(state, (uint32_t)k_basic, hist, counts_out);
+  const uint32_t k = (uint32_t)k_basic;
+  (void)state;
+  init_hist_kernel<<<1, 256, 0, st>>>(hist, counts_out);
   softmax_key_kernel<<<grid_stride, kThreads, 0, st>>>(logits_cons, m, logits_vars, n, keys, side, hist);
-  pick_digit_kernel<<<1, 256, 0, st>>>(hist, state, 24);
-  for (int shift = 16; shift >= 0; shift -= 8) {
-    digit_hist_kernel<<<grid_stride, kThreads, 0, st>>>(keys, total, state, shift, hist);
-    pick_digit_kernel<<<1, 256, 0, st>>>(hist, state, shift);
-  }
-  tie_count_kernel<<<ntiles, kThreads, 0, st>>>(keys, total, state, ties);
-  tie_scan_kernel<<<1, 1024, 0, st>>>(ties, ntiles);
+  for (int pass = 1; pass < 4; ++pass)
+    digit_hist_kernel<<<grid_stride, kThreads, 0, st>>>(keys, total, hist, pass, k);
+  tie_count_kernel<<<ntiles, kThreads, 0, st>>>(keys, total, hist, k, ties);
   if (status_is_i64)
-    status_kernel<int64_t><<<ntiles, kThreads, 0, st>>>(keys, side, total, m, state, ties,
+    status_kernel<int64_t><<<ntiles, kThreads, 0, st>>>(keys, side, total, m, hist, k, ties,
                                                         reinterpret_cast<int64_t*>(status), counts_out);
   else
-    status_kernel<uint8_t><<<ntiles, kThreads, 0, st>>>(keys, side, total, m, state, ties,
+    status_kernel<uint8_t><<<ntiles, kThreads, 0, st>>>(keys, side, total, m, hist, k, ties,
                                                         reinterpret_cast<uint8_t*>(status), counts_out);
   LPGNN_LAUNCH_OK();
-  count_launches(12);
+  count_launches(7);
   return LPGNN_OK;
 }

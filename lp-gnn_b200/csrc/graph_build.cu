@@ -48,26 +48,60 @@ __global__ void gather_entry_kernel(const uint32_t* __restrict__ col_src, const 
   if (i < n) { const uint32_t p = perm[i]; col_out[i] = col_src[p]; val_out[i] = val_src[p]; }
 }
 
-// CSC payload: csr2csc[k] = perm[k], row_csc[k] = rows[perm[k]], val_csc[k] = val[perm[k]]
-__global__ void gather_csc_kernel(const uint32_t* __restrict__ rows, const float* __restrict__ val,
-                                  const uint32_t* __restrict__ perm, uint32_t* __restrict__ csr2csc,
-                                  uint32_t* __restrict__ row_csc, float* __restrict__ val_csc, int64_t n) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n) { const uint32_t p = perm[i]; csr2csc[i] = p; row_csc[i] = rows[p]; val_csc[i] = val[p]; }
+// Sorted-COO fast path in ONE pass over the entries: verify the (row, col) order and the index range, emit the
+// CSR payload (col, val), fill rowptr from the row boundaries and set up the (key = col, payload = position)
+// pairs of the CSC sort.
+__global__ void prep_sorted_kernel(const uint32_t* __restrict__ row, const uint32_t* __restrict__ col,
+                                   const float* __restrict__ val, int64_t n, uint32_t m, uint32_t ncols,
+                                   uint32_t* __restrict__ col_out, float* __restrict__ val_out,
+                                   int32_t* __restrict__ rowptr, uint32_t* __restrict__ keys,
+                                   uint32_t* __restrict__ vals, uint32_t* __restrict__ status) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e > n) return;
+  const int64_t prev = (e == 0) ? -1 : (int64_t)row[e - 1];
+  int64_t cur = (int64_t)m;
+  if (e < n) {
+    const uint32_t r = row[e], c = col[e];
+    cur = r;
+    col_out[e] = c;
+    val_out[e] = val[e];
+    keys[e] = c;
+    vals[e] = (uint32_t)e;
+    if (status) {
+      if (r >= m || c >= ncols) atomicOr(status, 2u);
+      if (e > 0 && (r < (uint32_t)prev || (r == (uint32_t)prev && c < col[e - 1]))) atomicOr(status, 1u);
+    }
+    if (r >= m) cur = prev;  // out-of-range row: do not write past rowptr
+  }
+  for (int64_t q = prev + 1; q <= cur && q <= (int64_t)m; ++q) rowptr[q] = (int32_t)e;
 }
 
-// plain copies as kernels (a cudaMemcpyAsync D2D costs ~10x a small kernel on the launch path)
-__global__ void copy_entry_kernel(const uint32_t* __restrict__ col_src, const float* __restrict__ val_src,
-                                  uint32_t* __restrict__ col_out, float* __restrict__ val_out, int64_t n,
-                                  uint32_t* __restrict__ status) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n) { col_out[i] = col_src[i]; val_out[i] = val_src[i]; }
+// CSC payload + colptr in one pass: csr2csc[k] = perm[k], row_csc[k] = rows[perm[k]], val_csc[k] = val[perm[k]],
+// colptr from the boundaries of the sorted column keys.
+__global__ void finish_csc_kernel(const uint32_t* __restrict__ rows, const float* __restrict__ val,
+                                  const uint32_t* __restrict__ sorted_cols, const uint32_t* __restrict__ perm,
+                                  int64_t n, int32_t ncols, uint32_t* __restrict__ csr2csc,
+                                  uint32_t* __restrict__ row_csc, float* __restrict__ val_csc,
+                                  int32_t* __restrict__ colptr) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k > n) return;
+  const int64_t prev = (k == 0) ? -1 : (int64_t)sorted_cols[k - 1];
+  int64_t cur = ncols;
+  if (k < n) {
+    const uint32_t p = perm[k];
+    csr2csc[k] = p;
+    row_csc[k] = rows[p];
+    val_csc[k] = val[p];
+    cur = min((int64_t)sorted_cols[k], (int64_t)ncols);
+  }
+  for (int64_t q = prev + 1; q <= cur; ++q) colptr[q] = (int32_t)k;
 }
+
+// plain copy as a kernel (a cudaMemcpyAsync D2D costs ~10x a small kernel on the launch path)
 __global__ void copy_u32_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int64_t n) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i];
 }
-__global__ void reset_status_kernel(uint32_t* status) { *status = 0u; }
 
 // keys[i] = key_src[i], vals[i] = i   (start of a sort)
 __global__ void init_pairs_kernel(const uint32_t* __restrict__ key_src, uint32_t* __restrict__ keys,
@@ -76,15 +110,6 @@ __global__ void init_pairs_kernel(const uint32_t* __restrict__ key_src, uint32_t
   if (i < n) { keys[i] = key_src[i]; vals[i] = (uint32_t)i; }
 }
 
-// flag[0] |= 1 if the COO is NOT sorted by (row, col) (strictly non-decreasing linear index)
-__global__ void check_sorted_kernel(const uint32_t* __restrict__ row, const uint32_t* __restrict__ col, int64_t n,
-                                    uint32_t* __restrict__ flag) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i + 1 < n) {
-    const uint32_t r0 = row[i], r1 = row[i + 1];
-    if (r1 < r0 || (r1 == r0 && col[i + 1] < col[i])) atomicOr(flag, 1u);
-  }
-}
 __global__ void expand_check_range_kernel(const uint32_t* __restrict__ row, const uint32_t* __restrict__ col, int64_t n,
                                           uint32_t m, uint32_t ncols, uint32_t* __restrict__ flag) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -293,7 +318,6 @@ extern "C" int lpgnn_graph_build(const void* coo_row, const void* coo_col, int i
     return LPGNN_EWORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (status) reset_status_kernel<<<1, 1, 0, st>>>(reinterpret_cast<uint32_t*>(status));
   if (nnz == 0) {
     LPGNN_CUDA_OK(cudaMemsetAsync(rowptr, 0, sizeof(int32_t) * ((size_t)m + 1), st));
     LPGNN_CUDA_OK(cudaMemsetAsync(colptr, 0, sizeof(int32_t) * ((size_t)n + 1), st));
@@ -311,8 +335,9 @@ extern "C" int lpgnn_graph_build(const void* coo_row, const void* coo_col, int i
   uint32_t* rows_sorted = w + 6 * words;
   b.counts = w + 7 * words;
   b.totals = b.counts + align_up((size_t)kMaxRadix * ceil_div(z, kSortTile), 64);
-  const int tb = 256, gb = ceil_div(z, tb);
+  const int tb = 256, gb = ceil_div(z, tb), gb1 = ceil_div(z + 1, tb);
   int launches = 0;
+  uint32_t* u_status = reinterpret_cast<uint32_t*>(status);
 
   const uint32_t *rsrc, *csrc;
   if (idx_is_i64) {
@@ -327,15 +352,12 @@ extern "C" int lpgnn_graph_build(const void* coo_row, const void* coo_col, int i
   uint32_t* u_col = reinterpret_cast<uint32_t*>(col);
   const uint32_t* csr_rows;  // row of every CSR entry
   if (flags & LPGNN_COO_SORTED) {
-    // Caller asserts row-major order (what the reference's pipeline produces, dataset.py:251-252):
-    // the CSR arrays are the input; the claim is verified on the device and reported in *status.
-    if (status) {
-      check_sorted_kernel<<<gb, tb, 0, st>>>(rsrc, csrc, z, reinterpret_cast<uint32_t*>(status));
-      ++launches;
-    }
-    copy_entry_kernel<<<gb, tb, 0, st>>>(csrc, coo_val, u_col, val, z, nullptr);
-    ++launches;
+    // Caller asserts row-major order (what the reference's pipeline produces, dataset.py:251-252): the CSR
+    // arrays are the input; the claim and the index range are verified on the device and reported in *status.
+    prep_sorted_kernel<<<gb1, tb, 0, st>>>(rsrc, csrc, coo_val, z, (uint32_t)m, (uint32_t)n, u_col, val, rowptr, b.k[0],
+                                           b.v[0], u_status);
     csr_rows = rsrc;
+    launches += 1;
   } else {
     // ---- CSR: LSD over (row, col): column digits first, then row digits
     init_pairs_kernel<<<gb, tb, 0, st>>>(csrc, b.k[0], b.v[0], z);
@@ -347,21 +369,19 @@ extern "C" int lpgnn_graph_build(const void* coo_row, const void* coo_col, int i
     copy_u32_kernel<<<gb, tb, 0, st>>>(b.k[cur], rows_sorted, z);
     gather_entry_kernel<<<gb, tb, 0, st>>>(csrc, coo_val, b.v[cur], u_col, val, z);
     csr_rows = rows_sorted;
-    launches += 4;
+    if (status) {
+      expand_check_range_kernel<<<gb, tb, 0, st>>>(rsrc, csrc, z, (uint32_t)m, (uint32_t)n, u_status);
+      ++launches;
+    }
+    fill_ptr_kernel<<<gb1, tb, 0, st>>>(csr_rows, z, m, rowptr);
+    init_pairs_kernel<<<gb, tb, 0, st>>>(u_col, b.k[0], b.v[0], z);
+    launches += 6;
   }
-  if (status) {
-    expand_check_range_kernel<<<gb, tb, 0, st>>>(rsrc, csrc, z, (uint32_t)m, (uint32_t)n,
-                                                 reinterpret_cast<uint32_t*>(status));
-    ++launches;
-  }
-  fill_ptr_kernel<<<ceil_div(z + 1, tb), tb, 0, st>>>(csr_rows, z, m, rowptr);
-  // ---- CSC view: stable sort of CSR entries by column
-  init_pairs_kernel<<<gb, tb, 0, st>>>(u_col, b.k[0], b.v[0], z);
+  // ---- CSC view: stable sort of the CSR entries by column, then payload + colptr in one pass
   const int cur = radix_sort(b, z, bits_for(n), st);
-  gather_csc_kernel<<<gb, tb, 0, st>>>(csr_rows, val, b.v[cur], reinterpret_cast<uint32_t*>(csr2csc),
-                                       reinterpret_cast<uint32_t*>(row_csc), val_csc, z);
-  fill_ptr_kernel<<<ceil_div(z + 1, tb), tb, 0, st>>>(b.k[cur], z, n, colptr);
-  launches += 4 + (status ? 1 : 0);
+  finish_csc_kernel<<<gb1, tb, 0, st>>>(csr_rows, val, b.k[cur], b.v[cur], z, n, reinterpret_cast<uint32_t*>(csr2csc),
+                                        reinterpret_cast<uint32_t*>(row_csc), val_csc, colptr);
+  launches += 1;
   LPGNN_LAUNCH_OK();
   count_launches(launches);
   return LPGNN_OK;

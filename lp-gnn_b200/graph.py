@@ -20,6 +20,22 @@ import torch
 from . import _lib
 
 
+_STATUS_POOL = {}
+
+
+def _status_slot(dev, pool_words=4096):
+    """Hands out zero-initialised int32 status words from a per-device pool so that the hot loop does not pay a
+    memset launch per graph; the pool is replaced (one ``torch.zeros``) every ``pool_words`` graphs."""
+    key = (dev.type, dev.index)
+    pool = _STATUS_POOL.get(key)
+    if pool is None or pool[1] >= pool_words:
+        pool = [torch.zeros(pool_words, dtype=torch.int32, device=dev), 0]
+        _STATUS_POOL[key] = pool
+    word = pool[0][pool[1]:pool[1] + 1]
+    pool[1] += 1
+    return word
+
+
 class _StorageView:
     """``edge_index.storage.value()`` etc. (reference arch.py:21)."""
 
@@ -101,7 +117,7 @@ class BipartiteCSR:
         self.csr2csc = torch.empty(z, **i32)
         self.val = torch.empty(z, dtype=torch.float32, device=dev)
         self.val_csc = torch.empty(z, dtype=torch.float32, device=dev)
-        self._status = torch.empty(1, **i32)
+        self._status = _status_slot(dev)             # pre-zeroed word (the kernels only OR bits in)
         ws_bytes = lib.lpgnn_graph_build_workspace_bytes(z, self.m, self.n)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
