@@ -59,14 +59,23 @@ class ClockSampler:
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
+        """Starts the sampler and waits for its first sample, so that nvidia-smi's start-up (NVML init takes
+        driver locks for ~100 ms) does not land inside a timed region."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 5.0:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Samples taken from now on belong to the timed region."""
+        self.first = len(self.lines)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -82,7 +91,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "first", 0):]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
                 continue
@@ -217,12 +226,14 @@ def run_gpu(args):
         return h_status
 
     # ---- warm-up, then EXACTLY K timed steps between barrier + synchronize
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.mark()
     barrier(world)
     torch.cuda.synchronize()
     launches0 = lib.lpgnn_launch_count()
@@ -457,8 +468,8 @@ def main():
         args.warmup = args.warmup if args.warmup is not None else 1
         run_reference(args)
     else:
-        args.steps = args.steps if args.steps is not None else 50
-        args.warmup = args.warmup if args.warmup is not None else 5
+        args.steps = args.steps if args.steps is not None else 300
+        args.warmup = args.warmup if args.warmup is not None else 10
         run_gpu(args)
 
 

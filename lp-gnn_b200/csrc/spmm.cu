@@ -19,10 +19,12 @@ template <typename T> struct Chunk;  // 16-byte chunk of features
 template <> struct Chunk<float> {
   static constexpr int kElems = 4;
   __device__ static void fma(float (&acc)[4], float w, const uint4& v) {
-    acc[0] = fmaf(w, __uint_as_float(v.x), acc[0]);
-    acc[1] = fmaf(w, __uint_as_float(v.y), acc[1]);
-    acc[2] = fmaf(w, __uint_as_float(v.z), acc[2]);
-    acc[3] = fmaf(w, __uint_as_float(v.w), acc[3]);
+    const float2 ww = make_float2(w, w);
+    float2 a;
+    a = __ffma2_rn(ww, make_float2(__uint_as_float(v.x), __uint_as_float(v.y)), make_float2(acc[0], acc[1]));
+    acc[0] = a.x; acc[1] = a.y;
+    a = __ffma2_rn(ww, make_float2(__uint_as_float(v.z), __uint_as_float(v.w)), make_float2(acc[2], acc[3]));
+    acc[2] = a.x; acc[3] = a.y;
   }
   __device__ static uint4 pack(const float (&acc)[4]) {
     return make_uint4(__float_as_uint(acc[0]), __float_as_uint(acc[1]), __float_as_uint(acc[2]),
@@ -32,10 +34,13 @@ template <> struct Chunk<float> {
 template <> struct Chunk<__nv_bfloat16> {
   static constexpr int kElems = 8;
   __device__ static void fma(float (&acc)[8], float w, const uint4& v) {
-    acc[0] = fmaf(w, bf16_lo(v.x), acc[0]); acc[1] = fmaf(w, bf16_hi(v.x), acc[1]);
-    acc[2] = fmaf(w, bf16_lo(v.y), acc[2]); acc[3] = fmaf(w, bf16_hi(v.y), acc[3]);
-    acc[4] = fmaf(w, bf16_lo(v.z), acc[4]); acc[5] = fmaf(w, bf16_hi(v.z), acc[5]);
-    acc[6] = fmaf(w, bf16_lo(v.w), acc[6]); acc[7] = fmaf(w, bf16_hi(v.w), acc[7]);
+    // packed fp32 FMA (FFMA2, sm_100): the kernel is instruction-issue bound on unpack + FMA, not on DRAM
+    const float2 ww = make_float2(w, w);
+    float2 a;
+    a = __ffma2_rn(ww, make_float2(bf16_lo(v.x), bf16_hi(v.x)), make_float2(acc[0], acc[1])); acc[0] = a.x; acc[1] = a.y;
+    a = __ffma2_rn(ww, make_float2(bf16_lo(v.y), bf16_hi(v.y)), make_float2(acc[2], acc[3])); acc[2] = a.x; acc[3] = a.y;
+    a = __ffma2_rn(ww, make_float2(bf16_lo(v.z), bf16_hi(v.z)), make_float2(acc[4], acc[5])); acc[4] = a.x; acc[5] = a.y;
+    a = __ffma2_rn(ww, make_float2(bf16_lo(v.w), bf16_hi(v.w)), make_float2(acc[6], acc[7])); acc[6] = a.x; acc[7] = a.y;
   }
   __device__ static uint4 pack(const float (&acc)[8]) {
     return make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
@@ -111,102 +116,6 @@ spmm_rows_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ id
   }
 }
 
-// Wide-feature variant (one warp per row): persistent warps walk rows round-robin with a two-deep software
-// pipeline -- while row r is gathered, the (idx,val) list of row r+S and the ptr pair of row r+2S are already in
-// flight -- so the ptr -> idx -> feature-row dependent-load chain (three DRAM/L2 latencies per row, the bound of
-// the one-row-per-warp kernel above) is overlapped with the previous row's gather.  Warps that are resident
-// together work on a contiguous window of rows, which keeps banded LPs' gathers in L2.
-template <typename T, int CH>
-__global__ void __launch_bounds__(kThreads)
-spmm_rows_pipelined_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-                           const float* __restrict__ val, int32_t rows, const uint4* __restrict__ X,
-                           uint4* __restrict__ Y, int32_t chunks_per_row) {
-  constexpr int E = Chunk<T>::kElems;
-  const int lane = threadIdx.x & 31;
-  const int64_t stride = (int64_t)gridDim.x * (kThreads / 32);
-  int64_t r0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-  if (r0 >= rows) return;
-  int64_t r1 = r0 + stride, r2 = r1 + stride;
-  int32_t beg0 = ptr[r0], end0 = ptr[r0 + 1];
-  int32_t beg1 = 0, end1 = 0;
-  if (r1 < rows) { beg1 = ptr[r1]; end1 = ptr[r1 + 1]; }
-  int32_t idx0 = 0; float val0 = 0.f;
-  if (beg0 + lane < end0) { idx0 = __ldg(idx + beg0 + lane); val0 = __ldg(val + beg0 + lane); }
-  while (true) {
-    // prefetch: ptr of the row after next, (idx,val) of the next row
-    int32_t beg2 = 0, end2 = 0;
-    if (r2 < rows) { beg2 = ptr[r2]; end2 = ptr[r2 + 1]; }
-    int32_t idx1 = 0; float val1 = 0.f;
-    if (beg1 + lane < end1) { idx1 = __ldg(idx + beg1 + lane); val1 = __ldg(val + beg1 + lane); }
-
-    float acc[CH][E];
-#pragma unroll
-    for (int c = 0; c < CH; ++c)
-#pragma unroll
-      for (int k = 0; k < E; ++k) acc[c][k] = 0.f;
-    for (int32_t e0 = beg0; e0 < end0; e0 += 32) {
-      int32_t my_idx = idx0; float my_val = val0;
-      if (e0 != beg0) {  // rows longer than 32 entries: fetch the next slice of the list
-        my_idx = 0; my_val = 0.f;
-        if (e0 + lane < end0) { my_idx = __ldg(idx + e0 + lane); my_val = __ldg(val + e0 + lane); }
-      }
-      const int cnt = min(32, end0 - e0);
-      int j = 0;
-      for (; j + 2 <= cnt; j += 2) {  // two neighbours in flight, applied in CSR order
-        const int32_t i0 = __shfl_sync(0xffffffffu, my_idx, j), i1 = __shfl_sync(0xffffffffu, my_idx, j + 1);
-        const float w0 = __shfl_sync(0xffffffffu, my_val, j), w1 = __shfl_sync(0xffffffffu, my_val, j + 1);
-        uint4 v0[CH], v1[CH];
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const int ch = lane + c * 32;
-          if (ch < chunks_per_row) {
-            v0[c] = __ldg(X + (int64_t)i0 * chunks_per_row + ch);
-            v1[c] = __ldg(X + (int64_t)i1 * chunks_per_row + ch);
-          } else {
-            v0[c] = make_uint4(0, 0, 0, 0); v1[c] = make_uint4(0, 0, 0, 0);
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < CH; ++c) Chunk<T>::fma(acc[c], w0, v0[c]);
-#pragma unroll
-        for (int c = 0; c < CH; ++c) Chunk<T>::fma(acc[c], w1, v1[c]);
-      }
-      if (j < cnt) {
-        const int32_t i0 = __shfl_sync(0xffffffffu, my_idx, j);
-        const float w0 = __shfl_sync(0xffffffffu, my_val, j);
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const int ch = lane + c * 32;
-          if (ch < chunks_per_row) Chunk<T>::fma(acc[c], w0, __ldg(X + (int64_t)i0 * chunks_per_row + ch));
-        }
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int ch = lane + c * 32;
-      if (ch < chunks_per_row) Y[r0 * chunks_per_row + ch] = Chunk<T>::pack(acc[c]);
-    }
-    if (r1 >= rows) break;
-    r0 = r1; beg0 = beg1; end0 = end1; idx0 = idx1; val0 = val1;
-    r1 = r2; beg1 = beg2; end1 = end2;
-    r2 += stride;
-  }
-}
-
-template <typename T, int CH>
-int launch_pipelined(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const void* X, void* Y,
-                     int32_t chunks, cudaStream_t st) {
-  int per_sm = 0;
-  LPGNN_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmm_rows_pipelined_kernel<T, CH>, kThreads, 0));
-  if (per_sm < 1) per_sm = 1;
-  const int grid = min(ceil_div(rows, kThreads / 32), sm_count() * per_sm);
-  spmm_rows_pipelined_kernel<T, CH><<<grid, kThreads, 0, st>>>(ptr, idx, val, rows, reinterpret_cast<const uint4*>(X),
-                                                                reinterpret_cast<uint4*>(Y), chunks);
-  LPGNN_LAUNCH_OK();
-  count_launches(1);
-  return LPGNN_OK;
-}
-
 template <typename T, int G, int CH>
 int launch(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const void* X, void* Y,
            int32_t chunks, cudaStream_t st) {
@@ -227,10 +136,10 @@ int dispatch(const int32_t* ptr, const int32_t* idx, const float* val, int32_t r
   if (chunks <= 4) return launch<T, 4, 1>(ptr, idx, val, rows, X, Y, chunks, st);
   if (chunks <= 8) return launch<T, 8, 1>(ptr, idx, val, rows, X, Y, chunks, st);
   if (chunks <= 16) return launch<T, 16, 1>(ptr, idx, val, rows, X, Y, chunks, st);
-  if (chunks <= 32) return launch_pipelined<T, 1>(ptr, idx, val, rows, X, Y, chunks, st);
-  if (chunks <= 64) return launch_pipelined<T, 2>(ptr, idx, val, rows, X, Y, chunks, st);
-  if (chunks <= 128) return launch_pipelined<T, 4>(ptr, idx, val, rows, X, Y, chunks, st);
-  if (chunks <= 256) return launch_pipelined<T, 8>(ptr, idx, val, rows, X, Y, chunks, st);
+  if (chunks <= 32) return launch<T, 32, 1>(ptr, idx, val, rows, X, Y, chunks, st);
+  if (chunks <= 64) return launch<T, 32, 2>(ptr, idx, val, rows, X, Y, chunks, st);
+  if (chunks <= 128) return launch<T, 32, 4>(ptr, idx, val, rows, X, Y, chunks, st);
+  if (chunks <= 256) return launch<T, 32, 8>(ptr, idx, val, rows, X, Y, chunks, st);
   set_error("spmm: feature row of %d bytes exceeds the 4096-byte limit of one pass", chunks * 16);
   return LPGNN_EINVAL;
 }

@@ -66,7 +66,12 @@ class BipartiteCSR:
         self._transposed = False    # True: this object presents A^T (shares buffers with its parent)
         self._sorted_hint = False   # caller's is_sorted=True: skip the COO sort (verified on the device)
         self._status = None         # device int32: bit0 = sorted claim false, bit1 = index out of range
-        self.storage = _StorageView(self)
+
+    @property
+    def storage(self):
+        """``edge_index.storage`` (created on demand: a stored back-reference would make every graph a reference
+        cycle, which keeps its HBM buffers alive until the cyclic GC runs and forces fresh cudaMallocs)."""
+        return _StorageView(self)
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -109,14 +114,18 @@ class BipartiteCSR:
         dev = row.device
         z = int(row.shape[0])
         lib = _lib.load()
-        i32 = dict(dtype=torch.int32, device=dev)
-        self.rowptr = torch.empty(self.m + 1, **i32)
-        self.colptr = torch.empty(self.n + 1, **i32)
-        self.col = torch.empty(z, **i32)
-        self.row_csc = torch.empty(z, **i32)
-        self.csr2csc = torch.empty(z, **i32)
-        self.val = torch.empty(z, dtype=torch.float32, device=dev)
-        self.val_csc = torch.empty(z, dtype=torch.float32, device=dev)
+        # one allocation for all seven arrays (16-byte aligned segments); views are carved out of it
+        r4 = lambda k: (k + 3) // 4 * 4
+        sizes = [r4(self.m + 1), r4(self.n + 1), r4(z), r4(z), r4(z), r4(z), r4(z)]
+        offs = [0]
+        for sz in sizes:
+            offs.append(offs[-1] + sz)
+        buf = torch.empty(max(offs[-1], 4), dtype=torch.int32, device=dev)
+        seg = lambda i, k: buf[offs[i]:offs[i] + k]
+        self._buf = buf
+        self.rowptr, self.colptr = seg(0, self.m + 1), seg(1, self.n + 1)
+        self.col, self.row_csc, self.csr2csc = seg(2, z), seg(3, z), seg(4, z)
+        self.val, self.val_csc = seg(5, z).view(torch.float32), seg(6, z).view(torch.float32)
         self._status = _status_slot(dev)             # pre-zeroed word (the kernels only OR bits in)
         ws_bytes = lib.lpgnn_graph_build_workspace_bytes(z, self.m, self.n)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -128,8 +137,8 @@ class BipartiteCSR:
                                        self.csr2csc.data_ptr(), self._status.data_ptr(), ws.data_ptr(), ws_bytes,
                                        _lib.stream_ptr())
         _lib.check(rc, "lpgnn_graph_build")
-        # the caching allocator keeps `ws` / the COO alive until the stream has consumed them
-        ws.record_stream(torch.cuda.current_stream(dev))
+        # `ws` and the COO are allocated and consumed on the same (current) stream, so the caching allocator's
+        # stream-ordered reuse is already safe; no record_stream (it defers reuse and forces fresh cudaMallocs).
         self._coo = None
 
     def check(self):
@@ -193,7 +202,6 @@ class BipartiteCSR:
         v = BipartiteCSR.__new__(BipartiteCSR)
         v.__dict__.update(self.__dict__)
         v._transposed = not self._transposed
-        v.storage = _StorageView(v)
         return v
 
     def sparse_sizes(self):
@@ -234,7 +242,6 @@ class BipartiteCSR:
                 setattr(g, k, getattr(self, k).clone())
         if self._coo is not None:
             g._coo = tuple(t.clone() for t in self._coo)
-        g.storage = _StorageView(g)
         return g
 
     def set_value(self, value, layout="coo"):
