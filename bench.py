@@ -11,8 +11,9 @@ BASELINE.json, GCN_FC(8,8,hids=1024,depth=3) inference on a 50K x 100K LP with ~
     ->  basis selection (softmax / top-m / status)
 
 * ``value``  LPs/s with the step's inputs (COO, node features) already resident in HBM.
-* ``e2e``    the same metric through the public API with HOST (pinned) inputs: H2D copies of the COO
-             and the features, the step, and a D2H copy of the status vector inside the timed region.
+* ``e2e``    the same metric through the public API (``pipeline.BasisPipeline``) with HOST (pinned) inputs:
+             per step one H2D copy of the packed COO + features (prefetched on a side stream while the previous LP
+             computes), the step, and a D2H copy of the status vector, all inside the timed region.
 * ``roofline``      dominant kernel (tcgen05 node transform) against the measured bf16 peak, timed
                     live with CUDA events; ``kernels`` lists every kernel of the step the same way
                     (HBM-bound ones against the measured copy bandwidth).
@@ -190,23 +191,13 @@ def run_gpu(args):
     model.set_precision(args.precision)
 
     # host (pinned) inputs of one step: one packed staging buffer [row | col | val | x_s | x_t] (4-byte words)
-    parts = [lp.row.astype(np.int32).view(np.int32), lp.col.astype(np.int32), lp.a_data.astype(np.float32).view(np.int32),
-             lp.c_feas.reshape(-1).view(np.int32), lp.v_feas.reshape(-1).view(np.int32)]
-    h_pack = torch.from_numpy(np.concatenate(parts)).pin_memory()
-    offs = np.cumsum([0] + [p.shape[0] for p in parts])
-    h_row, h_col, h_val, h_xs, h_xt = (h_pack[offs[i]:offs[i + 1]] for i in range(5))
-    h_val, h_xs, h_xt = h_val.view(torch.float32), h_xs.view(torch.float32).view(m, 8), h_xt.view(torch.float32).view(n, 8)
-    h_status = torch.empty(m + n, dtype=torch.uint8).pin_memory()
-    h2d_bytes = h_pack.numel() * 4
-    d2h_bytes = h_status.numel()
-
-    def unpack(d_pack):
-        r, c, v, xs, xt = (d_pack[offs[i]:offs[i + 1]] for i in range(5))
-        return r, c, v.view(torch.float32), xs.view(torch.float32).view(m, 8), xt.view(torch.float32).view(n, 8)
+    from lpgnn_b200.pipeline import BasisPipeline, pack_lp, unpack_device
+    host_lp = pack_lp(lp.row, lp.col, lp.a_data, lp.c_feas, lp.v_feas, is_sorted=True)
+    h2d_bytes = host_lp.nbytes
+    d2h_bytes = m + n
 
     # device-resident copies for the HBM-resident arm
-    d_row, d_col, d_val = h_row.to(dev), h_col.to(dev), h_val.to(dev)
-    d_xs, d_xt = h_xs.to(dev), h_xt.to(dev)
+    d_row, d_col, d_val, d_xs, d_xt = (t.clone() for t in unpack_device(host_lp.pack.to(dev), host_lp))
 
     def step_resident():
         # the processed-file COO is row-major sorted (dataset.py:208-210: A.tocoo() of a CSR) -> is_sorted hint
@@ -215,15 +206,15 @@ def run_gpu(args):
         with torch.no_grad():
             return model.predict_basis(batch, int64=False)
 
-    def step_e2e():
-        row, col, val, xs, xt = unpack(h_pack.to(dev, non_blocking=True))     # ONE H2D copy of the step's inputs
-        g = BipartiteCSR.from_coo(row, col, val, m, n, is_sorted=True)
-        batch = types.SimpleNamespace(x_s=xs, x_t=xt, edge_index=g)
-        with torch.no_grad():
-            st = model.predict_basis(batch, int64=False)
-        h_status.copy_(st, non_blocking=True)
-        torch.cuda.current_stream().synchronize()       # the caller needs the statuses on the host
-        return h_status
+    pipe = BasisPipeline(model, dev)
+
+    def run_e2e(k):
+        """k steps through the public pipeline API: per step one H2D copy of the packed LP from pinned host memory
+        (prefetched on a side stream while the previous LP computes) and one D2H copy of its statuses."""
+        n_basic = 0
+        for _, st in pipe.run([host_lp] * k):
+            n_basic = int((st == 1).sum()) if _ == k - 1 else n_basic
+        return n_basic
 
     # ---- warm-up, then EXACTLY K timed steps between barrier + synchronize
     sampler = ClockSampler(local)
@@ -250,13 +241,11 @@ def run_gpu(args):
     assert n_basic == m, f"basis invariant violated: {n_basic} basic nodes for m={m}"
 
     # ---- end-to-end arm (host buffers, H2D + D2H inside the timed region)
-    for _ in range(3):
-        step_e2e()
+    run_e2e(3)
     barrier(world)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
+    assert run_e2e(args.steps) == m
     torch.cuda.synchronize()
     t_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
     barrier(world)

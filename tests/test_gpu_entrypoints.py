@@ -105,3 +105,29 @@ def test_two_gpu_data_parallel_training_matches_single_process(cuda, dataset_roo
     import json
     log = json.load(open(log_dir + "train_log.json"))
     assert log["world"] == 2 and log["history"][-1]["loss"] < log["history"][0]["loss"]
+
+
+def test_basis_pipeline_matches_direct_calls(cuda):
+    """Host-buffer pipeline (packed H2D on a side stream, uint8 D2H) == direct per-LP calls, for ragged sizes."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import arch, synth
+    from lpgnn_b200.graph import BipartiteCSR
+    from lpgnn_b200.pipeline import BasisPipeline, pack_lp
+    torch.manual_seed(0)
+    model = arch.GCN_FC(8, 8, hids=128, depth=3).to(cuda).eval().set_precision("bf16")
+    sizes = [(300, 700, 3000), (50, 90, 300), (1200, 2000, 9000), (5, 9, 20), (700, 1500, 6000)]
+    lps = [synth.processed_lp(m, n, z, seed=40 + i) for i, (m, n, z) in enumerate(sizes)]
+    hosts = [pack_lp(lp.row, lp.col, lp.a_data, lp.c_feas, lp.v_feas) for lp in lps]
+    pipe = BasisPipeline(model, cuda)
+    got = {i: st.copy() for i, st in pipe.run(hosts)}
+    assert sorted(got) == list(range(len(lps)))
+    for i, lp in enumerate(lps):
+        g = BipartiteCSR.from_coo_arrays(lp.row, lp.col, lp.a_data.astype(np.float32), lp.m, lp.n, cuda, is_sorted=True)
+        batch = types.SimpleNamespace(x_s=torch.from_numpy(lp.c_feas).to(cuda), x_t=torch.from_numpy(lp.v_feas).to(cuda),
+                                      edge_index=g)
+        exp = model.predict_basis(batch, int64=False).cpu().numpy()
+        np.testing.assert_array_equal(got[i], exp)
+        assert int((got[i] == 1).sum()) == lp.m
+    # a second pass over the same pipeline object reuses the slots
+    again = {i: st.copy() for i, st in pipe.run(hosts[::-1])}
+    np.testing.assert_array_equal(again[0], got[len(lps) - 1])
