@@ -269,6 +269,14 @@ def run_gpu(args):
         "clocks": clocks,
     }
 
+    if not args.no_train:
+        tr = train_throughput(cfg, lp, dev, args.precision, max(10, min(args.steps, 50)), 3, world)
+        c1 = workload_spec("C1")
+        lp1 = synth.processed_lp(c1["m"], c1["n"], c1["nnz"], seed=c1["seed"] + 1000 * rank, structure=args.structure)
+        tr1 = train_throughput(c1, lp1, dev, "fp32", max(10, min(args.steps, 100)), 3, world)
+        if rank == 0:
+            out["train"] = tr
+            out["train_c1_fp32"] = tr1
     if rank == 0 and not args.no_kernels:
         out.update(kernel_rooflines(model, lp, dev, peaks, bf16, args))
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -278,6 +286,53 @@ def run_gpu(args):
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def train_throughput(cfg, lp, dev, precision, steps, warmup, world):
+    """Training step of the same shape (reference train.py:117-129): forward, balanced loss, backward through the
+    CUDA kernels, gradient all-reduce (N > 1) and Adam, one LP graph per step per GPU.  Returns steps/s and
+    message-passing edges/s (fwd+bwd): nnz * 2 directions * (depth-1) conv layers * 2."""
+    import types as _t
+    from lpgnn_b200 import arch
+    from lpgnn_b200.graph import BipartiteCSR
+    from lpgnn_b200.losses import balanced
+    from lpgnn_b200.train import allreduce_gradients, broadcast_parameters
+    torch.manual_seed(0)
+    model = arch.GCN_FC(8, 8, hids=cfg["hids"], depth=cfg["depth"]).to(dev).train().set_precision(precision)
+    broadcast_parameters(model, world)
+    params = list(model.parameters())
+    opt = torch.optim.Adam(params, lr=1e-3, weight_decay=5e-4)
+    g = BipartiteCSR.from_coo_arrays(lp.row, lp.col, lp.a_data.astype(np.float32), lp.m, lp.n, dev, is_sorted=True)
+    batch = _t.SimpleNamespace(x_s=torch.from_numpy(lp.c_feas).to(dev), x_t=torch.from_numpy(lp.v_feas).to(dev), edge_index=g)
+    y_s, y_t = torch.from_numpy(lp.y_s).to(dev), torch.from_numpy(lp.y_t).to(dev)
+
+    def step():
+        lc, lv = model(batch)
+        loss = balanced(lc, lv, y_s, y_t)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        allreduce_gradients(params, world)
+        opt.step()
+        return loss
+
+    for _ in range(max(warmup, 3)):
+        step()
+    barrier(world)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    t_ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    assert bool(torch.isfinite(loss))
+    sps = world * steps / (t_ms / 1e3)
+    return {"workload": f"{cfg['name']}-shaped LP, GCN_FC(8,8,hids={cfg['hids']},depth={cfg['depth']}) training step "
+                        f"(fwd + balanced loss + bwd + Adam{' + NCCL grad all-reduce' if world > 1 else ''}), dp={model.dp}",
+            "precision": precision, "steps": steps, "ms_per_step": t_ms / steps, "lps_per_sec": sps,
+            "mp_edges_per_sec_fwd_bwd": mp_edges(lp.nnz, cfg["depth"], fwd_bwd=True) * sps}
 
 
 def kernel_rooflines(model, lp, dev, peaks, bf16, args):
@@ -451,6 +506,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-kernels", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 3

@@ -201,6 +201,15 @@ LPGNN_API int lpgnn_basis_select(const float* logits_cons, int32_t m, const floa
  * backward is lpgnn_spmm on the other orientation; the entry points below are the rest.
  * ============================================================================================= */
 
+/* out[M,N] (f32) = A[M,K] * B[N,K]^T, bf16 operands, K a multiple of 64 and LARGE (the node dimension): the
+ * weight-gradient GEMM dW = dPre^T X on transposed, zero-padded copies (lpgnn_transpose).  Few output
+ * tiles and a long reduction, so the tcgen05 kernel runs split-K: (tile, K-slice) work items fill the SMs,
+ * partial tiles go to `workspace` and are summed in a fixed order (deterministic). */
+LPGNN_API int32_t lpgnn_gemm_tn_splits(int32_t M, int32_t N, int32_t K);
+LPGNN_API size_t lpgnn_gemm_tn_workspace_bytes(int32_t M, int32_t N, int32_t K);
+LPGNN_API int lpgnn_gemm_tn(const void* A, const void* B, int32_t M, int32_t N, int32_t K, float* out,
+                  void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
+
 /* Backward of lpgnn_head_mask wrt the hidden activation (reference arch.py:186-191, 129-141), fused with
  * the ReLU / inverted-dropout mask of that activation:
  *   draw[i,:] = d(10*raw/max(|raw|,1e-12))^T dlogits[i,:]        (mask offsets are constants)

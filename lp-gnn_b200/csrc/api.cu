@@ -55,7 +55,7 @@ int node_transform_f32(const float* A1, int K1, const float* W1, const float* A2
                        const float* bias, int M, int N, float* out, int relu, cudaStream_t st);
 int node_transform_bf16(const void* A1, int K1, const void* W1, const void* A2, int K2, const void* W2,
                         const float* bias, int M, int N, void* out, int out_f32, int relu, const float* head_w,
-                        float* head_partial, cudaStream_t st);
+                        float* head_partial, int ksplit, cudaStream_t st);
 
 }  // namespace lpgnn
 
@@ -91,7 +91,7 @@ extern "C" int lpgnn_node_transform(const void* A1, int32_t K1, const void* W1, 
     return node_transform_f32((const float*)A1, K1, (const float*)W1, (const float*)A2, K2, (const float*)W2, bias, M,
                               N, (float*)out, relu, st);
   return node_transform_bf16(A1, K1, W1, A2, K2, W2, bias, M, N, out, out_dtype == LPGNN_F32 ? 1 : 0, relu, nullptr,
-                             nullptr, st);
+                             nullptr, 1, st);
 }
 
 extern "C" int32_t lpgnn_node_transform_head_parts(int32_t N) { return N % 256 == 0 ? N / 256 : (N % 128 == 0 ? N / 128 : N / 64); }
@@ -107,5 +107,61 @@ extern "C" int lpgnn_node_transform_head(const void* A1, int32_t K1, const void*
   LPGNN_REQUIRE(K2 == 0 || (A2 && W2), "node_transform_head: K2=%d but A2/W2 is null", K2);
   if (K2 == 0) { A2 = nullptr; W2 = nullptr; }
   return node_transform_bf16(A1, K1, W1, A2, K2, W2, bias, M, N, out, 0, (epilogue & LPGNN_EPI_RELU) ? 1 : 0, head_w,
-                             head_partial, (cudaStream_t)stream);
+                             head_partial, 1, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------- split-K GEMM
+namespace lpgnn {
+__global__ void splitk_reduce_kernel(const float4* __restrict__ partial, int splits, int64_t quads, float4* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= quads) return;
+  float4 acc = partial[i];
+  for (int s = 1; s < splits; ++s) {  // fixed order: deterministic
+    const float4 v = partial[(int64_t)s * quads + i];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  out[i] = acc;
+}
+}  // namespace lpgnn
+
+extern "C" int32_t lpgnn_gemm_tn_splits(int32_t M, int32_t N, int32_t K) {
+  // enough (tile, slice) work items to fill the machine, at least 8 K-blocks of 64 per slice
+  const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
+  const int tiles = ((M + 127) / 128) * (N / BN);
+  int splits = (2 * sm_count() + tiles - 1) / tiles;
+  const int max_by_k = K / 64 / 8;
+  if (splits > max_by_k) splits = max_by_k;
+  if (splits < 1) splits = 1;
+  if (splits > 32) splits = 32;
+  // every slice must own at least one K block: re-derive the slice count from the per-slice block count
+  const int kblocks = K / 64;
+  const int kb_per = (kblocks + splits - 1) / splits;
+  return (kblocks + kb_per - 1) / kb_per;
+}
+
+extern "C" size_t lpgnn_gemm_tn_workspace_bytes(int32_t M, int32_t N, int32_t K) {
+  return (size_t)lpgnn_gemm_tn_splits(M, N, K) * (size_t)M * (size_t)N * sizeof(float);
+}
+
+extern "C" int lpgnn_gemm_tn(const void* A, const void* B, int32_t M, int32_t N, int32_t K, float* out, void* workspace,
+                             size_t workspace_bytes, lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && out, "gemm_tn: bad arguments");
+  const int splits = lpgnn_gemm_tn_splits(M, N, K);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (splits == 1) return node_transform_bf16(A, K, B, nullptr, 0, nullptr, nullptr, M, N, out, 1, 0, nullptr, nullptr, 1, st);
+  if (workspace_bytes < lpgnn_gemm_tn_workspace_bytes(M, N, K) || !workspace) {
+    set_error("gemm_tn: workspace too small");
+    return LPGNN_EWORKSPACE;
+  }
+  LPGNN_REQUIRE(((int64_t)M * N) % 4 == 0 && (uintptr_t)workspace % 16 == 0 && (uintptr_t)out % 16 == 0,
+                "gemm_tn: M*N must be a multiple of 4 and buffers 16-byte aligned");
+  if (int rc = node_transform_bf16(A, K, B, nullptr, 0, nullptr, nullptr, M, N, workspace, 1, 0, nullptr, nullptr, splits, st))
+    return rc;
+  const int64_t quads = (int64_t)M * N / 4;
+  splitk_reduce_kernel<<<ceil_div(quads, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(workspace), splits, quads,
+                                                            reinterpret_cast<float4*>(out));
+  LPGNN_LAUNCH_OK();
+  count_launches(1);
+  return LPGNN_OK;
 }

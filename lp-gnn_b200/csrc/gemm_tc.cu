@@ -48,7 +48,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2, int kblocks1,
                int kblocks2, const float* __restrict__ bias, OutT* __restrict__ out, int M, int N,
                int relu, const float* __restrict__ head_w /*[3,N] or null*/,
-               float* __restrict__ head_partial /*[N/BN][M][3] or null*/) {
+               float* __restrict__ head_partial /*[N/BN][M][3] or null*/, int ksplit) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle atoms
@@ -68,8 +68,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_n = N / BN;
   const int num_m = (M + BM - 1) / BM;
-  const int num_tiles = num_m * num_n;
-  const int kblocks = kblocks1 + kblocks2;
+  // split-K (weight gradients: few output tiles, reduction over all nodes): work item = (output tile, K slice);
+  // slice s writes its partial tile to out + s*M*N (fp32), summed afterwards in a fixed order.
+  const int num_out_tiles = num_m * num_n;
+  const int num_tiles = num_out_tiles * ksplit;
+  const int kblocks_all = kblocks1 + kblocks2;
+  const int kb_per = (kblocks_all + ksplit - 1) / ksplit;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA1);
@@ -95,8 +99,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const int ot = tile % num_out_tiles, split = tile / num_out_tiles;
+        const int m_blk = ot / num_n, n_blk = ot % num_n;
+        const int kb_begin = split * kb_per, kb_end = min(kb_begin + kb_per, kblocks_all);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
           const bool first = kb < kblocks1;
@@ -119,7 +125,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         ptx::mbar_wait(&tmem_empty[buf], use_phase ^ 1);  // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const int split = tile / num_out_tiles;
+        const int kb_begin = split * kb_per, kb_end = min(kb_begin + kb_per, kblocks_all);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           const uint64_t adesc = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_a + stage * C::kABytes));
@@ -127,7 +135,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             // advance 16 elements = 32 bytes along K inside the swizzle row: +2 in 16-byte units
-            ptx::umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
           ptx::umma_commit(&empty_bar[stage]);  // slot free once these MMAs have read it
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -141,7 +149,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..127
     int t = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int ot = tile % num_out_tiles, split = tile / num_out_tiles;
+      const int m_blk = ot / num_n, n_blk = ot % num_n;
+      OutT* const out_t = out ? out + (int64_t)split * M * N : nullptr;
       const int buf = t & 1;
       const uint32_t use_phase = (t >> 1) & 1;
       // stage the bias slice of this tile
@@ -211,7 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           const uint4 v = *reinterpret_cast<const uint4*>(my_stage + rr * C::kStagePitch + piece * 16);
           const int64_t grow = row_base + rr;
           if (grow < M) {
-            uint8_t* dst = reinterpret_cast<uint8_t*>(out + grow * N + (int64_t)n_blk * BN + pc * kColsPerPiece);
+            uint8_t* dst = reinterpret_cast<uint8_t*>(out_t + grow * N + (int64_t)n_blk * BN + pc * kColsPerPiece);
             *reinterpret_cast<uint4*>(dst + piece * 16) = v;
           }
         }
@@ -270,7 +280,7 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int bo
 template <int BN, typename OutT>
 int launch(const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& a2, const CUtensorMap& w2, int kb1, int kb2,
            const float* bias, void* out, int M, int N, int relu, const float* head_w, float* head_partial,
-           cudaStream_t st) {
+           int ksplit, cudaStream_t st) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -278,11 +288,11 @@ int launch(const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& a2, 
                                        C::kSmemBytes));
     attr_set = true;
   }
-  const int tiles = ceil_div(M, BM) * (N / BN);
+  const int tiles = ceil_div(M, BM) * (N / BN) * ksplit;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   gemm_tc_kernel<BN, OutT><<<grid, kThreads, C::kSmemBytes, st>>>(a1, w1, a2, w2, kb1, kb2, bias,
                                                                   reinterpret_cast<OutT*>(out), M, N, relu, head_w,
-                                                                  head_partial);
+                                                                  head_partial, ksplit);
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;
@@ -292,13 +302,15 @@ int launch(const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& a2, 
 
 int node_transform_bf16(const void* A1, int K1, const void* W1, const void* A2, int K2, const void* W2,
                         const float* bias, int M, int N, void* out, int out_f32, int relu, const float* head_w,
-                        float* head_partial, cudaStream_t st) {
+                        float* head_partial, int ksplit, cudaStream_t st) {
   LPGNN_REQUIRE(K1 > 0 && K1 % BK == 0 && K2 % BK == 0, "node_transform(bf16): K1=%d, K2=%d must be multiples of 64", K1, K2);
   LPGNN_REQUIRE(N % 64 == 0, "node_transform(bf16): N=%d must be a multiple of 64", N);
   LPGNN_REQUIRE((uintptr_t)A1 % 16 == 0 && (uintptr_t)W1 % 16 == 0 && (uintptr_t)A2 % 16 == 0 &&
                     (uintptr_t)W2 % 16 == 0 && (uintptr_t)out % 16 == 0,
                 "node_transform(bf16): operands must be 16-byte aligned");
   LPGNN_REQUIRE(out || (head_w && head_partial), "node_transform(bf16): no output requested");
+  LPGNN_REQUIRE(ksplit >= 1 && (ksplit == 1 || (out_f32 && !bias && !relu && !head_w && ksplit <= (K1 + K2) / BK)),
+                "node_transform(bf16): split-K needs fp32 partial outputs, no epilogue, and ksplit <= K/64");
   LPGNN_REQUIRE(!head_w || (head_partial && !out_f32), "node_transform(bf16): fused head needs head_partial and bf16 mode");
   const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
   const bool two = A2 != nullptr && K2 > 0;
@@ -313,13 +325,13 @@ int node_transform_bf16(const void* A1, int K1, const void* W1, const void* A2, 
   }
   const int kb1 = K1 / BK, kb2 = two ? K2 / BK : 0;
   if (out_f32) {
-    if (BN == 256) return launch<256, float>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, st);
-    if (BN == 128) return launch<128, float>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, st);
-    return launch<64, float>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, st);
+    if (BN == 256) return launch<256, float>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, ksplit, st);
+    if (BN == 128) return launch<128, float>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, ksplit, st);
+    return launch<64, float>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, ksplit, st);
   }
-  if (BN == 256) return launch<256, __nv_bfloat16>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, st);
-  if (BN == 128) return launch<128, __nv_bfloat16>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, st);
-  return launch<64, __nv_bfloat16>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, st);
+  if (BN == 256) return launch<256, __nv_bfloat16>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, ksplit, st);
+  if (BN == 128) return launch<128, __nv_bfloat16>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, ksplit, st);
+  return launch<64, __nv_bfloat16>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, ksplit, st);
 }
 
 }  // namespace lpgnn

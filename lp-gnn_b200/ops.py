@@ -173,6 +173,25 @@ def basis_select(logits_cons, logits_vars, k_basic=None, int64=True, want_counts
 
 
 # ------------------------------------------------------------------------------------------------ backward ops
+def gemm_tn(a, b):
+    """``a @ b.T`` -> fp32, for bf16 ``a [M,K]``, ``b [N,K]`` with a long K (split-K tensor-core GEMM);
+    fp32 operands go through the CUDA-core kernel."""
+    require_cuda(a, b)
+    a, b = _contig(a), _contig(b)
+    if a.dtype != torch.bfloat16:
+        return node_transform(a, b, out_dtype=torch.float32)
+    M, K = a.shape
+    N = b.shape[0]
+    lib = _lib.load()
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    ws_bytes = lib.lpgnn_gemm_tn_workspace_bytes(M, N, K)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = lib.lpgnn_gemm_tn(a.data_ptr(), b.data_ptr(), M, N, K, out.data_ptr(), ws.data_ptr(), ws_bytes, stream_ptr())
+    check(rc, "lpgnn_gemm_tn")
+    return out
+
+
 def head_mask_bwd(dlogits, raw, h_act, w, scale=1.0):
     """Backward of ``head_mask`` wrt the hidden activation, fused with its ReLU/dropout mask.
     Returns ``(dH[rows,H], draw[rows,3])``."""

@@ -31,10 +31,13 @@ def _param_list(model):
     return out
 
 
-def _wgrad(d_pre, d_pre_t, x):
-    """dW[N,K] = d_pre^T x via the TN GEMM on transposed copies (reduction over the node dimension)."""
-    xt = ops.transpose(x)                                   # [K, M]
-    return ops.node_transform(d_pre_t, xt, out_dtype=torch.float32)
+def _wgrad_pair(d_pre_t, x_rel, x_root):
+    """(dW_rel, dW_root) = d_pre^T [x_rel | x_root] with ONE split-K GEMM over the node dimension: the two
+    operands are transposed into the halves of one [K_rel + K_root, M_pad] buffer."""
+    xt = torch.cat((ops.transpose(x_rel), ops.transpose(x_root)), dim=0)     # [2K, M_pad] (weights-sized rows, node-sized cols)
+    g = ops.gemm_tn(d_pre_t, xt)                                             # [N, 2K] fp32
+    k = x_rel.shape[1]
+    return g[:, :k].contiguous(), g[:, k:].contiguous()
 
 
 class _GCNFCFunction(torch.autograd.Function):
@@ -115,12 +118,10 @@ class _GCNFCFunction(torch.autograd.Function):
             left_in, right_in = acts[2 + 4 * i], acts[3 + 4 * i]       # inputs of this layer (outputs of the previous)
             dps_t, dpt_t = ops.transpose(d_pre_s), ops.transpose(d_pre_t)
             g = 6 + 6 * i
-            grads[g + 0] = _wgrad(d_pre_t, dpt_t, agg_t)               # l2r lin_rel.weight
+            grads[g + 0], grads[g + 2] = _wgrad_pair(dpt_t, agg_t, right_in)   # l2r lin_rel / lin_root weights
             grads[g + 1] = ops.colsum(d_pre_t)
-            grads[g + 2] = _wgrad(d_pre_t, dpt_t, right_in)            # l2r lin_root.weight
-            grads[g + 3] = _wgrad(d_pre_s, dps_t, agg_s)               # r2l lin_rel.weight
+            grads[g + 3], grads[g + 5] = _wgrad_pair(dps_t, agg_s, left_in)    # r2l lin_rel / lin_root weights
             grads[g + 4] = ops.colsum(d_pre_s)
-            grads[g + 5] = _wgrad(d_pre_s, dps_t, left_in)             # r2l lin_root.weight
             del dps_t, dpt_t
             # data gradients (weights transposed once per step: [K,N] K-major for the TN kernel)
             w_rel_l2r_t, w_root_l2r_t = cast(w[0]).t().contiguous(), cast(w[2]).t().contiguous()

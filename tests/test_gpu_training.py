@@ -167,3 +167,21 @@ def test_dropout_statistics_and_determinism(cuda):
     assert abs(keep - 0.9) < 2e-3
     assert abs(float(a.mean()) - 1.0) < 3e-3                        # inverted scaling keeps the mean
     assert set(torch.unique(a).cpu().tolist()) == {0.0, float(torch.tensor(1.0 / 0.9, dtype=torch.float32))}
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 2048, 100_032), (64, 128, 1024), (128, 256, 64 * 9), (1024, 1024, 50_048)])
+def test_gemm_tn_splitk(cuda, M, N, K):
+    """Split-K tensor-core GEMM (weight gradients): exact bf16 products, fp32 accumulate, deterministic."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import _lib, ops
+    g = torch.Generator(device="cuda").manual_seed(K % 1000)
+    a = torch.randn(M, K, device=cuda, generator=g).to(torch.bfloat16)
+    b = torch.randn(N, K, device=cuda, generator=g).to(torch.bfloat16)
+    out = ops.gemm_tn(a, b)
+    splits = _lib.load().lpgnn_gemm_tn_splits(M, N, K)
+    assert splits >= 1 and (K // 64 + splits - 1) // splits * (splits - 1) < K // 64      # no empty slice
+    rows = torch.randint(0, M, (16,), device=cuda, generator=g)
+    exp = a[rows].double() @ b.double().T
+    err = (out[rows].double() - exp).abs().max()
+    assert float(err) < 2e-4 * K ** 0.5 * 4, float(err)
+    assert torch.equal(out, ops.gemm_tn(a, b))
