@@ -301,7 +301,7 @@ def train_throughput(cfg, lp, dev, precision, steps, warmup, world):
     model = arch.GCN_FC(8, 8, hids=cfg["hids"], depth=cfg["depth"]).to(dev).train().set_precision(precision)
     broadcast_parameters(model, world)
     params = list(model.parameters())
-    opt = torch.optim.Adam(params, lr=1e-3, weight_decay=5e-4)
+    opt = torch.optim.Adam(params, lr=1e-3, weight_decay=5e-4, fused=True)
     g = BipartiteCSR.from_coo_arrays(lp.row, lp.col, lp.a_data.astype(np.float32), lp.m, lp.n, dev, is_sorted=True)
     batch = _t.SimpleNamespace(x_s=torch.from_numpy(lp.c_feas).to(dev), x_t=torch.from_numpy(lp.v_feas).to(dev), edge_index=g)
     y_s, y_t = torch.from_numpy(lp.y_s).to(dev), torch.from_numpy(lp.y_t).to(dev)

@@ -134,19 +134,26 @@ reduce_partials_kernel(const float* __restrict__ partial, int nchunks, int64_t w
 
 // ------------------------------------------------------------------------------------------- small_wgrad
 // dW[c][k] = sum_r dY[r][c] * Z[r][k]  (k < K <= KMAX), optionally dB[c] = sum_r dY[r][c].
-// Block = 256 columns x kChunkRows rows; a thread owns one column and keeps its K partial sums in
-// registers; Z rows are staged in shared memory 64 at a time (broadcast reads).
+// Block = 512 columns x kChunkRows rows; a thread owns TWO adjacent columns and keeps their K partial sums in
+// registers as float2 (packed FFMA2); Z rows are staged in shared memory 64 at a time and read as broadcast
+// 128-bit loads shared by both columns.
+__device__ __forceinline__ float2 load2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 load2(const __nv_bfloat16* p) {
+  const uint32_t w = *reinterpret_cast<const uint32_t*>(p);
+  return make_float2(bf16_lo(w), bf16_hi(w));
+}
+
 template <typename T, int KMAX>
 __global__ void __launch_bounds__(kThreads)
 small_wgrad_partial_kernel(const T* __restrict__ dY, const float* __restrict__ Z, int ldz, int K, int64_t M, int N,
                            float* __restrict__ partial /*[nchunks][N][KMAX+1]*/) {
-  __shared__ float zs[64][KMAX];
-  const int c = blockIdx.x * kThreads + threadIdx.x;
+  __shared__ __align__(16) float zs[64][KMAX];
+  const int c = (blockIdx.x * kThreads + threadIdx.x) * 2;      // N is even (checked on the host)
   const int64_t r0 = (int64_t)blockIdx.y * kChunkRows, r1 = min(r0 + kChunkRows, M);
-  float acc[KMAX];
+  float2 acc[KMAX];
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
-  float accb = 0.f;
+  for (int k = 0; k < KMAX; ++k) acc[k] = make_float2(0.f, 0.f);
+  float2 accb = make_float2(0.f, 0.f);
   for (int64_t rb = r0; rb < r1; rb += 64) {
     const int nr = (int)min((int64_t)64, r1 - rb);
     __syncthreads();
@@ -156,19 +163,27 @@ small_wgrad_partial_kernel(const T* __restrict__ dY, const float* __restrict__ Z
     }
     __syncthreads();
     if (c < N) {
+#pragma unroll 2
       for (int r = 0; r < nr; ++r) {
-        const float g = to_float(dY[(rb + r) * N + c]);
-        accb += g;
+        const float2 g = load2(dY + (rb + r) * N + c);
+        accb.x += g.x; accb.y += g.y;
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) acc[k] = fmaf(g, zs[r][k], acc[k]);
+        for (int k4 = 0; k4 < KMAX; k4 += 4) {
+          const float4 zz = *reinterpret_cast<const float4*>(&zs[r][k4]);
+          acc[k4 + 0] = __ffma2_rn(g, make_float2(zz.x, zz.x), acc[k4 + 0]);
+          acc[k4 + 1] = __ffma2_rn(g, make_float2(zz.y, zz.y), acc[k4 + 1]);
+          acc[k4 + 2] = __ffma2_rn(g, make_float2(zz.z, zz.z), acc[k4 + 2]);
+          acc[k4 + 3] = __ffma2_rn(g, make_float2(zz.w, zz.w), acc[k4 + 3]);
+        }
       }
     }
   }
   if (c < N) {
-    float* p = partial + ((int64_t)blockIdx.y * N + c) * (KMAX + 1);
+    float* p0 = partial + ((int64_t)blockIdx.y * N + c) * (KMAX + 1);
+    float* p1 = p0 + (KMAX + 1);
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) p[k] = acc[k];
-    p[KMAX] = accb;
+    for (int k = 0; k < KMAX; ++k) { p0[k] = acc[k].x; p1[k] = acc[k].y; }
+    p0[KMAX] = accb.x; p1[KMAX] = accb.y;
   }
 }
 
@@ -348,7 +363,7 @@ template <typename T, int KMAX>
 static int small_wgrad_launch(const void* dY, const float* Z, int ldz, int K, int64_t M, int N, float* dW, float* dB,
                               float* partial, cudaStream_t st) {
   const int nchunks = ceil_div(M, kChunkRows);
-  dim3 grid(ceil_div(N, kThreads), nchunks);
+  dim3 grid(ceil_div(N, 2 * kThreads), nchunks);
   small_wgrad_partial_kernel<T, KMAX><<<grid, kThreads, 0, st>>>((const T*)dY, Z, ldz, K, M, N, partial);
   small_wgrad_reduce_kernel<KMAX><<<ceil_div((int64_t)N * (KMAX + 1), kThreads), kThreads, 0, st>>>(partial, nchunks, N,
                                                                                                     K, dW, dB);
@@ -362,7 +377,8 @@ extern "C" int lpgnn_small_wgrad(const void* dY, int dtype, const float* Z, int3
                                  lpgnn_stream_t stream) {
   if (int rc = check_device()) return rc;
   LPGNN_DT_OK(dtype, "small_wgrad");
-  LPGNN_REQUIRE(M >= 0 && N > 0 && K >= 1 && K <= 64 && ldz >= K && dW, "small_wgrad: bad arguments (K=%d ldz=%d)", K, ldz);
+  LPGNN_REQUIRE(M >= 0 && N > 0 && N % 2 == 0 && K >= 1 && K <= 64 && ldz >= K && dW,
+                "small_wgrad: bad arguments (N=%d must be even, K=%d ldz=%d)", N, K, ldz);
   cudaStream_t st = (cudaStream_t)stream;
   if (M == 0) {
     LPGNN_CUDA_OK(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)N * K, st));

@@ -11,12 +11,14 @@ import torch.nn.functional as F
 def labels_to_balanced_weights(labels, merge_lu=True):
     """Inverse-frequency class weights; for two-sided problems the lower/upper weights are averaged
     (utils.py:286-299)."""
-    res = torch.zeros(3, device=labels.device)
-    lbl, cnt = torch.unique(labels, return_counts=True)
-    wei = cnt.sum() / cnt
-    res[lbl] = wei.to(res.dtype)
-    if len(lbl) != 2 and merge_lu:
-        res[0] = res[2] = (res[0] + res[2]) / 2.
+    # torch.unique(return_counts) of the reference == bincount over the 3 classes, without the device sort
+    cnt = torch.bincount(labels, minlength=3)[:3].to(torch.float32)
+    present = cnt > 0
+    res = torch.where(present, cnt.sum() / cnt.clamp_min(1.0), torch.zeros_like(cnt))
+    if merge_lu:
+        merged = (res[0] + res[2]) / 2.
+        two_sided = present.sum() != 2            # the reference merges lower/upper unless exactly 2 classes occur
+        res = torch.where(two_sided & torch.tensor([True, False, True], device=res.device), merged, res)
     return res
 
 

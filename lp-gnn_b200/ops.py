@@ -234,13 +234,17 @@ def dropout_(x, p, seed):
     return x
 
 
-def transpose(x, pad_to=64):
-    """``x^T`` as ``[N, ld]`` with ``ld = M`` rounded up to ``pad_to`` and zero-filled padding columns."""
+def transpose(x, pad_to=64, out=None):
+    """``x^T`` as ``[N, ld]`` with ``ld = M`` rounded up to ``pad_to`` and zero-filled padding columns.
+    ``out`` may be a row-slice ``[N, ld]`` of a larger buffer (the halves of a concatenated GEMM operand)."""
     require_cuda(x)
     x = _contig(x)
     M, N = x.shape
     ld = (M + pad_to - 1) // pad_to * pad_to
-    out = torch.empty((N, ld), dtype=x.dtype, device=x.device)
+    if out is None:
+        out = torch.empty((N, ld), dtype=x.dtype, device=x.device)
+    elif out.shape != (N, ld) or not out.is_contiguous() or out.dtype != x.dtype:
+        raise ValueError("transpose: out must be a contiguous [N, ld] tensor of the input dtype")
     with torch.cuda.device(x.device):
         rc = _lib.load().lpgnn_transpose(x.data_ptr(), dtype_code(x.dtype), M, N, out.data_ptr(), ld, stream_ptr())
     check(rc, "lpgnn_transpose")

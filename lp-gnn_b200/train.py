@@ -122,7 +122,7 @@ def run_exp(args):
     broadcast_parameters(model, world)
     params = list(model.parameters())
     if args.opt == "adam":
-        opt = torch.optim.Adam(params, lr=args.lr, weight_decay=5e-4)
+        opt = torch.optim.Adam(params, lr=args.lr, weight_decay=5e-4, fused=True)   # same update rule, one kernel
     else:
         opt = torch.optim.SGD(params, lr=args.lr, weight_decay=5e-4)
     scheduler = StepLR(opt, step_size=max(args.epochs // 4, 1), gamma=0.1)

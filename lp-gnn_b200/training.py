@@ -34,7 +34,10 @@ def _param_list(model):
 def _wgrad_pair(d_pre_t, x_rel, x_root):
     """(dW_rel, dW_root) = d_pre^T [x_rel | x_root] with ONE split-K GEMM over the node dimension: the two
     operands are transposed into the halves of one [K_rel + K_root, M_pad] buffer."""
-    xt = torch.cat((ops.transpose(x_rel), ops.transpose(x_root)), dim=0)     # [2K, M_pad] (weights-sized rows, node-sized cols)
+    k_rel, k_root = x_rel.shape[1], x_root.shape[1]
+    xt = torch.empty((k_rel + k_root, d_pre_t.shape[1]), dtype=x_rel.dtype, device=x_rel.device)   # [2K, M_pad]
+    ops.transpose(x_rel, out=xt[:k_rel])
+    ops.transpose(x_root, out=xt[k_rel:])
     g = ops.gemm_tn(d_pre_t, xt)                                             # [N, 2K] fp32
     k = x_rel.shape[1]
     return g[:, :k].contiguous(), g[:, k:].contiguous()

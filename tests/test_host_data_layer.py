@@ -126,3 +126,20 @@ def test_shard_indices_partition(pkg):
         assert sorted(sum(parts, [])) == list(range(37))
         loads = [w[p].sum() for p in parts]
         assert max(loads) - min(loads) <= w.max()                       # LPT balance
+
+
+def test_losses_match_reference_semantics(pkg):
+    """losses.py (train.py:32-53, utils.py:286-299) vs the oracle restatement, on CPU tensors."""
+    from lpgnn_b200 import losses
+    rng = np.random.default_rng(0)
+    for labels in ([0, 1, 1, 2, 2, 2], [1, 1, 0], [1, 2, 2, 2], [1, 1, 1], [0, 2], [0, 1, 2]):
+        y = torch.tensor(labels)
+        assert torch.allclose(losses.labels_to_balanced_weights(y), port.labels_to_balanced_weights(y))
+    m, n = 40, 90
+    lc = torch.from_numpy(rng.standard_normal((m, 3)).astype(np.float32))
+    lv = torch.from_numpy(rng.standard_normal((n, 3)).astype(np.float32))
+    ys, yt = torch.from_numpy(rng.integers(0, 3, m)), torch.from_numpy(rng.integers(1, 3, n))
+    assert torch.allclose(losses.balanced(lc, lv, ys, yt), port.balanced_loss(lc, lv, ys, yt), rtol=1e-6)
+    ce = torch.nn.functional.cross_entropy(torch.cat((lc, lv)), torch.cat((ys, yt)))
+    assert torch.allclose(losses.unbalanced(lc, lv, ys, yt), ce)
+    assert torch.allclose(losses.focal(lc, lv, ys, yt), (1 - torch.exp(-ce)) ** 2 * ce)
