@@ -194,6 +194,41 @@ LPGNN_API int lpgnn_basis_select(const float* logits_cons, int32_t m, const floa
                        int32_t k_basic, void* status, int status_is_i64, int32_t* counts_out,
                        void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * One-call basis prediction: (a1) graph build -> (a2-a5) GCN_FC forward -> (a6) basis selection,
+ * enqueued from native code on `stream`.  Replaces the per-LP body of the reference's prediction sweep
+ * (scripts/pred_basis.py:113-118 `inference_only` = model(batch) + val.inference_gnn) together with the graph
+ * construction of dataset.py:299-304.  Weights are passed by pointer (the caller owns them; bf16 mode
+ * expects bf16 copies of the hidden-layer weights and the [W_rel|W_root|0] bf16 [hids,64] matrices of
+ * the input layer).  status_out: uint8 [m+n] device, constraints first.  logits_out: optional f32
+ * [m+n,3].  graph_status: optional zero-initialised device int32 (see lpgnn_graph_build); if NULL an
+ * internal word is used.  All scratch memory comes from `workspace` (256-byte aligned).
+ * ------------------------------------------------------------------------------------------- */
+#define LPGNN_MAX_HIDDEN_LAYERS 8
+typedef struct lpgnn_gcn_fc_weights {
+  int32_t p, q, hids, depth, precision, reserved;  /* precision: LPGNN_F32 | LPGNN_BF16 */
+  /* conv1, fp32: lin_rel.weight [hids,in_src], lin_rel.bias [hids], lin_root.weight [hids,in_dst] */
+  const float *c1_l2r_wrel, *c1_l2r_b, *c1_l2r_wroot;   /* left2right: src = constraints (p), dst = variables (q) */
+  const float *c1_r2l_wrel, *c1_r2l_b, *c1_r2l_wroot;   /* right2left: src = variables (q), dst = constraints (p) */
+  const void *c1_l2r_wcat, *c1_r2l_wcat;                /* bf16 mode only */
+  /* hidden layers i = 0 .. depth-3: weights [hids,hids] in the compute dtype, biases fp32 */
+  const void* l2r_wrel[LPGNN_MAX_HIDDEN_LAYERS];
+  const void* l2r_wroot[LPGNN_MAX_HIDDEN_LAYERS];
+  const float* l2r_b[LPGNN_MAX_HIDDEN_LAYERS];
+  const void* r2l_wrel[LPGNN_MAX_HIDDEN_LAYERS];
+  const void* r2l_wroot[LPGNN_MAX_HIDDEN_LAYERS];
+  const float* r2l_b[LPGNN_MAX_HIDDEN_LAYERS];
+  /* heads, fp32: lin_left (constraints) / lin_right (variables): weight [3,hids], bias [3] */
+  const float *head_left_w, *head_left_b, *head_right_w, *head_right_b;
+} lpgnn_gcn_fc_weights;
+
+LPGNN_API size_t lpgnn_predict_workspace_bytes(int64_t nnz, int32_t m, int32_t n, int32_t p, int32_t q,
+                                     int32_t hids, int32_t depth, int precision);
+LPGNN_API int lpgnn_predict_basis(const lpgnn_gcn_fc_weights* w, const int32_t* coo_row, const int32_t* coo_col,
+                        const float* coo_val, int64_t nnz, int32_t m, int32_t n, int flags,
+                        const float* x_s, const float* x_t, uint8_t* status_out, float* logits_out,
+                        int32_t* graph_status, void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
+
 /* =============================================================================================
  * Backward pass (training step: reference train.py:121-129 calls loss.backward(), which runs the
  * autograd formulas of PyG GraphConv / torch_sparse spmm_sum / F.normalize / relu_ / dropout).

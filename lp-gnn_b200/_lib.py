@@ -21,6 +21,18 @@ COO_SORTED = 1
 _p = C.c_void_p
 _i32, _i64, _sz, _int = C.c_int32, C.c_int64, C.c_size_t, C.c_int
 
+MAX_HIDDEN_LAYERS = 8
+
+
+class GcnFcWeights(C.Structure):
+    """Mirror of ``lpgnn_gcn_fc_weights`` (include/lpgnn.h)."""
+    _fields_ = ([(k, _i32) for k in ("p", "q", "hids", "depth", "precision", "reserved")]
+                + [(k, _p) for k in ("c1_l2r_wrel", "c1_l2r_b", "c1_l2r_wroot", "c1_r2l_wrel", "c1_r2l_b", "c1_r2l_wroot",
+                                     "c1_l2r_wcat", "c1_r2l_wcat")]
+                + [(k, _p * MAX_HIDDEN_LAYERS) for k in ("l2r_wrel", "l2r_wroot", "l2r_b", "r2l_wrel", "r2l_wroot", "r2l_b")]
+                + [(k, _p) for k in ("head_left_w", "head_left_b", "head_right_w", "head_right_b")])
+
+
 # name -> (restype, argtypes); must list every symbol include/lpgnn.h declares
 SIGNATURES = {
     "lpgnn_version": (_int, []),
@@ -39,6 +51,8 @@ SIGNATURES = {
     "lpgnn_head_finish": (_int, [_p, _i32, _i32, _p, _p, _i32, _p, _p]),
     "lpgnn_head_mask": (_int, [_p, _int, _i32, _i32, _p, _p, _p, _i32, _p, _p, _p]),
     "lpgnn_add_knowledge": (_int, [_p, _i32, _p, _i32, _p, _p]),
+    "lpgnn_predict_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32, _i32, _i32, _int]),
+    "lpgnn_predict_basis": (_int, [C.POINTER(GcnFcWeights), _p, _p, _p, _i64, _i32, _i32, _int, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "lpgnn_gemm_tn_splits": (_i32, [_i32, _i32, _i32]),
     "lpgnn_gemm_tn_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "lpgnn_gemm_tn": (_int, [_p, _p, _i32, _i32, _i32, _p, _p, _sz, _p]),

@@ -155,6 +155,82 @@ class GCN_FC(GCNBase):
         from .autograd import gcn_fc_forward
         return gcn_fc_forward(self, batch.x_s, batch.x_t, batch.edge_index)
 
+    # -- native one-call prediction ---------------------------------------------------------
+    def _native_weights(self):
+        """``lpgnn_gcn_fc_weights`` for the current parameters (rebuilt when a parameter changes)."""
+        from . import _lib
+        from .autograd import wcat_bf16
+        ver = tuple(p._version for p in self.parameters()) + (self.precision, str(self.lin_left.weight.device))
+        hit = getattr(self, "_native_cache", None)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        bf16 = self.precision == "bf16"
+        dt = torch.bfloat16 if bf16 else torch.float32
+        keep = []                                           # tensors the struct points into
+
+        def f32(t):
+            t = t.detach().float().contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        def cd(t):
+            t = t.detach().to(dt).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        w = _lib.GcnFcWeights()
+        c1 = self.conv1
+        w.p, w.q = c1.left2right.in_channels[0], c1.left2right.in_channels[1]
+        w.hids, w.depth, w.precision = self.hids, len(self.layers) + 2, _lib.BF16 if bf16 else _lib.F32
+        if w.depth - 2 > _lib.MAX_HIDDEN_LAYERS:
+            raise ValueError("native prediction supports at most 8 hidden layers")
+        for tag, gc in (("l2r", c1.left2right), ("r2l", c1.right2left)):
+            setattr(w, f"c1_{tag}_wrel", f32(gc.lin_rel.weight))
+            setattr(w, f"c1_{tag}_b", f32(gc.lin_rel.bias))
+            setattr(w, f"c1_{tag}_wroot", f32(gc.lin_root.weight))
+            if bf16:
+                wc = wcat_bf16(c1._cache, gc)
+                keep.append(wc)
+                setattr(w, f"c1_{tag}_wcat", wc.data_ptr())
+        for i, conv in enumerate(self.layers):
+            for tag, gc in (("l2r", conv.left2right), ("r2l", conv.right2left)):
+                getattr(w, f"{tag}_wrel")[i] = cd(gc.lin_rel.weight)
+                getattr(w, f"{tag}_wroot")[i] = cd(gc.lin_root.weight)
+                getattr(w, f"{tag}_b")[i] = f32(gc.lin_rel.bias)
+        w.head_left_w, w.head_left_b = f32(self.lin_left.weight), f32(self.lin_left.bias)
+        w.head_right_w, w.head_right_b = f32(self.lin_right.weight), f32(self.lin_right.bias)
+        self._native_cache = (ver, w, keep)
+        return w
+
+    @torch.no_grad()
+    def predict_basis_coo(self, row, col, val, m, n, x_s, x_t, is_sorted=False, want_logits=False):
+        """Graph build + forward + basis decision as ONE native call (``lpgnn_predict_basis``): device int32
+        ``row/col``, fp32 ``val`` COO of the m x n matrix and fp32 features -> uint8 statuses [m+n] (constraints
+        first) [+ fp32 logits [m+n,3]].  The sorted claim / index range are reported in ``self.last_graph_status``
+        (device int32, bit 0 = not sorted, bit 1 = out of range)."""
+        import ctypes as C
+
+        from . import _lib
+        from .graph import _status_slot
+        _lib.require_cuda(row, col, val, x_s, x_t)
+        lib = _lib.load()
+        w = self._native_weights()
+        dev = x_s.device
+        z = int(row.shape[0])
+        ws_bytes = lib.lpgnn_predict_workspace_bytes(z, m, n, w.p, w.q, w.hids, w.depth, w.precision)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        status = torch.empty(m + n, dtype=torch.uint8, device=dev)
+        logits = torch.empty((m + n, 3), dtype=torch.float32, device=dev) if want_logits else None
+        gstat = _status_slot(dev)
+        with torch.cuda.device(dev):
+            rc = lib.lpgnn_predict_basis(C.byref(w), row.data_ptr(), col.data_ptr(), val.data_ptr(), z, m, n,
+                                         _lib.COO_SORTED if is_sorted else 0, x_s.data_ptr(), x_t.data_ptr(),
+                                         status.data_ptr(), _lib.ptr(logits), gstat.data_ptr(), ws.data_ptr(), ws_bytes,
+                                         _lib.stream_ptr())
+        _lib.check(rc, "lpgnn_predict_basis")
+        self.last_graph_status = gstat
+        return (status, logits) if want_logits else status
+
     @torch.no_grad()
     def predict_basis(self, batch, int64=True):
         """forward + ``val.inference_gnn`` without leaving the device (reference

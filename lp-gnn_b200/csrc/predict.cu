@@ -1,0 +1,173 @@
+// One-call basis prediction: graph build -> GCN_FC forward -> basis selection, enqueued from C++.
+//
+// Replaces the body of the reference's per-LP prediction (scripts/pred_basis.py:113-118 `inference_only`:
+// model(batch) + inference_gnn) including the graph construction that the reference does in the DataLoader
+// (dataset.py:299-304).  The host cost of a step is ~25 kernel launches from native code instead of ~25 Python
+// round trips, which is what bounds small LPs (BASELINE config C5: 10K small/medium LPs).
+// All device memory comes from ONE caller-provided workspace, carved with a bump allocator.
+#include "common.cuh"
+
+namespace lpgnn {
+namespace {
+
+struct Bump {
+  char* base;
+  size_t off = 0, cap;
+  Bump(void* p, size_t c) : base(reinterpret_cast<char*>(p)), cap(c) {}
+  template <typename T> T* take(size_t count) {
+    off = align_up(off, 256);
+    T* r = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return r;
+  }
+};
+
+}  // namespace
+}  // namespace lpgnn
+
+using namespace lpgnn;
+
+namespace {
+
+struct Buffers {
+  int32_t *rowptr, *colptr, *col, *row_csc, *csr2csc, *status;
+  float *val, *val_csc;
+  void* build_ws; size_t build_ws_bytes;
+  float *z_s, *z_t;          // fp32 [m,KT], [n,KT] (fp32 mode)
+  void *zb_s, *zb_t;         // bf16 [m,64], [n,64] (bf16 mode)
+  void *act[2][2];           // ping-pong activations: act[i][0] = left [m,H], act[i][1] = right [n,H]
+  void *agg_s, *agg_t;       // [m,H], [n,H]
+  float *part_s, *part_t;    // fused-head partials
+  float *logit_s, *logit_t;  // [m,3], [n,3]
+  void* sel_ws; size_t sel_ws_bytes;
+};
+
+size_t carve(Bump& b, Buffers& B, int64_t z, int32_t m, int32_t n, int32_t p, int32_t q, int32_t H, int32_t depth,
+             int bf16) {
+  const size_t es = bf16 ? 2 : 4;
+  B.rowptr = b.take<int32_t>((size_t)m + 1);
+  B.colptr = b.take<int32_t>((size_t)n + 1);
+  B.col = b.take<int32_t>(z); B.row_csc = b.take<int32_t>(z); B.csr2csc = b.take<int32_t>(z);
+  B.val = b.take<float>(z); B.val_csc = b.take<float>(z);
+  B.status = b.take<int32_t>(4);
+  B.build_ws_bytes = lpgnn_graph_build_workspace_bytes(z, m, n);
+  B.build_ws = b.take<char>(B.build_ws_bytes);
+  const int kt = lpgnn_conv_in_zcat_width(p, q);
+  if (bf16) {
+    B.zb_s = b.take<char>((size_t)m * 64 * 2); B.zb_t = b.take<char>((size_t)n * 64 * 2);
+    B.z_s = B.z_t = nullptr;
+  } else {
+    B.z_s = b.take<float>((size_t)m * kt); B.z_t = b.take<float>((size_t)n * kt);
+    B.zb_s = B.zb_t = nullptr;
+  }
+  const int n_act = depth > 3 ? 2 : 1;
+  for (int i = 0; i < 2; ++i) {
+    B.act[i][0] = i < n_act ? b.take<char>((size_t)m * H * es) : nullptr;
+    B.act[i][1] = i < n_act ? b.take<char>((size_t)n * H * es) : nullptr;
+  }
+  if (!bf16 && depth > 2 && n_act == 1) {  // fp32 mode has no fused head: the last layer's output is materialised
+    B.act[1][0] = b.take<char>((size_t)m * H * es);
+    B.act[1][1] = b.take<char>((size_t)n * H * es);
+  }
+  if (depth > 2) {
+    B.agg_s = b.take<char>((size_t)m * H * es); B.agg_t = b.take<char>((size_t)n * H * es);
+  } else {
+    B.agg_s = B.agg_t = nullptr;
+  }
+  const int nparts = lpgnn_node_transform_head_parts(H);
+  B.part_s = b.take<float>((size_t)nparts * m * 3); B.part_t = b.take<float>((size_t)nparts * n * 3);
+  B.logit_s = b.take<float>((size_t)m * 3); B.logit_t = b.take<float>((size_t)n * 3);
+  B.sel_ws_bytes = lpgnn_basis_select_workspace_bytes((int64_t)m + n);
+  B.sel_ws = b.take<char>(B.sel_ws_bytes);
+  return align_up(b.off, 256);
+}
+
+}  // namespace
+
+extern "C" size_t lpgnn_predict_workspace_bytes(int64_t nnz, int32_t m, int32_t n, int32_t p, int32_t q, int32_t hids,
+                                                int32_t depth, int precision) {
+  Bump b(nullptr, ~(size_t)0);
+  Buffers B;
+  return carve(b, B, nnz > 0 ? nnz : 1, m, n, p, q, hids, depth, precision == LPGNN_BF16);
+}
+
+extern "C" int lpgnn_predict_basis(const lpgnn_gcn_fc_weights* w, const int32_t* coo_row, const int32_t* coo_col,
+                                   const float* coo_val, int64_t nnz, int32_t m, int32_t n, int flags, const float* x_s,
+                                   const float* x_t, uint8_t* status_out, float* logits_out, int32_t* graph_status,
+                                   void* workspace, size_t workspace_bytes, lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(w && m > 0 && n > 0 && nnz >= 0 && x_s && x_t && status_out && workspace, "predict_basis: bad arguments");
+  const int H = w->hids, depth = w->depth, p = w->p, q = w->q;
+  const int bf16 = w->precision == LPGNN_BF16;
+  LPGNN_REQUIRE(depth >= 2 && depth - 2 <= LPGNN_MAX_HIDDEN_LAYERS, "predict_basis: depth %d unsupported", depth);
+  LPGNN_REQUIRE(!bf16 || H % 64 == 0, "predict_basis: bf16 mode needs hids %% 64 == 0");
+  const size_t need = lpgnn_predict_workspace_bytes(nnz, m, n, p, q, H, depth, w->precision);
+  if (workspace_bytes < need) { set_error("predict_basis: workspace %zu < required %zu", workspace_bytes, need); return LPGNN_EWORKSPACE; }
+  LPGNN_REQUIRE((uintptr_t)workspace % 256 == 0, "predict_basis: workspace must be 256-byte aligned");
+  Bump b(workspace, workspace_bytes);
+  Buffers B;
+  carve(b, B, nnz > 0 ? nnz : 1, m, n, p, q, H, depth, bf16);
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t* gstat = graph_status ? graph_status : B.status;
+  if (!graph_status) LPGNN_CUDA_OK(cudaMemsetAsync(B.status, 0, sizeof(int32_t), st));
+
+#define LPGNN_TRY(expr) do { if (int _rc = (expr)) return _rc; } while (0)
+  // ---- (a1) graph
+  LPGNN_TRY(lpgnn_graph_build(coo_row, coo_col, 0, coo_val, nnz, m, n, flags, B.rowptr, B.col, B.val, B.colptr, B.row_csc,
+                              B.val_csc, B.csr2csc, gstat, B.build_ws, B.build_ws_bytes, stream));
+  const int dt = bf16 ? LPGNN_BF16 : LPGNN_F32;
+  void *left = B.act[0][0], *right = B.act[0][1];
+  // ---- conv1 (+relu).  CSC view: dst = variables, src = constraints; CSR view: dst = constraints, src = variables
+  if (bf16) {
+    LPGNN_TRY(lpgnn_gather_cat(B.colptr, B.row_csc, B.val_csc, n, x_s, p, x_t, q, nullptr, B.zb_t, stream));
+    LPGNN_TRY(lpgnn_gather_cat(B.rowptr, B.col, B.val, m, x_t, q, x_s, p, nullptr, B.zb_s, stream));
+    LPGNN_TRY(lpgnn_node_transform(B.zb_t, 64, w->c1_l2r_wcat, nullptr, 0, nullptr, w->c1_l2r_b, n, H, right, dt, dt,
+                                   LPGNN_EPI_RELU, stream));
+    LPGNN_TRY(lpgnn_node_transform(B.zb_s, 64, w->c1_r2l_wcat, nullptr, 0, nullptr, w->c1_r2l_b, m, H, left, dt, dt,
+                                   LPGNN_EPI_RELU, stream));
+  } else {
+    LPGNN_TRY(lpgnn_conv_in_fused(B.colptr, B.row_csc, B.val_csc, n, x_s, p, x_t, q, w->c1_l2r_wrel, w->c1_l2r_b,
+                                  w->c1_l2r_wroot, H, right, dt, LPGNN_EPI_RELU, B.z_t, stream));
+    LPGNN_TRY(lpgnn_conv_in_fused(B.rowptr, B.col, B.val, m, x_t, q, x_s, p, w->c1_r2l_wrel, w->c1_r2l_b,
+                                  w->c1_r2l_wroot, H, left, dt, LPGNN_EPI_RELU, B.z_s, stream));
+  }
+  // ---- hidden layers
+  const int n_hidden = depth - 2;
+  bool head_done = false;
+  int cur = 0;
+  for (int li = 0; li < n_hidden; ++li) {
+    LPGNN_TRY(lpgnn_spmm(B.colptr, B.row_csc, B.val_csc, n, left, B.agg_t, H, dt, stream));    // A^T . left
+    LPGNN_TRY(lpgnn_spmm(B.rowptr, B.col, B.val, m, right, B.agg_s, H, dt, stream));           // A   . right
+    const bool last = li == n_hidden - 1;
+    if (last && bf16) {  // head fused into the epilogue; the last activation never reaches HBM
+      LPGNN_TRY(lpgnn_node_transform_head(B.agg_t, H, w->l2r_wrel[li], right, H, w->l2r_wroot[li], w->l2r_b[li], n, H,
+                                          nullptr, LPGNN_EPI_RELU, w->head_right_w, B.part_t, stream));
+      LPGNN_TRY(lpgnn_node_transform_head(B.agg_s, H, w->r2l_wrel[li], left, H, w->r2l_wroot[li], w->r2l_b[li], m, H,
+                                          nullptr, LPGNN_EPI_RELU, w->head_left_w, B.part_s, stream));
+      const int nparts = lpgnn_node_transform_head_parts(H);
+      LPGNN_TRY(lpgnn_head_finish(B.part_t, nparts, n, w->head_right_b, x_t, q, B.logit_t, stream));
+      LPGNN_TRY(lpgnn_head_finish(B.part_s, nparts, m, w->head_left_b, x_s, p, B.logit_s, stream));
+      head_done = true;
+    } else {
+      void *nl = B.act[cur ^ 1][0], *nr = B.act[cur ^ 1][1];
+      LPGNN_TRY(lpgnn_node_transform(B.agg_t, H, w->l2r_wrel[li], right, H, w->l2r_wroot[li], w->l2r_b[li], n, H, nr, dt,
+                                     dt, LPGNN_EPI_RELU, stream));
+      LPGNN_TRY(lpgnn_node_transform(B.agg_s, H, w->r2l_wrel[li], left, H, w->r2l_wroot[li], w->r2l_b[li], m, H, nl, dt,
+                                     dt, LPGNN_EPI_RELU, stream));
+      left = nl; right = nr; cur ^= 1;
+    }
+  }
+  if (!head_done) {
+    LPGNN_TRY(lpgnn_head_mask(left, dt, m, H, w->head_left_w, w->head_left_b, x_s, p, B.logit_s, nullptr, stream));
+    LPGNN_TRY(lpgnn_head_mask(right, dt, n, H, w->head_right_w, w->head_right_b, x_t, q, B.logit_t, nullptr, stream));
+  }
+  if (logits_out) {
+    LPGNN_CUDA_OK(cudaMemcpyAsync(logits_out, B.logit_s, sizeof(float) * 3 * (size_t)m, cudaMemcpyDeviceToDevice, st));
+    LPGNN_CUDA_OK(cudaMemcpyAsync(logits_out + 3 * (size_t)m, B.logit_t, sizeof(float) * 3 * (size_t)n,
+                                  cudaMemcpyDeviceToDevice, st));
+  }
+  // ---- (a6) basis decision
+  LPGNN_TRY(lpgnn_basis_select(B.logit_s, m, B.logit_t, n, m, status_out, 0, nullptr, B.sel_ws, B.sel_ws_bytes, stream));
+#undef LPGNN_TRY
+  return LPGNN_OK;
+}

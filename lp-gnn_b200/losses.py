@@ -11,8 +11,9 @@ import torch.nn.functional as F
 def labels_to_balanced_weights(labels, merge_lu=True):
     """Inverse-frequency class weights; for two-sided problems the lower/upper weights are averaged
     (utils.py:286-299)."""
-    # torch.unique(return_counts) of the reference == bincount over the 3 classes, without the device sort
-    cnt = torch.bincount(labels, minlength=3)[:3].to(torch.float32)
+    # torch.unique(return_counts) of the reference == per-class counts; computed with a comparison + sum so that
+    # there is neither a device sort nor a host sync (unique and bincount both read a size back to the host)
+    cnt = (labels.view(-1, 1) == torch.arange(3, device=labels.device)).sum(0).to(torch.float32)
     present = cnt > 0
     res = torch.where(present, cnt.sum() / cnt.clamp_min(1.0), torch.zeros_like(cnt))
     if merge_lu:

@@ -86,8 +86,7 @@ class BasisPipeline:
             self.h_status[slot] = torch.empty(int(nodes * 1.25) + 64, dtype=torch.uint8).pin_memory()
         cur.wait_event(self.ready[slot])
         row, col, val, x_s, x_t = unpack_device(self.d_buf[slot], lp)
-        g = BipartiteCSR.from_coo(row, col, val, lp.m, lp.n, is_sorted=lp.sorted)
-        st = self.model.predict_basis(types.SimpleNamespace(x_s=x_s, x_t=x_t, edge_index=g), int64=False)
+        st = self.model.predict_basis_coo(row, col, val, lp.m, lp.n, x_s, x_t, is_sorted=lp.sorted)   # one native call
         self.h_status[slot][:lp.m + lp.n].copy_(st, non_blocking=True)
         self.done[slot].record(cur)
 

@@ -14,7 +14,7 @@ cfg = synth.CONFIGS[name]
 lp = synth.config_lp(name)
 torch.manual_seed(0)
 model = arch.GCN_FC(8, 8, hids=cfg["hids"], depth=cfg["depth"]).to(dev).train().set_precision(prec)
-opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4)
+opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4, fused=True)
 g = BipartiteCSR.from_coo_arrays(lp.row, lp.col, lp.a_data.astype(np.float32), lp.m, lp.n, dev, is_sorted=True)
 batch = types.SimpleNamespace(x_s=torch.from_numpy(lp.c_feas).to(dev), x_t=torch.from_numpy(lp.v_feas).to(dev), edge_index=g)
 y_s, y_t = torch.from_numpy(lp.y_s).to(dev), torch.from_numpy(lp.y_t).to(dev)
@@ -26,3 +26,20 @@ for i in range(steps):
     opt.step()
 torch.cuda.synchronize()
 print("loss", float(loss))
+import time
+def step():
+    lc, lv = model(batch)
+    loss = balanced(lc, lv, y_s, y_t)
+    opt.zero_grad(set_to_none=True)
+    loss.backward()
+    opt.step()
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(20): step()
+t_cpu = (time.perf_counter() - t0) / 20
+torch.cuda.synchronize(); t_all = (time.perf_counter() - t0) / 20
+print(f"train step: enqueue {t_cpu*1e3:.3f} ms, enqueue+drain {t_all*1e3:.3f} ms")
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    for _ in range(5): step()
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=30, max_name_column_width=70))

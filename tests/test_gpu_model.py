@@ -89,3 +89,29 @@ def test_state_dict_keys_and_checkpoint_roundtrip(cuda, tmp_path):
     other.load(tmp_path / "mdl.pth")
     for k, v in model.state_dict().items():
         assert torch.equal(v, other.state_dict()[k])
+
+
+@pytest.mark.parametrize("hids,depth,precision", [(64, 2, "fp32"), (128, 3, "fp32"), (128, 3, "bf16"), (64, 4, "bf16"),
+                                                    (64, 5, "fp32"), (1024, 3, "bf16")])
+def test_native_one_call_prediction_matches_op_by_op_path(cuda, hids, depth, precision):
+    """lpgnn_predict_basis (graph build + forward + selection enqueued from C++) == the Python-orchestrated path."""
+    lp, model, ref, g_ref, batch = _setup((900, 1700, 8000, 21), hids, depth, cuda)
+    model.set_precision(precision)
+    t = lambda a, dt: torch.from_numpy(a.astype(dt)).to(cuda)
+    perm = np.random.default_rng(0).permutation(lp.nnz)            # unsorted COO on purpose
+    status, logits = model.predict_basis_coo(t(lp.row[perm], np.int32), t(lp.col[perm], np.int32),
+                                             t(lp.a_data[perm], np.float32), lp.m, lp.n, batch.x_s, batch.x_t,
+                                             is_sorted=False, want_logits=True)
+    with torch.no_grad():
+        lc, lv = model(batch)
+        exp = model.predict_basis(batch, int64=False)
+    assert torch.equal(logits[:lp.m], lc) and torch.equal(logits[lp.m:], lv)      # same kernels, same order
+    assert torch.equal(status, exp)
+    assert int(model.last_graph_status.item()) == 0
+    # sorted hint on sorted input gives the same answer; a false hint is flagged
+    s2 = model.predict_basis_coo(t(lp.row, np.int32), t(lp.col, np.int32), t(lp.a_data, np.float32), lp.m, lp.n,
+                                 batch.x_s, batch.x_t, is_sorted=True)
+    assert torch.equal(s2, exp) and int(model.last_graph_status.item()) == 0
+    model.predict_basis_coo(t(lp.row[perm], np.int32), t(lp.col[perm], np.int32), t(lp.a_data[perm], np.float32),
+                            lp.m, lp.n, batch.x_s, batch.x_t, is_sorted=True)
+    assert int(model.last_graph_status.item()) & 1
