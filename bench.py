@@ -286,6 +286,83 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_sweep(args):
+    """--workload C5: the batch basis-prediction sweep (scripts/pred_basis.py workload) over a population of
+    small/medium LPs (m log-uniform in [100, 20000], n = 2m, nnz = 5n).  A step = one LP.  The LPs are
+    independent units: with N ranks each rank takes every N-th LP (no collective)."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import _lib, arch, synth
+    from lpgnn_b200.pipeline import BasisPipeline, PackedBasisPipeline, pack_lp, unpack_device
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    pop = synth.lp_population(args.sweep_distinct, seed=1239)
+    mine = pop[rank::world] if world > 1 else pop
+    lps = [synth.processed_lp(m, n, z, seed=sd) for (m, n, z, sd) in mine]
+    hosts = [pack_lp(lp.row, lp.col, lp.a_data, lp.c_feas, lp.v_feas, is_sorted=True) for lp in lps]
+    torch.manual_seed(0)
+    model = arch.GCN_FC(8, 8, hids=args.sweep_hids, depth=3).to(dev).eval().set_precision(args.precision)
+    dev_lps = [(h, tuple(t.clone() for t in unpack_device(h.pack.to(dev), h))) for h in hosts]
+
+    def one(i):
+        h, (row, col, val, xs, xt) = dev_lps[i % len(dev_lps)]
+        return model.predict_basis_coo(row, col, val, h.m, h.n, xs, xt, is_sorted=True)
+
+    steps = args.steps
+    for i in range(max(args.warmup, 3)):
+        one(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.mark()
+    barrier(world)
+    torch.cuda.synchronize()
+    l0 = lib.lpgnn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        st = one(i)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = lib.lpgnn_launch_count() - l0
+    barrier(world)
+    t_ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    pipe = PackedBasisPipeline(model, dev) if args.sweep_pack else BasisPipeline(model, dev)
+    seq = [hosts[i % len(hosts)] for i in range(steps)]
+    for _ in pipe.run(seq[:8]):
+        pass
+    barrier(world)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_done = sum(1 for _ in pipe.run(seq))
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
+    clocks = sampler.stop() if rank == 0 else None
+    assert n_done == steps
+    nnz_mean = float(np.mean([lp.nnz for lp in lps]))
+    lps_s, lps_e2e = world * steps / (t_ms / 1e3), world * steps / (t_e2e / 1e3)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "LPs/sec (basis prediction: graph build + GCN_FC forward + basis selection)",
+            "value": lps_s, "unit": "LPs/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": t_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"C5: sweep over {len(pop)} distinct synthetic LPs (m log-uniform 100..20000, n=2m, "
+                                   f"nnz~5n, mean nnz {nnz_mean:.0f}), GCN_FC(8,8,hids={args.sweep_hids},depth=3), one LP per "
+                                   f"step, LPs sharded round-robin over ranks", "precision": args.precision,
+                       "l2": "small LPs: working set is L2-resident by nature of the workload",
+                       "e2e_api": "PackedBasisPipeline (block-diagonal packs, segmented basis decision)" if args.sweep_pack
+                       else "BasisPipeline (one native call per LP)"},
+            "mp_edges_per_sec": mp_edges(nnz_mean, 3) * lps_s,
+            "e2e": {"value": lps_e2e, "unit": "LPs/s", "h2d_bytes_per_step": float(np.mean([h.nbytes for h in hosts])),
+                    "d2h_bytes_per_step": float(np.mean([h.m + h.n for h in hosts])), "ms_per_step": t_e2e / steps},
+            "gpu_launches": int(launches), "clocks": clocks}))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
 def train_throughput(cfg, lp, dev, precision, steps, warmup, world):
     """Training step of the same shape (reference train.py:117-129): forward, balanced loss, backward through the
     CUDA kernels, gradient all-reduce (N > 1) and Adam, one LP graph per step per GPU.  Returns steps/s and
@@ -497,7 +574,10 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--sweep-distinct", type=int, default=96, help="C5: distinct LPs materialised (cycled)")
+    ap.add_argument("--sweep-hids", type=int, default=1024)
+    ap.add_argument("--sweep-pack", type=int, default=1, help="C5 e2e arm: pack LPs block-diagonally (1) or one call per LP (0)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--structure", default="staircase", choices=["staircase", "uniform"])
     ap.add_argument("--kernel-reps", type=int, default=10)
@@ -510,6 +590,10 @@ def main():
         args.steps = args.steps if args.steps is not None else 3
         args.warmup = args.warmup if args.warmup is not None else 1
         run_reference(args)
+    elif args.workload == "C5":
+        args.steps = args.steps if args.steps is not None else 1000
+        args.warmup = args.warmup if args.warmup is not None else 10
+        run_sweep(args)
     else:
         args.steps = args.steps if args.steps is not None else 300
         args.warmup = args.warmup if args.warmup is not None else 10

@@ -87,6 +87,14 @@ LPGNN_API int lpgnn_graph_build(const void* coo_row, const void* coo_col, int id
                       int32_t* csr2csc /*[nnz]*/, int32_t* status /*[1] device, optional*/,
                       void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
 
+/* Block-diagonal packing of several LPs into one graph (the direct sum of their matrices): the COO entries
+ * of LP b occupy [edge_ptr[b], edge_ptr[b+1]) with LP-local indices; this shifts them in place by the LP's
+ * first constraint (cons_ptr[b]) / variable (vars_ptr[b]) of the pack.  A pack of row-major sorted LPs is
+ * row-major sorted. */
+LPGNN_API int lpgnn_pack_offsets(int32_t* row, int32_t* col, int64_t nnz, const int32_t* edge_ptr,
+                       const int32_t* cons_ptr, const int32_t* vars_ptr, int32_t n_segments,
+                       lpgnn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (a2) Aggregation.  Replaces torch_sparse.matmul(adj_t, x, reduce='add') == spmm_sum, reached
  * from PyG GraphConv.message_and_aggregate (reference arch.py:75-80), forward AND backward
@@ -194,6 +202,16 @@ LPGNN_API int lpgnn_basis_select(const float* logits_cons, int32_t m, const floa
                        int32_t k_basic, void* status, int status_is_i64, int32_t* counts_out,
                        void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
 
+/* Segmented variant for a block-diagonal PACK of LPs: segment b owns constraints
+ * [cons_ptr[b], cons_ptr[b+1]) of logits_cons and variables [vars_ptr[b], vars_ptr[b+1]) of logits_vars and
+ * gets exactly (cons_ptr[b+1]-cons_ptr[b]) basic nodes (val.inference_gnn applied per LP).  One CTA per
+ * segment, one launch for the whole pack.  status: [total_cons + total_vars], all constraints first, in the
+ * packed order.  Workspace: lpgnn_basis_select_workspace_bytes(total_cons + total_vars). */
+LPGNN_API int lpgnn_basis_select_segmented(const float* logits_cons, const float* logits_vars,
+                                 const int32_t* cons_ptr, const int32_t* vars_ptr, int32_t n_segments,
+                                 int32_t total_cons, int32_t total_vars, void* status, int status_is_i64,
+                                 void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * One-call basis prediction: (a1) graph build -> (a2-a5) GCN_FC forward -> (a6) basis selection,
  * enqueued from native code on `stream`.  Replaces the per-LP body of the reference's prediction sweep
@@ -228,6 +246,16 @@ LPGNN_API int lpgnn_predict_basis(const lpgnn_gcn_fc_weights* w, const int32_t* 
                         const float* coo_val, int64_t nnz, int32_t m, int32_t n, int flags,
                         const float* x_s, const float* x_t, uint8_t* status_out, float* logits_out,
                         int32_t* graph_status, void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
+/* Same for a block-diagonal pack of n_segments LPs (the matrix is the direct sum of the LPs' matrices: rows
+ * and columns already offset; m, n, nnz are the pack totals): the forward pass runs once over the pack and
+ * the basis decision is taken per segment (lpgnn_basis_select_segmented).  cons_ptr / vars_ptr: device int32
+ * [n_segments+1]. */
+LPGNN_API int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const int32_t* coo_row, const int32_t* coo_col,
+                               const float* coo_val, int64_t nnz, int32_t m, int32_t n, int flags,
+                               const float* x_s, const float* x_t, const int32_t* cons_ptr,
+                               const int32_t* vars_ptr, int32_t n_segments, uint8_t* status_out,
+                               float* logits_out, int32_t* graph_status, void* workspace,
+                               size_t workspace_bytes, lpgnn_stream_t stream);
 
 /* =============================================================================================
  * Backward pass (training step: reference train.py:121-129 calls loss.backward(), which runs the

@@ -41,6 +41,7 @@ SIGNATURES = {
     "lpgnn_device_info": (_int, [C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)]),
     "lpgnn_graph_build_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "lpgnn_graph_build": (_int, [_p, _p, _int, _p, _i64, _i32, _i32, _int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "lpgnn_pack_offsets": (_int, [_p, _p, _i64, _p, _p, _p, _i32, _p]),
     "lpgnn_spmm": (_int, [_p, _p, _p, _i32, _p, _p, _i32, _int, _p]),
     "lpgnn_conv_in_zcat_width": (_i32, [_i32, _i32]),
     "lpgnn_gather_cat": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p]),
@@ -53,6 +54,9 @@ SIGNATURES = {
     "lpgnn_add_knowledge": (_int, [_p, _i32, _p, _i32, _p, _p]),
     "lpgnn_predict_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32, _i32, _i32, _int]),
     "lpgnn_predict_basis": (_int, [C.POINTER(GcnFcWeights), _p, _p, _p, _i64, _i32, _i32, _int, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "lpgnn_predict_basis_packed": (_int, [C.POINTER(GcnFcWeights), _p, _p, _p, _i64, _i32, _i32, _int, _p, _p, _p, _p, _i32, _p,
+                                          _p, _p, _p, _sz, _p]),
+    "lpgnn_basis_select_segmented": (_int, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _int, _p, _sz, _p]),
     "lpgnn_gemm_tn_splits": (_i32, [_i32, _i32, _i32]),
     "lpgnn_gemm_tn_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "lpgnn_gemm_tn": (_int, [_p, _p, _i32, _i32, _i32, _p, _p, _sz, _p]),

@@ -232,6 +232,35 @@ class GCN_FC(GCNBase):
         return (status, logits) if want_logits else status
 
     @torch.no_grad()
+    def predict_basis_packed(self, row, col, val, m, n, x_s, x_t, cons_ptr, vars_ptr, is_sorted=True, want_logits=False):
+        """Same for a block-diagonal pack of LPs (``row/col`` already in the pack's numbering, ``m/n`` the pack
+        totals, ``cons_ptr/vars_ptr`` device int32 [B+1]): one forward pass over the pack, basis decision per LP.
+        Returns uint8 statuses [m+n] in the packed layout (all constraints, then all variables)."""
+        import ctypes as C
+
+        from . import _lib
+        from .graph import _status_slot
+        _lib.require_cuda(row, col, val, x_s, x_t, cons_ptr, vars_ptr)
+        lib = _lib.load()
+        w = self._native_weights()
+        dev = x_s.device
+        z = int(row.shape[0])
+        ws_bytes = lib.lpgnn_predict_workspace_bytes(z, m, n, w.p, w.q, w.hids, w.depth, w.precision)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        status = torch.empty(m + n, dtype=torch.uint8, device=dev)
+        logits = torch.empty((m + n, 3), dtype=torch.float32, device=dev) if want_logits else None
+        gstat = _status_slot(dev)
+        with torch.cuda.device(dev):
+            rc = lib.lpgnn_predict_basis_packed(C.byref(w), row.data_ptr(), col.data_ptr(), val.data_ptr(), z, m, n,
+                                                _lib.COO_SORTED if is_sorted else 0, x_s.data_ptr(), x_t.data_ptr(),
+                                                cons_ptr.data_ptr(), vars_ptr.data_ptr(), int(cons_ptr.shape[0]) - 1,
+                                                status.data_ptr(), _lib.ptr(logits), gstat.data_ptr(), ws.data_ptr(),
+                                                ws_bytes, _lib.stream_ptr())
+        _lib.check(rc, "lpgnn_predict_basis_packed")
+        self.last_graph_status = gstat
+        return (status, logits) if want_logits else status
+
+    @torch.no_grad()
     def predict_basis(self, batch, int64=True):
         """forward + ``val.inference_gnn`` without leaving the device (reference
         scripts/pred_basis.py:113-118 ``inference_only``)."""

@@ -206,6 +206,80 @@ status_kernel(const uint32_t* __restrict__ keys, const uint8_t* __restrict__ sid
   }
 }
 
+// ------------------------------------------------------------------------------------------ segmented variant
+// One CTA per LP of a block-diagonal pack: the whole decision (softmax keys, 4-pass radix select, ordered tie
+// break, status) for that LP in a single launch.  Nodes of segment b: constraints [cptr[b], cptr[b+1]) of
+// logits_cons and variables [vptr[b], vptr[b+1]) of logits_vars; k = its number of constraints.  Keys and side
+// bytes live in the global scratch (L2-resident for the LP sizes this is used for); status is written in the packed
+// layout [all constraints | all variables].
+constexpr int kSegThreads = 1024;
+
+template <typename OutT>
+__global__ void __launch_bounds__(kSegThreads)
+segmented_select_kernel(const float* __restrict__ lc, const float* __restrict__ lv, const int32_t* __restrict__ cptr,
+                        const int32_t* __restrict__ vptr, int32_t total_cons, uint32_t* __restrict__ keys,
+                        uint8_t* __restrict__ side, OutT* __restrict__ status) {
+  __shared__ uint32_t hist[4 * 256];
+  __shared__ Threshold ts;
+  __shared__ uint32_t warp_ties[kSegThreads / 32];
+  __shared__ uint32_t run_s;
+  const int b = blockIdx.x;
+  const int32_t c0 = cptr[b], c1 = cptr[b + 1], v0 = vptr[b], v1 = vptr[b + 1];
+  const int32_t mb = c1 - c0, nb = v1 - v0, tot = mb + nb;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  hist[t] = 0;                                       // 4*256 == kSegThreads
+  __syncthreads();
+  // packed position of local node i
+  auto pos = [&](int32_t i) -> int64_t { return i < mb ? (int64_t)c0 + i : (int64_t)total_cons + v0 + (i - mb); };
+  for (int32_t i = t; i < tot; i += kSegThreads) {
+    const float* p = i < mb ? lc + (int64_t)(c0 + i) * 3 : lv + (int64_t)(v0 + i - mb) * 3;
+    const float x0 = p[0], x1 = p[1], x2 = p[2];
+    const float mx = fmaxf(x0, fmaxf(x1, x2));
+    const float e0 = expf(x0 - mx), e1 = expf(x1 - mx), e2 = expf(x2 - mx);
+    const float sum = e0 + e1 + e2;
+    const float p0 = nan_to_zero(e0 / sum), p1 = nan_to_zero(e1 / sum), p2 = nan_to_zero(e2 / sum);
+    const uint32_t key = __float_as_uint(p1);
+    const int64_t g = pos(i);
+    keys[g] = key;
+    side[g] = (p0 >= p2) ? 0 : 2;
+    atomicAdd(&hist[key >> 24], 1u);
+  }
+  __syncthreads();
+  for (int pass = 1; pass < 4; ++pass) {
+    if (t < 32) { const Threshold th = pick_chain(hist, pass, (uint32_t)mb); if (t == 0) ts = th; }
+    __syncthreads();
+    const Threshold th = ts;
+    const int shift = 24 - 8 * pass;
+    for (int32_t i = t; i < tot; i += kSegThreads) {
+      const uint32_t key = keys[pos(i)];
+      if ((key & th.mask) == th.prefix) atomicAdd(&hist[pass * 256 + ((key >> shift) & 0xff)], 1u);
+    }
+    __syncthreads();
+  }
+  if (t < 32) { const Threshold th = pick_chain(hist, 4, (uint32_t)mb); if (t == 0) { ts = th; run_s = 0; } }
+  __syncthreads();
+  const uint32_t thr = ts.prefix, k_rem = ts.k_rem;
+  // ordered pass: ties at the threshold go to the lowest local node index (constraints first)
+  for (int32_t base = 0; base < tot; base += kSegThreads) {
+    const int32_t i = base + t;
+    uint32_t key = 0; bool tie = false;
+    if (i < tot) { key = keys[pos(i)]; tie = key == thr; }
+    const uint32_t ballot = __ballot_sync(0xffffffffu, tie);
+    if (lane == 0) warp_ties[warp] = __popc(ballot);
+    __syncthreads();
+    uint32_t before = run_s + __popc(ballot & ((1u << lane) - 1));
+    for (int w = 0; w < warp; ++w) before += warp_ties[w];
+    if (i < tot) {
+      const bool sel = key > thr || (tie && before < k_rem);
+      const int64_t g = pos(i);
+      status[g] = (OutT)(sel ? 1 : (int)side[g]);
+    }
+    __syncthreads();
+    if (t == 0) { uint32_t s = 0; for (int w = 0; w < kSegThreads / 32; ++w) s += warp_ties[w]; run_s += s; }
+    __syncthreads();
+  }
+}
+
 struct Layout {
   size_t keys, side, hist, state, ties, total;
 };
@@ -271,5 +345,34 @@ extern "C" int lpgnn_basis_select(const float* logits_cons, int32_t m, const flo
                                                         reinterpret_cast<uint8_t*>(status), counts_out);
   LPGNN_LAUNCH_OK();
   count_launches(7);
+  return LPGNN_OK;
+}
+
+extern "C" int lpgnn_basis_select_segmented(const float* logits_cons, const float* logits_vars, const int32_t* cons_ptr,
+                                            const int32_t* vars_ptr, int32_t n_segments, int32_t total_cons,
+                                            int32_t total_vars, void* status, int status_is_i64, void* workspace,
+                                            size_t workspace_bytes, lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(n_segments >= 0 && total_cons >= 0 && total_vars >= 0, "basis_select_segmented: negative size");
+  if (n_segments == 0) return LPGNN_OK;
+  const int64_t total = (int64_t)total_cons + total_vars;
+  const Layout L = layout(total);
+  if (workspace_bytes < L.total) { set_error("basis_select_segmented: workspace too small"); return LPGNN_EWORKSPACE; }
+  LPGNN_REQUIRE(logits_cons && logits_vars && cons_ptr && vars_ptr && status && workspace,
+                "basis_select_segmented: null pointer");
+  char* w = reinterpret_cast<char*>(workspace);
+  uint32_t* keys = reinterpret_cast<uint32_t*>(w + L.keys);
+  uint8_t* side = reinterpret_cast<uint8_t*>(w + L.side);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (status_is_i64)
+    segmented_select_kernel<int64_t><<<n_segments, kSegThreads, 0, st>>>(logits_cons, logits_vars, cons_ptr, vars_ptr,
+                                                                         total_cons, keys, side,
+                                                                         reinterpret_cast<int64_t*>(status));
+  else
+    segmented_select_kernel<uint8_t><<<n_segments, kSegThreads, 0, st>>>(logits_cons, logits_vars, cons_ptr, vars_ptr,
+                                                                         total_cons, keys, side,
+                                                                         reinterpret_cast<uint8_t*>(status));
+  LPGNN_LAUNCH_OK();
+  count_launches(1);
   return LPGNN_OK;
 }

@@ -386,3 +386,34 @@ extern "C" int lpgnn_graph_build(const void* coo_row, const void* coo_col, int i
   count_launches(launches);
   return LPGNN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------- block-diagonal packs
+namespace lpgnn {
+namespace {
+// Entries of LP b sit at [edge_ptr[b], edge_ptr[b+1]) with LP-local indices; shift them to the pack's numbering.
+__global__ void pack_offsets_kernel(int32_t* __restrict__ row, int32_t* __restrict__ col, int64_t nnz,
+                                    const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ cons_ptr,
+                                    const int32_t* __restrict__ vars_ptr, int n_seg) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  int lo = 0, hi = n_seg;                       // largest b with edge_ptr[b] <= e
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (edge_ptr[mid] <= e) lo = mid; else hi = mid; }
+  row[e] += cons_ptr[lo];
+  col[e] += vars_ptr[lo];
+}
+}  // namespace
+}  // namespace lpgnn
+
+extern "C" int lpgnn_pack_offsets(int32_t* row, int32_t* col, int64_t nnz, const int32_t* edge_ptr,
+                                  const int32_t* cons_ptr, const int32_t* vars_ptr, int32_t n_segments,
+                                  lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(nnz >= 0 && n_segments >= 1, "pack_offsets: bad arguments");
+  if (nnz == 0) return LPGNN_OK;
+  LPGNN_REQUIRE(row && col && edge_ptr && cons_ptr && vars_ptr, "pack_offsets: null pointer");
+  pack_offsets_kernel<<<ceil_div(nnz, 256), 256, 0, (cudaStream_t)stream>>>(row, col, nnz, edge_ptr, cons_ptr, vars_ptr,
+                                                                           n_segments);
+  LPGNN_LAUNCH_OK();
+  count_launches(1);
+  return LPGNN_OK;
+}

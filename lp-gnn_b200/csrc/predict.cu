@@ -95,6 +95,16 @@ extern "C" int lpgnn_predict_basis(const lpgnn_gcn_fc_weights* w, const int32_t*
                                    const float* coo_val, int64_t nnz, int32_t m, int32_t n, int flags, const float* x_s,
                                    const float* x_t, uint8_t* status_out, float* logits_out, int32_t* graph_status,
                                    void* workspace, size_t workspace_bytes, lpgnn_stream_t stream) {
+  return lpgnn_predict_basis_packed(w, coo_row, coo_col, coo_val, nnz, m, n, flags, x_s, x_t, nullptr, nullptr, 0,
+                                    status_out, logits_out, graph_status, workspace, workspace_bytes, stream);
+}
+
+extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const int32_t* coo_row,
+                                          const int32_t* coo_col, const float* coo_val, int64_t nnz, int32_t m,
+                                          int32_t n, int flags, const float* x_s, const float* x_t,
+                                          const int32_t* cons_ptr, const int32_t* vars_ptr, int32_t n_segments,
+                                          uint8_t* status_out, float* logits_out, int32_t* graph_status,
+                                          void* workspace, size_t workspace_bytes, lpgnn_stream_t stream) {
   if (int rc = check_device()) return rc;
   LPGNN_REQUIRE(w && m > 0 && n > 0 && nnz >= 0 && x_s && x_t && status_out && workspace, "predict_basis: bad arguments");
   const int H = w->hids, depth = w->depth, p = w->p, q = w->q;
@@ -167,7 +177,13 @@ extern "C" int lpgnn_predict_basis(const lpgnn_gcn_fc_weights* w, const int32_t*
                                   cudaMemcpyDeviceToDevice, st));
   }
   // ---- (a6) basis decision
-  LPGNN_TRY(lpgnn_basis_select(B.logit_s, m, B.logit_t, n, m, status_out, 0, nullptr, B.sel_ws, B.sel_ws_bytes, stream));
+  if (n_segments > 0) {
+    LPGNN_REQUIRE(cons_ptr && vars_ptr, "predict_basis_packed: null segment pointers");
+    LPGNN_TRY(lpgnn_basis_select_segmented(B.logit_s, B.logit_t, cons_ptr, vars_ptr, n_segments, m, n, status_out, 0,
+                                           B.sel_ws, B.sel_ws_bytes, stream));
+  } else {
+    LPGNN_TRY(lpgnn_basis_select(B.logit_s, m, B.logit_t, n, m, status_out, 0, nullptr, B.sel_ws, B.sel_ws_bytes, stream));
+  }
 #undef LPGNN_TRY
   return LPGNN_OK;
 }

@@ -107,3 +107,124 @@ class BasisPipeline:
         last = len(lps) - 1
         self.done[last & 1].synchronize()
         yield last, self.h_status[last & 1][:lps[last].m + lps[last].n].numpy()
+
+
+class PackedBasisPipeline:
+    """Sweep over many small/medium LPs (the reference's pred_basis workload, BASELINE config C5): consecutive LPs
+    are packed block-diagonally up to a node / nonzero budget, one pack = one H2D burst (each LP's pinned arrays
+    are copied straight to their offsets in the pack), ONE native forward over the pack and a per-LP (segmented)
+    basis decision, one D2H copy of the pack's statuses.  Packs are double-buffered like ``BasisPipeline``.
+
+    ``for idx, status in pipe.run(host_lps)`` yields a fresh uint8 array [m+n] (constraints first) per LP, in order.
+    """
+
+    def __init__(self, model, device, max_nodes=200_000, max_nnz=1_000_000, max_lps=64):
+        if not torch.cuda.is_available():
+            raise RuntimeError("PackedBasisPipeline needs a CUDA device (no CPU fallback)")
+        self.model, self.dev = model, torch.device(device)
+        self.max_nodes, self.max_nnz, self.max_lps = max_nodes, max_nnz, max_lps
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self.d_buf, self.h_status, self.h_ptr = [None, None], [None, None], [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def _plan(self, lps):
+        packs, cur, nodes, nnz = [], [], 0, 0
+        for i, lp in enumerate(lps):
+            z = lp.offs[1] - lp.offs[0]
+            if cur and (nodes + lp.m + lp.n > self.max_nodes or nnz + z > self.max_nnz or len(cur) >= self.max_lps):
+                packs.append(cur)
+                cur, nodes, nnz = [], 0, 0
+            cur.append(i)
+            nodes += lp.m + lp.n
+            nnz += z
+        if cur:
+            packs.append(cur)
+        return packs
+
+    def _stage(self, slot, lps, ids, first_use):
+        """H2D of one pack on the copy stream.  Device layout (int32 words):
+        [row Z | col Z | val Z | x_s M*p | x_t N*q | edge_ptr B+1 | cons_ptr B+1 | vars_ptr B+1]."""
+        sub = [lps[i] for i in ids]
+        B = len(sub)
+        zs = [lp.offs[1] - lp.offs[0] for lp in sub]
+        e_ptr = np.concatenate([[0], np.cumsum(zs)]).astype(np.int32)
+        c_ptr = np.concatenate([[0], np.cumsum([lp.m for lp in sub])]).astype(np.int32)
+        v_ptr = np.concatenate([[0], np.cumsum([lp.n for lp in sub])]).astype(np.int32)
+        Z, M, N = int(e_ptr[-1]), int(c_ptr[-1]), int(v_ptr[-1])
+        p, q = sub[0].p, sub[0].q
+        o_row, o_col, o_val = 0, Z, 2 * Z
+        o_xs, o_xt = 3 * Z, 3 * Z + M * p
+        o_ptr = o_xt + N * q
+        words = o_ptr + 3 * (B + 1)
+        if self.d_buf[slot] is None or self.d_buf[slot].numel() < words:
+            self.d_buf[slot] = torch.empty(int(words * 1.25) + 64, dtype=torch.int32, device=self.dev)
+        if self.h_ptr[slot] is None or self.h_ptr[slot].numel() < 3 * (B + 1):
+            self.h_ptr[slot] = torch.empty(3 * (self.max_lps + 1), dtype=torch.int32).pin_memory()
+        hp = self.h_ptr[slot]
+        d = self.d_buf[slot]
+        if not first_use:
+            self.ready[slot].synchronize()      # the slot's previous H2D has consumed the pinned pointer array
+        with torch.cuda.stream(self.copy_stream):
+            if not first_use:
+                self.copy_stream.wait_event(self.done[slot])
+            hp[:3 * (B + 1)] = torch.from_numpy(np.concatenate([e_ptr, c_ptr, v_ptr]))
+            d[o_ptr:o_ptr + 3 * (B + 1)].copy_(hp[:3 * (B + 1)], non_blocking=True)
+            for b, lp in enumerate(sub):
+                o = lp.offs
+                e0, c0, v0 = int(e_ptr[b]), int(c_ptr[b]), int(v_ptr[b])
+                d[o_row + e0:o_row + e0 + zs[b]].copy_(lp.pack[o[0]:o[1]], non_blocking=True)
+                d[o_col + e0:o_col + e0 + zs[b]].copy_(lp.pack[o[1]:o[2]], non_blocking=True)
+                d[o_val + e0:o_val + e0 + zs[b]].copy_(lp.pack[o[2]:o[3]], non_blocking=True)
+                d[o_xs + c0 * p:o_xs + (c0 + lp.m) * p].copy_(lp.pack[o[3]:o[4]], non_blocking=True)
+                d[o_xt + v0 * q:o_xt + (v0 + lp.n) * q].copy_(lp.pack[o[4]:o[5]], non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+        return dict(B=B, Z=Z, M=M, N=N, p=p, q=q, offs=(o_row, o_col, o_val, o_xs, o_xt, o_ptr), c_ptr=c_ptr, v_ptr=v_ptr,
+                    sorted=all(lp.sorted for lp in sub))
+
+    @torch.no_grad()
+    def _compute(self, slot, meta):
+        from . import _lib
+        cur = torch.cuda.current_stream(self.dev)
+        M, N, Z, B, p, q = meta["M"], meta["N"], meta["Z"], meta["B"], meta["p"], meta["q"]
+        if self.h_status[slot] is None or self.h_status[slot].numel() < M + N:
+            self.h_status[slot] = torch.empty(int((M + N) * 1.25) + 64, dtype=torch.uint8).pin_memory()
+        cur.wait_event(self.ready[slot])
+        d = self.d_buf[slot]
+        o_row, o_col, o_val, o_xs, o_xt, o_ptr = meta["offs"]
+        row, col = d[o_row:o_row + Z], d[o_col:o_col + Z]
+        val = d[o_val:o_val + Z].view(torch.float32)
+        x_s = d[o_xs:o_xs + M * p].view(torch.float32).view(M, p)
+        x_t = d[o_xt:o_xt + N * q].view(torch.float32).view(N, q)
+        e_ptr, c_ptr, v_ptr = (d[o_ptr + k * (B + 1):o_ptr + (k + 1) * (B + 1)] for k in range(3))
+        with torch.cuda.device(self.dev):
+            rc = _lib.load().lpgnn_pack_offsets(row.data_ptr(), col.data_ptr(), Z, e_ptr.data_ptr(), c_ptr.data_ptr(),
+                                                v_ptr.data_ptr(), B, _lib.stream_ptr())
+        _lib.check(rc, "lpgnn_pack_offsets")
+        st = self.model.predict_basis_packed(row, col, val, M, N, x_s, x_t, c_ptr, v_ptr, is_sorted=meta["sorted"])
+        self.h_status[slot][:M + N].copy_(st, non_blocking=True)
+        self.done[slot].record(cur)
+
+    def _emit(self, slot, meta, ids):
+        self.done[slot].synchronize()
+        h = self.h_status[slot].numpy()
+        M, c, v = meta["M"], meta["c_ptr"], meta["v_ptr"]
+        for b, i in enumerate(ids):
+            yield i, np.concatenate([h[c[b]:c[b + 1]], h[M + v[b]:M + v[b + 1]]])
+
+    def run(self, host_lps):
+        lps = list(host_lps)
+        packs = self._plan(lps)
+        if not packs:
+            return
+        metas = [None] * len(packs)
+        metas[0] = self._stage(0, lps, packs[0], True)
+        for k, ids in enumerate(packs):
+            slot = k & 1
+            if k + 1 < len(packs):
+                metas[k + 1] = self._stage(slot ^ 1, lps, packs[k + 1], k + 1 < 2)
+            self._compute(slot, metas[k])
+            if k > 0:
+                yield from self._emit(slot ^ 1, metas[k - 1], packs[k - 1])
+        last = len(packs) - 1
+        yield from self._emit(last & 1, metas[last], packs[last])

@@ -131,3 +131,52 @@ def test_basis_pipeline_matches_direct_calls(cuda):
     # a second pass over the same pipeline object reuses the slots
     again = {i: st.copy() for i, st in pipe.run(hosts[::-1])}
     np.testing.assert_array_equal(again[0], got[len(lps) - 1])
+
+
+def test_packed_pipeline_matches_per_lp_prediction(cuda):
+    """Block-diagonal packs (one forward per pack, segmented basis decision) == one call per LP."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import arch, synth
+    from lpgnn_b200.pipeline import BasisPipeline, PackedBasisPipeline, pack_lp
+    torch.manual_seed(0)
+    model = arch.GCN_FC(8, 8, hids=128, depth=3).to(cuda).eval().set_precision("fp32")
+    rng = np.random.default_rng(5)
+    sizes = [(int(m), int(2 * m), int(10 * m)) for m in rng.integers(20, 3000, 37)] + [(5, 9, 20), (4000, 8000, 40_000)]
+    lps = [synth.processed_lp(m, n, z, seed=70 + i) for i, (m, n, z) in enumerate(sizes)]
+    hosts = [pack_lp(lp.row, lp.col, lp.a_data, lp.c_feas, lp.v_feas) for lp in lps]
+    single = {i: st.copy() for i, st in BasisPipeline(model, cuda).run(hosts)}
+    packed = PackedBasisPipeline(model, cuda, max_nodes=20_000, max_nnz=100_000, max_lps=8)
+    plan = packed._plan(hosts)
+    assert len(plan) > 4 and max(len(p) for p in plan) > 1 and sorted(sum(plan, [])) == list(range(len(lps)))
+    got = dict(packed.run(hosts))
+    assert sorted(got) == list(range(len(lps)))
+    for i, lp in enumerate(lps):
+        assert got[i].shape == (lp.m + lp.n,) and int((got[i] == 1).sum()) == lp.m      # per-LP top-m rule
+        np.testing.assert_array_equal(got[i], single[i])                                # fp32: same arithmetic per row
+
+
+def test_segmented_select_matches_single(cuda):
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import _lib, ops
+    rng = np.random.default_rng(9)
+    ms = [1, 7, 300, 2500, 40]
+    ns = [1, 20, 700, 4100, 90]
+    lc = torch.from_numpy((rng.standard_normal((sum(ms), 3)) * 3).astype(np.float32)).to(cuda)
+    lv = torch.from_numpy((rng.standard_normal((sum(ns), 3)) * 3).astype(np.float32)).to(cuda)
+    lv[5:25] = 0.0                                                  # ties inside segment 1
+    cptr = torch.tensor(np.concatenate([[0], np.cumsum(ms)]), dtype=torch.int32, device=cuda)
+    vptr = torch.tensor(np.concatenate([[0], np.cumsum(ns)]), dtype=torch.int32, device=cuda)
+    lib = _lib.load()
+    M, N = sum(ms), sum(ns)
+    status = torch.empty(M + N, dtype=torch.uint8, device=cuda)
+    nb = lib.lpgnn_basis_select_workspace_bytes(M + N)
+    ws = torch.empty(nb, dtype=torch.uint8, device=cuda)
+    rc = lib.lpgnn_basis_select_segmented(lc.data_ptr(), lv.data_ptr(), cptr.data_ptr(), vptr.data_ptr(), len(ms), M, N,
+                                          status.data_ptr(), 0, ws.data_ptr(), nb, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    status = status.cpu().numpy()
+    c, v = cptr.cpu().numpy(), vptr.cpu().numpy()
+    for b in range(len(ms)):
+        exp = ops.basis_select(lc[c[b]:c[b + 1]], lv[v[b]:v[b + 1]], int64=False).cpu().numpy()
+        got = np.concatenate([status[c[b]:c[b + 1]], status[M + v[b]:M + v[b + 1]]])
+        np.testing.assert_array_equal(got, exp)
