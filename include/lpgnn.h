@@ -87,6 +87,12 @@ LPGNN_API int lpgnn_graph_build(const void* coo_row, const void* coo_col, int id
                       int32_t* csr2csc /*[nnz]*/, int32_t* status /*[1] device, optional*/,
                       void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
 
+/* `count` independent pinned-host -> device copies enqueued on `stream` by one native call (addresses and
+ * sizes as host arrays of uint64).  Used to stage a pack of LPs: each LP's arrays go straight to their
+ * offsets in the pack. */
+LPGNN_API int lpgnn_copy_many_h2d(const uint64_t* dst_ptrs, const uint64_t* src_ptrs, const uint64_t* nbytes,
+                        int32_t count, lpgnn_stream_t stream);
+
 /* Block-diagonal packing of several LPs into one graph (the direct sum of their matrices): the COO entries
  * of LP b occupy [edge_ptr[b], edge_ptr[b+1]) with LP-local indices; this shifts them in place by the LP's
  * first constraint (cons_ptr[b]) / variable (vars_ptr[b]) of the pack.  A pack of row-major sorted LPs is

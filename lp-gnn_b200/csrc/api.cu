@@ -165,3 +165,19 @@ extern "C" int lpgnn_gemm_tn(const void* A, const void* B, int32_t M, int32_t N,
   count_launches(1);
   return LPGNN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------- host->device bursts
+// Enqueues `count` independent pinned-host -> device copies with one call (a plain loop of cudaMemcpyAsync):
+// the per-copy cost drops from a Python round trip to a native call, which is what bounds sweeps over small LPs.
+extern "C" int lpgnn_copy_many_h2d(const uint64_t* dst_ptrs, const uint64_t* src_ptrs, const uint64_t* nbytes,
+                                   int32_t count, lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(count >= 0 && (count == 0 || (dst_ptrs && src_ptrs && nbytes)), "copy_many_h2d: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < count; ++i) {
+    if (nbytes[i] == 0) continue;
+    LPGNN_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<void*>(dst_ptrs[i]), reinterpret_cast<const void*>(src_ptrs[i]),
+                                  (size_t)nbytes[i], cudaMemcpyHostToDevice, st));
+  }
+  return LPGNN_OK;
+}

@@ -165,20 +165,32 @@ class PackedBasisPipeline:
         d = self.d_buf[slot]
         if not first_use:
             self.ready[slot].synchronize()      # the slot's previous H2D has consumed the pinned pointer array
+        hp[:3 * (B + 1)] = torch.from_numpy(np.concatenate([e_ptr, c_ptr, v_ptr]))
+        # one native call enqueues all copies of the pack: 5 per LP (row, col, val, x_s, x_t straight to their
+        # offsets in the pack) + the segment pointer arrays
+        base = d.data_ptr()
+        src0 = np.array([lp.pack.data_ptr() for lp in sub], dtype=np.uint64)
+        offs = np.array([lp.offs for lp in sub], dtype=np.uint64)                       # [B, 6] word offsets in the LP pack
+        ms, ns = np.array([lp.m for lp in sub], dtype=np.uint64), np.array([lp.n for lp in sub], dtype=np.uint64)
+        e0, c0, v0 = e_ptr[:-1].astype(np.uint64), c_ptr[:-1].astype(np.uint64), v_ptr[:-1].astype(np.uint64)
+        dst_w = np.stack([o_row + e0, o_col + e0, o_val + e0, o_xs + c0 * p, o_xt + v0 * q], axis=1)   # [B,5] words
+        src = (src0[:, None] + 4 * offs[:, :5]).reshape(-1)
+        dst = (np.uint64(base) + 4 * dst_w).reshape(-1)
+        nby = (4 * (offs[:, 1:6] - offs[:, 0:5])).reshape(-1)
+        src = np.concatenate([src, np.array([hp.data_ptr()], dtype=np.uint64)])
+        dst = np.concatenate([dst, np.array([base + 4 * o_ptr], dtype=np.uint64)])
+        nby = np.ascontiguousarray(np.concatenate([nby, np.array([12 * (B + 1)], dtype=np.uint64)]))
+        src, dst = np.ascontiguousarray(src), np.ascontiguousarray(dst)
+        from . import _lib
         with torch.cuda.stream(self.copy_stream):
             if not first_use:
                 self.copy_stream.wait_event(self.done[slot])
-            hp[:3 * (B + 1)] = torch.from_numpy(np.concatenate([e_ptr, c_ptr, v_ptr]))
-            d[o_ptr:o_ptr + 3 * (B + 1)].copy_(hp[:3 * (B + 1)], non_blocking=True)
-            for b, lp in enumerate(sub):
-                o = lp.offs
-                e0, c0, v0 = int(e_ptr[b]), int(c_ptr[b]), int(v_ptr[b])
-                d[o_row + e0:o_row + e0 + zs[b]].copy_(lp.pack[o[0]:o[1]], non_blocking=True)
-                d[o_col + e0:o_col + e0 + zs[b]].copy_(lp.pack[o[1]:o[2]], non_blocking=True)
-                d[o_val + e0:o_val + e0 + zs[b]].copy_(lp.pack[o[2]:o[3]], non_blocking=True)
-                d[o_xs + c0 * p:o_xs + (c0 + lp.m) * p].copy_(lp.pack[o[3]:o[4]], non_blocking=True)
-                d[o_xt + v0 * q:o_xt + (v0 + lp.n) * q].copy_(lp.pack[o[4]:o[5]], non_blocking=True)
+            with torch.cuda.device(self.dev):
+                rc = _lib.load().lpgnn_copy_many_h2d(dst.ctypes.data, src.ctypes.data, nby.ctypes.data, int(src.shape[0]),
+                                                     self.copy_stream.cuda_stream)
+            _lib.check(rc, "lpgnn_copy_many_h2d")
             self.ready[slot].record(self.copy_stream)
+        del ms, ns
         return dict(B=B, Z=Z, M=M, N=N, p=p, q=q, offs=(o_row, o_col, o_val, o_xs, o_xt, o_ptr), c_ptr=c_ptr, v_ptr=v_ptr,
                     sorted=all(lp.sorted for lp in sub))
 
