@@ -438,14 +438,27 @@ def kernel_rooflines(model, lp, dev, peaks, bf16, args):
 
     c1 = model.conv1
     w = lambda p: p.detach()
-    # input layer (fused aggregate+transform), variables side: rows = n
-    f_in = lambda: ops.conv_in_fused(csc, xs, xt, w(c1.left2right.lin_rel.weight), w(c1.left2right.lin_rel.bias),
-                                     w(c1.left2right.lin_root.weight), dt, relu=True)
-    t = time_kernel(f_in, reps, flush)
-    add("conv_in_fused (vars side)", "hbm", t, n * H * s + (m + n) * 8 * 4 + z * 8 + (n + 1) * 4, 1)
-    right, _ = f_in()
-    left, _ = ops.conv_in_fused(csr, xt, xs, w(c1.right2left.lin_rel.weight), w(c1.right2left.lin_rel.bias),
-                                w(c1.right2left.lin_root.weight), dt, relu=True)
+    # input layer, variables side (rows = n): gather [A^T x_s | x_t] then the transform
+    if bf16:
+        from lpgnn_b200.autograd import wcat_bf16
+        wc = wcat_bf16(c1._cache, c1.left2right)
+        t_g = time_kernel(lambda: ops.gather_cat(csc, xs, xt, want_f32=False, want_bf16=True), reps, flush)
+        add("gather_cat (vars side)", "hbm", t_g, n * 64 * 2 + (m + n) * 8 * 4 + z * 8 + (n + 1) * 4, 1)
+        _, zb = ops.gather_cat(csc, xs, xt, want_f32=False, want_bf16=True)
+        f_in = lambda: ops.node_transform(zb, wc, bias=w(c1.left2right.lin_rel.bias), relu=True)
+        t = time_kernel(f_in, reps, flush)
+        add("input transform, one K block (tcgen05, vars side)", "hbm", t, n * H * s + n * 64 * 2, 1)
+        right = f_in()
+        _, zbs = ops.gather_cat(csr, xt, xs, want_f32=False, want_bf16=True)
+        left = ops.node_transform(zbs, wcat_bf16(c1._cache, c1.right2left), bias=w(c1.right2left.lin_rel.bias), relu=True)
+    else:
+        f_in = lambda: ops.conv_in_fused(csc, xs, xt, w(c1.left2right.lin_rel.weight), w(c1.left2right.lin_rel.bias),
+                                         w(c1.left2right.lin_root.weight), dt, relu=True)
+        t = time_kernel(f_in, reps, flush)
+        add("conv_in_fused (gather + CUDA-core transform, vars side)", "hbm", t, n * H * s + (m + n) * 8 * 4 + z * 8 + (n + 1) * 4, 2)
+        right, _ = f_in()
+        left, _ = ops.conv_in_fused(csr, xt, xs, w(c1.right2left.lin_rel.weight), w(c1.right2left.lin_rel.bias),
+                                    w(c1.right2left.lin_root.weight), dt, relu=True)
     if len(model.layers):
         conv = model.layers[0]
         cast = conv._cache.get
@@ -471,7 +484,7 @@ def kernel_rooflines(model, lp, dev, peaks, bf16, args):
     lc = torch.randn(m, 3, device=dev)
     lv = torch.randn(n, 3, device=dev)
     t_sel = time_kernel(lambda: ops.basis_select(lc, lv, int64=False), reps, flush)
-    add("basis_select (12 launches)", "hbm", t_sel, (m + n) * (12 + 4 + 1 + 4 * 4 + 4 + 1), 12)
+    add("basis_select (7 launches)", "hbm", t_sel, (m + n) * (12 + 4 + 1 + 4 * 4 + 4 + 1), 7)
     h_row = torch.from_numpy(lp.row.astype(np.int32)).to(dev)
     h_col = torch.from_numpy(lp.col.astype(np.int32)).to(dev)
     h_val = torch.from_numpy(lp.a_data.astype(np.float32)).to(dev)

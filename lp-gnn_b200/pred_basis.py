@@ -94,7 +94,21 @@ def run(args):
     times = {}
     pool = ThreadPoolExecutor(max_workers=4)
     futures = []
-    if sub is not None:
+    if sub is not None and getattr(args, "packed", 0):
+        # sweep mode: LPs packed block-diagonally, one native forward per pack, segmented basis decision, no
+        # per-LP Python round trips (the .sort probability files are not produced in this mode)
+        from .pipeline import PackedBasisPipeline, pack_lp
+        loader = DataLoader(sub, batch_size=1, shuffle=False, num_workers=args.num_workers)
+        names, hosts = [], []
+        for batch in loader:
+            r, c, v = batch.edge_index._coo
+            names.append(extract_fn(batch.processed_path[0]))
+            hosts.append(pack_lp(r.numpy(), c.numpy(), v.numpy(), batch.x_s.numpy(), batch.x_t.numpy(),
+                                 is_sorted=batch.edge_index._sorted_hint))
+        for i, status in PackedBasisPipeline(model, dev).run(hosts):
+            m = hosts[i].m
+            futures.append(pool.submit(write_bas_highs, f"{out_dir}/{names[i]}.bas", None, None, status[m:], status[:m]))
+    elif sub is not None:
         loader = DataLoader(sub, batch_size=1, shuffle=False, num_workers=args.num_workers)
         for batch in loader:
             fn = extract_fn(batch.processed_path[0])

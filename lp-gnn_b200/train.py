@@ -87,6 +87,7 @@ def parse_args(argv=None, **defaults):
     ap.add_argument("--split", type=str, default="val")
     ap.add_argument("--fp16", type=int, default=0)
     ap.add_argument("--log_every", type=int, default=9)
+    ap.add_argument("--packed", type=int, default=0, help="pred_basis: pack LPs block-diagonally (sweep mode)")
     ap.add_argument("--dataset_processed_prefix", type=str, default=None)
     ap.add_argument("--log_dir", type=str, default=None)
     ap.set_defaults(**defaults)

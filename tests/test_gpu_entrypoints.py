@@ -57,6 +57,14 @@ def test_train_then_predict_basis_files(cuda, dataset_root, tmp_path):
         agree = np.mean(np.concatenate([cbas, vbas]) == exp)
         assert agree >= 0.995, agree
         assert os.path.exists(f"{log_dir}/pred-basis/{fn}.bas.sort")
+    # sweep mode (block-diagonal packs, segmented basis decision) writes the same .bas files
+    log2 = str(tmp_path / "run_packed") + "/"
+    args3 = train.parse_args([], arch="GCN_FC(8,8,hids=64,depth=3)", load_from=log_dir + "mdl.pth", packed=1,
+                             dataset_processed_prefix=dataset_root, log_dir=log2, split="val", num_workers=0)
+    pred_basis.run(args3)
+    for i in val_ds.indices():
+        fn = os.path.basename(ds.get(i).processed_path).replace(".pk", "")
+        assert open(f"{log2}/pred-basis/{fn}.bas").read() == open(f"{log_dir}/pred-basis/{fn}.bas").read()
 
 
 def test_val_inference_gnn_and_accuracy_accept_cpu_logits(cuda):
