@@ -94,7 +94,8 @@ extern "C" int lpgnn_node_transform(const void* A1, int32_t K1, const void* W1, 
                              nullptr, 1, st);
 }
 
-extern "C" int32_t lpgnn_node_transform_head_parts(int32_t N) { return N % 256 == 0 ? N / 256 : (N % 128 == 0 ? N / 128 : N / 64); }
+// two partial slices per column tile (the tile's columns are drained by two warps per row)
+extern "C" int32_t lpgnn_node_transform_head_parts(int32_t N) { return 2 * (N % 256 == 0 ? N / 256 : (N % 128 == 0 ? N / 128 : N / 64)); }
 
 extern "C" int lpgnn_node_transform_head(const void* A1, int32_t K1, const void* W1, const void* A2, int32_t K2,
                                          const void* W2, const float* bias, int32_t M, int32_t N, void* out,

@@ -25,21 +25,23 @@ namespace {
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UK = 16;           // UMMA K for 16-bit inputs
-constexpr int kThreads = 256;
 constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarps = 8;                         // two warps per TMEM lane quarter, each takes half of the columns
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = kEpiWarp0 * 32 + kEpiThreads;  // 384
 
-template <int BN> struct Cfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+template <int BN, typename OutT> struct Cfg {
+  static constexpr int kRowBytes = 32 * (int)sizeof(OutT);   // one staged piece: 32 columns of one row
+  static constexpr int kStagingBytes = kEpiWarps * 32 * kRowBytes;
+  static constexpr bool kWide = sizeof(OutT) == 4;   // fp32 output needs twice the staging space
+  static constexpr int kStages = (BN == 256) ? (kWide ? 3 : 4) : (BN == 128 ? (kWide ? 5 : 6) : (kWide ? 6 : 8));
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;  // power of two >= 32 for BN in {64,128,256}
   static constexpr int kBarBytes = 5120;  // mbarriers + tmem ptr + bias slice (BN floats) + head weight slice (3*BN floats)
-  // epilogue staging: per epilogue warp 32 rows x (128 B payload + 16 B pad); the pad makes both the
-  // row-wise 16-byte writes and the 4-rows-per-instruction read-back bank-conflict free
-  static constexpr int kStagePitch = 144;
-  static constexpr int kStagingBytes = 4 * 32 * kStagePitch;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kStagingBytes + 1024 /*align slack*/;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 };
 
 template <int BN, typename OutT>
@@ -49,7 +51,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                int kblocks2, const float* __restrict__ bias, OutT* __restrict__ out, int M, int N,
                int relu, const float* __restrict__ head_w /*[3,N] or null*/,
                float* __restrict__ head_partial /*[N/BN][M][3] or null*/, int ksplit) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, OutT>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -82,7 +84,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tmem_full[b], 1); ptx::mbar_init(&tmem_empty[b], 128); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tmem_full[b], 1); ptx::mbar_init(&tmem_empty[b], kEpiThreads); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -145,8 +147,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     }
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------------ epilogue
-    const int q = warp - kEpiWarp0;               // TMEM lane quarter of this warp (== warp % 4)
-    const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..127
+    const int ew = warp - kEpiWarp0;              // 0..7
+    const int q = ew & 3;                         // TMEM lane quarter of this warp (== warp % 4)
+    const int hsel = ew >> 2;                     // which half of the tile's columns this warp drains
+    const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..255
+    constexpr int kPieces = BN / 32;              // 32-column pieces per tile row
+    constexpr int kPiecesPerWarp = kPieces / 2;
+    constexpr int P = C::kRowBytes / 16;          // 16-byte chunks per staged row: 4 (bf16) or 8 (fp32)
+    constexpr int kRowsPerInstr = 32 / P;         // rows covered by one warp-wide 16-byte store: 8 or 4
+    uint8_t* my_stage = staging + ew * (32 * C::kRowBytes);
     int t = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const int ot = tile % num_out_tiles, split = tile / num_out_tiles;
@@ -154,54 +163,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       OutT* const out_t = out ? out + (int64_t)split * M * N : nullptr;
       const int buf = t & 1;
       const uint32_t use_phase = (t >> 1) & 1;
-      // stage the bias slice of this tile
-      for (int j = et; j < BN; j += 128) bias_s[j] = bias ? __ldg(bias + n_blk * BN + j) : 0.f;
+      // stage the bias (and head weight) slice of this tile
+      for (int j = et; j < BN; j += kEpiThreads) bias_s[j] = bias ? __ldg(bias + n_blk * BN + j) : 0.f;
       if (head_w)
-        for (int j = et; j < 3 * BN; j += 128) headw_s[j] = __ldg(head_w + (int64_t)(j / BN) * N + n_blk * BN + (j % BN));
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int j = et; j < 3 * BN; j += kEpiThreads)
+          headw_s[j] = __ldg(head_w + (int64_t)(j / BN) * N + n_blk * BN + (j % BN));
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       ptx::mbar_wait(&tmem_full[buf], use_phase);
       ptx::tc_fence_after();
-      // Each lane owns accumulator row (q*32 + lane).  128 payload bytes per row (64 bf16 / 32 fp32 columns) are
-      // staged through shared memory so that one warp-wide 16-byte store covers 4 rows x 128 contiguous bytes
-      // instead of 32 rows x 16 bytes (32 cache lines per instruction).
-      constexpr int kColsPerPiece = 128 / (int)sizeof(OutT);       // 64 (bf16) or 32 (fp32)
-      uint8_t* my_stage = staging + q * (32 * C::kStagePitch);
+      // Each lane owns accumulator row (q*32 + lane).  A 32-column piece of the row (64 B bf16 / 128 B fp32) is
+      // staged through shared memory with an XOR swizzle (conflict-free both ways) so that one warp-wide 16-byte
+      // store covers 8 (4) rows x 64 (128) contiguous bytes instead of 32 rows x 16 bytes.
       const int64_t row_base = (int64_t)m_blk * BM + q * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+      const int wsw = (sizeof(OutT) == 2) ? ((lane >> 1) & 3) : (lane & 7);   // write-side swizzle of this lane's row
       float hd0 = 0.f, hd1 = 0.f, hd2 = 0.f;   // fused basis-status head: partial dot products of this row
 #pragma unroll 1
-      for (int pc = 0; pc < BN / kColsPerPiece; ++pc) {
-        uint4* srow = reinterpret_cast<uint4*>(my_stage + lane * C::kStagePitch);
+      for (int pi = 0; pi < kPiecesPerWarp; ++pi) {
+        const int pc = hsel * kPiecesPerWarp + pi;
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(taddr + pc * 32, r);
+        ptx::tmem_ld_wait();
+        uint4* srow = reinterpret_cast<uint4*>(my_stage + lane * C::kRowBytes);
         if constexpr (sizeof(OutT) == 2) {
+          uint32_t packed[16];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32(taddr + pc * 64 + h * 32, r);
-            ptx::tmem_ld_wait();
-            uint32_t packed[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float v0 = __uint_as_float(r[2 * j]) + bias_s[pc * 64 + h * 32 + 2 * j];
-              float v1 = __uint_as_float(r[2 * j + 1]) + bias_s[pc * 64 + h * 32 + 2 * j + 1];
-              if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-              packed[j] = pack_bf16(v0, v1);
-              if (head_w) {
-                const int col = pc * 64 + h * 32 + 2 * j;
-                hd0 = fmaf(v0, headw_s[col], hd0);          hd0 = fmaf(v1, headw_s[col + 1], hd0);
-                hd1 = fmaf(v0, headw_s[BN + col], hd1);     hd1 = fmaf(v1, headw_s[BN + col + 1], hd1);
-                hd2 = fmaf(v0, headw_s[2 * BN + col], hd2); hd2 = fmaf(v1, headw_s[2 * BN + col + 1], hd2);
-              }
-            }
-            if (out) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                srow[h * 4 + j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          for (int j = 0; j < 16; ++j) {
+            float v0 = __uint_as_float(r[2 * j]) + bias_s[pc * 32 + 2 * j];
+            float v1 = __uint_as_float(r[2 * j + 1]) + bias_s[pc * 32 + 2 * j + 1];
+            if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            packed[j] = pack_bf16(v0, v1);
+            if (head_w) {
+              const int col = pc * 32 + 2 * j;
+              hd0 = fmaf(v0, headw_s[col], hd0);          hd0 = fmaf(v1, headw_s[col + 1], hd0);
+              hd1 = fmaf(v0, headw_s[BN + col], hd1);     hd1 = fmaf(v1, headw_s[BN + col + 1], hd1);
+              hd2 = fmaf(v0, headw_s[2 * BN + col], hd2); hd2 = fmaf(v1, headw_s[2 * BN + col + 1], hd2);
             }
           }
+          if (out) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              srow[j ^ wsw] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          }
         } else {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(taddr + pc * 32, r);
-          ptx::tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float v = __uint_as_float(r[j]) + bias_s[pc * 32 + j];
@@ -209,19 +213,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             r[j] = __float_as_uint(v);
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) srow[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          for (int j = 0; j < 8; ++j) srow[j ^ wsw] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         }
         if (!out) continue;                       // head-only mode: the activation tile is never written
         __syncwarp();
-        // read back: instruction i covers rows 4i..4i+3, lane -> (row 4i + lane/8, 16-byte piece lane%8)
-        const int sub_row = lane >> 3, piece = lane & 7;
+        const int sub_row = lane / P, piece = lane % P;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = 4 * i + sub_row;
-          const uint4 v = *reinterpret_cast<const uint4*>(my_stage + rr * C::kStagePitch + piece * 16);
+        for (int i = 0; i < 32 / kRowsPerInstr; ++i) {
+          const int rr = kRowsPerInstr * i + sub_row;
+          const int rsw = (sizeof(OutT) == 2) ? ((rr >> 1) & 3) : (rr & 7);
+          const uint4 v = *reinterpret_cast<const uint4*>(my_stage + rr * C::kRowBytes + ((piece ^ rsw) * 16));
           const int64_t grow = row_base + rr;
           if (grow < M) {
-            uint8_t* dst = reinterpret_cast<uint8_t*>(out_t + grow * N + (int64_t)n_blk * BN + pc * kColsPerPiece);
+            uint8_t* dst = reinterpret_cast<uint8_t*>(out_t + grow * N + (int64_t)n_blk * BN + pc * 32);
             *reinterpret_cast<uint4*>(dst + piece * 16) = v;
           }
         }
@@ -230,13 +234,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       if (head_partial) {
         const int64_t grow = row_base + lane;
         if (grow < M) {
-          float* hp = head_partial + ((int64_t)n_blk * M + grow) * 3;
+          float* hp = head_partial + ((int64_t)(n_blk * 2 + hsel) * M + grow) * 3;
           hp[0] = hd0; hp[1] = hd1; hp[2] = hd2;
         }
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[buf]);
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // bias_s may be overwritten for the next tile
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // bias_s may be overwritten for the next tile
     }
   }
 
@@ -281,7 +285,7 @@ template <int BN, typename OutT>
 int launch(const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& a2, const CUtensorMap& w2, int kb1, int kb2,
            const float* bias, void* out, int M, int N, int relu, const float* head_w, float* head_partial,
            int ksplit, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, OutT>;
   static bool attr_set = false;
   if (!attr_set) {
     LPGNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,

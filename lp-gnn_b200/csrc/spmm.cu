@@ -19,12 +19,10 @@ template <typename T> struct Chunk;  // 16-byte chunk of features
 template <> struct Chunk<float> {
   static constexpr int kElems = 4;
   __device__ static void fma(float (&acc)[4], float w, const uint4& v) {
-    const float2 ww = make_float2(w, w);
-    float2 a;
-    a = __ffma2_rn(ww, make_float2(__uint_as_float(v.x), __uint_as_float(v.y)), make_float2(acc[0], acc[1]));
-    acc[0] = a.x; acc[1] = a.y;
-    a = __ffma2_rn(ww, make_float2(__uint_as_float(v.z), __uint_as_float(v.w)), make_float2(acc[2], acc[3]));
-    acc[2] = a.x; acc[3] = a.y;
+    acc[0] = fmaf(w, __uint_as_float(v.x), acc[0]);
+    acc[1] = fmaf(w, __uint_as_float(v.y), acc[1]);
+    acc[2] = fmaf(w, __uint_as_float(v.z), acc[2]);
+    acc[3] = fmaf(w, __uint_as_float(v.w), acc[3]);
   }
   __device__ static uint4 pack(const float (&acc)[4]) {
     return make_uint4(__float_as_uint(acc[0]), __float_as_uint(acc[1]), __float_as_uint(acc[2]),
@@ -34,13 +32,11 @@ template <> struct Chunk<float> {
 template <> struct Chunk<__nv_bfloat16> {
   static constexpr int kElems = 8;
   __device__ static void fma(float (&acc)[8], float w, const uint4& v) {
-    // packed fp32 FMA (FFMA2, sm_100): the kernel is instruction-issue bound on unpack + FMA, not on DRAM
-    const float2 ww = make_float2(w, w);
-    float2 a;
-    a = __ffma2_rn(ww, make_float2(bf16_lo(v.x), bf16_hi(v.x)), make_float2(acc[0], acc[1])); acc[0] = a.x; acc[1] = a.y;
-    a = __ffma2_rn(ww, make_float2(bf16_lo(v.y), bf16_hi(v.y)), make_float2(acc[2], acc[3])); acc[2] = a.x; acc[3] = a.y;
-    a = __ffma2_rn(ww, make_float2(bf16_lo(v.z), bf16_hi(v.z)), make_float2(acc[4], acc[5])); acc[4] = a.x; acc[5] = a.y;
-    a = __ffma2_rn(ww, make_float2(bf16_lo(v.w), bf16_hi(v.w)), make_float2(acc[6], acc[7])); acc[6] = a.x; acc[7] = a.y;
+    // plain FFMA: the packed FFMA2 form measured slower here (register-pair moves outweigh the saved issue slots)
+    acc[0] = fmaf(w, bf16_lo(v.x), acc[0]); acc[1] = fmaf(w, bf16_hi(v.x), acc[1]);
+    acc[2] = fmaf(w, bf16_lo(v.y), acc[2]); acc[3] = fmaf(w, bf16_hi(v.y), acc[3]);
+    acc[4] = fmaf(w, bf16_lo(v.z), acc[4]); acc[5] = fmaf(w, bf16_hi(v.z), acc[5]);
+    acc[6] = fmaf(w, bf16_lo(v.w), acc[6]); acc[7] = fmaf(w, bf16_hi(v.w), acc[7]);
   }
   __device__ static uint4 pack(const float (&acc)[8]) {
     return make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
