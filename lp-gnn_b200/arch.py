@@ -192,11 +192,18 @@ class GCN_FC(GCNBase):
                 wc = wcat_bf16(c1._cache, gc)
                 keep.append(wc)
                 setattr(w, f"c1_{tag}_wcat", wc.data_ptr())
+        from .autograd import split_cached, use_x3
         for i, conv in enumerate(self.layers):
             for tag, gc in (("l2r", conv.left2right), ("r2l", conv.right2left)):
                 getattr(w, f"{tag}_wrel")[i] = cd(gc.lin_rel.weight)
                 getattr(w, f"{tag}_wroot")[i] = cd(gc.lin_root.weight)
                 getattr(w, f"{tag}_b")[i] = f32(gc.lin_rel.bias)
+                if not bf16 and use_x3(conv):
+                    for nm, par in (("wrel", gc.lin_rel.weight), ("wroot", gc.lin_root.weight)):
+                        hi, lo = split_cached(conv._cache, par)
+                        keep.extend((hi, lo))
+                        getattr(w, f"{tag}_{nm}_hi")[i] = hi.data_ptr()
+                        getattr(w, f"{tag}_{nm}_lo")[i] = lo.data_ptr()
         w.head_left_w, w.head_left_b = f32(self.lin_left.weight), f32(self.lin_left.bias)
         w.head_right_w, w.head_right_b = f32(self.lin_right.weight), f32(self.lin_right.bias)
         self._native_cache = (ver, w, keep)
@@ -217,7 +224,8 @@ class GCN_FC(GCNBase):
         w = self._native_weights()
         dev = x_s.device
         z = int(row.shape[0])
-        ws_bytes = lib.lpgnn_predict_workspace_bytes(z, m, n, w.p, w.q, w.hids, w.depth, w.precision)
+        x3 = _lib.WS_X3 if (w.precision == _lib.F32 and w.depth > 2 and w.l2r_wrel_hi[0]) else 0
+        ws_bytes = lib.lpgnn_predict_workspace_bytes(z, m, n, w.p, w.q, w.hids, w.depth, w.precision | x3)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         status = torch.empty(m + n, dtype=torch.uint8, device=dev)
         logits = torch.empty((m + n, 3), dtype=torch.float32, device=dev) if want_logits else None
@@ -245,7 +253,8 @@ class GCN_FC(GCNBase):
         w = self._native_weights()
         dev = x_s.device
         z = int(row.shape[0])
-        ws_bytes = lib.lpgnn_predict_workspace_bytes(z, m, n, w.p, w.q, w.hids, w.depth, w.precision)
+        x3 = _lib.WS_X3 if (w.precision == _lib.F32 and w.depth > 2 and w.l2r_wrel_hi[0]) else 0
+        ws_bytes = lib.lpgnn_predict_workspace_bytes(z, m, n, w.p, w.q, w.hids, w.depth, w.precision | x3)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         status = torch.empty(m + n, dtype=torch.uint8, device=dev)
         logits = torch.empty((m + n, 3), dtype=torch.float32, device=dev) if want_logits else None

@@ -31,12 +31,38 @@ def _check_graph(g):
 # --------------------------------------------------------------------------------------------------
 # inference path
 # --------------------------------------------------------------------------------------------------
+def split_cached(conv_cache, p):
+    """(hi, lo) bf16 split of an fp32 weight, cached per parameter version."""
+    key = ("split", id(p))
+    hit = conv_cache._c.get(key)
+    if hit is not None and hit[0] == (p._version, p.device):
+        return hit[1]
+    pair = ops.split_bf16(p.detach())
+    conv_cache._c[key] = ((p._version, p.device), pair)
+    return pair
+
+
+def use_x3(conv) -> bool:
+    """fp32 mode runs the hidden transforms as three bf16 tensor-core passes when the shape allows it."""
+    gc = conv.left2right
+    return gc.in_channels[0] % 64 == 0 and gc.in_channels[1] % 64 == 0 and gc.out_channels % 64 == 0 \
+        and getattr(conv, "fp32_tensor_cores", True)
+
+
 def _conv_hidden_infer(conv, left, right, csr, csc, relu):
     dt = left.dtype
     cast = conv._cache.get
     l2r, r2l = conv.left2right, conv.right2left
     agg_t = ops.spmm(csc, left)     # [n,H]  A^T . left
     agg_s = ops.spmm(csr, right)    # [m,H]  A   . right
+    if dt == torch.float32 and use_x3(conv):
+        sp = lambda p: split_cached(conv._cache, p)
+        left_p, right_p = ops.split_bf16(left), ops.split_bf16(right)
+        right_new = ops.node_transform_x3(ops.split_bf16(agg_t), sp(l2r.lin_rel.weight), right_p, sp(l2r.lin_root.weight),
+                                          l2r.lin_rel.bias.detach(), relu=relu)
+        left_new = ops.node_transform_x3(ops.split_bf16(agg_s), sp(r2l.lin_rel.weight), left_p, sp(r2l.lin_root.weight),
+                                         r2l.lin_rel.bias.detach(), relu=relu)
+        return left_new, right_new
     right_new = ops.node_transform(agg_t, cast(l2r.lin_rel.weight, dt), right, cast(l2r.lin_root.weight, dt),
                                    l2r.lin_rel.bias.detach(), relu=relu)
     left_new = ops.node_transform(agg_s, cast(r2l.lin_rel.weight, dt), left, cast(r2l.lin_root.weight, dt),

@@ -57,9 +57,59 @@ int node_transform_bf16(const void* A1, int K1, const void* W1, const void* A2, 
                         const float* bias, int M, int N, void* out, int out_f32, int relu, const float* head_w,
                         float* head_partial, int ksplit, cudaStream_t st);
 
+int gemm_tc_run(const void* const* A, const void* const* W, const int* K, int nseg, const float* bias, int M, int N,
+                void* out, int out_f32, int relu, const float* head_w, float* head_partial, int ksplit, cudaStream_t st);
+
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): the operand form of the fp32-accurate tensor-core transform
+__global__ void split_bf16_kernel(const float4* __restrict__ x, int64_t quads, uint2* __restrict__ hi, uint2* __restrict__ lo) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < quads; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x + i);
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
+    const __nv_bfloat16 h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+    const float r0 = v.x - __bfloat162float(h0), r1 = v.y - __bfloat162float(h1);
+    const float r2 = v.z - __bfloat162float(h2), r3 = v.w - __bfloat162float(h3);
+    __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+    hi[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    lo[i] = make_uint2(pack_bf16(r0, r1), pack_bf16(r2, r3));
+  }
+}
+
 }  // namespace lpgnn
 
 using namespace lpgnn;
+
+extern "C" int lpgnn_split_bf16(const float* x, int64_t count, void* hi, void* lo, lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(count >= 0 && count % 4 == 0, "split_bf16: count must be a multiple of 4");
+  if (count == 0) return LPGNN_OK;
+  LPGNN_REQUIRE(x && hi && lo && (uintptr_t)x % 16 == 0 && (uintptr_t)hi % 8 == 0 && (uintptr_t)lo % 8 == 0,
+                "split_bf16: null or misaligned pointer");
+  const int64_t quads = count / 4;
+  const int64_t want = (quads + 255) / 256, cap = (int64_t)sm_count() * 16;
+  split_bf16_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(x), quads, reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo));
+  LPGNN_LAUNCH_OK();
+  count_launches(1);
+  return LPGNN_OK;
+}
+
+// fp32-accurate node transform on the tensor cores: every fp32 operand arrives split into bf16 (hi, lo);
+// out = epi( sum over pairs of a_hi*w_hi + a_hi*w_lo + a_lo*w_hi + bias ), fp32 out.
+extern "C" int lpgnn_node_transform_x3(const void* A1_hi, const void* A1_lo, int32_t K1, const void* W1_hi,
+                                       const void* W1_lo, const void* A2_hi, const void* A2_lo, int32_t K2,
+                                       const void* W2_hi, const void* W2_lo, const float* bias, int32_t M, int32_t N,
+                                       float* out, int epilogue, lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(M >= 0 && N > 0 && K1 > 0 && K2 >= 0, "node_transform_x3: bad shape");
+  if (M == 0) return LPGNN_OK;
+  LPGNN_REQUIRE(A1_hi && A1_lo && W1_hi && W1_lo && out, "node_transform_x3: null pointer");
+  LPGNN_REQUIRE(K2 == 0 || (A2_hi && A2_lo && W2_hi && W2_lo), "node_transform_x3: K2=%d but operands are null", K2);
+  const void* A[6] = {A1_hi, A1_hi, A1_lo, A2_hi, A2_hi, A2_lo};
+  const void* W[6] = {W1_hi, W1_lo, W1_hi, W2_hi, W2_lo, W2_hi};
+  const int K[6] = {K1, K1, K1, K2, K2, K2};
+  return gemm_tc_run(A, W, K, K2 > 0 ? 6 : 3, bias, M, N, out, 1, (epilogue & LPGNN_EPI_RELU) ? 1 : 0, nullptr, nullptr, 1,
+                     (cudaStream_t)stream);
+}
 
 extern "C" int lpgnn_version(void) { return LPGNN_VERSION; }
 extern "C" const char* lpgnn_last_error(void) { return g_err; }

@@ -44,11 +44,20 @@ template <int BN, typename OutT> struct Cfg {
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 };
 
+// The reduction is a concatenation of up to kMaxSegs (A, W) operand pairs: 2 for a hidden GraphConv layer
+// (lin_rel on the aggregate, lin_root on the node's own features), 6 for its fp32-accurate form, where every fp32
+// operand is split into bf16 (hi, lo) and a*w ~ a_hi*w_hi + a_hi*w_lo + a_lo*w_hi accumulates in the same TMEM tile.
+constexpr int kMaxSegs = 6;
+struct Segs {
+  CUtensorMap a[kMaxSegs];
+  CUtensorMap w[kMaxSegs];
+  int kb_end[kMaxSegs];   // cumulative K-block count at the end of each segment
+  int count;
+};
+
 template <int BN, typename OutT>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
-               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2, int kblocks1,
-               int kblocks2, const float* __restrict__ bias, OutT* __restrict__ out, int M, int N,
+gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias, OutT* __restrict__ out, int M, int N,
                int relu, const float* __restrict__ head_w /*[3,N] or null*/,
                float* __restrict__ head_partial /*[N/BN][M][3] or null*/, int ksplit) {
   using C = Cfg<BN, OutT>;
@@ -74,13 +83,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   // slice s writes its partial tile to out + s*M*N (fp32), summed afterwards in a fixed order.
   const int num_out_tiles = num_m * num_n;
   const int num_tiles = num_out_tiles * ksplit;
-  const int kblocks_all = kblocks1 + kblocks2;
+  const int kblocks_all = segs.kb_end[segs.count - 1];
   const int kb_per = (kblocks_all + ksplit - 1) / ksplit;
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tensormap(&tmA1);
-    ptx::prefetch_tensormap(&tmW1);
-    if (kblocks2 > 0) { ptx::prefetch_tensormap(&tmA2); ptx::prefetch_tensormap(&tmW2); }
+    for (int i = 0; i < segs.count; ++i) { ptx::prefetch_tensormap(&segs.a[i]); ptx::prefetch_tensormap(&segs.w[i]); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
@@ -107,10 +114,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-          const bool first = kb < kblocks1;
-          const int kc = (first ? kb : kb - kblocks1) * BK;
-          ptx::tma_load_2d(smem_a + stage * C::kABytes, first ? &tmA1 : &tmA2, &full_bar[stage], kc, m_blk * BM);
-          ptx::tma_load_2d(smem_b + stage * C::kBBytes, first ? &tmW1 : &tmW2, &full_bar[stage], kc, n_blk * BN);
+          int sg = 0;
+          while (kb >= segs.kb_end[sg]) ++sg;
+          const int kc = (kb - (sg ? segs.kb_end[sg - 1] : 0)) * BK;
+          ptx::tma_load_2d(smem_a + stage * C::kABytes, &segs.a[sg], &full_bar[stage], kc, m_blk * BM);
+          ptx::tma_load_2d(smem_b + stage * C::kBBytes, &segs.w[sg], &full_bar[stage], kc, n_blk * BN);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -282,9 +290,8 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int bo
 }
 
 template <int BN, typename OutT>
-int launch(const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& a2, const CUtensorMap& w2, int kb1, int kb2,
-           const float* bias, void* out, int M, int N, int relu, const float* head_w, float* head_partial,
-           int ksplit, cudaStream_t st) {
+int launch(const Segs& segs, const float* bias, void* out, int M, int N, int relu, const float* head_w,
+           float* head_partial, int ksplit, cudaStream_t st) {
   using C = Cfg<BN, OutT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -294,9 +301,8 @@ int launch(const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& a2, 
   }
   const int tiles = ceil_div(M, BM) * (N / BN) * ksplit;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<BN, OutT><<<grid, kThreads, C::kSmemBytes, st>>>(a1, w1, a2, w2, kb1, kb2, bias,
-                                                                  reinterpret_cast<OutT*>(out), M, N, relu, head_w,
-                                                                  head_partial, ksplit);
+  gemm_tc_kernel<BN, OutT><<<grid, kThreads, C::kSmemBytes, st>>>(segs, bias, reinterpret_cast<OutT*>(out), M, N, relu,
+                                                                  head_w, head_partial, ksplit);
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;
@@ -304,38 +310,50 @@ int launch(const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& a2, 
 
 }  // namespace
 
+// out[M,N] = epi( sum_i A_i[M,K_i] * W_i[N,K_i]^T + bias ) over nseg <= 6 bf16 operand pairs.
+int gemm_tc_run(const void* const* A, const void* const* W, const int* K, int nseg, const float* bias, int M, int N,
+                void* out, int out_f32, int relu, const float* head_w, float* head_partial, int ksplit, cudaStream_t st) {
+  LPGNN_REQUIRE(nseg >= 1 && nseg <= kMaxSegs, "gemm_tc: %d operand pairs (max %d)", nseg, kMaxSegs);
+  LPGNN_REQUIRE(N % 64 == 0, "node_transform(bf16): N=%d must be a multiple of 64", N);
+  LPGNN_REQUIRE((uintptr_t)out % 16 == 0, "node_transform(bf16): out must be 16-byte aligned");
+  LPGNN_REQUIRE(out || (head_w && head_partial), "node_transform(bf16): no output requested");
+  LPGNN_REQUIRE(!head_w || (head_partial && !out_f32), "node_transform(bf16): fused head needs head_partial and bf16 mode");
+  const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
+  Segs segs;
+  int kb = 0;
+  for (int i = 0; i < nseg; ++i) {
+    LPGNN_REQUIRE(A[i] && W[i] && K[i] > 0 && K[i] % BK == 0, "node_transform(bf16): K=%d must be a positive multiple of 64",
+                  K[i]);
+    LPGNN_REQUIRE((uintptr_t)A[i] % 16 == 0 && (uintptr_t)W[i] % 16 == 0, "node_transform(bf16): operands must be 16-byte aligned");
+    if (int rc = make_map(&segs.a[i], A[i], M, K[i], BM)) return rc;
+    if (int rc = make_map(&segs.w[i], W[i], N, K[i], BN)) return rc;
+    kb += K[i] / BK;
+    segs.kb_end[i] = kb;
+  }
+  for (int i = nseg; i < kMaxSegs; ++i) { segs.a[i] = segs.a[0]; segs.w[i] = segs.w[0]; segs.kb_end[i] = kb; }
+  segs.count = nseg;
+  LPGNN_REQUIRE(ksplit >= 1 && (ksplit == 1 || (out_f32 && !bias && !relu && !head_w && ksplit <= kb)),
+                "node_transform(bf16): split-K needs fp32 partial outputs, no epilogue, and ksplit <= K/64");
+#define LPGNN_GO(BNV, T) return launch<BNV, T>(segs, bias, out, M, N, relu, head_w, head_partial, ksplit, st)
+  if (out_f32) {
+    if (BN == 256) LPGNN_GO(256, float);
+    if (BN == 128) LPGNN_GO(128, float);
+    LPGNN_GO(64, float);
+  }
+  if (BN == 256) LPGNN_GO(256, __nv_bfloat16);
+  if (BN == 128) LPGNN_GO(128, __nv_bfloat16);
+  LPGNN_GO(64, __nv_bfloat16);
+#undef LPGNN_GO
+}
+
 int node_transform_bf16(const void* A1, int K1, const void* W1, const void* A2, int K2, const void* W2,
                         const float* bias, int M, int N, void* out, int out_f32, int relu, const float* head_w,
                         float* head_partial, int ksplit, cudaStream_t st) {
-  LPGNN_REQUIRE(K1 > 0 && K1 % BK == 0 && K2 % BK == 0, "node_transform(bf16): K1=%d, K2=%d must be multiples of 64", K1, K2);
-  LPGNN_REQUIRE(N % 64 == 0, "node_transform(bf16): N=%d must be a multiple of 64", N);
-  LPGNN_REQUIRE((uintptr_t)A1 % 16 == 0 && (uintptr_t)W1 % 16 == 0 && (uintptr_t)A2 % 16 == 0 &&
-                    (uintptr_t)W2 % 16 == 0 && (uintptr_t)out % 16 == 0,
-                "node_transform(bf16): operands must be 16-byte aligned");
-  LPGNN_REQUIRE(out || (head_w && head_partial), "node_transform(bf16): no output requested");
-  LPGNN_REQUIRE(ksplit >= 1 && (ksplit == 1 || (out_f32 && !bias && !relu && !head_w && ksplit <= (K1 + K2) / BK)),
-                "node_transform(bf16): split-K needs fp32 partial outputs, no epilogue, and ksplit <= K/64");
-  LPGNN_REQUIRE(!head_w || (head_partial && !out_f32), "node_transform(bf16): fused head needs head_partial and bf16 mode");
-  const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
-  const bool two = A2 != nullptr && K2 > 0;
-  CUtensorMap a1, w1, a2, w2;
-  if (int rc = make_map(&a1, A1, M, K1, BM)) return rc;
-  if (int rc = make_map(&w1, W1, N, K1, BN)) return rc;
-  if (two) {
-    if (int rc = make_map(&a2, A2, M, K2, BM)) return rc;
-    if (int rc = make_map(&w2, W2, N, K2, BN)) return rc;
-  } else {
-    a2 = a1; w2 = w1;
-  }
-  const int kb1 = K1 / BK, kb2 = two ? K2 / BK : 0;
-  if (out_f32) {
-    if (BN == 256) return launch<256, float>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, ksplit, st);
-    if (BN == 128) return launch<128, float>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, ksplit, st);
-    return launch<64, float>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, ksplit, st);
-  }
-  if (BN == 256) return launch<256, __nv_bfloat16>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, ksplit, st);
-  if (BN == 128) return launch<128, __nv_bfloat16>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, ksplit, st);
-  return launch<64, __nv_bfloat16>(a1, w1, a2, w2, kb1, kb2, bias, out, M, N, relu, head_w, head_partial, ksplit, st);
+  const void* A[2] = {A1, A2};
+  const void* W[2] = {W1, W2};
+  const int K[2] = {K1, K2};
+  const int nseg = (A2 != nullptr && K2 > 0) ? 2 : 1;
+  return gemm_tc_run(A, W, K, nseg, bias, M, N, out, out_f32, relu, head_w, head_partial, ksplit, st);
 }
 
 }  // namespace lpgnn

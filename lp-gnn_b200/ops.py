@@ -124,6 +124,41 @@ def node_transform_head(a1, w1, a2, w2, bias, head_w, head_b, feas, relu=True, w
     return logits, out
 
 
+def split_bf16(x):
+    """fp32 -> (hi, lo) bf16 with ``hi + lo ~ x`` to ~2^-17 relative (operands of ``node_transform_x3``)."""
+    require_cuda(x)
+    x = _contig(x.float())
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().lpgnn_split_bf16(x.data_ptr(), x.numel(), hi.data_ptr(), lo.data_ptr(), stream_ptr())
+    check(rc, "lpgnn_split_bf16")
+    return hi, lo
+
+
+def node_transform_x3(a1, w1, a2=None, w2=None, bias=None, relu=False):
+    """fp32-accurate transform on the tensor cores: ``a*`` / ``w*`` are ``(hi, lo)`` bf16 pairs (``split_bf16``);
+    returns fp32 ``epi(a1 w1^T + a2 w2^T + bias)``."""
+    (a1h, a1l), (w1h, w1l) = a1, w1
+    require_cuda(a1h, a1l, w1h, w1l, bias)
+    M, K1 = a1h.shape
+    N = w1h.shape[0]
+    K2 = 0
+    a2h = a2l = w2h = w2l = None
+    if a2 is not None:
+        (a2h, a2l), (w2h, w2l) = a2, w2
+        K2 = a2h.shape[1]
+    if bias is not None:
+        bias = _contig(bias.float())
+    out = torch.empty((M, N), dtype=torch.float32, device=a1h.device)
+    with torch.cuda.device(a1h.device):
+        rc = _lib.load().lpgnn_node_transform_x3(a1h.data_ptr(), a1l.data_ptr(), K1, w1h.data_ptr(), w1l.data_ptr(), ptr(a2h),
+                                                 ptr(a2l), K2, ptr(w2h), ptr(w2l), ptr(bias), M, N, out.data_ptr(),
+                                                 EPI_RELU if relu else EPI_NONE, stream_ptr())
+    check(rc, "lpgnn_node_transform_x3")
+    return out
+
+
 def head_mask(h, w, b, feas, want_raw=False):
     """Linear(H,3) + add_knowledge in one pass (reference arch.py:190-191, 129-141).
     Returns ``(logits[rows,3] f32, raw[rows,3] f32 | None)``."""

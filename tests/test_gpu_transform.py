@@ -124,3 +124,26 @@ def test_transform_with_fused_head(cuda, M, N, K, want_out):
     if want_out:
         ref = ops.node_transform(a1, w1, a2, w2, b, relu=True)
         assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("M,N,K1,K2", [(1000, 1024, 1024, 1024), (129, 64, 64, 64), (5000, 128, 128, 0), (333, 512, 192, 64)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_transform_fp32_via_three_bf16_tensor_core_passes(cuda, M, N, K1, K2, relu):
+    """bf16x3: fp32 operands split into (hi, lo) bf16; error must sit at fp32 level, far below plain bf16."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K1)
+    a1 = torch.randn(M, K1, device=cuda, generator=g)
+    w1 = torch.randn(N, K1, device=cuda, generator=g) / K1 ** 0.5
+    a2 = torch.randn(M, K2, device=cuda, generator=g) if K2 else None
+    w2 = torch.randn(N, K2, device=cuda, generator=g) / K2 ** 0.5 if K2 else None
+    b = torch.randn(N, device=cuda, generator=g)
+    hi, lo = ops.split_bf16(a1)
+    assert float((hi.float() + lo.float() - a1).abs().max()) < 2 ** -16 * float(a1.abs().max())
+    y = ops.node_transform_x3(ops.split_bf16(a1), ops.split_bf16(w1), ops.split_bf16(a2) if K2 else None,
+                              ops.split_bf16(w2) if K2 else None, b, relu=relu)
+    e = _ref(a1, w1, a2, w2, b, relu)
+    err = float((y.double() - e).abs().max()) / max(1.0, float(e.abs().max()))
+    assert err < 3e-5, err
+    y_simt = ops.node_transform(a1, w1, a2, w2, b, relu=relu)
+    assert float((y - y_simt).abs().max()) < 2e-4 * max(1.0, float(e.abs().max()))
