@@ -591,7 +591,7 @@ def main():
     ap.add_argument("--sweep-distinct", type=int, default=96, help="C5: distinct LPs materialised (cycled)")
     ap.add_argument("--sweep-hids", type=int, default=1024)
     ap.add_argument("--sweep-pack", type=int, default=1, help="C5 e2e arm: pack LPs block-diagonally (1) or one call per LP (0)")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp32_tc"])
     ap.add_argument("--structure", default="staircase", choices=["staircase", "uniform"])
     ap.add_argument("--kernel-reps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

@@ -161,16 +161,17 @@ LPGNN_API int lpgnn_node_transform(const void* A1, int32_t K1, const void* W1,
                          void* out, int dtype, int out_dtype, int epilogue, lpgnn_stream_t stream);
 
 /* (a3, fp32 parity mode on the tensor cores) The same transform with fp32 accuracy from bf16 tensor-core
- * products: every fp32 operand x is given as (hi, lo) = (bf16(x), bf16(x - hi)) (lpgnn_split_bf16) and
- * a*w is accumulated as a_hi*w_hi + a_hi*w_lo + a_lo*w_hi in the same fp32 TMEM tile (the dropped term is
- * ~2^-18 relative), i.e. three tensor-core passes instead of a CUDA-core SGEMM.  out is f32. */
-LPGNN_API int lpgnn_split_bf16(const float* x, int64_t count, void* hi, void* lo, lpgnn_stream_t stream);
-LPGNN_API int lpgnn_node_transform_x3(const void* A1_hi, const void* A1_lo, int32_t K1,
-                            const void* W1_hi, const void* W1_lo,
-                            const void* A2_hi, const void* A2_lo, int32_t K2,
-                            const void* W2_hi, const void* W2_lo,
-                            const float* bias, int32_t M, int32_t N, float* out, int epilogue,
-                            lpgnn_stream_t stream);
+ * products: every fp32 operand x is given as `parts` bf16 tensors p0 = bf16(x), p1 = bf16(x - p0)
+ * [, p2 = bf16(x - p0 - p1)] (lpgnn_split_bf16) and the significant cross products are accumulated in the
+ * same fp32 TMEM tile: parts = 2 -> 3 passes (a0w0 + a0w1 + a1w0, ~2^-17 relative per product);
+ * parts = 3 -> 6 passes (+ a0w2 + a2w0 + a1w1, ~2^-24: fp32 level; the mode that meets the 1e-4 logit bar).
+ * A1/W1/A2/W2 are host arrays of `parts` device pointers; out is f32. */
+LPGNN_API int lpgnn_split_bf16(const float* x, int64_t count, int parts, void* const* out_parts,
+                     lpgnn_stream_t stream);
+LPGNN_API int lpgnn_node_transform_split(int parts, const void* const* A1, int32_t K1, const void* const* W1,
+                               const void* const* A2, int32_t K2, const void* const* W2,
+                               const float* bias, int32_t M, int32_t N, float* out, int epilogue,
+                               lpgnn_stream_t stream);
 
 /* (a3+a4, inference) The LAST hidden transform fused with the basis-status head (reference
  * arch.py:185-190): the epilogue also forms, per row, the three dot products of the ReLU'd fp32
@@ -256,17 +257,14 @@ typedef struct lpgnn_gcn_fc_weights {
   const float* r2l_b[LPGNN_MAX_HIDDEN_LAYERS];
   /* heads, fp32: lin_left (constraints) / lin_right (variables): weight [3,hids], bias [3] */
   const float *head_left_w, *head_left_b, *head_right_w, *head_right_b;
-  /* fp32 mode on the tensor cores (optional): bf16 (hi, lo) splits of the hidden-layer weights
-   * (lpgnn_split_bf16).  When l2r_wrel_hi[0] != NULL and hids % 64 == 0 the hidden transforms run as
-   * lpgnn_node_transform_x3; otherwise the CUDA-core fp32 kernel is used. */
-  const void* l2r_wrel_hi[LPGNN_MAX_HIDDEN_LAYERS];
-  const void* l2r_wrel_lo[LPGNN_MAX_HIDDEN_LAYERS];
-  const void* l2r_wroot_hi[LPGNN_MAX_HIDDEN_LAYERS];
-  const void* l2r_wroot_lo[LPGNN_MAX_HIDDEN_LAYERS];
-  const void* r2l_wrel_hi[LPGNN_MAX_HIDDEN_LAYERS];
-  const void* r2l_wrel_lo[LPGNN_MAX_HIDDEN_LAYERS];
-  const void* r2l_wroot_hi[LPGNN_MAX_HIDDEN_LAYERS];
-  const void* r2l_wroot_lo[LPGNN_MAX_HIDDEN_LAYERS];
+  /* fp32 mode on the tensor cores (optional): 3-part bf16 splits of the hidden-layer weights
+   * (lpgnn_split_bf16, parts = 3), indexed [layer][part].  When l2r_wrel_parts[0][0] != NULL and
+   * hids % 64 == 0 the hidden transforms run as lpgnn_node_transform_split(parts = 3); otherwise the
+   * CUDA-core fp32 kernel is used. */
+  const void* l2r_wrel_parts[LPGNN_MAX_HIDDEN_LAYERS][3];
+  const void* l2r_wroot_parts[LPGNN_MAX_HIDDEN_LAYERS][3];
+  const void* r2l_wrel_parts[LPGNN_MAX_HIDDEN_LAYERS][3];
+  const void* r2l_wroot_parts[LPGNN_MAX_HIDDEN_LAYERS][3];
 } lpgnn_gcn_fc_weights;
 
 /* precision: LPGNN_F32, LPGNN_BF16, or LPGNN_F32 | LPGNN_WS_X3 to reserve the split buffers of the fp32

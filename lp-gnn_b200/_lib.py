@@ -32,8 +32,8 @@ class GcnFcWeights(C.Structure):
                                      "c1_l2r_wcat", "c1_r2l_wcat")]
                 + [(k, _p * MAX_HIDDEN_LAYERS) for k in ("l2r_wrel", "l2r_wroot", "l2r_b", "r2l_wrel", "r2l_wroot", "r2l_b")]
                 + [(k, _p) for k in ("head_left_w", "head_left_b", "head_right_w", "head_right_b")]
-                + [(k, _p * MAX_HIDDEN_LAYERS) for k in ("l2r_wrel_hi", "l2r_wrel_lo", "l2r_wroot_hi", "l2r_wroot_lo",
-                                                         "r2l_wrel_hi", "r2l_wrel_lo", "r2l_wroot_hi", "r2l_wroot_lo")])
+                + [(k, (_p * 3) * MAX_HIDDEN_LAYERS) for k in ("l2r_wrel_parts", "l2r_wroot_parts", "r2l_wrel_parts",
+                                                               "r2l_wroot_parts")])
 
 
 # name -> (restype, argtypes); must list every symbol include/lpgnn.h declares
@@ -51,8 +51,8 @@ SIGNATURES = {
     "lpgnn_gather_cat": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p]),
     "lpgnn_conv_in_fused": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p, _i32, _p, _int, _int, _p, _p]),
     "lpgnn_node_transform": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _int, _int, _p]),
-    "lpgnn_split_bf16": (_int, [_p, _i64, _p, _p, _p]),
-    "lpgnn_node_transform_x3": (_int, [_p, _p, _i32, _p, _p, _p, _p, _i32, _p, _p, _p, _i32, _i32, _p, _int, _p]),
+    "lpgnn_split_bf16": (_int, [_p, _i64, _int, _p, _p]),
+    "lpgnn_node_transform_split": (_int, [_int, _p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _p]),
     "lpgnn_node_transform_head_parts": (_i32, [_i32]),
     "lpgnn_node_transform_head": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _p, _p, _p]),
     "lpgnn_head_finish": (_int, [_p, _i32, _i32, _p, _p, _i32, _p, _p]),

@@ -131,15 +131,22 @@ class GCN_FC(GCNBase):
         self.lin_right = nn.Linear(hids, 3)
         self.dp = dp
         self.hids = hids
-        self.precision = "fp32"
+        self.set_precision("fp32")
 
     # -- precision switches ----------------------------------------------------------------
     def set_precision(self, precision: str):
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
-        if precision == "bf16" and self.hids % 64 != 0:
-            raise ValueError("bf16 mode needs hids to be a multiple of 64 (tensor-core tile)")
+        """'fp32'    strict-parity mode: fp32 CUDA-core transforms (logits within 1e-4 of the reference);
+        'fp32_tc' fp32 storage, hidden transforms as six bf16 tensor-core passes over 3-part splits (~4x faster;
+                  relative Frobenius error ~1e-5, worst logit entry ~3e-4 of the row norm at C2 size because the
+                  tensor core's fp32 accumulation truncates);
+        'bf16'    bf16 storage and single-pass tensor-core transforms (within 2e-2)."""
+        if precision not in ("fp32", "fp32_tc", "bf16"):
+            raise ValueError("precision must be 'fp32', 'fp32_tc' or 'bf16'")
+        if precision != "fp32" and self.hids % 64 != 0:
+            raise ValueError("tensor-core modes need hids to be a multiple of 64 (tensor-core tile)")
         self.precision = precision
+        for conv in self.layers:
+            conv.fp32_tensor_cores = precision == "fp32_tc"
         return self
 
     def half(self):       # reference `--fp16`: model.half() (val.py:269, pred_basis.py:146)
@@ -200,10 +207,10 @@ class GCN_FC(GCNBase):
                 getattr(w, f"{tag}_b")[i] = f32(gc.lin_rel.bias)
                 if not bf16 and use_x3(conv):
                     for nm, par in (("wrel", gc.lin_rel.weight), ("wroot", gc.lin_root.weight)):
-                        hi, lo = split_cached(conv._cache, par)
-                        keep.extend((hi, lo))
-                        getattr(w, f"{tag}_{nm}_hi")[i] = hi.data_ptr()
-                        getattr(w, f"{tag}_{nm}_lo")[i] = lo.data_ptr()
+                        parts = split_cached(conv._cache, par)
+                        keep.extend(parts)
+                        for k, t in enumerate(parts):
+                            getattr(w, f"{tag}_{nm}_parts")[i][k] = t.data_ptr()
         w.head_left_w, w.head_left_b = f32(self.lin_left.weight), f32(self.lin_left.bias)
         w.head_right_w, w.head_right_b = f32(self.lin_right.weight), f32(self.lin_right.bias)
         self._native_cache = (ver, w, keep)
@@ -224,7 +231,7 @@ class GCN_FC(GCNBase):
         w = self._native_weights()
         dev = x_s.device
         z = int(row.shape[0])
-        x3 = _lib.WS_X3 if (w.precision == _lib.F32 and w.depth > 2 and w.l2r_wrel_hi[0]) else 0
+        x3 = _lib.WS_X3 if (w.precision == _lib.F32 and w.depth > 2 and w.l2r_wrel_parts[0][0]) else 0
         ws_bytes = lib.lpgnn_predict_workspace_bytes(z, m, n, w.p, w.q, w.hids, w.depth, w.precision | x3)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         status = torch.empty(m + n, dtype=torch.uint8, device=dev)
@@ -253,7 +260,7 @@ class GCN_FC(GCNBase):
         w = self._native_weights()
         dev = x_s.device
         z = int(row.shape[0])
-        x3 = _lib.WS_X3 if (w.precision == _lib.F32 and w.depth > 2 and w.l2r_wrel_hi[0]) else 0
+        x3 = _lib.WS_X3 if (w.precision == _lib.F32 and w.depth > 2 and w.l2r_wrel_parts[0][0]) else 0
         ws_bytes = lib.lpgnn_predict_workspace_bytes(z, m, n, w.p, w.q, w.hids, w.depth, w.precision | x3)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         status = torch.empty(m + n, dtype=torch.uint8, device=dev)

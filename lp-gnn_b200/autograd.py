@@ -32,21 +32,22 @@ def _check_graph(g):
 # inference path
 # --------------------------------------------------------------------------------------------------
 def split_cached(conv_cache, p):
-    """(hi, lo) bf16 split of an fp32 weight, cached per parameter version."""
+    """3-part bf16 split of an fp32 weight, cached per parameter version."""
     key = ("split", id(p))
     hit = conv_cache._c.get(key)
     if hit is not None and hit[0] == (p._version, p.device):
         return hit[1]
-    pair = ops.split_bf16(p.detach())
+    pair = ops.split_bf16(p.detach(), parts=3)
     conv_cache._c[key] = ((p._version, p.device), pair)
     return pair
 
 
 def use_x3(conv) -> bool:
-    """fp32 mode runs the hidden transforms as three bf16 tensor-core passes when the shape allows it."""
+    """'fp32_tc' mode: hidden transforms as six bf16 tensor-core passes over 3-part splits (products exact to
+    ~2^-24; the result is limited by the tensor core's truncating fp32 accumulation) when the shape allows it."""
     gc = conv.left2right
     return gc.in_channels[0] % 64 == 0 and gc.in_channels[1] % 64 == 0 and gc.out_channels % 64 == 0 \
-        and getattr(conv, "fp32_tensor_cores", True)
+        and getattr(conv, "fp32_tensor_cores", False)
 
 
 def _conv_hidden_infer(conv, left, right, csr, csc, relu):
@@ -58,10 +59,10 @@ def _conv_hidden_infer(conv, left, right, csr, csc, relu):
     if dt == torch.float32 and use_x3(conv):
         sp = lambda p: split_cached(conv._cache, p)
         left_p, right_p = ops.split_bf16(left), ops.split_bf16(right)
-        right_new = ops.node_transform_x3(ops.split_bf16(agg_t), sp(l2r.lin_rel.weight), right_p, sp(l2r.lin_root.weight),
-                                          l2r.lin_rel.bias.detach(), relu=relu)
-        left_new = ops.node_transform_x3(ops.split_bf16(agg_s), sp(r2l.lin_rel.weight), left_p, sp(r2l.lin_root.weight),
-                                         r2l.lin_rel.bias.detach(), relu=relu)
+        right_new = ops.node_transform_split(ops.split_bf16(agg_t), sp(l2r.lin_rel.weight), right_p,
+                                             sp(l2r.lin_root.weight), l2r.lin_rel.bias.detach(), relu=relu)
+        left_new = ops.node_transform_split(ops.split_bf16(agg_s), sp(r2l.lin_rel.weight), left_p,
+                                            sp(r2l.lin_root.weight), r2l.lin_rel.bias.detach(), relu=relu)
         return left_new, right_new
     right_new = ops.node_transform(agg_t, cast(l2r.lin_rel.weight, dt), right, cast(l2r.lin_root.weight, dt),
                                    l2r.lin_rel.bias.detach(), relu=relu)

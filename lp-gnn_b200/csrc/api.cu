@@ -60,17 +60,23 @@ int node_transform_bf16(const void* A1, int K1, const void* W1, const void* A2, 
 int gemm_tc_run(const void* const* A, const void* const* W, const int* K, int nseg, const float* bias, int M, int N,
                 void* out, int out_f32, int relu, const float* head_w, float* head_partial, int ksplit, cudaStream_t st);
 
-// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): the operand form of the fp32-accurate tensor-core transform
-__global__ void split_bf16_kernel(const float4* __restrict__ x, int64_t quads, uint2* __restrict__ hi, uint2* __restrict__ lo) {
+// x = p0 + p1 (+ p2) with p0 = bf16(x), p1 = bf16(x - p0), p2 = bf16(x - p0 - p1): the operand form of the
+// fp32-accurate tensor-core transform (2 parts: ~2^-17 relative, 3 parts: ~2^-25)
+template <int PARTS>
+__global__ void split_bf16_kernel(const float4* __restrict__ x, int64_t quads, uint2* __restrict__ p0,
+                                  uint2* __restrict__ p1, uint2* __restrict__ p2) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < quads; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 v = __ldg(x + i);
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
-    const __nv_bfloat16 h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
-    const float r0 = v.x - __bfloat162float(h0), r1 = v.y - __bfloat162float(h1);
-    const float r2 = v.z - __bfloat162float(h2), r3 = v.w - __bfloat162float(h3);
-    __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
-    hi[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
-    lo[i] = make_uint2(pack_bf16(r0, r1), pack_bf16(r2, r3));
+    float r[4] = {v.x, v.y, v.z, v.w};
+    uint2* outs[3] = {p0, p1, p2};
+#pragma unroll
+    for (int part = 0; part < PARTS; ++part) {
+      __nv_bfloat16 h[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { h[k] = __float2bfloat16_rn(r[k]); r[k] -= __bfloat162float(h[k]); }
+      __nv_bfloat162 a = __halves2bfloat162(h[0], h[1]), b = __halves2bfloat162(h[2], h[3]);
+      outs[part][i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    }
   }
 }
 
@@ -78,36 +84,44 @@ __global__ void split_bf16_kernel(const float4* __restrict__ x, int64_t quads, u
 
 using namespace lpgnn;
 
-extern "C" int lpgnn_split_bf16(const float* x, int64_t count, void* hi, void* lo, lpgnn_stream_t stream) {
+extern "C" int lpgnn_split_bf16(const float* x, int64_t count, int parts, void* const* out_parts, lpgnn_stream_t stream) {
   if (int rc = check_device()) return rc;
-  LPGNN_REQUIRE(count >= 0 && count % 4 == 0, "split_bf16: count must be a multiple of 4");
+  LPGNN_REQUIRE(count >= 0 && count % 4 == 0 && (parts == 2 || parts == 3), "split_bf16: count %% 4 != 0 or parts not in {2,3}");
   if (count == 0) return LPGNN_OK;
-  LPGNN_REQUIRE(x && hi && lo && (uintptr_t)x % 16 == 0 && (uintptr_t)hi % 8 == 0 && (uintptr_t)lo % 8 == 0,
-                "split_bf16: null or misaligned pointer");
+  LPGNN_REQUIRE(x && out_parts && (uintptr_t)x % 16 == 0, "split_bf16: null or misaligned pointer");
+  for (int i = 0; i < parts; ++i)
+    LPGNN_REQUIRE(out_parts[i] && (uintptr_t)out_parts[i] % 8 == 0, "split_bf16: null or misaligned output %d", i);
   const int64_t quads = count / 4;
   const int64_t want = (quads + 255) / 256, cap = (int64_t)sm_count() * 16;
-  split_bf16_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float4*>(x), quads, reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo));
+  const int grid = (int)(want < cap ? want : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint2 *p0 = reinterpret_cast<uint2*>(out_parts[0]), *p1 = reinterpret_cast<uint2*>(out_parts[1]);
+  if (parts == 2) split_bf16_kernel<2><<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(x), quads, p0, p1, nullptr);
+  else split_bf16_kernel<3><<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(x), quads, p0, p1,
+                                                  reinterpret_cast<uint2*>(out_parts[2]));
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;
 }
 
-// fp32-accurate node transform on the tensor cores: every fp32 operand arrives split into bf16 (hi, lo);
-// out = epi( sum over pairs of a_hi*w_hi + a_hi*w_lo + a_lo*w_hi + bias ), fp32 out.
-extern "C" int lpgnn_node_transform_x3(const void* A1_hi, const void* A1_lo, int32_t K1, const void* W1_hi,
-                                       const void* W1_lo, const void* A2_hi, const void* A2_lo, int32_t K2,
-                                       const void* W2_hi, const void* W2_lo, const float* bias, int32_t M, int32_t N,
-                                       float* out, int epilogue, lpgnn_stream_t stream) {
+// fp32-accurate node transform on the tensor cores: every fp32 operand arrives split into `parts` bf16 tensors.
+//   parts = 2: a*w ~ a0*w0 + a0*w1 + a1*w0                                   (3 passes, ~2^-17 relative)
+//   parts = 3: a*w ~ a0*w0 + a0*w1 + a1*w0 + a0*w2 + a2*w0 + a1*w1           (6 passes, ~2^-24 relative)
+extern "C" int lpgnn_node_transform_split(int parts, const void* const* A1, int32_t K1, const void* const* W1,
+                                          const void* const* A2, int32_t K2, const void* const* W2,
+                                          const float* bias, int32_t M, int32_t N, float* out, int epilogue,
+                                          lpgnn_stream_t stream) {
   if (int rc = check_device()) return rc;
-  LPGNN_REQUIRE(M >= 0 && N > 0 && K1 > 0 && K2 >= 0, "node_transform_x3: bad shape");
+  LPGNN_REQUIRE((parts == 2 || parts == 3) && M >= 0 && N > 0 && K1 > 0 && K2 >= 0, "node_transform_split: bad arguments");
   if (M == 0) return LPGNN_OK;
-  LPGNN_REQUIRE(A1_hi && A1_lo && W1_hi && W1_lo && out, "node_transform_x3: null pointer");
-  LPGNN_REQUIRE(K2 == 0 || (A2_hi && A2_lo && W2_hi && W2_lo), "node_transform_x3: K2=%d but operands are null", K2);
-  const void* A[6] = {A1_hi, A1_hi, A1_lo, A2_hi, A2_hi, A2_lo};
-  const void* W[6] = {W1_hi, W1_lo, W1_hi, W2_hi, W2_lo, W2_hi};
-  const int K[6] = {K1, K1, K1, K2, K2, K2};
-  return gemm_tc_run(A, W, K, K2 > 0 ? 6 : 3, bias, M, N, out, 1, (epilogue & LPGNN_EPI_RELU) ? 1 : 0, nullptr, nullptr, 1,
+  LPGNN_REQUIRE(A1 && W1 && out && (K2 == 0 || (A2 && W2)), "node_transform_split: null pointer");
+  static const int pa[6] = {0, 0, 1, 0, 2, 1}, pw[6] = {0, 1, 0, 2, 0, 1};
+  const int nprod = parts == 2 ? 3 : 6;
+  const void* A[12]; const void* W[12]; int K[12];
+  int n = 0;
+  for (int i = 0; i < nprod; ++i, ++n) { A[n] = A1[pa[i]]; W[n] = W1[pw[i]]; K[n] = K1; }
+  if (K2 > 0) for (int i = 0; i < nprod; ++i, ++n) { A[n] = A2[pa[i]]; W[n] = W2[pw[i]]; K[n] = K2; }
+  return gemm_tc_run(A, W, K, n, bias, M, N, out, 1, (epilogue & LPGNN_EPI_RELU) ? 1 : 0, nullptr, nullptr, 1,
                      (cudaStream_t)stream);
 }
 

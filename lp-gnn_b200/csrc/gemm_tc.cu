@@ -45,9 +45,9 @@ template <int BN, typename OutT> struct Cfg {
 };
 
 // The reduction is a concatenation of up to kMaxSegs (A, W) operand pairs: 2 for a hidden GraphConv layer
-// (lin_rel on the aggregate, lin_root on the node's own features), 6 for its fp32-accurate form, where every fp32
-// operand is split into bf16 (hi, lo) and a*w ~ a_hi*w_hi + a_hi*w_lo + a_lo*w_hi accumulates in the same TMEM tile.
-constexpr int kMaxSegs = 6;
+// (lin_rel on the aggregate, lin_root on the node's own features), 6 or 12 for its fp32-accurate forms, where every
+// fp32 operand is split into 2 or 3 bf16 parts and the significant cross products accumulate in the same TMEM tile.
+constexpr int kMaxSegs = 12;
 struct Segs {
   CUtensorMap a[kMaxSegs];
   CUtensorMap w[kMaxSegs];
@@ -310,7 +310,7 @@ int launch(const Segs& segs, const float* bias, void* out, int M, int N, int rel
 
 }  // namespace
 
-// out[M,N] = epi( sum_i A_i[M,K_i] * W_i[N,K_i]^T + bias ) over nseg <= 6 bf16 operand pairs.
+// out[M,N] = epi( sum_i A_i[M,K_i] * W_i[N,K_i]^T + bias ) over nseg <= 12 bf16 operand pairs.
 int gemm_tc_run(const void* const* A, const void* const* W, const int* K, int nseg, const float* bias, int M, int N,
                 void* out, int out_f32, int relu, const float* head_w, float* head_partial, int ksplit, cudaStream_t st) {
   LPGNN_REQUIRE(nseg >= 1 && nseg <= kMaxSegs, "gemm_tc: %d operand pairs (max %d)", nseg, kMaxSegs);

@@ -37,7 +37,7 @@ struct Buffers {
   void *zb_s, *zb_t;         // bf16 [m,64], [n,64] (bf16 mode)
   void *act[2][2];           // ping-pong activations: act[i][0] = left [m,H], act[i][1] = right [n,H]
   void *agg_s, *agg_t;       // [m,H], [n,H]
-  void *sp[4][2];            // fp32 tensor-core mode: (hi, lo) bf16 splits of left, right, agg_s, agg_t
+  void *sp[4][3];            // fp32 tensor-core mode: 3-part bf16 splits of left, right, agg_s, agg_t
   float *part_s, *part_t;    // fused-head partials
   float *logit_s, *logit_t;  // [m,3], [n,3]
   void* sel_ws; size_t sel_ws_bytes;
@@ -76,7 +76,7 @@ size_t carve(Bump& b, Buffers& B, int64_t z, int32_t m, int32_t n, int32_t p, in
     B.agg_s = B.agg_t = nullptr;
   }
   for (int i = 0; i < 4; ++i)
-    for (int j = 0; j < 2; ++j)
+    for (int j = 0; j < 3; ++j)
       B.sp[i][j] = (x3 && depth > 2) ? b.take<char>((size_t)((i & 1) ? n : m) * H * 2) : nullptr;
   const int nparts = lpgnn_node_transform_head_parts(H);
   B.part_s = b.take<float>((size_t)nparts * m * 3); B.part_t = b.take<float>((size_t)nparts * n * 3);
@@ -116,7 +116,7 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
   const int bf16 = w->precision == LPGNN_BF16;
   LPGNN_REQUIRE(depth >= 2 && depth - 2 <= LPGNN_MAX_HIDDEN_LAYERS, "predict_basis: depth %d unsupported", depth);
   LPGNN_REQUIRE(!bf16 || H % 64 == 0, "predict_basis: bf16 mode needs hids %% 64 == 0");
-  const int x3 = !bf16 && depth > 2 && H % 64 == 0 && w->l2r_wrel_hi[0] != nullptr;
+  const int x3 = !bf16 && depth > 2 && H % 64 == 0 && w->l2r_wrel_parts[0][0] != nullptr;
   const size_t need = lpgnn_predict_workspace_bytes(nnz, m, n, p, q, H, depth, w->precision | (x3 ? LPGNN_WS_X3 : 0));
   if (workspace_bytes < need) { set_error("predict_basis: workspace %zu < required %zu", workspace_bytes, need); return LPGNN_EWORKSPACE; }
   LPGNN_REQUIRE((uintptr_t)workspace % 256 == 0, "predict_basis: workspace must be 256-byte aligned");
@@ -164,19 +164,17 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
       LPGNN_TRY(lpgnn_head_finish(B.part_t, nparts, n, w->head_right_b, x_t, q, B.logit_t, stream));
       LPGNN_TRY(lpgnn_head_finish(B.part_s, nparts, m, w->head_left_b, x_s, p, B.logit_s, stream));
       head_done = true;
-    } else if (x3) {  // fp32 accuracy from three bf16 tensor-core passes
+    } else if (x3) {  // fp32 accuracy from six bf16 tensor-core passes over 3-part splits
       void *nl = B.act[cur ^ 1][0], *nr = B.act[cur ^ 1][1];
       const int64_t cm = (int64_t)m * H, cn = (int64_t)n * H;
-      LPGNN_TRY(lpgnn_split_bf16((const float*)left, cm, B.sp[0][0], B.sp[0][1], stream));
-      LPGNN_TRY(lpgnn_split_bf16((const float*)right, cn, B.sp[1][0], B.sp[1][1], stream));
-      LPGNN_TRY(lpgnn_split_bf16((const float*)B.agg_s, cm, B.sp[2][0], B.sp[2][1], stream));
-      LPGNN_TRY(lpgnn_split_bf16((const float*)B.agg_t, cn, B.sp[3][0], B.sp[3][1], stream));
-      LPGNN_TRY(lpgnn_node_transform_x3(B.sp[3][0], B.sp[3][1], H, w->l2r_wrel_hi[li], w->l2r_wrel_lo[li], B.sp[1][0],
-                                        B.sp[1][1], H, w->l2r_wroot_hi[li], w->l2r_wroot_lo[li], w->l2r_b[li], n, H,
-                                        (float*)nr, LPGNN_EPI_RELU, stream));
-      LPGNN_TRY(lpgnn_node_transform_x3(B.sp[2][0], B.sp[2][1], H, w->r2l_wrel_hi[li], w->r2l_wrel_lo[li], B.sp[0][0],
-                                        B.sp[0][1], H, w->r2l_wroot_hi[li], w->r2l_wroot_lo[li], w->r2l_b[li], m, H,
-                                        (float*)nl, LPGNN_EPI_RELU, stream));
+      LPGNN_TRY(lpgnn_split_bf16((const float*)left, cm, 3, B.sp[0], stream));
+      LPGNN_TRY(lpgnn_split_bf16((const float*)right, cn, 3, B.sp[1], stream));
+      LPGNN_TRY(lpgnn_split_bf16((const float*)B.agg_s, cm, 3, B.sp[2], stream));
+      LPGNN_TRY(lpgnn_split_bf16((const float*)B.agg_t, cn, 3, B.sp[3], stream));
+      LPGNN_TRY(lpgnn_node_transform_split(3, B.sp[3], H, w->l2r_wrel_parts[li], B.sp[1], H, w->l2r_wroot_parts[li],
+                                           w->l2r_b[li], n, H, (float*)nr, LPGNN_EPI_RELU, stream));
+      LPGNN_TRY(lpgnn_node_transform_split(3, B.sp[2], H, w->r2l_wrel_parts[li], B.sp[0], H, w->r2l_wroot_parts[li],
+                                           w->r2l_b[li], m, H, (float*)nl, LPGNN_EPI_RELU, stream));
       left = nl; right = nr; cur ^= 1;
     } else {
       void *nl = B.act[cur ^ 1][0], *nr = B.act[cur ^ 1][1];

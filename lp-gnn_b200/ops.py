@@ -124,38 +124,40 @@ def node_transform_head(a1, w1, a2, w2, bias, head_w, head_b, feas, relu=True, w
     return logits, out
 
 
-def split_bf16(x):
-    """fp32 -> (hi, lo) bf16 with ``hi + lo ~ x`` to ~2^-17 relative (operands of ``node_transform_x3``)."""
+def _ptr_array(tensors):
+    import ctypes as C
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def split_bf16(x, parts=3):
+    """fp32 -> ``parts`` bf16 tensors whose sum reproduces x to ~2^-17 (parts=2) / ~2^-25 (parts=3) relative
+    (operands of ``node_transform_split``)."""
     require_cuda(x)
     x = _contig(x.float())
-    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    outs = tuple(torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) for _ in range(parts))
     with torch.cuda.device(x.device):
-        rc = _lib.load().lpgnn_split_bf16(x.data_ptr(), x.numel(), hi.data_ptr(), lo.data_ptr(), stream_ptr())
+        rc = _lib.load().lpgnn_split_bf16(x.data_ptr(), x.numel(), parts, _ptr_array(outs), stream_ptr())
     check(rc, "lpgnn_split_bf16")
-    return hi, lo
+    return outs
 
 
-def node_transform_x3(a1, w1, a2=None, w2=None, bias=None, relu=False):
-    """fp32-accurate transform on the tensor cores: ``a*`` / ``w*`` are ``(hi, lo)`` bf16 pairs (``split_bf16``);
+def node_transform_split(a1, w1, a2=None, w2=None, bias=None, relu=False):
+    """fp32-accurate transform on the tensor cores: ``a*`` / ``w*`` are tuples of bf16 parts (``split_bf16``);
     returns fp32 ``epi(a1 w1^T + a2 w2^T + bias)``."""
-    (a1h, a1l), (w1h, w1l) = a1, w1
-    require_cuda(a1h, a1l, w1h, w1l, bias)
-    M, K1 = a1h.shape
-    N = w1h.shape[0]
-    K2 = 0
-    a2h = a2l = w2h = w2l = None
-    if a2 is not None:
-        (a2h, a2l), (w2h, w2l) = a2, w2
-        K2 = a2h.shape[1]
+    parts = len(a1)
+    require_cuda(*a1, *w1, bias)
+    M, K1 = a1[0].shape
+    N = w1[0].shape[0]
+    K2 = a2[0].shape[1] if a2 is not None else 0
     if bias is not None:
         bias = _contig(bias.float())
-    out = torch.empty((M, N), dtype=torch.float32, device=a1h.device)
-    with torch.cuda.device(a1h.device):
-        rc = _lib.load().lpgnn_node_transform_x3(a1h.data_ptr(), a1l.data_ptr(), K1, w1h.data_ptr(), w1l.data_ptr(), ptr(a2h),
-                                                 ptr(a2l), K2, ptr(w2h), ptr(w2l), ptr(bias), M, N, out.data_ptr(),
-                                                 EPI_RELU if relu else EPI_NONE, stream_ptr())
-    check(rc, "lpgnn_node_transform_x3")
+    out = torch.empty((M, N), dtype=torch.float32, device=a1[0].device)
+    with torch.cuda.device(a1[0].device):
+        rc = _lib.load().lpgnn_node_transform_split(parts, _ptr_array(a1), K1, _ptr_array(w1),
+                                                    _ptr_array(a2) if a2 is not None else None, K2,
+                                                    _ptr_array(w2) if w2 is not None else None, ptr(bias), M, N,
+                                                    out.data_ptr(), EPI_RELU if relu else EPI_NONE, stream_ptr())
+    check(rc, "lpgnn_node_transform_split")
     return out
 
 

@@ -151,7 +151,7 @@ _step_counter = [0]
 
 
 def gcn_fc_train(model, x_s, x_t, csr, csc):
-    dt = torch.bfloat16 if model.precision == "bf16" else torch.float32
+    dt = torch.bfloat16 if model.precision == "bf16" else torch.float32      # fp32 / fp32_tc train in fp32
     _step_counter[0] += 1
     cfg = dict(dtype=dt, dp=float(model.dp), training=bool(model.training), n_hidden=len(model.layers),
                seed=(int(torch.initial_seed()) * 1_000_003 + _step_counter[0] * 7919) & (2 ** 62 - 1))

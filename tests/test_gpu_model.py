@@ -92,7 +92,8 @@ def test_state_dict_keys_and_checkpoint_roundtrip(cuda, tmp_path):
 
 
 @pytest.mark.parametrize("hids,depth,precision", [(64, 2, "fp32"), (128, 3, "fp32"), (128, 3, "bf16"), (64, 4, "bf16"),
-                                                    (64, 5, "fp32"), (1024, 3, "bf16")])
+                                                    (64, 5, "fp32"), (1024, 3, "bf16"), (128, 3, "fp32_tc"),
+                                                    (64, 4, "fp32_tc")])
 def test_native_one_call_prediction_matches_op_by_op_path(cuda, hids, depth, precision):
     """lpgnn_predict_basis (graph build + forward + selection enqueued from C++) == the Python-orchestrated path."""
     lp, model, ref, g_ref, batch = _setup((900, 1700, 8000, 21), hids, depth, cuda)
@@ -115,3 +116,34 @@ def test_native_one_call_prediction_matches_op_by_op_path(cuda, hids, depth, pre
     model.predict_basis_coo(t(lp.row[perm], np.int32), t(lp.col[perm], np.int32), t(lp.a_data[perm], np.float32),
                             lp.m, lp.n, batch.x_s, batch.x_t, is_sorted=True)
     assert int(model.last_graph_status.item()) & 1
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp32_tc", "bf16"])
+def test_full_size_c2_parity_against_oracle(cuda, precision):
+    """BASELINE config C2 at full size (50K x 100K, ~491K nnz, hids 1024, depth 3): logits and statuses of the
+    one-call native path vs the CPU oracle port on the same LP and weights."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import synth
+    lp, model, ref, g_ref, batch = _setup((50_000, 100_000, 500_000, 1236), 1024, 3, cuda)
+    model.set_precision(precision)
+    t = lambda a, dt: torch.from_numpy(a.astype(dt)).to(cuda)
+    status, logits = model.predict_basis_coo(t(lp.row, np.int32), t(lp.col, np.int32), t(lp.a_data, np.float32), lp.m,
+                                             lp.n, batch.x_s, batch.x_t, is_sorted=True, want_logits=True)
+    assert int(model.last_graph_status.item()) == 0
+    with torch.no_grad():
+        ec, ev = ref(torch.from_numpy(lp.c_feas), torch.from_numpy(lp.v_feas), port.TorchGraph(g_ref))
+    exp = torch.cat((ec, ev)).numpy()
+    got = logits.cpu().numpy()
+    d = np.abs(got - exp) / 10.0
+    fro = np.linalg.norm(got - exp) / np.linalg.norm(exp)
+    st = status.cpu().numpy()
+    agree = np.mean(st == port.inference_gnn_np(exp, lp.m))
+    print(f"C2 {precision}: max err/10 = {d.max():.3e}, fro = {fro:.3e}, status agreement = {agree:.5f}")
+    assert int((st == 1).sum()) == lp.m
+    if precision == "fp32":                       # strict-parity mode (north_star: fp32 logits within 1e-4)
+        assert d.max() < 1e-4, d.max()
+        assert agree >= 0.999
+    elif precision == "fp32_tc":                  # six bf16 tensor-core passes: bounded by the truncating accumulation
+        assert fro < 1e-4 and d.max() < 1e-3 and agree >= 0.999
+    else:
+        assert fro < 2e-2 and np.mean(d < 2e-2) >= 0.99 and agree >= 0.98

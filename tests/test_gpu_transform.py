@@ -127,9 +127,11 @@ def test_transform_with_fused_head(cuda, M, N, K, want_out):
 
 
 @pytest.mark.parametrize("M,N,K1,K2", [(1000, 1024, 1024, 1024), (129, 64, 64, 64), (5000, 128, 128, 0), (333, 512, 192, 64)])
-@pytest.mark.parametrize("relu", [False, True])
-def test_transform_fp32_via_three_bf16_tensor_core_passes(cuda, M, N, K1, K2, relu):
-    """bf16x3: fp32 operands split into (hi, lo) bf16; error must sit at fp32 level, far below plain bf16."""
+@pytest.mark.parametrize("parts,tol", [(2, 4e-5), (3, 2e-5)])
+def test_transform_fp32_via_split_bf16_tensor_core_passes(cuda, M, N, K1, K2, parts, tol):
+    """fp32 operands split into 2 / 3 bf16 parts, 3 / 6 tensor-core passes.  The split itself is exact to 2^-17 / 2^-25;
+    the result error is then bounded by the tensor core's own fp32 accumulation (truncating adds: ~1e-6 at K=128,
+    ~1.5e-5 at K=2048 measured), which is why parts=3 is only ~2x better than parts=2 at the largest K."""
     import lpgnn_b200  # noqa: F401
     from lpgnn_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(M + N + K1)
@@ -138,12 +140,13 @@ def test_transform_fp32_via_three_bf16_tensor_core_passes(cuda, M, N, K1, K2, re
     a2 = torch.randn(M, K2, device=cuda, generator=g) if K2 else None
     w2 = torch.randn(N, K2, device=cuda, generator=g) / K2 ** 0.5 if K2 else None
     b = torch.randn(N, device=cuda, generator=g)
-    hi, lo = ops.split_bf16(a1)
-    assert float((hi.float() + lo.float() - a1).abs().max()) < 2 ** -16 * float(a1.abs().max())
-    y = ops.node_transform_x3(ops.split_bf16(a1), ops.split_bf16(w1), ops.split_bf16(a2) if K2 else None,
-                              ops.split_bf16(w2) if K2 else None, b, relu=relu)
-    e = _ref(a1, w1, a2, w2, b, relu)
+    ps = ops.split_bf16(a1, parts)
+    resid = float((sum(p.float() for p in ps) - a1).abs().max()) / float(a1.abs().max())
+    assert resid < (2 ** -16 if parts == 2 else 2 ** -23)
+    sp = lambda x: ops.split_bf16(x, parts)
+    y = ops.node_transform_split(sp(a1), sp(w1), sp(a2) if K2 else None, sp(w2) if K2 else None, b, relu=True)
+    e = _ref(a1, w1, a2, w2, b, True)
     err = float((y.double() - e).abs().max()) / max(1.0, float(e.abs().max()))
-    assert err < 3e-5, err
-    y_simt = ops.node_transform(a1, w1, a2, w2, b, relu=relu)
+    assert err < tol, err
+    y_simt = ops.node_transform(a1, w1, a2, w2, b, relu=True)
     assert float((y - y_simt).abs().max()) < 2e-4 * max(1.0, float(e.abs().max()))
