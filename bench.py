@@ -492,9 +492,16 @@ def kernel_rooflines(model, lp, dev, peaks, bf16, args):
     add("graph_build (sorted COO->CSR+CSC)", "hbm", t_b, z * 12 * 2 * 2, -1)
     t_b2 = time_kernel(lambda: BipartiteCSR.from_coo(h_row, h_col, h_val, m, n, is_sorted=False), reps, flush)
     add("graph_build (unsorted COO->CSR+CSC)", "hbm", t_b2, z * 12 * 2 * 3, -1)
+    # measured DRAM traffic per launch from the committed ncu --set full capture (same workload / precision only)
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.isfile(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("workload") == args.workload and tj.get("precision") == args.precision and args.structure == "staircase":
+            for k in kernels:
+                k["traffic"] = tj["bytes"].get(k["kernel"])
     dom = max([k for k in kernels if "unsorted" not in k["kernel"]], key=lambda k: k["ms"])
     roof = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
-            "frac": dom["frac"], "traffic": None, "kernel": dom["kernel"], "peak_source": peaks["source"] +
+            "frac": dom["frac"], "traffic": dom.get("traffic"), "kernel": dom["kernel"], "peak_source": peaks["source"] +
             (" (burst bf16 figure: kernel timed alone)" if dom["bound"] == "tensor" else " (copy bandwidth)")}
     return {"roofline": roof, "kernels": kernels}
 
