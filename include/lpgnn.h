@@ -303,6 +303,14 @@ LPGNN_API size_t lpgnn_gemm_tn_workspace_bytes(int32_t M, int32_t N, int32_t K);
 LPGNN_API int lpgnn_gemm_tn(const void* A, const void* B, int32_t M, int32_t N, int32_t K, float* out,
                   void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
 
+/* dW[N_out, K_in] (f32) = dY[Mn, N_out]^T * X[Mn, K_in] (bf16, row-major, Mn = number of nodes): the weight
+ * gradient of a node transform straight from the row-major activations -- the tcgen05 operands are
+ * MN-major (TMA boxes of 64 nodes x 64 features), so no transposed copies exist; split-K over the nodes with
+ * a fixed-order reduction (deterministic).  N_out, K_in multiples of 8 (K_in of 64). */
+LPGNN_API size_t lpgnn_wgrad_workspace_bytes(int64_t Mn, int32_t N_out, int32_t K_in);
+LPGNN_API int lpgnn_wgrad(const void* dY, const void* X, int64_t Mn, int32_t N_out, int32_t K_in, float* out,
+                void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
+
 /* Backward of lpgnn_head_mask wrt the hidden activation (reference arch.py:186-191, 129-141), fused with
  * the ReLU / inverted-dropout mask of that activation:
  *   draw[i,:] = d(10*raw/max(|raw|,1e-12))^T dlogits[i,:]        (mask offsets are constants)

@@ -189,6 +189,37 @@ __global__ void splitk_reduce_kernel(const float4* __restrict__ partial, int spl
 }
 }  // namespace lpgnn
 
+namespace lpgnn {
+int gemm_tc_mn(const void* A, const void* B, int64_t Kred, int M, int N, void* out, int ksplit, cudaStream_t st);
+}
+
+// dW[N_out, K_in] = dY[Mn, N_out]^T * X[Mn, K_in]: weight gradient straight from the row-major activations
+// (MN-major tcgen05 operands: no transposed copies), split-K over the node dimension, deterministic reduce.
+extern "C" size_t lpgnn_wgrad_workspace_bytes(int64_t Mn, int32_t N_out, int32_t K_in) {
+  return (size_t)lpgnn_gemm_tn_splits(N_out, K_in, (int32_t)((Mn + 63) / 64 * 64)) * (size_t)N_out * (size_t)K_in * sizeof(float);
+}
+
+extern "C" int lpgnn_wgrad(const void* dY, const void* X, int64_t Mn, int32_t N_out, int32_t K_in, float* out,
+                           void* workspace, size_t workspace_bytes, lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(Mn > 0 && N_out > 0 && K_in > 0 && dY && X && out, "wgrad: bad arguments");
+  const int splits = lpgnn_gemm_tn_splits(N_out, K_in, (int32_t)((Mn + 63) / 64 * 64));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (splits == 1) return gemm_tc_mn(dY, X, Mn, N_out, K_in, out, 1, st);
+  if (!workspace || workspace_bytes < lpgnn_wgrad_workspace_bytes(Mn, N_out, K_in)) {
+    set_error("wgrad: workspace too small");
+    return LPGNN_EWORKSPACE;
+  }
+  LPGNN_REQUIRE(((int64_t)N_out * K_in) % 4 == 0 && (uintptr_t)workspace % 16 == 0, "wgrad: N_out*K_in must be a multiple of 4");
+  if (int rc = gemm_tc_mn(dY, X, Mn, N_out, K_in, workspace, splits, st)) return rc;
+  const int64_t quads = (int64_t)N_out * K_in / 4;
+  splitk_reduce_kernel<<<ceil_div(quads, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(workspace), splits, quads,
+                                                            reinterpret_cast<float4*>(out));
+  LPGNN_LAUNCH_OK();
+  count_launches(1);
+  return LPGNN_OK;
+}
+
 extern "C" int32_t lpgnn_gemm_tn_splits(int32_t M, int32_t N, int32_t K) {
   // enough (tile, slice) work items to fill the machine, at least 8 K-blocks of 64 per slice
   const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);

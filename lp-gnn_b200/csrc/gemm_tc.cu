@@ -55,7 +55,9 @@ struct Segs {
   int count;
 };
 
-template <int BN, typename OutT>
+// kMN = true: both operands are MN-major (out = A^T B with A [Kred, M], B [Kred, N] row-major; the weight gradient
+// dW = dY^T X without materialising any transpose): segment 0's maps describe A and B with 64 x 64 boxes.
+template <int BN, typename OutT, bool kMN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias, OutT* __restrict__ out, int M, int N,
                int relu, const float* __restrict__ head_w /*[3,N] or null*/,
@@ -114,11 +116,22 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-          int sg = 0;
-          while (kb >= segs.kb_end[sg]) ++sg;
-          const int kc = (kb - (sg ? segs.kb_end[sg - 1] : 0)) * BK;
-          ptx::tma_load_2d(smem_a + stage * C::kABytes, &segs.a[sg], &full_bar[stage], kc, m_blk * BM);
-          ptx::tma_load_2d(smem_b + stage * C::kBBytes, &segs.w[sg], &full_bar[stage], kc, n_blk * BN);
+          if constexpr (kMN) {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              ptx::tma_load_2d(smem_a + stage * C::kABytes + i * 8192, &segs.a[0], &full_bar[stage], m_blk * BM + 64 * i,
+                               kb * BK);
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              ptx::tma_load_2d(smem_b + stage * C::kBBytes + i * 8192, &segs.w[0], &full_bar[stage], n_blk * BN + 64 * i,
+                               kb * BK);
+          } else {
+            int sg = 0;
+            while (kb >= segs.kb_end[sg]) ++sg;
+            const int kc = (kb - (sg ? segs.kb_end[sg - 1] : 0)) * BK;
+            ptx::tma_load_2d(smem_a + stage * C::kABytes, &segs.a[sg], &full_bar[stage], kc, m_blk * BM);
+            ptx::tma_load_2d(smem_b + stage * C::kBBytes, &segs.w[sg], &full_bar[stage], kc, n_blk * BN);
+          }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -126,7 +139,7 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, kMN);
       int stage = 0; uint32_t phase = 0;
       int t = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
@@ -140,12 +153,16 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint64_t adesc = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_a + stage * C::kABytes));
-          const uint64_t bdesc = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_b + stage * C::kBBytes));
+          const uint32_t a_addr = ptx::smem_u32(smem_a + stage * C::kABytes);
+          const uint32_t b_addr = ptx::smem_u32(smem_b + stage * C::kBBytes);
+          const uint64_t adesc = kMN ? ptx::umma_desc_mn_sw128(a_addr, 8192) : ptx::umma_desc_k_sw128(a_addr);
+          const uint64_t bdesc = kMN ? ptx::umma_desc_mn_sw128(b_addr, 8192) : ptx::umma_desc_k_sw128(b_addr);
+          // K-major: 16 elements = 32 bytes along the swizzle row (+2 in 16-byte units);
+          // MN-major: 16 K-rows of 128 bytes = 2048 bytes (+128)
+          constexpr uint32_t kstep = kMN ? 128 : 2;
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
-            // advance 16 elements = 32 bytes along K inside the swizzle row: +2 in 16-byte units
-            ptx::umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            ptx::umma_bf16(tmem_d, adesc + kstep * k, bdesc + kstep * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
           ptx::umma_commit(&empty_bar[stage]);  // slot free once these MMAs have read it
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -289,19 +306,19 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int bo
   return LPGNN_OK;
 }
 
-template <int BN, typename OutT>
+template <int BN, typename OutT, bool kMN = false>
 int launch(const Segs& segs, const float* bias, void* out, int M, int N, int relu, const float* head_w,
            float* head_partial, int ksplit, cudaStream_t st) {
   using C = Cfg<BN, OutT>;
   static bool attr_set = false;
   if (!attr_set) {
-    LPGNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LPGNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, OutT, kMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        C::kSmemBytes));
     attr_set = true;
   }
   const int tiles = ceil_div(M, BM) * (N / BN) * ksplit;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<BN, OutT><<<grid, kThreads, C::kSmemBytes, st>>>(segs, bias, reinterpret_cast<OutT*>(out), M, N, relu,
+  gemm_tc_kernel<BN, OutT, kMN><<<grid, kThreads, C::kSmemBytes, st>>>(segs, bias, reinterpret_cast<OutT*>(out), M, N, relu,
                                                                   head_w, head_partial, ksplit);
   LPGNN_LAUNCH_OK();
   count_launches(1);
@@ -344,6 +361,38 @@ int gemm_tc_run(const void* const* A, const void* const* W, const int* K, int ns
   if (BN == 128) LPGNN_GO(128, __nv_bfloat16);
   LPGNN_GO(64, __nv_bfloat16);
 #undef LPGNN_GO
+}
+
+// out[M,N] (fp32) = A^T B for A [Kred, M], B [Kred, N] row-major bf16 (MN-major operands), split-K over Kred.
+// `out` is the [ksplit][M][N] partial buffer when ksplit > 1.
+int gemm_tc_mn(const void* A, const void* B, int64_t Kred, int M, int N, void* out, int ksplit, cudaStream_t st) {
+  LPGNN_REQUIRE(A && B && out && Kred > 0 && M > 0 && N % 64 == 0 && M % 8 == 0 && N % 8 == 0,
+                "gemm_mn: bad arguments (M=%d, N=%d must be multiples of 8; N of 64)", M, N);
+  LPGNN_REQUIRE((uintptr_t)A % 16 == 0 && (uintptr_t)B % 16 == 0 && (uintptr_t)out % 16 == 0, "gemm_mn: misaligned operand");
+  const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("gemm_mn: cuTensorMapEncodeTiled unavailable"); return LPGNN_ECUDA; }
+  Segs segs;
+  auto mk = [&](CUtensorMap* map, const void* base, int cols) -> int {
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)Kred};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("gemm_mn: cuTensorMapEncodeTiled failed (%d)", (int)r); return LPGNN_ECUDA; }
+    return LPGNN_OK;
+  };
+  if (int rc = mk(&segs.a[0], A, M)) return rc;
+  if (int rc = mk(&segs.w[0], B, N)) return rc;
+  const int kb = (int)((Kred + BK - 1) / BK);
+  for (int i = 0; i < kMaxSegs; ++i) { if (i) { segs.a[i] = segs.a[0]; segs.w[i] = segs.w[0]; } segs.kb_end[i] = kb; }
+  segs.count = 1;
+  LPGNN_REQUIRE(ksplit >= 1 && ksplit <= kb, "gemm_mn: bad ksplit %d for %d K blocks", ksplit, kb);
+  if (BN == 256) return launch<256, float, true>(segs, nullptr, out, M, N, 0, nullptr, nullptr, ksplit, st);
+  if (BN == 128) return launch<128, float, true>(segs, nullptr, out, M, N, 0, nullptr, nullptr, ksplit, st);
+  return launch<64, float, true>(segs, nullptr, out, M, N, 0, nullptr, nullptr, ksplit, st);
 }
 
 int node_transform_bf16(const void* A1, int K1, const void* W1, const void* A2, int K2, const void* W2,

@@ -127,9 +127,24 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand tile (the reduction index is the ROW index of the global matrix, e.g. dW = dY^T X reduces over
+// nodes): shared memory holds K-rows of 128 bytes = 64 consecutive M/N elements, 128-byte swizzle, exactly what a
+// TMA box {64 cols, 64 rows} writes.  Canonical layout ((8,n),(8,k)) in 16-byte units: the 64-element atoms along
+// M/N are LBO apart (one 8 KB box), the 8-row groups along K are SBO = 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, both operands K-major.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-  return (1u << 4)                    // D format: F32
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, bool mn_major = false) {
+  return (mn_major ? ((1u << 15) | (1u << 16)) : 0u)  // A / B major: 0 = K-major, 1 = MN-major
+         | (1u << 4)                  // D format: F32
          | (1u << 7)                  // A format: BF16
          | (1u << 10)                 // B format: BF16
          | ((uint32_t)(n >> 3) << 17) // N / 8

@@ -229,6 +229,23 @@ def gemm_tn(a, b):
     return out
 
 
+def wgrad(dy, x):
+    """``dy^T x`` -> fp32 ``[N_out, K_in]`` for bf16 row-major ``dy [Mn, N_out]``, ``x [Mn, K_in]`` (MN-major
+    tensor-core operands, split-K over the nodes; no transposed copies)."""
+    require_cuda(dy, x)
+    dy, x = _contig(dy), _contig(x)
+    Mn, N = dy.shape
+    K = x.shape[1]
+    lib = _lib.load()
+    out = torch.empty((N, K), dtype=torch.float32, device=dy.device)
+    ws_bytes = lib.lpgnn_wgrad_workspace_bytes(Mn, N, K)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dy.device)
+    with torch.cuda.device(dy.device):
+        rc = lib.lpgnn_wgrad(dy.data_ptr(), x.data_ptr(), Mn, N, K, out.data_ptr(), ws.data_ptr(), ws_bytes, stream_ptr())
+    check(rc, "lpgnn_wgrad")
+    return out
+
+
 def head_mask_bwd(dlogits, raw, h_act, w, scale=1.0):
     """Backward of ``head_mask`` wrt the hidden activation, fused with its ReLU/dropout mask.
     Returns ``(dH[rows,H], draw[rows,3])``."""

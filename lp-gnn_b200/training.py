@@ -119,13 +119,18 @@ class _GCNFCFunction(torch.autograd.Function):
             w = P[6 + 6 * i: 12 + 6 * i]
             agg_s, agg_t = acts[4 + 4 * i], acts[5 + 4 * i]
             left_in, right_in = acts[2 + 4 * i], acts[3 + 4 * i]       # inputs of this layer (outputs of the previous)
-            dps_t, dpt_t = ops.transpose(d_pre_s), ops.transpose(d_pre_t)
             g = 6 + 6 * i
-            grads[g + 0], grads[g + 2] = _wgrad_pair(dpt_t, agg_t, right_in)   # l2r lin_rel / lin_root weights
+            if dt == torch.bfloat16:
+                # MN-major tensor-core operands: dW = dPre^T X straight from the row-major activations
+                grads[g + 0], grads[g + 2] = ops.wgrad(d_pre_t, agg_t), ops.wgrad(d_pre_t, right_in)
+                grads[g + 3], grads[g + 5] = ops.wgrad(d_pre_s, agg_s), ops.wgrad(d_pre_s, left_in)
+            else:
+                dps_t, dpt_t = ops.transpose(d_pre_s), ops.transpose(d_pre_t)
+                grads[g + 0], grads[g + 2] = _wgrad_pair(dpt_t, agg_t, right_in)   # l2r lin_rel / lin_root weights
+                grads[g + 3], grads[g + 5] = _wgrad_pair(dps_t, agg_s, left_in)    # r2l lin_rel / lin_root weights
+                del dps_t, dpt_t
             grads[g + 1] = ops.colsum(d_pre_t)
-            grads[g + 3], grads[g + 5] = _wgrad_pair(dps_t, agg_s, left_in)    # r2l lin_rel / lin_root weights
             grads[g + 4] = ops.colsum(d_pre_s)
-            del dps_t, dpt_t
             # data gradients (weights transposed once per step: [K,N] K-major for the TN kernel)
             w_rel_l2r_t, w_root_l2r_t = cast(w[0]).t().contiguous(), cast(w[2]).t().contiguous()
             w_rel_r2l_t, w_root_r2l_t = cast(w[3]).t().contiguous(), cast(w[5]).t().contiguous()

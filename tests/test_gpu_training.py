@@ -185,3 +185,19 @@ def test_gemm_tn_splitk(cuda, M, N, K):
     err = (out[rows].double() - exp).abs().max()
     assert float(err) < 2e-4 * K ** 0.5 * 4, float(err)
     assert torch.equal(out, ops.gemm_tn(a, b))
+
+
+@pytest.mark.parametrize("Mn,N,K", [(100_000, 1024, 1024), (50_001, 1024, 1024), (777, 64, 64), (3000, 128, 256), (64, 256, 64)])
+def test_wgrad_mn_major_tensor_core(cuda, Mn, N, K):
+    """dW = dY^T X with MN-major tcgen05 operands (no transposes) vs float64, ragged node counts included."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(Mn % 1000 + N)
+    dy = torch.randn(Mn, N, device=cuda, generator=g).to(torch.bfloat16)
+    x = torch.randn(Mn, K, device=cuda, generator=g).to(torch.bfloat16)
+    out = ops.wgrad(dy, x)
+    rows = torch.randint(0, N, (8,), device=cuda, generator=g)
+    exp = dy[:, rows].double().t() @ x.double()
+    err = float((out[rows].double() - exp).abs().max())
+    assert err < 2e-4 * Mn ** 0.5 * 4, err
+    assert torch.equal(out, ops.wgrad(dy, x))                       # deterministic
