@@ -129,8 +129,9 @@ LPGNN_API int lpgnn_spmm(const int32_t* ptr, const int32_t* idx, const float* va
  * the weight gradient of this layer needs (lpgnn_small_wgrad).
  * ------------------------------------------------------------------------------------------- */
 LPGNN_API int32_t lpgnn_conv_in_zcat_width(int32_t k_src, int32_t k_dst);
-/* The gather half alone: z_cat (f32 [rows,KT], optional) and/or z_bf16 (bf16 [rows,64], zero-padded,
- * optional).  In bf16 mode the input layer is gather_cat -> lpgnn_node_transform(z_bf16, [W_rel|W_root|0]
+/* The gather half alone: z_cat (f32 [rows,KT], optional) and/or z_bf16 (bf16 [rows,64], optional: zero-padded
+ * except column k_src+k_dst, which holds 1.0 when it exists -- its weight column is zero in the forward
+ * transform, and the weight-gradient GEMM lpgnn_wgrad(dPre, z_bf16) finds the bias gradient there).  In bf16 mode the input layer is gather_cat -> lpgnn_node_transform(z_bf16, [W_rel|W_root|0]
  * as bf16 [N,64]): the tensor-core kernel with a single K block, bound by its epilogue (the output
  * write), which is ~4x faster than the CUDA-core transform. */
 LPGNN_API int lpgnn_gather_cat(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,
@@ -316,10 +317,12 @@ LPGNN_API int lpgnn_wgrad(const void* dY, const void* X, int64_t Mn, int32_t N_o
  *   draw[i,:] = d(10*raw/max(|raw|,1e-12))^T dlogits[i,:]        (mask offsets are constants)
  *   dH[i,:]   = (draw[i,:] * W) * scale * (Hact[i,:] > 0)
  * dlogits, raw, draw [rows,3] f32; Hact, dH [rows,Hdim] of h_dtype; W [3,Hdim] f32.  draw (optional
- * output) feeds the head's weight / bias gradients (lpgnn_small_wgrad, lpgnn_colsum). */
+ * output) feeds the head's weight / bias gradients (lpgnn_small_wgrad, lpgnn_colsum).  draw_bf16 (optional
+ * output, bf16 [rows,64] = [draw | 0]) is the same as an operand of the tensor-core weight gradient:
+ * lpgnn_wgrad(Hact, draw_bf16) = [dW_head^T | 0]. */
 LPGNN_API int lpgnn_head_mask_bwd(const float* dlogits, const float* raw, const void* Hact, int h_dtype,
                         int32_t rows, int32_t Hdim, const float* W, float scale, void* dH, float* draw,
-                        lpgnn_stream_t stream);
+                        void* draw_bf16, lpgnn_stream_t stream);
 
 /* out = (a [+ b]) * scale * (act > 0), elementwise; b may be NULL; out may alias a.  Backward of
  * relu_ (reference arch.py:182,188) and of dropout followed by relu_ (arch.py:186-188: `act` is the
@@ -349,6 +352,39 @@ LPGNN_API size_t lpgnn_small_wgrad_workspace_bytes(int64_t M, int32_t N, int32_t
 LPGNN_API int lpgnn_small_wgrad(const void* dY, int dtype, const float* Z, int32_t ldz, int32_t K,
                       int64_t M, int32_t N, float* dW, float* dB,
                       void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a1-a5, training) One training step of GCN_FC enqueued from native code.  Replaces `model(batch)` and the
+ * activation-sized part of `loss.backward()` in the reference's training loop (train.py:121-128, the model of
+ * arch.py:179-193 with dropout arch.py:186-187); the loss (train.py:32-53) and the optimiser (train.py:85-89)
+ * stay with the caller, who passes d(loss)/d(logits) and receives fp32 parameter gradients.  Same kernels, order
+ * and arithmetic as the op-by-op orchestration; ~75 launches come from two C calls.  The workspace holds every
+ * activation the backward pass needs and must stay untouched between the two calls.  Weights as for
+ * lpgnn_predict_basis (bf16 mode: bf16 copies of the hidden weights + the [hids,64] input-layer matrices).
+ * Graph views as written by lpgnn_graph_build (CSR of A [m x n] and CSC).  dropout_p = 0 for eval mode.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct lpgnn_gcn_fc_grads {   /* all fp32, shapes of the corresponding parameters */
+  float *c1_l2r_wrel, *c1_l2r_b, *c1_l2r_wroot, *c1_r2l_wrel, *c1_r2l_b, *c1_r2l_wroot;
+  float* l2r_wrel[LPGNN_MAX_HIDDEN_LAYERS];
+  float* l2r_wroot[LPGNN_MAX_HIDDEN_LAYERS];
+  float* l2r_b[LPGNN_MAX_HIDDEN_LAYERS];
+  float* r2l_wrel[LPGNN_MAX_HIDDEN_LAYERS];
+  float* r2l_wroot[LPGNN_MAX_HIDDEN_LAYERS];
+  float* r2l_b[LPGNN_MAX_HIDDEN_LAYERS];
+  float *head_left_w, *head_left_b, *head_right_w, *head_right_b;
+} lpgnn_gcn_fc_grads;
+LPGNN_API size_t lpgnn_train_workspace_bytes(int32_t m, int32_t n, int32_t p, int32_t q, int32_t hids,
+                                             int32_t depth, int precision);
+LPGNN_API int lpgnn_train_forward(const lpgnn_gcn_fc_weights* w, const int32_t* rowptr, const int32_t* col,
+                        const float* val, const int32_t* colptr, const int32_t* row_csc, const float* val_csc,
+                        int32_t m, int32_t n, const float* x_s, const float* x_t, float dropout_p, uint64_t seed,
+                        float* logits_s, float* logits_t, void* workspace, size_t workspace_bytes,
+                        lpgnn_stream_t stream);
+LPGNN_API int lpgnn_train_backward(const lpgnn_gcn_fc_weights* w, const int32_t* rowptr, const int32_t* col,
+                         const float* val, const int32_t* colptr, const int32_t* row_csc, const float* val_csc,
+                         int32_t m, int32_t n, float dropout_p, const float* dlogits_s, const float* dlogits_t,
+                         const lpgnn_gcn_fc_grads* grads, void* workspace, size_t workspace_bytes,
+                         lpgnn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,13 @@ class GcnFcWeights(C.Structure):
                                                                "r2l_wroot_parts")])
 
 
+class GcnFcGrads(C.Structure):
+    """Mirror of ``lpgnn_gcn_fc_grads`` (include/lpgnn.h)."""
+    _fields_ = ([(k, _p) for k in ("c1_l2r_wrel", "c1_l2r_b", "c1_l2r_wroot", "c1_r2l_wrel", "c1_r2l_b", "c1_r2l_wroot")]
+                + [(k, _p * MAX_HIDDEN_LAYERS) for k in ("l2r_wrel", "l2r_wroot", "l2r_b", "r2l_wrel", "r2l_wroot", "r2l_b")]
+                + [(k, _p) for k in ("head_left_w", "head_left_b", "head_right_w", "head_right_b")])
+
+
 # name -> (restype, argtypes); must list every symbol include/lpgnn.h declares
 SIGNATURES = {
     "lpgnn_version": (_int, []),
@@ -68,7 +75,7 @@ SIGNATURES = {
     "lpgnn_gemm_tn": (_int, [_p, _p, _i32, _i32, _i32, _p, _p, _sz, _p]),
     "lpgnn_wgrad_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "lpgnn_wgrad": (_int, [_p, _p, _i64, _i32, _i32, _p, _p, _sz, _p]),
-    "lpgnn_head_mask_bwd": (_int, [_p, _p, _p, _int, _i32, _i32, _p, C.c_float, _p, _p, _p]),
+    "lpgnn_head_mask_bwd": (_int, [_p, _p, _p, _int, _i32, _i32, _p, C.c_float, _p, _p, _p, _p]),
     "lpgnn_relu_bwd": (_int, [_p, _p, _p, _i64, _int, C.c_float, _p, _p]),
     "lpgnn_dropout": (_int, [_p, _i64, _int, C.c_float, C.c_uint64, _p]),
     "lpgnn_transpose": (_int, [_p, _int, _i64, _i64, _p, _i64, _p]),
@@ -76,6 +83,11 @@ SIGNATURES = {
     "lpgnn_colsum": (_int, [_p, _int, _i64, _i32, _p, _p, _sz, _p]),
     "lpgnn_small_wgrad_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "lpgnn_small_wgrad": (_int, [_p, _int, _p, _i32, _i32, _i64, _i32, _p, _p, _p, _sz, _p]),
+    "lpgnn_train_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32, _int]),
+    "lpgnn_train_forward": (_int, [C.POINTER(GcnFcWeights), _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, C.c_float, C.c_uint64,
+                                   _p, _p, _p, _sz, _p]),
+    "lpgnn_train_backward": (_int, [C.POINTER(GcnFcWeights), _p, _p, _p, _p, _p, _p, _i32, _i32, C.c_float, _p, _p,
+                                    C.POINTER(GcnFcGrads), _p, _sz, _p]),
     "lpgnn_basis_select_workspace_bytes": (_sz, [_i64]),
     "lpgnn_basis_select": (_int, [_p, _i32, _p, _i32, _i32, _p, _int, _p, _p, _sz, _p]),
 }

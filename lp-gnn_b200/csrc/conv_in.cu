@@ -56,7 +56,8 @@ gather_cat_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ i
     if (zbr) zbr[k_src + k] = __float2bfloat16_rn(v);
   }
   if (zr) for (int k = K + f0; k < KT; k += 8) zr[k] = 0.f;
-  if (zbr) for (int k = K + f0; k < 64; k += 8) zbr[k] = __float2bfloat16_rn(0.f);
+  // column K carries 1.0: the forward weight column there is zero, and dPre^T z_bf16 (lpgnn_wgrad) gets the bias gradient
+  if (zbr) for (int k = K + f0; k < 64; k += 8) zbr[k] = __float2bfloat16_rn(k == K ? 1.f : 0.f);
 }
 
 // ---- kernel 2: out[r, c] = epi(b[c] + sum_k z[r][k] * Wcat[c][k]).  Block = 64 rows x 512 columns; a thread

@@ -207,7 +207,7 @@ template <typename T, int CH>
 __global__ void __launch_bounds__(128)
 head_mask_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ raw, const T* __restrict__ Hact,
                      int32_t rows, int32_t Hdim, const float* __restrict__ W, float scale, T* __restrict__ dH,
-                     float* __restrict__ draw_out) {
+                     float* __restrict__ draw_out, __nv_bfloat16* __restrict__ draw_bf16) {
   constexpr int E = Vec16<T>::E;
   const int lane = threadIdx.x & 31;
   const int chunks = Hdim / E;
@@ -242,6 +242,14 @@ head_mask_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict_
       d0 = 1e13f * g0; d1 = 1e13f * g1; d2 = 1e13f * g2;
     }
     if (lane == 0 && draw_out) { draw_out[row * 3] = d0; draw_out[row * 3 + 1] = d1; draw_out[row * 3 + 2] = d2; }
+    if (draw_bf16 && lane < 8) {   // [d0 d1 d2 0 ... 0] as one 128-byte row: the MN-major operand of the head's weight gradient
+      uint4 o = make_uint4(0, 0, 0, 0);
+      if (lane == 0) {
+        o.x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(d0)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(d1)) << 16);
+        o.y = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(d2));
+      }
+      reinterpret_cast<uint4*>(draw_bf16 + row * 64)[lane] = o;
+    }
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int ch = lane + 32 * c;
@@ -401,9 +409,9 @@ extern "C" int lpgnn_small_wgrad(const void* dY, int dtype, const float* Z, int3
 
 template <typename T>
 static int head_bwd_dispatch(const float* dlogits, const float* raw, const void* Hact, int32_t rows, int32_t Hdim,
-                             const float* W, float scale, void* dH, float* draw, int ch, cudaStream_t st) {
+                             const float* W, float scale, void* dH, float* draw, void* draw_bf16, int ch, cudaStream_t st) {
   const int grid = min(ceil_div(rows, 4), sm_count() * 16);
-#define LPGNN_HB(CHV) head_mask_bwd_kernel<T, CHV><<<grid, 128, 0, st>>>(dlogits, raw, (const T*)Hact, rows, Hdim, W, scale, (T*)dH, draw)
+#define LPGNN_HB(CHV) head_mask_bwd_kernel<T, CHV><<<grid, 128, 0, st>>>(dlogits, raw, (const T*)Hact, rows, Hdim, W, scale, (T*)dH, draw, (__nv_bfloat16*)draw_bf16)
   if (ch <= 1) LPGNN_HB(1); else if (ch <= 2) LPGNN_HB(2); else if (ch <= 4) LPGNN_HB(4); else LPGNN_HB(8);
 #undef LPGNN_HB
   LPGNN_LAUNCH_OK();
@@ -413,7 +421,7 @@ static int head_bwd_dispatch(const float* dlogits, const float* raw, const void*
 
 extern "C" int lpgnn_head_mask_bwd(const float* dlogits, const float* raw, const void* Hact, int h_dtype, int32_t rows,
                                    int32_t Hdim, const float* W, float scale, void* dH, float* draw,
-                                   lpgnn_stream_t stream) {
+                                   void* draw_bf16, lpgnn_stream_t stream) {
   if (int rc = check_device()) return rc;
   LPGNN_DT_OK(h_dtype, "head_mask_bwd");
   LPGNN_REQUIRE(rows >= 0 && Hdim > 0, "head_mask_bwd: bad shape");
@@ -424,6 +432,6 @@ extern "C" int lpgnn_head_mask_bwd(const float* dlogits, const float* raw, const
   const int ch = (Hdim * esz / 16 + 31) / 32;
   LPGNN_REQUIRE(ch <= 8, "head_mask_bwd: Hdim=%d too wide (max 4096 bytes per row)", Hdim);
   cudaStream_t st = (cudaStream_t)stream;
-  if (h_dtype == LPGNN_F32) return head_bwd_dispatch<float>(dlogits, raw, Hact, rows, Hdim, W, scale, dH, draw, ch, st);
-  return head_bwd_dispatch<__nv_bfloat16>(dlogits, raw, Hact, rows, Hdim, W, scale, dH, draw, ch, st);
+  if (h_dtype == LPGNN_F32) return head_bwd_dispatch<float>(dlogits, raw, Hact, rows, Hdim, W, scale, dH, draw, draw_bf16, ch, st);
+  return head_bwd_dispatch<__nv_bfloat16>(dlogits, raw, Hact, rows, Hdim, W, scale, dH, draw, draw_bf16, ch, st);
 }

@@ -13,13 +13,14 @@ def labels_to_balanced_weights(labels, merge_lu=True):
     (utils.py:286-299)."""
     # torch.unique(return_counts) of the reference == per-class counts; computed with a comparison + sum so that
     # there is neither a device sort nor a host sync (unique and bincount both read a size back to the host)
-    cnt = (labels.view(-1, 1) == torch.arange(3, device=labels.device)).sum(0).to(torch.float32)
+    cls = torch.arange(3, device=labels.device)
+    cnt = (labels.view(-1, 1) == cls).sum(0).to(torch.float32)
     present = cnt > 0
     res = torch.where(present, cnt.sum() / cnt.clamp_min(1.0), torch.zeros_like(cnt))
     if merge_lu:
         merged = (res[0] + res[2]) / 2.
         two_sided = present.sum() != 2            # the reference merges lower/upper unless exactly 2 classes occur
-        res = torch.where(two_sided & torch.tensor([True, False, True], device=res.device), merged, res)
+        res = torch.where(two_sided & (cls != 1), merged, res)     # (no host-built mask: a pageable H2D copy would sync)
     return res
 
 

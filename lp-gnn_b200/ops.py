@@ -246,20 +246,21 @@ def wgrad(dy, x):
     return out
 
 
-def head_mask_bwd(dlogits, raw, h_act, w, scale=1.0):
+def head_mask_bwd(dlogits, raw, h_act, w, scale=1.0, want_bf16=False):
     """Backward of ``head_mask`` wrt the hidden activation, fused with its ReLU/dropout mask.
-    Returns ``(dH[rows,H], draw[rows,3])``."""
+    Returns ``(dH[rows,H], draw[rows,3])`` [+ ``draw_bf16 [rows,64] = [draw | 0]``, the ``wgrad`` operand]."""
     require_cuda(dlogits, raw, h_act, w)
     dlogits, raw, h_act, w = _contig(dlogits.float()), _contig(raw), _contig(h_act), _contig(w.float())
     rows, H = h_act.shape
     dH = torch.empty_like(h_act)
     draw = torch.empty((rows, 3), dtype=torch.float32, device=h_act.device)
+    draw_b = torch.empty((rows, 64), dtype=torch.bfloat16, device=h_act.device) if want_bf16 else None
     with torch.cuda.device(h_act.device):
         rc = _lib.load().lpgnn_head_mask_bwd(dlogits.data_ptr(), raw.data_ptr(), h_act.data_ptr(), dtype_code(h_act.dtype),
                                              rows, H, w.data_ptr(), float(scale), dH.data_ptr(), draw.data_ptr(),
-                                             stream_ptr())
+                                             _lib.ptr(draw_b), stream_ptr())
     check(rc, "lpgnn_head_mask_bwd")
-    return dH, draw
+    return (dH, draw, draw_b) if want_bf16 else (dH, draw)
 
 
 def relu_bwd(a, b, act, scale=1.0, out=None):

@@ -59,11 +59,11 @@ class _GCNFCFunction(torch.autograd.Function):
                 w[:, :w_rel.shape[1]] = w_rel
                 w[:, w_rel.shape[1]:w_rel.shape[1] + w_root.shape[1]] = w_root
                 return w
-            z_t, zb_t = ops.gather_cat(csc, x_s, x_t, want_f32=True, want_bf16=True)
-            z_s, zb_s = ops.gather_cat(csr, x_t, x_s, want_f32=True, want_bf16=True)
+            _, zb_t = ops.gather_cat(csc, x_s, x_t, want_f32=False, want_bf16=True)
+            _, zb_s = ops.gather_cat(csr, x_t, x_s, want_f32=False, want_bf16=True)
             right = ops.node_transform(zb_t, wcat(P[0], P[2]), bias=P[1], relu=True)
             left = ops.node_transform(zb_s, wcat(P[3], P[5]), bias=P[4], relu=True)
-            del zb_t, zb_s
+            z_s, z_t = zb_s, zb_t            # the bf16 operands (with their ones column) feed the tensor-core weight gradient
         else:
             right, z_t = ops.conv_in_fused(csc, x_s, x_t, P[0], P[1], P[2], dt, relu=True)
             left, z_s = ops.conv_in_fused(csr, x_t, x_s, P[3], P[4], P[5], dt, relu=True)
@@ -106,13 +106,20 @@ class _GCNFCFunction(torch.autograd.Function):
         # ---- heads: dPre of the last layer's activations (relu/dropout mask fused)
         left, right = acts[2 + 4 * n_layers], acts[3 + 4 * n_layers]
         last_scale = ctx.scale if n_layers > 0 else 1.0
-        d_pre_s, draw_s = ops.head_mask_bwd(d_logit_s.contiguous(), raw_s, left, P[hbase], last_scale)
-        d_pre_t, draw_t = ops.head_mask_bwd(d_logit_t.contiguous(), raw_t, right, P[hbase + 2], last_scale)
-        gw, _ = ops.small_wgrad(left, draw_s, 3)            # [H,3] = left^T draw
-        grads[hbase] = gw.t().contiguous()
+        tc_small = z_s.dtype == torch.bfloat16              # bf16 mode: narrow weight gradients on the tensor cores too
+        if tc_small:
+            d_pre_s, draw_s, drawb_s = ops.head_mask_bwd(d_logit_s.contiguous(), raw_s, left, P[hbase], last_scale, want_bf16=True)
+            d_pre_t, draw_t, drawb_t = ops.head_mask_bwd(d_logit_t.contiguous(), raw_t, right, P[hbase + 2], last_scale, want_bf16=True)
+            grads[hbase] = ops.wgrad(left, drawb_s)[:, :3].t().contiguous()       # [H,64] = left^T [draw | 0]
+            grads[hbase + 2] = ops.wgrad(right, drawb_t)[:, :3].t().contiguous()
+        else:
+            d_pre_s, draw_s = ops.head_mask_bwd(d_logit_s.contiguous(), raw_s, left, P[hbase], last_scale)
+            d_pre_t, draw_t = ops.head_mask_bwd(d_logit_t.contiguous(), raw_t, right, P[hbase + 2], last_scale)
+            gw, _ = ops.small_wgrad(left, draw_s, 3)            # [H,3] = left^T draw
+            grads[hbase] = gw.t().contiguous()
+            gw, _ = ops.small_wgrad(right, draw_t, 3)
+            grads[hbase + 2] = gw.t().contiguous()
         grads[hbase + 1] = ops.colsum(draw_s)
-        gw, _ = ops.small_wgrad(right, draw_t, 3)
-        grads[hbase + 2] = gw.t().contiguous()
         grads[hbase + 3] = ops.colsum(draw_t)
         # ---- hidden layers, last to first
         for i in reversed(range(n_layers)):
@@ -145,11 +152,120 @@ class _GCNFCFunction(torch.autograd.Function):
             d_pre_t = ops.relu_bwd(d_right_root, d_right_agg, right_in, prev_scale, out=d_right_root)
         # ---- conv1: weight gradients only (inputs are data)
         k_s, k_t = x_s.shape[1], x_t.shape[1]
-        gw, gb = ops.small_wgrad(d_pre_t, z_t, k_s + k_t, want_bias=True)   # z_t = [A^T x_s | x_t]
-        grads[0], grads[1], grads[2] = gw[:, :k_s].contiguous(), gb, gw[:, k_s:].contiguous()
-        gw, gb = ops.small_wgrad(d_pre_s, z_s, k_s + k_t, want_bias=True)   # z_s = [A x_t | x_s]
-        grads[3], grads[4], grads[5] = gw[:, :k_t].contiguous(), gb, gw[:, k_t:].contiguous()
+        K = k_s + k_t
+        if tc_small:                                                        # z = [agg | x_dst | 1 | 0] bf16 [rows,64]
+            gw = ops.wgrad(d_pre_t, z_t)
+            gb = gw[:, K].contiguous() if K < 64 else ops.colsum(d_pre_t)
+            grads[0], grads[1], grads[2] = gw[:, :k_s].contiguous(), gb, gw[:, k_s:K].contiguous()
+            gw = ops.wgrad(d_pre_s, z_s)
+            gb = gw[:, K].contiguous() if K < 64 else ops.colsum(d_pre_s)
+            grads[3], grads[4], grads[5] = gw[:, :k_t].contiguous(), gb, gw[:, k_t:K].contiguous()
+        else:
+            gw, gb = ops.small_wgrad(d_pre_t, z_t, K, want_bias=True)       # z_t = [A^T x_s | x_t]
+            grads[0], grads[1], grads[2] = gw[:, :k_s].contiguous(), gb, gw[:, k_s:].contiguous()
+            gw, gb = ops.small_wgrad(d_pre_s, z_s, K, want_bias=True)       # z_s = [A x_t | x_s]
+            grads[3], grads[4], grads[5] = gw[:, :k_t].contiguous(), gb, gw[:, k_t:].contiguous()
         return (None, None, None, None, None, *grads)
+
+
+class _NativeTrainFunction(torch.autograd.Function):
+    """The same step through ``lpgnn_train_forward`` / ``lpgnn_train_backward``: two C calls enqueue every
+    kernel; activations live in one workspace tensor that the autograd node keeps alive; the parameter
+    gradients are views of one flat fp32 buffer."""
+
+    @staticmethod
+    def forward(ctx, x_s, x_t, csr, csc, cfg, *params):
+        import ctypes as C
+
+        from . import _lib
+        lib = _lib.load()
+        w = cfg["weights"]
+        dev = x_s.device
+        x_s, x_t = x_s.float().contiguous(), x_t.float().contiguous()
+        m, n = x_s.shape[0], x_t.shape[0]
+        ws_bytes = lib.lpgnn_train_workspace_bytes(m, n, w.p, w.q, w.hids, w.depth, w.precision)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        logits = torch.empty((m + n, 3), dtype=torch.float32, device=dev)
+        dp = cfg["dp"] if cfg["training"] else 0.0
+        with torch.cuda.device(dev):
+            rc = lib.lpgnn_train_forward(C.byref(w), csr[0].data_ptr(), csr[1].data_ptr(), csr[2].data_ptr(),
+                                         csc[0].data_ptr(), csc[1].data_ptr(), csc[2].data_ptr(), m, n,
+                                         x_s.data_ptr(), x_t.data_ptr(), dp, cfg["seed"], logits.data_ptr(),
+                                         logits[m:].data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr())
+        _lib.check(rc, "lpgnn_train_forward")
+        ctx.csr, ctx.csc, ctx.cfg, ctx.dp, ctx.mn = csr, csc, cfg, dp, (m, n)
+        ctx.ws = ws
+        ctx.shapes = [p.shape for p in params]
+        ctx.keep = (x_s, x_t)
+        return logits[:m], logits[m:]
+
+    @staticmethod
+    def backward(ctx, d_logit_s, d_logit_t):
+        import ctypes as C
+
+        from . import _lib
+        lib = _lib.load()
+        w, (m, n), csr, csc = ctx.cfg["weights"], ctx.mn, ctx.csr, ctx.csc
+        if ctx.ws is None:
+            raise RuntimeError("the native training step frees its activations after backward (no retain_graph)")
+        dev = ctx.ws.device
+        d_logit_s = torch.zeros((m, 3), device=dev) if d_logit_s is None else d_logit_s.float().contiguous()
+        d_logit_t = torch.zeros((n, 3), device=dev) if d_logit_t is None else d_logit_t.float().contiguous()
+        sizes = [int(torch.Size(s).numel()) for s in ctx.shapes]
+        offs = [0]
+        for k in sizes:
+            offs.append(offs[-1] + (k + 3) // 4 * 4)                       # 16-byte aligned views
+        flat = torch.empty(offs[-1], dtype=torch.float32, device=dev)
+        grads = [flat[o:o + k].view(s) for o, k, s in zip(offs, sizes, ctx.shapes)]
+        g = _lib.GcnFcGrads()
+        names = ["c1_l2r_wrel", "c1_l2r_b", "c1_l2r_wroot", "c1_r2l_wrel", "c1_r2l_b", "c1_r2l_wroot"]
+        for k, nm in enumerate(names):
+            setattr(g, nm, grads[k].data_ptr())
+        nh = w.depth - 2
+        for i in range(nh):
+            for k, nm in enumerate(("l2r_wrel", "l2r_b", "l2r_wroot", "r2l_wrel", "r2l_b", "r2l_wroot")):
+                getattr(g, nm)[i] = grads[6 + 6 * i + k].data_ptr()
+        for k, nm in enumerate(("head_left_w", "head_left_b", "head_right_w", "head_right_b")):
+            setattr(g, nm, grads[6 + 6 * nh + k].data_ptr())
+        ws = ctx.ws
+        with torch.cuda.device(dev):
+            rc = lib.lpgnn_train_backward(C.byref(w), csr[0].data_ptr(), csr[1].data_ptr(), csr[2].data_ptr(),
+                                          csc[0].data_ptr(), csc[1].data_ptr(), csc[2].data_ptr(), m, n, ctx.dp,
+                                          d_logit_s.data_ptr(), d_logit_t.data_ptr(), C.byref(g), ws.data_ptr(),
+                                          ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, "lpgnn_train_backward")
+        ctx.ws = None
+        return (None, None, None, None, None, *grads)
+
+
+def _train_weights(model, params):
+    """``lpgnn_gcn_fc_weights`` over the fp32 MASTER parameters (no copies: the optimiser updates them in place, so
+    the struct stays valid until a parameter is re-allocated).  None when the native step does not cover the model."""
+    from . import _lib
+    bf16 = model.precision == "bf16"
+    c1 = model.conv1.left2right
+    p_, q_ = c1.in_channels[0], c1.in_channels[1]
+    nh = len(model.layers)
+    if nh > _lib.MAX_HIDDEN_LAYERS or any(t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda for t in params):
+        return None
+    if bf16 and (model.hids % 64 != 0 or p_ + q_ > 64):
+        return None
+    key = tuple(t.data_ptr() for t in params) + (model.precision,)
+    hit = getattr(model, "_train_cache", None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    w = _lib.GcnFcWeights()
+    w.p, w.q, w.hids, w.depth = p_, q_, model.hids, nh + 2
+    w.precision = _lib.BF16 if bf16 else _lib.F32
+    for k, nm in enumerate(("c1_l2r_wrel", "c1_l2r_b", "c1_l2r_wroot", "c1_r2l_wrel", "c1_r2l_b", "c1_r2l_wroot")):
+        setattr(w, nm, params[k].data_ptr())
+    for i in range(nh):
+        for k, nm in enumerate(("l2r_wrel", "l2r_b", "l2r_wroot", "r2l_wrel", "r2l_b", "r2l_wroot")):
+            getattr(w, nm)[i] = params[6 + 6 * i + k].data_ptr()
+    for k, nm in enumerate(("head_left_w", "head_left_b", "head_right_w", "head_right_b")):
+        setattr(w, nm, params[6 + 6 * nh + k].data_ptr())
+    model._train_cache = (key, w)
+    return w
 
 
 _step_counter = [0]
@@ -160,7 +276,13 @@ def gcn_fc_train(model, x_s, x_t, csr, csc):
     _step_counter[0] += 1
     cfg = dict(dtype=dt, dp=float(model.dp), training=bool(model.training), n_hidden=len(model.layers),
                seed=(int(torch.initial_seed()) * 1_000_003 + _step_counter[0] * 7919) & (2 ** 62 - 1))
-    return _GCNFCFunction.apply(x_s, x_t, csr, csc, cfg, *_param_list(model))
+    params = _param_list(model)
+    if getattr(model, "native_train", True):
+        w = _train_weights(model, params)
+        if w is not None:
+            cfg["weights"] = w
+            return _NativeTrainFunction.apply(x_s, x_t, csr, csc, cfg, *params)
+    return _GCNFCFunction.apply(x_s, x_t, csr, csc, cfg, *params)
 
 
 def conv_train(conv, left, right, csr, csc, relu, dropout_p=0.0, training=False):

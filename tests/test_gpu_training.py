@@ -94,7 +94,73 @@ def test_training_reduces_loss_with_dropout(cuda):
     assert min(losses[-5:]) < losses[0]
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,dp", [("small_300x600", 0.0), ("c1_1000x2000", 0.2)])
+def test_native_step_equals_op_by_op_step(cuda, precision, name, dp):
+    """lpgnn_train_forward/backward enqueue the same kernels as the op-by-op orchestration: identical bits."""
+    from lpgnn_b200 import training
+    from lpgnn_b200.losses import balanced
+    out = []
+    for native in (True, False):
+        model, batch, y_s, y_t, _ = _golden_setup(name, cuda, precision)
+        model.train()
+        model.dp, model.native_train = dp, native
+        training._step_counter[0] = 41                               # same dropout seed for both paths
+        lc, lv = model(batch)
+        assert (type(lc.grad_fn).__name__.startswith("_NativeTrainFunction")) == native
+        loss = balanced(lc, lv, y_s, y_t)
+        loss.backward()
+        out.append((lc.detach().clone(), lv.detach().clone(), [p.grad.clone() for p in model.parameters()]))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    for (k, _), a, b in zip(model.named_parameters(), out[0][2], out[1][2]):
+        assert torch.equal(a, b), (k, (a - b).abs().max().item())
+
+
+def test_native_step_rejects_second_backward(cuda):
+    from lpgnn_b200.losses import balanced
+    model, batch, y_s, y_t, _ = _golden_setup("small_300x600", cuda, "fp32")
+    lc, lv = model(batch)
+    loss = balanced(lc, lv, y_s, y_t)
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError):
+        loss.backward()
+
+
 # ------------------------------------------------------------------------------------------- kernel units
+def test_bf16_operands_of_the_narrow_weight_gradients(cuda):
+    """gather_cat's bf16 output carries a ones column after the features (bias gradient through the tensor-core
+    weight gradient); head_mask_bwd's bf16 draw is [draw | 0]; wgrad over them matches fp32 matmuls."""
+    from conftest import make_graph_arrays
+    from lpgnn_b200 import ops
+    from lpgnn_b200.graph import BipartiteCSR
+    m, n, H = 700, 1300, 128
+    row, col, val = make_graph_arrays(m, n, 6000, seed=3)
+    g = BipartiteCSR.from_coo_arrays(row, col, val, m, n, cuda)
+    csr, csc = g.views()
+    gen = torch.Generator(device="cpu").manual_seed(0)
+    x_s, x_t = torch.randn(m, 8, generator=gen).to(cuda), torch.randn(n, 8, generator=gen).to(cuda)
+    z32, zb = ops.gather_cat(csc, x_s, x_t, want_f32=True, want_bf16=True)
+    assert torch.equal(zb[:, :16], z32[:, :16].to(torch.bfloat16))
+    assert torch.all(zb[:, 16] == 1) and torch.all(zb[:, 17:] == 0)
+    d_pre = (torch.randn(n, H, generator=gen) * 0.1).to(cuda).to(torch.bfloat16)
+    gw = ops.wgrad(d_pre, zb)                                        # [H,64]
+    ref = d_pre.float().t() @ zb.float()
+    assert (gw - ref).abs().max() / ref.abs().max() < 1e-4
+    assert (gw[:, 16] - d_pre.float().sum(0)).abs().max() < 1e-3 * d_pre.float().abs().sum(0).max()
+    assert torch.all(gw[:, 17:] == 0)
+    # head: draw as a bf16 operand
+    h_act = torch.relu(torch.randn(n, H, generator=gen)).to(cuda).to(torch.bfloat16)
+    w = torch.randn(3, H, generator=gen).to(cuda)
+    raw, dlog = torch.randn(n, 3, generator=gen).to(cuda), torch.randn(n, 3, generator=gen).to(cuda)
+    dH, draw, draw_b = ops.head_mask_bwd(dlog, raw, h_act, w, 1.0, want_bf16=True)
+    dH2, draw2 = ops.head_mask_bwd(dlog, raw, h_act, w, 1.0)
+    assert torch.equal(dH, dH2) and torch.equal(draw, draw2)
+    assert torch.equal(draw_b[:, :3], draw.to(torch.bfloat16)) and torch.all(draw_b[:, 3:] == 0)
+    gh = ops.wgrad(h_act, draw_b)[:, :3]
+    ref = h_act.float().t() @ draw_b[:, :3].float()
+    assert (gh - ref).abs().max() / ref.abs().max() < 1e-4
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_relu_bwd_and_transpose_and_colsum(cuda, dtype):
     import lpgnn_b200  # noqa: F401
