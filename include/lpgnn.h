@@ -161,6 +161,26 @@ LPGNN_API int lpgnn_node_transform(const void* A1, int32_t K1, const void* W1,
                          const float* bias, int32_t M, int32_t N,
                          void* out, int dtype, int out_dtype, int epilogue, lpgnn_stream_t stream);
 
+/* lpgnn_node_transform with keep-masks fused into the epilogue (training; out is of `dtype`):
+ *   out = keep ? epi(A1 W1^T + A2 W2^T + bias) * s : 0
+ *   mask_act != NULL  keep &= (mask_act > 0), s *= mask_scale: the data gradient of a layer masked by the ReLU /
+ *                     inverted-dropout pattern of that layer's input activation (reference arch.py:182,186-188
+ *                     differentiated); mask_act has the shape and dtype of out.
+ *   dropout_p > 0     keep &= lpgnn_dropout's hash of (dropout_seed, element index), s *= 1/(1-p): F.dropout
+ *                     after the layer (arch.py:186-187; dropout and relu_ commute).
+ * bf16: applied on the fp32 accumulators inside the tensor-core kernel, no extra pass over the activations.
+ * fp32: the CUDA-core transform followed by lpgnn_relu_bwd / lpgnn_dropout (same result semantics). */
+typedef struct lpgnn_epilogue_args {
+  int32_t epilogue;        /* LPGNN_EPI_NONE | LPGNN_EPI_RELU */
+  float dropout_p;
+  uint64_t dropout_seed;
+  const void* mask_act;
+  float mask_scale;
+} lpgnn_epilogue_args;
+LPGNN_API int lpgnn_node_transform_ex(const void* A1, int32_t K1, const void* W1, const void* A2, int32_t K2,
+                            const void* W2, const float* bias, int32_t M, int32_t N, void* out, int dtype,
+                            const lpgnn_epilogue_args* epi, lpgnn_stream_t stream);
+
 /* (a3, fp32 parity mode on the tensor cores) The same transform with fp32 accuracy from bf16 tensor-core
  * products: every fp32 operand x is given as `parts` bf16 tensors p0 = bf16(x), p1 = bf16(x - p0)
  * [, p2 = bf16(x - p0 - p1)] (lpgnn_split_bf16) and the significant cross products are accumulated in the

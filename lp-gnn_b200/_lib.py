@@ -36,6 +36,12 @@ class GcnFcWeights(C.Structure):
                                                                "r2l_wroot_parts")])
 
 
+class EpilogueArgs(C.Structure):
+    """Mirror of ``lpgnn_epilogue_args`` (include/lpgnn.h)."""
+    _fields_ = [("epilogue", _i32), ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("mask_act", _p),
+                ("mask_scale", C.c_float)]
+
+
 class GcnFcGrads(C.Structure):
     """Mirror of ``lpgnn_gcn_fc_grads`` (include/lpgnn.h)."""
     _fields_ = ([(k, _p) for k in ("c1_l2r_wrel", "c1_l2r_b", "c1_l2r_wroot", "c1_r2l_wrel", "c1_r2l_b", "c1_r2l_wroot")]
@@ -58,6 +64,7 @@ SIGNATURES = {
     "lpgnn_gather_cat": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p]),
     "lpgnn_conv_in_fused": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p, _i32, _p, _int, _int, _p, _p]),
     "lpgnn_node_transform": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _int, _int, _p]),
+    "lpgnn_node_transform_ex": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, C.POINTER(EpilogueArgs), _p]),
     "lpgnn_split_bf16": (_int, [_p, _i64, _int, _p, _p]),
     "lpgnn_node_transform_split": (_int, [_int, _p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _p]),
     "lpgnn_node_transform_head_parts": (_i32, [_i32]),

@@ -55,10 +55,11 @@ int node_transform_f32(const float* A1, int K1, const float* W1, const float* A2
                        const float* bias, int M, int N, float* out, int relu, cudaStream_t st);
 int node_transform_bf16(const void* A1, int K1, const void* W1, const void* A2, int K2, const void* W2,
                         const float* bias, int M, int N, void* out, int out_f32, int relu, const float* head_w,
-                        float* head_partial, int ksplit, cudaStream_t st);
+                        float* head_partial, int ksplit, cudaStream_t st, const EpiX& epx = EpiX());
 
 int gemm_tc_run(const void* const* A, const void* const* W, const int* K, int nseg, const float* bias, int M, int N,
-                void* out, int out_f32, int relu, const float* head_w, float* head_partial, int ksplit, cudaStream_t st);
+                void* out, int out_f32, int relu, const float* head_w, float* head_partial, int ksplit, cudaStream_t st,
+                const EpiX& epx = EpiX());
 
 // x = p0 + p1 (+ p2) with p0 = bf16(x), p1 = bf16(x - p0), p2 = bf16(x - p0 - p1): the operand form of the
 // fp32-accurate tensor-core transform (2 parts: ~2^-17 relative, 3 parts: ~2^-25)
@@ -156,6 +157,40 @@ extern "C" int lpgnn_node_transform(const void* A1, int32_t K1, const void* W1, 
                               N, (float*)out, relu, st);
   return node_transform_bf16(A1, K1, W1, A2, K2, W2, bias, M, N, out, out_dtype == LPGNN_F32 ? 1 : 0, relu, nullptr,
                              nullptr, 1, st);
+}
+
+// node_transform + fused keep-masks (training): see include/lpgnn.h
+extern "C" int lpgnn_node_transform_ex(const void* A1, int32_t K1, const void* W1, const void* A2, int32_t K2,
+                                       const void* W2, const float* bias, int32_t M, int32_t N, void* out, int dtype,
+                                       const lpgnn_epilogue_args* epi, lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(epi, "node_transform_ex: null epilogue arguments");
+  LPGNN_REQUIRE(dtype == LPGNN_F32 || dtype == LPGNN_BF16, "node_transform_ex: bad dtype %d", dtype);
+  LPGNN_REQUIRE(epi->dropout_p >= 0.f && epi->dropout_p < 1.f, "node_transform_ex: dropout_p=%f outside [0,1)", epi->dropout_p);
+  const float mscale = epi->mask_act ? epi->mask_scale : 1.f;
+  if (dtype == LPGNN_F32) {   // CUDA-core transform, then the stand-alone mask / dropout kernels (same semantics)
+    if (int rc = lpgnn_node_transform(A1, K1, W1, A2, K2, W2, bias, M, N, out, dtype, dtype, epi->epilogue, stream)) return rc;
+    if (epi->mask_act)
+      if (int rc = lpgnn_relu_bwd(out, nullptr, epi->mask_act, (int64_t)M * N, dtype, mscale, out, stream)) return rc;
+    if (epi->dropout_p > 0.f) return lpgnn_dropout(out, (int64_t)M * N, dtype, epi->dropout_p, epi->dropout_seed, stream);
+    return LPGNN_OK;
+  }
+  LPGNN_REQUIRE(M >= 0 && N > 0 && K1 > 0 && K2 >= 0, "node_transform_ex: bad shape M=%d N=%d K1=%d K2=%d", M, N, K1, K2);
+  if (M == 0) return LPGNN_OK;
+  LPGNN_REQUIRE(A1 && W1 && out, "node_transform_ex: null pointer");
+  LPGNN_REQUIRE(K2 == 0 || (A2 && W2), "node_transform_ex: K2=%d but A2/W2 is null", K2);
+  LPGNN_REQUIRE(!epi->mask_act || (uintptr_t)epi->mask_act % 16 == 0, "node_transform_ex: mask_act must be 16-byte aligned");
+  if (K2 == 0) { A2 = nullptr; W2 = nullptr; }
+  EpiX epx;
+  epx.mask_act = epi->mask_act;
+  epx.out_scale = mscale;
+  if (epi->dropout_p > 0.f) {
+    epx.drop_threshold = (uint32_t)((double)epi->dropout_p * 4294967296.0);
+    epx.drop_seed = epi->dropout_seed;
+    epx.out_scale *= 1.f / (1.f - epi->dropout_p);
+  }
+  return node_transform_bf16(A1, K1, W1, A2, K2, W2, bias, M, N, out, 0, (epi->epilogue & LPGNN_EPI_RELU) ? 1 : 0, nullptr,
+                             nullptr, 1, (cudaStream_t)stream, epx);
 }
 
 // two partial slices per column tile (the tile's columns are drained by two warps per row)

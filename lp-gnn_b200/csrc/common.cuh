@@ -42,6 +42,29 @@ void count_launches(int n);  // kernels enqueued by the library (lpgnn_launch_co
     }                                                                                    \
   } while (0)
 
+// Optional extras of the tensor-core transform's epilogue (bf16 output only): out = keep ? epi(acc + bias) * out_scale : 0
+// with keep = (mask_act > 0) [backward of relu / dropout] and/or the inverted-dropout hash of (seed, element index).
+struct EpiX {
+  const void* mask_act = nullptr;   // bf16 [M,N], same layout as out
+  float out_scale = 1.f;
+  uint32_t drop_threshold = 0;      // P(drop) = threshold / 2^32
+  uint64_t drop_seed = 0;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t hash_u64(uint64_t x) {  // splitmix64 finaliser, top 32 bits
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return (uint32_t)(x >> 32);
+}
+// keep-decision of lpgnn_dropout for element `idx` (shared by the stand-alone kernel and the fused epilogue)
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, uint32_t threshold) {
+  return hash_u64(seed ^ idx * 0xD6E8FEB86659FD93ull) >= threshold;
+}
+#endif
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

@@ -55,13 +55,20 @@ struct Segs {
   int count;
 };
 
+// 0xffff per 16-bit lane whose bf16 value is > 0 (positive, non-zero), else 0
+__device__ __forceinline__ uint32_t bf16x2_pos_mask(uint32_t a) {
+  const uint32_t lo = ((a & 0x8000u) == 0u && (a & 0x7fffu) != 0u) ? 0x0000ffffu : 0u;
+  const uint32_t hi = ((a & 0x80000000u) == 0u && (a & 0x7fff0000u) != 0u) ? 0xffff0000u : 0u;
+  return lo | hi;
+}
+
 // kMN = true: both operands are MN-major (out = A^T B with A [Kred, M], B [Kred, N] row-major; the weight gradient
 // dW = dY^T X without materialising any transpose): segment 0's maps describe A and B with 64 x 64 boxes.
 template <int BN, typename OutT, bool kMN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias, OutT* __restrict__ out, int M, int N,
                int relu, const float* __restrict__ head_w /*[3,N] or null*/,
-               float* __restrict__ head_partial /*[N/BN][M][3] or null*/, int ksplit) {
+               float* __restrict__ head_partial /*[N/BN][M][3] or null*/, int ksplit, const EpiX epx) {
   using C = Cfg<BN, OutT>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle atoms
@@ -217,6 +224,7 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
             float v0 = __uint_as_float(r[2 * j]) + bias_s[pc * 32 + 2 * j];
             float v1 = __uint_as_float(r[2 * j + 1]) + bias_s[pc * 32 + 2 * j + 1];
             if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            v0 *= epx.out_scale; v1 *= epx.out_scale;
             packed[j] = pack_bf16(v0, v1);
             if (head_w) {
               const int col = pc * 32 + 2 * j;
@@ -247,10 +255,29 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
         for (int i = 0; i < 32 / kRowsPerInstr; ++i) {
           const int rr = kRowsPerInstr * i + sub_row;
           const int rsw = (sizeof(OutT) == 2) ? ((rr >> 1) & 3) : (rr & 7);
-          const uint4 v = *reinterpret_cast<const uint4*>(my_stage + rr * C::kRowBytes + ((piece ^ rsw) * 16));
+          uint4 v = *reinterpret_cast<const uint4*>(my_stage + rr * C::kRowBytes + ((piece ^ rsw) * 16));
           const int64_t grow = row_base + rr;
           if (grow < M) {
-            uint8_t* dst = reinterpret_cast<uint8_t*>(out_t + grow * N + (int64_t)n_blk * BN + pc * 32);
+            const int64_t e0 = grow * N + (int64_t)n_blk * BN + pc * 32;   // first element of this row piece
+            if constexpr (sizeof(OutT) == 2) {
+              // keep-masks act on whole bf16 lanes of the 16-byte chunk this thread stores (elements e0 + piece*8 ..)
+              if (epx.mask_act) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(
+                    reinterpret_cast<const uint8_t*>(epx.mask_act) + (e0 * 2 + piece * 16)));
+                v.x &= bf16x2_pos_mask(a.x); v.y &= bf16x2_pos_mask(a.y);
+                v.z &= bf16x2_pos_mask(a.z); v.w &= bf16x2_pos_mask(a.w);
+              }
+              if (epx.drop_threshold) {
+                const uint64_t i0 = (uint64_t)(e0 + piece * 8);
+                auto keep2 = [&](int k) -> uint32_t {
+                  const uint32_t lo = dropout_keep(epx.drop_seed, i0 + 2 * k, epx.drop_threshold) ? 0x0000ffffu : 0u;
+                  const uint32_t hi = dropout_keep(epx.drop_seed, i0 + 2 * k + 1, epx.drop_threshold) ? 0xffff0000u : 0u;
+                  return lo | hi;
+                };
+                v.x &= keep2(0); v.y &= keep2(1); v.z &= keep2(2); v.w &= keep2(3);
+              }
+            }
+            uint8_t* dst = reinterpret_cast<uint8_t*>(out_t + e0);
             *reinterpret_cast<uint4*>(dst + piece * 16) = v;
           }
         }
@@ -308,7 +335,7 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int bo
 
 template <int BN, typename OutT, bool kMN = false>
 int launch(const Segs& segs, const float* bias, void* out, int M, int N, int relu, const float* head_w,
-           float* head_partial, int ksplit, cudaStream_t st) {
+           float* head_partial, int ksplit, cudaStream_t st, const EpiX& epx = EpiX()) {
   using C = Cfg<BN, OutT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -319,7 +346,7 @@ int launch(const Segs& segs, const float* bias, void* out, int M, int N, int rel
   const int tiles = ceil_div(M, BM) * (N / BN) * ksplit;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   gemm_tc_kernel<BN, OutT, kMN><<<grid, kThreads, C::kSmemBytes, st>>>(segs, bias, reinterpret_cast<OutT*>(out), M, N, relu,
-                                                                  head_w, head_partial, ksplit);
+                                                                  head_w, head_partial, ksplit, epx);
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;
@@ -329,7 +356,10 @@ int launch(const Segs& segs, const float* bias, void* out, int M, int N, int rel
 
 // out[M,N] = epi( sum_i A_i[M,K_i] * W_i[N,K_i]^T + bias ) over nseg <= 12 bf16 operand pairs.
 int gemm_tc_run(const void* const* A, const void* const* W, const int* K, int nseg, const float* bias, int M, int N,
-                void* out, int out_f32, int relu, const float* head_w, float* head_partial, int ksplit, cudaStream_t st) {
+                void* out, int out_f32, int relu, const float* head_w, float* head_partial, int ksplit, cudaStream_t st,
+                const EpiX& epx) {
+  LPGNN_REQUIRE(!(out_f32 || !out) || (!epx.mask_act && !epx.drop_threshold && epx.out_scale == 1.f),
+                "node_transform(bf16): mask / dropout epilogues need a bf16 output");
   LPGNN_REQUIRE(nseg >= 1 && nseg <= kMaxSegs, "gemm_tc: %d operand pairs (max %d)", nseg, kMaxSegs);
   LPGNN_REQUIRE(N % 64 == 0, "node_transform(bf16): N=%d must be a multiple of 64", N);
   LPGNN_REQUIRE((uintptr_t)out % 16 == 0, "node_transform(bf16): out must be 16-byte aligned");
@@ -351,7 +381,7 @@ int gemm_tc_run(const void* const* A, const void* const* W, const int* K, int ns
   segs.count = nseg;
   LPGNN_REQUIRE(ksplit >= 1 && (ksplit == 1 || (out_f32 && !bias && !relu && !head_w && ksplit <= kb)),
                 "node_transform(bf16): split-K needs fp32 partial outputs, no epilogue, and ksplit <= K/64");
-#define LPGNN_GO(BNV, T) return launch<BNV, T>(segs, bias, out, M, N, relu, head_w, head_partial, ksplit, st)
+#define LPGNN_GO(BNV, T) return launch<BNV, T>(segs, bias, out, M, N, relu, head_w, head_partial, ksplit, st, epx)
   if (out_f32) {
     if (BN == 256) LPGNN_GO(256, float);
     if (BN == 128) LPGNN_GO(128, float);
@@ -397,12 +427,12 @@ int gemm_tc_mn(const void* A, const void* B, int64_t Kred, int M, int N, void* o
 
 int node_transform_bf16(const void* A1, int K1, const void* W1, const void* A2, int K2, const void* W2,
                         const float* bias, int M, int N, void* out, int out_f32, int relu, const float* head_w,
-                        float* head_partial, int ksplit, cudaStream_t st) {
+                        float* head_partial, int ksplit, cudaStream_t st, const EpiX& epx) {
   const void* A[2] = {A1, A2};
   const void* W[2] = {W1, W2};
   const int K[2] = {K1, K2};
   const int nseg = (A2 != nullptr && K2 > 0) ? 2 : 1;
-  return gemm_tc_run(A, W, K, nseg, bias, M, N, out, out_f32, relu, head_w, head_partial, ksplit, st);
+  return gemm_tc_run(A, W, K, nseg, bias, M, N, out, out_f32, relu, head_w, head_partial, ksplit, st, epx);
 }
 
 }  // namespace lpgnn

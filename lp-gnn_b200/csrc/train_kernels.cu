@@ -65,14 +65,6 @@ relu_bwd_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, const 
 }
 
 // ------------------------------------------------------------------------------------------- dropout
-__device__ __forceinline__ uint32_t hash_u64(uint64_t x) {  // splitmix64 finaliser, top 32 bits
-  x += 0x9E3779B97F4A7C15ull;
-  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-  x ^= x >> 31;
-  return (uint32_t)(x >> 32);
-}
-
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 dropout_kernel(uint4* __restrict__ x, int64_t chunks, uint32_t threshold, float scale, uint64_t seed) {
@@ -82,8 +74,7 @@ dropout_kernel(uint4* __restrict__ x, int64_t chunks, uint32_t threshold, float 
     Vec16<T>::unpack(x[i], v);
 #pragma unroll
     for (int k = 0; k < E; ++k) {
-      const uint32_t h = hash_u64(seed ^ (uint64_t)(i * E + k) * 0xD6E8FEB86659FD93ull);
-      v[k] = (h >= threshold) ? v[k] * scale : 0.f;  // P(drop) = threshold / 2^32 = p
+      v[k] = dropout_keep(seed, (uint64_t)(i * E + k), threshold) ? v[k] * scale : 0.f;  // P(drop) = threshold / 2^32 = p
     }
     x[i] = Vec16<T>::pack(v);
   }

@@ -36,7 +36,7 @@ struct TB {
   void *agg_s[LPGNN_MAX_HIDDEN_LAYERS], *agg_t[LPGNN_MAX_HIDDEN_LAYERS];
   float *raw_s, *raw_t;
   // backward
-  void *dpre_s, *dpre_t, *dagg_s, *dagg_t, *droot_s, *droot_t, *dlagg, *dragg;
+  void *dpre_s, *dpre_t, *droot_s, *droot_t, *dlagg, *dragg;
   float *draw_s, *draw_t;
   void *drawb_s, *drawb_t;   // bf16 [rows,64] = [draw | 0]
   void *wS[LPGNN_MAX_HIDDEN_LAYERS][4], *wT[LPGNN_MAX_HIDDEN_LAYERS][4];  // compute-dtype weights, straight / transposed
@@ -58,7 +58,6 @@ size_t carve(Bump& b, TB& B, int32_t m, int32_t n, int32_t p, int32_t q, int32_t
   for (int i = 0; i < nh; ++i) { B.agg_s[i] = b.take<char>((size_t)m * H * es); B.agg_t[i] = b.take<char>((size_t)n * H * es); }
   B.raw_s = b.take<float>((size_t)m * 3); B.raw_t = b.take<float>((size_t)n * 3);
   B.dpre_s = b.take<char>((size_t)m * H * es); B.dpre_t = b.take<char>((size_t)n * H * es);
-  B.dagg_s = b.take<char>((size_t)m * H * es); B.dagg_t = b.take<char>((size_t)n * H * es);
   B.droot_s = b.take<char>((size_t)m * H * es); B.droot_t = b.take<char>((size_t)n * H * es);
   B.dlagg = b.take<char>((size_t)m * H * es); B.dragg = b.take<char>((size_t)n * H * es);
   B.draw_s = b.take<float>((size_t)m * 3); B.draw_t = b.take<float>((size_t)n * 3);
@@ -246,14 +245,15 @@ extern "C" int lpgnn_train_forward(const lpgnn_gcn_fc_weights* w, const int32_t*
   for (int li = 0; li < nh; ++li) {
     LPGNN_TRY(lpgnn_spmm(colptr, row_csc, val_csc, n, B.left[li], B.agg_t[li], H, dt, stream));
     LPGNN_TRY(lpgnn_spmm(rowptr, col, val, m, B.right[li], B.agg_s[li], H, dt, stream));
-    LPGNN_TRY(lpgnn_node_transform(B.agg_t[li], H, wl2r_rel[li], B.right[li], H, wl2r_root[li], w->l2r_b[li], n, H,
-                                   B.right[li + 1], dt, dt, LPGNN_EPI_RELU, stream));
-    LPGNN_TRY(lpgnn_node_transform(B.agg_s[li], H, wr2l_rel[li], B.left[li], H, wr2l_root[li], w->r2l_b[li], m, H,
-                                   B.left[li + 1], dt, dt, LPGNN_EPI_RELU, stream));
-    if (dropout_p > 0.f) {  // reference order is dropout then relu_ (arch.py:186-188); the two commute
-      LPGNN_TRY(lpgnn_dropout(B.right[li + 1], (int64_t)n * H, dt, dropout_p, seed + 2 * li, stream));
-      LPGNN_TRY(lpgnn_dropout(B.left[li + 1], (int64_t)m * H, dt, dropout_p, seed + 2 * li + 1, stream));
-    }
+    // reference order is dropout then relu_ (arch.py:186-188); the two commute and both sit in the epilogue
+    lpgnn_epilogue_args ea;
+    ea.epilogue = LPGNN_EPI_RELU; ea.dropout_p = dropout_p; ea.mask_act = nullptr; ea.mask_scale = 1.f;
+    ea.dropout_seed = seed + 2 * li;
+    LPGNN_TRY(lpgnn_node_transform_ex(B.agg_t[li], H, wl2r_rel[li], B.right[li], H, wl2r_root[li], w->l2r_b[li], n, H,
+                                      B.right[li + 1], dt, &ea, stream));
+    ea.dropout_seed = seed + 2 * li + 1;
+    LPGNN_TRY(lpgnn_node_transform_ex(B.agg_s[li], H, wr2l_rel[li], B.left[li], H, wr2l_root[li], w->r2l_b[li], m, H,
+                                      B.left[li + 1], dt, &ea, stream));
   }
   LPGNN_TRY(lpgnn_head_mask(B.left[nh], dt, m, H, w->head_left_w, w->head_left_b, x_s, p, logits_s, B.raw_s, stream));
   LPGNN_TRY(lpgnn_head_mask(B.right[nh], dt, n, H, w->head_right_w, w->head_right_b, x_t, q, logits_t, B.raw_t, stream));
@@ -328,18 +328,19 @@ extern "C" int lpgnn_train_backward(const lpgnn_gcn_fc_weights* w, const int32_t
     }
     LPGNN_TRY(lpgnn_colsum(dpt, dt, n, H, g->l2r_b[li], B.scratch, B.scratch_bytes, stream));
     LPGNN_TRY(lpgnn_colsum(dps, dt, m, H, g->r2l_b[li], B.scratch, B.scratch_bytes, stream));
-    // data gradients: transform with the transposed weights prepared by the forward call
-    LPGNN_TRY(lpgnn_node_transform(dpt, H, B.wT[li][0], nullptr, 0, nullptr, nullptr, n, H, B.dagg_t, dt, dt, LPGNN_EPI_NONE, stream));
-    LPGNN_TRY(lpgnn_node_transform(dpt, H, B.wT[li][1], nullptr, 0, nullptr, nullptr, n, H, B.droot_t, dt, dt, LPGNN_EPI_NONE, stream));
-    LPGNN_TRY(lpgnn_node_transform(dps, H, B.wT[li][2], nullptr, 0, nullptr, nullptr, m, H, B.dagg_s, dt, dt, LPGNN_EPI_NONE, stream));
-    LPGNN_TRY(lpgnn_node_transform(dps, H, B.wT[li][3], nullptr, 0, nullptr, nullptr, m, H, B.droot_s, dt, dt, LPGNN_EPI_NONE, stream));
-    // aggregation backward: agg_t = A^T left  =>  d(left) += A dAgg_t ;  agg_s = A right  =>  d(right) += A^T dAgg_s
-    LPGNN_TRY(lpgnn_spmm(rowptr, col, val, m, B.dagg_t, B.dlagg, H, dt, stream));
-    LPGNN_TRY(lpgnn_spmm(colptr, row_csc, val_csc, n, B.dagg_s, B.dragg, H, dt, stream));
-    const float prev_scale = li > 0 ? scale : 1.f;   // conv1's output has no dropout
-    LPGNN_TRY(lpgnn_relu_bwd(B.droot_s, B.dlagg, B.left[li], (int64_t)m * H, dt, prev_scale, B.droot_s, stream));
-    LPGNN_TRY(lpgnn_relu_bwd(B.droot_t, B.dragg, B.right[li], (int64_t)n * H, dt, prev_scale, B.droot_t, stream));
-    // the masked sums are the next dPre; recycle the old dPre buffers as the next layer's GEMM outputs
+    // data gradients.  dL = A (dPre_t W_rel^{l2r}) + dPre_s W_root^{r2l} = [A dPre_t | dPre_s] [W_rel^{l2r} ; W_root^{r2l}]:
+    // aggregate first, then ONE two-operand transform per side (transposed weights prepared by the forward call)
+    // whose epilogue applies the ReLU / dropout mask of the layer input.
+    LPGNN_TRY(lpgnn_spmm(rowptr, col, val, m, dpt, B.dlagg, H, dt, stream));          // A   dPre_t  [m,H]
+    LPGNN_TRY(lpgnn_spmm(colptr, row_csc, val_csc, n, dps, B.dragg, H, dt, stream));  // A^T dPre_s  [n,H]
+    lpgnn_epilogue_args ea;
+    ea.epilogue = LPGNN_EPI_NONE; ea.dropout_p = 0.f; ea.dropout_seed = 0;
+    ea.mask_scale = li > 0 ? scale : 1.f;   // conv1's output has no dropout
+    ea.mask_act = B.left[li];
+    LPGNN_TRY(lpgnn_node_transform_ex(B.dlagg, H, B.wT[li][0], dps, H, B.wT[li][3], nullptr, m, H, B.droot_s, dt, &ea, stream));
+    ea.mask_act = B.right[li];
+    LPGNN_TRY(lpgnn_node_transform_ex(B.dragg, H, B.wT[li][2], dpt, H, B.wT[li][1], nullptr, n, H, B.droot_t, dt, &ea, stream));
+    // the masked sums are the next dPre; recycle the old dPre buffers as the next layer's outputs
     void* t;
     t = dps; dps = B.droot_s; B.droot_s = t;
     t = dpt; dpt = B.droot_t; B.droot_t = t;

@@ -71,9 +71,11 @@ def gather_cat(view, x_src, x_dst, want_f32=True, want_bf16=False):
     return z32, zb
 
 
-def node_transform(a1, w1, a2=None, w2=None, bias=None, relu=False, out_dtype=None) -> torch.Tensor:
+def node_transform(a1, w1, a2=None, w2=None, bias=None, relu=False, out_dtype=None, dropout=None, mask=None) -> torch.Tensor:
     """``epi(a1 @ w1.T + a2 @ w2.T + bias)``: bf16 operands -> tcgen05 kernel, fp32 -> CUDA-core
-    kernel.  Replaces ``lin_rel(agg) + lin_root(x_dst)`` (+ relu_) (reference arch.py:75-80, 188)."""
+    kernel.  Replaces ``lin_rel(agg) + lin_root(x_dst)`` (+ relu_) (reference arch.py:75-80, 188).
+    Training epilogues (``lpgnn_node_transform_ex``): ``dropout=(p, seed)`` applies inverted dropout to the output,
+    ``mask=(act, scale)`` multiplies it by ``scale * (act > 0)``."""
     require_cuda(a1, w1, a2, w2, bias)
     dt = a1.dtype
     a1, w1 = _contig(a1), _contig(w1)
@@ -91,6 +93,25 @@ def node_transform(a1, w1, a2=None, w2=None, bias=None, relu=False, out_dtype=No
         bias = _contig(bias.float())
     out_dtype = dt if out_dtype is None else out_dtype
     out = torch.empty((M, N), dtype=out_dtype, device=a1.device)
+    if (dropout is not None and dropout[0] > 0) or mask is not None:
+        import ctypes as C
+        if out_dtype != dt:
+            raise TypeError("node_transform: dropout / mask epilogues write the operand dtype")
+        epi = _lib.EpilogueArgs()
+        epi.epilogue = EPI_RELU if relu else EPI_NONE
+        if dropout is not None:
+            epi.dropout_p, epi.dropout_seed = float(dropout[0]), int(dropout[1])
+        if mask is not None:
+            act = mask[0]
+            require_cuda(act)
+            if act.shape != out.shape or act.dtype != dt or not act.is_contiguous():
+                raise ValueError("node_transform: mask activation must be a contiguous tensor of the output's shape and dtype")
+            epi.mask_act, epi.mask_scale = act.data_ptr(), float(mask[1])
+        with torch.cuda.device(a1.device):
+            rc = _lib.load().lpgnn_node_transform_ex(a1.data_ptr(), K1, w1.data_ptr(), ptr(a2), K2, ptr(w2), ptr(bias), M, N,
+                                                     out.data_ptr(), dtype_code(dt), C.byref(epi), stream_ptr())
+        check(rc, "lpgnn_node_transform_ex")
+        return out
     with torch.cuda.device(a1.device):
         rc = _lib.load().lpgnn_node_transform(a1.data_ptr(), K1, w1.data_ptr(), ptr(a2), K2, ptr(w2), ptr(bias), M, N,
                                               out.data_ptr(), dtype_code(dt), dtype_code(out_dtype),

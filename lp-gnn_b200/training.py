@@ -10,8 +10,8 @@ Backward algebra for one GraphConvTwoDirection layer (reference arch.py:65-81; A
     L' = relu(drop(S W_rel^{r2l T} + L W_root^{r2l T} + b)),  S = A  R        (constraints)
     dPre_t = dR' * mask(R'), dPre_s = dL' * mask(L')                         -> ops.relu_bwd / head_mask_bwd
     dW_rel^{l2r} = dPre_t^T T, dW_root^{l2r} = dPre_t^T R, db = colsum(dPre_t)   -> transposes + GEMM / colsum
-    dL = dPre_s W_root^{r2l} + A   (dPre_t W_rel^{l2r})                       -> GEMM + ops.spmm(csr)
-    dR = dPre_t W_root^{l2r} + A^T (dPre_s W_rel^{r2l})                       -> GEMM + ops.spmm(csc)
+    dL = (dPre_s W_root^{r2l} + (A   dPre_t) W_rel^{l2r}) * mask(L)          -> ops.spmm(csr) + two-operand GEMM
+    dR = (dPre_t W_root^{l2r} + (A^T dPre_s) W_rel^{r2l}) * mask(R)          -> ops.spmm(csc) + two-operand GEMM
 Everything is atomics-free, so a step is bit-reproducible.
 """
 from __future__ import annotations
@@ -72,12 +72,14 @@ class _GCNFCFunction(torch.autograd.Function):
         for i in range(n_layers):
             w = P[6 + 6 * i: 12 + 6 * i]
             agg_t, agg_s = ops.spmm(csc, left), ops.spmm(csr, right)
-            right_new = ops.node_transform(agg_t, cast(w[0]), right, cast(w[2]), w[1], relu=True)
-            left_new = ops.node_transform(agg_s, cast(w[3]), left, cast(w[5]), w[4], relu=True)
-            if training and dp > 0:
-                # reference order is dropout then relu_ (arch.py:186-188); relu(drop(x)) == drop(relu(x))
-                ops.dropout_(right_new, dp, seed + 2 * i)
-                ops.dropout_(left_new, dp, seed + 2 * i + 1)
+            # reference order is dropout then relu_ (arch.py:186-188); relu(drop(x)) == drop(relu(x)), and both are
+            # fused into the transform's epilogue
+            drop = training and dp > 0
+            right_new = ops.node_transform(agg_t, cast(w[0]), right, cast(w[2]), w[1], relu=True,
+                                           dropout=(dp, seed + 2 * i) if drop else None)
+            left_new = ops.node_transform(agg_s, cast(w[3]), left, cast(w[5]), w[4], relu=True,
+                                          dropout=(dp, seed + 2 * i + 1) if drop else None)
+            if drop:
                 scale = 1.0 / (1.0 - dp)
             saved += [agg_s, agg_t, left_new, right_new]
             left, right = left_new, right_new
@@ -141,15 +143,15 @@ class _GCNFCFunction(torch.autograd.Function):
             # data gradients (weights transposed once per step: [K,N] K-major for the TN kernel)
             w_rel_l2r_t, w_root_l2r_t = cast(w[0]).t().contiguous(), cast(w[2]).t().contiguous()
             w_rel_r2l_t, w_root_r2l_t = cast(w[3]).t().contiguous(), cast(w[5]).t().contiguous()
-            d_agg_t = ops.node_transform(d_pre_t, w_rel_l2r_t)          # [n,H]
-            d_right_root = ops.node_transform(d_pre_t, w_root_l2r_t)    # [n,H]
-            d_agg_s = ops.node_transform(d_pre_s, w_rel_r2l_t)          # [m,H]
-            d_left_root = ops.node_transform(d_pre_s, w_root_r2l_t)     # [m,H]
-            d_left_agg = ops.spmm(csr, d_agg_t)                         # A   . dAgg_t  [m,H]
-            d_right_agg = ops.spmm(csc, d_agg_s)                        # A^T . dAgg_s  [n,H]
+            # dL = A (dPre_t W_rel^{l2r}) + dPre_s W_root^{r2l} = [A dPre_t | dPre_s] [W_rel^{l2r} ; W_root^{r2l}]: aggregate
+            # first, then ONE two-operand transform per side (the forward kernel) whose epilogue applies the
+            # ReLU / dropout mask of the layer input -- no separate sum / mask pass over the activations
+            a_dpre_t = ops.spmm(csr, d_pre_t)                           # A   . dPre_t  [m,H]
+            at_dpre_s = ops.spmm(csc, d_pre_s)                          # A^T . dPre_s  [n,H]
             prev_scale = ctx.scale if i > 0 else 1.0                    # conv1 output has no dropout
-            d_pre_s = ops.relu_bwd(d_left_root, d_left_agg, left_in, prev_scale, out=d_left_root)
-            d_pre_t = ops.relu_bwd(d_right_root, d_right_agg, right_in, prev_scale, out=d_right_root)
+            d_pre_s, d_pre_t = (
+                ops.node_transform(a_dpre_t, w_rel_l2r_t, d_pre_s, w_root_r2l_t, mask=(left_in, prev_scale)),
+                ops.node_transform(at_dpre_s, w_rel_r2l_t, d_pre_t, w_root_l2r_t, mask=(right_in, prev_scale)))
         # ---- conv1: weight gradients only (inputs are data)
         k_s, k_t = x_s.shape[1], x_t.shape[1]
         K = k_s + k_t

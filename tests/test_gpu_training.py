@@ -127,6 +127,50 @@ def test_native_step_rejects_second_backward(cuda):
 
 
 # ------------------------------------------------------------------------------------------- kernel units
+@pytest.mark.parametrize("M,N,K", [(1000, 256, 128), (4097, 1024, 1024), (300, 64, 64)])
+def test_transform_epilogue_dropout_and_mask_bf16(cuda, M, N, K):
+    """Fused keep-masks of the tensor-core transform == fp32-output transform + torch scale/mask, rounded once; the
+    dropout pattern is exactly lpgnn_dropout's."""
+    from lpgnn_b200 import ops
+    gen = torch.Generator(device="cpu").manual_seed(M + N)
+    bf = torch.bfloat16
+    a1, a2 = torch.randn(M, K, generator=gen).to(cuda).to(bf), torch.randn(M, K, generator=gen).to(cuda).to(bf)
+    w1, w2 = (torch.randn(N, K, generator=gen) / K ** 0.5).to(cuda).to(bf), (torch.randn(N, K, generator=gen) / K ** 0.5).to(cuda).to(bf)
+    bias = torch.randn(N, generator=gen).to(cuda)
+    ref32 = ops.node_transform(a1, w1, a2, w2, bias, relu=True, out_dtype=torch.float32)
+    p, seed = 0.25, 123456789
+    keep = torch.ones(M, N, device=cuda, dtype=bf)
+    ops.dropout_(keep, p, seed)
+    keep = keep > 0
+    assert abs(keep.float().mean().item() - (1 - p)) < 0.01
+    got = ops.node_transform(a1, w1, a2, w2, bias, relu=True, dropout=(p, seed))
+    want = (ref32 * torch.tensor(1.0 / (1.0 - p), dtype=torch.float32, device=cuda)).to(bf) * keep
+    assert torch.equal(got, want)
+    # backward-style mask: no bias, no relu, scale * (act > 0)
+    act = torch.relu(torch.randn(M, N, generator=gen)).to(cuda).to(bf)
+    ref32 = ops.node_transform(a1, w1, a2, w2, out_dtype=torch.float32)
+    got = ops.node_transform(a1, w1, a2, w2, mask=(act, 1.25))
+    want = (ref32 * 1.25).to(bf) * (act > 0)
+    assert torch.equal(got, want)
+    # both at once
+    got = ops.node_transform(a1, w1, None, None, bias, relu=True, dropout=(p, seed), mask=(act, 2.0))
+    ref32 = ops.node_transform(a1, w1, None, None, bias, relu=True, out_dtype=torch.float32)
+    want = (ref32 * (torch.tensor(2.0, device=cuda) * torch.tensor(1.0 / (1.0 - p), dtype=torch.float32, device=cuda))).to(bf) * keep * (act > 0)
+    assert torch.equal(got, want)
+
+
+def test_transform_epilogue_fp32_matches_separate_kernels(cuda):
+    from lpgnn_b200 import ops
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    M, N, K = 777, 64, 64
+    a, w = torch.randn(M, K, generator=gen).to(cuda), torch.randn(N, K, generator=gen).to(cuda)
+    act = torch.relu(torch.randn(M, N, generator=gen)).to(cuda)
+    got = ops.node_transform(a, w, relu=True, dropout=(0.5, 77), mask=(act, 1.5))
+    ref = ops.node_transform(a, w, relu=True)
+    ref = ops.relu_bwd(ref, None, act, 1.5)
+    ops.dropout_(ref, 0.5, 77)
+    assert torch.equal(got, ref)
+
 def test_bf16_operands_of_the_narrow_weight_gradients(cuda):
     """gather_cat's bf16 output carries a ones column after the features (bias gradient through the tensor-core
     weight gradient); head_mask_bwd's bf16 draw is [draw | 0]; wgrad over them matches fp32 matmuls."""
