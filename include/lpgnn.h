@@ -406,6 +406,19 @@ LPGNN_API int lpgnn_train_backward(const lpgnn_gcn_fc_weights* w, const int32_t*
                          const lpgnn_gcn_fc_grads* grads, void* workspace, size_t workspace_bytes,
                          lpgnn_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (f-3) Balanced cross-entropy of the training loop, value and gradient in one pass.  Replaces balanced()
+ * (reference train.py:39-46) = (m+n)/m * CE_w(logits_cons, y_s) + (m+n)/n * CE_w(logits_vars, y_t) with the
+ * inverse-frequency class weights of labels_to_balanced_weights (utils.py:286-299; merge_lu averages the
+ * lower / upper weights unless exactly two classes occur) and CrossEntropyLoss(weight=w) (weighted mean).
+ * logits [rows,3] f32, labels int64 in {0,1,2} (other values are ignored, weight 0); loss_out: 1 float
+ * (device); dlogits_* (optional, both or neither, f32 [rows,3]) = d loss / d logits.  Deterministic.
+ * ------------------------------------------------------------------------------------------- */
+LPGNN_API size_t lpgnn_balanced_ce_workspace_bytes(int32_t m, int32_t n);
+LPGNN_API int lpgnn_balanced_ce(const float* logits_s, const int64_t* y_s, int32_t m, const float* logits_t,
+                      const int64_t* y_t, int32_t n, int merge_lu, float* loss_out, float* dlogits_s,
+                      float* dlogits_t, void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

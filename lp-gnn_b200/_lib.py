@@ -95,6 +95,8 @@ SIGNATURES = {
                                    _p, _p, _p, _sz, _p]),
     "lpgnn_train_backward": (_int, [C.POINTER(GcnFcWeights), _p, _p, _p, _p, _p, _p, _i32, _i32, C.c_float, _p, _p,
                                     C.POINTER(GcnFcGrads), _p, _sz, _p]),
+    "lpgnn_balanced_ce_workspace_bytes": (_sz, [_i32, _i32]),
+    "lpgnn_balanced_ce": (_int, [_p, _p, _i32, _p, _p, _i32, _int, _p, _p, _p, _p, _sz, _p]),
     "lpgnn_basis_select_workspace_bytes": (_sz, [_i64]),
     "lpgnn_basis_select": (_int, [_p, _i32, _p, _i32, _i32, _p, _int, _p, _p, _sz, _p]),
 }

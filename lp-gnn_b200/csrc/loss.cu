@@ -1,0 +1,162 @@
+// Balanced cross-entropy of the reference's training loop, forward value and d(loss)/d(logits) in one pass.
+//
+// Replaces balanced() (reference train.py:39-46) with the class weights of labels_to_balanced_weights
+// (utils.py:286-299) and torch.nn.CrossEntropyLoss(weight=...) (weighted mean):
+//   w_side[c]  = total / cnt[c] for the classes that occur (0 otherwise); unless exactly two classes occur and with
+//                merge_lu, w[0] = w[2] = (w[0] + w[2]) / 2
+//   CE_side    = sum_i w[y_i] * (-log softmax(x_i)[y_i]) / sum_i w[y_i]
+//   loss       = (m+n)/m * CE_cons + (m+n)/n * CE_vars
+//   dlogits[i] = coef_side * w[y_i] / sum_j w[y_j] * (softmax(x_i) - onehot(y_i))
+// ~30 framework launches (unique, where, log_softmax, nll_loss, ... and their backward) become 2 kernels + 1 memset.
+// Integer atomics only (class counts, block counter); floating-point sums run in a fixed order: bit-reproducible.
+#include "common.cuh"
+
+namespace lpgnn {
+namespace {
+
+constexpr int kThreads = 256;
+
+struct CeWs {
+  int cnt[2][4];          // class counts per side (3 used)
+  unsigned int done;      // blocks finished (last-block reduction)
+  unsigned int pad[7];
+};
+
+__global__ void __launch_bounds__(kThreads)
+ce_count_kernel(const int64_t* __restrict__ y_s, int m, const int64_t* __restrict__ y_t, int n, int blocks_s, CeWs* ws) {
+  __shared__ int c[3];
+  if (threadIdx.x < 3) c[threadIdx.x] = 0;
+  __syncthreads();
+  const int side = blockIdx.x >= blocks_s;
+  const int64_t* y = side ? y_t : y_s;
+  const int rows = side ? n : m;
+  const int i = (blockIdx.x - (side ? blocks_s : 0)) * kThreads + threadIdx.x;
+  if (i < rows) {
+    const int64_t l = y[i];
+    if (l >= 0 && l < 3) atomicAdd(&c[(int)l], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 && c[threadIdx.x]) atomicAdd(&ws->cnt[side][threadIdx.x], c[threadIdx.x]);
+}
+
+__device__ __forceinline__ void class_weights(const int* cnt, int merge_lu, float* w, float* denom) {
+  const int total = cnt[0] + cnt[1] + cnt[2];
+  int present = 0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    w[c] = cnt[c] > 0 ? (float)total / (float)cnt[c] : 0.f;
+    present += cnt[c] > 0;
+  }
+  if (merge_lu && present != 2) w[0] = w[2] = (w[0] + w[2]) / 2.f;
+  *denom = (float)cnt[0] * w[0] + (float)cnt[1] * w[1] + (float)cnt[2] * w[2];   // = sum_i w[y_i]
+}
+
+__global__ void __launch_bounds__(kThreads)
+ce_loss_kernel(const float* __restrict__ x_s, const int64_t* __restrict__ y_s, int m, const float* __restrict__ x_t,
+               const int64_t* __restrict__ y_t, int n, int blocks_s, int merge_lu, CeWs* ws, float* __restrict__ partials,
+               float* __restrict__ d_s, float* __restrict__ d_t, float* __restrict__ loss_out) {
+  const int side = blockIdx.x >= blocks_s;
+  const float* x = side ? x_t : x_s;
+  const int64_t* y = side ? y_t : y_s;
+  float* d = side ? d_t : d_s;
+  const int rows = side ? n : m;
+  float w[3], denom;
+  class_weights(ws->cnt[side], merge_lu, w, &denom);
+  const float coef = (float)(m + n) / (float)rows;
+  const int i = (blockIdx.x - (side ? blocks_s : 0)) * kThreads + threadIdx.x;
+  float part = 0.f;
+  if (i < rows) {
+    const float a = x[3 * (int64_t)i], b = x[3 * (int64_t)i + 1], c = x[3 * (int64_t)i + 2];
+    const float mx = fmaxf(a, fmaxf(b, c));
+    const float ea = expf(a - mx), eb = expf(b - mx), ec = expf(c - mx);
+    const float se = ea + eb + ec;
+    const float lse = mx + logf(se);
+    const int64_t l = y[i];
+    const bool ok = l >= 0 && l < 3;
+    const float wi = ok ? w[(int)l] : 0.f;
+    const float xl = l == 0 ? a : (l == 1 ? b : c);
+    part = ok ? wi * (lse - xl) : 0.f;
+    if (d) {
+      const float g = coef * wi / denom, inv = 1.f / se;
+      d[3 * (int64_t)i] = g * (ea * inv - (l == 0 ? 1.f : 0.f));
+      d[3 * (int64_t)i + 1] = g * (eb * inv - (l == 1 ? 1.f : 0.f));
+      d[3 * (int64_t)i + 2] = g * (ec * inv - (l == 2 ? 1.f : 0.f));
+    }
+  }
+  // block sum, fixed order
+  __shared__ float red[kThreads / 32];
+  __shared__ bool last;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; ++k) s += red[k];
+    partials[blockIdx.x] = s;
+    __threadfence();
+    last = atomicAdd(&ws->done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // last block: both sides' partials summed in index order (double), then the weighted means
+  __shared__ double acc[2][kThreads];
+  for (int sd = 0; sd < 2; ++sd) {
+    const int b0 = sd ? blocks_s : 0, b1 = sd ? (int)gridDim.x : blocks_s;
+    const int per = (b1 - b0 + kThreads - 1) / kThreads;
+    double s = 0.0;
+    for (int k = 0; k < per; ++k) {
+      const int b = b0 + threadIdx.x * per + k;
+      if (b < b1) s += (double)__ldcg(partials + b);
+    }
+    acc[sd][threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double loss = 0.0;
+    for (int sd = 0; sd < 2; ++sd) {
+      double s = 0.0;
+      for (int k = 0; k < kThreads; ++k) s += acc[sd][k];
+      float ww[3], dn;
+      class_weights(ws->cnt[sd], merge_lu, ww, &dn);
+      loss += (double)((float)(m + n) / (float)(sd ? n : m)) * (s / (double)dn);
+    }
+    *loss_out = (float)loss;
+  }
+}
+
+}  // namespace
+}  // namespace lpgnn
+
+using namespace lpgnn;
+
+extern "C" size_t lpgnn_balanced_ce_workspace_bytes(int32_t m, int32_t n) {
+  return sizeof(CeWs) + (size_t)(ceil_div(m, kThreads) + ceil_div(n, kThreads)) * sizeof(float);
+}
+
+extern "C" int lpgnn_balanced_ce(const float* logits_s, const int64_t* y_s, int32_t m, const float* logits_t,
+                                 const int64_t* y_t, int32_t n, int merge_lu, float* loss_out, float* dlogits_s,
+                                 float* dlogits_t, void* workspace, size_t workspace_bytes, lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(m > 0 && n > 0, "balanced_ce: m=%d, n=%d must be positive", m, n);
+  LPGNN_REQUIRE(logits_s && y_s && logits_t && y_t && loss_out && workspace, "balanced_ce: null pointer");
+  LPGNN_REQUIRE((dlogits_s == nullptr) == (dlogits_t == nullptr), "balanced_ce: pass both gradient outputs or neither");
+  LPGNN_REQUIRE((uintptr_t)workspace % 16 == 0, "balanced_ce: workspace must be 16-byte aligned");
+  if (workspace_bytes < lpgnn_balanced_ce_workspace_bytes(m, n)) {
+    set_error("balanced_ce: workspace too small");
+    return LPGNN_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  CeWs* ws = reinterpret_cast<CeWs*>(workspace);
+  float* partials = reinterpret_cast<float*>(ws + 1);
+  const int bs = ceil_div(m, kThreads), bt = ceil_div(n, kThreads);
+  LPGNN_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(CeWs), st));
+  ce_count_kernel<<<bs + bt, kThreads, 0, st>>>(y_s, m, y_t, n, bs, ws);
+  ce_loss_kernel<<<bs + bt, kThreads, 0, st>>>(logits_s, y_s, m, logits_t, y_t, n, bs, merge_lu, ws, partials, dlogits_s,
+                                              dlogits_t, loss_out);
+  LPGNN_LAUNCH_OK();
+  count_launches(2);
+  return LPGNN_OK;
+}

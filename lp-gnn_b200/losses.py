@@ -45,11 +45,51 @@ def unbalanced(logpr_cons, logpr_vars, y_s, y_t):
     return F.cross_entropy(torch.cat((logpr_cons, logpr_vars), dim=0), torch.cat((y_s, y_t), dim=0))
 
 
-def balanced(logpr_cons, logpr_vars, y_s, y_t):
+def balanced_torch(logpr_cons, logpr_vars, y_s, y_t):
+    """balanced() spelled with framework ops, as the reference does (train.py:39-46): CPU tensors and the tests."""
     m, n = len(y_s), len(y_t)
     loss = (m + n) / m * F.cross_entropy(logpr_cons, y_s, weight=labels_to_balanced_weights(y_s))
     loss = loss + (m + n) / n * F.cross_entropy(logpr_vars, y_t, weight=labels_to_balanced_weights(y_t))
     return loss
+
+
+class _BalancedCE(torch.autograd.Function):
+    """``lpgnn_balanced_ce``: the loss value and d(loss)/d(logits) from two kernels."""
+
+    @staticmethod
+    def forward(ctx, logit_s, logit_t, y_s, y_t):
+        from . import _lib
+        lib = _lib.load()
+        logit_s, logit_t = logit_s.contiguous(), logit_t.contiguous()
+        y_s, y_t = y_s.contiguous(), y_t.contiguous()
+        m, n = logit_s.shape[0], logit_t.shape[0]
+        dev = logit_s.device
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        d = torch.empty((m + n, 3), dtype=torch.float32, device=dev) if need else None
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        ws_bytes = lib.lpgnn_balanced_ce_workspace_bytes(m, n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.lpgnn_balanced_ce(logit_s.data_ptr(), y_s.data_ptr(), m, logit_t.data_ptr(), y_t.data_ptr(), n, 1,
+                                       loss.data_ptr(), _lib.ptr(d), d[m:].data_ptr() if need else None, ws.data_ptr(),
+                                       ws_bytes, _lib.stream_ptr())
+        _lib.check(rc, "lpgnn_balanced_ce")
+        ctx.d, ctx.m = d, m
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        d = ctx.d * g                       # one small [m+n,3] kernel; g is the scalar upstream gradient
+        return d[:ctx.m], d[ctx.m:], None, None
+
+
+def balanced(logpr_cons, logpr_vars, y_s, y_t):
+    """train.py:39-46.  CUDA fp32 logits with int64 labels take the fused kernel; anything else the framework ops."""
+    if (logpr_cons.is_cuda and logpr_vars.is_cuda and logpr_cons.dtype == torch.float32 and logpr_vars.dtype == torch.float32
+            and y_s.dtype == torch.int64 and y_t.dtype == torch.int64 and len(y_s) > 0 and len(y_t) > 0
+            and logpr_cons.shape[1] == 3 and logpr_vars.shape[1] == 3):
+        return _BalancedCE.apply(logpr_cons, logpr_vars, y_s, y_t)
+    return balanced_torch(logpr_cons, logpr_vars, y_s, y_t)
 
 
 def focal(logpr_cons, logpr_vars, y_s, y_t):

@@ -127,6 +127,33 @@ def test_native_step_rejects_second_backward(cuda):
 
 
 # ------------------------------------------------------------------------------------------- kernel units
+@pytest.mark.parametrize("classes_s,classes_t", [((0, 1, 2), (0, 1, 2)), ((0, 1), (1, 2)), ((1,), (0, 1, 2)), ((0, 2), (0,)),
+                                                 ((0, 1, 2), (1,))])
+@pytest.mark.parametrize("m,n", [(5, 7), (1000, 2000), (50_000, 100_001)])
+def test_fused_balanced_ce_matches_framework_ops(cuda, classes_s, classes_t, m, n):
+    """lpgnn_balanced_ce == reference balanced() (train.py:39-46) spelled with torch ops, value and gradient, for every
+    class-presence pattern of labels_to_balanced_weights (utils.py:286-299)."""
+    from lpgnn_b200 import losses
+    gen = torch.Generator(device="cpu").manual_seed(m * 31 + n)
+    ys = torch.tensor(classes_s)[torch.randint(0, len(classes_s), (m,), generator=gen)]
+    yt = torch.tensor(classes_t)[torch.randint(0, len(classes_t), (n,), generator=gen)]
+    ys[:len(classes_s)] = torch.tensor(classes_s)                     # every listed class occurs
+    yt[:len(classes_t)] = torch.tensor(classes_t)
+    ls = (torch.randn(m, 3, generator=gen) * 6).to(cuda).requires_grad_()
+    lt = (torch.randn(n, 3, generator=gen) * 6).to(cuda).requires_grad_()
+    ys, yt = ys.to(cuda), yt.to(cuda)
+    ref = losses.balanced_torch(ls, lt, ys, yt)
+    gs_ref, gt_ref = torch.autograd.grad(ref, (ls, lt))
+    got = losses.balanced(ls, lt, ys, yt)
+    assert type(got.grad_fn).__name__.startswith("_BalancedCE")
+    gs, gt = torch.autograd.grad(got * 1.0, (ls, lt))
+    assert abs(got.item() - ref.item()) <= 2e-6 * max(1.0, abs(ref.item()))
+    for a, b in ((gs, gs_ref), (gt, gt_ref)):
+        assert (a - b).abs().max().item() <= 1e-5 * max(b.abs().max().item(), 1e-12) + 1e-12
+    got2 = losses.balanced(ls, lt, ys, yt)
+    assert torch.equal(got, got2)                                    # fixed summation order
+
+
 @pytest.mark.parametrize("M,N,K", [(1000, 256, 128), (4097, 1024, 1024), (300, 64, 64)])
 def test_transform_epilogue_dropout_and_mask_bf16(cuda, M, N, K):
     """Fused keep-masks of the tensor-core transform == fp32-output transform + torch scale/mask, rounded once; the
