@@ -137,10 +137,10 @@ __device__ __forceinline__ float2 load2(const __nv_bfloat16* p) {
 template <typename T, int KMAX>
 __global__ void __launch_bounds__(kThreads)
 small_wgrad_partial_kernel(const T* __restrict__ dY, const float* __restrict__ Z, int ldz, int K, int64_t M, int N,
-                           float* __restrict__ partial /*[nchunks][N][KMAX+1]*/) {
+                           float* __restrict__ partial /*[nchunks][N][KMAX+1]*/, int chunk_rows) {
   __shared__ __align__(16) float zs[64][KMAX];
   const int c = (blockIdx.x * kThreads + threadIdx.x) * 2;      // N is even (checked on the host)
-  const int64_t r0 = (int64_t)blockIdx.y * kChunkRows, r1 = min(r0 + kChunkRows, M);
+  const int64_t r0 = (int64_t)blockIdx.y * chunk_rows, r1 = min(r0 + chunk_rows, M);
   float2 acc[KMAX];
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) acc[k] = make_float2(0.f, 0.f);
@@ -354,16 +354,28 @@ extern "C" int lpgnn_colsum(const void* X, int dtype, int64_t M, int32_t N, floa
 
 static int wgrad_kmax(int K) { return K <= 4 ? 4 : (K <= 16 ? 16 : (K <= 32 ? 32 : 64)); }
 
+// Rows per partial-sum chunk: 512 for big inputs, down to 64 when that is what it takes to put ~4 blocks on every SM
+// (small LPs would otherwise run a handful of long serial loops).
+static int small_wgrad_chunk_rows(int64_t M, int N) {
+  const int64_t colblocks = ceil_div(N, 2 * kThreads);
+  int64_t rows = (M * colblocks + 4 * sm_count() - 1) / (4 * (int64_t)sm_count());
+  rows = (rows + 63) / 64 * 64;
+  return (int)(rows < 64 ? 64 : (rows > kChunkRows ? kChunkRows : rows));
+}
+
 extern "C" size_t lpgnn_small_wgrad_workspace_bytes(int64_t M, int32_t N, int32_t K) {
-  return (size_t)ceil_div(M > 0 ? M : 1, kChunkRows) * (size_t)N * (wgrad_kmax(K) + 1) * sizeof(float);
+  const int64_t m = M > 0 ? M : 1;
+  (void)check_device();   // the chunking depends on the SM count: make sure it is the device's
+  return (size_t)ceil_div(m, small_wgrad_chunk_rows(m, N)) * (size_t)N * (wgrad_kmax(K) + 1) * sizeof(float);
 }
 
 template <typename T, int KMAX>
 static int small_wgrad_launch(const void* dY, const float* Z, int ldz, int K, int64_t M, int N, float* dW, float* dB,
                               float* partial, cudaStream_t st) {
-  const int nchunks = ceil_div(M, kChunkRows);
+  const int chunk = small_wgrad_chunk_rows(M, N);
+  const int nchunks = ceil_div(M, chunk);
   dim3 grid(ceil_div(N, 2 * kThreads), nchunks);
-  small_wgrad_partial_kernel<T, KMAX><<<grid, kThreads, 0, st>>>((const T*)dY, Z, ldz, K, M, N, partial);
+  small_wgrad_partial_kernel<T, KMAX><<<grid, kThreads, 0, st>>>((const T*)dY, Z, ldz, K, M, N, partial, chunk);
   small_wgrad_reduce_kernel<KMAX><<<ceil_div((int64_t)N * (KMAX + 1), kThreads), kThreads, 0, st>>>(partial, nchunks, N,
                                                                                                     K, dW, dB);
   LPGNN_LAUNCH_OK();

@@ -332,6 +332,6 @@ def smoke_step(dev):
         opt.zero_grad()
         loss.backward()
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert all(np.isfinite(losses)), losses
     print(f"smoke[train]: losses {losses}")
