@@ -113,6 +113,14 @@ LPGNN_API int lpgnn_pack_offsets(int32_t* row, int32_t* col, int64_t nnz, const 
  * ------------------------------------------------------------------------------------------- */
 LPGNN_API int lpgnn_spmm(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,
                const void* X, void* Y, int32_t F, int dtype, lpgnn_stream_t stream);
+/* Same operation with explicit tuning (results are bit-identical for every setting).  Wide feature rows are
+ * aggregated by a banded sweep: one CTA per SM owns one slab of the feature row and a contiguous range of output rows,
+ * so the source rows shared by neighbouring output rows are served from the SM's L1 (see csrc/spmm.cu).
+ * slab_bytes: 512 or 1024 (the row must be a multiple of it); 0 = automatic; -1 = the row-per-warp kernel.
+ * unroll: neighbours gathered in flight per warp, 2 or 4; 0 = automatic. */
+LPGNN_API int lpgnn_spmm_ex(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,
+                  const void* X, void* Y, int32_t F, int dtype, int slab_bytes, int unroll,
+                  lpgnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a2+a3, input layer) Fused aggregation + node transform for narrow inputs (conv1 of GCN_FC:
@@ -418,6 +426,26 @@ LPGNN_API size_t lpgnn_balanced_ce_workspace_bytes(int32_t m, int32_t n);
 LPGNN_API int lpgnn_balanced_ce(const float* logits_s, const int64_t* y_s, int32_t m, const float* logits_t,
                       const int64_t* y_t, int32_t n, int merge_lu, float* loss_out, float* dlogits_s,
                       float* dlogits_t, void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (f-2) LP scaling + node features on the device.  Replaces dataset.scaling (reference dataset.py:23-76,
+ * utils.py:323-332) and dataset.cvt_to_features (dataset.py:79-96, utils.py:335-383), float64 like the
+ * reference: a raw LP  min c^T x, b_l <= A x <= b_u, l <= x <= u  becomes the scaled matrix values of both graph
+ * orientations (fp32, written over val / val_csc of a structure built by lpgnn_graph_build) and the feature
+ * rows x_s [m,8], x_t [n,8] (fp32, layout of SURVEY Appendix A; columns 5 and 7 are the +-inf tags the mask
+ * kernel tests).  a_csr: raw float64 values in canonical CSR order.  The scaled LP is also returned in float64
+ * (a_scaled [nnz] CSR order, c_out [n], bl_out/bu_out [m], l_out/u_out [n]; all required).  Per-row / per-column
+ * sums run in CSR / CSC order with separately rounded multiplies and adds: scaled values and dot products are
+ * bit-identical to the reference's scipy arithmetic; the five vector norms differ from numpy's pairwise sums in
+ * the last bits only.
+ * ------------------------------------------------------------------------------------------- */
+LPGNN_API size_t lpgnn_lp_features_workspace_bytes(int64_t nnz, int32_t m, int32_t n);
+LPGNN_API int lpgnn_lp_features(const int32_t* rowptr, const int32_t* col, const int32_t* colptr, const int32_t* row_csc,
+                      const int32_t* csr2csc, const double* a_csr, const double* c, const double* b_l,
+                      const double* b_u, const double* l, const double* u, int64_t nnz, int32_t m, int32_t n,
+                      float* val, float* val_csc, float* x_s, float* x_t, double* a_scaled, double* c_out,
+                      double* bl_out, double* bu_out, double* l_out, double* u_out, void* workspace,
+                      size_t workspace_bytes, lpgnn_stream_t stream);
 
 #ifdef __cplusplus
 }

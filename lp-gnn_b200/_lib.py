@@ -60,6 +60,7 @@ SIGNATURES = {
     "lpgnn_copy_many_h2d": (_int, [_p, _p, _p, _i32, _p]),
     "lpgnn_pack_offsets": (_int, [_p, _p, _i64, _p, _p, _p, _i32, _p]),
     "lpgnn_spmm": (_int, [_p, _p, _p, _i32, _p, _p, _i32, _int, _p]),
+    "lpgnn_spmm_ex": (_int, [_p, _p, _p, _i32, _p, _p, _i32, _int, _int, _int, _p]),
     "lpgnn_conv_in_zcat_width": (_i32, [_i32, _i32]),
     "lpgnn_gather_cat": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p]),
     "lpgnn_conv_in_fused": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p, _i32, _p, _int, _int, _p, _p]),
@@ -95,6 +96,8 @@ SIGNATURES = {
                                    _p, _p, _p, _sz, _p]),
     "lpgnn_train_backward": (_int, [C.POINTER(GcnFcWeights), _p, _p, _p, _p, _p, _p, _i32, _i32, C.c_float, _p, _p,
                                     C.POINTER(GcnFcGrads), _p, _sz, _p]),
+    "lpgnn_lp_features_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "lpgnn_lp_features": (_int, [_p] * 11 + [_i64, _i32, _i32] + [_p] * 10 + [_p, _sz, _p]),
     "lpgnn_balanced_ce_workspace_bytes": (_sz, [_i32, _i32]),
     "lpgnn_balanced_ce": (_int, [_p, _p, _i32, _p, _p, _i32, _int, _p, _p, _p, _p, _sz, _p]),
     "lpgnn_basis_select_workspace_bytes": (_sz, [_i64]),

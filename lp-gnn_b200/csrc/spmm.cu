@@ -12,6 +12,8 @@
 // UNROLL neighbours in flight per lane.  HBM/L2-bound: see DESIGN.md for the byte model.
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace lpgnn {
 namespace {
 
@@ -112,6 +114,158 @@ spmm_rows_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ id
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Wide features: banded sweep.
+//
+// The row-per-warp kernel above moves the gather-model bytes (z*F*s) from L2 to the SMs; on C2 that is 1 GB per
+// direction at ~11.7 TB/s, the measured L2 throughput cap (ncu: L1 hit rate 8 %), i.e. 0.44 of the HBM roofline.
+// LP matrices are banded in their natural ordering (staircase / time-indexed structure), so the source rows gathered
+// by neighbouring output rows overlap.  Here ONE 1024-thread CTA per SM owns one SLAB of the feature row (32 lanes x
+// CH x 16 bytes: 512 B or 1 KB) and a contiguous range of output rows, and sweeps that range top to bottom with its 32
+// warps on 32 adjacent rows.  With the slab narrow enough, the active band (band rows x slab bytes) stays resident
+// in the SM's L1, so every source-row slab travels L2 -> SM about once per sweep instead of once per nonzero (ncu on
+// C2: L1 hit rate 60-72 %, L2->L1 sectors / 2.6-6, DRAM traffic = compulsory).  Matrices without locality lose
+// nothing (measured: uniform-random C2 6 % faster than the row kernel).
+//   * per gathered 16-byte chunk: 2 SHFL + 1 IMAD.WIDE + 1 LDG.128 + 8 unpack (4 IMAD.SHL on the FMA pipe, 4 LOP3 on the
+//     ALU pipe) + 4 FFMA2 (packed two-lane FMA, per lane the same rounding as fmaf);
+//   * (ptr) two rows ahead and the row's first (idx,val) fetch one row ahead are software-pipelined, the tail of a
+//     row is gathered in batches of U, U/2, .., 1 so no load is issued alone behind another's latency.
+// Same arithmetic as the row kernel: fp32 accumulation in CSR order, one owner per output element, no atomics --
+// results are bit-identical between the two kernels and for every tuning.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> struct PairAcc;   // 16-byte chunk -> fp32 pair accumulators
+template <> struct PairAcc<__nv_bfloat16> {
+  static constexpr int kPairs = 4;
+  __device__ static float2 unpack(uint32_t x) {
+    return make_float2(__uint_as_float(x << 16), __uint_as_float(x & 0xffff0000u));
+  }
+  __device__ static void fma(float2 (&acc)[4], float2 ww, const uint4& v) {
+    acc[0] = __ffma2_rn(ww, unpack(v.x), acc[0]);
+    acc[1] = __ffma2_rn(ww, unpack(v.y), acc[1]);
+    acc[2] = __ffma2_rn(ww, unpack(v.z), acc[2]);
+    acc[3] = __ffma2_rn(ww, unpack(v.w), acc[3]);
+  }
+  __device__ static uint4 pack(const float2 (&acc)[4]) {
+    return make_uint4(pack_bf16(acc[0].x, acc[0].y), pack_bf16(acc[1].x, acc[1].y), pack_bf16(acc[2].x, acc[2].y),
+                      pack_bf16(acc[3].x, acc[3].y));
+  }
+};
+template <> struct PairAcc<float> {
+  static constexpr int kPairs = 2;
+  __device__ static void fma(float2 (&acc)[2], float2 ww, const uint4& v) {
+    acc[0] = __ffma2_rn(ww, make_float2(__uint_as_float(v.x), __uint_as_float(v.y)), acc[0]);
+    acc[1] = __ffma2_rn(ww, make_float2(__uint_as_float(v.z), __uint_as_float(v.w)), acc[1]);
+  }
+  __device__ static uint4 pack(const float2 (&acc)[2]) {
+    return make_uint4(__float_as_uint(acc[0].x), __float_as_uint(acc[0].y), __float_as_uint(acc[1].x),
+                      __float_as_uint(acc[1].y));
+  }
+};
+
+constexpr int kSweepThreads = 1024;
+
+// Each lane owns CH 16-byte chunks (chunk c at lane*16 + c*512 bytes of the slab); a warp owns one row at a time.
+template <typename T, int CH, int U>
+__global__ void __launch_bounds__(kSweepThreads, 1)
+spmm_sweep_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ val,
+                  int32_t rows, const char* __restrict__ X, char* __restrict__ Y, uint32_t row_bytes,
+                  int32_t nslabs, int32_t rows_per_block) {
+  constexpr int P = PairAcc<T>::kPairs;
+  constexpr int kWarps = kSweepThreads / 32;
+  constexpr uint32_t kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slab = blockIdx.x % nslabs;
+  const int32_t r_begin = (blockIdx.x / nslabs) * rows_per_block;
+  const int32_t r_end = min(rows, r_begin + rows_per_block);
+  const uint32_t col0 = (uint32_t)(slab * 32 * CH + lane) * 16u;    // byte column of this lane's first chunk
+  const uint64_t xbase = reinterpret_cast<uint64_t>(X) + col0;      // (row_bytes is a multiple of the slab: no bounds tests)
+
+  int32_t row = r_begin + warp;
+  int32_t beg = 0, end = 0, nbeg = 0, nend = 0;
+  int32_t my_idx = 0; float my_val = 0.f;
+  if (row < r_end) { beg = __ldg(ptr + row); end = __ldg(ptr + row + 1); }
+  if (row + kWarps < r_end) { nbeg = __ldg(ptr + row + kWarps); nend = __ldg(ptr + row + kWarps + 1); }
+  if (beg + lane < end) { my_idx = __ldg(idx + beg + lane); my_val = __ldg(val + beg + lane); }
+
+  for (; row < r_end; row += kWarps) {
+    int32_t nnbeg = 0, nnend = 0, n_idx = 0; float n_val = 0.f;
+    if (row + 2 * kWarps < r_end) { nnbeg = __ldg(ptr + row + 2 * kWarps); nnend = __ldg(ptr + row + 2 * kWarps + 1); }
+    if (nbeg + lane < nend) { n_idx = __ldg(idx + nbeg + lane); n_val = __ldg(val + nbeg + lane); }
+
+    float2 acc[CH][P];
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int k = 0; k < P; ++k) acc[c][k] = make_float2(0.f, 0.f);
+
+    for (int32_t e0 = beg; e0 < end; e0 += 32) {
+      if (e0 != beg) {
+        my_idx = 0; my_val = 0.f;
+        if (e0 + lane < end) { my_idx = __ldg(idx + e0 + lane); my_val = __ldg(val + e0 + lane); }
+      }
+      const int cnt = min(32, end - e0);
+      int j = 0;
+      auto batch = [&](auto nb) {                       // nb neighbours in flight: shuffles, then loads, then math
+        constexpr int N = decltype(nb)::value;
+        uint4 v[N][CH]; float w[N]; uint32_t i[N];
+#pragma unroll
+        for (int u = 0; u < N; ++u) {
+          i[u] = (uint32_t)__shfl_sync(kFull, my_idx, j + u);
+          w[u] = __shfl_sync(kFull, my_val, j + u);
+        }
+#pragma unroll
+        for (int u = 0; u < N; ++u) {
+          const uint4* src = reinterpret_cast<const uint4*>(xbase + (uint64_t)i[u] * row_bytes);   // one IMAD.WIDE
+#pragma unroll
+          for (int c = 0; c < CH; ++c) v[u][c] = __ldg(src + c * 32);
+        }
+#pragma unroll
+        for (int u = 0; u < N; ++u)
+#pragma unroll
+          for (int c = 0; c < CH; ++c) PairAcc<T>::fma(acc[c], make_float2(w[u], w[u]), v[u][c]);
+        j += N;
+      };
+      while (j + U <= cnt) batch(std::integral_constant<int, U>{});
+      if (U > 2 && j + 2 <= cnt) batch(std::integral_constant<int, 2>{});
+      if (j < cnt) batch(std::integral_constant<int, 1>{});
+    }
+    uint4* dst = reinterpret_cast<uint4*>(Y + (uint64_t)(uint32_t)row * row_bytes + col0);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) __stcs(dst + c * 32, PairAcc<T>::pack(acc[c]));
+    beg = nbeg; end = nend; nbeg = nnbeg; nend = nnend;
+    my_idx = n_idx; my_val = n_val;
+  }
+}
+
+template <typename T, int CH, int U>
+int launch_sweep(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const void* X, void* Y,
+                 int32_t chunks, cudaStream_t st) {
+  const int nslabs = chunks / (32 * CH);
+  constexpr int kWarps = kSweepThreads / 32;
+  const int want_blocks = max(1, sm_count() / nslabs);          // one CTA per SM, all co-resident
+  int rows_per_block = ceil_div(rows, want_blocks);
+  rows_per_block = ceil_div(rows_per_block, kWarps) * kWarps;
+  const int nblocks = ceil_div(rows, rows_per_block);
+  spmm_sweep_kernel<T, CH, U><<<nblocks * nslabs, kSweepThreads, 0, st>>>(
+      ptr, idx, val, rows, reinterpret_cast<const char*>(X), reinterpret_cast<char*>(Y), (uint32_t)chunks * 16u, nslabs,
+      rows_per_block);
+  LPGNN_LAUNCH_OK();
+  count_launches(1);
+  return LPGNN_OK;
+}
+
+template <typename T>
+int dispatch_sweep(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const void* X, void* Y,
+                   int32_t chunks, int slab_bytes, int unroll, cudaStream_t st) {
+  if (slab_bytes == 512 && unroll == 2) return launch_sweep<T, 1, 2>(ptr, idx, val, rows, X, Y, chunks, st);
+  if (slab_bytes == 512 && unroll == 4) return launch_sweep<T, 1, 4>(ptr, idx, val, rows, X, Y, chunks, st);
+  if (slab_bytes == 1024 && unroll == 2) return launch_sweep<T, 2, 2>(ptr, idx, val, rows, X, Y, chunks, st);
+  if (slab_bytes == 1024 && unroll == 4) return launch_sweep<T, 2, 4>(ptr, idx, val, rows, X, Y, chunks, st);
+  set_error("spmm: unsupported tuning slab_bytes=%d unroll=%d", slab_bytes, unroll);
+  return LPGNN_EINVAL;
+}
+
 template <typename T, int G, int CH>
 int launch(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const void* X, void* Y,
            int32_t chunks, cudaStream_t st) {
@@ -145,8 +299,8 @@ int dispatch(const int32_t* ptr, const int32_t* idx, const float* val, int32_t r
 
 using namespace lpgnn;
 
-extern "C" int lpgnn_spmm(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const void* X,
-                          void* Y, int32_t F, int dtype, lpgnn_stream_t stream) {
+extern "C" int lpgnn_spmm_ex(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const void* X,
+                             void* Y, int32_t F, int dtype, int slab_bytes, int unroll, lpgnn_stream_t stream) {
   if (int rc = check_device()) return rc;
   LPGNN_REQUIRE(rows >= 0 && F > 0, "spmm: bad shape rows=%d F=%d", rows, F);
   LPGNN_REQUIRE(dtype == LPGNN_F32 || dtype == LPGNN_BF16, "spmm: bad dtype %d", dtype);
@@ -156,7 +310,24 @@ extern "C" int lpgnn_spmm(const int32_t* ptr, const int32_t* idx, const float* v
   LPGNN_REQUIRE((F * esz) % 16 == 0, "spmm: F*sizeof(elem)=%d must be a multiple of 16", F * esz);
   LPGNN_REQUIRE(((uintptr_t)X % 16 == 0) && ((uintptr_t)Y % 16 == 0), "spmm: X/Y must be 16-byte aligned");
   const int32_t chunks = F * esz / 16;
+  const int row_bytes = chunks * 16;
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == LPGNN_F32) return dispatch<float>(ptr, idx, val, rows, X, Y, chunks, st);
-  return dispatch<__nv_bfloat16>(ptr, idx, val, rows, X, Y, chunks, st);
+  if (slab_bytes == 0) {            // automatic: 1 KB slabs when the row is made of them, else 512 B, else the row kernel
+    slab_bytes = row_bytes % 1024 == 0 ? 1024 : (row_bytes % 512 == 0 ? 512 : -1);
+    // a sweep has one CTA per (SM, slab): small matrices (few rows per CTA) keep the row kernel
+    if (slab_bytes > 0 && (int64_t)rows * (row_bytes / slab_bytes) < (int64_t)sm_count() * 64) slab_bytes = -1;
+  }
+  if (slab_bytes < 0) {             // row-per-warp kernel
+    if (dtype == LPGNN_F32) return dispatch<float>(ptr, idx, val, rows, X, Y, chunks, st);
+    return dispatch<__nv_bfloat16>(ptr, idx, val, rows, X, Y, chunks, st);
+  }
+  LPGNN_REQUIRE(row_bytes % slab_bytes == 0, "spmm: row of %d bytes is not a multiple of the %d-byte slab", row_bytes, slab_bytes);
+  if (unroll <= 0) unroll = dtype == LPGNN_F32 ? 4 : 2;
+  if (dtype == LPGNN_F32) return dispatch_sweep<float>(ptr, idx, val, rows, X, Y, chunks, slab_bytes, unroll, st);
+  return dispatch_sweep<__nv_bfloat16>(ptr, idx, val, rows, X, Y, chunks, slab_bytes, unroll, st);
+}
+
+extern "C" int lpgnn_spmm(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const void* X,
+                          void* Y, int32_t F, int dtype, lpgnn_stream_t stream) {
+  return lpgnn_spmm_ex(ptr, idx, val, rows, X, Y, F, dtype, 0, 0, stream);
 }

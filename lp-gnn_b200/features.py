@@ -97,3 +97,25 @@ def node_features(c, b_l, A, b_u, l, u):
         _cosine_with_columns(l, At_csc), _cosine_with_columns(u, At_csc),
         _value_tag(b_l), _value_tag(b_u)])
     return v_feas, c_feas
+
+
+def prepare_lp_device(c, b_l, A, b_u, l, u, device):
+    """Raw LP on the host -> model inputs on ``device`` with scaling and features computed THERE
+    (``lpgnn_lp_features``; same arithmetic as :func:`scale_lp` + :func:`node_features`, i.e. reference
+    dataset.py:23-96).  Returns ``(graph, x_s, x_t, scaled)``: a built ``BipartiteCSR`` with the scaled
+    coefficients, the feature rows, and the float64 scaled LP.  This is the "predict on a fresh LP" entry:
+    no offline ``process()`` pass."""
+    import torch
+    from . import ops
+    from .graph import BipartiteCSR
+    A = sp.csr_matrix(A, dtype=np.float64, copy=True)
+    A.sum_duplicates()
+    A.sort_indices()
+    m, n = A.shape
+    row = np.repeat(np.arange(m, dtype=np.int32), np.diff(A.indptr))
+    dev = torch.device(device)
+    g = BipartiteCSR.from_coo(torch.from_numpy(row), torch.from_numpy(A.indices.astype(np.int32)),
+                              torch.zeros(A.nnz, dtype=torch.float32), m, n, is_sorted=True).to(dev)
+    up = lambda v: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(dev)
+    x_s, x_t, scaled = ops.lp_features(g, up(A.data), up(c), up(b_l), up(b_u), up(l), up(u))
+    return g, x_s, x_t, scaled

@@ -16,18 +16,19 @@ def _contig(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
-def spmm(view, x: torch.Tensor) -> torch.Tensor:
+def spmm(view, x: torch.Tensor, slab_bytes: int = 0, unroll: int = 0) -> torch.Tensor:
     """``Y[i] = sum_e val[e] * X[idx[e]]`` for one orientation ``view = (ptr, idx, val, rows)``
     (``BipartiteCSR.views()``).  Replaces ``torch_sparse.matmul(adj_t, x, reduce='add')``
-    (reference arch.py:75-80 through PyG GraphConv)."""
+    (reference arch.py:75-80 through PyG GraphConv).  ``slab_bytes`` / ``unroll`` select the kernel explicitly
+    (``lpgnn_spmm_ex``; 0 = automatic, ``slab_bytes=-1`` = row-per-warp kernel); results do not depend on them."""
     ptr_, idx, val, rows = view
     require_cuda(ptr_, x)
     x = _contig(x)
     F = x.shape[1]
     y = torch.empty((rows, F), dtype=x.dtype, device=x.device)
     with torch.cuda.device(x.device):
-        rc = _lib.load().lpgnn_spmm(ptr_.data_ptr(), idx.data_ptr(), val.data_ptr(), rows, x.data_ptr(), y.data_ptr(), F,
-                                    dtype_code(x.dtype), stream_ptr())
+        rc = _lib.load().lpgnn_spmm_ex(ptr_.data_ptr(), idx.data_ptr(), val.data_ptr(), rows, x.data_ptr(), y.data_ptr(), F,
+                                       dtype_code(x.dtype), slab_bytes, unroll, stream_ptr())
     check(rc, "lpgnn_spmm")
     return y
 
@@ -356,3 +357,34 @@ def small_wgrad(dy, z, k, want_bias=False):
                                    ptr(dB), ws.data_ptr(), ws_bytes, stream_ptr())
     check(rc, "lpgnn_small_wgrad")
     return dW, dB
+
+
+def lp_features(g, a_csr, c, b_l, b_u, l, u):
+    """(f-2) ``dataset.scaling`` + ``dataset.cvt_to_features`` (reference dataset.py:23-96) on the device.
+    ``g``: a built ``BipartiteCSR`` holding the STRUCTURE of the raw A (its values are overwritten with the scaled
+    coefficients of both orientations); ``a_csr`` float64 raw values in canonical CSR order; ``c, l, u`` [n] and
+    ``b_l, b_u`` [m] float64.  Returns ``(x_s[m,8], x_t[n,8], scaled)`` with ``scaled`` a dict of the float64
+    scaled LP (``A`` in CSR order, ``c, b_l, b_u, l, u``)."""
+    g._require_built()
+    require_cuda(g.rowptr, a_csr, c, b_l, b_u, l, u)
+    f64 = lambda t: _contig(t.to(torch.float64))
+    a_csr, c, b_l, b_u, l, u = f64(a_csr), f64(c), f64(b_l), f64(b_u), f64(l), f64(u)
+    m, n, z = g.m, g.n, g.nnz()
+    if a_csr.shape[0] != z or c.shape[0] != n or l.shape[0] != n or u.shape[0] != n or b_l.shape[0] != m or b_u.shape[0] != m:
+        raise ValueError("lp_features: array lengths do not match the graph (m, n, nnz)")
+    dev = g.rowptr.device
+    lib = _lib.load()
+    x_s = torch.empty((m, 8), dtype=torch.float32, device=dev)
+    x_t = torch.empty((n, 8), dtype=torch.float32, device=dev)
+    out = torch.empty(z + 3 * n + 2 * m, dtype=torch.float64, device=dev)
+    o_a, o_c, o_bl, o_bu, o_l, o_u = torch.split(out, [z, n, m, m, n, n])
+    ws_bytes = lib.lpgnn_lp_features_workspace_bytes(z, m, n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.lpgnn_lp_features(g.rowptr.data_ptr(), g.col.data_ptr(), g.colptr.data_ptr(), g.row_csc.data_ptr(),
+                                   g.csr2csc.data_ptr(), a_csr.data_ptr(), c.data_ptr(), b_l.data_ptr(), b_u.data_ptr(),
+                                   l.data_ptr(), u.data_ptr(), z, m, n, g.val.data_ptr(), g.val_csc.data_ptr(),
+                                   x_s.data_ptr(), x_t.data_ptr(), o_a.data_ptr(), o_c.data_ptr(), o_bl.data_ptr(),
+                                   o_bu.data_ptr(), o_l.data_ptr(), o_u.data_ptr(), ws.data_ptr(), ws_bytes, stream_ptr())
+    check(rc, "lpgnn_lp_features")
+    return x_s, x_t, {"A": o_a, "c": o_c, "b_l": o_bl, "b_u": o_bu, "l": o_l, "u": o_u}

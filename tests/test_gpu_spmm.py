@@ -85,3 +85,61 @@ def test_spmm_linearity_full_size_c2(cuda):
         w = torch.from_numpy(ref.val[lo:hi]).to(cuda).double()
         e = (w[:, None] * xc[cols]).sum(0)
         assert float((a[r].double() - e).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("structure", ["staircase", "uniform"])
+def test_banded_sweep_kernel_is_bit_identical_to_row_kernel(cuda, dtype, structure):
+    """Every kernel setting of lpgnn_spmm_ex (row-per-warp, 512 B / 1 KB slabs, 2 / 4 gathers in flight, automatic)
+    returns the same bits, on a banded LP and on one without locality, both orientations; the row kernel itself is
+    pinned to the oracle (sequential CSR-order fp32 accumulation) on a sample of rows."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops, synth
+    from lpgnn_b200.graph import BipartiteCSR
+    m, n, F = 12_000, 24_000, 1024 if dtype == torch.bfloat16 else 512
+    c, b_l, A, b_u, l, u = synth.raw_lp(m, n, 5 * n, 31, structure)
+    A = A.tocsr()
+    A.sort_indices()
+    row = np.repeat(np.arange(m), np.diff(A.indptr))
+    val = (A.data / 10.0).astype(np.float32)
+    g = BipartiteCSR.from_coo_arrays(row, A.indices, val, m, n, cuda, is_sorted=True)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    xs = {0: torch.randn(n, F, device=cuda, generator=gen).to(dtype), 1: torch.randn(m, F, device=cuda, generator=gen).to(dtype)}
+    for k, view in enumerate(g.views()):
+        ref = ops.spmm(view, xs[k], slab_bytes=-1)
+        for slab, unroll in ((0, 0), (512, 2), (512, 4), (1024, 2), (1024, 4)):
+            got = ops.spmm(view, xs[k], slab_bytes=slab, unroll=unroll)
+            assert torch.equal(got.view(torch.int16 if dtype == torch.bfloat16 else torch.int32),
+                               ref.view(torch.int16 if dtype == torch.bfloat16 else torch.int32)), (k, slab, unroll)
+        ptr_, idx, v, rows = (t.cpu().numpy() if torch.is_tensor(t) else t for t in view)
+        pick = np.unique(np.concatenate([[0, rows - 1], np.random.default_rng(k).integers(0, rows, 200)]))
+        sub_ptr = np.concatenate([[0], np.cumsum(ptr_[pick + 1] - ptr_[pick])])
+        sub_idx = np.concatenate([idx[ptr_[r]:ptr_[r + 1]] for r in pick])
+        sub_val = np.concatenate([v[ptr_[r]:ptr_[r + 1]] for r in pick])
+        e = port.spmm_sequential(sub_ptr, sub_idx, sub_val, xs[k].float().cpu().numpy())
+        got = ref[torch.from_numpy(pick).to(cuda)].float().cpu().numpy()
+        if dtype == torch.bfloat16:
+            assert np.mean(got == torch.from_numpy(e).to(torch.bfloat16).float().numpy()) > 0.99
+        else:
+            np.testing.assert_allclose(got, e, rtol=1e-5, atol=1e-5)
+
+
+def test_sweep_kernel_ragged_rows(cuda):
+    """Rows longer than one 32-entry fetch, empty rows and a row count that is not a multiple of the CTA's 32 warps."""
+    from lpgnn_b200 import ops
+    from lpgnn_b200.graph import BipartiteCSR
+    m, n, F = 10_007, 5_003, 256
+    rng = np.random.default_rng(9)
+    lens = rng.choice([0, 1, 3, 31, 32, 33, 70, 200], size=m, p=[.2, .3, .3, .05, .05, .05, .04, .01])
+    row = np.repeat(np.arange(m), lens)
+    col = np.concatenate([np.sort(rng.choice(n, k, replace=False)) for k in lens]).astype(np.int64)
+    val = rng.uniform(-1, 1, row.shape[0]).astype(np.float32)
+    g = BipartiteCSR.from_coo_arrays(row, col, val, m, n, cuda, is_sorted=True)
+    ref = port.graph_from_coo(row, col, val, m, n)
+    x = rng.standard_normal((n, F)).astype(np.float32)
+    e = port.spmm_sequential(ref.rowptr, ref.col, ref.val, x)
+    xd = torch.from_numpy(x).to(cuda)
+    for slab, unroll in ((-1, 0), (512, 2), (512, 4), (1024, 2), (1024, 4)):
+        y = ops.spmm(g.views()[0], xd, slab_bytes=slab, unroll=unroll).cpu().numpy()
+        np.testing.assert_allclose(y, e, rtol=1e-5, atol=1e-4)
+        assert not y[lens == 0].any()
