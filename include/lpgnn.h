@@ -447,6 +447,27 @@ LPGNN_API int lpgnn_lp_features(const int32_t* rowptr, const int32_t* col, const
                       double* bl_out, double* bu_out, double* l_out, double* u_out, void* workspace,
                       size_t workspace_bytes, lpgnn_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (f-4) Sampled-subgraph path for LPs above edge_num_thresh.  Replaces torch_geometric NeighborLoader as driven at
+ * reference train.py:107-116 (num_neighbors=[6]*depth, directed=False) and val.py:22-27 (num_neighbors=[-1]*depth)
+ * plus the relabelling of MyToBipartite (dataset.py:275-332), on the resident CSR / CSC of the full LP.
+ *
+ * lpgnn_sample_mark: for every node f of `frontier` (ids in the row space of (ptr, idx)) choose min(deg, fanout) of
+ * its neighbours without replacement (fanout < 0: all) and set marks_other[neighbour] = 1 (uint8, other side's id
+ * space).  The choice is a pure function of (seed, f): reproducible; callers fold the hop number into `seed`.
+ * lpgnn_induced_count / _fill: subgraph induced by the sampled nodes.  rows[i] = global id of local row i;
+ * map_other[j] = local id of other-side node j or -1.  counts[i] = surviving entries of row i; with
+ * offsets = exclusive scan of counts, _fill writes the COO (local row, local col, value) in local row order
+ * (columns in the order of the full matrix's row, so only sorted if map_other is monotone).
+ * ------------------------------------------------------------------------------------------- */
+LPGNN_API int lpgnn_sample_mark(const int32_t* ptr, const int32_t* idx, const int32_t* frontier, int32_t n_frontier,
+                      int32_t fanout, uint64_t seed, uint8_t* marks_other, lpgnn_stream_t stream);
+LPGNN_API int lpgnn_induced_count(const int32_t* ptr, const int32_t* idx, const int32_t* rows, int32_t n_rows,
+                        const int32_t* map_other, int32_t* counts, lpgnn_stream_t stream);
+LPGNN_API int lpgnn_induced_fill(const int32_t* ptr, const int32_t* idx, const float* val, const int32_t* rows,
+                       int32_t n_rows, const int32_t* map_other, const int64_t* offsets, int32_t* out_row,
+                       int32_t* out_col, float* out_val, lpgnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,8 @@ def parse_args(argv=None, **defaults):
     ap.add_argument("--data_prefix", type=str, default="./lp-dataset/")
     ap.add_argument("--log_prefix", type=str, default="./runs/")
     ap.add_argument("--edge_num_thresh", type=float, default=4e6 * 3)
+    ap.add_argument("--batch_size", type=int, default=int(4096 * 40 * 2),
+                    help="seed nodes per sampled mini-batch for LPs above edge_num_thresh (utils.py:807)")
     ap.add_argument("--loss", type=str, default="balanced")
     ap.add_argument("--inference_manager", type=str, default="InferenceManager(0,)")
     ap.add_argument("--split", type=str, default="val")
@@ -140,24 +142,32 @@ def run_exp(args):
         for it, batch in enumerate(loader):
             if it >= steps_per_epoch:
                 break
-            if not hasattr(batch, "x_s"):
-                raise NotImplementedError("graphs above edge_num_thresh need the sampled path (SURVEY 8 f-4)")
-            batch.to(dev, non_blocking=True)
-            glstep += 1
-            logit_cons, logit_vars = model(batch)
-            logit_cons, logit_vars = logit_cons[:batch.s_bs], logit_vars[:batch.t_bs]
-            y_s, y_t = batch.y_s[:batch.s_bs], batch.y_t[:batch.t_bs]
-            loss = loss_fn(logit_cons, logit_vars, y_s, y_t)
-            opt.zero_grad()
-            loss.backward()
-            allreduce_gradients(params, world)
-            opt.step()
-            if (glstep - 1) % max(args.log_every, 1) == 0:
-                lv = float(loss.item())
-                assert not np.isnan(lv)              # train.py:126
-                history.append(dict(epoch=epoch, step=glstep, loss=lv, lr=scheduler.get_last_lr()[0]))
-                if rank == 0:
-                    logging.info(f"{epoch} {it}/{steps_per_epoch} step {glstep} loss {lv:.4f}")
+            if hasattr(batch, "x_s"):                # already bipartite: one whole LP per step (train.py:103-104)
+                sub_loader = [batch]
+            else:                                    # above edge_num_thresh: sampled mini-batches (train.py:105-116)
+                if batch.edge_index.shape[-1] == 0:
+                    continue
+                from .sampling import NeighborSubgraphLoader, ResidentLP, conv_depth
+                lp_res = ResidentLP.from_unipartite(batch, dev)
+                sub_loader = NeighborSubgraphLoader(lp_res, [6] * conv_depth(args.arch), min(args.batch_size, lp_res.num_nodes),
+                                                    shuffle=True, drop_last=True, seed=args.seed + glstep)
+            for batch in sub_loader:
+                batch.to(dev, non_blocking=True)
+                glstep += 1
+                logit_cons, logit_vars = model(batch)
+                logit_cons, logit_vars = logit_cons[:batch.s_bs], logit_vars[:batch.t_bs]
+                y_s, y_t = batch.y_s[:batch.s_bs], batch.y_t[:batch.t_bs]
+                loss = loss_fn(logit_cons, logit_vars, y_s, y_t)
+                opt.zero_grad()
+                loss.backward()
+                allreduce_gradients(params, world)
+                opt.step()
+                if (glstep - 1) % max(args.log_every, 1) == 0:
+                    lv = float(loss.item())
+                    assert not np.isnan(lv)              # train.py:126
+                    history.append(dict(epoch=epoch, step=glstep, loss=lv, lr=scheduler.get_last_lr()[0]))
+                    if rank == 0:
+                        logging.info(f"{epoch} {it}/{steps_per_epoch} step {glstep} loss {lv:.4f}")
         scheduler.step()
         if rank == 0:
             model.save(f"{args.log_dir}/mdl.pth")

@@ -36,16 +36,29 @@ def inference_gnn(logits, m, **kwargs):
 
 @torch.no_grad()
 def model_inference_with_batch(model, batched_graphs, args=None):
-    """Reference val.py:12-36 for graphs that fit the bipartite full-graph path (every LP below
-    ``edge_num_thresh``); returns CPU logits like the reference."""
-    if not hasattr(batched_graphs, "x_s"):
-        raise NotImplementedError("sampled-subgraph inference (NeighborLoader, reference val.py:22-27) is the f-4 "
-                                  "follow-up row of SURVEY.md section 8; transform the graph with MyToBipartite first")
+    """Reference val.py:12-36.  Bipartite batches (every LP below ``edge_num_thresh``) run the full-graph path; a
+    unipartite graph (above the threshold) is kept resident on the device and walked in seed batches of
+    ``args.batch_size`` nodes with FULL neighbourhoods over ``depth - 1`` hops (``num_neighbors=[-1]*depth``,
+    val.py:22-27) by ``sampling.NeighborSubgraphLoader``.  Returns CPU logits like the reference."""
     dev = _device()
     model.eval()
-    batch = batch_to(batched_graphs, dev, bool(getattr(args, "fp16", 0)))
-    logit_cons, logit_vars = model(batch)
-    return logit_cons[:batch.s_bs].cpu(), logit_vars[:batch.t_bs].cpu()
+    fp16 = bool(getattr(args, "fp16", 0))
+    if hasattr(batched_graphs, "x_s"):
+        batch = batch_to(batched_graphs, dev, fp16)
+        logit_cons, logit_vars = model(batch)
+        return logit_cons[:batch.s_bs].cpu(), logit_vars[:batch.t_bs].cpu()
+    from .sampling import NeighborSubgraphLoader, ResidentLP, conv_depth
+    lp = ResidentLP.from_unipartite(batched_graphs, dev)
+    depth = conv_depth(getattr(args, "arch", ""))
+    bs = min(int(getattr(args, "batch_size", 327_680)), lp.num_nodes)
+    lc, lv = [], []
+    for batch in NeighborSubgraphLoader(lp, [-1] * depth, bs, shuffle=False, drop_last=False):
+        if fp16:
+            batch.x_s, batch.x_t = batch.x_s.half(), batch.x_t.half()
+        logit_cons, logit_vars = model(batch)
+        lc.append(logit_cons[:batch.s_bs].cpu())
+        lv.append(logit_vars[:batch.t_bs].cpu())
+    return torch.cat(lc, dim=0), torch.cat(lv, dim=0)
 
 
 @torch.no_grad()

@@ -393,3 +393,38 @@ def balanced_loss(logit_cons, logit_vars, y_s, y_t):
     loss = (m + n) / m * F.cross_entropy(logit_cons, y_s, weight=labels_to_balanced_weights(y_s))
     loss = loss + (m + n) / n * F.cross_entropy(logit_vars, y_t, weight=labels_to_balanced_weights(y_t))
     return loss
+
+
+# ---------------------------------------------------------------------------------------------
+# (f-4) sampled-subgraph path: what NeighborLoader(directed=False) + MyToBipartite produce for a
+# GIVEN node set (reference train.py:107-116, val.py:22-27, dataset.py:275-332).  The sampler's
+# random choices are third-party (pyg-lib / torch_sparse neighbor_sample) and not reproducible, so
+# the oracle restates the deterministic parts: full-neighbourhood expansion and the induced,
+# relabelled bipartite subgraph.
+# ---------------------------------------------------------------------------------------------
+def khop_full_neighbourhood(A_csr, cons_seeds, var_seeds, hops):
+    """Node lists (seeds first, then the nodes discovered at hop 1, 2, ... in ascending id order) reached from the
+    seeds by `hops` full-neighbourhood expansions of the bipartite graph of A."""
+    A = sp.csr_matrix(A_csr)
+    At = A.T.tocsr()
+    cons, vars_ = [np.asarray(cons_seeds, dtype=np.int64)], [np.asarray(var_seeds, dtype=np.int64)]
+    in_c = np.zeros(A.shape[0], dtype=bool); in_c[cons[0]] = True
+    in_v = np.zeros(A.shape[1], dtype=bool); in_v[vars_[0]] = True
+    front_c, front_v = cons[0], vars_[0]
+    for _ in range(hops):
+        nv = np.unique(A[front_c].indices) if front_c.size else np.zeros(0, dtype=np.int64)
+        nc = np.unique(At[front_v].indices) if front_v.size else np.zeros(0, dtype=np.int64)
+        nv, nc = nv[~in_v[nv]], nc[~in_c[nc]]
+        in_v[nv] = True; in_c[nc] = True
+        cons.append(nc.astype(np.int64)); vars_.append(nv.astype(np.int64))
+        front_c, front_v = nc, nv
+    return np.concatenate(cons), np.concatenate(vars_)
+
+
+def induced_bipartite_subgraph(A_csr, cons_nodes, var_nodes):
+    """(rowptr, col, val) of A[cons_nodes][:, var_nodes] in canonical order (rows = local constraint ids, ascending local
+    column ids inside a row): the graph MyToBipartite builds from the sampled, relabelled unipartite subgraph."""
+    A = sp.csr_matrix(A_csr)
+    sub = A[np.asarray(cons_nodes)][:, np.asarray(var_nodes)].tocsr()
+    sub.sort_indices()
+    return sub.indptr.astype(np.int64), sub.indices.astype(np.int64), sub.data.astype(np.float32)

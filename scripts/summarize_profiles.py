@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def short(name):
-    name = re.sub(r"void (lpgnn::)?(\(anonymous namespace\)::|unnamed>::)?", "", name)
+    name = re.sub(r"void |lpgnn::|\(anonymous namespace\)::|unnamed>::", "", name)
     name = re.sub(r"\(.*", "", name)
     return name.replace("lpgnn::", "")
 
@@ -24,11 +24,16 @@ for r in rows:
     a[0] += t; a[1] += 1
 tot = sum(a[0] for a in agg.values())
 with open(os.path.join(ROOT, "profiles", f"{tag}_step_shares.txt"), "w") as f:
-    f.write(f"# ncu launch list (gpu__time_duration.sum, --clock-control none) of ONE C2 bf16 step = {len(rows)} launches\n")
+    what = sys.argv[4] if len(sys.argv) > 4 else "prediction step (lpgnn_predict_basis)"
+    f.write(f"# ncu launch list (gpu__time_duration.sum, --clock-control none) of ONE C2 bf16 {what} = {len(rows)} launches\n")
     f.write("# (scripts/profile_step.py inside cudaProfilerStart/Stop).  Cold-cache, serialised: compare SHARES, not absolutes.\n\n")
     for k, (t, c) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         f.write(f"{t:9.1f} us  {100 * t / tot:5.1f} %  x{c:<2d} {k}\n")
     f.write(f"{tot:9.1f} us  total\n")
+
+if full == "-":
+    print(open(os.path.join(ROOT, "profiles", f"{tag}_step_shares.txt")).read())
+    sys.exit(0)
 
 # ---- full capture (--page raw: one row per launch, one column per metric)
 raw = list(csv.reader(open(full)))

@@ -143,3 +143,16 @@ def test_losses_match_reference_semantics(pkg):
     ce = torch.nn.functional.cross_entropy(torch.cat((lc, lv)), torch.cat((ys, yt)))
     assert torch.allclose(losses.unbalanced(lc, lv, ys, yt), ce)
     assert torch.allclose(losses.focal(lc, lv, ys, yt), (1 - torch.exp(-ce)) ** 2 * ce)
+
+
+def test_oracle_induced_subgraph_and_khop_expansion():
+    """(f-4) the oracle's deterministic restatement of NeighborLoader(directed=False) + MyToBipartite on a hand case."""
+    import scipy.sparse as sp
+    from oracle import port
+    A = sp.csr_matrix(np.array([[1., 0, 2, 0], [0, 3, 0, 0], [0, 0, 4, 5]], dtype=np.float32))
+    cn, vn = port.khop_full_neighbourhood(A, [1], [], 2)          # c1 -> v1 -> (no new constraint)
+    assert list(cn) == [1] and list(vn) == [1]
+    cn, vn = port.khop_full_neighbourhood(A, [0], [], 2)          # c0 -> v0, v2 -> c2
+    assert list(cn) == [0, 2] and list(vn) == [0, 2]
+    rowptr, col, val = port.induced_bipartite_subgraph(A, [2, 0], [2, 0])   # relabelled: rows (c2, c0), cols (v2, v0)
+    assert list(rowptr) == [0, 1, 3] and list(col) == [0, 0, 1] and list(val) == [4., 2., 1.]
