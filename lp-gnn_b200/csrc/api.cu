@@ -259,11 +259,19 @@ extern "C" int32_t lpgnn_gemm_tn_splits(int32_t M, int32_t N, int32_t K) {
   // enough (tile, slice) work items to fill the machine, at least 8 K-blocks of 64 per slice
   const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
   const int tiles = ((M + 127) / 128) * (N / BN);
-  int splits = (2 * sm_count() + tiles - 1) / tiles;
+  // (tile, K-slice) work items all cost the same, so the GEMM runs in ceil(items / SMs) equal waves: pick the slice
+  // count whose last wave is fullest (e.g. 32 tiles on 148 SMs: 9 slices = 288 items = 1.95 waves, not 10 = 2.16),
+  // with a small price per slice for the partial tiles it writes and the reduce re-reads; >= 8 K-blocks per slice.
+  const int sms = sm_count();
   const int max_by_k = K / 64 / 8;
-  if (splits > max_by_k) splits = max_by_k;
-  if (splits < 1) splits = 1;
-  if (splits > 32) splits = 32;
+  int splits = 1;
+  double best = -1.0;
+  for (int sp = 1; sp <= 32 && sp <= (max_by_k > 1 ? max_by_k : 1); ++sp) {
+    const int items = tiles * sp;
+    const int waves = (items + sms - 1) / sms;
+    const double score = (double)items / ((double)waves * sms) - 0.004 * sp;
+    if (score > best) { best = score; splits = sp; }
+  }
   // every slice must own at least one K block: re-derive the slice count from the per-slice block count
   const int kblocks = K / 64;
   const int kb_per = (kblocks + splits - 1) / splits;

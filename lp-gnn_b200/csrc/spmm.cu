@@ -247,6 +247,11 @@ int launch_sweep(const int32_t* ptr, const int32_t* idx, const float* val, int32
   int rows_per_block = ceil_div(rows, want_blocks);
   rows_per_block = ceil_div(rows_per_block, kWarps) * kWarps;
   const int nblocks = ceil_div(rows, rows_per_block);
+  static bool carved = false;      // no shared memory is used: ask for the whole 228 KB as L1 (it holds the band)
+  if (!carved) {
+    cudaFuncSetAttribute(spmm_sweep_kernel<T, CH, U>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    carved = true;
+  }
   spmm_sweep_kernel<T, CH, U><<<nblocks * nslabs, kSweepThreads, 0, st>>>(
       ptr, idx, val, rows, reinterpret_cast<const char*>(X), reinterpret_cast<char*>(Y), (uint32_t)chunks * 16u, nslabs,
       rows_per_block);
