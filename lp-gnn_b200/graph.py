@@ -25,8 +25,9 @@ _STATUS_POOL = {}
 
 def _status_slot(dev, pool_words=4096):
     """Hands out zero-initialised int32 status words from a per-device pool so that the hot loop does not pay a
-    memset launch per graph; the pool is replaced (one ``torch.zeros``) every ``pool_words`` graphs."""
-    key = (dev.type, dev.index)
+    memset launch per graph; the pool is replaced (one ``torch.zeros``) every ``pool_words`` graphs.  One pool per
+    (device, stream), so a word is always zeroed on the stream that uses it."""
+    key = (dev.type, dev.index, torch.cuda.current_stream(dev).cuda_stream)   # per stream: the zero fill is stream-ordered
     pool = _STATUS_POOL.get(key)
     if pool is None or pool[1] >= pool_words:
         pool = [torch.zeros(pool_words, dtype=torch.int32, device=dev), 0]

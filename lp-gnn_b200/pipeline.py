@@ -57,11 +57,15 @@ class BasisPipeline:
     (constraints first) of every LP, in order.  The yielded array is a view of a pinned slot that is reused two
     LPs later -- copy it if it must outlive the next iteration."""
 
-    def __init__(self, model, device):
+    def __init__(self, model, device, compute_streams=2):
+        """``compute_streams=2``: consecutive LPs run on alternating streams, so the latency-bound small kernels of
+        one LP (graph build, basis selection) overlap the neighbouring LP's work; 1 = strictly one LP at a time on
+        the caller's current stream."""
         if not torch.cuda.is_available():
             raise RuntimeError("BasisPipeline needs a CUDA device (no CPU fallback)")
         self.model, self.dev = model, torch.device(device)
         self.copy_stream = torch.cuda.Stream(self.dev)
+        self.compute = [torch.cuda.Stream(self.dev) for _ in range(2)] if compute_streams > 1 else None
         self.d_buf = [None, None]
         self.h_status = [None, None]
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]      # H2D of the slot finished
@@ -79,7 +83,12 @@ class BasisPipeline:
 
     @torch.no_grad()
     def _compute(self, slot, lp: HostLP):
-        cur = torch.cuda.current_stream(self.dev)
+        if self.compute is None:
+            return self._compute_on(slot, lp, torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(self.compute[slot]):
+            return self._compute_on(slot, lp, self.compute[slot])
+
+    def _compute_on(self, slot, lp: HostLP, cur):
         # the slot's previous result (LP i-2) was handed out one iteration ago, so its host buffer may be replaced
         nodes = lp.m + lp.n
         if self.h_status[slot] is None or self.h_status[slot].numel() < nodes:
@@ -94,6 +103,9 @@ class BasisPipeline:
         lps = list(host_lps)
         if not lps:
             return
+        if self.compute is not None:                               # weights etc. were produced on the caller's stream
+            for st in self.compute:
+                st.wait_stream(torch.cuda.current_stream(self.dev))
         self._copy_in(0, lps[0], True)
         for i, lp in enumerate(lps):
             slot = i & 1
