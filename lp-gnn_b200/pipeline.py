@@ -130,12 +130,15 @@ class PackedBasisPipeline:
     ``for idx, status in pipe.run(host_lps)`` yields a fresh uint8 array [m+n] (constraints first) per LP, in order.
     """
 
-    def __init__(self, model, device, max_nodes=200_000, max_nnz=1_000_000, max_lps=64):
+    def __init__(self, model, device, max_nodes=200_000, max_nnz=1_000_000, max_lps=64, compute_streams=1):
         if not torch.cuda.is_available():
             raise RuntimeError("PackedBasisPipeline needs a CUDA device (no CPU fallback)")
         self.model, self.dev = model, torch.device(device)
         self.max_nodes, self.max_nnz, self.max_lps = max_nodes, max_nnz, max_lps
         self.copy_stream = torch.cuda.Stream(self.dev)
+        # optional alternating compute streams as in BasisPipeline; off by default: packs already fill the GPU and
+        # their varying workspace sizes defeat the per-stream allocator caches (measured 2.7x slower on C5)
+        self.compute = [torch.cuda.Stream(self.dev) for _ in range(2)] if compute_streams > 1 else None
         self.d_buf, self.h_status, self.h_ptr = [None, None], [None, None], [None, None]
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]
         self.done = [torch.cuda.Event(), torch.cuda.Event()]
@@ -208,8 +211,13 @@ class PackedBasisPipeline:
 
     @torch.no_grad()
     def _compute(self, slot, meta):
+        if self.compute is None:
+            return self._compute_on(slot, meta, torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(self.compute[slot]):
+            return self._compute_on(slot, meta, self.compute[slot])
+
+    def _compute_on(self, slot, meta, cur):
         from . import _lib
-        cur = torch.cuda.current_stream(self.dev)
         M, N, Z, B, p, q = meta["M"], meta["N"], meta["Z"], meta["B"], meta["p"], meta["q"]
         if self.h_status[slot] is None or self.h_status[slot].numel() < M + N:
             self.h_status[slot] = torch.empty(int((M + N) * 1.25) + 64, dtype=torch.uint8).pin_memory()
@@ -241,6 +249,9 @@ class PackedBasisPipeline:
         packs = self._plan(lps)
         if not packs:
             return
+        if self.compute is not None:
+            for st in self.compute:
+                st.wait_stream(torch.cuda.current_stream(self.dev))
         metas = [None] * len(packs)
         metas[0] = self._stage(0, lps, packs[0], True)
         for k, ids in enumerate(packs):
