@@ -293,6 +293,8 @@ def run_gpu(args):
         if rank == 0:
             out["train"] = tr
             out["train_c1_fp32"] = tr1
+            if world == 1 and not args.no_cpu:
+                out["train_c1_fp32"]["cpu_baseline"] = cpu_train_baseline(c1, lp1)
     if rank == 0 and not args.no_kernels:
         out.update(kernel_rooflines(model, lp, dev, peaks, bf16, args))
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -562,6 +564,41 @@ def cpu_baseline(cfg, lp, args, sample_budget_s=20.0):
             "sample": f"{reps} LPs of the same workload ({cfg['name']}, fp32), {dt * 1e3:.0f} ms/LP; oracle port of the "
                       f"reference CPU path (PyG-equivalent restatement, not the PyG binary); torch threads={cores}",
             "mp_edges_per_sec": mp_edges(lp.nnz, cfg["depth"]) / dt}
+
+
+def cpu_train_baseline(cfg, lp, sample_budget_s=8.0, max_steps=200):
+    """configs[0] of BASELINE.json: the reference's CPU training step (train.py:117-129: forward, balanced loss,
+    backward, Adam) on the oracle port, all host threads; a bounded sample of steps on the same LP."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    from oracle import port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = port.PortGCN_FC(8, 8, hids=cfg["hids"], depth=cfg["depth"]).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4)
+    tg = port.TorchGraph(port.graph_from_coo(lp.row, lp.col, lp.a_data.astype(np.float32), lp.m, lp.n))
+    x_s, x_t = torch.from_numpy(lp.c_feas), torch.from_numpy(lp.v_feas)
+    y_s, y_t = torch.from_numpy(lp.y_s), torch.from_numpy(lp.y_t)
+
+    def step():
+        lc, lv = model(x_s, x_t, tg)
+        loss = port.balanced_loss(lc, lv, y_s, y_t)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+
+    for _ in range(3):
+        step()
+    t0, reps = time.perf_counter(), 0
+    while reps < max_steps and time.perf_counter() - t0 < sample_budget_s:
+        step()
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": 1.0 / dt, "unit": "LPs/s", "cores": cores, "kind": "port", "ms_per_step": dt * 1e3,
+            "sample": f"{reps} training steps (fwd + balanced loss + bwd + Adam) on one {cfg['name']}-shaped LP, fp32; oracle port "
+                      f"of the reference CPU path (PyG-equivalent restatement, not the PyG binary); torch threads={cores}",
+            "mp_edges_per_sec_fwd_bwd": mp_edges(lp.nnz, cfg["depth"], fwd_bwd=True) / dt}
 
 
 def run_reference(args):
