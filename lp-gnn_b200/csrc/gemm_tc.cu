@@ -39,7 +39,7 @@ template <int BN, typename OutT> struct Cfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;  // power of two >= 32 for BN in {64,128,256}
-  static constexpr int kBarBytes = 1024 + 2 * 4 * BN * 4;  // mbarriers + tmem ptr, then 2 x (bias slice [BN] + head weight slice [3][BN])
+  static constexpr int kBarBytes = 5120;  // mbarriers + tmem ptr + bias slice (BN floats) + head weight slice (3*BN floats)
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kStagingBytes + 1024 /*align slack*/;
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 };
@@ -81,7 +81,8 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
   uint64_t* tmem_full = bars + 2 * C::kStages;     // [2]
   uint64_t* tmem_empty = bars + 2 * C::kStages + 2;// [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
-  float* epi_consts = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + 1024);  // [2][4*BN], see the epilogue
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * C::kStages + 6);  // [BN]
+  float* headw_s = bias_s + BN;                                         // [3][BN]
   uint8_t* staging = smem + C::kStages * C::kStageBytes + C::kBarBytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -187,18 +188,6 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
     constexpr int P = C::kRowBytes / 16;          // 16-byte chunks per staged row: 4 (bf16) or 8 (fp32)
     constexpr int kRowsPerInstr = 32 / P;         // rows covered by one warp-wide 16-byte store: 8 or 4
     uint8_t* my_stage = staging + ew * (32 * C::kRowBytes);
-    constexpr int kConstPerThread = (4 * BN + kEpiThreads - 1) / kEpiThreads;
-    float cst[kConstPerThread];
-    auto load_consts = [&](int nb) {     // element j of [bias | head_w row 0 | row 1 | row 2] of column block nb
-#pragma unroll
-      for (int k = 0; k < kConstPerThread; ++k) {
-        const int j = et + k * kEpiThreads;
-        float v = 0.f;
-        if (j < BN) { if (bias) v = __ldg(bias + nb * BN + j); }
-        else if (j < 4 * BN && head_w) v = __ldg(head_w + (int64_t)(j / BN - 1) * N + nb * BN + (j % BN));
-        cst[k] = v;
-      }
-    };
     int t = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const int ot = tile % num_out_tiles, split = tile / num_out_tiles;
@@ -206,22 +195,12 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
       OutT* const out_t = out ? out + (int64_t)split * M * N : nullptr;
       const int buf = t & 1;
       const uint32_t use_phase = (t >> 1) & 1;
-      // Bias (and head weight) slice of this tile: fetched into registers one tile ahead, parked in the (t & 1) half
-      // of a double buffer, so the global-load latency is off the critical path and ONE named barrier per tile orders
-      // both the buffer reuse and the staging area.
-      float* const bias_s = epi_consts + (t & 1) * 4 * BN;   // [BN]
-      float* const headw_s = bias_s + BN;                     // [3][BN]
-      if (t == 0) load_consts(n_blk);
-#pragma unroll
-      for (int k = 0; k < kConstPerThread; ++k) {
-        const int j = et + k * kEpiThreads;
-        if (j < 4 * BN) bias_s[j] = cst[k];
-      }
+      // stage the bias (and head weight) slice of this tile
+      for (int j = et; j < BN; j += kEpiThreads) bias_s[j] = bias ? __ldg(bias + n_blk * BN + j) : 0.f;
+      if (head_w)
+        for (int j = et; j < 3 * BN; j += kEpiThreads)
+          headw_s[j] = __ldg(head_w + (int64_t)(j / BN) * N + n_blk * BN + (j % BN));
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-      {
-        const int next = tile + gridDim.x;
-        if (next < num_tiles) load_consts((next % num_out_tiles) % num_n);
-      }
       ptx::mbar_wait(&tmem_full[buf], use_phase);
       ptx::tc_fence_after();
       // Each lane owns accumulator row (q*32 + lane).  A 32-column piece of the row (64 B bf16 / 128 B fp32) is
@@ -231,18 +210,12 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
       const int wsw = (sizeof(OutT) == 2) ? ((lane >> 1) & 3) : (lane & 7);   // write-side swizzle of this lane's row
       float hd0 = 0.f, hd1 = 0.f, hd2 = 0.f;   // fused basis-status head: partial dot products of this row
-      // two TMEM loads are issued back to back and waited for together: one exposed load latency per 64 columns
-      constexpr int kLd = (kPiecesPerWarp % 2 == 0) ? 2 : 1;
 #pragma unroll 1
-      for (int pi0 = 0; pi0 < kPiecesPerWarp; pi0 += kLd) {
-       uint32_t rr2[kLd][32];
-#pragma unroll
-       for (int h = 0; h < kLd; ++h) ptx::tmem_ld_32x32(taddr + (hsel * kPiecesPerWarp + pi0 + h) * 32, rr2[h]);
-       ptx::tmem_ld_wait();
-#pragma unroll
-       for (int h = 0; h < kLd; ++h) {
-        const int pc = hsel * kPiecesPerWarp + pi0 + h;
-        uint32_t (&r)[32] = rr2[h];
+      for (int pi = 0; pi < kPiecesPerWarp; ++pi) {
+        const int pc = hsel * kPiecesPerWarp + pi;
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(taddr + pc * 32, r);
+        ptx::tmem_ld_wait();
         uint4* srow = reinterpret_cast<uint4*>(my_stage + lane * C::kRowBytes);
         if constexpr (sizeof(OutT) == 2) {
           uint32_t packed[16];
@@ -309,7 +282,6 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
           }
         }
         __syncwarp();
-       }
       }
       if (head_partial) {
         const int64_t grow = row_base + lane;
@@ -320,6 +292,7 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[buf]);
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // bias_s may be overwritten for the next tile
     }
   }
 
