@@ -447,6 +447,10 @@ LPGNN_API int lpgnn_lp_features(const int32_t* rowptr, const int32_t* col, const
                       double* bl_out, double* bu_out, double* l_out, double* u_out, void* workspace,
                       size_t workspace_bytes, lpgnn_stream_t stream);
 
+/* Tuning knob (process-wide): the wide bf16 node transform runs as 2-CTA clusters that share the W tiles through TMA
+ * multicast (default on); 0 selects the one-CTA-per-tile form.  Returns the previous setting; results are identical. */
+LPGNN_API int lpgnn_set_gemm_cluster(int enable);
+
 /* ---------------------------------------------------------------------------------------------
  * (f-4) Sampled-subgraph path for LPs above edge_num_thresh.  Replaces torch_geometric NeighborLoader as driven at
  * reference train.py:107-116 (num_neighbors=[6]*depth, directed=False) and val.py:22-27 (num_neighbors=[-1]*depth)

@@ -96,6 +96,7 @@ SIGNATURES = {
                                    _p, _p, _p, _sz, _p]),
     "lpgnn_train_backward": (_int, [C.POINTER(GcnFcWeights), _p, _p, _p, _p, _p, _p, _i32, _i32, C.c_float, _p, _p,
                                     C.POINTER(GcnFcGrads), _p, _sz, _p]),
+    "lpgnn_set_gemm_cluster": (_int, [_int]),
     "lpgnn_sample_mark": (_int, [_p, _p, _p, _i32, _i32, C.c_uint64, _p, _p]),
     "lpgnn_induced_count": (_int, [_p, _p, _p, _i32, _p, _p, _p]),
     "lpgnn_induced_fill": (_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),

@@ -16,6 +16,8 @@
 //               row segments to global
 // Tiles are ordered n-fastest so CTAs resident together share the same A row block through L2.
 // Bound: tensor pipe (2*M*N*(K1+K2) flops against the measured bf16 peak); see DESIGN.md.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -30,13 +32,13 @@ constexpr int kEpiWarps = 8;                         // two warps per TMEM lane 
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = kEpiWarp0 * 32 + kEpiThreads;  // 384
 
-template <int BN, typename OutT> struct Cfg {
+template <int BN, typename OutT, int kCl = 1> struct Cfg {
   static constexpr int kRowBytes = 32 * (int)sizeof(OutT);   // one staged piece: 32 columns of one row
   static constexpr int kStagingBytes = kEpiWarps * 32 * kRowBytes;
   static constexpr bool kWide = sizeof(OutT) == 4;   // fp32 output needs twice the staging space
-  static constexpr int kStages = (BN == 256) ? (kWide ? 3 : 4) : (BN == 128 ? (kWide ? 5 : 6) : (kWide ? 6 : 8));
+  static constexpr int kStages = (kCl == 2) ? 6 : (BN == 256) ? (kWide ? 3 : 4) : (BN == 128 ? (kWide ? 5 : 6) : (kWide ? 6 : 8));
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (BN / kCl) * BK * 2;       // a CTA pair keeps half of the W tile in each CTA
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;  // power of two >= 32 for BN in {64,128,256}
   static constexpr int kBarBytes = 5120;  // mbarriers + tmem ptr + bias slice (BN floats) + head weight slice (3*BN floats)
@@ -64,12 +66,19 @@ __device__ __forceinline__ uint32_t bf16x2_pos_mask(uint32_t a) {
 
 // kMN = true: both operands are MN-major (out = A^T B with A [Kred, M], B [Kred, N] row-major; the weight gradient
 // dW = dY^T X without materialising any transpose): segment 0's maps describe A and B with 64 x 64 boxes.
-template <int BN, typename OutT, bool kMN>
+// kCl = 2: CTA pair (tcgen05 cta_group::2).  The two CTAs of a cluster own two vertically adjacent 128-row blocks of
+// the same column block; the leader (rank 0) issues ONE 256 x BN x 16 MMA per step that reads each CTA's A tile and
+// each CTA's HALF of the W tile from their shared memories and accumulates into both TMEMs.  Per SM and K block the
+// shared-memory traffic drops from 48 KB written + 48 KB read to 32 + 32 KB (one-CTA tiles are bound by exactly that:
+// 96 + 96 B/clk against the 128 B/clk of an SM's shared memory), and the ring holds 6 stages instead of 4.
+//   barriers: every TMA of the pair completes on the LEADER's full barrier; the leader's tcgen05.commit multicasts the
+//   "slot free" / "accumulator ready" arrivals to both CTAs; both epilogues arrive on the leader's tmem_empty barrier.
+template <int BN, typename OutT, bool kMN, int kCl>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias, OutT* __restrict__ out, int M, int N,
                int relu, const float* __restrict__ head_w /*[3,N] or null*/,
                float* __restrict__ head_partial /*[N/BN][M][3] or null*/, int ksplit, const EpiX epx) {
-  using C = Cfg<BN, OutT>;
+  using C = Cfg<BN, OutT, kCl>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -94,21 +103,35 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
   const int num_tiles = num_out_tiles * ksplit;
   const int kblocks_all = segs.kb_end[segs.count - 1];
   const int kb_per = (kblocks_all + ksplit - 1) / ksplit;
+  // Work loop.  kCl = 1: CTA b takes tiles b, b + grid, ...  kCl = 2 (no split-K): cluster c takes the tile PAIRS
+  // c, c + clusters, ...; pair p = rows blocks (2*(p / num_n), +1) of column block p % num_n, one per CTA rank.  A rank
+  // whose row block lies beyond M still runs the loads and MMAs (TMA zero-fills, stores are masked): the two CTAs must
+  // stay in lock step because they fill each other's shared memory.
+  const uint32_t crank = (kCl > 1) ? ptx::cluster_ctarank() : 0u;
+  const int w_first = (kCl > 1) ? (int)(blockIdx.x / kCl) : (int)blockIdx.x;
+  const int w_step = (kCl > 1) ? (int)(gridDim.x / kCl) : (int)gridDim.x;
+  const int w_count = (kCl > 1) ? ((num_m + kCl - 1) / kCl) * num_n : num_tiles;
+  auto tile_of = [&](int wi, int& m_blk, int& n_blk, int& split) {
+    if (kCl > 1) { m_blk = kCl * (wi / num_n) + (int)crank; n_blk = wi % num_n; split = 0; }
+    else { const int ot = wi % num_out_tiles; split = wi / num_out_tiles; m_blk = ot / num_n; n_blk = ot % num_n; }
+  };
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < segs.count; ++i) { ptx::prefetch_tensormap(&segs.a[i]); ptx::prefetch_tensormap(&segs.w[i]); }
   }
   if (warp == 1 && lane == 0) {
+    // pair: the leader's full barrier counts the bytes of both producers, its tmem_empty barrier hears both epilogues
     for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tmem_full[b], 1); ptx::mbar_init(&tmem_empty[b], kEpiThreads); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tmem_full[b], 1); ptx::mbar_init(&tmem_empty[b], kCl * kEpiThreads); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_ptr, C::kTmemCols);
-    ptx::tmem_relinquish();
+    if constexpr (kCl > 1) { ptx::tmem_alloc_pair(tmem_ptr, C::kTmemCols); ptx::tmem_relinquish_pair(); }
+    else { ptx::tmem_alloc(tmem_ptr, C::kTmemCols); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (kCl > 1) ptx::cluster_sync();      // the peer's barriers exist before anything is sent to them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -116,12 +139,25 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int ot = tile % num_out_tiles, split = tile / num_out_tiles;
-        const int m_blk = ot / num_n, n_blk = ot % num_n;
+      for (int tile = w_first; tile < w_count; tile += w_step) {
+        int m_blk, n_blk, split;
+        tile_of(tile, m_blk, n_blk, split);
         const int kb_begin = split * kb_per, kb_end = min(kb_begin + kb_per, kblocks_all);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if constexpr (kCl > 1) {
+            // both CTAs' tiles complete on the leader's barrier (address of my barrier mapped into CTA 0)
+            // (the leader alone arrives, expecting the bytes of both CTAs: a remote arrive per K block would put a
+            // cluster round trip on the peer producer's critical path; bytes that land before the leader's
+            // expect_tx just run the transaction count negative until it is posted)
+            const uint32_t lead_bar = ptx::mapa_shared(ptx::smem_u32(&full_bar[stage]), 0);
+            if (crank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], kCl * C::kStageBytes);
+            int sg = 0;
+            while (kb >= segs.kb_end[sg]) ++sg;
+            const int kc = (kb - (sg ? segs.kb_end[sg - 1] : 0)) * BK;
+            ptx::tma_load_2d_pair(smem_a + stage * C::kABytes, &segs.a[sg], lead_bar, kc, m_blk * BM);
+            ptx::tma_load_2d_pair(smem_b + stage * C::kBBytes, &segs.w[sg], lead_bar, kc, n_blk * BN + (int)crank * (BN / kCl));
+          } else {
           ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
           if constexpr (kMN) {
 #pragma unroll
@@ -139,23 +175,25 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
             ptx::tma_load_2d(smem_a + stage * C::kABytes, &segs.a[sg], &full_bar[stage], kc, m_blk * BM);
             ptx::tma_load_2d(smem_b + stage * C::kBBytes, &segs.w[sg], &full_bar[stage], kc, n_blk * BN);
           }
+          }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, kMN);
+    // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
+    if (lane == 0 && (kCl == 1 || crank == 0)) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM * kCl, BN, kMN);
       int stage = 0; uint32_t phase = 0;
       int t = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      for (int tile = w_first; tile < w_count; tile += w_step, ++t) {
         const int buf = t & 1;
         const uint32_t use_phase = (t >> 1) & 1;
         ptx::mbar_wait(&tmem_empty[buf], use_phase ^ 1);  // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
-        const int split = tile / num_out_tiles;
+        int m_blk_u, n_blk_u, split;
+        tile_of(tile, m_blk_u, n_blk_u, split);
         const int kb_begin = split * kb_per, kb_end = min(kb_begin + kb_per, kblocks_all);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
@@ -169,12 +207,15 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
           constexpr uint32_t kstep = kMN ? 128 : 2;
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
-            ptx::umma_bf16(tmem_d, adesc + kstep * k, bdesc + kstep * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            if constexpr (kCl > 1) ptx::umma_bf16_pair(tmem_d, adesc + kstep * k, bdesc + kstep * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            else ptx::umma_bf16(tmem_d, adesc + kstep * k, bdesc + kstep * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
-          ptx::umma_commit(&empty_bar[stage]);  // slot free once these MMAs have read it
+          if constexpr (kCl > 1) ptx::umma_commit_pair(&empty_bar[stage]);   // slot free in both CTAs
+          else ptx::umma_commit(&empty_bar[stage]);  // slot free once these MMAs have read it
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tmem_full[buf]);      // accumulator complete
+        if constexpr (kCl > 1) ptx::umma_commit_pair(&tmem_full[buf]);    // both halves of the accumulator complete
+        else ptx::umma_commit(&tmem_full[buf]);      // accumulator complete
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -189,9 +230,9 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
     constexpr int kRowsPerInstr = 32 / P;         // rows covered by one warp-wide 16-byte store: 8 or 4
     uint8_t* my_stage = staging + ew * (32 * C::kRowBytes);
     int t = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-      const int ot = tile % num_out_tiles, split = tile / num_out_tiles;
-      const int m_blk = ot / num_n, n_blk = ot % num_n;
+    for (int tile = w_first; tile < w_count; tile += w_step, ++t) {
+      int m_blk, n_blk, split;
+      tile_of(tile, m_blk, n_blk, split);
       OutT* const out_t = out ? out + (int64_t)split * M * N : nullptr;
       const int buf = t & 1;
       const uint32_t use_phase = (t >> 1) & 1;
@@ -291,14 +332,19 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
         }
       }
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&tmem_empty[buf]);
+      if constexpr (kCl > 1) ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&tmem_empty[buf]), 0));
+      else ptx::mbar_arrive(&tmem_empty[buf]);
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // bias_s may be overwritten for the next tile
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+  if constexpr (kCl > 1) ptx::cluster_sync();      // nothing of the peer is still in flight towards this CTA
+  if (warp == 2) {
+    if constexpr (kCl > 1) ptx::tmem_dealloc_pair(tmem_base, C::kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+  }
 }
 
 // ---------------------------------------------------------------------------- host side
@@ -339,18 +385,54 @@ int launch(const Segs& segs, const float* bias, void* out, int M, int N, int rel
   using C = Cfg<BN, OutT>;
   static bool attr_set = false;
   if (!attr_set) {
-    LPGNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, OutT, kMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LPGNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, OutT, kMN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        C::kSmemBytes));
     attr_set = true;
   }
   const int tiles = ceil_div(M, BM) * (N / BN) * ksplit;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<BN, OutT, kMN><<<grid, kThreads, C::kSmemBytes, st>>>(segs, bias, reinterpret_cast<OutT*>(out), M, N, relu,
-                                                                  head_w, head_partial, ksplit, epx);
+  gemm_tc_kernel<BN, OutT, kMN, 1><<<grid, kThreads, C::kSmemBytes, st>>>(segs, bias, reinterpret_cast<OutT*>(out), M, N, relu,
+                                                                     head_w, head_partial, ksplit, epx);
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;
 }
+
+// CTA pairs (K-major, no split-K).  `segs.w` must have been encoded with BN / 2 box rows.
+template <int BN, typename OutT>
+int launch_cluster2(const Segs& segs, const float* bias, void* out, int M, int N, int relu, const float* head_w,
+                    float* head_partial, cudaStream_t st, const EpiX& epx) {
+  using C = Cfg<BN, OutT, 2>;
+  static int max_clusters = -1;
+  auto kern = gemm_tc_kernel<BN, OutT, false, 2>;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters < 0) {
+    LPGNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    cfg.gridDim = dim3(sm_count() / 2 * 2);
+    int n = 0;
+    LPGNN_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    max_clusters = n > 0 ? n : 1;
+    if (getenv("LPGNN_DEBUG")) fprintf(stderr, "lpgnn: gemm pair kernel: max active clusters = %d (SMs %d)\n", n, sm_count());
+  }
+  const int pairs = ceil_div(ceil_div(M, BM), 2) * (N / BN);
+  const int clusters = pairs < max_clusters ? pairs : max_clusters;
+  cfg.gridDim = dim3(2 * clusters);
+  OutT* out_t = reinterpret_cast<OutT*>(out);
+  int one = 1;
+  LPGNN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, segs, bias, out_t, M, N, relu, head_w, head_partial, one, epx));
+  count_launches(1);
+  return LPGNN_OK;
+}
+
+int g_gemm_cluster = 1;   // 0 disables the 2-CTA cluster kernel (lpgnn_set_gemm_cluster, for A/B measurements)
 
 }  // namespace
 
@@ -366,6 +448,12 @@ int gemm_tc_run(const void* const* A, const void* const* W, const int* K, int ns
   LPGNN_REQUIRE(out || (head_w && head_partial), "node_transform(bf16): no output requested");
   LPGNN_REQUIRE(!head_w || (head_partial && !out_f32), "node_transform(bf16): fused head needs head_partial and bf16 mode");
   const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
+  // wide layers with many row blocks: pairs of CTAs share the W tiles (see the kernel); bf16 output or fused head only
+  // (long reductions only: with one or two K blocks per tile the kernel is epilogue-bound and the pair's extra
+  // synchronisation costs more than it saves -- measured 103 vs 88 us on the C2 input layer)
+  int kb_total = 0;
+  for (int i = 0; i < nseg; ++i) kb_total += K[i] / BK;
+  const bool use_cluster = g_gemm_cluster && BN == 256 && ksplit == 1 && !out_f32 && M >= 16 * BM && kb_total >= 8;
   Segs segs;
   int kb = 0;
   for (int i = 0; i < nseg; ++i) {
@@ -373,7 +461,7 @@ int gemm_tc_run(const void* const* A, const void* const* W, const int* K, int ns
                   K[i]);
     LPGNN_REQUIRE((uintptr_t)A[i] % 16 == 0 && (uintptr_t)W[i] % 16 == 0, "node_transform(bf16): operands must be 16-byte aligned");
     if (int rc = make_map(&segs.a[i], A[i], M, K[i], BM)) return rc;
-    if (int rc = make_map(&segs.w[i], W[i], N, K[i], BN)) return rc;
+    if (int rc = make_map(&segs.w[i], W[i], N, K[i], use_cluster ? BN / 2 : BN)) return rc;
     kb += K[i] / BK;
     segs.kb_end[i] = kb;
   }
@@ -387,6 +475,7 @@ int gemm_tc_run(const void* const* A, const void* const* W, const int* K, int ns
     if (BN == 128) LPGNN_GO(128, float);
     LPGNN_GO(64, float);
   }
+  if (use_cluster) return launch_cluster2<256, __nv_bfloat16>(segs, bias, out, M, N, relu, head_w, head_partial, st, epx);
   if (BN == 256) LPGNN_GO(256, __nv_bfloat16);
   if (BN == 128) LPGNN_GO(128, __nv_bfloat16);
   LPGNN_GO(64, __nv_bfloat16);
@@ -436,3 +525,11 @@ int node_transform_bf16(const void* A1, int K1, const void* W1, const void* A2, 
 }
 
 }  // namespace lpgnn
+
+// Tuning knob: enable (default) / disable the 2-CTA cluster form of the wide bf16 transform; returns the previous
+// setting.  Results are identical either way (same MMAs in the same order per output tile).
+extern "C" int lpgnn_set_gemm_cluster(int enable) {
+  const int prev = lpgnn::g_gemm_cluster;
+  lpgnn::g_gemm_cluster = enable ? 1 : 0;
+  return prev;
+}
