@@ -36,7 +36,7 @@ template <int BN, typename OutT, int kCl = 1> struct Cfg {
   static constexpr int kRowBytes = 32 * (int)sizeof(OutT);   // one staged piece: 32 columns of one row
   static constexpr int kStagingBytes = kEpiWarps * 32 * kRowBytes;
   static constexpr bool kWide = sizeof(OutT) == 4;   // fp32 output needs twice the staging space
-  static constexpr int kStages = (kCl == 2) ? 6 : (BN == 256) ? (kWide ? 3 : 4) : (BN == 128 ? (kWide ? 5 : 6) : (kWide ? 6 : 8));
+  static constexpr int kStages = (kCl == 2) ? (kWide ? 5 : 6) : (BN == 256) ? (kWide ? 3 : 4) : (BN == 128 ? (kWide ? 5 : 6) : (kWide ? 6 : 8));
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (BN / kCl) * BK * 2;       // a CTA pair keeps half of the W tile in each CTA
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -110,9 +110,10 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
   const uint32_t crank = (kCl > 1) ? ptx::cluster_ctarank() : 0u;
   const int w_first = (kCl > 1) ? (int)(blockIdx.x / kCl) : (int)blockIdx.x;
   const int w_step = (kCl > 1) ? (int)(gridDim.x / kCl) : (int)gridDim.x;
-  const int w_count = (kCl > 1) ? ((num_m + kCl - 1) / kCl) * num_n : num_tiles;
+  const int num_pairs = ((num_m + kCl - 1) / kCl) * num_n;            // output tile pairs (kCl = 2)
+  const int w_count = (kCl > 1) ? num_pairs * ksplit : num_tiles;
   auto tile_of = [&](int wi, int& m_blk, int& n_blk, int& split) {
-    if (kCl > 1) { m_blk = kCl * (wi / num_n) + (int)crank; n_blk = wi % num_n; split = 0; }
+    if (kCl > 1) { const int op = wi % num_pairs; split = wi / num_pairs; m_blk = kCl * (op / num_n) + (int)crank; n_blk = op % num_n; }
     else { const int ot = wi % num_out_tiles; split = wi / num_out_tiles; m_blk = ot / num_n; n_blk = ot % num_n; }
   };
 
@@ -152,11 +153,21 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
             // expect_tx just run the transaction count negative until it is posted)
             const uint32_t lead_bar = ptx::mapa_shared(ptx::smem_u32(&full_bar[stage]), 0);
             if (crank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], kCl * C::kStageBytes);
-            int sg = 0;
-            while (kb >= segs.kb_end[sg]) ++sg;
-            const int kc = (kb - (sg ? segs.kb_end[sg - 1] : 0)) * BK;
-            ptx::tma_load_2d_pair(smem_a + stage * C::kABytes, &segs.a[sg], lead_bar, kc, m_blk * BM);
-            ptx::tma_load_2d_pair(smem_b + stage * C::kBBytes, &segs.w[sg], lead_bar, kc, n_blk * BN + (int)crank * (BN / kCl));
+            if constexpr (kMN) {
+#pragma unroll
+              for (int i = 0; i < BM / 64; ++i)
+                ptx::tma_load_2d_pair(smem_a + stage * C::kABytes + i * 8192, &segs.a[0], lead_bar, m_blk * BM + 64 * i, kb * BK);
+#pragma unroll
+              for (int i = 0; i < BN / kCl / 64; ++i)
+                ptx::tma_load_2d_pair(smem_b + stage * C::kBBytes + i * 8192, &segs.w[0], lead_bar,
+                                      n_blk * BN + (int)crank * (BN / kCl) + 64 * i, kb * BK);
+            } else {
+              int sg = 0;
+              while (kb >= segs.kb_end[sg]) ++sg;
+              const int kc = (kb - (sg ? segs.kb_end[sg - 1] : 0)) * BK;
+              ptx::tma_load_2d_pair(smem_a + stage * C::kABytes, &segs.a[sg], lead_bar, kc, m_blk * BM);
+              ptx::tma_load_2d_pair(smem_b + stage * C::kBBytes, &segs.w[sg], lead_bar, kc, n_blk * BN + (int)crank * (BN / kCl));
+            }
           } else {
           ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
           if constexpr (kMN) {
@@ -399,12 +410,12 @@ int launch(const Segs& segs, const float* bias, void* out, int M, int N, int rel
 }
 
 // CTA pairs (K-major, no split-K).  `segs.w` must have been encoded with BN / 2 box rows.
-template <int BN, typename OutT>
+template <int BN, typename OutT, bool kMN = false>
 int launch_cluster2(const Segs& segs, const float* bias, void* out, int M, int N, int relu, const float* head_w,
-                    float* head_partial, cudaStream_t st, const EpiX& epx) {
+                    float* head_partial, cudaStream_t st, const EpiX& epx, int ksplit = 1) {
   using C = Cfg<BN, OutT, 2>;
   static int max_clusters = -1;
-  auto kern = gemm_tc_kernel<BN, OutT, false, 2>;
+  auto kern = gemm_tc_kernel<BN, OutT, kMN, 2>;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -422,12 +433,11 @@ int launch_cluster2(const Segs& segs, const float* bias, void* out, int M, int N
     max_clusters = n > 0 ? n : 1;
     if (getenv("LPGNN_DEBUG")) fprintf(stderr, "lpgnn: gemm pair kernel: max active clusters = %d (SMs %d)\n", n, sm_count());
   }
-  const int pairs = ceil_div(ceil_div(M, BM), 2) * (N / BN);
+  const int pairs = ceil_div(ceil_div(M, BM), 2) * (N / BN) * ksplit;
   const int clusters = pairs < max_clusters ? pairs : max_clusters;
   cfg.gridDim = dim3(2 * clusters);
   OutT* out_t = reinterpret_cast<OutT*>(out);
-  int one = 1;
-  LPGNN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, segs, bias, out_t, M, N, relu, head_w, head_partial, one, epx));
+  LPGNN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, segs, bias, out_t, M, N, relu, head_w, head_partial, ksplit, epx));
   count_launches(1);
   return LPGNN_OK;
 }
@@ -509,6 +519,9 @@ int gemm_tc_mn(const void* A, const void* B, int64_t Kred, int M, int N, void* o
   for (int i = 0; i < kMaxSegs; ++i) { if (i) { segs.a[i] = segs.a[0]; segs.w[i] = segs.w[0]; } segs.kb_end[i] = kb; }
   segs.count = 1;
   LPGNN_REQUIRE(ksplit >= 1 && ksplit <= kb, "gemm_mn: bad ksplit %d for %d K blocks", ksplit, kb);
+  // wide weight gradients: CTA pairs (M = output rows = dY columns must give whole pairs of 128-row blocks)
+  if (g_gemm_cluster && BN == 256 && M % (2 * BM) == 0 && kb / ksplit >= 8)
+    return launch_cluster2<256, float, true>(segs, nullptr, out, M, N, 0, nullptr, nullptr, st, EpiX(), ksplit);
   if (BN == 256) return launch<256, float, true>(segs, nullptr, out, M, N, 0, nullptr, nullptr, ksplit, st);
   if (BN == 128) return launch<128, float, true>(segs, nullptr, out, M, N, 0, nullptr, nullptr, ksplit, st);
   return launch<64, float, true>(segs, nullptr, out, M, N, 0, nullptr, nullptr, ksplit, st);

@@ -150,3 +150,60 @@ def test_transform_fp32_via_split_bf16_tensor_core_passes(cuda, M, N, K1, K2, pa
     assert err < tol, err
     y_simt = ops.node_transform(a1, w1, a2, w2, b, relu=True)
     assert float((y - y_simt).abs().max()) < 2e-4 * max(1.0, float(e.abs().max()))
+
+
+@pytest.mark.parametrize("M", [2048, 2049, 2304, 5000, 33_333])
+def test_cta_pair_transform_is_bit_identical_to_single_cta(cuda, M):
+    """The cta_group::2 form of the wide bf16 transform (two CTAs, one 256-row MMA, half of W per CTA) against the
+    one-CTA-per-tile kernel: same MMAs per output element -> same bits; odd row-block counts exercise the pair whose
+    second CTA lies beyond M; with ReLU, bias, the fused head, and the training epilogues (mask, dropout)."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import _lib, ops
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(M)
+    bf = torch.bfloat16
+    a1 = torch.randn(M, 1024, device=cuda, generator=g).to(bf)
+    a2 = torch.randn(M, 512, device=cuda, generator=g).to(bf)
+    w1 = (torch.randn(1024, 1024, device=cuda, generator=g) / 32).to(bf)
+    w2 = (torch.randn(1024, 512, device=cuda, generator=g) / 32).to(bf)
+    b = torch.randn(1024, device=cuda, generator=g)
+    hw, hb = torch.randn(3, 1024, device=cuda, generator=g), torch.randn(3, device=cuda, generator=g)
+    x = torch.randn(M, 8, device=cuda, generator=g)
+    act = torch.randn(M, 1024, device=cuda, generator=g).to(bf)
+    outs = {}
+    try:
+        for mode in (0, 1):
+            lib.lpgnn_set_gemm_cluster(mode)
+            head = ops.node_transform_head(a1, w1, a2, w2, b, hw, hb, x)
+            outs[mode] = (ops.node_transform(a1, w1, a2, w2, b, relu=True),
+                          ops.node_transform(a1, w1, None, None, None, relu=False),
+                          head[0] if isinstance(head, tuple) else head,
+                          ops.node_transform(a1, w1, a2, w2, b, relu=True, dropout=(0.1, 1234)),
+                          ops.node_transform(a1, w1, a2, w2, None, relu=False, mask=(act, 1.0 / 0.9)))
+    finally:
+        lib.lpgnn_set_gemm_cluster(1)
+    for u, v in zip(outs[0], outs[1]):
+        assert torch.equal(u, v)
+    ref = torch.relu(a1.float() @ w1.float().t() + a2.float() @ w2.float().t() + b)
+    assert float((outs[1][0].float() - ref).abs().max()) < 0.05 * float(ref.abs().max())
+
+
+def test_cta_pair_wgrad_is_bit_identical_to_single_cta(cuda):
+    """Weight gradient dW = dY^T X (MN-major operands, split-K) in the pair form vs the one-CTA form and vs fp32 torch."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import _lib, ops
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    Mn = 30_000
+    dy = torch.randn(Mn, 1024, device=cuda, generator=g).to(torch.bfloat16)
+    xx = torch.randn(Mn, 1024, device=cuda, generator=g).to(torch.bfloat16)
+    try:
+        lib.lpgnn_set_gemm_cluster(0)
+        d0 = ops.wgrad(dy, xx)
+        lib.lpgnn_set_gemm_cluster(1)
+        d1 = ops.wgrad(dy, xx)
+    finally:
+        lib.lpgnn_set_gemm_cluster(1)
+    assert torch.equal(d0, d1)
+    ref = dy.float().t() @ xx.float()
+    assert float((d1 - ref).abs().max()) < 2e-3 * float(ref.abs().max())
