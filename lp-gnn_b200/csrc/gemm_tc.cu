@@ -73,12 +73,16 @@ __device__ __forceinline__ uint32_t bf16x2_pos_mask(uint32_t a) {
 // 96 + 96 B/clk against the 128 B/clk of an SM's shared memory), and the ring holds 6 stages instead of 4.
 //   barriers: every TMA of the pair completes on the LEADER's full barrier; the leader's tcgen05.commit multicasts the
 //   "slot free" / "accumulator ready" arrivals to both CTAs; both epilogues arrive on the leader's tmem_empty barrier.
-template <int BN, typename OutT, bool kMN, int kCl>
+// kEpi selects the epilogue features that are COMPILED IN (bit 0: fused basis-status head, bit 1: training extras --
+// keep-mask, dropout, output scale).  Predicated-off code still costs issue slots, and with one or two K blocks per
+// tile the kernel is bound by the epilogue's instruction stream, so the plain transform carries none of it.
+template <int BN, typename OutT, bool kMN, int kCl, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias, OutT* __restrict__ out, int M, int N,
                int relu, const float* __restrict__ head_w /*[3,N] or null*/,
                float* __restrict__ head_partial /*[N/BN][M][3] or null*/, int ksplit, const EpiX epx) {
   using C = Cfg<BN, OutT, kCl>;
+  constexpr bool kHead = (kEpi & 1) != 0, kEpx = (kEpi & 2) != 0;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -249,7 +253,7 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
       const uint32_t use_phase = (t >> 1) & 1;
       // stage the bias (and head weight) slice of this tile
       for (int j = et; j < BN; j += kEpiThreads) bias_s[j] = bias ? __ldg(bias + n_blk * BN + j) : 0.f;
-      if (head_w)
+      if (kHead && head_w)
         for (int j = et; j < 3 * BN; j += kEpiThreads)
           headw_s[j] = __ldg(head_w + (int64_t)(j / BN) * N + n_blk * BN + (j % BN));
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
@@ -276,9 +280,9 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
             float v0 = __uint_as_float(r[2 * j]) + bias_s[pc * 32 + 2 * j];
             float v1 = __uint_as_float(r[2 * j + 1]) + bias_s[pc * 32 + 2 * j + 1];
             if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-            v0 *= epx.out_scale; v1 *= epx.out_scale;
+            if constexpr (kEpx) { v0 *= epx.out_scale; v1 *= epx.out_scale; }
             packed[j] = pack_bf16(v0, v1);
-            if (head_w) {
+            if (kHead && head_w) {
               const int col = pc * 32 + 2 * j;
               hd0 = fmaf(v0, headw_s[col], hd0);          hd0 = fmaf(v1, headw_s[col + 1], hd0);
               hd1 = fmaf(v0, headw_s[BN + col], hd1);     hd1 = fmaf(v1, headw_s[BN + col + 1], hd1);
@@ -313,13 +317,13 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
             const int64_t e0 = grow * N + (int64_t)n_blk * BN + pc * 32;   // first element of this row piece
             if constexpr (sizeof(OutT) == 2) {
               // keep-masks act on whole bf16 lanes of the 16-byte chunk this thread stores (elements e0 + piece*8 ..)
-              if (epx.mask_act) {
+              if (kEpx && epx.mask_act) {
                 const uint4 a = __ldg(reinterpret_cast<const uint4*>(
                     reinterpret_cast<const uint8_t*>(epx.mask_act) + (e0 * 2 + piece * 16)));
                 v.x &= bf16x2_pos_mask(a.x); v.y &= bf16x2_pos_mask(a.y);
                 v.z &= bf16x2_pos_mask(a.z); v.w &= bf16x2_pos_mask(a.w);
               }
-              if (epx.drop_threshold) {
+              if (kEpx && epx.drop_threshold) {
                 const uint64_t i0 = (uint64_t)(e0 + piece * 8);
                 auto keep2 = [&](int k) -> uint32_t {
                   const uint32_t lo = dropout_keep(epx.drop_seed, i0 + 2 * k, epx.drop_threshold) ? 0x0000ffffu : 0u;
@@ -335,7 +339,7 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
         }
         __syncwarp();
       }
-      if (head_partial) {
+      if (kHead && head_partial) {
         const int64_t grow = row_base + lane;
         if (grow < M) {
           float* hp = head_partial + ((int64_t)(n_blk * 2 + hsel) * M + grow) * 3;
@@ -390,32 +394,55 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int bo
   return LPGNN_OK;
 }
 
-template <int BN, typename OutT, bool kMN = false>
-int launch(const Segs& segs, const float* bias, void* out, int M, int N, int relu, const float* head_w,
-           float* head_partial, int ksplit, cudaStream_t st, const EpiX& epx = EpiX()) {
+template <int BN, typename OutT, bool kMN, int kEpi>
+int launch_epi(const Segs& segs, const float* bias, void* out, int M, int N, int relu, const float* head_w,
+               float* head_partial, int ksplit, cudaStream_t st, const EpiX& epx) {
   using C = Cfg<BN, OutT>;
   static bool attr_set = false;
+  auto kern = gemm_tc_kernel<BN, OutT, kMN, 1, kEpi>;
   if (!attr_set) {
-    LPGNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, OutT, kMN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       C::kSmemBytes));
+    LPGNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
   const int tiles = ceil_div(M, BM) * (N / BN) * ksplit;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<BN, OutT, kMN, 1><<<grid, kThreads, C::kSmemBytes, st>>>(segs, bias, reinterpret_cast<OutT*>(out), M, N, relu,
-                                                                     head_w, head_partial, ksplit, epx);
+  kern<<<grid, kThreads, C::kSmemBytes, st>>>(segs, bias, reinterpret_cast<OutT*>(out), M, N, relu, head_w, head_partial,
+                                              ksplit, epx);
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;
 }
 
-// CTA pairs (K-major, no split-K).  `segs.w` must have been encoded with BN / 2 box rows.
+inline int epi_features(const float* head_w, const EpiX& epx) {
+  return (head_w ? 1 : 0) | ((epx.mask_act || epx.drop_threshold || epx.out_scale != 1.f) ? 2 : 0);
+}
+
 template <int BN, typename OutT, bool kMN = false>
-int launch_cluster2(const Segs& segs, const float* bias, void* out, int M, int N, int relu, const float* head_w,
-                    float* head_partial, cudaStream_t st, const EpiX& epx, int ksplit = 1) {
+int launch(const Segs& segs, const float* bias, void* out, int M, int N, int relu, const float* head_w,
+           float* head_partial, int ksplit, cudaStream_t st, const EpiX& epx = EpiX()) {
+  // the wide bf16 tile gets one instantiation per feature set; fp32 outputs and MN-major operands never use the
+  // extras, the narrow tiles (rare, small) share the full-featured one
+  if constexpr (sizeof(OutT) == 4 || kMN) {
+    return launch_epi<BN, OutT, kMN, 0>(segs, bias, out, M, N, relu, head_w, head_partial, ksplit, st, epx);
+  } else if constexpr (BN != 256) {
+    return launch_epi<BN, OutT, kMN, 3>(segs, bias, out, M, N, relu, head_w, head_partial, ksplit, st, epx);
+  } else {
+    switch (epi_features(head_w, epx)) {
+      case 0: return launch_epi<BN, OutT, kMN, 0>(segs, bias, out, M, N, relu, head_w, head_partial, ksplit, st, epx);
+      case 1: return launch_epi<BN, OutT, kMN, 1>(segs, bias, out, M, N, relu, head_w, head_partial, ksplit, st, epx);
+      case 2: return launch_epi<BN, OutT, kMN, 2>(segs, bias, out, M, N, relu, head_w, head_partial, ksplit, st, epx);
+      default: return launch_epi<BN, OutT, kMN, 3>(segs, bias, out, M, N, relu, head_w, head_partial, ksplit, st, epx);
+    }
+  }
+}
+
+// CTA pairs (K-major, no split-K).  `segs.w` must have been encoded with BN / 2 box rows.
+template <int BN, typename OutT, bool kMN, int kEpi>
+int launch_cluster2_epi(const Segs& segs, const float* bias, void* out, int M, int N, int relu, const float* head_w,
+                        float* head_partial, cudaStream_t st, const EpiX& epx, int ksplit) {
   using C = Cfg<BN, OutT, 2>;
   static int max_clusters = -1;
-  auto kern = gemm_tc_kernel<BN, OutT, kMN, 2>;
+  auto kern = gemm_tc_kernel<BN, OutT, kMN, 2, kEpi>;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -440,6 +467,21 @@ int launch_cluster2(const Segs& segs, const float* bias, void* out, int M, int N
   LPGNN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, segs, bias, out_t, M, N, relu, head_w, head_partial, ksplit, epx));
   count_launches(1);
   return LPGNN_OK;
+}
+
+template <int BN, typename OutT, bool kMN = false>
+int launch_cluster2(const Segs& segs, const float* bias, void* out, int M, int N, int relu, const float* head_w,
+                    float* head_partial, cudaStream_t st, const EpiX& epx, int ksplit = 1) {
+  if constexpr (sizeof(OutT) == 4 || kMN) {
+    return launch_cluster2_epi<BN, OutT, kMN, 0>(segs, bias, out, M, N, relu, head_w, head_partial, st, epx, ksplit);
+  } else {
+    switch (epi_features(head_w, epx)) {
+      case 0: return launch_cluster2_epi<BN, OutT, kMN, 0>(segs, bias, out, M, N, relu, head_w, head_partial, st, epx, ksplit);
+      case 1: return launch_cluster2_epi<BN, OutT, kMN, 1>(segs, bias, out, M, N, relu, head_w, head_partial, st, epx, ksplit);
+      case 2: return launch_cluster2_epi<BN, OutT, kMN, 2>(segs, bias, out, M, N, relu, head_w, head_partial, st, epx, ksplit);
+      default: return launch_cluster2_epi<BN, OutT, kMN, 3>(segs, bias, out, M, N, relu, head_w, head_partial, st, epx, ksplit);
+    }
+  }
 }
 
 int g_gemm_cluster = 1;   // 0 disables the 2-CTA cluster kernel (lpgnn_set_gemm_cluster, for A/B measurements)
