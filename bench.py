@@ -513,7 +513,7 @@ def kernel_rooflines(model, lp, dev, peaks, bf16, args):
     t_b2 = time_kernel(lambda: BipartiteCSR.from_coo(h_row, h_col, h_val, m, n, is_sorted=False), reps, flush)
     add("graph_build (unsorted COO->CSR+CSC)", "hbm", t_b2, z * 12 * 2 * 3, -1)
     # measured DRAM traffic per launch from the committed ncu --set full capture (same workload / precision only)
-    tpath = os.path.join(ROOT, "profiles", "r01c_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01d_traffic.json")
     if os.path.isfile(tpath):
         tj = json.load(open(tpath))
         if tj.get("workload") == args.workload and tj.get("precision") == args.precision and args.structure == "staircase":
