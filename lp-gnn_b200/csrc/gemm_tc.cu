@@ -85,7 +85,9 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
   constexpr bool kHead = (kEpi & 1) != 0, kEpx = (kEpi & 2) != 0;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle atoms
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (aligned by OFFSET, not by rounding the pointer through an integer: that would turn every access to the staging area
+  // and the epilogue constants into generic LD / ST -- long-scoreboard latency on each -- instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::kStages * C::kABytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
