@@ -154,3 +154,35 @@ def test_train_and_validate_on_lp_above_threshold(cuda, tmp_path):
     full = dataset.MyToBipartite(thresh_num=np.inf)(ds.get(0))
     fc, fv = val.model_inference_with_batch(model, full, args)
     assert float((lc - fc).abs().max()) < 1e-3 and float((lv - fv).abs().max()) < 1e-3
+
+
+def test_induced_fill_writes_only_its_output(cuda):
+    """Canary regions around the COO arrays written by lpgnn_induced_fill (no compute-sanitizer on the GPU pool)."""
+    from lpgnn_b200 import _lib
+    lib = _lib.load()
+    m, n = 1500, 3000
+    lp, res, A = _resident(m, n, 13, cuda, "uniform")
+    (ptr_, idx, val, _), _ = res.graph.views()
+    rng = np.random.default_rng(0)
+    cons = torch.from_numpy(rng.permutation(m)[:700].astype(np.int32)).to(cuda)
+    vars_ = rng.permutation(n)[:1100]
+    map_v = torch.full((n,), -1, dtype=torch.int32, device=cuda)
+    map_v[torch.from_numpy(vars_).to(cuda)] = torch.arange(len(vars_), dtype=torch.int32, device=cuda)
+    counts = torch.zeros(700, dtype=torch.int32, device=cuda)
+    _lib.check(lib.lpgnn_induced_count(ptr_.data_ptr(), idx.data_ptr(), cons.data_ptr(), 700, map_v.data_ptr(), counts.data_ptr(),
+                                       _lib.stream_ptr()), "count")
+    csum = torch.cumsum(counts.long(), 0)
+    z = int(csum[-1])
+    offsets = (csum - counts.long()).contiguous()
+    pad = 256
+    bufs = [torch.full((z + 2 * pad,), -7, dtype=torch.int32, device=cuda) for _ in range(2)] + \
+           [torch.full((z + 2 * pad,), -7.0, dtype=torch.float32, device=cuda)]
+    _lib.check(lib.lpgnn_induced_fill(ptr_.data_ptr(), idx.data_ptr(), val.data_ptr(), cons.data_ptr(), 700, map_v.data_ptr(),
+                                      offsets.data_ptr(), bufs[0][pad:].data_ptr(), bufs[1][pad:].data_ptr(),
+                                      bufs[2][pad:].data_ptr(), _lib.stream_ptr()), "fill")
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert bool((b[:pad] == -7).all()) and bool((b[pad + z:] == -7).all())
+    sub = A[cons.cpu().numpy()][:, vars_]
+    assert z == sub.nnz
+    assert bool((bufs[0][pad:pad + z] >= 0).all()) and int(bufs[1][pad:pad + z].max()) < len(vars_)

@@ -143,3 +143,28 @@ def test_sweep_kernel_ragged_rows(cuda):
         y = ops.spmm(g.views()[0], xd, slab_bytes=slab, unroll=unroll).cpu().numpy()
         np.testing.assert_allclose(y, e, rtol=1e-5, atol=1e-4)
         assert not y[lens == 0].any()
+
+
+def test_sweep_kernel_writes_only_its_output(cuda):
+    """Canary regions around Y (compute-sanitizer is not available on the GPU pool): the banded sweep with a row count
+    that is not a multiple of its 32 warps, nor of the per-CTA row range, must not touch a byte outside [rows, F]."""
+    from lpgnn_b200 import _lib, synth
+    from lpgnn_b200.graph import BipartiteCSR
+    lib = _lib.load()
+    m, n, F = 10_013, 20_011, 512
+    c, b_l, A, b_u, l, u = synth.raw_lp(m, n, 5 * n, 41)
+    A = A.tocsr(); A.sort_indices()
+    row = np.repeat(np.arange(m), np.diff(A.indptr))
+    g = BipartiteCSR.from_coo_arrays(row, A.indices, (A.data / 10).astype(np.float32), m, n, cuda, is_sorted=True)
+    for dtype in (torch.float32, torch.bfloat16):
+        for (ptr_, idx, val, rows), src_rows in zip(g.views(), (n, m)):
+            x = torch.randn(src_rows, F, device=cuda).to(dtype)
+            pad = 4096
+            buf = torch.full((rows * F + 2 * pad,), 7.0, device=cuda).to(dtype)
+            y = buf[pad:pad + rows * F]
+            for slab in (512, 1024):
+                rc = lib.lpgnn_spmm_ex(ptr_.data_ptr(), idx.data_ptr(), val.data_ptr(), rows, x.data_ptr(), y.data_ptr(), F,
+                                       _lib.dtype_code(dtype), slab, 0, _lib.stream_ptr())
+                _lib.check(rc, "spmm_ex")
+                torch.cuda.synchronize()
+                assert bool((buf[:pad] == 7.0).all()) and bool((buf[pad + rows * F:] == 7.0).all())
