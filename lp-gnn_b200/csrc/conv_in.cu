@@ -36,6 +36,52 @@ gather_cat_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ i
   const int32_t beg = ptr[row], end = ptr[row + 1];
   float* zr = z ? z + row * KT : nullptr;
   __nv_bfloat16* zbr = zb ? zb + row * 64 : nullptr;
+  if (k_src == 8 && k_dst == 8) {
+    // The reference's shape (GCN_FC(8, 8, ...)): lane f0 aggregates feature f0, the 8 lanes of the row exchange their
+    // sums, and every lane then writes ONE 16-byte chunk of the row -- a single coalesced store per output instead of
+    // 8 scalar ones per lane.
+    float v = 0.f;
+    int32_t e = beg;
+    for (; e + 4 <= end; e += 4) {
+      const int32_t i0 = __ldg(idx + e), i1 = __ldg(idx + e + 1), i2 = __ldg(idx + e + 2), i3 = __ldg(idx + e + 3);
+      const float w0 = __ldg(val + e), w1 = __ldg(val + e + 1), w2 = __ldg(val + e + 2), w3 = __ldg(val + e + 3);
+      const float x0 = __ldg(Xsrc + (int64_t)i0 * 8 + f0), x1 = __ldg(Xsrc + (int64_t)i1 * 8 + f0);
+      const float x2 = __ldg(Xsrc + (int64_t)i2 * 8 + f0), x3 = __ldg(Xsrc + (int64_t)i3 * 8 + f0);
+      v = fmaf(w0, x0, v); v = fmaf(w1, x1, v); v = fmaf(w2, x2, v); v = fmaf(w3, x3, v);   // CSR order
+    }
+    for (; e < end; ++e) v = fmaf(__ldg(val + e), __ldg(Xsrc + (int64_t)__ldg(idx + e) * 8 + f0), v);
+    const int gbase = (threadIdx.x & 31) & ~7;
+    const uint32_t gmask = 0xffu << gbase;
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = __shfl_sync(gmask, v, gbase + k);
+    float4 xa, xb;                        // the node's own 8 features (vector loads only when the caller's array allows)
+    if ((reinterpret_cast<uintptr_t>(Xdst) & 15) == 0) {
+      const float4* xd = reinterpret_cast<const float4*>(Xdst + row * 8);
+      xa = __ldg(xd); xb = __ldg(xd + 1);
+    } else {
+      const float* xd = Xdst + row * 8;
+      xa = make_float4(__ldg(xd), __ldg(xd + 1), __ldg(xd + 2), __ldg(xd + 3));
+      xb = make_float4(__ldg(xd + 4), __ldg(xd + 5), __ldg(xd + 6), __ldg(xd + 7));
+    }
+    if (zr && f0 < KT / 4) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f0 == 0) o = make_float4(a[0], a[1], a[2], a[3]);
+      else if (f0 == 1) o = make_float4(a[4], a[5], a[6], a[7]);
+      else if (f0 == 2) o = xa;
+      else if (f0 == 3) o = xb;
+      reinterpret_cast<float4*>(zr)[f0] = o;
+    }
+    if (KT / 4 > 8 && zr) for (int c = 8 + f0; c < KT / 4; c += 8) reinterpret_cast<float4*>(zr)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (zbr) {
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (f0 == 0) o = make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
+      else if (f0 == 1) o = make_uint4(pack_bf16(xa.x, xa.y), pack_bf16(xa.z, xa.w), pack_bf16(xb.x, xb.y), pack_bf16(xb.z, xb.w));
+      else if (f0 == 2) o.x = pack_bf16(1.f, 0.f);   // column K = 16 carries 1.0 (bias gradient through lpgnn_wgrad)
+      reinterpret_cast<uint4*>(zbr)[f0] = o;
+    }
+    return;
+  }
   for (int k = f0; k < k_src; k += 8) {
     float v = 0.f;
     int32_t e = beg;
