@@ -244,8 +244,7 @@ int launch_sweep(const int32_t* ptr, const int32_t* idx, const float* val, int32
   const int nslabs = chunks / (32 * CH);
   constexpr int kWarps = kSweepThreads / 32;
   const int want_blocks = max(1, sm_count() / nslabs);          // one CTA per SM, all co-resident
-  int rows_per_block = ceil_div(rows, want_blocks);
-  rows_per_block = ceil_div(rows_per_block, kWarps) * kWarps;
+  const int rows_per_block = max(ceil_div(rows, want_blocks), kWarps);   // even split: every SM gets the same share
   const int nblocks = ceil_div(rows, rows_per_block);
   static bool carved = false;      // no shared memory is used: ask for the whole 228 KB as L1 (it holds the band)
   if (!carved) {
