@@ -59,9 +59,23 @@ __device__ __forceinline__ uint32_t hash_u64(uint64_t x) {  // splitmix64 finali
   x ^= x >> 31;
   return (uint32_t)(x >> 32);
 }
-// keep-decision of lpgnn_dropout for element `idx` (shared by the stand-alone kernel and the fused epilogue)
+// Keep-decisions of lpgnn_dropout (shared by the stand-alone kernel and the fused GEMM epilogue).  One 64-bit hash
+// serves FOUR consecutive elements (a 16-bit field each, compared against the top 16 bits of the threshold), so an
+// epilogue thread that stores 8 elements pays two hashes instead of eight: P(drop) = (threshold >> 16) / 2^16.
+__device__ __forceinline__ uint64_t hash64(uint64_t x) {  // splitmix64 finaliser
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+// bit k of the result = element 4*quad + k is kept
+__device__ __forceinline__ uint32_t dropout_keep4(uint64_t seed, uint64_t quad, uint32_t threshold) {
+  const uint64_t h = hash64(seed ^ quad * 0xD6E8FEB86659FD93ull);
+  const uint32_t t = threshold >> 16, lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+  return ((lo & 0xffffu) >= t ? 1u : 0u) | ((lo >> 16) >= t ? 2u : 0u) | ((hi & 0xffffu) >= t ? 4u : 0u) | ((hi >> 16) >= t ? 8u : 0u);
+}
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, uint32_t threshold) {
-  return hash_u64(seed ^ idx * 0xD6E8FEB86659FD93ull) >= threshold;
+  return (dropout_keep4(seed, idx >> 2, threshold) >> (idx & 3)) & 1u;
 }
 #endif
 

@@ -273,6 +273,21 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
         const int pc = hsel * kPiecesPerWarp + pi;
         uint32_t r[32];
         ptx::tmem_ld_32x32(taddr + pc * 32, r);
+        // keep-mask activations of the chunks this thread will store: fetched now, used after the staging round trip
+        constexpr int kStoreIters = 32 / kRowsPerInstr;
+        uint4 am[(kEpx && sizeof(OutT) == 2) ? kStoreIters : 1];
+        if constexpr (kEpx && sizeof(OutT) == 2) {
+          if (epx.mask_act && out) {
+#pragma unroll
+            for (int i = 0; i < kStoreIters; ++i) {
+              const int64_t grow = row_base + kRowsPerInstr * i + lane / P;
+              am[i] = make_uint4(0u, 0u, 0u, 0u);
+              if (grow < M)
+                am[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(epx.mask_act) +
+                                                             ((grow * N + (int64_t)n_blk * BN + pc * 32) * 2 + (lane % P) * 16)));
+            }
+          }
+        }
         ptx::tmem_ld_wait();
         uint4* srow = reinterpret_cast<uint4*>(my_stage + lane * C::kRowBytes);
         if constexpr (sizeof(OutT) == 2) {
@@ -320,19 +335,16 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
             if constexpr (sizeof(OutT) == 2) {
               // keep-masks act on whole bf16 lanes of the 16-byte chunk this thread stores (elements e0 + piece*8 ..)
               if (kEpx && epx.mask_act) {
-                const uint4 a = __ldg(reinterpret_cast<const uint4*>(
-                    reinterpret_cast<const uint8_t*>(epx.mask_act) + (e0 * 2 + piece * 16)));
+                const uint4 a = am[i];
                 v.x &= bf16x2_pos_mask(a.x); v.y &= bf16x2_pos_mask(a.y);
                 v.z &= bf16x2_pos_mask(a.z); v.w &= bf16x2_pos_mask(a.w);
               }
               if (kEpx && epx.drop_threshold) {
-                const uint64_t i0 = (uint64_t)(e0 + piece * 8);
-                auto keep2 = [&](int k) -> uint32_t {
-                  const uint32_t lo = dropout_keep(epx.drop_seed, i0 + 2 * k, epx.drop_threshold) ? 0x0000ffffu : 0u;
-                  const uint32_t hi = dropout_keep(epx.drop_seed, i0 + 2 * k + 1, epx.drop_threshold) ? 0xffff0000u : 0u;
-                  return lo | hi;
-                };
-                v.x &= keep2(0); v.y &= keep2(1); v.z &= keep2(2); v.w &= keep2(3);
+                const uint64_t q0 = (uint64_t)(e0 + piece * 8) >> 2;       // this thread's 8 elements = 2 hash quads
+                const uint32_t k0 = dropout_keep4(epx.drop_seed, q0, epx.drop_threshold);
+                const uint32_t k1 = dropout_keep4(epx.drop_seed, q0 + 1, epx.drop_threshold);
+                auto lanes = [](uint32_t two) -> uint32_t { return ((two & 1u) ? 0x0000ffffu : 0u) | ((two & 2u) ? 0xffff0000u : 0u); };
+                v.x &= lanes(k0); v.y &= lanes(k0 >> 2); v.z &= lanes(k1); v.w &= lanes(k1 >> 2);
               }
             }
             uint8_t* dst = reinterpret_cast<uint8_t*>(out_t + e0);

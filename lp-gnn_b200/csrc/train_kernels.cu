@@ -73,8 +73,10 @@ dropout_kernel(uint4* __restrict__ x, int64_t chunks, uint32_t threshold, float 
     float v[E];
     Vec16<T>::unpack(x[i], v);
 #pragma unroll
-    for (int k = 0; k < E; ++k) {
-      v[k] = dropout_keep(seed, (uint64_t)(i * E + k), threshold) ? v[k] * scale : 0.f;  // P(drop) = threshold / 2^32 = p
+    for (int q = 0; q < E / 4; ++q) {           // one hash per four elements (P(drop) = (threshold >> 16) / 2^16 = p)
+      const uint32_t keep = dropout_keep4(seed, (uint64_t)i * (E / 4) + q, threshold);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[4 * q + k] = ((keep >> k) & 1u) ? v[4 * q + k] * scale : 0.f;
     }
     x[i] = Vec16<T>::pack(v);
   }
