@@ -247,7 +247,8 @@ class GCN_FC(GCNBase):
         return (status, logits) if want_logits else status
 
     @torch.no_grad()
-    def predict_basis_packed(self, row, col, val, m, n, x_s, x_t, cons_ptr, vars_ptr, is_sorted=True, want_logits=False):
+    def predict_basis_packed(self, row, col, val, m, n, x_s, x_t, cons_ptr, vars_ptr, is_sorted=True, want_logits=False,
+                             buffers=None):
         """Same for a block-diagonal pack of LPs (``row/col`` already in the pack's numbering, ``m/n`` the pack
         totals, ``cons_ptr/vars_ptr`` device int32 [B+1]): one forward pass over the pack, basis decision per LP.
         Returns uint8 statuses [m+n] in the packed layout (all constraints, then all variables)."""
@@ -262,8 +263,17 @@ class GCN_FC(GCNBase):
         z = int(row.shape[0])
         x3 = _lib.WS_X3 if (w.precision == _lib.F32 and w.depth > 2 and w.l2r_wrel_parts[0][0]) else 0
         ws_bytes = lib.lpgnn_predict_workspace_bytes(z, m, n, w.p, w.q, w.hids, w.depth, w.precision | x3)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        status = torch.empty(m + n, dtype=torch.uint8, device=dev)
+        if buffers is not None:
+            # caller-owned grow-only buffers (a sweep must not go through cudaMalloc for every new pack size):
+            # buffers = {"ws": uint8 tensor or None, "status": uint8 tensor or None}, replaced in place when too small
+            if buffers.get("ws") is None or buffers["ws"].numel() < ws_bytes:
+                buffers["ws"] = torch.empty(int(ws_bytes * 1.25) + 256, dtype=torch.uint8, device=dev)
+            if buffers.get("status") is None or buffers["status"].numel() < m + n:
+                buffers["status"] = torch.empty(int((m + n) * 1.25) + 256, dtype=torch.uint8, device=dev)
+            ws, status = buffers["ws"], buffers["status"][:m + n]
+        else:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            status = torch.empty(m + n, dtype=torch.uint8, device=dev)
         logits = torch.empty((m + n, 3), dtype=torch.float32, device=dev) if want_logits else None
         gstat = _status_slot(dev)
         with torch.cuda.device(dev):

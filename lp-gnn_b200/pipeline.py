@@ -140,6 +140,7 @@ class PackedBasisPipeline:
         # their varying workspace sizes defeat the per-stream allocator caches (measured 2.7x slower on C5)
         self.compute = [torch.cuda.Stream(self.dev) for _ in range(2)] if compute_streams > 1 else None
         self.d_buf, self.h_status, self.h_ptr = [None, None], [None, None], [None, None]
+        self.bufs = [dict(), dict()]          # per slot: grow-only workspace / status buffers of the native call
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]
         self.done = [torch.cuda.Event(), torch.cuda.Event()]
 
@@ -233,7 +234,8 @@ class PackedBasisPipeline:
             rc = _lib.load().lpgnn_pack_offsets(row.data_ptr(), col.data_ptr(), Z, e_ptr.data_ptr(), c_ptr.data_ptr(),
                                                 v_ptr.data_ptr(), B, _lib.stream_ptr())
         _lib.check(rc, "lpgnn_pack_offsets")
-        st = self.model.predict_basis_packed(row, col, val, M, N, x_s, x_t, c_ptr, v_ptr, is_sorted=meta["sorted"])
+        st = self.model.predict_basis_packed(row, col, val, M, N, x_s, x_t, c_ptr, v_ptr, is_sorted=meta["sorted"],
+                                             buffers=self.bufs[slot])
         self.h_status[slot][:M + N].copy_(st, non_blocking=True)
         self.done[slot].record(cur)
 
