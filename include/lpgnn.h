@@ -43,6 +43,7 @@ extern "C" {
 /* epilogue flags of the node transforms */
 /* lpgnn_graph_build flags */
 #define LPGNN_COO_SORTED 1
+#define LPGNN_GRAPH_MEAN 4   /* degree normalisation: val /= deg(row), val_csc /= deg(column) (mean aggregation) */
 
 #define LPGNN_EPI_NONE 0
 #define LPGNN_EPI_RELU 1
@@ -78,6 +79,10 @@ LPGNN_API int lpgnn_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * which skips the COO sort.  status (device int32, optional, ZERO-INITIALISED BY THE CALLER) gets bits
  * OR-ed in by the kernels: bit 0 = the SORTED claim was false (outputs are then NOT canonical),
  * bit 1 = an index was out of range.  Written asynchronously; read it after synchronising the stream.
+ * LPGNN_GRAPH_MEAN = degree normalisation (OFF in the reference: GraphConv aggr='add', arch.py:57,60 keep 'mean'
+ * commented out): each orientation's values are divided by the degree of its destination node (IEEE division), so the
+ * aggregation becomes the mean over the neighbours.  The two orientations then hold DIFFERENT values, i.e. the other
+ * orientation is no longer the transpose: forward / inference only.
  * ------------------------------------------------------------------------------------------- */
 LPGNN_API size_t lpgnn_graph_build_workspace_bytes(int64_t nnz, int32_t m, int32_t n);
 LPGNN_API int lpgnn_graph_build(const void* coo_row, const void* coo_col, int idx_is_i64,

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "liblpgnn.so")
 F32, BF16 = 0, 1
 EPI_NONE, EPI_RELU = 0, 1
 COO_SORTED = 1
+GRAPH_MEAN = 4
 WS_X3 = 16
 
 _p = C.c_void_p

@@ -126,6 +126,9 @@ def gcn_fc_forward(model, x_s, x_t, graph):
     """GCN_FC.forward (reference arch.py:179-193)."""
     csr, csc = _check_graph(graph)
     if _needs_grad(model):
+        if getattr(graph, "normalize", None):
+            raise NotImplementedError("degree-normalised graphs (normalize='mean') are forward / inference only: the "
+                                      "backward pass needs the transposes of both normalised orientations")
         from .training import gcn_fc_train
         return gcn_fc_train(model, x_s, x_t, csr, csc)
     dt = _act_dtype(model)

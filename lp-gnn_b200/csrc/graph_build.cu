@@ -290,6 +290,17 @@ int radix_sort(SortBufs& b, int64_t n, int bits, cudaStream_t st) {
   return cur;
 }
 
+// val[e] /= deg(row) for the entries of every row (one thread per row: LP rows are short); IEEE division, so the
+// result equals numpy's float32 `val / deg` bit for bit
+__global__ void mean_normalize_kernel(const int32_t* __restrict__ ptr, float* __restrict__ val, int32_t rows) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int32_t beg = ptr[r], end = ptr[r + 1];
+  if (end - beg <= 1) return;
+  const float d = (float)(end - beg);
+  for (int32_t e = beg; e < end; ++e) val[e] = __fdiv_rn(val[e], d);
+}
+
 }  // namespace
 }  // namespace lpgnn
 
@@ -382,6 +393,13 @@ extern "C" int lpgnn_graph_build(const void* coo_row, const void* coo_col, int i
   finish_csc_kernel<<<gb1, tb, 0, st>>>(csr_rows, val, b.k[cur], b.v[cur], z, n, reinterpret_cast<uint32_t*>(csr2csc),
                                         reinterpret_cast<uint32_t*>(row_csc), val_csc, colptr);
   launches += 1;
+  if (flags & LPGNN_GRAPH_MEAN) {
+    // mean aggregation (PyG aggr='mean', the option left commented out at reference arch.py:57,60): every orientation's
+    // values are divided by the degree of ITS destination node, so lpgnn_spmm returns neighbourhood means
+    mean_normalize_kernel<<<ceil_div(m, 256), 256, 0, st>>>(rowptr, val, m);
+    mean_normalize_kernel<<<ceil_div(n, 256), 256, 0, st>>>(colptr, val_csc, n);
+    launches += 2;
+  }
   LPGNN_LAUNCH_OK();
   count_launches(launches);
   return LPGNN_OK;

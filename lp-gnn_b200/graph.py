@@ -66,6 +66,7 @@ class BipartiteCSR:
         self.colptr = self.row_csc = self.val_csc = self.csr2csc = None
         self._transposed = False    # True: this object presents A^T (shares buffers with its parent)
         self._sorted_hint = False   # caller's is_sorted=True: skip the COO sort (verified on the device)
+        self.normalize = None       # 'mean': values divided by the destination degree at build time (inference only)
         self._status = None         # device int32: bit0 = sorted claim false, bit1 = index out of range
 
     @property
@@ -76,19 +77,24 @@ class BipartiteCSR:
 
     # ------------------------------------------------------------------ construction
     @classmethod
-    def from_edge_index(cls, edge_index, edge_attr=None, sparse_sizes=None, is_sorted=False):
+    def from_edge_index(cls, edge_index, edge_attr=None, sparse_sizes=None, is_sorted=False, normalize=None):
         """Same signature as ``SparseTensor.from_edge_index`` (reference dataset.py:301-304).
         ``edge_index`` [2,z] integer (any order), ``edge_attr`` [z] float (default: ones)."""
         if sparse_sizes is None:
             raise ValueError("sparse_sizes=(m, n) is required")
         return cls.from_coo(edge_index[0], edge_index[1], edge_attr, int(sparse_sizes[0]), int(sparse_sizes[1]),
-                            is_sorted=is_sorted)
+                            is_sorted=is_sorted, normalize=normalize)
 
     @classmethod
-    def from_coo(cls, row, col, val, m, n, is_sorted=False):
+    def from_coo(cls, row, col, val, m, n, is_sorted=False, normalize=None):
         """COO given as separate tensors (host or device, any integer dtype).  Device inputs are built
-        immediately on the current stream; host inputs are kept until ``.to(cuda)``."""
+        immediately on the current stream; host inputs are kept until ``.to(cuda)``.  ``normalize='mean'`` bakes the
+        degree normalisation into the values (mean aggregation; the reference runs with sum aggregation, so this is
+        OFF by default and supported for the forward pass only: SURVEY Appendix D)."""
+        if normalize not in (None, "mean"):
+            raise ValueError("normalize must be None or 'mean'")
         g = cls()
+        g.normalize = normalize
         g.m, g.n = int(m), int(n)
         if val is None:
             val = torch.ones(row.shape[0], dtype=torch.float32, device=row.device)
@@ -105,9 +111,10 @@ class BipartiteCSR:
         return g
 
     @classmethod
-    def from_coo_arrays(cls, row, col, val, m, n, device, is_sorted=False):
+    def from_coo_arrays(cls, row, col, val, m, n, device, is_sorted=False, normalize=None):
         """numpy / tensor COO -> built graph on ``device`` (one H2D copy per array)."""
-        g = cls.from_coo(torch.as_tensor(row), torch.as_tensor(col), torch.as_tensor(val), m, n, is_sorted=is_sorted)
+        g = cls.from_coo(torch.as_tensor(row), torch.as_tensor(col), torch.as_tensor(val), m, n, is_sorted=is_sorted,
+                         normalize=normalize)
         return g.to(device)
 
     def _build(self):
@@ -132,7 +139,7 @@ class BipartiteCSR:
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             rc = lib.lpgnn_graph_build(row.data_ptr(), col.data_ptr(), 0, val.data_ptr(), z, self.m, self.n,
-                                       _lib.COO_SORTED if self._sorted_hint else 0,
+                                       (_lib.COO_SORTED if self._sorted_hint else 0) | (_lib.GRAPH_MEAN if self.normalize == "mean" else 0),
                                        self.rowptr.data_ptr(), self.col.data_ptr(), self.val.data_ptr(),
                                        self.colptr.data_ptr(), self.row_csc.data_ptr(), self.val_csc.data_ptr(),
                                        self.csr2csc.data_ptr(), self._status.data_ptr(), ws.data_ptr(), ws_bytes,

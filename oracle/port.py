@@ -157,9 +157,11 @@ def unipartite_edges(row, col, a_data, ncons):
     return np.stack([src[order], dst[order]]), att[order]
 
 
-def graph_from_coo(row, col, val, m, n) -> BipartiteGraph:
+def graph_from_coo(row, col, val, m, n, normalize=None) -> BipartiteGraph:
     """SparseTensor.from_edge_index (dataset.py:301-304) + .t() (arch.py:71): canonical CSR =
-    stable sort by row*n+col; CSC view = stable sort of the CSR entries by col*m+row."""
+    stable sort by row*n+col; CSC view = stable sort of the CSR entries by col*m+row.
+    ``normalize='mean'``: the aggregation PyG calls aggr='mean' (left commented out at arch.py:57,60): each
+    orientation's values divided by the degree of its destination node (float32 division)."""
     row = np.asarray(row, dtype=np.int64)
     col = np.asarray(col, dtype=np.int64)
     val = np.asarray(val, dtype=np.float32)
@@ -170,7 +172,15 @@ def graph_from_coo(row, col, val, m, n) -> BipartiteGraph:
     csr2csc = np.argsort(col * m + row, kind="stable")
     colptr = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(np.bincount(col, minlength=n), out=colptr[1:])
-    return BipartiteGraph(m, n, rowptr, col, val, colptr, row[csr2csc], val[csr2csc], csr2csc)
+    val_csc = val[csr2csc]
+    if normalize == "mean":
+        deg_r = np.maximum(np.diff(rowptr), 1).astype(np.float32)
+        deg_c = np.maximum(np.diff(colptr), 1).astype(np.float32)
+        val = (val / deg_r[row]).astype(np.float32)
+        val_csc = (val_csc / deg_c[col[csr2csc]]).astype(np.float32)
+    elif normalize is not None:
+        raise ValueError(normalize)
+    return BipartiteGraph(m, n, rowptr, col, val, colptr, row[csr2csc], val_csc, csr2csc)
 
 
 def to_bipartite(edge_index, edge_attr, is_vars):

@@ -141,3 +141,34 @@ def test_sparse_tensor_api_subset(cuda):
     assert torch.equal(g.storage.value(), g.val) and torch.equal(g.t().storage.value(), g.val_csc)
     r, c, v = g.t().coo()
     np.testing.assert_array_equal(dense.T[r.cpu().numpy(), c.cpu().numpy()].astype(np.float32), v.cpu().numpy())
+
+
+def test_mean_normalised_build_matches_oracle_and_feeds_the_model(cuda):
+    """LPGNN_GRAPH_MEAN (north_star "degree normalisation"; OFF in the reference): both orientations'
+    values divided by the destination degree, bit-exact with the oracle; the forward pass on the normalised graph
+    matches the oracle model on the same graph; training refuses it."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import arch, synth
+    from lpgnn_b200.data import Data
+    from lpgnn_b200.graph import BipartiteCSR
+    lp = synth.processed_lp(700, 1500, 7500, seed=17)
+    val = lp.a_data.astype(np.float32)
+    for is_sorted in (True, False):
+        row, col, v = (lp.row, lp.col, val) if is_sorted else (lp.row[::-1].copy(), lp.col[::-1].copy(), val[::-1].copy())
+        g = BipartiteCSR.from_coo_arrays(row, col, v, lp.m, lp.n, cuda, is_sorted=is_sorted, normalize="mean")
+        torch.cuda.synchronize()
+        _assert_equal(g.check(), port.graph_from_coo(row, col, v, lp.m, lp.n, normalize="mean"))
+    ref_g = port.graph_from_coo(lp.row, lp.col, val, lp.m, lp.n, normalize="mean")
+    assert not np.array_equal(ref_g.val, port.graph_from_coo(lp.row, lp.col, val, lp.m, lp.n).val)
+    torch.manual_seed(0)
+    model = arch.GCN_FC(8, 8, hids=64, depth=3).to(cuda).eval()
+    torch.manual_seed(0)
+    ref = port.PortGCN_FC(8, 8, hids=64, depth=3).eval()
+    xs, xt = torch.from_numpy(lp.c_feas), torch.from_numpy(lp.v_feas)
+    with torch.no_grad():
+        lc, lv = model(Data(x_s=xs.to(cuda), x_t=xt.to(cuda), edge_index=g))
+        ec, ev = ref(xs, xt, port.TorchGraph(ref_g))
+    assert float((lc.cpu() - ec).abs().max()) < 1e-3 and float((lv.cpu() - ev).abs().max()) < 1e-3
+    model.train()
+    with pytest.raises(NotImplementedError):
+        model(Data(x_s=xs.to(cuda), x_t=xt.to(cuda), edge_index=g))
