@@ -196,12 +196,19 @@ small_wgrad_reduce_kernel(const float* __restrict__ partial, int nchunks, int N,
 
 // ------------------------------------------------------------------------------------------- head_mask_bwd
 // One warp per row.  draw = d(10 * raw / max(|raw|, eps)) ; dH[row, :] = (draw . W) * scale * (Hact > 0).
-template <typename T, int CH>
+// CS: also emits per-block partial column sums of dH (fp32, before the output rounding) -- the bias gradient of the
+// layer under the head -- so that no separate pass has to read dH back (cs_partials [gridDim.x][Hdim]).
+template <typename T, int CH, bool CS>
 __global__ void __launch_bounds__(128)
 head_mask_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ raw, const T* __restrict__ Hact,
                      int32_t rows, int32_t Hdim, const float* __restrict__ W, float scale, T* __restrict__ dH,
-                     float* __restrict__ draw_out, __nv_bfloat16* __restrict__ draw_bf16) {
+                     float* __restrict__ draw_out, __nv_bfloat16* __restrict__ draw_bf16, float* __restrict__ cs_partials) {
   constexpr int E = Vec16<T>::E;
+  float cs[CS ? CH : 1][E];
+#pragma unroll
+  for (int c = 0; c < (CS ? CH : 1); ++c)
+#pragma unroll
+    for (int k = 0; k < E; ++k) cs[c][k] = 0.f;
   const int lane = threadIdx.x & 31;
   const int chunks = Hdim / E;
   float w[3][CH][E];
@@ -253,10 +260,41 @@ head_mask_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict_
         for (int k = 0; k < E; ++k) {
           const float g = fmaf(d0, w[0][c][k], fmaf(d1, w[1][c][k], d2 * w[2][c][k]));
           y[k] = (x[k] > 0.f) ? g * scale : 0.f;
+          if constexpr (CS) cs[c][k] += y[k];          // rows in a fixed order per warp: deterministic
         }
         reinterpret_cast<uint4*>(dH + row * Hdim)[ch] = Vec16<T>::pack(y);
       }
     }
+  }
+  if constexpr (CS) {
+    __shared__ float red[4][CH * 32 * E];
+    const int warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int k = 0; k < E; ++k) red[warp][(lane + 32 * c) * E + k] = cs[c][k];
+    __syncthreads();
+    for (int j = threadIdx.x; j < Hdim; j += 128)
+      cs_partials[(int64_t)blockIdx.x * Hdim + j] = ((red[0][j] + red[1][j]) + red[2][j]) + red[3][j];
+  }
+}
+
+// out[j] = sum over the partial rows, in a fixed order: block = 32 columns x 8 row strides, then 8 -> 1 in shared memory
+__global__ void __launch_bounds__(256)
+colsum_finish_kernel(const float* __restrict__ partials, int nrows, int N, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + c;
+  float acc = 0.f;
+  if (j < N)
+    for (int i = r; i < nrows; i += 8) acc += partials[(int64_t)i * N + j];
+  red[r][c] = acc;
+  __syncthreads();
+  if (r == 0 && j < N) {
+    float s = red[0][c];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) s += red[i][c];
+    out[j] = s;
   }
 }
 
@@ -412,13 +450,62 @@ extern "C" int lpgnn_small_wgrad(const void* dY, int dtype, const float* Z, int3
 #undef LPGNN_WG
 }
 
+static int head_bwd_grid(int32_t rows, bool colsum) {
+  // with fused column sums the grid is also the number of partial rows the finishing kernel reads
+  return min(ceil_div(rows, 4), sm_count() * (colsum ? 8 : 16));
+}
+
 template <typename T>
 static int head_bwd_dispatch(const float* dlogits, const float* raw, const void* Hact, int32_t rows, int32_t Hdim,
-                             const float* W, float scale, void* dH, float* draw, void* draw_bf16, int ch, cudaStream_t st) {
-  const int grid = min(ceil_div(rows, 4), sm_count() * 16);
-#define LPGNN_HB(CHV) head_mask_bwd_kernel<T, CHV><<<grid, 128, 0, st>>>(dlogits, raw, (const T*)Hact, rows, Hdim, W, scale, (T*)dH, draw, (__nv_bfloat16*)draw_bf16)
-  if (ch <= 1) LPGNN_HB(1); else if (ch <= 2) LPGNN_HB(2); else if (ch <= 4) LPGNN_HB(4); else LPGNN_HB(8);
+                             const float* W, float scale, void* dH, float* draw, void* draw_bf16, int ch, float* cs_partials,
+                             cudaStream_t st) {
+  const int grid = head_bwd_grid(rows, cs_partials != nullptr);
+#define LPGNN_HB(CHV, CSV) head_mask_bwd_kernel<T, CHV, CSV><<<grid, 128, 0, st>>>(dlogits, raw, (const T*)Hact, rows, Hdim, W, scale, (T*)dH, draw, (__nv_bfloat16*)draw_bf16, cs_partials)
+  if (cs_partials) {
+    if (ch <= 1) LPGNN_HB(1, true); else if (ch <= 2) LPGNN_HB(2, true); else if (ch <= 4) LPGNN_HB(4, true); else LPGNN_HB(8, true);
+  } else {
+    if (ch <= 1) LPGNN_HB(1, false); else if (ch <= 2) LPGNN_HB(2, false); else if (ch <= 4) LPGNN_HB(4, false); else LPGNN_HB(8, false);
+  }
 #undef LPGNN_HB
+  LPGNN_LAUNCH_OK();
+  count_launches(1);
+  return LPGNN_OK;
+}
+
+extern "C" size_t lpgnn_head_mask_bwd_colsum_workspace_bytes(int32_t rows, int32_t Hdim) {
+  return (size_t)head_bwd_grid(rows > 0 ? rows : 1, true) * (size_t)Hdim * sizeof(float) + 256;
+}
+
+extern "C" int lpgnn_head_mask_bwd_colsum(const float* dlogits, const float* raw, const void* Hact, int h_dtype, int32_t rows,
+                                          int32_t Hdim, const float* W, float scale, void* dH, float* draw,
+                                          void* draw_bf16, float* colsum_out, void* workspace, size_t workspace_bytes,
+                                          lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_DT_OK(h_dtype, "head_mask_bwd");
+  LPGNN_REQUIRE(rows >= 0 && Hdim > 0, "head_mask_bwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows == 0) {
+    if (colsum_out) LPGNN_CUDA_OK(cudaMemsetAsync(colsum_out, 0, sizeof(float) * (size_t)Hdim, st));
+    return LPGNN_OK;
+  }
+  LPGNN_REQUIRE(dlogits && raw && Hact && W && dH, "head_mask_bwd: null pointer");
+  const int esz = h_dtype == LPGNN_F32 ? 4 : 2;
+  LPGNN_REQUIRE((Hdim * esz) % 16 == 0, "head_mask_bwd: row bytes must be a multiple of 16");
+  const int ch = (Hdim * esz / 16 + 31) / 32;
+  LPGNN_REQUIRE(ch <= 8, "head_mask_bwd: Hdim=%d too wide (max 4096 bytes per row)", Hdim);
+  float* partials = nullptr;
+  if (colsum_out) {
+    if (!workspace || workspace_bytes < lpgnn_head_mask_bwd_colsum_workspace_bytes(rows, Hdim)) {
+      set_error("head_mask_bwd_colsum: workspace too small");
+      return LPGNN_EWORKSPACE;
+    }
+    partials = reinterpret_cast<float*>(workspace);
+  }
+  int rc = h_dtype == LPGNN_F32
+               ? head_bwd_dispatch<float>(dlogits, raw, Hact, rows, Hdim, W, scale, dH, draw, draw_bf16, ch, partials, st)
+               : head_bwd_dispatch<__nv_bfloat16>(dlogits, raw, Hact, rows, Hdim, W, scale, dH, draw, draw_bf16, ch, partials, st);
+  if (rc || !colsum_out) return rc;
+  colsum_finish_kernel<<<ceil_div(Hdim, 32), 256, 0, st>>>(partials, head_bwd_grid(rows, true), Hdim, colsum_out);
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;
@@ -427,16 +514,6 @@ static int head_bwd_dispatch(const float* dlogits, const float* raw, const void*
 extern "C" int lpgnn_head_mask_bwd(const float* dlogits, const float* raw, const void* Hact, int h_dtype, int32_t rows,
                                    int32_t Hdim, const float* W, float scale, void* dH, float* draw,
                                    void* draw_bf16, lpgnn_stream_t stream) {
-  if (int rc = check_device()) return rc;
-  LPGNN_DT_OK(h_dtype, "head_mask_bwd");
-  LPGNN_REQUIRE(rows >= 0 && Hdim > 0, "head_mask_bwd: bad shape");
-  if (rows == 0) return LPGNN_OK;
-  LPGNN_REQUIRE(dlogits && raw && Hact && W && dH, "head_mask_bwd: null pointer");
-  const int esz = h_dtype == LPGNN_F32 ? 4 : 2;
-  LPGNN_REQUIRE((Hdim * esz) % 16 == 0, "head_mask_bwd: row bytes must be a multiple of 16");
-  const int ch = (Hdim * esz / 16 + 31) / 32;
-  LPGNN_REQUIRE(ch <= 8, "head_mask_bwd: Hdim=%d too wide (max 4096 bytes per row)", Hdim);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (h_dtype == LPGNN_F32) return head_bwd_dispatch<float>(dlogits, raw, Hact, rows, Hdim, W, scale, dH, draw, draw_bf16, ch, st);
-  return head_bwd_dispatch<__nv_bfloat16>(dlogits, raw, Hact, rows, Hdim, W, scale, dH, draw, draw_bf16, ch, st);
+  return lpgnn_head_mask_bwd_colsum(dlogits, raw, Hact, h_dtype, rows, Hdim, W, scale, dH, draw, draw_bf16, nullptr, nullptr, 0,
+                                    stream);
 }

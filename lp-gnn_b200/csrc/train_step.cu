@@ -83,6 +83,8 @@ size_t carve(Bump& b, TB& B, int32_t m, int32_t n, int32_t p, int32_t q, int32_t
   const size_t c1 = lpgnn_colsum_workspace_bytes(big, H), c3 = lpgnn_colsum_workspace_bytes(big, 3);
   if (c1 > sc) sc = c1;
   if (c3 > sc) sc = c3;
+  const size_t c5 = lpgnn_head_mask_bwd_colsum_workspace_bytes((int32_t)big, H);
+  if (c5 > sc) sc = c5;
   if (bf16) {
     const size_t c2 = nh > 0 ? lpgnn_wgrad_workspace_bytes(big, H, H) : 0, c4 = lpgnn_wgrad_workspace_bytes(big, H, 64);
     if (c2 > sc) sc = c2;
@@ -282,10 +284,11 @@ extern "C" int lpgnn_train_backward(const lpgnn_gcn_fc_weights* w, const int32_t
   const float scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
   // ---- heads: dPre of the last activations (relu / dropout mask fused), head weight + bias grads
   const float last_scale = nh > 0 ? scale : 1.f;
-  LPGNN_TRY(lpgnn_head_mask_bwd(dlogits_s, B.raw_s, B.left[nh], dt, m, H, w->head_left_w, last_scale, B.dpre_s, B.draw_s,
-                                B.drawb_s, stream));
-  LPGNN_TRY(lpgnn_head_mask_bwd(dlogits_t, B.raw_t, B.right[nh], dt, n, H, w->head_right_w, last_scale, B.dpre_t, B.draw_t,
-                                B.drawb_t, stream));
+  // with a hidden layer under the head, dPre's column sums (that layer's bias gradients) come out of the same pass
+  LPGNN_TRY(lpgnn_head_mask_bwd_colsum(dlogits_s, B.raw_s, B.left[nh], dt, m, H, w->head_left_w, last_scale, B.dpre_s, B.draw_s,
+                                       B.drawb_s, nh > 0 ? g->r2l_b[nh - 1] : nullptr, B.scratch, B.scratch_bytes, stream));
+  LPGNN_TRY(lpgnn_head_mask_bwd_colsum(dlogits_t, B.raw_t, B.right[nh], dt, n, H, w->head_right_w, last_scale, B.dpre_t, B.draw_t,
+                                       B.drawb_t, nh > 0 ? g->l2r_b[nh - 1] : nullptr, B.scratch, B.scratch_bytes, stream));
   for (int side = 0; side < 2; ++side) {   // head weight [3,H] and bias [3] gradients
     const int64_t rows = side ? n : m;
     const void* act = side ? B.right[nh] : B.left[nh];
@@ -326,8 +329,10 @@ extern "C" int lpgnn_train_backward(const lpgnn_gcn_fc_weights* w, const int32_t
         LPGNN_TRY(copy2d(side ? g->r2l_wroot[li] : g->l2r_wroot[li], H, B.g_tmp + H, 2 * H, H, H, st));
       }
     }
-    LPGNN_TRY(lpgnn_colsum(dpt, dt, n, H, g->l2r_b[li], B.scratch, B.scratch_bytes, stream));
-    LPGNN_TRY(lpgnn_colsum(dps, dt, m, H, g->r2l_b[li], B.scratch, B.scratch_bytes, stream));
+    if (li < nh - 1) {   // the layer under the head got its bias gradients from head_mask_bwd
+      LPGNN_TRY(lpgnn_colsum(dpt, dt, n, H, g->l2r_b[li], B.scratch, B.scratch_bytes, stream));
+      LPGNN_TRY(lpgnn_colsum(dps, dt, m, H, g->r2l_b[li], B.scratch, B.scratch_bytes, stream));
+    }
     // data gradients.  dL = A (dPre_t W_rel^{l2r}) + dPre_s W_root^{r2l} = [A dPre_t | dPre_s] [W_rel^{l2r} ; W_root^{r2l}]:
     // aggregate first, then ONE two-operand transform per side (transposed weights prepared by the forward call)
     // whose epilogue applies the ReLU / dropout mask of the layer input.

@@ -108,15 +108,16 @@ class _GCNFCFunction(torch.autograd.Function):
         # ---- heads: dPre of the last layer's activations (relu/dropout mask fused)
         left, right = acts[2 + 4 * n_layers], acts[3 + 4 * n_layers]
         last_scale = ctx.scale if n_layers > 0 else 1.0
+        fuse_cs = n_layers > 0                              # bias gradients of the layer under the head from the same pass
         tc_small = z_s.dtype == torch.bfloat16              # bf16 mode: narrow weight gradients on the tensor cores too
         if tc_small:
-            d_pre_s, draw_s, drawb_s = ops.head_mask_bwd(d_logit_s.contiguous(), raw_s, left, P[hbase], last_scale, want_bf16=True)
-            d_pre_t, draw_t, drawb_t = ops.head_mask_bwd(d_logit_t.contiguous(), raw_t, right, P[hbase + 2], last_scale, want_bf16=True)
+            d_pre_s, draw_s, drawb_s, *cs_s = ops.head_mask_bwd(d_logit_s.contiguous(), raw_s, left, P[hbase], last_scale, want_bf16=True, want_colsum=fuse_cs)
+            d_pre_t, draw_t, drawb_t, *cs_t = ops.head_mask_bwd(d_logit_t.contiguous(), raw_t, right, P[hbase + 2], last_scale, want_bf16=True, want_colsum=fuse_cs)
             grads[hbase] = ops.wgrad(left, drawb_s)[:, :3].t().contiguous()       # [H,64] = left^T [draw | 0]
             grads[hbase + 2] = ops.wgrad(right, drawb_t)[:, :3].t().contiguous()
         else:
-            d_pre_s, draw_s = ops.head_mask_bwd(d_logit_s.contiguous(), raw_s, left, P[hbase], last_scale)
-            d_pre_t, draw_t = ops.head_mask_bwd(d_logit_t.contiguous(), raw_t, right, P[hbase + 2], last_scale)
+            d_pre_s, draw_s, *cs_s = ops.head_mask_bwd(d_logit_s.contiguous(), raw_s, left, P[hbase], last_scale, want_colsum=fuse_cs)
+            d_pre_t, draw_t, *cs_t = ops.head_mask_bwd(d_logit_t.contiguous(), raw_t, right, P[hbase + 2], last_scale, want_colsum=fuse_cs)
             gw, _ = ops.small_wgrad(left, draw_s, 3)            # [H,3] = left^T draw
             grads[hbase] = gw.t().contiguous()
             gw, _ = ops.small_wgrad(right, draw_t, 3)
@@ -138,8 +139,11 @@ class _GCNFCFunction(torch.autograd.Function):
                 grads[g + 0], grads[g + 2] = _wgrad_pair(dpt_t, agg_t, right_in)   # l2r lin_rel / lin_root weights
                 grads[g + 3], grads[g + 5] = _wgrad_pair(dps_t, agg_s, left_in)    # r2l lin_rel / lin_root weights
                 del dps_t, dpt_t
-            grads[g + 1] = ops.colsum(d_pre_t)
-            grads[g + 4] = ops.colsum(d_pre_s)
+            if i == n_layers - 1:      # the layer under the head: column sums fused into head_mask_bwd (fp32, pre-rounding)
+                grads[g + 1], grads[g + 4] = cs_t[0], cs_s[0]
+            else:
+                grads[g + 1] = ops.colsum(d_pre_t)
+                grads[g + 4] = ops.colsum(d_pre_s)
             # data gradients (weights transposed once per step: [K,N] K-major for the TN kernel)
             w_rel_l2r_t, w_root_l2r_t = cast(w[0]).t().contiguous(), cast(w[2]).t().contiguous()
             w_rel_r2l_t, w_root_r2l_t = cast(w[3]).t().contiguous(), cast(w[5]).t().contiguous()

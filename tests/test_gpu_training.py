@@ -292,6 +292,33 @@ def test_head_mask_bwd_vs_autograd(cuda, dtype, H):
     assert float((gw.t() - ww.grad).abs().max()) < 1e-2 * max(1.0, float(ww.grad.abs().max()))
 
 
+@pytest.mark.parametrize("dtype,H,rows", [(torch.float32, 64, 2000), (torch.float32, 1024, 777), (torch.bfloat16, 1024, 30011),
+                                          (torch.bfloat16, 128, 3), (torch.bfloat16, 2048, 1500)])
+def test_head_mask_bwd_fused_column_sums(cuda, dtype, H, rows):
+    """head_mask_bwd(want_colsum) = same dH / draw bit for bit + colsum(dH) taken in fp32 before the rounding
+    (bias gradient of the layer under the head, GraphConv.lin_rel.bias); deterministic."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(H + rows)
+    h = torch.randn(rows, H, device=cuda, generator=g).relu().to(dtype)
+    w = torch.randn(3, H, device=cuda, generator=g) / H ** 0.5
+    b = torch.randn(3, device=cuda, generator=g)
+    feas = torch.randint(-1, 2, (rows, 8), device=cuda, generator=g).float()
+    dl = torch.randn(rows, 3, device=cuda, generator=g)
+    _, raw = ops.head_mask(h, w, b, feas, want_raw=True)
+    dH, draw = ops.head_mask_bwd(dl, raw, h, w, scale=1.25)
+    dH2, draw2, cs = ops.head_mask_bwd(dl, raw, h, w, scale=1.25, want_colsum=True)
+    assert torch.equal(dH, dH2) and torch.equal(draw, draw2)
+    # exact (unrounded) dH from the kernel's own draw, in float64
+    exact = (draw.double() @ w.double()) * 1.25 * (h.double() > 0)
+    exp = exact.sum(0)
+    assert float((cs.double() - exp).abs().max()) < 1e-4 * max(1.0, float(exact.abs().sum(0).max()))
+    _, _, cs2 = ops.head_mask_bwd(dl, raw, h, w, scale=1.25, want_colsum=True)
+    assert torch.equal(cs, cs2)
+    # canary: the partial-sum workspace is the only scratch; the [H] output has no neighbours overwritten
+    assert cs.shape == (H,) and torch.isfinite(cs).all()
+
+
 def test_dropout_statistics_and_determinism(cuda):
     import lpgnn_b200  # noqa: F401
     from lpgnn_b200 import ops
