@@ -13,7 +13,7 @@
  *    *_workspace_bytes queries).  All work is enqueued on `stream` (a cudaStream_t); nothing
  *    synchronises unless stated.
  *  - Row-major dense matrices, leading dimension = number of columns.  Feature matrices are
- *    float32 (LPGNN_F32) or bfloat16 (LPGNN_BF16); accumulation is always float32.
+ *    float32 (LPGNN_F32), bfloat16 (LPGNN_BF16) or IEEE half (LPGNN_F16, inference); accumulation is always float32.
  *  - Graph indices are int32 (max(m, n, nnz) < 2^31; BASELINE C4 has nnz = 1e7).
  *  - Return value: 0 on success, a negative LPGNN_E* code otherwise; lpgnn_last_error() gives a
  *    thread-local message.  There is no CPU fallback anywhere: without an sm_100 device every
@@ -39,6 +39,12 @@ extern "C" {
 
 #define LPGNN_F32 0
 #define LPGNN_BF16 1
+/* IEEE half storage with fp32 accumulation: the reference's `--fp16 1` mode (model.half() val.py:269,
+ * scripts/pred_basis.py:146; batch_to utils.py:909-915).  Same tensor-core rate as bf16 with 3 more mantissa bits (basis
+ * statuses agree with fp32 on >= 99.9 % of the nodes where bf16 reaches ~99.8 %).  Inference entry points only
+ * (spmm, gather_cat_ex, node_transform, node_transform_head_ex, head_mask, predict_basis*): the training-only
+ * calls reject it. */
+#define LPGNN_F16 2
 
 /* epilogue flags of the node transforms */
 /* lpgnn_graph_build flags */
@@ -150,6 +156,10 @@ LPGNN_API int32_t lpgnn_conv_in_zcat_width(int32_t k_src, int32_t k_dst);
 LPGNN_API int lpgnn_gather_cat(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,
                      const float* Xsrc, int32_t k_src, const float* Xdst, int32_t k_dst,
                      float* z_cat, void* z_bf16, lpgnn_stream_t stream);
+/* Same with the 16-bit operand in z16_dtype (LPGNN_BF16 or LPGNN_F16). */
+LPGNN_API int lpgnn_gather_cat_ex(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,
+                        const float* Xsrc, int32_t k_src, const float* Xdst, int32_t k_dst,
+                        float* z_cat, void* z16, int z16_dtype, lpgnn_stream_t stream);
 LPGNN_API int lpgnn_conv_in_fused(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,
                         const float* Xsrc, int32_t k_src, const float* Xdst, int32_t k_dst,
                         const float* W_rel, const float* b_rel, const float* W_root, int32_t N,
@@ -164,8 +174,8 @@ LPGNN_API int lpgnn_conv_in_fused(const int32_t* ptr, const int32_t* idx, const 
  *
  *   out[M,N] = epi( A1[M,K1] * W1[N,K1]^T + A2[M,K2] * W2[N,K2]^T + bias[N] )
  *
- * dtype LPGNN_BF16: tcgen05 tensor-core kernel (TMA-fed, TMEM accumulators, fp32 accumulate);
- * operands are bf16, out is bf16 or f32 (out_dtype; f32 is used by the weight-gradient GEMMs),
+ * dtype LPGNN_BF16 / LPGNN_F16: tcgen05 tensor-core kernel (TMA-fed, TMEM accumulators, fp32 accumulate);
+ * operands are bf16 (or IEEE half, out_dtype = LPGNN_F16), out is bf16 or f32 (out_dtype; f32 is used by the weight-gradient GEMMs),
  * bias f32; K1,K2 multiples of 64, N multiple of 64 (A2/W2 may be NULL with K2 = 0).  dtype LPGNN_F32: fp32 CUDA-core kernel (the 1e-4 parity mode); operands,
  * bias and out are f32 (K1,K2 multiples of 4).
  * ------------------------------------------------------------------------------------------- */
@@ -218,6 +228,11 @@ LPGNN_API int lpgnn_node_transform_head(const void* A1, int32_t K1, const void* 
                               const void* A2, int32_t K2, const void* W2,
                               const float* bias, int32_t M, int32_t N, void* out, int epilogue,
                               const float* head_w, float* head_partial, lpgnn_stream_t stream);
+/* Same with the operand / output type given: dtype = LPGNN_BF16 or LPGNN_F16. */
+LPGNN_API int lpgnn_node_transform_head_ex(const void* A1, int32_t K1, const void* W1,
+                                 const void* A2, int32_t K2, const void* W2,
+                                 const float* bias, int32_t M, int32_t N, void* out, int dtype, int epilogue,
+                                 const float* head_w, float* head_partial, lpgnn_stream_t stream);
 /* logits = add_knowledge(sum_p head_partial[p] + b): finishes the fused head (arch.py:190-191). */
 LPGNN_API int lpgnn_head_finish(const float* head_partial, int32_t nparts, int32_t rows, const float* b,
                       const float* feas, int32_t q, float* logits, lpgnn_stream_t stream);
@@ -277,7 +292,7 @@ LPGNN_API int lpgnn_basis_select_segmented(const float* logits_cons, const float
  * ------------------------------------------------------------------------------------------- */
 #define LPGNN_MAX_HIDDEN_LAYERS 8
 typedef struct lpgnn_gcn_fc_weights {
-  int32_t p, q, hids, depth, precision, reserved;  /* precision: LPGNN_F32 | LPGNN_BF16 */
+  int32_t p, q, hids, depth, precision, reserved;  /* precision: LPGNN_F32 | LPGNN_BF16 | LPGNN_F16 (inference) */
   /* conv1, fp32: lin_rel.weight [hids,in_src], lin_rel.bias [hids], lin_root.weight [hids,in_dst] */
   const float *c1_l2r_wrel, *c1_l2r_b, *c1_l2r_wroot;   /* left2right: src = constraints (p), dst = variables (q) */
   const float *c1_r2l_wrel, *c1_r2l_b, *c1_r2l_wroot;   /* right2left: src = variables (q), dst = constraints (p) */

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblpgnn.so")
 
 F32, BF16 = 0, 1
+F16 = 2      # IEEE half storage (the reference's --fp16 mode): inference entry points only
 EPI_NONE, EPI_RELU = 0, 1
 COO_SORTED = 1
 GRAPH_MEAN = 4
@@ -68,6 +69,8 @@ SIGNATURES = {
     "lpgnn_node_transform": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _int, _int, _p]),
     "lpgnn_node_transform_ex": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, C.POINTER(EpilogueArgs), _p]),
     "lpgnn_split_bf16": (_int, [_p, _i64, _int, _p, _p]),
+    "lpgnn_gather_cat_ex": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _int, _p]),
+    "lpgnn_node_transform_head_ex": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _int, _p, _p, _p]),
     "lpgnn_node_transform_split": (_int, [_int, _p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _p]),
     "lpgnn_node_transform_head_parts": (_i32, [_i32]),
     "lpgnn_node_transform_head": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _p, _p, _p]),
@@ -154,7 +157,9 @@ def dtype_code(dt: torch.dtype) -> int:
         return F32
     if dt == torch.bfloat16:
         return BF16
-    raise TypeError(f"lpgnn kernels take float32 or bfloat16 features, got {dt}")
+    if dt == torch.float16:
+        return F16
+    raise TypeError(f"lpgnn kernels take float32, bfloat16 or float16 features, got {dt}")
 
 
 def require_cuda(*tensors) -> None:

@@ -11,10 +11,11 @@ in the hand-written sm_100a kernels of ``liblpgnn.so``:
     F.dropout + relu_                      (186-188)      fused into the transform epilogue (relu) + mask
     lin_left / lin_right + add_knowledge   (190-191)      ops.head_mask x2
 
-Precision: ``model.precision = 'fp32'`` (default; logits within 1e-4 of the reference) or
-``'bf16'`` (bf16 activations / tensor-core GEMMs, fp32 accumulate; within 2e-2).  ``.half()`` /
-``.bfloat16()`` select the bf16 mode (the reference's ``--fp16`` inference switch, val.py:269,
-pred_basis.py:146) while the parameters stay fp32 master copies.
+Precision: ``model.precision = 'fp32'`` (default; logits within 1e-4 of the reference), ``'bf16'`` (bf16
+activations / tensor-core GEMMs, fp32 accumulate; within 2e-2) or ``'fp16'`` (IEEE half storage, same kernels and
+speed, 8x smaller rounding error; inference only).  ``.half()`` selects ``'fp16'`` -- the reference's ``--fp16``
+inference switch (``model.half()``, val.py:269, pred_basis.py:146) -- and ``.bfloat16()`` the bf16 mode, while the
+parameters stay fp32 master copies.
 """
 from __future__ import annotations
 
@@ -139,9 +140,12 @@ class GCN_FC(GCNBase):
         'fp32_tc' fp32 storage, hidden transforms as six bf16 tensor-core passes over 3-part splits (~4x faster;
                   relative Frobenius error ~1e-5, worst logit entry ~3e-4 of the row norm at C2 size because the
                   tensor core's fp32 accumulation truncates);
-        'bf16'    bf16 storage and single-pass tensor-core transforms (within 2e-2)."""
-        if precision not in ("fp32", "fp32_tc", "bf16"):
-            raise ValueError("precision must be 'fp32', 'fp32_tc' or 'bf16'")
+        'bf16'    bf16 storage and single-pass tensor-core transforms (within 2e-2);
+        'fp16'    IEEE half storage, the same tensor-core kernels at the same rate (fp32 accumulate): logits within
+                  ~2e-3, statuses agree with fp32 on >= 99.9 % of the nodes.  Inference only, like the reference's
+                  `--fp16` (val.py:269): activations must stay below 65504, which scaled LPs (|A|, |c| <= 1) do."""
+        if precision not in ("fp32", "fp32_tc", "bf16", "fp16"):
+            raise ValueError("precision must be 'fp32', 'fp32_tc', 'bf16' or 'fp16'")
         if precision != "fp32" and self.hids % 64 != 0:
             raise ValueError("tensor-core modes need hids to be a multiple of 64 (tensor-core tile)")
         self.precision = precision
@@ -150,7 +154,7 @@ class GCN_FC(GCNBase):
         return self
 
     def half(self):       # reference `--fp16`: model.half() (val.py:269, pred_basis.py:146)
-        return self.set_precision("bf16")
+        return self.set_precision("fp16")
 
     def bfloat16(self):
         return self.set_precision("bf16")
@@ -171,8 +175,8 @@ class GCN_FC(GCNBase):
         hit = getattr(self, "_native_cache", None)
         if hit is not None and hit[0] == ver:
             return hit[1]
-        bf16 = self.precision == "bf16"
-        dt = torch.bfloat16 if bf16 else torch.float32
+        bf16 = self.precision in ("bf16", "fp16")            # 16-bit storage: the tensor-core path
+        dt = {"bf16": torch.bfloat16, "fp16": torch.float16}.get(self.precision, torch.float32)
         keep = []                                           # tensors the struct points into
 
         def f32(t):
@@ -188,7 +192,7 @@ class GCN_FC(GCNBase):
         w = _lib.GcnFcWeights()
         c1 = self.conv1
         w.p, w.q = c1.left2right.in_channels[0], c1.left2right.in_channels[1]
-        w.hids, w.depth, w.precision = self.hids, len(self.layers) + 2, _lib.BF16 if bf16 else _lib.F32
+        w.hids, w.depth, w.precision = self.hids, len(self.layers) + 2, _lib.dtype_code(dt)
         if w.depth - 2 > _lib.MAX_HIDDEN_LAYERS:
             raise ValueError("native prediction supports at most 8 hidden layers")
         for tag, gc in (("l2r", c1.left2right), ("r2l", c1.right2left)):
@@ -196,7 +200,7 @@ class GCN_FC(GCNBase):
             setattr(w, f"c1_{tag}_b", f32(gc.lin_rel.bias))
             setattr(w, f"c1_{tag}_wroot", f32(gc.lin_root.weight))
             if bf16:
-                wc = wcat_bf16(c1._cache, gc)
+                wc = wcat_bf16(c1._cache, gc, dt)
                 keep.append(wc)
                 setattr(w, f"c1_{tag}_wcat", wc.data_ptr())
         from .autograd import split_cached, use_x3

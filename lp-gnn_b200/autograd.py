@@ -13,8 +13,12 @@ from . import ops
 from .graph import BipartiteCSR
 
 
+_ACT_DTYPES = {"bf16": torch.bfloat16, "fp16": torch.float16}
+_HALF_TYPES = (torch.bfloat16, torch.float16)
+
+
 def _act_dtype(model) -> torch.dtype:
-    return torch.bfloat16 if getattr(model, "precision", "fp32") == "bf16" else torch.float32
+    return _ACT_DTYPES.get(getattr(model, "precision", "fp32"), torch.float32)
 
 
 def _needs_grad(module) -> bool:
@@ -71,36 +75,36 @@ def _conv_hidden_infer(conv, left, right, csr, csc, relu):
     return left_new, right_new
 
 
-def wcat_bf16(conv_cache, gc):
-    """[W_rel | W_root | 0] as bf16 [N,64] (cached per parameter version): B operand of the bf16 input layer."""
-    key = ("wcat", id(gc))
+def wcat_bf16(conv_cache, gc, dtype=torch.bfloat16):
+    """[W_rel | W_root | 0] as bf16 (or half) [N,64] (cached per parameter version): B operand of the 16-bit input layer."""
+    key = ("wcat", id(gc), dtype)
     ver = (gc.lin_rel.weight._version, gc.lin_root.weight._version, gc.lin_rel.weight.device)
     hit = conv_cache._c.get(key)
     if hit is not None and hit[0] == ver:
         return hit[1]
     w_rel, w_root = gc.lin_rel.weight.detach(), gc.lin_root.weight.detach()
-    w = torch.zeros((w_rel.shape[0], 64), dtype=torch.bfloat16, device=w_rel.device)
+    w = torch.zeros((w_rel.shape[0], 64), dtype=dtype, device=w_rel.device)
     w[:, :w_rel.shape[1]] = w_rel
     w[:, w_rel.shape[1]:w_rel.shape[1] + w_root.shape[1]] = w_root
     conv_cache._c[key] = (ver, w)
     return w
 
 
-def conv_in_bf16(conv, x_left, x_right, csr, csc, relu, want_f32=False):
-    """bf16 input layer: gather_cat (fp32 accumulate, bf16 out) -> tensor-core transform with one K block."""
+def conv_in_bf16(conv, x_left, x_right, csr, csc, relu, want_f32=False, dtype=torch.bfloat16):
+    """16-bit input layer: gather_cat (fp32 accumulate, bf16 / half out) -> tensor-core transform with one K block."""
     l2r, r2l = conv.left2right, conv.right2left
-    z32_t, zb_t = ops.gather_cat(csc, x_left, x_right, want_f32=want_f32, want_bf16=True)
-    z32_s, zb_s = ops.gather_cat(csr, x_right, x_left, want_f32=want_f32, want_bf16=True)
-    right_new = ops.node_transform(zb_t, wcat_bf16(conv._cache, l2r), bias=l2r.lin_rel.bias.detach(), relu=relu)
-    left_new = ops.node_transform(zb_s, wcat_bf16(conv._cache, r2l), bias=r2l.lin_rel.bias.detach(), relu=relu)
+    z32_t, zb_t = ops.gather_cat(csc, x_left, x_right, want_f32=want_f32, want_bf16=True, dtype16=dtype)
+    z32_s, zb_s = ops.gather_cat(csr, x_right, x_left, want_f32=want_f32, want_bf16=True, dtype16=dtype)
+    right_new = ops.node_transform(zb_t, wcat_bf16(conv._cache, l2r, dtype), bias=l2r.lin_rel.bias.detach(), relu=relu)
+    left_new = ops.node_transform(zb_s, wcat_bf16(conv._cache, r2l, dtype), bias=r2l.lin_rel.bias.detach(), relu=relu)
     return left_new, right_new, z32_s, z32_t
 
 
 def _conv_in_infer(conv, x_left, x_right, csr, csc, dt, relu):
     l2r, r2l = conv.left2right, conv.right2left
     k_tot = l2r.in_channels[0] + l2r.in_channels[1]
-    if dt == torch.bfloat16 and k_tot <= 64 and l2r.out_channels % 64 == 0:
-        left_new, right_new, _, _ = conv_in_bf16(conv, x_left, x_right, csr, csc, relu)
+    if dt in _HALF_TYPES and k_tot <= 64 and l2r.out_channels % 64 == 0:
+        left_new, right_new, _, _ = conv_in_bf16(conv, x_left, x_right, csr, csc, relu, dtype=dt)
         return left_new, right_new
     right_new, _ = ops.conv_in_fused(csc, x_left, x_right, l2r.lin_rel.weight.detach(), l2r.lin_rel.bias.detach(),
                                      l2r.lin_root.weight.detach(), dt, relu=relu)
@@ -126,6 +130,9 @@ def gcn_fc_forward(model, x_s, x_t, graph):
     """GCN_FC.forward (reference arch.py:179-193)."""
     csr, csc = _check_graph(graph)
     if _needs_grad(model):
+        if getattr(model, "precision", "fp32") == "fp16":
+            raise NotImplementedError("precision 'fp16' is the reference's inference switch (--fp16, val.py:269): train in "
+                                      "'fp32' or 'bf16', or call the model under torch.no_grad()")
         if getattr(graph, "normalize", None):
             raise NotImplementedError("degree-normalised graphs (normalize='mean') are forward / inference only: the "
                                       "backward pass needs the transposes of both normalised orientations")
@@ -136,7 +143,7 @@ def gcn_fc_forward(model, x_s, x_t, graph):
     n_layers = len(model.layers)
     for li, conv in enumerate(model.layers):
         # eval mode: dropout is the identity; relu is fused into the transform epilogue
-        if li == n_layers - 1 and dt == torch.bfloat16:
+        if li == n_layers - 1 and dt in _HALF_TYPES:
             # last layer: the head is fused into the transform epilogue; the hidden activation never reaches HBM
             cast = conv._cache.get
             l2r, r2l = conv.left2right, conv.right2left

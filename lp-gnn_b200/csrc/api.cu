@@ -143,8 +143,8 @@ extern "C" int lpgnn_node_transform(const void* A1, int32_t K1, const void* W1, 
                                     int out_dtype, int epilogue, lpgnn_stream_t stream) {
   if (int rc = check_device()) return rc;
   LPGNN_REQUIRE(M >= 0 && N > 0 && K1 > 0 && K2 >= 0, "node_transform: bad shape M=%d N=%d K1=%d K2=%d", M, N, K1, K2);
-  LPGNN_REQUIRE(dtype == LPGNN_F32 || dtype == LPGNN_BF16, "node_transform: bad dtype %d", dtype);
-  LPGNN_REQUIRE(out_dtype == LPGNN_F32 || (out_dtype == LPGNN_BF16 && dtype == LPGNN_BF16),
+  LPGNN_REQUIRE(dtype_ok(dtype), "node_transform: bad dtype %d", dtype);
+  LPGNN_REQUIRE((out_dtype == LPGNN_F32 && dtype != LPGNN_F16) || (is_16bit(out_dtype) && out_dtype == dtype),
                 "node_transform: out_dtype %d not available for operand dtype %d", out_dtype, dtype);
   if (M == 0) return LPGNN_OK;
   LPGNN_REQUIRE(A1 && W1 && out, "node_transform: null pointer");
@@ -155,8 +155,8 @@ extern "C" int lpgnn_node_transform(const void* A1, int32_t K1, const void* W1, 
   if (dtype == LPGNN_F32)
     return node_transform_f32((const float*)A1, K1, (const float*)W1, (const float*)A2, K2, (const float*)W2, bias, M,
                               N, (float*)out, relu, st);
-  return node_transform_bf16(A1, K1, W1, A2, K2, W2, bias, M, N, out, out_dtype == LPGNN_F32 ? 1 : 0, relu, nullptr,
-                             nullptr, 1, st);
+  return node_transform_bf16(A1, K1, W1, A2, K2, W2, bias, M, N, out, dtype == LPGNN_F16 ? 2 : (out_dtype == LPGNN_F32 ? 1 : 0),
+                             relu, nullptr, nullptr, 1, st);
 }
 
 // node_transform + fused keep-masks (training): see include/lpgnn.h
@@ -165,7 +165,7 @@ extern "C" int lpgnn_node_transform_ex(const void* A1, int32_t K1, const void* W
                                        const lpgnn_epilogue_args* epi, lpgnn_stream_t stream) {
   if (int rc = check_device()) return rc;
   LPGNN_REQUIRE(epi, "node_transform_ex: null epilogue arguments");
-  LPGNN_REQUIRE(dtype == LPGNN_F32 || dtype == LPGNN_BF16, "node_transform_ex: bad dtype %d", dtype);
+  LPGNN_REQUIRE(dtype == LPGNN_F32 || dtype == LPGNN_BF16, "node_transform_ex: bad dtype %d (training epilogues: f32 / bf16)", dtype);
   LPGNN_REQUIRE(epi->dropout_p >= 0.f && epi->dropout_p < 1.f, "node_transform_ex: dropout_p=%f outside [0,1)", epi->dropout_p);
   const float mscale = epi->mask_act ? epi->mask_scale : 1.f;
   if (dtype == LPGNN_F32) {   // CUDA-core transform, then the stand-alone mask / dropout kernels (same semantics)
@@ -200,14 +200,23 @@ extern "C" int lpgnn_node_transform_head(const void* A1, int32_t K1, const void*
                                          const void* W2, const float* bias, int32_t M, int32_t N, void* out,
                                          int epilogue, const float* head_w, float* head_partial,
                                          lpgnn_stream_t stream) {
+  return lpgnn_node_transform_head_ex(A1, K1, W1, A2, K2, W2, bias, M, N, out, LPGNN_BF16, epilogue, head_w, head_partial,
+                                      stream);
+}
+
+extern "C" int lpgnn_node_transform_head_ex(const void* A1, int32_t K1, const void* W1, const void* A2, int32_t K2,
+                                            const void* W2, const float* bias, int32_t M, int32_t N, void* out,
+                                            int dtype, int epilogue, const float* head_w, float* head_partial,
+                                            lpgnn_stream_t stream) {
   if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(is_16bit(dtype), "node_transform_head: dtype %d is not a tensor-core operand type", dtype);
   LPGNN_REQUIRE(M >= 0 && N > 0 && K1 > 0 && K2 >= 0, "node_transform_head: bad shape M=%d N=%d K1=%d K2=%d", M, N, K1, K2);
   if (M == 0) return LPGNN_OK;
   LPGNN_REQUIRE(A1 && W1 && head_w && head_partial, "node_transform_head: null pointer");
   LPGNN_REQUIRE(K2 == 0 || (A2 && W2), "node_transform_head: K2=%d but A2/W2 is null", K2);
   if (K2 == 0) { A2 = nullptr; W2 = nullptr; }
-  return node_transform_bf16(A1, K1, W1, A2, K2, W2, bias, M, N, out, 0, (epilogue & LPGNN_EPI_RELU) ? 1 : 0, head_w,
-                             head_partial, 1, (cudaStream_t)stream);
+  return node_transform_bf16(A1, K1, W1, A2, K2, W2, bias, M, N, out, dtype == LPGNN_F16 ? 2 : 0,
+                             (epilogue & LPGNN_EPI_RELU) ? 1 : 0, head_w, head_partial, 1, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------- split-K GEMM

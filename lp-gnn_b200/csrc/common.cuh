@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -88,6 +89,25 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);  // .x = a (low half), .y = b
   return *reinterpret_cast<uint32_t*>(&p);
 }
+
+// IEEE half (LPGNN_F16: the reference's `--fp16 1` storage, utils.py:909-915 / val.py:269) -- inference only
+__device__ __forceinline__ float2 f16x2_unpack(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  __half2 p = __floats2half2_rn(a, b);  // .x = a (low half), .y = b
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+// Two 16-bit floats in a 32-bit word <-> two fp32, by storage type
+template <typename T> struct Half16;
+template <> struct Half16<__nv_bfloat16> {
+  __device__ static __forceinline__ float2 unpack(uint32_t w) { return make_float2(bf16_lo(w), bf16_hi(w)); }
+  __device__ static __forceinline__ uint32_t pack(float a, float b) { return pack_bf16(a, b); }
+};
+template <> struct Half16<__half> {
+  __device__ static __forceinline__ float2 unpack(uint32_t w) { return f16x2_unpack(w); }
+  __device__ static __forceinline__ uint32_t pack(float a, float b) { return pack_f16(a, b); }
+};
+static inline bool is_16bit(int dtype) { return dtype == LPGNN_BF16 || dtype == LPGNN_F16; }
+static inline bool dtype_ok(int dtype) { return dtype == LPGNN_F32 || is_16bit(dtype); }
 
 // 128-bit read-only streaming load / store
 __device__ __forceinline__ uint4 ldg128(const void* p) {

@@ -13,6 +13,8 @@
 // HBM-bound on the output write: rows*N*sizeof(out) bytes; see DESIGN.md.
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace lpgnn {
 namespace {
 
@@ -23,11 +25,11 @@ constexpr int kColsPerBlock = 2 * kThreads;
 // ---- kernel 1: z[row] = [ sum_e val[e]*Xsrc[idx[e],:] | Xdst[row,:] | 0-pad ]   (fp32, CSR order)
 // 8 adjacent lanes share a row: they read the same (idx,val) pair through one broadcast transaction and
 // 32 contiguous bytes of the source row; four neighbours are in flight per lane.
-template <int KT>
+template <int KT, typename ZT>
 __global__ void __launch_bounds__(kThreads)
 gather_cat_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ val,
                   int32_t rows, const float* __restrict__ Xsrc, int k_src, const float* __restrict__ Xdst, int k_dst,
-                  float* __restrict__ z, __nv_bfloat16* __restrict__ zb /*[rows,64] or null*/) {
+                  float* __restrict__ z, ZT* __restrict__ zb /*[rows,64] bf16 / half, or null*/) {
   const int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const int64_t row = p >> 3;
   const int f0 = (int)(p & 7);
@@ -35,7 +37,9 @@ gather_cat_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ i
   const int K = k_src + k_dst;
   const int32_t beg = ptr[row], end = ptr[row + 1];
   float* zr = z ? z + row * KT : nullptr;
-  __nv_bfloat16* zbr = zb ? zb + row * 64 : nullptr;
+  ZT* zbr = zb ? zb + row * 64 : nullptr;
+  auto pk = [](float a, float b) { return Half16<ZT>::pack(a, b); };
+  auto cv = [](float a) -> ZT { if constexpr (sizeof(ZT) == 2 && std::is_same<ZT, __half>::value) return __float2half_rn(a); else return __float2bfloat16_rn(a); };
   if (k_src == 8 && k_dst == 8) {
     // The reference's shape (GCN_FC(8, 8, ...)): lane f0 aggregates feature f0, the 8 lanes of the row exchange their
     // sums, and every lane then writes ONE 16-byte chunk of the row -- a single coalesced store per output instead of
@@ -75,9 +79,9 @@ gather_cat_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ i
     if (KT / 4 > 8 && zr) for (int c = 8 + f0; c < KT / 4; c += 8) reinterpret_cast<float4*>(zr)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (zbr) {
       uint4 o = make_uint4(0u, 0u, 0u, 0u);
-      if (f0 == 0) o = make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
-      else if (f0 == 1) o = make_uint4(pack_bf16(xa.x, xa.y), pack_bf16(xa.z, xa.w), pack_bf16(xb.x, xb.y), pack_bf16(xb.z, xb.w));
-      else if (f0 == 2) o.x = pack_bf16(1.f, 0.f);   // column K = 16 carries 1.0 (bias gradient through lpgnn_wgrad)
+      if (f0 == 0) o = make_uint4(pk(a[0], a[1]), pk(a[2], a[3]), pk(a[4], a[5]), pk(a[6], a[7]));
+      else if (f0 == 1) o = make_uint4(pk(xa.x, xa.y), pk(xa.z, xa.w), pk(xb.x, xb.y), pk(xb.z, xb.w));
+      else if (f0 == 2) o.x = pk(1.f, 0.f);   // column K = 16 carries 1.0 (bias gradient through lpgnn_wgrad)
       reinterpret_cast<uint4*>(zbr)[f0] = o;
     }
     return;
@@ -94,16 +98,16 @@ gather_cat_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ i
     }
     for (; e < end; ++e) v = fmaf(__ldg(val + e), __ldg(Xsrc + (int64_t)__ldg(idx + e) * k_src + k), v);
     if (zr) zr[k] = v;
-    if (zbr) zbr[k] = __float2bfloat16_rn(v);
+    if (zbr) zbr[k] = cv(v);
   }
   for (int k = f0; k < k_dst; k += 8) {
     const float v = __ldg(Xdst + row * k_dst + k);
     if (zr) zr[k_src + k] = v;
-    if (zbr) zbr[k_src + k] = __float2bfloat16_rn(v);
+    if (zbr) zbr[k_src + k] = cv(v);
   }
   if (zr) for (int k = K + f0; k < KT; k += 8) zr[k] = 0.f;
   // column K carries 1.0: the forward weight column there is zero, and dPre^T z_bf16 (lpgnn_wgrad) gets the bias gradient
-  if (zbr) for (int k = K + f0; k < 64; k += 8) zbr[k] = __float2bfloat16_rn(k == K ? 1.f : 0.f);
+  if (zbr) for (int k = K + f0; k < 64; k += 8) zbr[k] = cv(k == K ? 1.f : 0.f);
 }
 
 // ---- kernel 2: out[r, c] = epi(b[c] + sum_k z[r][k] * Wcat[c][k]).  Block = 64 rows x 512 columns; a thread
@@ -162,8 +166,8 @@ template <int KT>
 int launch(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const float* Xsrc, int k_src,
            const float* Xdst, int k_dst, const float* W_rel, const float* b_rel, const float* W_root, int N,
            void* out, int out_dtype, int relu, float* z, cudaStream_t st) {
-  gather_cat_kernel<KT><<<ceil_div((int64_t)rows * 8, kThreads), kThreads, 0, st>>>(ptr, idx, val, rows, Xsrc, k_src,
-                                                                                   Xdst, k_dst, z, nullptr);
+  gather_cat_kernel<KT, __nv_bfloat16><<<ceil_div((int64_t)rows * 8, kThreads), kThreads, 0, st>>>(
+      ptr, idx, val, rows, Xsrc, k_src, Xdst, k_dst, z, nullptr);
   dim3 grid(ceil_div(N, kColsPerBlock), ceil_div(rows, kRows));
   if (out_dtype == LPGNN_F32)
     small_k_transform_kernel<KT, float><<<grid, kThreads, 0, st>>>(z, rows, W_rel, k_src, W_root, k_dst, b_rel, N,
@@ -186,23 +190,33 @@ extern "C" int32_t lpgnn_conv_in_zcat_width(int32_t k_src, int32_t k_dst) {
   return K <= 16 ? 16 : (K <= 32 ? 32 : 64);
 }
 
-extern "C" int lpgnn_gather_cat(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,
-                                const float* Xsrc, int32_t k_src, const float* Xdst, int32_t k_dst, float* z_cat,
-                                void* z_bf16, lpgnn_stream_t stream) {
+extern "C" int lpgnn_gather_cat_ex(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,
+                                   const float* Xsrc, int32_t k_src, const float* Xdst, int32_t k_dst, float* z_cat,
+                                   void* z16, int z16_dtype, lpgnn_stream_t stream) {
   if (int rc = check_device()) return rc;
   LPGNN_REQUIRE(rows >= 0 && k_src >= 1 && k_dst >= 0 && k_src + k_dst <= 64, "gather_cat: bad shape");
+  LPGNN_REQUIRE(!z16 || is_16bit(z16_dtype), "gather_cat: z16_dtype %d is not a 16-bit type", z16_dtype);
   if (rows == 0) return LPGNN_OK;
-  LPGNN_REQUIRE(ptr && Xsrc && (z_cat || z_bf16) && (k_dst == 0 || Xdst), "gather_cat: null pointer");
+  LPGNN_REQUIRE(ptr && Xsrc && (z_cat || z16) && (k_dst == 0 || Xdst), "gather_cat: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int KT = lpgnn_conv_in_zcat_width(k_src, k_dst);
   const int grid = ceil_div((int64_t)rows * 8, kThreads);
-  __nv_bfloat16* zb = reinterpret_cast<__nv_bfloat16*>(z_bf16);
-  if (KT == 16) gather_cat_kernel<16><<<grid, kThreads, 0, st>>>(ptr, idx, val, rows, Xsrc, k_src, Xdst, k_dst, z_cat, zb);
-  else if (KT == 32) gather_cat_kernel<32><<<grid, kThreads, 0, st>>>(ptr, idx, val, rows, Xsrc, k_src, Xdst, k_dst, z_cat, zb);
-  else gather_cat_kernel<64><<<grid, kThreads, 0, st>>>(ptr, idx, val, rows, Xsrc, k_src, Xdst, k_dst, z_cat, zb);
+#define LPGNN_GC(KTV, ZT) gather_cat_kernel<KTV, ZT><<<grid, kThreads, 0, st>>>(ptr, idx, val, rows, Xsrc, k_src, Xdst, k_dst, z_cat, reinterpret_cast<ZT*>(z16))
+  if (z16 && z16_dtype == LPGNN_F16) {
+    if (KT == 16) LPGNN_GC(16, __half); else if (KT == 32) LPGNN_GC(32, __half); else LPGNN_GC(64, __half);
+  } else {
+    if (KT == 16) LPGNN_GC(16, __nv_bfloat16); else if (KT == 32) LPGNN_GC(32, __nv_bfloat16); else LPGNN_GC(64, __nv_bfloat16);
+  }
+#undef LPGNN_GC
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;
+}
+
+extern "C" int lpgnn_gather_cat(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,
+                                const float* Xsrc, int32_t k_src, const float* Xdst, int32_t k_dst, float* z_cat,
+                                void* z_bf16, lpgnn_stream_t stream) {
+  return lpgnn_gather_cat_ex(ptr, idx, val, rows, Xsrc, k_src, Xdst, k_dst, z_cat, z_bf16, LPGNN_BF16, stream);
 }
 
 extern "C" int lpgnn_conv_in_fused(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,

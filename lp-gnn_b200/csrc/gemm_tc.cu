@@ -21,6 +21,8 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <type_traits>
+
 namespace lpgnn {
 namespace {
 
@@ -200,7 +202,7 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
     if (lane == 0 && (kCl == 1 || crank == 0)) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM * kCl, BN, kMN);
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM * kCl, BN, kMN, std::is_same<OutT, __half>::value);
       int stage = 0; uint32_t phase = 0;
       int t = 0;
       for (int tile = w_first; tile < w_count; tile += w_step, ++t) {
@@ -298,7 +300,7 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
             float v1 = __uint_as_float(r[2 * j + 1]) + bias_s[pc * 32 + 2 * j + 1];
             if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
             if constexpr (kEpx) { v0 *= epx.out_scale; v1 *= epx.out_scale; }
-            packed[j] = pack_bf16(v0, v1);
+            packed[j] = Half16<OutT>::pack(v0, v1);
             if (kHead && head_w) {
               const int col = pc * 32 + 2 * j;
               hd0 = fmaf(v0, headw_s[col], hd0);          hd0 = fmaf(v1, headw_s[col + 1], hd0);
@@ -394,16 +396,16 @@ EncodeTiledFn encode_fn() {
 }
 
 // [rows, K] bf16 row-major, box = [box_rows, 64], 128-byte swizzle, OOB rows read as zero.
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int box_rows) {
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int box_rows, bool f16 = false) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("node_transform(bf16): cuTensorMapEncodeTiled unavailable"); return LPGNN_ECUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
+                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("node_transform(bf16): cuTensorMapEncodeTiled failed (%d)", (int)r); return LPGNN_ECUDA; }
   return LPGNN_OK;
 }
@@ -437,6 +439,9 @@ int launch(const Segs& segs, const float* bias, void* out, int M, int N, int rel
   // the wide bf16 tile gets one instantiation per feature set; fp32 outputs and MN-major operands never use the
   // extras, the narrow tiles (rare, small) share the full-featured one
   if constexpr (sizeof(OutT) == 4 || kMN) {
+    return launch_epi<BN, OutT, kMN, 0>(segs, bias, out, M, N, relu, head_w, head_partial, ksplit, st, epx);
+  } else if constexpr (std::is_same<OutT, __half>::value) {   // inference only: plain transform or fused head
+    if (head_w) return launch_epi<BN, OutT, kMN, 1>(segs, bias, out, M, N, relu, head_w, head_partial, ksplit, st, epx);
     return launch_epi<BN, OutT, kMN, 0>(segs, bias, out, M, N, relu, head_w, head_partial, ksplit, st, epx);
   } else if constexpr (BN != 256) {
     return launch_epi<BN, OutT, kMN, 3>(segs, bias, out, M, N, relu, head_w, head_partial, ksplit, st, epx);
@@ -488,6 +493,9 @@ int launch_cluster2(const Segs& segs, const float* bias, void* out, int M, int N
                     float* head_partial, cudaStream_t st, const EpiX& epx, int ksplit = 1) {
   if constexpr (sizeof(OutT) == 4 || kMN) {
     return launch_cluster2_epi<BN, OutT, kMN, 0>(segs, bias, out, M, N, relu, head_w, head_partial, st, epx, ksplit);
+  } else if constexpr (std::is_same<OutT, __half>::value) {
+    if (head_w) return launch_cluster2_epi<BN, OutT, kMN, 1>(segs, bias, out, M, N, relu, head_w, head_partial, st, epx, ksplit);
+    return launch_cluster2_epi<BN, OutT, kMN, 0>(segs, bias, out, M, N, relu, head_w, head_partial, st, epx, ksplit);
   } else {
     switch (epi_features(head_w, epx)) {
       case 0: return launch_cluster2_epi<BN, OutT, kMN, 0>(segs, bias, out, M, N, relu, head_w, head_partial, st, epx, ksplit);
@@ -503,9 +511,14 @@ int g_gemm_cluster = 1;   // 0 disables the 2-CTA cluster kernel (lpgnn_set_gemm
 }  // namespace
 
 // out[M,N] = epi( sum_i A_i[M,K_i] * W_i[N,K_i]^T + bias ) over nseg <= 12 bf16 operand pairs.
+// fmt: 0 = bf16 operands and output, 1 = bf16 operands, fp32 output, 2 = IEEE half operands and output (inference only).
 int gemm_tc_run(const void* const* A, const void* const* W, const int* K, int nseg, const float* bias, int M, int N,
-                void* out, int out_f32, int relu, const float* head_w, float* head_partial, int ksplit, cudaStream_t st,
+                void* out, int fmt, int relu, const float* head_w, float* head_partial, int ksplit, cudaStream_t st,
                 const EpiX& epx) {
+  const int out_f32 = fmt == 1;
+  const bool f16 = fmt == 2;
+  LPGNN_REQUIRE(!f16 || (!epx.mask_act && !epx.drop_threshold && epx.out_scale == 1.f && ksplit == 1),
+                "node_transform(f16): the half format is inference-only (no mask / dropout epilogues, no split-K)");
   LPGNN_REQUIRE(!(out_f32 || !out) || (!epx.mask_act && !epx.drop_threshold && epx.out_scale == 1.f),
                 "node_transform(bf16): mask / dropout epilogues need a bf16 output");
   LPGNN_REQUIRE(nseg >= 1 && nseg <= kMaxSegs, "gemm_tc: %d operand pairs (max %d)", nseg, kMaxSegs);
@@ -526,8 +539,8 @@ int gemm_tc_run(const void* const* A, const void* const* W, const int* K, int ns
     LPGNN_REQUIRE(A[i] && W[i] && K[i] > 0 && K[i] % BK == 0, "node_transform(bf16): K=%d must be a positive multiple of 64",
                   K[i]);
     LPGNN_REQUIRE((uintptr_t)A[i] % 16 == 0 && (uintptr_t)W[i] % 16 == 0, "node_transform(bf16): operands must be 16-byte aligned");
-    if (int rc = make_map(&segs.a[i], A[i], M, K[i], BM)) return rc;
-    if (int rc = make_map(&segs.w[i], W[i], N, K[i], use_cluster ? BN / 2 : BN)) return rc;
+    if (int rc = make_map(&segs.a[i], A[i], M, K[i], BM, f16)) return rc;
+    if (int rc = make_map(&segs.w[i], W[i], N, K[i], use_cluster ? BN / 2 : BN, f16)) return rc;
     kb += K[i] / BK;
     segs.kb_end[i] = kb;
   }
@@ -540,6 +553,12 @@ int gemm_tc_run(const void* const* A, const void* const* W, const int* K, int ns
     if (BN == 256) LPGNN_GO(256, float);
     if (BN == 128) LPGNN_GO(128, float);
     LPGNN_GO(64, float);
+  }
+  if (f16) {
+    if (use_cluster) return launch_cluster2<256, __half>(segs, bias, out, M, N, relu, head_w, head_partial, st, epx);
+    if (BN == 256) LPGNN_GO(256, __half);
+    if (BN == 128) LPGNN_GO(128, __half);
+    LPGNN_GO(64, __half);
   }
   if (use_cluster) return launch_cluster2<256, __nv_bfloat16>(segs, bias, out, M, N, relu, head_w, head_partial, st, epx);
   if (BN == 256) LPGNN_GO(256, __nv_bfloat16);
@@ -584,13 +603,13 @@ int gemm_tc_mn(const void* A, const void* B, int64_t Kred, int M, int N, void* o
 }
 
 int node_transform_bf16(const void* A1, int K1, const void* W1, const void* A2, int K2, const void* W2,
-                        const float* bias, int M, int N, void* out, int out_f32, int relu, const float* head_w,
+                        const float* bias, int M, int N, void* out, int fmt, int relu, const float* head_w,
                         float* head_partial, int ksplit, cudaStream_t st, const EpiX& epx) {
   const void* A[2] = {A1, A2};
   const void* W[2] = {W1, W2};
   const int K[2] = {K1, K2};
   const int nseg = (A2 != nullptr && K2 > 0) ? 2 : 1;
-  return gemm_tc_run(A, W, K, nseg, bias, M, N, out, out_f32, relu, head_w, head_partial, ksplit, st, epx);
+  return gemm_tc_run(A, W, K, nseg, bias, M, N, out, fmt, relu, head_w, head_partial, ksplit, st, epx);
 }
 
 }  // namespace lpgnn

@@ -40,6 +40,15 @@ __device__ __forceinline__ void finish_row(float r0, float r1, float r2, const f
   logits[row * 3 + 2] = y2;
 }
 
+// eight 16-bit floats of a 16-byte chunk -> fp32 (T = __nv_bfloat16 or __half; never instantiated for float)
+template <typename T, int E>
+__device__ __forceinline__ void unpack8(const uint4& v, float (&x)[E]) {
+  if constexpr (sizeof(T) == 2) {
+    const float2 a = Half16<T>::unpack(v.x), b = Half16<T>::unpack(v.y), c = Half16<T>::unpack(v.z), d = Half16<T>::unpack(v.w);
+    x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y; x[6] = d.x; x[7] = d.y;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 head_mask_kernel(const T* __restrict__ H, int32_t rows, int32_t Hdim, const float* __restrict__ W,
@@ -62,8 +71,7 @@ head_mask_kernel(const T* __restrict__ H, int32_t rows, int32_t Hdim, const floa
       if constexpr (sizeof(T) == 4) {
         x[0] = __uint_as_float(v.x); x[1] = __uint_as_float(v.y); x[2] = __uint_as_float(v.z); x[3] = __uint_as_float(v.w);
       } else {
-        x[0] = bf16_lo(v.x); x[1] = bf16_hi(v.x); x[2] = bf16_lo(v.y); x[3] = bf16_hi(v.y);
-        x[4] = bf16_lo(v.z); x[5] = bf16_hi(v.z); x[6] = bf16_lo(v.w); x[7] = bf16_hi(v.w);
+        unpack8<T>(v, x);
       }
       const float* w0 = w_s + c * E;
 #pragma unroll
@@ -137,10 +145,8 @@ head_mask_fast_kernel(const T* __restrict__ H, int32_t rows, int32_t Hdim, const
         y[0] = __uint_as_float(v1[c].x); y[1] = __uint_as_float(v1[c].y);
         y[2] = __uint_as_float(v1[c].z); y[3] = __uint_as_float(v1[c].w);
       } else {
-        x[0] = bf16_lo(v0[c].x); x[1] = bf16_hi(v0[c].x); x[2] = bf16_lo(v0[c].y); x[3] = bf16_hi(v0[c].y);
-        x[4] = bf16_lo(v0[c].z); x[5] = bf16_hi(v0[c].z); x[6] = bf16_lo(v0[c].w); x[7] = bf16_hi(v0[c].w);
-        y[0] = bf16_lo(v1[c].x); y[1] = bf16_hi(v1[c].x); y[2] = bf16_lo(v1[c].y); y[3] = bf16_hi(v1[c].y);
-        y[4] = bf16_lo(v1[c].z); y[5] = bf16_hi(v1[c].z); y[6] = bf16_lo(v1[c].w); y[7] = bf16_hi(v1[c].w);
+        unpack8<T>(v0[c], x);
+        unpack8<T>(v1[c], y);
       }
 #pragma unroll
       for (int k = 0; k < E; ++k) {
@@ -220,7 +226,7 @@ extern "C" int lpgnn_head_mask(const void* H, int h_dtype, int32_t rows, int32_t
                                const float* feas, int32_t q, float* logits, float* raw_out, lpgnn_stream_t stream) {
   if (int rc = check_device()) return rc;
   LPGNN_REQUIRE(rows >= 0 && Hdim > 0 && q >= 3, "head_mask: bad shape rows=%d Hdim=%d q=%d", rows, Hdim, q);
-  LPGNN_REQUIRE(h_dtype == LPGNN_F32 || h_dtype == LPGNN_BF16, "head_mask: bad dtype %d", h_dtype);
+  LPGNN_REQUIRE(dtype_ok(h_dtype), "head_mask: bad dtype %d", h_dtype);
   if (rows == 0) return LPGNN_OK;
   LPGNN_REQUIRE(H && W && b && feas && logits, "head_mask: null pointer");
   const int esz = h_dtype == LPGNN_F32 ? 4 : 2;
@@ -229,11 +235,12 @@ extern "C" int lpgnn_head_mask(const void* H, int h_dtype, int32_t rows, int32_t
   cudaStream_t st = (cudaStream_t)stream;
   const int chunks = Hdim * esz / 16;
   const int ch = (chunks + 31) / 32;
-  const bool f32 = h_dtype == LPGNN_F32;
+  const bool f32 = h_dtype == LPGNN_F32, f16 = h_dtype == LPGNN_F16;
   if (ch <= 8) {
 #define LPGNN_HEAD(CHV)                                                                                   \
   (f32 ? launch_reg<float, CHV>(H, rows, Hdim, W, b, feas, q, logits, raw_out, st)                        \
-       : launch_reg<__nv_bfloat16, CHV>(H, rows, Hdim, W, b, feas, q, logits, raw_out, st))
+       : f16 ? launch_reg<__half, CHV>(H, rows, Hdim, W, b, feas, q, logits, raw_out, st)                 \
+             : launch_reg<__nv_bfloat16, CHV>(H, rows, Hdim, W, b, feas, q, logits, raw_out, st))
     if (ch <= 1) LPGNN_HEAD(1); else if (ch <= 2) LPGNN_HEAD(2); else if (ch <= 4) LPGNN_HEAD(4); else LPGNN_HEAD(8);
 #undef LPGNN_HEAD
   } else {
@@ -243,6 +250,10 @@ extern "C" int lpgnn_head_mask(const void* H, int h_dtype, int32_t rows, int32_t
       LPGNN_CUDA_OK(cudaFuncSetAttribute(head_mask_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       head_mask_kernel<float><<<grid, kThreads, smem, st>>>(reinterpret_cast<const float*>(H), rows, Hdim, W, b, feas,
                                                             q, logits, raw_out);
+    } else if (f16) {
+      LPGNN_CUDA_OK(cudaFuncSetAttribute(head_mask_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      head_mask_kernel<__half><<<grid, kThreads, smem, st>>>(reinterpret_cast<const __half*>(H), rows, Hdim, W, b, feas, q,
+                                                             logits, raw_out);
     } else {
       LPGNN_CUDA_OK(cudaFuncSetAttribute(head_mask_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          96 * 1024));

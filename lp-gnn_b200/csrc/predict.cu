@@ -92,7 +92,7 @@ extern "C" size_t lpgnn_predict_workspace_bytes(int64_t nnz, int32_t m, int32_t 
                                                 int32_t depth, int precision) {
   Bump b(nullptr, ~(size_t)0);
   Buffers B;
-  return carve(b, B, nnz > 0 ? nnz : 1, m, n, p, q, hids, depth, (precision & 15) == LPGNN_BF16,
+  return carve(b, B, nnz > 0 ? nnz : 1, m, n, p, q, hids, depth, is_16bit(precision & 15),
                (precision & LPGNN_WS_X3) != 0);
 }
 
@@ -113,7 +113,8 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
   if (int rc = check_device()) return rc;
   LPGNN_REQUIRE(w && m > 0 && n > 0 && nnz >= 0 && x_s && x_t && status_out && workspace, "predict_basis: bad arguments");
   const int H = w->hids, depth = w->depth, p = w->p, q = w->q;
-  const int bf16 = w->precision == LPGNN_BF16;
+  const int bf16 = is_16bit(w->precision);   // 16-bit storage (bf16 or IEEE half): the tensor-core path
+  LPGNN_REQUIRE(dtype_ok(w->precision), "predict_basis: bad precision %d", w->precision);
   LPGNN_REQUIRE(depth >= 2 && depth - 2 <= LPGNN_MAX_HIDDEN_LAYERS, "predict_basis: depth %d unsupported", depth);
   LPGNN_REQUIRE(!bf16 || H % 64 == 0, "predict_basis: bf16 mode needs hids %% 64 == 0");
   const int x3 = !bf16 && depth > 2 && H % 64 == 0 && w->l2r_wrel_parts[0][0] != nullptr;
@@ -131,12 +132,12 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
   // ---- (a1) graph
   LPGNN_TRY(lpgnn_graph_build(coo_row, coo_col, 0, coo_val, nnz, m, n, flags, B.rowptr, B.col, B.val, B.colptr, B.row_csc,
                               B.val_csc, B.csr2csc, gstat, B.build_ws, B.build_ws_bytes, stream));
-  const int dt = bf16 ? LPGNN_BF16 : LPGNN_F32;
+  const int dt = bf16 ? w->precision : LPGNN_F32;
   void *left = B.act[0][0], *right = B.act[0][1];
   // ---- conv1 (+relu).  CSC view: dst = variables, src = constraints; CSR view: dst = constraints, src = variables
   if (bf16) {
-    LPGNN_TRY(lpgnn_gather_cat(B.colptr, B.row_csc, B.val_csc, n, x_s, p, x_t, q, nullptr, B.zb_t, stream));
-    LPGNN_TRY(lpgnn_gather_cat(B.rowptr, B.col, B.val, m, x_t, q, x_s, p, nullptr, B.zb_s, stream));
+    LPGNN_TRY(lpgnn_gather_cat_ex(B.colptr, B.row_csc, B.val_csc, n, x_s, p, x_t, q, nullptr, B.zb_t, dt, stream));
+    LPGNN_TRY(lpgnn_gather_cat_ex(B.rowptr, B.col, B.val, m, x_t, q, x_s, p, nullptr, B.zb_s, dt, stream));
     LPGNN_TRY(lpgnn_node_transform(B.zb_t, 64, w->c1_l2r_wcat, nullptr, 0, nullptr, w->c1_l2r_b, n, H, right, dt, dt,
                                    LPGNN_EPI_RELU, stream));
     LPGNN_TRY(lpgnn_node_transform(B.zb_s, 64, w->c1_r2l_wcat, nullptr, 0, nullptr, w->c1_r2l_b, m, H, left, dt, dt,
@@ -156,10 +157,10 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
     LPGNN_TRY(lpgnn_spmm(B.rowptr, B.col, B.val, m, right, B.agg_s, H, dt, stream));           // A   . right
     const bool last = li == n_hidden - 1;
     if (last && bf16) {  // head fused into the epilogue; the last activation never reaches HBM
-      LPGNN_TRY(lpgnn_node_transform_head(B.agg_t, H, w->l2r_wrel[li], right, H, w->l2r_wroot[li], w->l2r_b[li], n, H,
-                                          nullptr, LPGNN_EPI_RELU, w->head_right_w, B.part_t, stream));
-      LPGNN_TRY(lpgnn_node_transform_head(B.agg_s, H, w->r2l_wrel[li], left, H, w->r2l_wroot[li], w->r2l_b[li], m, H,
-                                          nullptr, LPGNN_EPI_RELU, w->head_left_w, B.part_s, stream));
+      LPGNN_TRY(lpgnn_node_transform_head_ex(B.agg_t, H, w->l2r_wrel[li], right, H, w->l2r_wroot[li], w->l2r_b[li], n, H,
+                                             nullptr, dt, LPGNN_EPI_RELU, w->head_right_w, B.part_t, stream));
+      LPGNN_TRY(lpgnn_node_transform_head_ex(B.agg_s, H, w->r2l_wrel[li], left, H, w->r2l_wroot[li], w->r2l_b[li], m, H,
+                                             nullptr, dt, LPGNN_EPI_RELU, w->head_left_w, B.part_s, stream));
       const int nparts = lpgnn_node_transform_head_parts(H);
       LPGNN_TRY(lpgnn_head_finish(B.part_t, nparts, n, w->head_right_b, x_t, q, B.logit_t, stream));
       LPGNN_TRY(lpgnn_head_finish(B.part_s, nparts, m, w->head_left_b, x_s, p, B.logit_s, stream));

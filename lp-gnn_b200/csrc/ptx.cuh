@@ -218,12 +218,12 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
   return d;
 }
 
-// Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, both operands K-major.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, bool mn_major = false) {
+// Instruction descriptor for kind::f16: bf16 x bf16 (or f16 x f16) -> fp32, both operands K-major.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, bool mn_major = false, bool f16 = false) {
   return (mn_major ? ((1u << 15) | (1u << 16)) : 0u)  // A / B major: 0 = K-major, 1 = MN-major
          | (1u << 4)                  // D format: F32
-         | (1u << 7)                  // A format: BF16
-         | (1u << 10)                 // B format: BF16
+         | ((f16 ? 0u : 1u) << 7)     // A format: 0 = F16, 1 = BF16
+         | ((f16 ? 0u : 1u) << 10)    // B format
          | ((uint32_t)(n >> 3) << 17) // N / 8
          | ((uint32_t)(m >> 4) << 24);// M / 16
 }

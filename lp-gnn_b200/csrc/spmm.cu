@@ -46,6 +46,21 @@ template <> struct Chunk<__nv_bfloat16> {
   }
 };
 
+template <> struct Chunk<__half> {
+  static constexpr int kElems = 8;
+  __device__ static void fma(float (&acc)[8], float w, const uint4& v) {
+    const float2 a = f16x2_unpack(v.x), b = f16x2_unpack(v.y), c = f16x2_unpack(v.z), d = f16x2_unpack(v.w);
+    acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]);
+    acc[2] = fmaf(w, b.x, acc[2]); acc[3] = fmaf(w, b.y, acc[3]);
+    acc[4] = fmaf(w, c.x, acc[4]); acc[5] = fmaf(w, c.y, acc[5]);
+    acc[6] = fmaf(w, d.x, acc[6]); acc[7] = fmaf(w, d.y, acc[7]);
+  }
+  __device__ static uint4 pack(const float (&acc)[8]) {
+    return make_uint4(pack_f16(acc[0], acc[1]), pack_f16(acc[2], acc[3]), pack_f16(acc[4], acc[5]),
+                      pack_f16(acc[6], acc[7]));
+  }
+};
+
 constexpr int kThreads = 256;
 
 // chunks_per_row = F*sizeof(T)/16.  G lanes per row, CH chunks per lane (G*CH >= chunks_per_row).
@@ -149,6 +164,19 @@ template <> struct PairAcc<__nv_bfloat16> {
   __device__ static uint4 pack(const float2 (&acc)[4]) {
     return make_uint4(pack_bf16(acc[0].x, acc[0].y), pack_bf16(acc[1].x, acc[1].y), pack_bf16(acc[2].x, acc[2].y),
                       pack_bf16(acc[3].x, acc[3].y));
+  }
+};
+template <> struct PairAcc<__half> {
+  static constexpr int kPairs = 4;
+  __device__ static void fma(float2 (&acc)[4], float2 ww, const uint4& v) {
+    acc[0] = __ffma2_rn(ww, f16x2_unpack(v.x), acc[0]);
+    acc[1] = __ffma2_rn(ww, f16x2_unpack(v.y), acc[1]);
+    acc[2] = __ffma2_rn(ww, f16x2_unpack(v.z), acc[2]);
+    acc[3] = __ffma2_rn(ww, f16x2_unpack(v.w), acc[3]);
+  }
+  __device__ static uint4 pack(const float2 (&acc)[4]) {
+    return make_uint4(pack_f16(acc[0].x, acc[0].y), pack_f16(acc[1].x, acc[1].y), pack_f16(acc[2].x, acc[2].y),
+                      pack_f16(acc[3].x, acc[3].y));
   }
 };
 template <> struct PairAcc<float> {
@@ -307,7 +335,7 @@ extern "C" int lpgnn_spmm_ex(const int32_t* ptr, const int32_t* idx, const float
                              void* Y, int32_t F, int dtype, int slab_bytes, int unroll, lpgnn_stream_t stream) {
   if (int rc = check_device()) return rc;
   LPGNN_REQUIRE(rows >= 0 && F > 0, "spmm: bad shape rows=%d F=%d", rows, F);
-  LPGNN_REQUIRE(dtype == LPGNN_F32 || dtype == LPGNN_BF16, "spmm: bad dtype %d", dtype);
+  LPGNN_REQUIRE(dtype_ok(dtype), "spmm: bad dtype %d", dtype);
   if (rows == 0) return LPGNN_OK;
   LPGNN_REQUIRE(ptr && X && Y, "spmm: null pointer");
   const int esz = dtype == LPGNN_F32 ? 4 : 2;
@@ -323,11 +351,13 @@ extern "C" int lpgnn_spmm_ex(const int32_t* ptr, const int32_t* idx, const float
   }
   if (slab_bytes < 0) {             // row-per-warp kernel
     if (dtype == LPGNN_F32) return dispatch<float>(ptr, idx, val, rows, X, Y, chunks, st);
+    if (dtype == LPGNN_F16) return dispatch<__half>(ptr, idx, val, rows, X, Y, chunks, st);
     return dispatch<__nv_bfloat16>(ptr, idx, val, rows, X, Y, chunks, st);
   }
   LPGNN_REQUIRE(row_bytes % slab_bytes == 0, "spmm: row of %d bytes is not a multiple of the %d-byte slab", row_bytes, slab_bytes);
   if (unroll <= 0) unroll = dtype == LPGNN_F32 ? 4 : 2;
   if (dtype == LPGNN_F32) return dispatch_sweep<float>(ptr, idx, val, rows, X, Y, chunks, slab_bytes, unroll, st);
+  if (dtype == LPGNN_F16) return dispatch_sweep<__half>(ptr, idx, val, rows, X, Y, chunks, slab_bytes, unroll, st);
   return dispatch_sweep<__nv_bfloat16>(ptr, idx, val, rows, X, Y, chunks, slab_bytes, unroll, st);
 }
 

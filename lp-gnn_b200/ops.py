@@ -55,20 +55,20 @@ def conv_in_fused(view, x_src, x_dst, w_rel, b_rel, w_root, out_dtype, relu=True
     return out, z_cat
 
 
-def gather_cat(view, x_src, x_dst, want_f32=True, want_bf16=False):
-    """``z = [A_view @ x_src | x_dst | 0]``: fp32 ``[rows,KT]`` and/or bf16 ``[rows,64]`` (input of the
-    tensor-core transform in bf16 mode)."""
+def gather_cat(view, x_src, x_dst, want_f32=True, want_bf16=False, dtype16=torch.bfloat16):
+    """``z = [A_view @ x_src | x_dst | 0]``: fp32 ``[rows,KT]`` and/or 16-bit ``[rows,64]`` (``dtype16``: bf16 or
+    half; input of the tensor-core transform in the 16-bit modes)."""
     ptr_, idx, val, rows = view
     require_cuda(ptr_, x_src, x_dst)
     x_src, x_dst = _contig(x_src.float()), _contig(x_dst.float())
     lib = _lib.load()
     kt = lib.lpgnn_conv_in_zcat_width(x_src.shape[1], x_dst.shape[1])
     z32 = torch.empty((rows, kt), dtype=torch.float32, device=x_src.device) if want_f32 else None
-    zb = torch.empty((rows, 64), dtype=torch.bfloat16, device=x_src.device) if want_bf16 else None
+    zb = torch.empty((rows, 64), dtype=dtype16, device=x_src.device) if want_bf16 else None
     with torch.cuda.device(x_src.device):
-        rc = lib.lpgnn_gather_cat(ptr_.data_ptr(), idx.data_ptr(), val.data_ptr(), rows, x_src.data_ptr(), x_src.shape[1],
-                                  x_dst.data_ptr(), x_dst.shape[1], ptr(z32), ptr(zb), stream_ptr())
-    check(rc, "lpgnn_gather_cat")
+        rc = lib.lpgnn_gather_cat_ex(ptr_.data_ptr(), idx.data_ptr(), val.data_ptr(), rows, x_src.data_ptr(), x_src.shape[1],
+                                     x_dst.data_ptr(), x_dst.shape[1], ptr(z32), ptr(zb), dtype_code(dtype16), stream_ptr())
+    check(rc, "lpgnn_gather_cat_ex")
     return z32, zb
 
 
@@ -136,10 +136,11 @@ def node_transform_head(a1, w1, a2, w2, bias, head_w, head_b, feas, relu=True, w
     out = torch.empty((M, N), dtype=a1.dtype, device=a1.device) if want_out else None
     logits = torch.empty((M, 3), dtype=torch.float32, device=a1.device)
     with torch.cuda.device(a1.device):
-        rc = lib.lpgnn_node_transform_head(a1.data_ptr(), K1, w1.data_ptr(), a2.data_ptr(), K2, w2.data_ptr(), bias.data_ptr(),
-                                           M, N, ptr(out), EPI_RELU if relu else EPI_NONE, head_w.data_ptr(),
-                                           partial.data_ptr(), stream_ptr())
-        check(rc, "lpgnn_node_transform_head")
+        rc = lib.lpgnn_node_transform_head_ex(a1.data_ptr(), K1, w1.data_ptr(), a2.data_ptr(), K2, w2.data_ptr(),
+                                              bias.data_ptr(), M, N, ptr(out), dtype_code(a1.dtype),
+                                              EPI_RELU if relu else EPI_NONE, head_w.data_ptr(), partial.data_ptr(),
+                                              stream_ptr())
+        check(rc, "lpgnn_node_transform_head_ex")
         rc = lib.lpgnn_head_finish(partial.data_ptr(), nparts, M, head_b.data_ptr(), feas.data_ptr(), feas.shape[1],
                                    logits.data_ptr(), stream_ptr())
     check(rc, "lpgnn_head_finish")

@@ -121,7 +121,7 @@ def run_exp(args):
         model.load(args.load_from)
     model = model.to(dev)
     if args.fp16:
-        model.half()
+        model.bfloat16()     # 16-bit TRAINING uses bf16 storage (half would need loss scaling); `.half()` is inference-only
     broadcast_parameters(model, world)
     params = list(model.parameters())
     if args.opt == "adam":

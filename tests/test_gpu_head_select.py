@@ -16,7 +16,8 @@ def _feas(rows, rng):
 
 
 @pytest.mark.parametrize("H,dtype", [(64, torch.float32), (128, torch.float32), (1024, torch.float32),
-                                      (1024, torch.bfloat16), (64, torch.bfloat16)])
+                                      (1024, torch.bfloat16), (64, torch.bfloat16), (1024, torch.float16),
+                                      (128, torch.float16), (2048, torch.float16)])
 def test_head_mask_vs_oracle(cuda, H, dtype):
     import lpgnn_b200  # noqa: F401
     from lpgnn_b200 import ops

@@ -36,17 +36,18 @@ def test_spmm_fp32_both_orientations(cuda, m, n, z, F):
 
 
 @pytest.mark.parametrize("F", [8, 64, 128, 1024])
-def test_spmm_bf16(cuda, F):
+@pytest.mark.parametrize("dt16", [torch.bfloat16, torch.float16])
+def test_spmm_bf16(cuda, F, dt16):
     from lpgnn_b200 import ops
     m, n, z = 500, 900, 6000
     g, ref = _graph(m, n, z, 7, cuda)
-    x = torch.randn(n, F, generator=torch.Generator().manual_seed(F)).to(torch.bfloat16)
+    x = torch.randn(n, F, generator=torch.Generator().manual_seed(F)).to(dt16)
     csr, _ = g.views()
     y = ops.spmm(csr, x.to(cuda)).float().cpu().numpy()
     e = port.spmm_sequential(ref.rowptr, ref.col, ref.val, x.float().numpy())   # fp32 accumulate of bf16 inputs
     np.testing.assert_allclose(y, e, rtol=1e-2, atol=1e-2)                       # output rounding to bf16
     # and the rounding is the ONLY difference: re-round the oracle
-    e_bf = torch.from_numpy(e).to(torch.bfloat16).float().numpy()
+    e_bf = torch.from_numpy(e).to(dt16).float().numpy()
     assert np.mean(y == e_bf) > 0.99
 
 
@@ -87,7 +88,7 @@ def test_spmm_linearity_full_size_c2(cuda):
         assert float((a[r].double() - e).abs().max()) < 1e-4
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("structure", ["staircase", "uniform"])
 def test_banded_sweep_kernel_is_bit_identical_to_row_kernel(cuda, dtype, structure):
     """Every kernel setting of lpgnn_spmm_ex (row-per-warp, 512 B / 1 KB slabs, 2 / 4 gathers in flight, automatic)
@@ -96,7 +97,7 @@ def test_banded_sweep_kernel_is_bit_identical_to_row_kernel(cuda, dtype, structu
     import lpgnn_b200  # noqa: F401
     from lpgnn_b200 import ops, synth
     from lpgnn_b200.graph import BipartiteCSR
-    m, n, F = 12_000, 24_000, 1024 if dtype == torch.bfloat16 else 512
+    m, n, F = 12_000, 24_000, 1024 if dtype != torch.float32 else 512
     c, b_l, A, b_u, l, u = synth.raw_lp(m, n, 5 * n, 31, structure)
     A = A.tocsr()
     A.sort_indices()
@@ -109,8 +110,8 @@ def test_banded_sweep_kernel_is_bit_identical_to_row_kernel(cuda, dtype, structu
         ref = ops.spmm(view, xs[k], slab_bytes=-1)
         for slab, unroll in ((0, 0), (512, 2), (512, 4), (1024, 2), (1024, 4)):
             got = ops.spmm(view, xs[k], slab_bytes=slab, unroll=unroll)
-            assert torch.equal(got.view(torch.int16 if dtype == torch.bfloat16 else torch.int32),
-                               ref.view(torch.int16 if dtype == torch.bfloat16 else torch.int32)), (k, slab, unroll)
+            assert torch.equal(got.view(torch.int16 if dtype != torch.float32 else torch.int32),
+                               ref.view(torch.int16 if dtype != torch.float32 else torch.int32)), (k, slab, unroll)
         ptr_, idx, v, rows = (t.cpu().numpy() if torch.is_tensor(t) else t for t in view)
         pick = np.unique(np.concatenate([[0, rows - 1], np.random.default_rng(k).integers(0, rows, 200)]))
         sub_ptr = np.concatenate([[0], np.cumsum(ptr_[pick + 1] - ptr_[pick])])
@@ -118,8 +119,8 @@ def test_banded_sweep_kernel_is_bit_identical_to_row_kernel(cuda, dtype, structu
         sub_val = np.concatenate([v[ptr_[r]:ptr_[r + 1]] for r in pick])
         e = port.spmm_sequential(sub_ptr, sub_idx, sub_val, xs[k].float().cpu().numpy())
         got = ref[torch.from_numpy(pick).to(cuda)].float().cpu().numpy()
-        if dtype == torch.bfloat16:
-            assert np.mean(got == torch.from_numpy(e).to(torch.bfloat16).float().numpy()) > 0.99
+        if dtype != torch.float32:
+            assert np.mean(got == torch.from_numpy(e).to(dtype).float().numpy()) > 0.99
         else:
             np.testing.assert_allclose(got, e, rtol=1e-5, atol=1e-5)
 
