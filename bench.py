@@ -214,7 +214,7 @@ def run_gpu(args):
         with torch.cuda.stream(st):
             return model.predict_basis_coo(d_row, d_col, d_val, m, n, d_xs, d_xt, is_sorted=True)
 
-    pipe = BasisPipeline(model, dev)
+    pipe = BasisPipeline(model, dev, compute_streams=max(args.inflight, 1))
 
     def run_e2e(k):
         """k steps through the public pipeline API: per step one H2D copy of the packed LP from pinned host memory
@@ -688,7 +688,7 @@ def main():
     ap.add_argument("--sweep-pack", type=int, default=1, help="C5 e2e arm: pack LPs block-diagonally (1) or one call per LP (0)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32", "fp32_tc"])
     ap.add_argument("--structure", default="staircase", choices=["staircase", "uniform"])
-    ap.add_argument("--inflight", type=int, default=2, help="LPs in flight on alternating streams (HBM-resident arm)")
+    ap.add_argument("--inflight", type=int, default=3, help="LPs in flight on alternating streams (both arms)")
     ap.add_argument("--kernel-reps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")

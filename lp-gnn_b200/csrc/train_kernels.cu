@@ -195,87 +195,89 @@ small_wgrad_reduce_kernel(const float* __restrict__ partial, int nchunks, int N,
 }
 
 // ------------------------------------------------------------------------------------------- head_mask_bwd
-// One warp per row.  draw = d(10 * raw / max(|raw|, eps)) ; dH[row, :] = (draw . W) * scale * (Hact > 0).
-// CS: also emits per-block partial column sums of dH (fp32, before the output rounding) -- the bias gradient of the
-// layer under the head -- so that no separate pass has to read dH back (cs_partials [gridDim.x][Hdim]).
-template <typename T, int CH, bool CS>
-__global__ void __launch_bounds__(128)
+// draw = d(10 * raw / max(|raw|, eps)) ; dH[row, :] = (draw . W) * scale * (Hact > 0).
+// A block covers the whole feature row: lane l of warp w owns the 16-byte chunk 32*w + l of EVERY row the block
+// visits, so the three head-weight values of its columns live in 3*E registers (not 3*E*chunks-per-lane as with a warp
+// per row) and the R independent row loads of a group are all in flight before the first is used -- the kernel is a
+// pure stream (read Hact once, write dH once) and needs that memory parallelism to approach the HBM roofline.
+// CS: per-block partial column sums of dH (fp32, before the output rounding) -- the bias gradient of the layer under
+// the head -- without a pass that reads dH back; a column belongs to one thread of the block, rows are visited in
+// a fixed order: deterministic (cs_partials [gridDim.x][Hdim], combined by colsum_finish_kernel).
+template <typename T, int R, bool CS>
+__global__ void __launch_bounds__(256)
 head_mask_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ raw, const T* __restrict__ Hact,
                      int32_t rows, int32_t Hdim, const float* __restrict__ W, float scale, T* __restrict__ dH,
                      float* __restrict__ draw_out, __nv_bfloat16* __restrict__ draw_bf16, float* __restrict__ cs_partials) {
   constexpr int E = Vec16<T>::E;
-  float cs[CS ? CH : 1][E];
-#pragma unroll
-  for (int c = 0; c < (CS ? CH : 1); ++c)
-#pragma unroll
-    for (int k = 0; k < E; ++k) cs[c][k] = 0.f;
-  const int lane = threadIdx.x & 31;
+  static_assert(R <= 32 && (R % 4) == 0, "a group's rows are handled by the first R lanes");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int chunks = Hdim / E;
-  float w[3][CH][E];
+  const int ch = warp * 32 + lane;
+  const bool live = ch < chunks;
+  float w[3][E], cs[E];
 #pragma unroll
-  for (int c = 0; c < CH; ++c) {
-    const int ch = lane + 32 * c;
+  for (int k = 0; k < E; ++k) {
+    cs[k] = 0.f;
 #pragma unroll
-    for (int j = 0; j < 3; ++j)
-#pragma unroll
-      for (int k = 0; k < E; ++k) w[j][c][k] = (ch < chunks) ? __ldg(W + (int64_t)j * Hdim + ch * E + k) : 0.f;
+    for (int j = 0; j < 3; ++j) w[j][k] = live ? __ldg(W + (int64_t)j * Hdim + ch * E + k) : 0.f;
   }
-  const int warps_total = gridDim.x * 4;
-  for (int64_t row = blockIdx.x * 4 + (threadIdx.x >> 5); row < rows; row += warps_total) {
-    uint4 v[CH];
+  for (int64_t r0 = (int64_t)blockIdx.x * R; r0 < rows; r0 += (int64_t)gridDim.x * R) {
+    uint4 v[R];
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int ch = lane + 32 * c;
-      v[c] = (ch < chunks) ? __ldg(reinterpret_cast<const uint4*>(Hact + row * Hdim) + ch) : make_uint4(0, 0, 0, 0);
-    }
-    const float x0 = __ldg(raw + row * 3), x1 = __ldg(raw + row * 3 + 1), x2 = __ldg(raw + row * 3 + 2);
-    const float g0 = __ldg(dlogits + row * 3), g1 = __ldg(dlogits + row * 3 + 1), g2 = __ldg(dlogits + row * 3 + 2);
-    const float nrm = sqrtf(x0 * x0 + x1 * x1 + x2 * x2);
-    float d0, d1, d2;
-    if (nrm > 1e-12f) {
-      const float inv = 1.f / nrm;
-      const float u0 = x0 * inv, u1 = x1 * inv, u2 = x2 * inv;
-      const float dot = u0 * g0 + u1 * g1 + u2 * g2;
-      const float s = 10.f * inv;
-      d0 = s * (g0 - u0 * dot); d1 = s * (g1 - u1 * dot); d2 = s * (g2 - u2 * dot);
-    } else {  // clamp branch of F.normalize: the denominator is the constant eps
-      d0 = 1e13f * g0; d1 = 1e13f * g1; d2 = 1e13f * g2;
-    }
-    if (lane == 0 && draw_out) { draw_out[row * 3] = d0; draw_out[row * 3 + 1] = d1; draw_out[row * 3 + 2] = d2; }
-    if (draw_bf16 && lane < 8) {   // [d0 d1 d2 0 ... 0] as one 128-byte row: the MN-major operand of the head's weight gradient
-      uint4 o = make_uint4(0, 0, 0, 0);
-      if (lane == 0) {
-        o.x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(d0)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(d1)) << 16);
-        o.y = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(d2));
+    for (int i = 0; i < R; ++i)
+      v[i] = (live && r0 + i < rows) ? __ldg(reinterpret_cast<const uint4*>(Hact + (r0 + i) * Hdim) + ch) : make_uint4(0, 0, 0, 0);
+    // lane i < R: the normalise-Jacobian of row r0 + i (every warp redoes these 24 bytes per row: L1 hits)
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    const int64_t myrow = r0 + lane;
+    if (lane < R && myrow < rows) {
+      const float x0 = __ldg(raw + myrow * 3), x1 = __ldg(raw + myrow * 3 + 1), x2 = __ldg(raw + myrow * 3 + 2);
+      const float g0 = __ldg(dlogits + myrow * 3), g1 = __ldg(dlogits + myrow * 3 + 1), g2 = __ldg(dlogits + myrow * 3 + 2);
+      const float nrm = sqrtf(x0 * x0 + x1 * x1 + x2 * x2);
+      if (nrm > 1e-12f) {
+        const float inv = 1.f / nrm;
+        const float u0 = x0 * inv, u1 = x1 * inv, u2 = x2 * inv;
+        const float dot = u0 * g0 + u1 * g1 + u2 * g2;
+        const float s = 10.f * inv;
+        d0 = s * (g0 - u0 * dot); d1 = s * (g1 - u1 * dot); d2 = s * (g2 - u2 * dot);
+      } else {  // clamp branch of F.normalize: the denominator is the constant eps
+        d0 = 1e13f * g0; d1 = 1e13f * g1; d2 = 1e13f * g2;
       }
-      reinterpret_cast<uint4*>(draw_bf16 + row * 64)[lane] = o;
+      if (warp == 0 && draw_out) { draw_out[myrow * 3] = d0; draw_out[myrow * 3 + 1] = d1; draw_out[myrow * 3 + 2] = d2; }
+    }
+    if (warp == 0 && draw_bf16) {   // [d0 d1 d2 0 ... 0] as one 128-byte row: the MN-major operand of the head's weight gradient
+#pragma unroll
+      for (int i = 0; i < R / 4; ++i) {          // lane -> (row 4*i + lane / 8, 16-byte piece lane % 8)
+        const int rr = 4 * i + (lane >> 3);
+        const float e0 = __shfl_sync(0xffffffffu, d0, rr), e1 = __shfl_sync(0xffffffffu, d1, rr), e2 = __shfl_sync(0xffffffffu, d2, rr);
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if ((lane & 7) == 0) {
+          o.x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(e0)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(e1)) << 16);
+          o.y = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(e2));
+        }
+        if (r0 + rr < rows) reinterpret_cast<uint4*>(draw_bf16 + (r0 + rr) * 64)[lane & 7] = o;
+      }
     }
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int ch = lane + 32 * c;
-      if (ch < chunks) {
+    for (int i = 0; i < R; ++i) {
+      const float e0 = __shfl_sync(0xffffffffu, d0, i), e1 = __shfl_sync(0xffffffffu, d1, i), e2 = __shfl_sync(0xffffffffu, d2, i);
+      if (live && r0 + i < rows) {
         float x[E], y[E];
-        Vec16<T>::unpack(v[c], x);
+        Vec16<T>::unpack(v[i], x);
 #pragma unroll
         for (int k = 0; k < E; ++k) {
-          const float g = fmaf(d0, w[0][c][k], fmaf(d1, w[1][c][k], d2 * w[2][c][k]));
+          const float g = fmaf(e0, w[0][k], fmaf(e1, w[1][k], e2 * w[2][k]));
           y[k] = (x[k] > 0.f) ? g * scale : 0.f;
-          if constexpr (CS) cs[c][k] += y[k];          // rows in a fixed order per warp: deterministic
+          if constexpr (CS) cs[k] += y[k];
         }
-        reinterpret_cast<uint4*>(dH + row * Hdim)[ch] = Vec16<T>::pack(y);
+        reinterpret_cast<uint4*>(dH + (r0 + i) * Hdim)[ch] = Vec16<T>::pack(y);
       }
     }
   }
   if constexpr (CS) {
-    __shared__ float red[4][CH * 32 * E];
-    const int warp = threadIdx.x >> 5;
+    if (live) {
 #pragma unroll
-    for (int c = 0; c < CH; ++c)
-#pragma unroll
-      for (int k = 0; k < E; ++k) red[warp][(lane + 32 * c) * E + k] = cs[c][k];
-    __syncthreads();
-    for (int j = threadIdx.x; j < Hdim; j += 128)
-      cs_partials[(int64_t)blockIdx.x * Hdim + j] = ((red[0][j] + red[1][j]) + red[2][j]) + red[3][j];
+      for (int k = 0; k < E; ++k) cs_partials[(int64_t)blockIdx.x * Hdim + ch * E + k] = cs[k];
+    }
   }
 }
 
@@ -450,30 +452,31 @@ extern "C" int lpgnn_small_wgrad(const void* dY, int dtype, const float* Z, int3
 #undef LPGNN_WG
 }
 
-static int head_bwd_grid(int32_t rows, bool colsum) {
-  // with fused column sums the grid is also the number of partial rows the finishing kernel reads
-  return min(ceil_div(rows, 4), sm_count() * (colsum ? 8 : 16));
+constexpr int kHeadBwdRows = 8;     // rows of one group: independent 16-byte loads in flight per lane
+
+static int head_bwd_grid(int32_t rows) {
+  // also the number of partial rows the column-sum finishing kernel reads
+  return min(ceil_div(rows, kHeadBwdRows), sm_count() * 8);
 }
 
 template <typename T>
 static int head_bwd_dispatch(const float* dlogits, const float* raw, const void* Hact, int32_t rows, int32_t Hdim,
-                             const float* W, float scale, void* dH, float* draw, void* draw_bf16, int ch, float* cs_partials,
+                             const float* W, float scale, void* dH, float* draw, void* draw_bf16, int warps, float* cs_partials,
                              cudaStream_t st) {
-  const int grid = head_bwd_grid(rows, cs_partials != nullptr);
-#define LPGNN_HB(CHV, CSV) head_mask_bwd_kernel<T, CHV, CSV><<<grid, 128, 0, st>>>(dlogits, raw, (const T*)Hact, rows, Hdim, W, scale, (T*)dH, draw, (__nv_bfloat16*)draw_bf16, cs_partials)
-  if (cs_partials) {
-    if (ch <= 1) LPGNN_HB(1, true); else if (ch <= 2) LPGNN_HB(2, true); else if (ch <= 4) LPGNN_HB(4, true); else LPGNN_HB(8, true);
-  } else {
-    if (ch <= 1) LPGNN_HB(1, false); else if (ch <= 2) LPGNN_HB(2, false); else if (ch <= 4) LPGNN_HB(4, false); else LPGNN_HB(8, false);
-  }
-#undef LPGNN_HB
+  const int grid = head_bwd_grid(rows);
+  if (cs_partials)
+    head_mask_bwd_kernel<T, kHeadBwdRows, true><<<grid, 32 * warps, 0, st>>>(dlogits, raw, (const T*)Hact, rows, Hdim, W, scale, (T*)dH,
+                                                                            draw, (__nv_bfloat16*)draw_bf16, cs_partials);
+  else
+    head_mask_bwd_kernel<T, kHeadBwdRows, false><<<grid, 32 * warps, 0, st>>>(dlogits, raw, (const T*)Hact, rows, Hdim, W, scale, (T*)dH,
+                                                                             draw, (__nv_bfloat16*)draw_bf16, nullptr);
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;
 }
 
 extern "C" size_t lpgnn_head_mask_bwd_colsum_workspace_bytes(int32_t rows, int32_t Hdim) {
-  return (size_t)head_bwd_grid(rows > 0 ? rows : 1, true) * (size_t)Hdim * sizeof(float) + 256;
+  return (size_t)head_bwd_grid(rows > 0 ? rows : 1) * (size_t)Hdim * sizeof(float) + 256;
 }
 
 extern "C" int lpgnn_head_mask_bwd_colsum(const float* dlogits, const float* raw, const void* Hact, int h_dtype, int32_t rows,
@@ -491,8 +494,9 @@ extern "C" int lpgnn_head_mask_bwd_colsum(const float* dlogits, const float* raw
   LPGNN_REQUIRE(dlogits && raw && Hact && W && dH, "head_mask_bwd: null pointer");
   const int esz = h_dtype == LPGNN_F32 ? 4 : 2;
   LPGNN_REQUIRE((Hdim * esz) % 16 == 0, "head_mask_bwd: row bytes must be a multiple of 16");
-  const int ch = (Hdim * esz / 16 + 31) / 32;
+  const int ch = (Hdim * esz / 16 + 31) / 32;    // warps per block: one 16-byte chunk of the row per lane
   LPGNN_REQUIRE(ch <= 8, "head_mask_bwd: Hdim=%d too wide (max 4096 bytes per row)", Hdim);
+  LPGNN_REQUIRE((uintptr_t)Hact % 16 == 0 && (uintptr_t)dH % 16 == 0, "head_mask_bwd: Hact / dH must be 16-byte aligned");
   float* partials = nullptr;
   if (colsum_out) {
     if (!workspace || workspace_bytes < lpgnn_head_mask_bwd_colsum_workspace_bytes(rows, Hdim)) {
@@ -505,7 +509,7 @@ extern "C" int lpgnn_head_mask_bwd_colsum(const float* dlogits, const float* raw
                ? head_bwd_dispatch<float>(dlogits, raw, Hact, rows, Hdim, W, scale, dH, draw, draw_bf16, ch, partials, st)
                : head_bwd_dispatch<__nv_bfloat16>(dlogits, raw, Hact, rows, Hdim, W, scale, dH, draw, draw_bf16, ch, partials, st);
   if (rc || !colsum_out) return rc;
-  colsum_finish_kernel<<<ceil_div(Hdim, 32), 256, 0, st>>>(partials, head_bwd_grid(rows, true), Hdim, colsum_out);
+  colsum_finish_kernel<<<ceil_div(Hdim, 32), 256, 0, st>>>(partials, head_bwd_grid(rows), Hdim, colsum_out);
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;

@@ -53,23 +53,24 @@ def unpack_device(d_pack, lp: HostLP):
 
 
 class BasisPipeline:
-    """Double-buffered predict loop: ``for idx, status in pipe.run(host_lps)`` yields the uint8 status vector
-    (constraints first) of every LP, in order.  The yielded array is a view of a pinned slot that is reused two
-    LPs later -- copy it if it must outlive the next iteration."""
+    """Multi-buffered predict loop: ``for idx, status in pipe.run(host_lps)`` yields the uint8 status vector
+    (constraints first) of every LP, in order.  The yielded array is a view of a pinned slot that is reused
+    ``depth`` LPs later -- copy it if it must outlive the next iteration."""
 
-    def __init__(self, model, device, compute_streams=2):
-        """``compute_streams=2``: consecutive LPs run on alternating streams, so the latency-bound small kernels of
-        one LP (graph build, basis selection) overlap the neighbouring LP's work; 1 = strictly one LP at a time on
-        the caller's current stream."""
+    def __init__(self, model, device, compute_streams=3):
+        """``compute_streams=k > 1``: k LPs in flight, consecutive LPs on k alternating streams (one staging slot
+        each), so the latency-bound small kernels of one LP (graph build, basis selection) overlap the neighbouring
+        LPs' work; 1 = strictly one LP at a time on the caller's current stream (two staging slots)."""
         if not torch.cuda.is_available():
             raise RuntimeError("BasisPipeline needs a CUDA device (no CPU fallback)")
         self.model, self.dev = model, torch.device(device)
+        self.depth = D = max(2, int(compute_streams))
         self.copy_stream = torch.cuda.Stream(self.dev)
-        self.compute = [torch.cuda.Stream(self.dev) for _ in range(2)] if compute_streams > 1 else None
-        self.d_buf = [None, None]
-        self.h_status = [None, None]
-        self.ready = [torch.cuda.Event(), torch.cuda.Event()]      # H2D of the slot finished
-        self.done = [torch.cuda.Event(), torch.cuda.Event()]       # compute + D2H of the slot finished
+        self.compute = [torch.cuda.Stream(self.dev) for _ in range(D)] if compute_streams > 1 else None
+        self.d_buf = [None] * D
+        self.h_status = [None] * D
+        self.ready = [torch.cuda.Event() for _ in range(D)]        # H2D of the slot finished
+        self.done = [torch.cuda.Event() for _ in range(D)]         # compute + D2H of the slot finished
 
     def _copy_in(self, slot, lp: HostLP, first_use):
         words = lp.pack.numel()
@@ -89,7 +90,7 @@ class BasisPipeline:
             return self._compute_on(slot, lp, self.compute[slot])
 
     def _compute_on(self, slot, lp: HostLP, cur):
-        # the slot's previous result (LP i-2) was handed out one iteration ago, so its host buffer may be replaced
+        # the slot's previous result (LP i-depth) was handed out at least one iteration ago, so its host buffer may be replaced
         nodes = lp.m + lp.n
         if self.h_status[slot] is None or self.h_status[slot].numel() < nodes:
             self.h_status[slot] = torch.empty(int(nodes * 1.25) + 64, dtype=torch.uint8).pin_memory()
@@ -103,22 +104,22 @@ class BasisPipeline:
         lps = list(host_lps)
         if not lps:
             return
+        D = self.depth
         if self.compute is not None:                               # weights etc. were produced on the caller's stream
             for st in self.compute:
                 st.wait_stream(torch.cuda.current_stream(self.dev))
         self._copy_in(0, lps[0], True)
         for i, lp in enumerate(lps):
-            slot = i & 1
             if i + 1 < len(lps):
-                self._copy_in(slot ^ 1, lps[i + 1], i + 1 < 2)     # prefetch the next LP while this one computes
-            self._compute(slot, lp)
-            if i > 0:
-                self.done[slot ^ 1].synchronize()
-                prev = lps[i - 1]
-                yield i - 1, self.h_status[slot ^ 1][:prev.m + prev.n].numpy()
-        last = len(lps) - 1
-        self.done[last & 1].synchronize()
-        yield last, self.h_status[last & 1][:lps[last].m + lps[last].n].numpy()
+                self._copy_in((i + 1) % D, lps[i + 1], i + 1 < D)  # prefetch the next LP while this one computes
+            self._compute(i % D, lp)
+            j = i - (D - 1)                                        # oldest LP in flight: its slot is needed next
+            if j >= 0:
+                self.done[j % D].synchronize()
+                yield j, self.h_status[j % D][:lps[j].m + lps[j].n].numpy()
+        for j in range(max(0, len(lps) - (D - 1)), len(lps)):
+            self.done[j % D].synchronize()
+            yield j, self.h_status[j % D][:lps[j].m + lps[j].n].numpy()
 
 
 class PackedBasisPipeline:

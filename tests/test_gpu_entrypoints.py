@@ -139,6 +139,15 @@ def test_basis_pipeline_matches_direct_calls(cuda):
     # a second pass over the same pipeline object reuses the slots
     again = {i: st.copy() for i, st in pipe.run(hosts[::-1])}
     np.testing.assert_array_equal(again[0], got[len(lps) - 1])
+    # any number of LPs in flight (1 = the caller's stream), including more slots than LPs: same statuses, in order
+    for k in (1, 2, 4, 8):
+        p2 = BasisPipeline(model, cuda, compute_streams=k)
+        order = []
+        for i, st in p2.run(hosts):
+            order.append(i)
+            np.testing.assert_array_equal(st, got[i])
+        assert order == list(range(len(lps)))
+        assert [i for i, _ in p2.run(hosts[:2])] == [0, 1]
 
 
 def test_packed_pipeline_matches_per_lp_prediction(cuda):
