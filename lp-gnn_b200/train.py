@@ -49,12 +49,34 @@ def broadcast_parameters(model, world):
             torch.distributed.broadcast(p.data, src=0)
 
 
+def _shared_flat_view(grads):
+    """The gradients as ONE flat tensor when they already are consecutive views of a single buffer (the native training
+    step hands them out that way, 16-byte aligned), else None."""
+    g0 = grads[0]
+    st = g0.untyped_storage()
+    end = g0.storage_offset()
+    for g in grads:
+        if (g.dtype != g0.dtype or not g.is_contiguous() or g.untyped_storage().data_ptr() != st.data_ptr()
+                or g.storage_offset() < end or g.storage_offset() - end > 3):
+            return None
+        end = g.storage_offset() + g.numel()
+    return torch.empty(0, dtype=g0.dtype, device=g0.device).set_(st, g0.storage_offset(), (end - g0.storage_offset(),))
+
+
 def allreduce_gradients(params, world):
-    """Mean of the gradients over ranks with one collective: flatten -> all_reduce(SUM) -> scale -> unflatten.
-    NCCL over NVLink/NVSwitch on the GPU box; gloo in the CPU tests.  Deterministic (fixed bucket layout)."""
+    """Mean of the gradients over ranks with one collective.  NCCL over NVLink/NVSwitch on the GPU box; gloo in the
+    CPU tests.  Deterministic (fixed bucket layout).  Gradients of the native training step live in one flat buffer and
+    are reduced in place; otherwise flatten -> all_reduce(SUM) -> scale -> unflatten."""
     if world == 1:
         return
     grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = _shared_flat_view(grads)
+    if flat is not None:                       # (alignment gaps of <= 3 floats between the views are reduced too: harmless)
+        torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM)
+        flat.mul_(1.0 / world)
+        return
     flat = torch.cat([g.reshape(-1) for g in grads])
     torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM)
     flat.mul_(1.0 / world)

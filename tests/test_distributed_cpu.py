@@ -36,7 +36,21 @@ def _worker(rank, world, port, out_dir):
         p.grad = torch.randn_like(p)
     local = [p.grad.clone() for p in model.parameters()]
     train.allreduce_gradients(list(model.parameters()), world)
-    torch.save(dict(w=[p.detach().clone() for p in model.parameters()], g=[p.grad.clone() for p in model.parameters()],
+    g_cat = [p.grad.clone() for p in model.parameters()]
+    # the native training step hands the gradients out as consecutive 16-byte-aligned views of ONE buffer: reduced in place
+    params = list(model.parameters())
+    assert train._shared_flat_view([p.grad for p in params]) is None
+    offs = [0]
+    for p in params:
+        offs.append(offs[-1] + (p.numel() + 3) // 4 * 4)
+    flat = torch.zeros(offs[-1])
+    for p, o, l in zip(params, offs, local):
+        p.grad = flat[o:o + p.numel()].view(p.shape)
+        p.grad.copy_(l)
+    fv = train._shared_flat_view([p.grad for p in params])
+    assert fv is not None and fv.data_ptr() == flat.data_ptr() and fv.numel() == offs[-2] + params[-1].numel()
+    train.allreduce_gradients(params, world)
+    torch.save(dict(w=[p.detach().clone() for p in model.parameters()], g=g_cat, g_flat=[p.grad.clone() for p in params],
                     local=local, shard=io_utils.shard_indices(11, rank, world)), os.path.join(out_dir, f"r{rank}.pt"))
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
@@ -52,4 +66,6 @@ def test_two_rank_gloo_broadcast_allreduce_and_sharding(tmp_path):
     for g0, g1, l0, l1 in zip(r0["g"], r1["g"], r0["local"], r1["local"]):
         assert torch.equal(g0, g1)                                  # every rank holds the same averaged gradient
         assert torch.allclose(g0, (l0 + l1) / 2, atol=1e-6)
+    for g0, gf0, gf1 in zip(r0["g"], r0["g_flat"], r1["g_flat"]):
+        assert torch.equal(gf0, gf1) and torch.equal(gf0, g0)       # in-place flat path == flatten / unflatten path
     assert sorted(r0["shard"] + r1["shard"]) == list(range(11)) and not set(r0["shard"]) & set(r1["shard"])
