@@ -441,6 +441,18 @@ LPGNN_API int lpgnn_train_backward(const lpgnn_gcn_fc_weights* w, const int32_t*
                          int32_t m, int32_t n, float dropout_p, const float* dlogits_s, const float* dlogits_t,
                          const lpgnn_gcn_fc_grads* grads, void* workspace, size_t workspace_bytes,
                          lpgnn_stream_t stream);
+/* The same pass in two parts for data-parallel training: LPGNN_BWD_TAIL = head gradients + weight / bias gradients of
+ * the LAST hidden layer (at depth 3: all [hids,hids] matrices, i.e. 99 % of the parameters), LPGNN_BWD_REST = the rest
+ * (data gradients, earlier layers, input layer).  TAIL then REST enqueues exactly the kernels of lpgnn_train_backward in
+ * the same order (bit-identical gradients); the caller starts the all-reduce of the tail gradients in between, so the
+ * collective overlaps the remaining ~40 % of the backward pass (train.py, `training.set_gradient_sync`). */
+#define LPGNN_BWD_TAIL 1
+#define LPGNN_BWD_REST 2
+LPGNN_API int lpgnn_train_backward_ex(const lpgnn_gcn_fc_weights* w, const int32_t* rowptr, const int32_t* col,
+                         const float* val, const int32_t* colptr, const int32_t* row_csc, const float* val_csc,
+                         int32_t m, int32_t n, float dropout_p, const float* dlogits_s, const float* dlogits_t,
+                         const lpgnn_gcn_fc_grads* grads, int phases, void* workspace, size_t workspace_bytes,
+                         lpgnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (f-3) Balanced cross-entropy of the training loop, value and gradient in one pass.  Replaces balanced()

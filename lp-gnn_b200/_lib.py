@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblpgnn.so")
 
 F32, BF16 = 0, 1
+BWD_TAIL, BWD_REST = 1, 2
 F16 = 2      # IEEE half storage (the reference's --fp16 mode): inference entry points only
 EPI_NONE, EPI_RELU = 0, 1
 COO_SORTED = 1
@@ -102,6 +103,8 @@ SIGNATURES = {
                                    _p, _p, _p, _sz, _p]),
     "lpgnn_train_backward": (_int, [C.POINTER(GcnFcWeights), _p, _p, _p, _p, _p, _p, _i32, _i32, C.c_float, _p, _p,
                                     C.POINTER(GcnFcGrads), _p, _sz, _p]),
+    "lpgnn_train_backward_ex": (_int, [C.POINTER(GcnFcWeights), _p, _p, _p, _p, _p, _p, _i32, _i32, C.c_float, _p, _p,
+                                       C.POINTER(GcnFcGrads), _int, _p, _sz, _p]),
     "lpgnn_set_gemm_cluster": (_int, [_int]),
     "lpgnn_sample_mark": (_int, [_p, _p, _p, _i32, _i32, C.c_uint64, _p, _p]),
     "lpgnn_induced_count": (_int, [_p, _p, _p, _i32, _p, _p, _p]),

@@ -267,7 +267,21 @@ extern "C" int lpgnn_train_backward(const lpgnn_gcn_fc_weights* w, const int32_t
                                     const float* val_csc, int32_t m, int32_t n, float dropout_p,
                                     const float* dlogits_s, const float* dlogits_t, const lpgnn_gcn_fc_grads* g,
                                     void* workspace, size_t workspace_bytes, lpgnn_stream_t stream) {
+  return lpgnn_train_backward_ex(w, rowptr, col, val, colptr, row_csc, val_csc, m, n, dropout_p, dlogits_s, dlogits_t, g,
+                                 LPGNN_BWD_TAIL | LPGNN_BWD_REST, workspace, workspace_bytes, stream);
+}
+
+// phases: LPGNN_BWD_TAIL = head gradients + the weight / bias gradients of the LAST hidden layer (the bulk of the
+// parameters at depth 3), LPGNN_BWD_REST = everything else (data gradients, earlier layers, input layer).  Calling TAIL
+// then REST enqueues exactly the kernels of the one-call form in the same order; a data-parallel caller starts the
+// all-reduce of the tail gradients between the two calls so that it overlaps the rest of the backward pass.
+extern "C" int lpgnn_train_backward_ex(const lpgnn_gcn_fc_weights* w, const int32_t* rowptr, const int32_t* col,
+                                       const float* val, const int32_t* colptr, const int32_t* row_csc,
+                                       const float* val_csc, int32_t m, int32_t n, float dropout_p,
+                                       const float* dlogits_s, const float* dlogits_t, const lpgnn_gcn_fc_grads* g,
+                                       int phases, void* workspace, size_t workspace_bytes, lpgnn_stream_t stream) {
   if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(phases != 0 && (phases & ~(LPGNN_BWD_TAIL | LPGNN_BWD_REST)) == 0, "train_backward: bad phases %d", phases);
   LPGNN_REQUIRE(w && g && rowptr && colptr && dlogits_s && dlogits_t && workspace && m > 0 && n > 0,
                 "train_backward: bad arguments");
   const int H = w->hids, depth = w->depth, p = w->p, q = w->q, nh = depth - 2;
@@ -284,30 +298,7 @@ extern "C" int lpgnn_train_backward(const lpgnn_gcn_fc_weights* w, const int32_t
   const float scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
   // ---- heads: dPre of the last activations (relu / dropout mask fused), head weight + bias grads
   const float last_scale = nh > 0 ? scale : 1.f;
-  // with a hidden layer under the head, dPre's column sums (that layer's bias gradients) come out of the same pass
-  LPGNN_TRY(lpgnn_head_mask_bwd_colsum(dlogits_s, B.raw_s, B.left[nh], dt, m, H, w->head_left_w, last_scale, B.dpre_s, B.draw_s,
-                                       B.drawb_s, nh > 0 ? g->r2l_b[nh - 1] : nullptr, B.scratch, B.scratch_bytes, stream));
-  LPGNN_TRY(lpgnn_head_mask_bwd_colsum(dlogits_t, B.raw_t, B.right[nh], dt, n, H, w->head_right_w, last_scale, B.dpre_t, B.draw_t,
-                                       B.drawb_t, nh > 0 ? g->l2r_b[nh - 1] : nullptr, B.scratch, B.scratch_bytes, stream));
-  for (int side = 0; side < 2; ++side) {   // head weight [3,H] and bias [3] gradients
-    const int64_t rows = side ? n : m;
-    const void* act = side ? B.right[nh] : B.left[nh];
-    float* gw = side ? g->head_right_w : g->head_left_w;
-    const int ld = bf16 ? 64 : 3;
-    if (bf16)    // tensor cores: [H,64] = act^T [draw | 0]
-      LPGNN_TRY(lpgnn_wgrad(act, side ? B.drawb_t : B.drawb_s, rows, H, 64, B.g_tmp, B.scratch, B.scratch_bytes, stream));
-    else
-      LPGNN_TRY(lpgnn_small_wgrad(act, dt, side ? B.draw_t : B.draw_s, 3, 3, rows, H, B.g_tmp, nullptr, B.scratch,
-                                  B.scratch_bytes, stream));
-    take_cols_t_kernel<<<(3 * H + 255) / 256, 256, 0, st>>>(B.g_tmp, ld, H, 3, gw);
-    LPGNN_LAUNCH_OK();
-    count_launches(1);
-    LPGNN_TRY(lpgnn_colsum(side ? B.draw_t : B.draw_s, LPGNN_F32, rows, 3, side ? g->head_right_b : g->head_left_b,
-                           B.scratch, B.scratch_bytes, stream));
-  }
-  void *dps = B.dpre_s, *dpt = B.dpre_t;
-  // ---- hidden layers, last to first
-  for (int li = nh - 1; li >= 0; --li) {
+  auto hidden_wgrads = [&](int li, const void* dps, const void* dpt) -> int {
     if (bf16) {  // MN-major tensor-core operands: dW = dPre^T X straight from the row-major activations
       LPGNN_TRY(lpgnn_wgrad(dpt, B.agg_t[li], n, H, H, g->l2r_wrel[li], B.scratch, B.scratch_bytes, stream));
       LPGNN_TRY(lpgnn_wgrad(dpt, B.right[li], n, H, H, g->l2r_wroot[li], B.scratch, B.scratch_bytes, stream));
@@ -333,6 +324,37 @@ extern "C" int lpgnn_train_backward(const lpgnn_gcn_fc_weights* w, const int32_t
       LPGNN_TRY(lpgnn_colsum(dpt, dt, n, H, g->l2r_b[li], B.scratch, B.scratch_bytes, stream));
       LPGNN_TRY(lpgnn_colsum(dps, dt, m, H, g->r2l_b[li], B.scratch, B.scratch_bytes, stream));
     }
+    return LPGNN_OK;
+  };
+  if (phases & LPGNN_BWD_TAIL) {
+  // with a hidden layer under the head, dPre's column sums (that layer's bias gradients) come out of the same pass
+  LPGNN_TRY(lpgnn_head_mask_bwd_colsum(dlogits_s, B.raw_s, B.left[nh], dt, m, H, w->head_left_w, last_scale, B.dpre_s, B.draw_s,
+                                       B.drawb_s, nh > 0 ? g->r2l_b[nh - 1] : nullptr, B.scratch, B.scratch_bytes, stream));
+  LPGNN_TRY(lpgnn_head_mask_bwd_colsum(dlogits_t, B.raw_t, B.right[nh], dt, n, H, w->head_right_w, last_scale, B.dpre_t, B.draw_t,
+                                       B.drawb_t, nh > 0 ? g->l2r_b[nh - 1] : nullptr, B.scratch, B.scratch_bytes, stream));
+  for (int side = 0; side < 2; ++side) {   // head weight [3,H] and bias [3] gradients
+    const int64_t rows = side ? n : m;
+    const void* act = side ? B.right[nh] : B.left[nh];
+    float* gw = side ? g->head_right_w : g->head_left_w;
+    const int ld = bf16 ? 64 : 3;
+    if (bf16)    // tensor cores: [H,64] = act^T [draw | 0]
+      LPGNN_TRY(lpgnn_wgrad(act, side ? B.drawb_t : B.drawb_s, rows, H, 64, B.g_tmp, B.scratch, B.scratch_bytes, stream));
+    else
+      LPGNN_TRY(lpgnn_small_wgrad(act, dt, side ? B.draw_t : B.draw_s, 3, 3, rows, H, B.g_tmp, nullptr, B.scratch,
+                                  B.scratch_bytes, stream));
+    take_cols_t_kernel<<<(3 * H + 255) / 256, 256, 0, st>>>(B.g_tmp, ld, H, 3, gw);
+    LPGNN_LAUNCH_OK();
+    count_launches(1);
+    LPGNN_TRY(lpgnn_colsum(side ? B.draw_t : B.draw_s, LPGNN_F32, rows, 3, side ? g->head_right_b : g->head_left_b,
+                           B.scratch, B.scratch_bytes, stream));
+  }
+  if (nh > 0) LPGNN_TRY(hidden_wgrads(nh - 1, B.dpre_s, B.dpre_t));
+  }   // LPGNN_BWD_TAIL
+  if (!(phases & LPGNN_BWD_REST)) return LPGNN_OK;
+  void *dps = B.dpre_s, *dpt = B.dpre_t;
+  // ---- hidden layers, last to first
+  for (int li = nh - 1; li >= 0; --li) {
+    if (li < nh - 1) LPGNN_TRY(hidden_wgrads(li, dps, dpt));
     // data gradients.  dL = A (dPre_t W_rel^{l2r}) + dPre_s W_root^{r2l} = [A dPre_t | dPre_s] [W_rel^{l2r} ; W_root^{r2l}]:
     // aggregate first, then ONE two-operand transform per side (transposed weights prepared by the forward call)
     // whose epilogue applies the ReLU / dropout mask of the layer input.

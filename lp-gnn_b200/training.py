@@ -234,14 +234,62 @@ class _NativeTrainFunction(torch.autograd.Function):
         for k, nm in enumerate(("head_left_w", "head_left_b", "head_right_w", "head_right_b")):
             setattr(g, nm, grads[6 + 6 * nh + k].data_ptr())
         ws = ctx.ws
-        with torch.cuda.device(dev):
-            rc = lib.lpgnn_train_backward(C.byref(w), csr[0].data_ptr(), csr[1].data_ptr(), csr[2].data_ptr(),
-                                          csc[0].data_ptr(), csc[1].data_ptr(), csc[2].data_ptr(), m, n, ctx.dp,
-                                          d_logit_s.data_ptr(), d_logit_t.data_ptr(), C.byref(g), ws.data_ptr(),
-                                          ws.numel(), _lib.stream_ptr())
-        _lib.check(rc, "lpgnn_train_backward")
+
+        def run(phases):
+            with torch.cuda.device(dev):
+                rc = lib.lpgnn_train_backward_ex(C.byref(w), csr[0].data_ptr(), csr[1].data_ptr(), csr[2].data_ptr(),
+                                                 csc[0].data_ptr(), csc[1].data_ptr(), csc[2].data_ptr(), m, n, ctx.dp,
+                                                 d_logit_s.data_ptr(), d_logit_t.data_ptr(), C.byref(g), phases,
+                                                 ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+            _lib.check(rc, "lpgnn_train_backward")
+
+        sync = _gradient_sync[0]
+        if sync is None:
+            run(_lib.BWD_TAIL | _lib.BWD_REST)
+        else:
+            # data parallel: the head + last-hidden-layer gradients (the tail of the flat buffer, ~all of the parameters at
+            # depth 3) are reduced while the rest of the backward pass runs; the small remainder follows
+            cut = offs[6 + 6 * (nh - 1)] if nh > 0 else offs[6]
+            run(_lib.BWD_TAIL)
+            h1 = sync(flat[cut:])
+            run(_lib.BWD_REST)
+            h0 = sync(flat[:cut])
+            for h in (h1, h0):
+                if h is not None:
+                    h.wait()
+            if _gradient_sync[1] != 1.0:
+                flat.mul_(_gradient_sync[1])
+            _gradient_sync[2] = 1
         ctx.ws = None
         return (None, None, None, None, None, *grads)
+
+
+# [reduce(flat_slice) -> handle with .wait() | None, scale applied to the whole buffer afterwards, #backward passes synced]
+_gradient_sync = [None, 1.0, 0]
+
+
+def set_gradient_sync(reduce_fn=None, scale=1.0):
+    """Data-parallel hook of the native training step: ``reduce_fn(flat_slice)`` is called on the tail of the flat
+    gradient buffer right after it is complete and on the head at the end (it starts an in-place SUM all-reduce and
+    returns a handle with ``.wait()``, or None), then the buffer is multiplied by ``scale`` (1 / world).  ``None``
+    restores the one-call backward.  `train.allreduce_gradients` skips gradients that were reduced here."""
+    _gradient_sync[0], _gradient_sync[1] = reduce_fn, float(scale)
+
+
+def enable_overlapped_allreduce(world):
+    """Mean over ranks with the all-reduce of the tail gradients overlapped with the rest of the backward pass
+    (torch.distributed, async_op: NCCL runs it on its own stream behind the kernels enqueued so far)."""
+    if world <= 1:
+        return set_gradient_sync(None)
+    import torch.distributed as dist
+    set_gradient_sync(lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True), 1.0 / world)
+
+
+def consume_synced_backward() -> bool:
+    """True once per backward pass whose gradients were already reduced by the hook above."""
+    done = _gradient_sync[2] > 0
+    _gradient_sync[2] = 0
+    return done
 
 
 def _train_weights(model, params):

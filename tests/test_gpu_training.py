@@ -116,6 +116,47 @@ def test_native_step_equals_op_by_op_step(cuda, precision, name, dp):
         assert torch.equal(a, b), (k, (a - b).abs().max().item())
 
 
+@pytest.mark.parametrize("precision,name", [("fp32", "small_300x600"), ("bf16", "c1_1000x2000")])
+def test_two_phase_backward_with_gradient_sync_hook(cuda, precision, name):
+    """Data-parallel form of the native backward (TAIL, hook, REST, hook): same bits as the one-call form; the hook sees
+    the tail of the flat gradient buffer (last hidden layer + head) first, then the head of it, and the scale is applied."""
+    from lpgnn_b200 import training
+    from lpgnn_b200.losses import balanced
+    from lpgnn_b200.train import allreduce_gradients
+    res, seen = [], []
+
+    class _H:
+        def wait(self):
+            seen.append("wait")
+
+    def hook(t):
+        seen.append((t.data_ptr(), t.numel()))
+        return _H()
+
+    for sync in (False, True):
+        model, batch, y_s, y_t, _ = _golden_setup(name, cuda, precision)
+        model.train()
+        model.dp = 0.1
+        training._step_counter[0] = 7
+        training.set_gradient_sync(hook if sync else None, 0.5)
+        try:
+            lc, lv = model(batch)
+            balanced(lc, lv, y_s, y_t).backward()
+        finally:
+            training.set_gradient_sync(None)
+        res.append([p.grad.clone() for p in model.parameters()])
+    params = list(model.parameters())
+    for (k, _), a, b in zip(model.named_parameters(), res[0], res[1]):
+        assert torch.equal(a * 0.5, b), k
+    n_tail = sum(p.numel() for p in params[-(10 if len(params) > 10 else 4):])   # last hidden layer (6 tensors) + head (4)
+    (p1, c1), (p0, c0) = seen[0], seen[1]
+    assert seen[2:] == ["wait", "wait"]
+    assert c1 >= n_tail and c1 < n_tail + 4 * 10 and p0 + 4 * c0 == p1      # tail first; the two slices tile the buffer
+    # the training loop's all-reduce skips a backward pass that was reduced by the hook (flag consumed once)
+    assert training.consume_synced_backward() and not training.consume_synced_backward()
+    allreduce_gradients(params, 1)
+
+
 def test_native_step_rejects_second_backward(cuda):
     from lpgnn_b200.losses import balanced
     model, batch, y_s, y_t, _ = _golden_setup("small_300x600", cuda, "fp32")
