@@ -371,14 +371,15 @@ LPGNN_API int lpgnn_wgrad(const void* dY, const void* X, int64_t Mn, int32_t N_o
 LPGNN_API int lpgnn_head_mask_bwd(const float* dlogits, const float* raw, const void* Hact, int h_dtype,
                         int32_t rows, int32_t Hdim, const float* W, float scale, void* dH, float* draw,
                         void* draw_bf16, lpgnn_stream_t stream);
-/* Same, and colsum_out[Hdim] (f32) = column sums of dH accumulated in fp32 before the output rounding: the bias gradient
- * of the layer under the head (db = colsum(dPre), PyG GraphConv.lin_rel.bias) without a pass that reads dH back.
+/* Same, and colsum_out[Hdim] (f32, optional) = column sums of dH accumulated in fp32 before the output rounding: the bias
+ * gradient of the layer under the head (db = colsum(dPre), PyG GraphConv.lin_rel.bias) without a pass that reads dH back;
+ * draw_colsum_out[3] (f32, optional) = column sums of draw: the head's own bias gradient (nn.Linear(H,3).bias).
  * Per-block partial sums in `workspace`, combined in a fixed order: deterministic. */
 LPGNN_API size_t lpgnn_head_mask_bwd_colsum_workspace_bytes(int32_t rows, int32_t Hdim);
 LPGNN_API int lpgnn_head_mask_bwd_colsum(const float* dlogits, const float* raw, const void* Hact, int h_dtype,
                                int32_t rows, int32_t Hdim, const float* W, float scale, void* dH, float* draw,
-                               void* draw_bf16, float* colsum_out, void* workspace, size_t workspace_bytes,
-                               lpgnn_stream_t stream);
+                               void* draw_bf16, float* colsum_out, float* draw_colsum_out, void* workspace,
+                               size_t workspace_bytes, lpgnn_stream_t stream);
 
 /* out = (a [+ b]) * scale * (act > 0), elementwise; b may be NULL; out may alias a.  Backward of
  * relu_ (reference arch.py:182,188) and of dropout followed by relu_ (arch.py:186-188: `act` is the

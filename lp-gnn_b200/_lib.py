@@ -90,7 +90,7 @@ SIGNATURES = {
     "lpgnn_wgrad": (_int, [_p, _p, _i64, _i32, _i32, _p, _p, _sz, _p]),
     "lpgnn_head_mask_bwd": (_int, [_p, _p, _p, _int, _i32, _i32, _p, C.c_float, _p, _p, _p, _p]),
     "lpgnn_head_mask_bwd_colsum_workspace_bytes": (_sz, [_i32, _i32]),
-    "lpgnn_head_mask_bwd_colsum": (_int, [_p, _p, _p, _int, _i32, _i32, _p, C.c_float, _p, _p, _p, _p, _p, _sz, _p]),
+    "lpgnn_head_mask_bwd_colsum": (_int, [_p, _p, _p, _int, _i32, _i32, _p, C.c_float, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "lpgnn_relu_bwd": (_int, [_p, _p, _p, _i64, _int, C.c_float, _p, _p]),
     "lpgnn_dropout": (_int, [_p, _i64, _int, C.c_float, C.c_uint64, _p]),
     "lpgnn_transpose": (_int, [_p, _int, _i64, _i64, _p, _i64, _p]),

@@ -202,7 +202,8 @@ small_wgrad_reduce_kernel(const float* __restrict__ partial, int nchunks, int N,
 // pure stream (read Hact once, write dH once) and needs that memory parallelism to approach the HBM roofline.
 // CS: per-block partial column sums of dH (fp32, before the output rounding) -- the bias gradient of the layer under
 // the head -- without a pass that reads dH back; a column belongs to one thread of the block, rows are visited in
-// a fixed order: deterministic (cs_partials [gridDim.x][Hdim], combined by colsum_finish_kernel).
+// a fixed order: deterministic (cs_partials [gridDim.x][Hdim + 4], combined by colsum_finish_kernel); columns
+// Hdim .. Hdim+2 of a partial row carry the block's column sums of draw (the head's bias gradient).
 template <typename T, int R, bool CS>
 __global__ void __launch_bounds__(256)
 head_mask_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ raw, const T* __restrict__ Hact,
@@ -215,6 +216,7 @@ head_mask_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict_
   const int ch = warp * 32 + lane;
   const bool live = ch < chunks;
   float w[3][E], cs[E];
+  float ds0 = 0.f, ds1 = 0.f, ds2 = 0.f;      // lane i < R: sums of draw over rows r0 + i of this block's groups
 #pragma unroll
   for (int k = 0; k < E; ++k) {
     cs[k] = 0.f;
@@ -243,6 +245,7 @@ head_mask_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict_
         d0 = 1e13f * g0; d1 = 1e13f * g1; d2 = 1e13f * g2;
       }
       if (warp == 0 && draw_out) { draw_out[myrow * 3] = d0; draw_out[myrow * 3 + 1] = d1; draw_out[myrow * 3 + 2] = d2; }
+      if constexpr (CS) { ds0 += d0; ds1 += d1; ds2 += d2; }
     }
     if (warp == 0 && draw_bf16) {   // [d0 d1 d2 0 ... 0] as one 128-byte row: the MN-major operand of the head's weight gradient
 #pragma unroll
@@ -274,29 +277,40 @@ head_mask_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict_
     }
   }
   if constexpr (CS) {
+    float* prow = cs_partials + (int64_t)blockIdx.x * (Hdim + 4);
     if (live) {
 #pragma unroll
-      for (int k = 0; k < E; ++k) cs_partials[(int64_t)blockIdx.x * Hdim + ch * E + k] = cs[k];
+      for (int k = 0; k < E; ++k) prow[ch * E + k] = cs[k];
+    }
+    if (warp == 0) {                          // lanes >= R hold zeros: a fixed-shape butterfly, deterministic
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ds0 += __shfl_xor_sync(0xffffffffu, ds0, o); ds1 += __shfl_xor_sync(0xffffffffu, ds1, o); ds2 += __shfl_xor_sync(0xffffffffu, ds2, o);
+      }
+      if (lane == 0) { prow[Hdim] = ds0; prow[Hdim + 1] = ds1; prow[Hdim + 2] = ds2; prow[Hdim + 3] = 0.f; }
     }
   }
 }
 
-// out[j] = sum over the partial rows, in a fixed order: block = 32 columns x 8 row strides, then 8 -> 1 in shared memory
-__global__ void __launch_bounds__(256)
-colsum_finish_kernel(const float* __restrict__ partials, int nrows, int N, float* __restrict__ out) {
-  __shared__ float red[8][33];
+// Column sums of the [nrows][ld] partials in a fixed order: block = 32 columns x 32 row strides, then 32 -> 1 in shared
+// memory.  Columns < N0 go to out0 (if given), columns N0 .. N0+2 to out1 (if given).
+__global__ void __launch_bounds__(1024)
+colsum_finish_kernel(const float* __restrict__ partials, int nrows, int ld, int N0, float* __restrict__ out0,
+                     float* __restrict__ out1) {
+  __shared__ float red[32][33];
   const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + c;
   float acc = 0.f;
-  if (j < N)
-    for (int i = r; i < nrows; i += 8) acc += partials[(int64_t)i * N + j];
+  if (j < N0 + 3)
+    for (int i = r; i < nrows; i += 32) acc += partials[(int64_t)i * ld + j];
   red[r][c] = acc;
   __syncthreads();
-  if (r == 0 && j < N) {
+  if (r == 0 && j < N0 + 3) {
     float s = red[0][c];
 #pragma unroll
-    for (int i = 1; i < 8; ++i) s += red[i][c];
-    out[j] = s;
+    for (int i = 1; i < 32; ++i) s += red[i][c];
+    if (j < N0) { if (out0) out0[j] = s; }
+    else if (out1) out1[j - N0] = s;
   }
 }
 
@@ -476,19 +490,20 @@ static int head_bwd_dispatch(const float* dlogits, const float* raw, const void*
 }
 
 extern "C" size_t lpgnn_head_mask_bwd_colsum_workspace_bytes(int32_t rows, int32_t Hdim) {
-  return (size_t)head_bwd_grid(rows > 0 ? rows : 1) * (size_t)Hdim * sizeof(float) + 256;
+  return (size_t)head_bwd_grid(rows > 0 ? rows : 1) * (size_t)(Hdim + 4) * sizeof(float) + 256;
 }
 
 extern "C" int lpgnn_head_mask_bwd_colsum(const float* dlogits, const float* raw, const void* Hact, int h_dtype, int32_t rows,
                                           int32_t Hdim, const float* W, float scale, void* dH, float* draw,
-                                          void* draw_bf16, float* colsum_out, void* workspace, size_t workspace_bytes,
-                                          lpgnn_stream_t stream) {
+                                          void* draw_bf16, float* colsum_out, float* draw_colsum_out, void* workspace,
+                                          size_t workspace_bytes, lpgnn_stream_t stream) {
   if (int rc = check_device()) return rc;
   LPGNN_DT_OK(h_dtype, "head_mask_bwd");
   LPGNN_REQUIRE(rows >= 0 && Hdim > 0, "head_mask_bwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   if (rows == 0) {
     if (colsum_out) LPGNN_CUDA_OK(cudaMemsetAsync(colsum_out, 0, sizeof(float) * (size_t)Hdim, st));
+    if (draw_colsum_out) LPGNN_CUDA_OK(cudaMemsetAsync(draw_colsum_out, 0, sizeof(float) * 3, st));
     return LPGNN_OK;
   }
   LPGNN_REQUIRE(dlogits && raw && Hact && W && dH, "head_mask_bwd: null pointer");
@@ -498,7 +513,7 @@ extern "C" int lpgnn_head_mask_bwd_colsum(const float* dlogits, const float* raw
   LPGNN_REQUIRE(ch <= 8, "head_mask_bwd: Hdim=%d too wide (max 4096 bytes per row)", Hdim);
   LPGNN_REQUIRE((uintptr_t)Hact % 16 == 0 && (uintptr_t)dH % 16 == 0, "head_mask_bwd: Hact / dH must be 16-byte aligned");
   float* partials = nullptr;
-  if (colsum_out) {
+  if (colsum_out || draw_colsum_out) {
     if (!workspace || workspace_bytes < lpgnn_head_mask_bwd_colsum_workspace_bytes(rows, Hdim)) {
       set_error("head_mask_bwd_colsum: workspace too small");
       return LPGNN_EWORKSPACE;
@@ -508,8 +523,11 @@ extern "C" int lpgnn_head_mask_bwd_colsum(const float* dlogits, const float* raw
   int rc = h_dtype == LPGNN_F32
                ? head_bwd_dispatch<float>(dlogits, raw, Hact, rows, Hdim, W, scale, dH, draw, draw_bf16, ch, partials, st)
                : head_bwd_dispatch<__nv_bfloat16>(dlogits, raw, Hact, rows, Hdim, W, scale, dH, draw, draw_bf16, ch, partials, st);
-  if (rc || !colsum_out) return rc;
-  colsum_finish_kernel<<<ceil_div(Hdim, 32), 256, 0, st>>>(partials, head_bwd_grid(rows), Hdim, colsum_out);
+  if (rc || !partials) return rc;
+  const int first = colsum_out ? 0 : Hdim / 32;     // only the draw columns when the dH sums are not wanted
+  colsum_finish_kernel<<<ceil_div(Hdim + 3, 32) - first, 1024, 0, st>>>(partials + first * 32, head_bwd_grid(rows), Hdim + 4,
+                                                                         Hdim - first * 32, colsum_out ? colsum_out : nullptr,
+                                                                         draw_colsum_out);
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;
@@ -518,6 +536,6 @@ extern "C" int lpgnn_head_mask_bwd_colsum(const float* dlogits, const float* raw
 extern "C" int lpgnn_head_mask_bwd(const float* dlogits, const float* raw, const void* Hact, int h_dtype, int32_t rows,
                                    int32_t Hdim, const float* W, float scale, void* dH, float* draw,
                                    void* draw_bf16, lpgnn_stream_t stream) {
-  return lpgnn_head_mask_bwd_colsum(dlogits, raw, Hact, h_dtype, rows, Hdim, W, scale, dH, draw, draw_bf16, nullptr, nullptr, 0,
-                                    stream);
+  return lpgnn_head_mask_bwd_colsum(dlogits, raw, Hact, h_dtype, rows, Hdim, W, scale, dH, draw, draw_bf16, nullptr, nullptr,
+                                    nullptr, 0, stream);
 }

@@ -328,10 +328,13 @@ extern "C" int lpgnn_train_backward_ex(const lpgnn_gcn_fc_weights* w, const int3
   };
   if (phases & LPGNN_BWD_TAIL) {
   // with a hidden layer under the head, dPre's column sums (that layer's bias gradients) come out of the same pass
+  // (and the column sums of draw: the heads' own bias gradients)
   LPGNN_TRY(lpgnn_head_mask_bwd_colsum(dlogits_s, B.raw_s, B.left[nh], dt, m, H, w->head_left_w, last_scale, B.dpre_s, B.draw_s,
-                                       B.drawb_s, nh > 0 ? g->r2l_b[nh - 1] : nullptr, B.scratch, B.scratch_bytes, stream));
+                                       B.drawb_s, nh > 0 ? g->r2l_b[nh - 1] : nullptr, g->head_left_b, B.scratch,
+                                       B.scratch_bytes, stream));
   LPGNN_TRY(lpgnn_head_mask_bwd_colsum(dlogits_t, B.raw_t, B.right[nh], dt, n, H, w->head_right_w, last_scale, B.dpre_t, B.draw_t,
-                                       B.drawb_t, nh > 0 ? g->l2r_b[nh - 1] : nullptr, B.scratch, B.scratch_bytes, stream));
+                                       B.drawb_t, nh > 0 ? g->l2r_b[nh - 1] : nullptr, g->head_right_b, B.scratch,
+                                       B.scratch_bytes, stream));
   for (int side = 0; side < 2; ++side) {   // head weight [3,H] and bias [3] gradients
     const int64_t rows = side ? n : m;
     const void* act = side ? B.right[nh] : B.left[nh];
@@ -345,8 +348,6 @@ extern "C" int lpgnn_train_backward_ex(const lpgnn_gcn_fc_weights* w, const int3
     take_cols_t_kernel<<<(3 * H + 255) / 256, 256, 0, st>>>(B.g_tmp, ld, H, 3, gw);
     LPGNN_LAUNCH_OK();
     count_launches(1);
-    LPGNN_TRY(lpgnn_colsum(side ? B.draw_t : B.draw_s, LPGNN_F32, rows, 3, side ? g->head_right_b : g->head_left_b,
-                           B.scratch, B.scratch_bytes, stream));
   }
   if (nh > 0) LPGNN_TRY(hidden_wgrads(nh - 1, B.dpre_s, B.dpre_t));
   }   // LPGNN_BWD_TAIL

@@ -269,10 +269,11 @@ def wgrad(dy, x):
     return out
 
 
-def head_mask_bwd(dlogits, raw, h_act, w, scale=1.0, want_bf16=False, want_colsum=False):
+def head_mask_bwd(dlogits, raw, h_act, w, scale=1.0, want_bf16=False, want_colsum=False, want_bias_grad=False):
     """Backward of ``head_mask`` wrt the hidden activation, fused with its ReLU/dropout mask.
     Returns ``(dH[rows,H], draw[rows,3])`` [+ ``draw_bf16 [rows,64] = [draw | 0]``, the ``wgrad`` operand]
-    [+ ``colsum(dH) [H]`` accumulated in fp32 before the output rounding: the bias gradient of the layer under the head]."""
+    [+ ``colsum(dH) [H]`` accumulated in fp32 before the output rounding: the bias gradient of the layer under the head]
+    [+ ``colsum(draw) [3]``: the head's own bias gradient]."""
     require_cuda(dlogits, raw, h_act, w)
     dlogits, raw, h_act, w = _contig(dlogits.float()), _contig(raw), _contig(h_act), _contig(w.float())
     rows, H = h_act.shape
@@ -280,22 +281,25 @@ def head_mask_bwd(dlogits, raw, h_act, w, scale=1.0, want_bf16=False, want_colsu
     dH = torch.empty_like(h_act)
     draw = torch.empty((rows, 3), dtype=torch.float32, device=h_act.device)
     draw_b = torch.empty((rows, 64), dtype=torch.bfloat16, device=h_act.device) if want_bf16 else None
-    cs = ws = None
+    cs = db = ws = None
     ws_bytes = 0
-    if want_colsum:
-        cs = torch.empty(H, dtype=torch.float32, device=h_act.device)
+    if want_colsum or want_bias_grad:
+        cs = torch.empty(H, dtype=torch.float32, device=h_act.device) if want_colsum else None
+        db = torch.empty(3, dtype=torch.float32, device=h_act.device) if want_bias_grad else None
         ws_bytes = lib.lpgnn_head_mask_bwd_colsum_workspace_bytes(rows, H)
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=h_act.device)
     with torch.cuda.device(h_act.device):
         rc = lib.lpgnn_head_mask_bwd_colsum(dlogits.data_ptr(), raw.data_ptr(), h_act.data_ptr(), dtype_code(h_act.dtype),
                                             rows, H, w.data_ptr(), float(scale), dH.data_ptr(), draw.data_ptr(),
-                                            _lib.ptr(draw_b), _lib.ptr(cs), _lib.ptr(ws), ws_bytes, stream_ptr())
+                                            _lib.ptr(draw_b), _lib.ptr(cs), _lib.ptr(db), _lib.ptr(ws), ws_bytes, stream_ptr())
     check(rc, "lpgnn_head_mask_bwd_colsum")
     out = (dH, draw)
     if want_bf16:
         out += (draw_b,)
     if want_colsum:
         out += (cs,)
+    if want_bias_grad:
+        out += (db,)
     return out
 
 

@@ -111,19 +111,18 @@ class _GCNFCFunction(torch.autograd.Function):
         fuse_cs = n_layers > 0                              # bias gradients of the layer under the head from the same pass
         tc_small = z_s.dtype == torch.bfloat16              # bf16 mode: narrow weight gradients on the tensor cores too
         if tc_small:
-            d_pre_s, draw_s, drawb_s, *cs_s = ops.head_mask_bwd(d_logit_s.contiguous(), raw_s, left, P[hbase], last_scale, want_bf16=True, want_colsum=fuse_cs)
-            d_pre_t, draw_t, drawb_t, *cs_t = ops.head_mask_bwd(d_logit_t.contiguous(), raw_t, right, P[hbase + 2], last_scale, want_bf16=True, want_colsum=fuse_cs)
+            d_pre_s, draw_s, drawb_s, *cs_s = ops.head_mask_bwd(d_logit_s.contiguous(), raw_s, left, P[hbase], last_scale, want_bf16=True, want_colsum=fuse_cs, want_bias_grad=True)
+            d_pre_t, draw_t, drawb_t, *cs_t = ops.head_mask_bwd(d_logit_t.contiguous(), raw_t, right, P[hbase + 2], last_scale, want_bf16=True, want_colsum=fuse_cs, want_bias_grad=True)
             grads[hbase] = ops.wgrad(left, drawb_s)[:, :3].t().contiguous()       # [H,64] = left^T [draw | 0]
             grads[hbase + 2] = ops.wgrad(right, drawb_t)[:, :3].t().contiguous()
         else:
-            d_pre_s, draw_s, *cs_s = ops.head_mask_bwd(d_logit_s.contiguous(), raw_s, left, P[hbase], last_scale, want_colsum=fuse_cs)
-            d_pre_t, draw_t, *cs_t = ops.head_mask_bwd(d_logit_t.contiguous(), raw_t, right, P[hbase + 2], last_scale, want_colsum=fuse_cs)
+            d_pre_s, draw_s, *cs_s = ops.head_mask_bwd(d_logit_s.contiguous(), raw_s, left, P[hbase], last_scale, want_colsum=fuse_cs, want_bias_grad=True)
+            d_pre_t, draw_t, *cs_t = ops.head_mask_bwd(d_logit_t.contiguous(), raw_t, right, P[hbase + 2], last_scale, want_colsum=fuse_cs, want_bias_grad=True)
             gw, _ = ops.small_wgrad(left, draw_s, 3)            # [H,3] = left^T draw
             grads[hbase] = gw.t().contiguous()
             gw, _ = ops.small_wgrad(right, draw_t, 3)
             grads[hbase + 2] = gw.t().contiguous()
-        grads[hbase + 1] = ops.colsum(draw_s)
-        grads[hbase + 3] = ops.colsum(draw_t)
+        grads[hbase + 1], grads[hbase + 3] = cs_s.pop(), cs_t.pop()      # colsum(draw): same pass as head_mask_bwd
         # ---- hidden layers, last to first
         for i in reversed(range(n_layers)):
             w = P[6 + 6 * i: 12 + 6 * i]

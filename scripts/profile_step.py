@@ -1,6 +1,7 @@
 """Exactly one C2 bf16 prediction step (lpgnn_predict_basis: graph build + GCN_FC forward + basis selection) inside a
 cudaProfilerStart/Stop window, after warm-up -- the target of the ncu captures under profiles/ (run ncu with
---profile-from-start off).  `train` as first argument profiles one training step (forward + loss + backward) instead."""
+--profile-from-start off).  `train` as first argument profiles one training step (forward + loss + backward) instead; the optional second argument is
+the precision (bf16 | fp16)."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,12 +10,13 @@ from lpgnn_b200 import arch, synth
 from lpgnn_b200.pipeline import pack_lp, unpack_device
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "predict"
+precision = sys.argv[2] if len(sys.argv) > 2 else "bf16"       # bf16 | fp16 (prediction only)
 dev = torch.device("cuda:0")
 cfg = synth.CONFIGS["C2"]
 lp = synth.processed_lp(cfg["m"], cfg["n"], cfg["nnz"], seed=cfg["seed"], structure="staircase")
 torch.manual_seed(0)
 model = arch.GCN_FC(8, 8, hids=cfg["hids"], depth=cfg["depth"]).to(dev)
-model.set_precision("bf16")
+model.set_precision(precision)
 host_lp = pack_lp(lp.row, lp.col, lp.a_data, lp.c_feas, lp.v_feas, is_sorted=True)
 d_row, d_col, d_val, d_xs, d_xt = (t.clone() for t in unpack_device(host_lp.pack.to(dev), host_lp))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

@@ -356,6 +356,12 @@ def test_head_mask_bwd_fused_column_sums(cuda, dtype, H, rows):
     assert float((cs.double() - exp).abs().max()) < 1e-4 * max(1.0, float(exact.abs().sum(0).max()))
     _, _, cs2 = ops.head_mask_bwd(dl, raw, h, w, scale=1.25, want_colsum=True)
     assert torch.equal(cs, cs2)
+    # the head's own bias gradient colsum(draw) from the same pass, with or without the dH sums
+    dH3, draw3, cs3, db3 = ops.head_mask_bwd(dl, raw, h, w, scale=1.25, want_colsum=True, want_bias_grad=True)
+    _, _, db4 = ops.head_mask_bwd(dl, raw, h, w, scale=1.25, want_bias_grad=True)
+    assert torch.equal(dH3, dH) and torch.equal(cs3, cs) and torch.equal(db3, db4) and db3.shape == (3,)
+    expd = draw.double().sum(0)
+    assert float((db3.double() - expd).abs().max()) < 1e-5 * max(1.0, float(draw.double().abs().sum(0).max()))
     # canary: the partial-sum workspace is the only scratch; the [H] output has no neighbours overwritten
     assert cs.shape == (H,) and torch.isfinite(cs).all()
 
