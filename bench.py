@@ -292,10 +292,12 @@ def run_gpu(args):
         st32 = model.predict_basis_coo(d_row, d_col, d_val, m, n, d_xs, d_xt, is_sorted=True)
         model.set_precision(args.precision)
         out["status_agreement_vs_fp32"] = float((st32 == status).float().mean().item())
-        if world == 1 and args.precision == "bf16":
-            # the other 16-bit storage format (IEEE half = the reference's --fp16 switch) on the same kernels, same
-            # protocol: the mode that meets the 99.9 % status-agreement bar; slower only through the power cap
-            model.set_precision("fp16")
+        if world == 1:
+            # the other 16-bit storage format on the same kernels, same protocol.  fp16 = IEEE half, the reference's own
+            # --fp16 switch (val.py:269): the mode that meets the 99.9 % status-agreement bar; bf16 = the format named in
+            # BASELINE.json's north star.  Same tensor-core rate; half data draws a little more power under the cap.
+            other = "bf16" if args.precision == "fp16" else "fp16"
+            model.set_precision(other)
             for _ in range(3):
                 st16 = step_resident()
             torch.cuda.synchronize()
@@ -311,10 +313,10 @@ def run_gpu(args):
                     torch.cuda.current_stream().wait_stream(st)
             a1.record()
             torch.cuda.synchronize()
-            out["fp16"] = {"value": args.steps / (a0.elapsed_time(a1) / 1e3), "unit": "LPs/s",
-                           "ms_per_step": a0.elapsed_time(a1) / args.steps,
-                           "status_agreement_vs_fp32": float((st32 == st16).float().mean().item()),
-                           "note": "same workload and timed region as `value`, precision='fp16' (HBM-resident arm)"}
+            out[other] = {"value": args.steps / (a0.elapsed_time(a1) / 1e3), "unit": "LPs/s",
+                          "ms_per_step": a0.elapsed_time(a1) / args.steps,
+                          "status_agreement_vs_fp32": float((st32 == st16).float().mean().item()),
+                          "note": f"same workload and timed region as `value`, precision='{other}' (HBM-resident arm)"}
             model.set_precision(args.precision)
 
     if not args.no_train:
@@ -546,8 +548,10 @@ def kernel_rooflines(model, lp, dev, peaks, bf16, args):
     t_b2 = time_kernel(lambda: BipartiteCSR.from_coo(h_row, h_col, h_val, m, n, is_sorted=False), reps, flush)
     add("graph_build (unsorted COO->CSR+CSC)", "hbm", t_b2, z * 12 * 2 * 3, -1)
     # measured DRAM traffic per launch from the committed ncu --set full capture (same workload / precision only)
-    tpath = os.path.join(ROOT, "profiles", "r01d_traffic.json")
-    if os.path.isfile(tpath):
+    for tname in ("r01d_traffic.json", "r01e_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if not os.path.isfile(tpath):
+            continue
         tj = json.load(open(tpath))
         if tj.get("workload") == args.workload and tj.get("precision") == args.precision and args.structure == "staircase":
             for k in kernels:
@@ -686,7 +690,10 @@ def main():
     ap.add_argument("--sweep-distinct", type=int, default=96, help="C5: distinct LPs materialised (cycled)")
     ap.add_argument("--sweep-hids", type=int, default=1024)
     ap.add_argument("--sweep-pack", type=int, default=1, help="C5 e2e arm: pack LPs block-diagonally (1) or one call per LP (0)")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32", "fp32_tc"])
+    # fp16 (IEEE half storage, fp32 accumulate) is the 16-bit mode that passes every parity gate of the north star
+    # (>= 99.9 % status agreement); bf16 runs the same kernels at the same rate and is reported beside it
+    # (default: fp16; C4 is named "bf16 full-graph inference" in BASELINE.json and defaults to bf16)
+    ap.add_argument("--precision", default=None, choices=["bf16", "fp16", "fp32", "fp32_tc"])
     ap.add_argument("--structure", default="staircase", choices=["staircase", "uniform"])
     ap.add_argument("--inflight", type=int, default=3, help="LPs in flight on alternating streams (both arms)")
     ap.add_argument("--kernel-reps", type=int, default=10)
@@ -695,6 +702,8 @@ def main():
     ap.add_argument("--no-kernels", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
+    if args.precision is None:
+        args.precision = "bf16" if args.workload == "C4" else "fp16"
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 3
         args.warmup = args.warmup if args.warmup is not None else 1
