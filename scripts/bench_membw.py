@@ -13,4 +13,4 @@ for mb in (205, 1024, 4096):
     x = torch.empty(n, dtype=torch.bfloat16, device=dev); y = torch.empty_like(x)
     t = timeit(lambda: x.zero_());      print(f"{mb} MB fill : {t*1e3:8.1f} us  {mb*1.048576/t:8.1f} GB/s")
     t = timeit(lambda: y.copy_(x));     print(f"{mb} MB copy : {t*1e3:8.1f} us  {2*mb*1.048576/t:8.1f} GB/s (read+write)")
-    t = timeit(lambda: x.view(torch.int16).max()); print(f"{mb} MB read : {t*1e3:8.1f} us  {mb*1.048576/t:8.1f} GB/s")
+    t = timeit(lambda: x.view(torch.int16).max()); print(f"{mb} MB read (torch max)  : {t*1e3:8.1f} us  {mb*1.048576/t:8.1f} GB/s")
