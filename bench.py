@@ -655,11 +655,15 @@ def run_reference(args):
     port, model, _ = _port_setup(cfg, lp)
     for _ in range(max(1, min(args.warmup, 3))):
         cpu_step(port, model, lp)
+    # bounded: a driver-chosen K sized for the GPU arm must not turn into tens of minutes of CPU work
+    requested, done = args.steps, 0
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    while done < requested and (done == 0 or time.perf_counter() - t0 < args.cpu_cap_seconds):
         status = cpu_step(port, model, lp)
+        done += 1
     dt = time.perf_counter() - t0
     assert int((status == 1).sum()) == lp.m
+    args.steps = done
     lps = args.steps / dt
     print(json.dumps({
         "impl": "reference",
@@ -676,7 +680,7 @@ def run_reference(args):
                                    f"(reference arch.py/val.py restated with torch CPU ops; PyG/torch_sparse are not "
                                    f"installable here), torch threads={cores}"},
         "e2e": {"value": lps, "unit": "LPs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "steps_requested": requested,
     }))
 
 
@@ -698,6 +702,8 @@ def main():
     ap.add_argument("--inflight", type=int, default=3, help="LPs in flight on alternating streams (both arms)")
     ap.add_argument("--kernel-reps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-cap-seconds", type=float, default=180.0,
+                    help="--impl reference: stop after this much timed CPU work even if fewer than --steps LPs ran")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-kernels", action="store_true")
     ap.add_argument("--no-train", action="store_true")

@@ -211,12 +211,15 @@ def test_full_size_c4_replication_property(cuda, precision):
     assert torch.equal(lg[:M].view(T, m, 3), lg1[:m].expand(T, m, 3))
     assert torch.equal(lg[M:].view(T, n, 3), lg1[m:].expand(T, n, 3))
     # global decision by its definition (ties at the threshold may fall on either side of an equal key)
-    p = torch.softmax(lg, dim=1)
+    # (the kernel's fp32 expf and this float64 softmax may order values one ulp apart differently: 1e-6 slack)
+    p = torch.softmax(lg.double(), dim=1)
     basic = st == 1
     assert int(basic.sum()) == M
-    assert float(p[basic, 1].min()) >= float(p[~basic, 1].max())
-    rest = torch.where(p[:, 0] >= p[:, 2], 0, 2).to(torch.uint8)
-    assert torch.equal(st[~basic], rest[~basic])
+    assert float(p[basic, 1].min()) >= float(p[~basic, 1].max()) - 1e-6
+    rest = torch.where(p[:, 0] >= p[:, 2], 0, 2).to(st.dtype)
+    clear = ~basic & ((p[:, 0] - p[:, 2]).abs() > 1e-6)
+    assert torch.equal(st[clear], rest[clear])
+    del clear
     del p, rest, basic, st, lg
     # per-LP decision over the same pack: every block repeats the single LP's statuses
     cptr = torch.arange(T + 1, device=cuda, dtype=torch.int32) * m
