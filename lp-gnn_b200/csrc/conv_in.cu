@@ -114,7 +114,7 @@ gather_cat_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ i
 // owns two adjacent columns (weights in registers as float2, packed FFMA2) and walks the rows; the z tile is a
 // broadcast shared-memory read.  Stores are coalesced (4 / 8 bytes per lane, 128 / 256 bytes per warp).
 template <int KT, typename OutT>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, KT <= 32 ? 2 : 1)   // KT = 64: 128 weight registers per thread
 small_k_transform_kernel(const float* __restrict__ z, int32_t rows, const float* __restrict__ W_rel, int k_src,
                          const float* __restrict__ W_root, int k_dst, const float* __restrict__ b_rel, int N,
                          OutT* __restrict__ out, int relu) {

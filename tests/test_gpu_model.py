@@ -184,13 +184,13 @@ def test_full_size_c2_parity_against_oracle(cuda, precision):
 def test_full_size_c4_replication_property(cuda, precision):
     """BASELINE config C4 at full size (1M x 2M, ~9.8M nnz, hids 1024, depth 3, 16-bit full-graph inference): the CPU
     oracle does not finish at this size, so parity is carried by a size-independent property.  The LP is the
-    block-diagonal of 20 copies of the C2 LP (whose logits are checked against the oracle above); message passing never
+    block-diagonal of 22 copies of the C2 LP (1.1M x 2.2M, just above C4's 1M x 2M so that element offsets pass 2^31) (whose logits are checked against the oracle above); message passing never
     crosses blocks and every kernel computes a row from that row's inputs in a fixed order, so every block's logits
     must be BIT-identical to the single C2 run -- this also exercises every offset above 2^31 elements
-    (2M rows x 1024 features).  The global basis decision is checked against its definition (val.py:106-124):
+    (2.2M rows x 1024 features).  The global basis decision is checked against its definition (val.py:106-124):
     exactly m basic nodes, they are the m largest P(basic), the rest follow ``0 if p0 >= p2 else 2``; the packed
     (per-LP decision) call must reproduce the single LP's statuses in every block."""
-    T = 20
+    T = 22
     lp, model, ref, g_ref, batch = _setup((50_000, 100_000, 500_000, 1236), 1024, 3, cuda)
     model.set_precision(precision)
     m, n, z = lp.m, lp.n, lp.nnz
@@ -205,7 +205,7 @@ def test_full_size_c4_replication_property(cuda, precision):
     del k
     x_s, x_t = batch.x_s.repeat(T, 1), batch.x_t.repeat(T, 1)
     M, N = T * m, T * n
-    assert M == 1_000_000 and N == 2_000_000 and N * 1024 >= 2 ** 31
+    assert M >= 1_000_000 and N >= 2_000_000 and N * 1024 >= 2 ** 31
     st, lg = model.predict_basis_coo(row, col, val, M, N, x_s, x_t, is_sorted=True, want_logits=True)
     assert int(model.last_graph_status.item()) == 0
     assert torch.equal(lg[:M].view(T, m, 3), lg1[:m].expand(T, m, 3))
