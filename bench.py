@@ -344,7 +344,7 @@ def run_gpu(args):
 def run_sweep(args):
     """--workload C5: the batch basis-prediction sweep (scripts/pred_basis.py workload) over a population of
     small/medium LPs (m log-uniform in [100, 20000], n = 2m, nnz = 5n).  A step = one LP.  The LPs are
-    independent units: with N ranks each rank takes every N-th LP (no collective)."""
+    independent units: with N ranks the population is N times larger and dealt over the ranks (no collective)."""
     import lpgnn_b200  # noqa: F401
     from lpgnn_b200 import _lib, arch, synth
     from lpgnn_b200.pipeline import BasisPipeline, PackedBasisPipeline, pack_lp, unpack_device
@@ -352,8 +352,17 @@ def run_sweep(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     lib = _lib.load()
-    pop = synth.lp_population(args.sweep_distinct, seed=1239)
-    mine = pop[rank::world] if world > 1 else pop
+    # weak scaling: `sweep_distinct` LPs PER RANK.  The population of world * sweep_distinct sizes is dealt in
+    # descending-nnz order, forwards then backwards over the ranks ("snake"), so every rank holds the same number
+    # of LPs and a near-equal share of the work -- a rank-dependent size mix would only measure the deal.
+    pop = synth.lp_population(args.sweep_distinct * world, seed=1239)
+    if world > 1:
+        from lpgnn_b200.io_utils import shard_indices
+        mine = [pop[i] for i in shard_indices(len(pop), rank, world, weights=[p[2] for p in pop], equal_counts=True)]
+        perm = np.random.default_rng(1239 + rank).permutation(len(mine))     # sweep order: shuffled, not sorted
+        mine = [mine[i] for i in perm]
+    else:
+        mine = pop
     lps = [synth.processed_lp(m, n, z, seed=sd) for (m, n, z, sd) in mine]
     hosts = [pack_lp(lp.row, lp.col, lp.a_data, lp.c_feas, lp.v_feas, is_sorted=True) for lp in lps]
     torch.manual_seed(0)
@@ -405,7 +414,8 @@ def run_sweep(args):
             "dtype": args.precision if args.precision in ("bf16", "fp16") else "f32", "data": "synthetic",
             "config": {"workload": f"C5: sweep over {len(pop)} distinct synthetic LPs (m log-uniform 100..20000, n=2m, "
                                    f"nnz~5n, mean nnz {nnz_mean:.0f}), GCN_FC(8,8,hids={args.sweep_hids},depth=3), one LP per "
-                                   f"step, LPs sharded round-robin over ranks", "precision": args.precision,
+                                   f"step; {len(mine)} LPs per rank, population dealt over ranks in descending-nnz snake order "
+                                   f"(equal counts, near-equal work)", "precision": args.precision,
                        "l2": "small LPs: working set is L2-resident by nature of the workload",
                        "e2e_api": "PackedBasisPipeline (block-diagonal packs, segmented basis decision)" if args.sweep_pack
                        else "BasisPipeline (one native call per LP)"},

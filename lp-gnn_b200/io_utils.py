@@ -98,12 +98,20 @@ def batch_to(batch, dev, half=False):
     return batch
 
 
-def shard_indices(n_items, rank, world, weights=None):
+def shard_indices(n_items, rank, world, weights=None, equal_counts=False):
     """Deterministic partition of ``range(n_items)`` over ``world`` ranks: greedy longest-processing-time on
-    ``weights`` (e.g. nnz) when given, round-robin otherwise.  Every rank computes the same answer locally."""
+    ``weights`` (e.g. nnz) when given, round-robin otherwise.  ``equal_counts`` (with weights): deal the items in
+    descending weight forwards then backwards over the ranks ("snake"), so shard sizes differ by at most one item and
+    the shards carry a near-equal share of the weight -- for sweeps that process a fixed number of LPs per rank.
+    Every rank computes the same answer locally."""
     if weights is None:
         return list(range(rank, n_items, world))
     order = np.argsort(-np.asarray(weights, dtype=np.float64), kind="stable")
+    if equal_counts:
+        pos = np.arange(n_items)
+        lap, slot = pos // world, pos % world
+        owner = np.where(lap % 2 == 0, slot, world - 1 - slot)
+        return sorted(int(i) for i in order[owner == rank])
     load = np.zeros(world)
     mine = []
     for i in order:

@@ -126,6 +126,11 @@ def test_shard_indices_partition(pkg):
         assert sorted(sum(parts, [])) == list(range(37))
         loads = [w[p].sum() for p in parts]
         assert max(loads) - min(loads) <= w.max()                       # LPT balance
+        parts = [io.shard_indices(37, r, world, weights=w, equal_counts=True) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(37))
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1         # snake deal: equal counts ...
+        loads = [w[p].sum() for p in parts]
+        assert max(loads) - min(loads) <= w.max()                       # ... and near-equal weight
 
 
 def test_losses_match_reference_semantics(pkg):
