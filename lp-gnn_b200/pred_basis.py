@@ -43,8 +43,34 @@ def write_bas_highs(fn, vnms=None, cnms=None, vbas=None, cbas=None):
         f.write(enc_vec(np.asarray(cbas).tolist()) + "\n")
 
 
-def write_sort_vars(fn, p_basic_vars, p_basic_cons):
-    """``.bas.sort`` file (pred_basis.py:57-67): P(basic) of the variables, then of the constraints."""
+def write_bas(fn, var_nms, con_nms, pred_var, pred_con):
+    """Named (MPS-style) basis file (pred_basis.py:25-55, the alternative ``write_func``): basic variables are paired
+    with the constraints at their lower (``XL``) then upper (``XU``) bound, in file order; then ``UL`` for the
+    variables at their upper bound.  Variables at the lower bound are the format's default and are not written."""
+    var_nms, con_nms = np.asarray(var_nms), np.asarray(con_nms)
+    pred_var, pred_con = np.asarray(pred_var), np.asarray(pred_con)
+    basic_vars = var_nms[pred_var == 1]
+    cons_lo, cons_up = con_nms[pred_con == 0], con_nms[pred_con == 2]
+    assert len(basic_vars) == len(cons_lo) + len(cons_up)
+    lines = [f"NAME          0.mps  Iterations 0  Rows {len(con_nms)}  Cols {len(var_nms)} \n"]
+    lines += [f" XL {v} {c} \n" for v, c in zip(basic_vars[:len(cons_lo)], cons_lo)]
+    lines += [f" XU {v} {c} \n" for v, c in zip(basic_vars[len(cons_lo):], cons_up)]
+    lines += [f" UL {v} \n" for v in var_nms[pred_var == 2]]
+    lines.append("ENDATA")
+    with open(fn, "w") as f:
+        f.writelines(lines)
+
+
+def write_sort_vars(fn, logits, m):
+    """``.bas.sort`` file (pred_basis.py:57-67): P(basic) of the variables, then of the constraints.  Two call
+    forms: the reference's ``(fn, logits[m+n,3], m)`` (constraints first; softmax taken here), or
+    ``(fn, p_basic_vars, p_basic_cons)`` with the probabilities already split (what ``run`` has in hand after the
+    device-side decision)."""
+    if isinstance(m, (int, np.integer)):
+        pr = torch.softmax(torch.as_tensor(logits), dim=-1)[:, 1].cpu().numpy()
+        p_basic_vars, p_basic_cons = pr[int(m):], pr[:int(m)]
+    else:
+        p_basic_vars, p_basic_cons = logits, m
     with open(fn, "w") as f:
         f.write(f"{len(p_basic_vars)} \n")
         f.write(enc_vec(p_basic_vars) + "\n")

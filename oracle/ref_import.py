@@ -119,6 +119,13 @@ def load_reference():
         ref_arch = importlib.import_module("arch")
         ref_dataset = importlib.import_module("dataset")
         ref_val = importlib.import_module("val")
+        # scripts/pred_basis.py (the writers of SURVEY 8 f-1): star-imports utils / arch / dataset / val, its
+        # entry point sits under `if __name__ == '__main__'`
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_pred_basis",
+                                                      os.path.join(REFERENCE_ROOT, "scripts", "pred_basis.py"))
+        ref_pred = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref_pred)
     finally:
         sys.path[:] = saved_path
         for k, v in saved_modules.items():
@@ -127,5 +134,5 @@ def load_reference():
             else:
                 sys.modules[k] = v
     _CACHE = types.SimpleNamespace(arch=ref_arch, dataset=ref_dataset, utils=ref_utils,
-                                   val=ref_val, Data=_Data, SparseTensor=S.SparseTensor)
+                                   val=ref_val, pred_basis=ref_pred, Data=_Data, SparseTensor=S.SparseTensor)
     return _CACHE

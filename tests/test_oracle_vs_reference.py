@@ -68,3 +68,30 @@ def test_add_knowledge_matches_reference(R):
     np.testing.assert_allclose(d, b.numpy(), rtol=0, atol=2e-6)
     e, f = port.add_knowledge_t(torch.from_numpy(l), torch.from_numpy(r), torch.from_numpy(fl), torch.from_numpy(fr))
     assert torch.equal(e, a) and torch.equal(f, b)
+
+
+def test_basis_file_writers_match_reference_byte_for_byte(R, tmp_path):
+    """write_bas_highs / write_bas / write_sort_vars (scripts/pred_basis.py:14-67) vs the product's."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import pred_basis as mine
+    rng = np.random.default_rng(7)
+    m, n = 9, 17
+    logits = torch.from_numpy(rng.standard_normal((m + n, 3)).astype(np.float32) * 3)
+    pred = R.val.inference_gnn(logits.clone(), m).numpy()
+    pred_con, pred_var = pred[:m], pred[m:]
+    # a consistent named basis for write_bas: as many basic variables as non-basic constraints
+    pv = np.zeros(n, dtype=np.int64); pc = np.ones(m, dtype=np.int64)
+    pc[[1, 4, 6]] = [0, 2, 0]; pv[[2, 3, 11]] = 1; pv[[5, 16]] = 2
+    var_nms, con_nms = [f"x{i}" for i in range(n)], [f"c{i}" for i in range(m)]
+    ref_dir, my_dir = tmp_path / "ref", tmp_path / "mine"
+    ref_dir.mkdir(); my_dir.mkdir()
+    for mod, d in ((R.pred_basis, ref_dir), (mine, my_dir)):
+        mod.write_bas_highs(str(d / "a.bas"), var_nms, con_nms, pred_var, pred_con)
+        mod.write_bas(str(d / "b.bas"), var_nms, con_nms, pv, pc)
+        mod.write_sort_vars(str(d / "a.bas.sort"), logits, m)
+    for name in ("a.bas", "b.bas", "a.bas.sort"):
+        assert (ref_dir / name).read_bytes() == (my_dir / name).read_bytes(), name
+    # the split-probability form used by run() writes the same file
+    p1 = torch.softmax(logits, dim=-1)[:, 1].numpy()
+    mine.write_sort_vars(str(my_dir / "c.sort"), p1[m:], p1[:m])
+    assert (my_dir / "c.sort").read_bytes() == (ref_dir / "a.bas.sort").read_bytes()
