@@ -27,6 +27,7 @@ from .data import DataLoader
 from .dataset import LPDataset, MyToBipartite
 from .io_utils import shard_indices, split_train_val
 from .losses import LOSSES
+from .val import accuracy
 
 
 def dist_info():
@@ -196,7 +197,11 @@ def run_exp(args):
                 if (glstep - 1) % max(args.log_every, 1) == 0:
                     lv = float(loss.item())
                     assert not np.isnan(lv)              # train.py:126
-                    history.append(dict(epoch=epoch, step=glstep, loss=lv, lr=scheduler.get_last_lr()[0]))
+                    # train.py:131-137 (acc_meter): the reference scores every step; here on the logged steps only,
+                    # since accuracy() ends in a host read
+                    acc = float(accuracy(torch.cat((logit_cons, logit_vars), dim=0).detach(),
+                                         torch.cat((y_s, y_t), dim=0), logit_cons.shape[0]))
+                    history.append(dict(epoch=epoch, step=glstep, loss=lv, acc=acc, lr=scheduler.get_last_lr()[0]))
                     if rank == 0:
                         logging.info(f"{epoch} {it}/{steps_per_epoch} step {glstep} loss {lv:.4f}")
         scheduler.step()

@@ -1,8 +1,11 @@
 """Drop-in for the hot-path parts of the reference ``val.py``: ``inference_gnn`` (106-124),
-``model_inference_with_batch`` (12-36), ``accuracy`` (199-237), ``InferenceManager`` naming (167-197)."""
+``model_inference_with_batch`` (12-36), ``validation`` (43-69), ``accuracy`` (199-237), ``InferenceManager`` naming
+(167-197) and the entry point (238-281: ``python -m lpgnn_b200.val --arch ... --load_from .../mdl.pth``)."""
 from __future__ import annotations
 
+import json
 import logging
+import os
 
 import numpy as np
 import torch
@@ -62,6 +65,67 @@ def model_inference_with_batch(model, batched_graphs, args=None):
 
 
 @torch.no_grad()
+def validation(model, loader, dev, dump_info=None, args=None):
+    """Reference val.py:43-69: per LP, logits through ``model_inference_with_batch`` and ``accuracy(...,
+    return_pr=True)`` against the labels of the bipartite view; returns ``(avg_loss, avg_acc)`` with ``avg_loss`` = 0
+    like the reference (it never accumulates a loss here).  The model's training flag is restored.  ``dump_info``:
+    the reference updates the acc / prec / recl columns of a pandas HDF file (``tables`` is not on this image); here
+    it names a JSON file that receives ``{file name: {acc, prec, recl}}``."""
+    from .dataset import MyToBipartite
+    from .io_utils import extract_fn
+    model.to(dev)
+    was_training = model.training
+    model.eval()
+    avg_loss = avg_acc = 0.
+    rows = {}
+    n_lps = len(loader)
+    for idx, batch in enumerate(loader):
+        fn = extract_fn(batch.processed_path[0])
+        logit_cons, logit_vars = model_inference_with_batch(model, batch, args)
+        if not hasattr(batch, "x_s"):                     # above edge_num_thresh: labels from the bipartite view
+            batch = MyToBipartite(thresh_num=np.inf)(batch)
+        acc, prec, recl = accuracy(torch.cat((logit_cons, logit_vars), dim=0),
+                                   torch.cat((batch.y_s, batch.y_t), dim=0).cpu(), logit_cons.shape[0], return_pr=True,
+                                   dataset_name=getattr(args, "dataset", "") or "")
+        avg_acc += acc / n_lps
+        rows[fn] = dict(acc=float(acc), prec=float(prec), recl=float(recl))
+        if idx % 9 == 1:
+            logging.info(f"{idx} {fn} {n_lps} {acc} {prec} {recl}")
+    if was_training:
+        model.train()
+    if dump_info:
+        with open(dump_info, "w") as f:
+            json.dump(rows, f)
+    return avg_loss, avg_acc
+
+
+def run(args):
+    """Reference val.py:238-281: load the dataset, split, build ``eval(args.arch)``, load the checkpoint, optional
+    ``model.half()`` and report the mean validation accuracy."""
+    from .arch import GCN_FC  # noqa: F401  (eval(args.arch))
+    from .data import DataLoader
+    from .dataset import LPDataset, MyToBipartite
+    from .io_utils import split_train_val
+    _device()                                             # raises without a CUDA device: no CPU fallback
+    dev = torch.device("cuda", int(args.dev))
+    torch.cuda.set_device(dev)
+    os.makedirs(args.log_dir, exist_ok=True)
+    ds = LPDataset(args.dataset_processed_prefix, transform=MyToBipartite(thresh_num=args.edge_num_thresh))
+    assert len(ds) != 0, "should not empty"
+    _, val_ds = split_train_val(ds, args.seed)
+    loader = DataLoader(val_ds, batch_size=1, shuffle=False, drop_last=False, num_workers=args.num_workers)
+    model = eval(args.arch).to(dev)                       # noqa: S307  (the reference's plugin mechanism, val.py:266)
+    if args.load_from.lower() != "none":
+        model.load(args.load_from)
+    if args.fp16:
+        model.half()
+    model.eval()
+    avg_loss, avg_acc = validation(model, loader, dev, dump_info=f"{args.log_dir}/val_metrics.json", args=args)
+    print("avg val acc", avg_acc)
+    return avg_loss, avg_acc
+
+
+@torch.no_grad()
 def accuracy(logits, gt, num_cons, return_pr=False, dataset_name=""):
     """Reference val.py:199-237: mean of constraint / variable accuracy, macro precision / recall of class 1."""
     from sklearn import metrics
@@ -102,3 +166,9 @@ class InferenceManager:
 
     def get_basis_folder(self):
         return "pred-basis" + (f"-{self.run}" if self.run != 0 else "")
+
+
+if __name__ == "__main__":
+    from .train import parse_args
+    logging.basicConfig(level=logging.INFO)
+    run(parse_args())

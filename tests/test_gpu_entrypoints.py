@@ -1,5 +1,6 @@
 """The reference's entry points end to end on the GPU: dataset files -> train.run_exp -> mdl.pth ->
 pred_basis.run -> HiGHS .bas files, and val.inference_gnn / accuracy on CPU-resident logits like the callers use."""
+import json
 import os
 import types
 
@@ -57,6 +58,30 @@ def test_train_then_predict_basis_files(cuda, dataset_root, tmp_path):
         agree = np.mean(np.concatenate([cbas, vbas]) == exp)
         assert agree >= 0.995, agree
         assert os.path.exists(f"{log_dir}/pred-basis/{fn}.bas.sort")
+    # val.py entry point (val.py:238-281 -> validation, 43-69) with the same weights: per-LP accuracy vs the oracle's
+    from lpgnn_b200 import val
+    assert all(0.0 <= h["acc"] <= 1.0 for h in history)                      # train.py:131-137 accuracy meter
+    was = model.training
+    avg_loss, avg_acc = val.run(args2)
+    rows = json.load(open(log_dir + "val_metrics.json"))
+    assert avg_loss == 0.0 and len(rows) == 3 and abs(avg_acc - np.mean([r["acc"] for r in rows.values()])) < 1e-12
+    for i in val_ds.indices():
+        uni = ds.get(i)
+        fn = os.path.basename(uni.processed_path).replace(".pk", "")
+        g = port.to_bipartite(uni.edge_index.numpy(), uni.edge_attr.numpy(), uni.is_vars.numpy())
+        m = g.m
+        with torch.no_grad():
+            lc, lv = ref(uni.x[:m], uni.x[m:], port.TorchGraph(g))
+        exp = port.inference_gnn_np(torch.cat((lc, lv)).numpy(), m)
+        y = uni.y.numpy()
+        exp_acc = ((exp[:m] == y[:m]).mean() + (exp[m:] == y[m:]).mean()) / 2
+        assert abs(rows[fn]["acc"] - exp_acc) < 0.02, (fn, rows[fn], exp_acc)
+        assert 0.0 <= rows[fn]["prec"] <= 1.0 and 0.0 <= rows[fn]["recl"] <= 1.0
+    # validation() restores the training flag of the model it is given
+    model.train()
+    val.validation(model, [], torch.device(cuda))
+    assert model.training
+    model.train(was)
     # sweep mode (block-diagonal packs, segmented basis decision) writes the same .bas files
     log2 = str(tmp_path / "run_packed") + "/"
     args3 = train.parse_args([], arch="GCN_FC(8,8,hids=64,depth=3)", load_from=log_dir + "mdl.pth", packed=1,
