@@ -26,7 +26,7 @@ from .arch import *  # noqa: F401,F403  (``eval(args.arch)`` resolves GCN_FC(...
 from .data import DataLoader
 from .dataset import LPDataset, MyToBipartite
 from .io_utils import shard_indices, split_train_val
-from .losses import LOSSES
+from .losses import LOSSES, FocalLoss, balanced, focal, unbalanced  # noqa: F401  (module-level names of train.py:18-53)
 from .val import accuracy
 
 
