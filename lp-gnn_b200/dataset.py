@@ -47,6 +47,51 @@ class LPDataset(Dataset):
         self.p = self.q = 8
         super().__init__(root, transform, pre_transform, pre_filter)
 
+    def cache_size_info(self, recache=False):
+        """dataset.py:119-157: one row per LP -- ``idx, nedges, nnodes, fn, ncons, nvars, density, num_basis_vars`` --
+        cached in ``<root>/size.json``; returned as a DataFrame restricted to this (sub-)dataset's indices.  Needs the
+        bipartite transform (it reads ``x_s / x_t / y_t`` and ``edge_index.nnz() / .density()``); host only."""
+        import json
+
+        import pandas as pd
+        dump_fn = osp.join(self.root, "size.json")
+        res = None
+        if not recache and osp.exists(dump_fn):
+            try:
+                with open(dump_fn) as f:
+                    res = json.load(f)
+            except (OSError, ValueError) as e:
+                logging.info(f"err {e}, recache")
+        if res is None:
+            res = []
+            for idx in range(self.len()):                 # the whole dataset, also when called on a sub-dataset
+                data = self.get(idx)
+                data = data if self.transform is None else self.transform(data)
+                res.append(dict(idx=idx, nedges=int(data.edge_index.nnz()), nnodes=int(data.num_nodes),
+                                fn=osp.basename(data.processed_path), ncons=int(data.x_s.shape[0]),
+                                nvars=int(data.x_t.shape[0]), density=float(data.edge_index.density()),
+                                num_basis_vars=int((data.y_t == 1).sum())))
+            with open(dump_fn, "w") as f:
+                json.dump(res, f, sort_keys=True, indent=4)
+        df = pd.DataFrame(res).loc[list(self.indices()), :]
+        if len(self.indices()) != len(res):
+            logging.warning("sub-dataset get info, please use full dataset ")
+        df["fn"] = df.fn.str.replace(".pk", "", regex=False)
+        return df
+
+    def dump_size_info(self, dst):
+        """dataset.py:107-117: the size table with a ``split`` column (seed-0 train / val split).  The reference
+        writes a pandas HDF file (``tables``, not on this image); here ``dst`` receives the same table as JSON."""
+        from .io_utils import split_train_val
+        df = self.cache_size_info()
+        if osp.exists(dst):
+            return None
+        train_ds, val_ds = split_train_val(self, seed=0)
+        df.loc[list(train_ds.indices()), "split"] = "train"
+        df.loc[list(val_ds.indices()), "split"] = "val"
+        df.to_json(dst, orient="records", indent=1)
+        return df
+
     @property
     def raw_file_names(self):
         fns = []

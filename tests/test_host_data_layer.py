@@ -88,6 +88,19 @@ def test_loader_split_and_process(pkg, tmp_path):
     np.random.seed(0)
     perm = np.random.permutation(10)                                   # utils.py:259-262 semantics
     assert list(tr.indices()) == sorted(perm[:7].tolist())
+    # dataset.py:107-157 size table: whole dataset cached in size.json, rows restricted to the (sub-)dataset
+    info = ds.cache_size_info()
+    assert set(info.columns) == {"idx", "nedges", "nnodes", "fn", "ncons", "nvars", "density", "num_basis_vars"}
+    assert len(info) == 10 and os.path.exists(os.path.join(root, "size.json"))
+    b0 = ds[0]
+    r0 = info.loc[0]
+    assert (r0.ncons, r0.nvars, r0.nnodes) == (20, 50, 70) and r0.nedges == b0.edge_index.nnz()
+    assert abs(r0.density - r0.nedges / (20 * 50)) < 1e-15 and r0.num_basis_vars == int((b0.y_t == 1).sum())
+    assert not r0.fn.endswith(".pk")
+    assert list(va.cache_size_info().index) == list(va.indices())
+    dumped = ds.dump_size_info(os.path.join(root, "size_split.json"))
+    assert sorted(dumped.index[dumped.split == "val"]) == sorted(va.indices())
+    assert ds.dump_size_info(os.path.join(root, "size_split.json")) is None          # exists: left alone
     loader = data.DataLoader(va, batch_size=1, shuffle=False, num_workers=0)
     names = [b.processed_path[0] for b in loader]
     assert len(names) == 3 and all(isinstance(b, str) for b in names)
