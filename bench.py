@@ -407,7 +407,7 @@ def run_sweep(args):
     nnz_mean = float(np.mean([lp.nnz for lp in lps]))
     lps_s, lps_e2e = world * steps / (t_ms / 1e3), world * steps / (t_e2e / 1e3)
     if rank == 0:
-        print(json.dumps({
+        out = {
             "metric": "LPs/sec (basis prediction: graph build + GCN_FC forward + basis selection)",
             "value": lps_s, "unit": "LPs/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
             "ms_per_step": t_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -422,7 +422,10 @@ def run_sweep(args):
             "mp_edges_per_sec": mp_edges(nnz_mean, 3) * lps_s,
             "e2e": {"value": lps_e2e, "unit": "LPs/s", "h2d_bytes_per_step": float(np.mean([h.nbytes for h in hosts])),
                     "d2h_bytes_per_step": float(np.mean([h.m + h.n for h in hosts])), "ms_per_step": t_e2e / steps},
-            "gpu_launches": int(launches), "clocks": clocks}))
+            "gpu_launches": int(launches), "clocks": clocks}
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_sweep_baseline(lps, args.sweep_hids, sample_budget_s=args.cpu_seconds)
+        print(json.dumps(out))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -613,6 +616,27 @@ def cpu_baseline(cfg, lp, args, sample_budget_s=20.0):
             "mp_edges_per_sec": mp_edges(lp.nnz, cfg["depth"]) / dt}
 
 
+def cpu_sweep_baseline(lps, hids, sample_budget_s=15.0):
+    """C5: the same sweep order on the oracle port of the reference CPU path, all host threads, until the time
+    budget is spent (a bounded sample: the first LPs of the population)."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    port, model, _ = _port_setup(dict(hids=hids, depth=3), lps[0])
+    cpu_step(port, model, lps[0])
+    t0, reps = time.perf_counter(), 0
+    while reps < len(lps) and time.perf_counter() - t0 < sample_budget_s:
+        cpu_step(port, model, lps[reps])
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    nnz_mean = float(np.mean([lp.nnz for lp in lps[:reps]]))
+    return {"value": 1.0 / dt, "unit": "LPs/s", "cores": cores, "kind": "port",
+            "sample": f"the first {reps} LPs of the sweep (mean nnz {nnz_mean:.0f}), fp32, {dt * 1e3:.0f} ms/LP; oracle port of "
+                      f"the reference CPU path (PyG-equivalent restatement, not the PyG binary); torch threads={cores}",
+            "mp_edges_per_sec": mp_edges(nnz_mean, 3) / dt}
+
+
 def cpu_train_baseline(cfg, lp, sample_budget_s=8.0, max_steps=200):
     """configs[0] of BASELINE.json: the reference's CPU training step (train.py:117-129: forward, balanced loss,
     backward, Adam) on the oracle port, all host threads; a bounded sample of steps on the same LP."""
@@ -658,33 +682,45 @@ def run_reference(args):
         return
     import lpgnn_b200  # noqa: F401
     from lpgnn_b200 import synth
-    cfg = workload_spec(args.workload)
-    lp = synth.processed_lp(cfg["m"], cfg["n"], cfg["nnz"], seed=cfg["seed"], structure=args.structure)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    if args.workload == "C5":
+        # the sweep population of the GPU arm (rank 0's share at N=1): one LP per step, cycled in the same order
+        cfg = dict(name="C5", hids=args.sweep_hids, depth=3)
+        pop = synth.lp_population(args.sweep_distinct, seed=1239)[:max(1, min(args.sweep_distinct, args.steps + 3))]
+        lps_list = [synth.processed_lp(m, n, z, seed=sd) for (m, n, z, sd) in pop]
+    else:
+        cfg = workload_spec(args.workload)
+        lps_list = [synth.processed_lp(cfg["m"], cfg["n"], cfg["nnz"], seed=cfg["seed"], structure=args.structure)]
+    lp = lps_list[0]
     port, model, _ = _port_setup(cfg, lp)
-    for _ in range(max(1, min(args.warmup, 3))):
-        cpu_step(port, model, lp)
+    for i in range(max(1, min(args.warmup, 3))):
+        cpu_step(port, model, lps_list[i % len(lps_list)])
     # bounded: a driver-chosen K sized for the GPU arm must not turn into tens of minutes of CPU work
     requested, done = args.steps, 0
     t0 = time.perf_counter()
     while done < requested and (done == 0 or time.perf_counter() - t0 < args.cpu_cap_seconds):
-        status = cpu_step(port, model, lp)
+        cur = lps_list[done % len(lps_list)]
+        status = cpu_step(port, model, cur)
+        assert int((status == 1).sum()) == cur.m
         done += 1
     dt = time.perf_counter() - t0
-    assert int((status == 1).sum()) == lp.m
     args.steps = done
     lps = args.steps / dt
+    nnz_mean = float(np.mean([x.nnz for x in lps_list[:max(1, min(done, len(lps_list)))]]))
     print(json.dumps({
         "impl": "reference",
         "metric": "LPs/sec (basis prediction: graph build + GCN_FC forward + basis selection)",
         "value": lps, "unit": "LPs/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{cfg['name']}: GCN_FC(8,8,hids={cfg['hids']},depth={cfg['depth']}) inference, synthetic "
-                               f"{args.structure} LP {lp.m}x{lp.n}, nnz={lp.nnz}, one LP per step",
+        "config": {"workload": (f"C5: sweep over {len(lps_list)} distinct synthetic LPs (m log-uniform 100..20000, n=2m, "
+                                f"nnz~5n, mean nnz {nnz_mean:.0f}), GCN_FC(8,8,hids={cfg['hids']},depth=3), one LP per step"
+                                if args.workload == "C5" else
+                                f"{cfg['name']}: GCN_FC(8,8,hids={cfg['hids']},depth={cfg['depth']}) inference, synthetic "
+                                f"{args.structure} LP {lp.m}x{lp.n}, nnz={lp.nnz}, one LP per step"),
                    "precision": "fp32", "structure": args.structure},
-        "mp_edges_per_sec": mp_edges(lp.nnz, cfg["depth"]) * lps,
+        "mp_edges_per_sec": mp_edges(nnz_mean, cfg["depth"]) * lps,
         "cpu_baseline": {"value": lps, "unit": "LPs/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} LPs, one per step; oracle port of the reference CPU path "
                                    f"(reference arch.py/val.py restated with torch CPU ops; PyG/torch_sparse are not "
