@@ -75,6 +75,10 @@ class BasisPipeline:
     def _copy_in(self, slot, lp: HostLP, first_use):
         words = lp.pack.numel()
         if self.d_buf[slot] is None or self.d_buf[slot].numel() < words:
+            if not first_use:
+                # the slot's previous LP may still be computing on another stream: it must be finished before its
+                # staging buffer goes back to the allocator (growth is rare, the host wait is not on the steady path)
+                self.done[slot].synchronize()
             self.d_buf[slot] = torch.empty(int(words * 1.25) + 64, dtype=torch.int32, device=self.dev)
         with torch.cuda.stream(self.copy_stream):
             if not first_use:
@@ -175,6 +179,8 @@ class PackedBasisPipeline:
         o_ptr = o_xt + N * q
         words = o_ptr + 3 * (B + 1)
         if self.d_buf[slot] is None or self.d_buf[slot].numel() < words:
+            if not first_use:
+                self.done[slot].synchronize()   # the slot's previous pack may still be computing on this buffer
             self.d_buf[slot] = torch.empty(int(words * 1.25) + 64, dtype=torch.int32, device=self.dev)
         if self.h_ptr[slot] is None or self.h_ptr[slot].numel() < 3 * (B + 1):
             self.h_ptr[slot] = torch.empty(3 * (self.max_lps + 1), dtype=torch.int32).pin_memory()
