@@ -31,7 +31,6 @@ import subprocess
 import sys
 import threading
 import time
-import types
 
 import numpy as np
 import torch

@@ -7,13 +7,10 @@ computed, so PCIe time hides behind the kernels; every LP's copies still happen 
 """
 from __future__ import annotations
 
-import types
 from dataclasses import dataclass
 
 import numpy as np
 import torch
-
-from .graph import BipartiteCSR
 
 
 @dataclass

@@ -10,7 +10,6 @@ from __future__ import annotations
 
 import json
 import logging
-import os
 import os.path as osp
 import time
 from concurrent.futures import ThreadPoolExecutor
