@@ -95,3 +95,31 @@ def test_basis_file_writers_match_reference_byte_for_byte(R, tmp_path):
     p1 = torch.softmax(logits, dim=-1)[:, 1].numpy()
     mine.write_sort_vars(str(my_dir / "c.sort"), p1[m:], p1[:m])
     assert (my_dir / "c.sort").read_bytes() == (ref_dir / "a.bas.sort").read_bytes()
+
+
+def test_golden_fixtures_are_reproducible_outputs_of_the_reference(R, tmp_path, monkeypatch):
+    """tests/golden/*.npz are what pins the oracle and the CUDA path (the reference ships no vectors of its own):
+    re-running oracle/make_golden.py on the verbatim reference must reproduce every committed array -- integer
+    arrays exactly, floating-point arrays to 1e-6 (thread-count dependent summation order in MKL)."""
+    import glob
+    import os
+
+    from oracle import make_golden
+    committed = os.path.join(os.path.dirname(__file__), "golden")
+    monkeypatch.setattr(make_golden, "OUT", str(tmp_path))
+    with contextlib.redirect_stdout(io.StringIO()):
+        make_golden.main()
+    names = sorted(os.path.basename(f) for f in glob.glob(os.path.join(committed, "*.npz")))
+    assert names == sorted(os.listdir(tmp_path)) and len(names) >= 10
+    for nm in names:
+        a, b = np.load(os.path.join(committed, nm)), np.load(os.path.join(tmp_path, nm))
+        assert sorted(a.files) == sorted(b.files), nm
+        for k in a.files:
+            x, y = a[k], b[k]
+            assert x.shape == y.shape and x.dtype == y.dtype, (nm, k)
+            if np.issubdtype(x.dtype, np.floating):
+                # gradients / logits: relative to the array's scale
+                scale = max(1.0, float(np.abs(x[np.isfinite(x)]).max())) if x.size and np.isfinite(x).any() else 1.0
+                np.testing.assert_allclose(y, x, rtol=0, atol=1e-5 * scale, err_msg=f"{nm}:{k}")
+            else:
+                np.testing.assert_array_equal(y, x, err_msg=f"{nm}:{k}")
