@@ -123,3 +123,51 @@ def test_golden_fixtures_are_reproducible_outputs_of_the_reference(R, tmp_path, 
                 np.testing.assert_allclose(y, x, rtol=0, atol=1e-5 * scale, err_msg=f"{nm}:{k}")
             else:
                 np.testing.assert_array_equal(y, x, err_msg=f"{nm}:{k}")
+
+
+def test_graph_construction_port_vs_reference_random_patterns(R):
+    """Property test (hypothesis): LPDataset.get's to_undirected + the verbatim MyToBipartite + SparseTensor.t()
+    (dataset.py:250-252, 275-332; arch.py:71) vs oracle.port on random sparsity patterns -- empty rows / columns,
+    single entries, dense blocks, COO given in shuffled order -- bit-exact indices and values in both orientations."""
+    import scipy.sparse as sp
+    from hypothesis import given, settings, strategies as st
+
+    from oracle.make_golden import reference_batch_via_stubs
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(m=st.integers(1, 12), n=st.integers(1, 15), density=st.floats(0.02, 0.9), seed=st.integers(0, 10_000))
+    def check(m, n, density, seed):
+        rng = np.random.default_rng(seed)
+        mask = rng.random((m, n)) < density
+        if not mask.any():
+            mask[rng.integers(m), rng.integers(n)] = True
+        r, c = np.nonzero(mask)
+        v = rng.uniform(-1, 1, r.shape[0]).astype(np.float32)
+        v[v == 0] = 0.5
+        perm = rng.permutation(r.shape[0])
+        A = sp.coo_matrix((v[perm], (r[perm], c[perm])), shape=(m, n))
+        cf, vf = rng.standard_normal((m, 8)).astype(np.float32), rng.standard_normal((n, 8)).astype(np.float32)
+        y_s, y_t = rng.integers(0, 3, m), rng.integers(0, 3, n)
+        uni, batch = reference_batch_via_stubs(R, A, cf, vf, y_s, y_t)
+        ei, ea = port.unipartite_edges(A.row, A.col, A.data, m)
+        np.testing.assert_array_equal(ei, uni["edge_index"])
+        np.testing.assert_array_equal(ea, uni["edge_attr"])
+        g = port.to_bipartite(uni["edge_index"], uni["edge_attr"], uni["is_vars"])
+        adj = batch.edge_index
+        st_, tt = adj.storage, adj.t().storage
+        np.testing.assert_array_equal(g.rowptr, st_.rowptr().numpy())
+        np.testing.assert_array_equal(g.col, st_.col().numpy())
+        np.testing.assert_array_equal(g.val, st_.value().numpy())
+        np.testing.assert_array_equal(g.colptr, tt.rowptr().numpy())
+        np.testing.assert_array_equal(g.row_csc, tt.col().numpy())
+        np.testing.assert_array_equal(g.val_csc, tt.value().numpy())
+        # independent check of the stand-in itself: both orientations equal scipy's canonical CSR / CSC
+        ref_csr = sp.csr_matrix((A.data, (A.row, A.col)), shape=(m, n)); ref_csr.sort_indices()
+        ref_csc = ref_csr.tocsc(); ref_csc.sort_indices()
+        np.testing.assert_array_equal(g.col, ref_csr.indices); np.testing.assert_array_equal(g.val, ref_csr.data)
+        np.testing.assert_array_equal(g.row_csc, ref_csc.indices); np.testing.assert_array_equal(g.val_csc, ref_csc.data)
+        assert (batch.s_bs, batch.t_bs) == (m, n)
+        np.testing.assert_array_equal(batch.x_s.numpy(), cf)
+        np.testing.assert_array_equal(batch.y_t.numpy(), y_t)
+
+    check()
