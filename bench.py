@@ -627,7 +627,7 @@ def cpu_baseline(cfg, lp, args, sample_budget_s=20.0):
 
 
 def train_sampled_throughput(cfg, lp, dev, precision, steps, world, seeds_per_batch=16_384, fanout=6):
-    """C3's sampled mini-batch variant (reference train.py:105-116: NeighborLoader with num_neighbors=[6]*depth over an
+    """C3's sampled mini-batch variant (reference train.py:105-116: NeighborLoader with num_neighbors=[6]*(depth-1) over an
     LP kept whole on the device): every step = neighbour sampling + induced-subgraph build (csrc/sample.cu,
     graph_build.cu) + forward + balanced loss + backward + gradient all-reduce (N > 1) + Adam on the mini-batch."""
     from lpgnn_b200 import arch
@@ -643,7 +643,8 @@ def train_sampled_throughput(cfg, lp, dev, precision, steps, world, seeds_per_ba
     g = BipartiteCSR.from_coo_arrays(lp.row, lp.col, lp.a_data.astype(np.float32), lp.m, lp.n, dev, is_sorted=True)
     res = ResidentLP(g, torch.from_numpy(lp.c_feas).to(dev), torch.from_numpy(lp.v_feas).to(dev),
                      torch.from_numpy(lp.y_s).to(dev), torch.from_numpy(lp.y_t).to(dev))
-    loader = NeighborSubgraphLoader(res, [fanout] * cfg["depth"], seeds_per_batch, shuffle=True, drop_last=True, seed=1)
+    hops = max(cfg["depth"] - 1, 1)          # train.py:108-110: depth - 1 hops for GCN_FC (the last layer is the FC head)
+    loader = NeighborSubgraphLoader(res, [fanout] * hops, seeds_per_batch, shuffle=True, drop_last=True, seed=1)
     sizes = []
 
     def run(count):
@@ -679,7 +680,7 @@ def train_sampled_throughput(cfg, lp, dev, precision, steps, world, seeds_per_ba
     nodes, nnz = float(np.mean([a for a, _ in sizes])), float(np.mean([b for _, b in sizes]))
     sps = world * steps / (t_ms / 1e3)
     return {"workload": f"{cfg['name']}-shaped LP resident on the device, mini-batches of {loader.batch_size} seed nodes, fan-out "
-                        f"[{fanout}]*{cfg['depth']}: sampling + induced subgraph + training step"
+                        f"[{fanout}]*{hops}: sampling + induced subgraph + training step"
                         f"{' + NCCL grad all-reduce' if world > 1 else ''}",
             "precision": precision, "steps": steps, "ms_per_step": t_ms / steps, "minibatches_per_sec": sps,
             "seed_nodes_per_sec": sps * loader.batch_size, "mean_sampled_nodes": nodes, "mean_sampled_nnz": nnz,
