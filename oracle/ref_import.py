@@ -126,6 +126,10 @@ def load_reference():
                                                       os.path.join(REFERENCE_ROOT, "scripts", "pred_basis.py"))
         ref_pred = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(ref_pred)
+        # train.py (losses of SURVEY 8 a8; run_exp sits behind `if __name__ == '__main__'`)
+        spec = importlib.util.spec_from_file_location("ref_train", os.path.join(REFERENCE_ROOT, "train.py"))
+        ref_train = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref_train)
     finally:
         sys.path[:] = saved_path
         for k, v in saved_modules.items():
@@ -134,5 +138,5 @@ def load_reference():
             else:
                 sys.modules[k] = v
     _CACHE = types.SimpleNamespace(arch=ref_arch, dataset=ref_dataset, utils=ref_utils,
-                                   val=ref_val, pred_basis=ref_pred, Data=_Data, SparseTensor=S.SparseTensor)
+                                   val=ref_val, pred_basis=ref_pred, train=ref_train, Data=_Data, SparseTensor=S.SparseTensor)
     return _CACHE

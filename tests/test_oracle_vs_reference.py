@@ -209,3 +209,34 @@ def test_inference_gnn_with_ties_nan_and_extreme_k(R):
         assert (got[tie_idx[:k_tie]] == 1).all() and (got[tie_idx[k_tie:]] != 1).all()
 
     check()
+
+
+@pytest.mark.parametrize("labels_s,labels_t", [([0, 1, 1, 2, 2, 2, 1], [1, 0, 0, 2, 0, 1, 1, 0, 2]),
+                                               ([1, 1, 0, 1], [0, 0, 1, 0, 0]),          # two classes: no l/u merge
+                                               ([1, 2, 2, 1, 1], [0, 2, 1, 0, 2, 1])])
+def test_training_losses_match_reference_train_py(R, labels_s, labels_t):
+    """train.py:18-53 (`balanced`, `unbalanced`, `focal`) and utils.py:286-299 (`labels_to_balanced_weights`) of the
+    verbatim reference vs the product's losses.py and the oracle port: values and gradients w.r.t. the logits."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import losses
+    rng = np.random.default_rng(5)
+    y_s, y_t = torch.tensor(labels_s), torch.tensor(labels_t)
+    base_c = torch.from_numpy(rng.standard_normal((len(labels_s), 3)).astype(np.float32) * 4)
+    base_v = torch.from_numpy(rng.standard_normal((len(labels_t), 3)).astype(np.float32) * 4)
+    for y in (y_s, y_t):
+        assert torch.allclose(losses.labels_to_balanced_weights(y), R.utils.labels_to_balanced_weights(y).float())
+
+    def run(fn):
+        lc, lv = base_c.clone().requires_grad_(), base_v.clone().requires_grad_()
+        loss = fn(lc, lv, y_s, y_t)
+        loss.backward()
+        return float(loss), lc.grad.clone(), lv.grad.clone()
+
+    for name in ("balanced", "unbalanced", "focal"):
+        ref = run(getattr(R.train, name))
+        mine = run(losses.LOSSES[name])
+        assert abs(ref[0] - mine[0]) <= 1e-6 * max(1.0, abs(ref[0])), name
+        assert torch.allclose(ref[1], mine[1], rtol=1e-5, atol=1e-7) and torch.allclose(ref[2], mine[2], rtol=1e-5, atol=1e-7), name
+    ref = run(R.train.balanced)
+    got = run(port.balanced_loss)
+    assert abs(ref[0] - got[0]) <= 1e-6 * max(1.0, abs(ref[0])) and torch.allclose(ref[1], got[1], rtol=1e-5, atol=1e-7)
