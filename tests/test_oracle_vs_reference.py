@@ -240,3 +240,19 @@ def test_training_losses_match_reference_train_py(R, labels_s, labels_t):
     ref = run(R.train.balanced)
     got = run(port.balanced_loss)
     assert abs(ref[0] - got[0]) <= 1e-6 * max(1.0, abs(ref[0])) and torch.allclose(ref[1], got[1], rtol=1e-5, atol=1e-7)
+
+
+def test_host_helpers_match_reference_utils(R):
+    """utils.py:256-263 (split_idxs_train_val), 301-309 (extract_fn, including the upstream 'sol' 'txt' literal that
+    fuses into one suffix) vs lpgnn_b200.io_utils."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import io_utils
+    for n in (1, 2, 3, 10, 37, 128):
+        for seed in (0, 3):
+            a, b = R.utils.split_idxs_train_val(n, seed)
+            c, d = io_utils.split_idxs_train_val(n, seed)
+            np.testing.assert_array_equal(a, c)
+            np.testing.assert_array_equal(b, d)
+    for name in ("/a/b/lp7.mps.gz", "x.y.pk", "model.sol", "notes.txt", "a.soltxt", "q.bas.sort", "plain", "d/e.lp.json",
+                 "run.log.tar.gz", "k.1.2.pk"):
+        assert io_utils.extract_fn(name) == R.utils.extract_fn(name), name
