@@ -13,8 +13,8 @@ Contents
                      torch_sparse.SparseTensor 0.6.12, torch_geometric.utils.to_undirected).
                      They are NOT under /root/reference (pinned only in prose,
                      readme.md:51-52), so their published algorithm is restated.
-``ref_import.py``    imports the reference's own arch.py / dataset.py / utils.py / val.py
-                     VERBATIM from /root/reference with the stand-ins injected.  Works only
+``ref_import.py``    imports the reference's own arch.py / dataset.py / utils.py / val.py /
+                     train.py / scripts/pred_basis.py VERBATIM from /root/reference with the stand-ins injected.  Works only
                      where /root/reference exists (the build container); used to validate
                      ``port.py`` and to generate ``tests/golden/*.npz``.
 ``port.py``          standalone CPU restatement (numpy / torch-CPU) of the hot path that
