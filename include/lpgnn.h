@@ -100,11 +100,13 @@ LPGNN_API int lpgnn_graph_build(const void* coo_row, const void* coo_col, int id
 
 /* `count` independent pinned-host -> device copies enqueued on `stream` by one native call (addresses and
  * sizes as host arrays of uint64).  Used to stage a pack of LPs: each LP's arrays go straight to their
- * offsets in the pack. */
+ * offsets in the pack.  Replaces the per-LP `batch_to(batch, dev)` of the reference's prediction sweep
+ * (val.py:31 via scripts/pred_basis.py:153-154, and pred_basis.py:170; utils.py:909-915: five tensor moves per LP). */
 LPGNN_API int lpgnn_copy_many_h2d(const uint64_t* dst_ptrs, const uint64_t* src_ptrs, const uint64_t* nbytes,
                         int32_t count, lpgnn_stream_t stream);
 
-/* Block-diagonal packing of several LPs into one graph (the direct sum of their matrices): the COO entries
+/* Block-diagonal packing of several LPs into one graph (the direct sum of their matrices; what a PyG DataLoader
+ * with batch_size > 1 would produce -- the reference runs batch_size=1, scripts/pred_basis.py:138): the COO entries
  * of LP b occupy [edge_ptr[b], edge_ptr[b+1]) with LP-local indices; this shifts them in place by the LP's
  * first constraint (cons_ptr[b]) / variable (vars_ptr[b]) of the pack.  A pack of row-major sorted LPs is
  * row-major sorted. */
