@@ -783,7 +783,8 @@ def run_reference(args):
         "impl": "reference",
         "metric": "LPs/sec (basis prediction: graph build + GCN_FC forward + basis selection)",
         "value": lps, "unit": "LPs/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(1, min(args.warmup, 3)), "warmup_requested": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": (f"C5: sweep over {len(lps_list)} distinct synthetic LPs (m log-uniform 100..20000, n=2m, "
                                 f"nnz~5n, mean nnz {nnz_mean:.0f}), GCN_FC(8,8,hids={cfg['hids']},depth=3), one LP per step"
