@@ -166,6 +166,8 @@ template <int KT>
 int launch(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const float* Xsrc, int k_src,
            const float* Xdst, int k_dst, const float* W_rel, const float* b_rel, const float* W_root, int N,
            void* out, int out_dtype, int relu, float* z, cudaStream_t st) {
+  LPGNN_REQUIRE(ceil_div(rows, kRows) <= 65535, "conv_in_fused: rows=%d exceeds the %d rows one launch covers", rows,
+                65535 * kRows);
   gather_cat_kernel<KT, __nv_bfloat16><<<ceil_div((int64_t)rows * 8, kThreads), kThreads, 0, st>>>(
       ptr, idx, val, rows, Xsrc, k_src, Xdst, k_dst, z, nullptr);
   dim3 grid(ceil_div(N, kColsPerBlock), ceil_div(rows, kRows));

@@ -116,6 +116,7 @@ int node_transform_f32(const float* A1, int K1, const float* W1, const float* A2
                     (uintptr_t)W2 % 16 == 0,
                 "node_transform(f32): operands must be 16-byte aligned");
   Seg s0{A1, W1, K1}, s1{A2, W2, A2 ? K2 : 0};
+  LPGNN_REQUIRE(ceil_div(M, BM) <= 65535, "node_transform(f32): M=%d exceeds the %d rows one launch covers", M, 65535 * BM);
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
   sgemm_cat_kernel<<<grid, kThreads, 0, st>>>(s0, s1, bias, M, N, out, relu);
   LPGNN_LAUNCH_OK();

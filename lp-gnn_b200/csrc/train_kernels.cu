@@ -376,6 +376,8 @@ extern "C" int lpgnn_transpose(const void* X, int dtype, int64_t M, int64_t N, v
                 (long long)N, (long long)ld_out);
   if (ld_out == 0 || N == 0) return LPGNN_OK;
   LPGNN_REQUIRE(X && out, "transpose: null pointer");
+  LPGNN_REQUIRE(ceil_div(ld_out, 64) <= 65535, "transpose: ld_out=%lld exceeds the %d rows one launch covers",
+                (long long)ld_out, 65535 * 64);
   dim3 grid(ceil_div(N, 64), ceil_div(ld_out, 64));
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == LPGNN_F32) transpose_kernel<float><<<grid, 256, 0, st>>>((const float*)X, M, N, (float*)out, ld_out);
