@@ -132,3 +132,14 @@ def test_bench_reference_arm_prints_the_contract_line():
                           "--steps", "1"], capture_output=True, text=True, timeout=120, env=dict(env, RANK="1", WORLD_SIZE="2"),
                          cwd=root)
     assert out.returncode == 0 and not [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour on a box without a GPU")
+def test_bench_gpu_arm_fails_loudly_without_a_device():
+    """No CPU fallback: the product arm of bench.py must not print a number on a box without a GPU."""
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1", "--no-cpu"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode != 0
+    assert not [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert "CUDA" in out.stderr or "cuda" in out.stderr
