@@ -143,3 +143,29 @@ def test_bench_gpu_arm_fails_loudly_without_a_device():
     assert out.returncode != 0
     assert not [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
     assert "CUDA" in out.stderr or "cuda" in out.stderr
+
+
+def test_ctypes_bindings_match_the_header_signatures():
+    """Every entry point of include/lpgnn.h is bound in _lib.py with explicit argtypes whose count equals the C
+    parameter count (a call through ctypes without argtypes would truncate 64-bit pointers and sizes), and every
+    `size_t` / `uint64_t` / `const char*` return type is declared."""
+    import ctypes
+
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import _lib
+    lib = _lib.load()
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "lpgnn.h")).read(), flags=re.S)
+    seen = 0
+    for m in re.finditer(r"LPGNN_API\s+([\w\s\*]+?)(lpgnn_\w+)\s*\((.*?)\)\s*;", src, flags=re.S):
+        ret, name, params = m.group(1).strip(), m.group(2), m.group(3).strip()
+        n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
+        fn = getattr(lib, name)
+        assert fn.argtypes is not None and len(fn.argtypes) == n, (name, n, fn.argtypes)
+        if ret == "size_t":
+            assert fn.restype is ctypes.c_size_t, name
+        elif ret == "uint64_t":
+            assert fn.restype is ctypes.c_uint64, name
+        elif ret.replace(" ", "") == "constchar*":
+            assert fn.restype is ctypes.c_char_p, name
+        seen += 1
+    assert seen == len(_header_symbols())
