@@ -169,3 +169,21 @@ def test_ctypes_bindings_match_the_header_signatures():
             assert fn.restype is ctypes.c_char_p, name
         seen += 1
     assert seen == len(_header_symbols())
+
+
+def test_integration_md_stubs_match_the_header():
+    """The ctypes stubs a maintainer would copy from INTEGRATION.md declare as many arguments as the header does."""
+    import ctypes as C
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "lpgnn.h")).read(), flags=re.S)
+    hdr = {}
+    for m in re.finditer(r"LPGNN_API\s+[\w\s\*]+?(lpgnn_\w+)\s*\((.*?)\)\s*;", src, flags=re.S):
+        params = m.group(2).strip()
+        hdr[m.group(1)] = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    ns = {"C": C, "_p": C.c_void_p, "_i32": C.c_int32, "_i64": C.c_int64}
+    stubs = re.findall(r"_lib\.(lpgnn_\w+)\.argtypes = (.*)", doc)
+    assert len(stubs) >= 6
+    for name, expr in stubs:
+        assert len(eval(expr, ns)) == hdr[name], name                      # noqa: S307 (repo-owned document)
+    for name in re.findall(r"`(lpgnn_[a-z0-9_]+)`", doc):
+        assert any(h == name or h.startswith(name) for h in hdr), f"INTEGRATION.md names an unknown entry point {name}"
