@@ -219,6 +219,28 @@ LPGNN_API int lpgnn_node_transform_split(int parts, const void* const* A1, int32
                                const float* bias, int32_t M, int32_t N, float* out, int epilogue,
                                lpgnn_stream_t stream);
 
+/* (a3, the reference's DEFAULT precision -- `--fp16 0`, utils.py:770 -- on the tensor cores)  fp32-accurate node
+ * transform from "x2" operands.  lpgnn_split_x2 stores every fp32 row of x1 [rows,K1] (and, with the SAME row scale,
+ * of x2 [rows,K2]; x2 may be NULL with K2 = 0) as two IEEE-half rows and a power-of-two scale:
+ *     x[i,k] = scale[i] * ( hi[i,k] + 2^-11 * lo[i,k] )      (22 significant bits, no overflow for any fp32 row)
+ * lpgnn_node_transform_x2 computes out = epi( A1 W1^T + A2 W2^T + bias ) from such operands (activations with row
+ * scales `rowscale` [M], weights with output-feature scales `colscale` [N]; NULL = 1) as THREE half x half -> fp32
+ * tcgen05 passes (hi*hi + 2^-11 (hi*lo + lo*hi)); a TMEM accumulator only holds a short chunk of the reduction and
+ * the chunks are summed in fp32 registers with round-to-nearest, so the tensor core's truncating accumulation does
+ * not drift (csrc/gemm_x2.cu).  out: f32 [M,N] or NULL; head_w [3,N] / head_partial [nparts][M][3] (optional, as
+ * lpgnn_node_transform_head; finish with lpgnn_head_finish): the fused basis-status head of the last layer.
+ * K1, K2, N multiples of 64.  Replaces lin_rel(agg) + lin_root(x) + relu_ (reference arch.py:75-80, 185-188). */
+LPGNN_API int lpgnn_split_x2(const float* x1, int32_t K1, const float* x2, int32_t K2, int64_t rows,
+                   void* hi1, void* lo1, void* hi2, void* lo2, float* scale, lpgnn_stream_t stream);
+LPGNN_API int lpgnn_node_transform_x2(const void* A1_hi, const void* A1_lo, int32_t K1, const void* W1_hi, const void* W1_lo,
+                            const void* A2_hi, const void* A2_lo, int32_t K2, const void* W2_hi, const void* W2_lo,
+                            const float* rowscale, const float* colscale, const float* bias, int32_t M, int32_t N,
+                            float* out, int epilogue, const float* head_w, float* head_partial,
+                            lpgnn_stream_t stream);
+/* Tuning knob (process-wide): K-blocks of 64 accumulated inside TMEM before a chunk is added to the fp32 registers
+ * (main passes; default 4; the 2^-11-weighted correction passes use 4x that, at least 16).  Returns the previous value. */
+LPGNN_API int lpgnn_set_x2_chunk(int kblocks);
+
 /* (a3+a4, inference) The LAST hidden transform fused with the basis-status head (reference
  * arch.py:185-190): the epilogue also forms, per row, the three dot products of the ReLU'd fp32
  * accumulator row with head_w [3,N] f32 over the tile's columns and writes them to
@@ -308,19 +330,26 @@ typedef struct lpgnn_gcn_fc_weights {
   const float* r2l_b[LPGNN_MAX_HIDDEN_LAYERS];
   /* heads, fp32: lin_left (constraints) / lin_right (variables): weight [3,hids], bias [3] */
   const float *head_left_w, *head_left_b, *head_right_w, *head_right_b;
-  /* fp32 mode on the tensor cores (optional): 3-part bf16 splits of the hidden-layer weights
-   * (lpgnn_split_bf16, parts = 3), indexed [layer][part].  When l2r_wrel_parts[0][0] != NULL and
-   * hids % 64 == 0 the hidden transforms run as lpgnn_node_transform_split(parts = 3); otherwise the
-   * CUDA-core fp32 kernel is used. */
-  const void* l2r_wrel_parts[LPGNN_MAX_HIDDEN_LAYERS][3];
-  const void* l2r_wroot_parts[LPGNN_MAX_HIDDEN_LAYERS][3];
-  const void* r2l_wrel_parts[LPGNN_MAX_HIDDEN_LAYERS][3];
-  const void* r2l_wroot_parts[LPGNN_MAX_HIDDEN_LAYERS][3];
+  /* fp32 mode on the tensor cores (optional): x2 form of the hidden-layer weights, indexed [layer]: IEEE-half hi / lo
+   * parts of W_rel and W_root [hids,hids] and ONE power-of-two scale per output feature shared by the two matrices
+   * (lpgnn_split_x2(W_rel, hids, W_root, hids, rows = hids, ...)).  When l2r_wrel_hi[0] != NULL and hids % 64 == 0 the
+   * hidden transforms of an LPGNN_F32 prediction run as lpgnn_node_transform_x2 (fp32-level accuracy from three
+   * half x half tensor-core passes, chunked accumulation); otherwise the CUDA-core fp32 kernel is used. */
+  const void* l2r_wrel_hi[LPGNN_MAX_HIDDEN_LAYERS];
+  const void* l2r_wrel_lo[LPGNN_MAX_HIDDEN_LAYERS];
+  const void* l2r_wroot_hi[LPGNN_MAX_HIDDEN_LAYERS];
+  const void* l2r_wroot_lo[LPGNN_MAX_HIDDEN_LAYERS];
+  const float* l2r_wscale[LPGNN_MAX_HIDDEN_LAYERS];
+  const void* r2l_wrel_hi[LPGNN_MAX_HIDDEN_LAYERS];
+  const void* r2l_wrel_lo[LPGNN_MAX_HIDDEN_LAYERS];
+  const void* r2l_wroot_hi[LPGNN_MAX_HIDDEN_LAYERS];
+  const void* r2l_wroot_lo[LPGNN_MAX_HIDDEN_LAYERS];
+  const float* r2l_wscale[LPGNN_MAX_HIDDEN_LAYERS];
 } lpgnn_gcn_fc_weights;
 
-/* precision: LPGNN_F32, LPGNN_BF16, or LPGNN_F32 | LPGNN_WS_X3 to reserve the split buffers of the fp32
- * tensor-core mode. */
-#define LPGNN_WS_X3 16
+/* precision: LPGNN_F32, LPGNN_BF16, LPGNN_F16, or LPGNN_F32 | LPGNN_WS_X2 to reserve the x2 operand buffers of the
+ * fp32 tensor-core mode. */
+#define LPGNN_WS_X2 16
 LPGNN_API size_t lpgnn_predict_workspace_bytes(int64_t nnz, int32_t m, int32_t n, int32_t p, int32_t q,
                                      int32_t hids, int32_t depth, int precision);
 LPGNN_API int lpgnn_predict_basis(const lpgnn_gcn_fc_weights* w, const int32_t* coo_row, const int32_t* coo_col,

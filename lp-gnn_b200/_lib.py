@@ -20,7 +20,7 @@ F16 = 2      # IEEE half storage (the reference's --fp16 mode): inference entry 
 EPI_NONE, EPI_RELU = 0, 1
 COO_SORTED = 1
 GRAPH_MEAN = 4
-WS_X3 = 16
+WS_X2 = 16
 
 _p = C.c_void_p
 _i32, _i64, _sz, _int = C.c_int32, C.c_int64, C.c_size_t, C.c_int
@@ -35,8 +35,8 @@ class GcnFcWeights(C.Structure):
                                      "c1_l2r_wcat", "c1_r2l_wcat")]
                 + [(k, _p * MAX_HIDDEN_LAYERS) for k in ("l2r_wrel", "l2r_wroot", "l2r_b", "r2l_wrel", "r2l_wroot", "r2l_b")]
                 + [(k, _p) for k in ("head_left_w", "head_left_b", "head_right_w", "head_right_b")]
-                + [(k, (_p * 3) * MAX_HIDDEN_LAYERS) for k in ("l2r_wrel_parts", "l2r_wroot_parts", "r2l_wrel_parts",
-                                                               "r2l_wroot_parts")])
+                + [(f"{d}_{k}", _p * MAX_HIDDEN_LAYERS) for d in ("l2r", "r2l")
+                   for k in ("wrel_hi", "wrel_lo", "wroot_hi", "wroot_lo", "wscale")])
 
 
 class EpilogueArgs(C.Structure):
@@ -73,6 +73,9 @@ SIGNATURES = {
     "lpgnn_gather_cat_ex": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _int, _p]),
     "lpgnn_node_transform_head_ex": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _int, _p, _p, _p]),
     "lpgnn_node_transform_split": (_int, [_int, _p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _p]),
+    "lpgnn_split_x2": (_int, [_p, _i32, _p, _i32, _i64, _p, _p, _p, _p, _p, _p]),
+    "lpgnn_node_transform_x2": (_int, [_p, _p, _i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _p, _int, _p, _p, _p]),
+    "lpgnn_set_x2_chunk": (_int, [_int]),
     "lpgnn_node_transform_head_parts": (_i32, [_i32]),
     "lpgnn_node_transform_head": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _p, _p, _p]),
     "lpgnn_head_finish": (_int, [_p, _i32, _i32, _p, _p, _i32, _p, _p]),

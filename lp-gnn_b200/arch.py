@@ -136,21 +136,24 @@ class GCN_FC(GCNBase):
 
     # -- precision switches ----------------------------------------------------------------
     def set_precision(self, precision: str):
-        """'fp32'    strict-parity mode: fp32 CUDA-core transforms (logits within 1e-4 of the reference);
-        'fp32_tc' fp32 storage, hidden transforms as six bf16 tensor-core passes over 3-part splits (~4x faster;
-                  relative Frobenius error ~1e-5, worst logit entry ~3e-4 of the row norm at C2 size because the
-                  tensor core's fp32 accumulation truncates);
-        'bf16'    bf16 storage and single-pass tensor-core transforms (within 2e-2);
-        'fp16'    IEEE half storage, the same tensor-core kernels at the same rate (fp32 accumulate): logits within
-                  ~2e-3, statuses agree with fp32 on >= 99.9 % of the nodes.  Inference only, like the reference's
-                  `--fp16` (val.py:269): activations must stay below 65504, which scaled LPs (|A|, |c| <= 1) do."""
-        if precision not in ("fp32", "fp32_tc", "bf16", "fp16"):
-            raise ValueError("precision must be 'fp32', 'fp32_tc', 'bf16' or 'fp16'")
-        if precision != "fp32" and self.hids % 64 != 0:
-            raise ValueError("tensor-core modes need hids to be a multiple of 64 (tensor-core tile)")
+        """'fp32'      the reference's default arithmetic (`--fp16 0`, utils.py:770): fp32 storage; hidden transforms on the
+                    tensor cores from x2 operands (three half x half passes, chunked fp32 accumulation: logits within
+                    1e-4 of the reference, csrc/gemm_x2.cu) when hids % 64 == 0, else the CUDA-core kernel;
+        'fp32_simt' fp32 storage, every transform on the CUDA cores (csrc/gemm_simt.cu; the cross-check of 'fp32');
+        'fp32_tc'   alias of 'fp32' (the name of round 1's tensor-core fp32 mode);
+        'bf16'      bf16 storage and single-pass tensor-core transforms (within 2e-2);
+        'fp16'      IEEE half storage, the same tensor-core kernels at the same rate (fp32 accumulate): logits within
+                    ~2e-3, statuses agree with fp32 on >= 99.9 % of the nodes.  Inference only, like the reference's
+                    `--fp16` (val.py:269): activations must stay below 65504, which scaled LPs (|A|, |c| <= 1) do."""
+        if precision == "fp32_tc":
+            precision = "fp32"
+        if precision not in ("fp32", "fp32_simt", "bf16", "fp16"):
+            raise ValueError("precision must be 'fp32', 'fp32_simt', 'bf16' or 'fp16'")
+        if precision in ("bf16", "fp16") and self.hids % 64 != 0:
+            raise ValueError("16-bit modes need hids to be a multiple of 64 (tensor-core tile)")
         self.precision = precision
         for conv in self.layers:
-            conv.fp32_tensor_cores = precision == "fp32_tc"
+            conv.fp32_cuda_cores = precision == "fp32_simt"
         return self
 
     def half(self):       # reference `--fp16`: model.half() (val.py:269, pred_basis.py:146)
@@ -203,18 +206,18 @@ class GCN_FC(GCNBase):
                 wc = wcat_bf16(c1._cache, gc, dt)
                 keep.append(wc)
                 setattr(w, f"c1_{tag}_wcat", wc.data_ptr())
-        from .autograd import split_cached, use_x3
+        from .autograd import use_x2, x2_weights_cached
         for i, conv in enumerate(self.layers):
             for tag, gc in (("l2r", conv.left2right), ("r2l", conv.right2left)):
                 getattr(w, f"{tag}_wrel")[i] = cd(gc.lin_rel.weight)
                 getattr(w, f"{tag}_wroot")[i] = cd(gc.lin_root.weight)
                 getattr(w, f"{tag}_b")[i] = f32(gc.lin_rel.bias)
-                if not bf16 and use_x3(conv):
-                    for nm, par in (("wrel", gc.lin_rel.weight), ("wroot", gc.lin_root.weight)):
-                        parts = split_cached(conv._cache, par)
-                        keep.extend(parts)
-                        for k, t in enumerate(parts):
-                            getattr(w, f"{tag}_{nm}_parts")[i][k] = t.data_ptr()
+                if not bf16 and use_x2(conv):
+                    wrel, wroot, wscale = x2_weights_cached(conv._cache, gc)
+                    keep.extend([*wrel, *wroot, wscale])
+                    getattr(w, f"{tag}_wrel_hi")[i], getattr(w, f"{tag}_wrel_lo")[i] = wrel[0].data_ptr(), wrel[1].data_ptr()
+                    getattr(w, f"{tag}_wroot_hi")[i], getattr(w, f"{tag}_wroot_lo")[i] = wroot[0].data_ptr(), wroot[1].data_ptr()
+                    getattr(w, f"{tag}_wscale")[i] = wscale.data_ptr()
         w.head_left_w, w.head_left_b = f32(self.lin_left.weight), f32(self.lin_left.bias)
         w.head_right_w, w.head_right_b = f32(self.lin_right.weight), f32(self.lin_right.bias)
         self._native_cache = (ver, w, keep)
@@ -235,8 +238,8 @@ class GCN_FC(GCNBase):
         w = self._native_weights()
         dev = x_s.device
         z = int(row.shape[0])
-        x3 = _lib.WS_X3 if (w.precision == _lib.F32 and w.depth > 2 and w.l2r_wrel_parts[0][0]) else 0
-        ws_bytes = lib.lpgnn_predict_workspace_bytes(z, m, n, w.p, w.q, w.hids, w.depth, w.precision | x3)
+        x2 = _lib.WS_X2 if (w.precision == _lib.F32 and w.depth > 2 and w.l2r_wrel_hi[0]) else 0
+        ws_bytes = lib.lpgnn_predict_workspace_bytes(z, m, n, w.p, w.q, w.hids, w.depth, w.precision | x2)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         status = torch.empty(m + n, dtype=torch.uint8, device=dev)
         logits = torch.empty((m + n, 3), dtype=torch.float32, device=dev) if want_logits else None
@@ -265,8 +268,8 @@ class GCN_FC(GCNBase):
         w = self._native_weights()
         dev = x_s.device
         z = int(row.shape[0])
-        x3 = _lib.WS_X3 if (w.precision == _lib.F32 and w.depth > 2 and w.l2r_wrel_parts[0][0]) else 0
-        ws_bytes = lib.lpgnn_predict_workspace_bytes(z, m, n, w.p, w.q, w.hids, w.depth, w.precision | x3)
+        x2 = _lib.WS_X2 if (w.precision == _lib.F32 and w.depth > 2 and w.l2r_wrel_hi[0]) else 0
+        ws_bytes = lib.lpgnn_predict_workspace_bytes(z, m, n, w.p, w.q, w.hids, w.depth, w.precision | x2)
         if buffers is not None:
             # caller-owned grow-only buffers (a sweep must not go through cudaMalloc for every new pack size):
             # buffers = {"ws": uint8 tensor or None, "status": uint8 tensor or None}, replaced in place when too small

@@ -35,39 +35,57 @@ def _check_graph(g):
 # --------------------------------------------------------------------------------------------------
 # inference path
 # --------------------------------------------------------------------------------------------------
-def split_cached(conv_cache, p):
-    """3-part bf16 split of an fp32 weight, cached per parameter version."""
-    key = ("split", id(p))
+def x2_weights_cached(conv_cache, gc):
+    """x2 form of one GraphConv's hidden weights, cached per parameter version: ``((rel_hi, rel_lo), (root_hi, root_lo),
+    colscale[N])`` with one power-of-two scale per output feature shared by W_rel and W_root."""
+    key = ("x2", id(gc))
+    ver = (gc.lin_rel.weight._version, gc.lin_root.weight._version, gc.lin_rel.weight.device)
     hit = conv_cache._c.get(key)
-    if hit is not None and hit[0] == (p._version, p.device):
+    if hit is not None and hit[0] == ver:
         return hit[1]
-    pair = ops.split_bf16(p.detach(), parts=3)
-    conv_cache._c[key] = ((p._version, p.device), pair)
-    return pair
+    trip = ops.split_x2(gc.lin_rel.weight.detach(), gc.lin_root.weight.detach())
+    conv_cache._c[key] = (ver, trip)
+    return trip
 
 
-def use_x3(conv) -> bool:
-    """'fp32_tc' mode: hidden transforms as six bf16 tensor-core passes over 3-part splits (products exact to
-    ~2^-24; the result is limited by the tensor core's truncating fp32 accumulation) when the shape allows it."""
+def use_x2(conv) -> bool:
+    """'fp32' mode on the tensor cores: hidden transforms as three half x half passes over x2 operands with chunked
+    accumulation (``ops.node_transform_x2``) when the shape allows it; ``conv.fp32_cuda_cores`` forces the CUDA-core
+    kernel ('fp32_simt')."""
     gc = conv.left2right
     return gc.in_channels[0] % 64 == 0 and gc.in_channels[1] % 64 == 0 and gc.out_channels % 64 == 0 \
-        and getattr(conv, "fp32_tensor_cores", False)
+        and not getattr(conv, "fp32_cuda_cores", False)
+
+
+def _conv_hidden_x2(conv, left, right, csr, csc, relu, heads=None):
+    """One hidden layer in the fp32 tensor-core mode.  ``heads = ((w, b, feas)_left, (w, b, feas)_right)`` fuses the
+    basis-status heads (last layer): returns the logits instead of the activations."""
+    l2r, r2l = conv.left2right, conv.right2left
+    agg_t = ops.spmm(csc, left)     # [n,H]  A^T . left
+    agg_s = ops.spmm(csr, right)    # [m,H]  A   . right
+    at, xt, st = ops.split_x2(agg_t, right)
+    as_, xs, ss = ops.split_x2(agg_s, left)
+    wrel_t, wroot_t, cs_t = x2_weights_cached(conv._cache, l2r)
+    wrel_s, wroot_s, cs_s = x2_weights_cached(conv._cache, r2l)
+    if heads is not None:
+        _, logit_t = ops.node_transform_x2(at, wrel_t, xt, wroot_t, st, cs_t, l2r.lin_rel.bias.detach(), relu=relu,
+                                           head=heads[1], want_out=False)
+        _, logit_s = ops.node_transform_x2(as_, wrel_s, xs, wroot_s, ss, cs_s, r2l.lin_rel.bias.detach(), relu=relu,
+                                           head=heads[0], want_out=False)
+        return logit_s, logit_t
+    right_new = ops.node_transform_x2(at, wrel_t, xt, wroot_t, st, cs_t, l2r.lin_rel.bias.detach(), relu=relu)
+    left_new = ops.node_transform_x2(as_, wrel_s, xs, wroot_s, ss, cs_s, r2l.lin_rel.bias.detach(), relu=relu)
+    return left_new, right_new
 
 
 def _conv_hidden_infer(conv, left, right, csr, csc, relu):
     dt = left.dtype
     cast = conv._cache.get
     l2r, r2l = conv.left2right, conv.right2left
+    if dt == torch.float32 and use_x2(conv):
+        return _conv_hidden_x2(conv, left, right, csr, csc, relu)
     agg_t = ops.spmm(csc, left)     # [n,H]  A^T . left
     agg_s = ops.spmm(csr, right)    # [m,H]  A   . right
-    if dt == torch.float32 and use_x3(conv):
-        sp = lambda p: split_cached(conv._cache, p)
-        left_p, right_p = ops.split_bf16(left), ops.split_bf16(right)
-        right_new = ops.node_transform_split(ops.split_bf16(agg_t), sp(l2r.lin_rel.weight), right_p,
-                                             sp(l2r.lin_root.weight), l2r.lin_rel.bias.detach(), relu=relu)
-        left_new = ops.node_transform_split(ops.split_bf16(agg_s), sp(r2l.lin_rel.weight), left_p,
-                                            sp(r2l.lin_root.weight), r2l.lin_rel.bias.detach(), relu=relu)
-        return left_new, right_new
     right_new = ops.node_transform(agg_t, cast(l2r.lin_rel.weight, dt), right, cast(l2r.lin_root.weight, dt),
                                    l2r.lin_rel.bias.detach(), relu=relu)
     left_new = ops.node_transform(agg_s, cast(r2l.lin_rel.weight, dt), left, cast(r2l.lin_root.weight, dt),
@@ -155,6 +173,10 @@ def gcn_fc_forward(model, x_s, x_t, graph):
                                                  r2l.lin_rel.bias.detach(), model.lin_left.weight.detach(),
                                                  model.lin_left.bias.detach(), x_s)
             return logit_s, logit_t
+        if li == n_layers - 1 and dt == torch.float32 and use_x2(conv):
+            heads = ((model.lin_left.weight.detach(), model.lin_left.bias.detach(), x_s),
+                     (model.lin_right.weight.detach(), model.lin_right.bias.detach(), x_t))
+            return _conv_hidden_x2(conv, left, right, csr, csc, True, heads=heads)
         left, right = _conv_hidden_infer(conv, left, right, csr, csc, relu=True)
     logit_s, _ = ops.head_mask(left, model.lin_left.weight.detach(), model.lin_left.bias.detach(), x_s)
     logit_t, _ = ops.head_mask(right, model.lin_right.weight.detach(), model.lin_right.bias.detach(), x_t)

@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tma_host.cuh"
 
 #include <type_traits>
 
@@ -379,35 +380,9 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
 }
 
 // ---------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// [rows, K] bf16 row-major, box = [box_rows, 64], 128-byte swizzle, OOB rows read as zero.
+// [rows, K] bf16 / half row-major, box = [box_rows, 64], 128-byte swizzle, OOB rows read as zero.
 int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int box_rows, bool f16 = false) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) { set_error("node_transform(bf16): cuTensorMapEncodeTiled unavailable"); return LPGNN_ECUDA; }
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
-                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("node_transform(bf16): cuTensorMapEncodeTiled failed (%d)", (int)r); return LPGNN_ECUDA; }
-  return LPGNN_OK;
+  return make_map_16bit(map, base, rows, K, K, box_rows, f16, "node_transform(bf16)");
 }
 
 template <int BN, typename OutT, bool kMN, int kEpi>

@@ -37,14 +37,16 @@ struct Buffers {
   void *zb_s, *zb_t;         // bf16 [m,64], [n,64] (bf16 mode)
   void *act[2][2];           // ping-pong activations: act[i][0] = left [m,H], act[i][1] = right [n,H]
   void *agg_s, *agg_t;       // [m,H], [n,H]
-  void *sp[4][3];            // fp32 tensor-core mode: 3-part bf16 splits of left, right, agg_s, agg_t
+  // fp32 tensor-core mode: x2 operands (half hi / lo) of the aggregate and of the node's own features, row scales
+  void *xa_hi[2], *xa_lo[2], *xx_hi[2], *xx_lo[2];   // [0] = constraint side [m,H], [1] = variable side [n,H]
+  float* xscale[2];
   float *part_s, *part_t;    // fused-head partials
   float *logit_s, *logit_t;  // [m,3], [n,3]
   void* sel_ws; size_t sel_ws_bytes;
 };
 
 size_t carve(Bump& b, Buffers& B, int64_t z, int32_t m, int32_t n, int32_t p, int32_t q, int32_t H, int32_t depth,
-             int bf16, int x3) {
+             int bf16, int x2) {
   const size_t es = bf16 ? 2 : 4;
   B.rowptr = b.take<int32_t>((size_t)m + 1);
   B.colptr = b.take<int32_t>((size_t)n + 1);
@@ -66,7 +68,7 @@ size_t carve(Bump& b, Buffers& B, int64_t z, int32_t m, int32_t n, int32_t p, in
     B.act[i][0] = i < n_act ? b.take<char>((size_t)m * H * es) : nullptr;
     B.act[i][1] = i < n_act ? b.take<char>((size_t)n * H * es) : nullptr;
   }
-  if (!bf16 && depth > 2 && n_act == 1) {  // fp32 mode has no fused head: the last layer's output is materialised
+  if (!bf16 && !x2 && depth > 2 && n_act == 1) {  // CUDA-core fp32 mode has no fused head: the last layer's output is materialised
     B.act[1][0] = b.take<char>((size_t)m * H * es);
     B.act[1][1] = b.take<char>((size_t)n * H * es);
   }
@@ -75,9 +77,13 @@ size_t carve(Bump& b, Buffers& B, int64_t z, int32_t m, int32_t n, int32_t p, in
   } else {
     B.agg_s = B.agg_t = nullptr;
   }
-  for (int i = 0; i < 4; ++i)
-    for (int j = 0; j < 3; ++j)
-      B.sp[i][j] = (x3 && depth > 2) ? b.take<char>((size_t)((i & 1) ? n : m) * H * 2) : nullptr;
+  for (int i = 0; i < 2; ++i) {
+    const size_t rows = i ? n : m;
+    const bool on = x2 && depth > 2;
+    B.xa_hi[i] = on ? b.take<char>(rows * H * 2) : nullptr; B.xa_lo[i] = on ? b.take<char>(rows * H * 2) : nullptr;
+    B.xx_hi[i] = on ? b.take<char>(rows * H * 2) : nullptr; B.xx_lo[i] = on ? b.take<char>(rows * H * 2) : nullptr;
+    B.xscale[i] = on ? b.take<float>(rows) : nullptr;
+  }
   const int nparts = lpgnn_node_transform_head_parts(H);
   B.part_s = b.take<float>((size_t)nparts * m * 3); B.part_t = b.take<float>((size_t)nparts * n * 3);
   B.logit_s = b.take<float>((size_t)m * 3); B.logit_t = b.take<float>((size_t)n * 3);
@@ -93,7 +99,7 @@ extern "C" size_t lpgnn_predict_workspace_bytes(int64_t nnz, int32_t m, int32_t 
   Bump b(nullptr, ~(size_t)0);
   Buffers B;
   return carve(b, B, nnz > 0 ? nnz : 1, m, n, p, q, hids, depth, is_16bit(precision & 15),
-               (precision & LPGNN_WS_X3) != 0);
+               (precision & LPGNN_WS_X2) != 0);
 }
 
 extern "C" int lpgnn_predict_basis(const lpgnn_gcn_fc_weights* w, const int32_t* coo_row, const int32_t* coo_col,
@@ -117,13 +123,13 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
   LPGNN_REQUIRE(dtype_ok(w->precision), "predict_basis: bad precision %d", w->precision);
   LPGNN_REQUIRE(depth >= 2 && depth - 2 <= LPGNN_MAX_HIDDEN_LAYERS, "predict_basis: depth %d unsupported", depth);
   LPGNN_REQUIRE(!bf16 || H % 64 == 0, "predict_basis: bf16 mode needs hids %% 64 == 0");
-  const int x3 = !bf16 && depth > 2 && H % 64 == 0 && w->l2r_wrel_parts[0][0] != nullptr;
-  const size_t need = lpgnn_predict_workspace_bytes(nnz, m, n, p, q, H, depth, w->precision | (x3 ? LPGNN_WS_X3 : 0));
+  const int x2 = !bf16 && depth > 2 && H % 64 == 0 && w->l2r_wrel_hi[0] != nullptr;
+  const size_t need = lpgnn_predict_workspace_bytes(nnz, m, n, p, q, H, depth, w->precision | (x2 ? LPGNN_WS_X2 : 0));
   if (workspace_bytes < need) { set_error("predict_basis: workspace %zu < required %zu", workspace_bytes, need); return LPGNN_EWORKSPACE; }
   LPGNN_REQUIRE((uintptr_t)workspace % 256 == 0, "predict_basis: workspace must be 256-byte aligned");
   Bump b(workspace, workspace_bytes);
   Buffers B;
-  carve(b, B, nnz > 0 ? nnz : 1, m, n, p, q, H, depth, bf16, x3);
+  carve(b, B, nnz > 0 ? nnz : 1, m, n, p, q, H, depth, bf16, x2);
   cudaStream_t st = (cudaStream_t)stream;
   int32_t* gstat = graph_status ? graph_status : B.status;
   if (!graph_status) LPGNN_CUDA_OK(cudaMemsetAsync(B.status, 0, sizeof(int32_t), st));
@@ -165,18 +171,28 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
       LPGNN_TRY(lpgnn_head_finish(B.part_t, nparts, n, w->head_right_b, x_t, q, B.logit_t, stream));
       LPGNN_TRY(lpgnn_head_finish(B.part_s, nparts, m, w->head_left_b, x_s, p, B.logit_s, stream));
       head_done = true;
-    } else if (x3) {  // fp32 accuracy from six bf16 tensor-core passes over 3-part splits
-      void *nl = B.act[cur ^ 1][0], *nr = B.act[cur ^ 1][1];
-      const int64_t cm = (int64_t)m * H, cn = (int64_t)n * H;
-      LPGNN_TRY(lpgnn_split_bf16((const float*)left, cm, 3, B.sp[0], stream));
-      LPGNN_TRY(lpgnn_split_bf16((const float*)right, cn, 3, B.sp[1], stream));
-      LPGNN_TRY(lpgnn_split_bf16((const float*)B.agg_s, cm, 3, B.sp[2], stream));
-      LPGNN_TRY(lpgnn_split_bf16((const float*)B.agg_t, cn, 3, B.sp[3], stream));
-      LPGNN_TRY(lpgnn_node_transform_split(3, B.sp[3], H, w->l2r_wrel_parts[li], B.sp[1], H, w->l2r_wroot_parts[li],
-                                           w->l2r_b[li], n, H, (float*)nr, LPGNN_EPI_RELU, stream));
-      LPGNN_TRY(lpgnn_node_transform_split(3, B.sp[2], H, w->r2l_wrel_parts[li], B.sp[0], H, w->r2l_wroot_parts[li],
-                                           w->r2l_b[li], m, H, (float*)nl, LPGNN_EPI_RELU, stream));
-      left = nl; right = nr; cur ^= 1;
+    } else if (x2) {  // the reference's default precision on the tensor cores: three half x half passes over x2 operands
+      LPGNN_TRY(lpgnn_split_x2((const float*)B.agg_s, H, (const float*)left, H, m, B.xa_hi[0], B.xa_lo[0], B.xx_hi[0],
+                               B.xx_lo[0], B.xscale[0], stream));
+      LPGNN_TRY(lpgnn_split_x2((const float*)B.agg_t, H, (const float*)right, H, n, B.xa_hi[1], B.xa_lo[1], B.xx_hi[1],
+                               B.xx_lo[1], B.xscale[1], stream));
+      void *nl = last ? nullptr : B.act[cur ^ 1][0], *nr = last ? nullptr : B.act[cur ^ 1][1];
+      LPGNN_TRY(lpgnn_node_transform_x2(B.xa_hi[1], B.xa_lo[1], H, w->l2r_wrel_hi[li], w->l2r_wrel_lo[li], B.xx_hi[1],
+                                        B.xx_lo[1], H, w->l2r_wroot_hi[li], w->l2r_wroot_lo[li], B.xscale[1],
+                                        w->l2r_wscale[li], w->l2r_b[li], n, H, (float*)nr, LPGNN_EPI_RELU,
+                                        last ? w->head_right_w : nullptr, last ? B.part_t : nullptr, stream));
+      LPGNN_TRY(lpgnn_node_transform_x2(B.xa_hi[0], B.xa_lo[0], H, w->r2l_wrel_hi[li], w->r2l_wrel_lo[li], B.xx_hi[0],
+                                        B.xx_lo[0], H, w->r2l_wroot_hi[li], w->r2l_wroot_lo[li], B.xscale[0],
+                                        w->r2l_wscale[li], w->r2l_b[li], m, H, (float*)nl, LPGNN_EPI_RELU,
+                                        last ? w->head_left_w : nullptr, last ? B.part_s : nullptr, stream));
+      if (last) {
+        const int nparts = lpgnn_node_transform_head_parts(H);
+        LPGNN_TRY(lpgnn_head_finish(B.part_t, nparts, n, w->head_right_b, x_t, q, B.logit_t, stream));
+        LPGNN_TRY(lpgnn_head_finish(B.part_s, nparts, m, w->head_left_b, x_s, p, B.logit_s, stream));
+        head_done = true;
+      } else {
+        left = nl; right = nr; cur ^= 1;
+      }
     } else {
       void *nl = B.act[cur ^ 1][0], *nr = B.act[cur ^ 1][1];
       LPGNN_TRY(lpgnn_node_transform(B.agg_t, H, w->l2r_wrel[li], right, H, w->l2r_wroot[li], w->l2r_b[li], n, H, nr, dt,

@@ -184,6 +184,74 @@ def node_transform_split(a1, w1, a2=None, w2=None, bias=None, relu=False):
     return out
 
 
+def split_x2(x1, x2=None):
+    """fp32 rows -> x2 operands of ``node_transform_x2``: ``x[i,k] = scale[i] * (hi[i,k] + 2^-11 lo[i,k])`` with IEEE-half
+    ``hi`` / ``lo`` and one power-of-two scale per row shared by ``x1 [rows,K1]`` and ``x2 [rows,K2]``.
+    Returns ``((hi1, lo1), (hi2, lo2) | None, scale[rows])``."""
+    require_cuda(x1, x2)
+    x1 = _contig(x1.float())
+    rows, K1 = x1.shape
+    K2 = 0
+    if x2 is not None:
+        x2 = _contig(x2.float())
+        if x2.shape[0] != rows:
+            raise ValueError("split_x2: x1 and x2 must have the same number of rows")
+        K2 = x2.shape[1]
+    h = lambda K: torch.empty((rows, K), dtype=torch.float16, device=x1.device)
+    p1 = (h(K1), h(K1))
+    p2 = (h(K2), h(K2)) if x2 is not None else None
+    scale = torch.empty(rows, dtype=torch.float32, device=x1.device)
+    with torch.cuda.device(x1.device):
+        rc = _lib.load().lpgnn_split_x2(x1.data_ptr(), K1, ptr(x2), K2, rows, p1[0].data_ptr(), p1[1].data_ptr(),
+                                        ptr(p2[0]) if p2 else None, ptr(p2[1]) if p2 else None, scale.data_ptr(),
+                                        stream_ptr())
+    check(rc, "lpgnn_split_x2")
+    return p1, p2, scale
+
+
+def node_transform_x2(a1, w1, a2=None, w2=None, rowscale=None, colscale=None, bias=None, relu=False, head=None,
+                      want_out=True):
+    """fp32-accurate ``epi(a1 w1^T + a2 w2^T + bias)`` on the tensor cores from x2 operands (``split_x2`` pairs
+    ``(hi, lo)``; three half x half passes, chunked accumulation: csrc/gemm_x2.cu).  ``head=(head_w, head_b, feas)``
+    fuses the basis-status head + knowledge masking of the last layer and returns ``(out | None, logits[M,3])``."""
+    require_cuda(*a1, *w1, rowscale, colscale, bias)
+    M, K1 = a1[0].shape
+    N = w1[0].shape[0]
+    K2 = a2[0].shape[1] if a2 is not None else 0
+    dev = a1[0].device
+    if bias is not None:
+        bias = _contig(bias.float())
+    lib = _lib.load()
+    out = torch.empty((M, N), dtype=torch.float32, device=dev) if want_out else None
+    partial = head_w = None
+    if head is not None:
+        head_w, head_b, feas = (_contig(t.float()) for t in head)
+        require_cuda(head_w, head_b, feas)
+        nparts = lib.lpgnn_node_transform_head_parts(N)
+        partial = torch.empty((nparts, M, 3), dtype=torch.float32, device=dev)
+    elif not want_out:
+        raise ValueError("node_transform_x2: nothing to compute (no output, no head)")
+    with torch.cuda.device(dev):
+        rc = lib.lpgnn_node_transform_x2(a1[0].data_ptr(), a1[1].data_ptr(), K1, w1[0].data_ptr(), w1[1].data_ptr(),
+                                         ptr(a2[0]) if a2 else None, ptr(a2[1]) if a2 else None, K2,
+                                         ptr(w2[0]) if w2 else None, ptr(w2[1]) if w2 else None, ptr(rowscale),
+                                         ptr(colscale), ptr(bias), M, N, ptr(out), EPI_RELU if relu else EPI_NONE,
+                                         ptr(head_w), ptr(partial), stream_ptr())
+        check(rc, "lpgnn_node_transform_x2")
+        if head is None:
+            return out
+        logits = torch.empty((M, 3), dtype=torch.float32, device=dev)
+        rc = lib.lpgnn_head_finish(partial.data_ptr(), nparts, M, head_b.data_ptr(), feas.data_ptr(), feas.shape[1],
+                                   logits.data_ptr(), stream_ptr())
+    check(rc, "lpgnn_head_finish")
+    return out, logits
+
+
+def set_x2_chunk(kblocks: int) -> int:
+    """Tuning knob of ``node_transform_x2`` (K-blocks of 64 per TMEM chunk); returns the previous value."""
+    return _lib.load().lpgnn_set_x2_chunk(int(kblocks))
+
+
 def head_mask(h, w, b, feas, want_raw=False):
     """Linear(H,3) + add_knowledge in one pass (reference arch.py:190-191, 129-141).
     Returns ``(logits[rows,3] f32, raw[rows,3] f32 | None)``."""

@@ -1,6 +1,6 @@
 """End-to-end GCN_FC forward through the drop-in arch module vs the oracle port (same weights, same
 inputs): fp32 logits within 1e-4 relative to the row norm 10, 16-bit modes within 2e-2, status agreement >= 99.9 %
-(fp32, fp32_tc, fp16; bf16 reaches ~99.8 % on random-initialised weights and is asserted at 98 %)."""
+(fp32 on the tensor cores, fp32_simt, fp16; bf16 reaches ~99.8 % on random-initialised weights and is asserted at 98 %)."""
 import types
 
 import numpy as np
@@ -120,8 +120,8 @@ def test_state_dict_keys_and_checkpoint_roundtrip(cuda, tmp_path):
 
 
 @pytest.mark.parametrize("hids,depth,precision", [(64, 2, "fp32"), (128, 3, "fp32"), (128, 3, "bf16"), (64, 4, "bf16"),
-                                                    (64, 5, "fp32"), (1024, 3, "bf16"), (128, 3, "fp32_tc"),
-                                                    (64, 4, "fp32_tc"), (1024, 3, "fp16"), (64, 2, "fp16"),
+                                                    (64, 5, "fp32"), (1024, 3, "bf16"), (128, 3, "fp32_simt"),
+                                                    (64, 4, "fp32_simt"), (1024, 3, "fp32"), (1024, 3, "fp16"), (64, 2, "fp16"),
                                                     (128, 4, "fp16")])
 def test_native_one_call_prediction_matches_op_by_op_path(cuda, hids, depth, precision):
     """lpgnn_predict_basis (graph build + forward + selection enqueued from C++) == the Python-orchestrated path."""
@@ -147,7 +147,7 @@ def test_native_one_call_prediction_matches_op_by_op_path(cuda, hids, depth, pre
     assert int(model.last_graph_status.item()) & 1
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp32_tc", "bf16", "fp16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp32_simt", "bf16", "fp16"])
 def test_full_size_c2_parity_against_oracle(cuda, precision):
     """BASELINE config C2 at full size (50K x 100K, ~491K nnz, hids 1024, depth 3): logits and statuses of the
     one-call native path vs the CPU oracle port on the same LP and weights."""
@@ -169,11 +169,9 @@ def test_full_size_c2_parity_against_oracle(cuda, precision):
     agree = np.mean(st == port.inference_gnn_np(exp, lp.m))
     print(f"C2 {precision}: max err/10 = {d.max():.3e}, fro = {fro:.3e}, status agreement = {agree:.5f}")
     assert int((st == 1).sum()) == lp.m
-    if precision == "fp32":                       # strict-parity mode (north_star: fp32 logits within 1e-4)
-        assert d.max() < 1e-4, d.max()
+    if precision in ("fp32", "fp32_simt"):        # north_star: fp32 logits within 1e-4 -- on the tensor cores ('fp32':
+        assert d.max() < 1e-4, d.max()            # x2 operands, chunked accumulation) and on the CUDA cores alike
         assert agree >= 0.999
-    elif precision == "fp32_tc":                  # six bf16 tensor-core passes: bounded by the truncating accumulation
-        assert fro < 1e-4 and d.max() < 1e-3 and agree >= 0.999
     elif precision == "fp16":                     # half storage: every entry within 2e-2 of the row norm... and 99.9 %
         assert fro < 2.5e-3 and np.mean(d < 2e-2) >= 0.9999 and d.max() < 5e-2 and agree >= 0.999
     else:

@@ -154,6 +154,113 @@ def test_transform_fp32_via_split_bf16_tensor_core_passes(cuda, M, N, K1, K2, pa
     assert float((y - y_simt).abs().max()) < 2e-4 * max(1.0, float(e.abs().max()))
 
 
+def test_split_x2_is_a_22_bit_power_of_two_scaled_representation(cuda):
+    """x = scale * (hi + 2^-11 lo): scale is a power of two per row, shared by the two tensors of a call; the
+    reconstruction error is 2^-22 of the element (huge and tiny rows alike, no overflow), zero rows stay zero."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x1 = torch.randn(300, 192, device=cuda, generator=g)
+    x2 = torch.randn(300, 64, device=cuda, generator=g) * 3
+    x1[0] *= 1e30; x2[0] *= 1e28          # far above the half range
+    x1[1] *= 1e-30; x2[1] *= 1e-33        # far below it
+    x1[2] = 0; x2[2] = 0
+    x1[3, 5] = 7e4                        # one element above 65504 in an otherwise ordinary row
+    (h1, l1), (h2, l2), sc = ops.split_x2(x1, x2)
+    assert h1.dtype == torch.float16 and sc.shape == (300,)
+    assert torch.isfinite(h1.float()).all() and torch.isfinite(l1.float()).all() and torch.isfinite(h2.float()).all()
+    mant = torch.frexp(sc)[0]
+    assert torch.equal(mant, torch.full_like(mant, 0.5))          # exact powers of two
+    assert float(sc[2]) == 1.0
+    for x, h, l in ((x1, h1, l1), (x2, h2, l2)):
+        rec = sc.double()[:, None] * (h.double() + l.double() / 2048)
+        rowmax = torch.maximum(x1.abs().amax(1), x2.abs().amax(1)).double()[:, None].clamp_min(1e-300)
+        err = (rec - x.double()).abs()
+        assert float((err / x.abs().double().clamp_min(1e-300))[x != 0].max()) < 2 ** -21 or float((err / rowmax).max()) < 2 ** -33
+        assert float((err / rowmax).max()) < 2 ** -22
+    # scaled row maximum sits in [2^12, 2^13)
+    top = torch.maximum(h1.float().abs().amax(1), h2.float().abs().amax(1))
+    nz = torch.ones(300, dtype=torch.bool, device=cuda); nz[2] = False
+    assert float(top[nz].min()) >= 4096 and float(top[nz].max()) <= 8192
+
+
+@pytest.mark.parametrize("M,N,K1,K2", [(1, 64, 64, 0), (129, 64, 64, 64), (1000, 128, 128, 128), (333, 512, 192, 64),
+                                        (2047, 256, 256, 256), (2048, 1024, 1024, 1024), (2049, 1024, 1024, 1024),
+                                        (5000, 1024, 1024, 1024), (50_000, 1024, 1024, 1024)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_transform_fp32_on_tensor_cores_x2(cuda, M, N, K1, K2, relu):
+    """lpgnn_node_transform_x2 (three half x half passes, chunked accumulation) vs float64 on the same fp32 inputs:
+    as accurate as the CUDA-core SGEMM-style kernel, rows of very different magnitudes included."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K1)
+    rowmag = torch.exp(torch.randn(M, 1, device=cuda, generator=g) * 3)
+    a1 = torch.randn(M, K1, device=cuda, generator=g).relu() * rowmag
+    w1 = torch.randn(N, K1, device=cuda, generator=g) / K1 ** 0.5
+    a2 = torch.randn(M, K2, device=cuda, generator=g) * rowmag if K2 else None
+    w2 = torch.randn(N, K2, device=cuda, generator=g) / K2 ** 0.5 if K2 else None
+    b = torch.randn(N, device=cuda, generator=g)
+    pa1, pa2, rs = ops.split_x2(a1, a2)
+    pw1, pw2, cs = ops.split_x2(w1, w2)
+    y = ops.node_transform_x2(pa1, pw1, pa2, pw2, rs, cs, b, relu=relu)
+    torch.cuda.synchronize()
+    e = _ref(a1, w1, a2, w2, b, relu)
+    # error relative to the row's own scale (the row normalisation of add_knowledge makes exactly this matter)
+    rscale = e.abs().amax(1, keepdim=True).clamp_min(1.0)
+    err = float(((y.double() - e).abs() / rscale).max())
+    y_simt = ops.node_transform(a1, w1, a2, w2, b, relu=relu)
+    err_simt = float(((y_simt.double() - e).abs() / rscale).max())
+    print(f"x2 M={M} K={K1}+{K2}: err {err:.2e}  (CUDA-core fp32 kernel: {err_simt:.2e})")
+    assert err < 2e-6, (err, err_simt)
+
+
+def test_transform_x2_chunk_length_bounds_the_accumulation_drift(cuda):
+    """The reason for the chunked accumulation: one TMEM chunk over the whole reduction drifts (truncating adds);
+    short chunks summed in registers do not."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    M, N, K = 4096, 1024, 1024
+    a1, a2 = torch.randn(M, K, device=cuda, generator=g).relu(), torch.randn(M, K, device=cuda, generator=g).relu()
+    w1, w2 = torch.randn(N, K, device=cuda, generator=g) / 32, torch.randn(N, K, device=cuda, generator=g) / 32
+    pa1, pa2, rs = ops.split_x2(a1, a2)
+    pw1, pw2, cs = ops.split_x2(w1, w2)
+    e = _ref(a1, w1, a2, w2, None, False)
+    errs = {}
+    prev = ops.set_x2_chunk(4)
+    try:
+        for ck in (1, 2, 4, 8, 16, 64):
+            ops.set_x2_chunk(ck)
+            y = ops.node_transform_x2(pa1, pw1, pa2, pw2, rs, cs, None)
+            errs[ck] = float((y.double() - e).norm() / e.norm())
+    finally:
+        ops.set_x2_chunk(prev)
+    print("x2 relative Frobenius error by chunk length (K-blocks of 64):", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs[4] < 5e-7
+    assert errs[1] <= errs[64]
+
+
+@pytest.mark.parametrize("M,N", [(3000, 1024), (700, 128), (129, 64)])
+def test_transform_x2_fused_head_equals_head_on_the_written_activation(cuda, M, N):
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M)
+    a1, a2 = torch.randn(M, N, device=cuda, generator=g), torch.randn(M, N, device=cuda, generator=g)
+    w1, w2 = torch.randn(N, N, device=cuda, generator=g) / N ** 0.5, torch.randn(N, N, device=cuda, generator=g) / N ** 0.5
+    b = torch.randn(N, device=cuda, generator=g)
+    hw, hb = torch.randn(3, N, device=cuda, generator=g) / N ** 0.5, torch.randn(3, device=cuda, generator=g)
+    feas = torch.randn(M, 8, device=cuda, generator=g)
+    feas[:, 5] = (feas[:, 5] > 0.5).float(); feas[:, 7] = (feas[:, 7] < -0.5).float()
+    pa1, pa2, rs = ops.split_x2(a1, a2)
+    pw1, pw2, cs = ops.split_x2(w1, w2)
+    out, logits = ops.node_transform_x2(pa1, pw1, pa2, pw2, rs, cs, b, relu=True, head=(hw, hb, feas))
+    none, logits2 = ops.node_transform_x2(pa1, pw1, pa2, pw2, rs, cs, b, relu=True, head=(hw, hb, feas), want_out=False)
+    assert none is None and torch.equal(logits, logits2)
+    assert torch.equal(out, ops.node_transform_x2(pa1, pw1, pa2, pw2, rs, cs, b, relu=True))
+    exp, _ = ops.head_mask(out, hw, hb, feas)
+    assert float((logits - exp).abs().max()) < 2e-4
+
+
 @pytest.mark.parametrize("M", [2048, 2049, 2304, 5000, 33_333])
 def test_cta_pair_transform_is_bit_identical_to_single_cta(cuda, M):
     """The cta_group::2 form of the wide bf16 transform (two CTAs, one 256-row MMA, half of W per CTA) against the
