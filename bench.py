@@ -19,8 +19,13 @@ BASELINE.json, GCN_FC(8,8,hids=1024,depth=3) inference on a 50K x 100K LP with ~
                     (HBM-bound ones against the measured copy bandwidth).
 * ``cpu_baseline``  the oracle port of the reference's CPU path, timed on this box's host cores on a
                     bounded sample (rank 0, N=1 only).
+* ``fp32``          the same step at the reference's DEFAULT precision (`--fp16 0`): fp32 storage, hidden transforms on
+                    the tensor cores from x2 operands (csrc/gemm_x2.cu) -- the like-for-like figure against the fp32 CPU arm.
+* ``parity``        logits / statuses of every precision against the CPU oracle on the bench LP (N=1).
 With N > 1 (torchrun, one rank per GPU) every rank runs its own LPs (independent units, no data-path
-collective): weak scaling, value = N * K LPs / max-over-ranks time.
+collective): weak scaling, value = N * K LPs / max-over-ranks time.  The two workloads that really shard ride in the
+same line at every N: ``train_ms_per_step`` / ``train_lps_per_sec`` (C3: data-parallel training step with the NCCL
+gradient all-reduce) and ``sweep_lps_per_sec`` / ``sweep_e2e_lps_per_sec`` (C5: packed sweep, LPs dealt over ranks).
 """
 from __future__ import annotations
 
@@ -113,7 +118,8 @@ def dist_setup(n_gpus):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
+        # NCCL_DEBUG is left to the caller (the driver counts ranks from NCCL's INFO lines); the JSON line is the one
+        # stdout line that starts with '{"metric"' (or '{"impl"')
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
         dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world,
@@ -143,6 +149,17 @@ def workload_spec(name):
     return cfg
 
 
+def workload_string(name, H, D, structure, m, n, z):
+    """config.workload, identical in both arms (the driver compares the strings)."""
+    return (f"{name}: GCN_FC(8,8,hids={H},depth={D}) inference, synthetic {structure} LP {m}x{n}, nnz={z}, "
+            f"one LP per step per GPU")
+
+
+def sweep_workload_string(n_distinct, nnz_mean, hids):
+    return (f"C5: sweep over {n_distinct} distinct synthetic LPs per GPU (m log-uniform 100..20000, n=2m, nnz~5n, "
+            f"mean nnz {nnz_mean:.0f}), GCN_FC(8,8,hids={hids},depth=3), one LP per step")
+
+
 def mp_edges(nnz, depth, fwd_bwd=False):
     # SURVEY 8d: z * 2 directions * (D-1) conv layers * (1 fwd | 2 fwd+bwd)
     return nnz * 2 * (depth - 1) * (2 if fwd_bwd else 1)
@@ -169,8 +186,7 @@ def time_kernel(fn, reps, flush=None):
 
 def run_gpu(args):
     import lpgnn_b200  # noqa: F401
-    from lpgnn_b200 import _lib, arch, ops, synth
-    from lpgnn_b200.graph import BipartiteCSR
+    from lpgnn_b200 import _lib, arch, synth
 
     rank, world, local = dist_setup(args.gpus)
     if not torch.cuda.is_available():
@@ -181,191 +197,239 @@ def run_gpu(args):
     peaks = load_peaks()
     cfg = workload_spec(args.workload)
     bf16 = args.precision in ("bf16", "fp16")      # 16-bit storage on the tensor-core path
+    H, D = cfg["hids"], cfg["depth"]
 
-    # every rank draws its own LP of the workload's shape (independent units)
-    lp = synth.processed_lp(cfg["m"], cfg["n"], cfg["nnz"], seed=cfg["seed"] + 1000 * rank, structure=args.structure)
-    m, n, z, H, D = lp.m, lp.n, lp.nnz, cfg["hids"], cfg["depth"]
+    # every rank draws its own ring of distinct LPs of the workload's shape (independent units); the timed loops cycle
+    # through the ring, so no step finds its COO / features left in L2 by the step before it
+    ring = max(1, args.distinct if cfg["nnz"] <= 2_000_000 else 1)
+    lps = [synth.processed_lp(cfg["m"], cfg["n"], cfg["nnz"], seed=cfg["seed"] + 1000 * rank + 17 * i, structure=args.structure)
+           for i in range(ring)]
+    lp = lps[0]
+    m, n, z = lp.m, lp.n, lp.nnz
     torch.manual_seed(0)
     model = arch.GCN_FC(8, 8, hids=H, depth=D).to(dev).eval()
     model.set_precision(args.precision)
 
     # host (pinned) inputs of one step: one packed staging buffer [row | col | val | x_s | x_t] (4-byte words)
     from lpgnn_b200.pipeline import BasisPipeline, pack_lp, unpack_device
-    host_lp = pack_lp(lp.row, lp.col, lp.a_data, lp.c_feas, lp.v_feas, is_sorted=True)
-    h2d_bytes = host_lp.nbytes
-    d2h_bytes = m + n
-
+    hosts = [pack_lp(x.row, x.col, x.a_data, x.c_feas, x.v_feas, is_sorted=True) for x in lps]
+    h2d_bytes = float(np.mean([h.nbytes for h in hosts]))
+    d2h_bytes = float(np.mean([h.m + h.n for h in hosts]))
     # device-resident copies for the HBM-resident arm
-    d_row, d_col, d_val, d_xs, d_xt = (t.clone() for t in unpack_device(host_lp.pack.to(dev), host_lp))
+    dev_lps = [(h, tuple(t.clone() for t in unpack_device(h.pack.to(dev), h))) for h in hosts]
 
-    # LPs of a sweep are independent: `--inflight 2` enqueues consecutive LPs on alternating streams, so the
-    # latency-bound small kernels of one LP (graph build, basis selection) overlap the other LP's work.
+    # LPs of a sweep are independent: `--inflight k` enqueues consecutive LPs on alternating streams, so the
+    # latency-bound small kernels of one LP (graph build, basis selection) overlap the other LPs' work.
     streams = [torch.cuda.Stream(device=dev) for _ in range(max(args.inflight, 1))] if args.inflight > 1 else None
     step_no = [0]
 
     def step_resident():
         # the processed-file COO is row-major sorted (dataset.py:208-210: A.tocoo() of a CSR) -> is_sorted hint
         # one native call: graph build + forward + basis selection (lpgnn_predict_basis)
-        if streams is None:
-            return model.predict_basis_coo(d_row, d_col, d_val, m, n, d_xs, d_xt, is_sorted=True)
-        st = streams[step_no[0] % len(streams)]
+        i = step_no[0]
         step_no[0] += 1
-        with torch.cuda.stream(st):
-            return model.predict_basis_coo(d_row, d_col, d_val, m, n, d_xs, d_xt, is_sorted=True)
+        h, (row, col, val, xs, xt) = dev_lps[i % ring]
+        if streams is None:
+            return h, model.predict_basis_coo(row, col, val, h.m, h.n, xs, xt, is_sorted=True)
+        with torch.cuda.stream(streams[i % len(streams)]):
+            return h, model.predict_basis_coo(row, col, val, h.m, h.n, xs, xt, is_sorted=True)
 
     pipe = BasisPipeline(model, dev, compute_streams=max(args.inflight, 1))
 
     def run_e2e(k):
         """k steps through the public pipeline API: per step one H2D copy of the packed LP from pinned host memory
         (prefetched on a side stream while the previous LP computes) and one D2H copy of its statuses."""
-        n_basic = 0
-        for _, st in pipe.run([host_lp] * k):
-            n_basic = int((st == 1).sum()) if _ == k - 1 else n_basic
-        return n_basic
+        ok = True
+        for j, st in pipe.run([hosts[i % ring] for i in range(k)]):
+            if j == k - 1:
+                ok = int((st == 1).sum()) == hosts[j % ring].m
+        return ok
 
-    # ---- warm-up, then EXACTLY K timed steps between barrier + synchronize
+    def timed_resident(k):
+        """EXACTLY k steps between barrier + synchronize, CUDA events on the launching stream, max over ranks."""
+        barrier(world)
+        torch.cuda.synchronize()
+        l0 = lib.lpgnn_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if streams is not None:
+            for st in streams:
+                st.wait_stream(torch.cuda.current_stream())
+        for _ in range(k):
+            h, status = step_resident()
+        if streams is not None:
+            for st in streams:
+                torch.cuda.current_stream().wait_stream(st)
+        e1.record()
+        torch.cuda.synchronize()
+        launches = lib.lpgnn_launch_count() - l0
+        barrier(world)
+        n_basic = int((status == 1).sum().item())
+        assert n_basic == h.m, f"basis invariant violated: {n_basic} basic nodes for m={h.m}"
+        return max_over_ranks(e0.elapsed_time(e1), world, dev), int(launches)
+
+    def timed_e2e(k):
+        assert run_e2e(3)
+        barrier(world)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        assert run_e2e(k)
+        torch.cuda.synchronize()
+        t = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
+        barrier(world)
+        return t
+
+    def measure(precision, k):
+        model.set_precision(precision)
+        for _ in range(max(args.warmup, 3)):
+            step_resident()
+        torch.cuda.synchronize()
+        t_ms, launches = timed_resident(k)
+        t_e2e = timed_e2e(k)
+        return t_ms, t_e2e, launches
+
+    # ---- warm-up, then the timed regions of the headline precision
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    torch.cuda.synchronize()
-    if rank == 0:
         sampler.mark()
-    barrier(world)
-    torch.cuda.synchronize()
-    launches0 = lib.lpgnn_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    if streams is not None:
-        for st in streams:
-            st.wait_stream(torch.cuda.current_stream())
-    for _ in range(args.steps):
-        status = step_resident()
-    if streams is not None:
-        for st in streams:
-            torch.cuda.current_stream().wait_stream(st)
-    e1.record()
-    torch.cuda.synchronize()
-    launches = lib.lpgnn_launch_count() - launches0
-    barrier(world)
-    t_ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
-    n_basic = int((status == 1).sum().item())
-    assert n_basic == m, f"basis invariant violated: {n_basic} basic nodes for m={m}"
-
-    # ---- end-to-end arm (host buffers, H2D + D2H inside the timed region)
-    run_e2e(3)
-    barrier(world)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    assert run_e2e(args.steps) == m
-    torch.cuda.synchronize()
-    t_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
-    barrier(world)
+    t_ms, t_e2e, launches = measure(args.precision, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    lps = world * args.steps / (t_ms / 1e3)
+    lps_s = world * args.steps / (t_ms / 1e3)
     lps_e2e = world * args.steps / (t_e2e / 1e3)
     out = {
         "metric": "LPs/sec (basis prediction: graph build + GCN_FC forward + basis selection)",
-        "value": lps, "unit": "LPs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "value": lps_s, "unit": "LPs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.precision if bf16 else "f32", "data": "synthetic",
-        "config": {"workload": f"{cfg['name']}: GCN_FC(8,8,hids={H},depth={D}) inference, synthetic {args.structure} LP "
-                               f"{m}x{n}, nnz={z}, one LP per step per GPU",
-                   "l2": "activations per layer (>=300 MB) exceed the 126 MB L2; no explicit flush in the step loop",
+        "config": {"workload": workload_string(cfg["name"], H, D, args.structure, m, n, z),
+                   "ring": f"{ring} distinct LPs of this shape per GPU, cycled (sizes of the first one in `workload`)",
+                   "l2": "activations per layer (>=300 MB) exceed the 126 MB L2 and consecutive steps use different LPs; "
+                         "no explicit flush in the step loop",
                    "precision": args.precision, "structure": args.structure,
                    "in_flight": f"{max(args.inflight, 1)} LP(s) in flight on alternating streams in both arms "
                                 "(LPs are independent units; ms_per_step = 1 / throughput)"},
-        "mp_edges_per_sec": mp_edges(z, D) * lps,
+        "mp_edges_per_sec": mp_edges(z, D) * lps_s,
         "e2e": {"value": lps_e2e, "unit": "LPs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": t_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
 
-    if rank == 0 and bf16 and H % 64 == 0 and D > 2:
-        # parity gate beside the number: statuses of this precision vs the fp32-accurate tensor-core mode on the same LP
-        # (fp32_tc agrees with the CPU oracle on 100 % of the nodes at this size: tests/test_gpu_model.py)
-        model.set_precision("fp32_tc")
-        st32 = model.predict_basis_coo(d_row, d_col, d_val, m, n, d_xs, d_xt, is_sorted=True)
+    # ---- the other precisions on the same workload and protocol (all ranks take part: same barriers)
+    if H % 64 == 0 and D > 2 and not args.no_precisions:
+        k2 = max(10, min(args.steps, 100))
+        others = [p for p in ("fp32", "fp16", "bf16") if p != args.precision]
+        for p in others:
+            t2, t2e, l2 = measure(p, k2)
+            if rank == 0:
+                out[p] = {"value": world * k2 / (t2 / 1e3), "unit": "LPs/s", "ms_per_step": t2 / k2, "steps": k2,
+                          "e2e": {"value": world * k2 / (t2e / 1e3), "unit": "LPs/s", "ms_per_step": t2e / k2},
+                          "gpu_launches": int(l2),
+                          "note": f"same workload, ring and timed regions as `value` / `e2e`, precision='{p}'"
+                                  + ("; the reference's default arithmetic (--fp16 0): the like-for-like figure against the "
+                                     "fp32 CPU arm" if p == "fp32" else "")}
         model.set_precision(args.precision)
-        out["status_agreement_vs_fp32"] = float((st32 == status).float().mean().item())
-        if world == 1:
-            # the other 16-bit storage format on the same kernels, same protocol.  fp16 = IEEE half, the reference's own
-            # --fp16 switch (val.py:269): the mode that meets the 99.9 % status-agreement bar; bf16 = the format named in
-            # BASELINE.json's north star.  Same tensor-core rate; half data draws a little more power under the cap.
-            other = "bf16" if args.precision == "fp16" else "fp16"
-            model.set_precision(other)
-            for _ in range(3):
-                st16 = step_resident()
-            torch.cuda.synchronize()
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            if streams is not None:
-                for st in streams:
-                    st.wait_stream(torch.cuda.current_stream())
-            for _ in range(args.steps):
-                st16 = step_resident()
-            if streams is not None:
-                for st in streams:
-                    torch.cuda.current_stream().wait_stream(st)
-            a1.record()
-            torch.cuda.synchronize()
-            out[other] = {"value": args.steps / (a0.elapsed_time(a1) / 1e3), "unit": "LPs/s",
-                          "ms_per_step": a0.elapsed_time(a1) / args.steps,
-                          "status_agreement_vs_fp32": float((st32 == st16).float().mean().item()),
-                          "note": f"same workload and timed region as `value`, precision='{other}' (HBM-resident arm)"}
-            model.set_precision(args.precision)
+    if rank == 0 and world == 1 and not args.no_cpu and H % 64 == 0 and D > 2:
+        out["parity"] = parity_vs_oracle(model, cfg, lp, dev_lps[0], args.precision)
+    elif rank == 0 and bf16 and H % 64 == 0 and D > 2:
+        # cheap live gate when the CPU oracle is not run: statuses against this library's own fp32 mode
+        h, (row, col, val, xs, xt) = dev_lps[0]
+        st16 = model.predict_basis_coo(row, col, val, h.m, h.n, xs, xt, is_sorted=True)
+        model.set_precision("fp32")
+        st32 = model.predict_basis_coo(row, col, val, h.m, h.n, xs, xt, is_sorted=True)
+        model.set_precision(args.precision)
+        out["status_agreement_vs_gpu_fp32_mode"] = float((st32 == st16).float().mean().item())
 
+    # ---- the workloads that shard: C3 data-parallel training step, C5 packed sweep (every N, same line)
     if not args.no_train:
-        tr = train_throughput(cfg, lp, dev, "bf16" if args.precision == "fp16" else args.precision,
-                              max(10, min(args.steps, 50)), 3, world)
+        tp = "bf16" if args.precision == "fp16" else ("fp32" if args.precision.startswith("fp32") else args.precision)
+        tr = train_throughput(cfg, lp, dev, tp, max(10, min(args.steps, 50)), 3, world)
         c1 = workload_spec("C1")
         lp1 = synth.processed_lp(c1["m"], c1["n"], c1["nnz"], seed=c1["seed"] + 1000 * rank, structure=args.structure)
         tr1 = train_throughput(c1, lp1, dev, "fp32", max(10, min(args.steps, 100)), 3, world)
         ts = None
         if args.workload == "C3":
             try:
-                ts = train_sampled_throughput(cfg, lp, dev, "bf16" if args.precision == "fp16" else args.precision,
-                                              max(10, min(args.steps, 30)), world)
+                ts = train_sampled_throughput(cfg, lp, dev, tp, max(10, min(args.steps, 30)), world)
             except Exception as e:          # keep the bench line: the sampled variant is an extra of --workload C3
                 if world > 1:
                     raise                   # ranks must not diverge around collectives
                 ts = {"error": f"{type(e).__name__}: {e}"}
         if rank == 0:
             out["train"] = tr
+            out["train_ms_per_step"] = tr["ms_per_step"]
+            out["train_lps_per_sec"] = tr["lps_per_sec"]
             out["train_c1_fp32"] = tr1
             if ts is not None:
                 out["train_sampled"] = ts
             if world == 1 and not args.no_cpu:
                 out["train_c1_fp32"]["cpu_baseline"] = cpu_train_baseline(c1, lp1)
+                out["train"]["cpu_baseline"] = cpu_train_baseline(cfg, lp, sample_budget_s=20.0, max_steps=3, warm=1)
+    if not args.no_sweep and args.workload in ("C2", "C3"):
+        sw = sweep_measure(args, rank, world, dev, lib, args.precision, steps=max(200, min(10 * args.steps, 1000)),
+                           distinct=args.sweep_distinct, with_cpu=False)
+        if rank == 0:
+            out["sweep"] = sw
+            out["sweep_lps_per_sec"] = sw["value"]
+            out["sweep_e2e_lps_per_sec"] = sw["e2e"]["value"]
     if rank == 0 and not args.no_kernels:
         out.update(kernel_rooflines(model, lp, dev, peaks, bf16, args))
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(cfg, lp, args, sample_budget_s=args.cpu_seconds)
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
 
 
-def run_sweep(args):
-    """--workload C5: the batch basis-prediction sweep (scripts/pred_basis.py workload) over a population of
+# Known deviations of the 16-bit storage modes from the north-star logit bar (2e-2 of the row norm on EVERY entry): with
+# random-initialised weights a handful of rows have a raw logit vector 10-100x shorter than typical and F.normalize
+# (arch.py:134-135) amplifies their rounding error by that factor.  Stated in the record, asserted in the tests.
+KNOWN_DEVIATION = {
+    "bf16": "worst entry ~2e-1 (bar 2e-2) and status agreement ~99.8 % (bar 99.9 %) at C2 size: bf16's 8 mantissa bits; "
+            "the gate-passing 16-bit mode is fp16",
+    "fp16": "a handful of entries reach ~4e-2 (bar 2e-2) at C2 size; status agreement >= 99.9 % holds",
+}
+
+
+def parity_vs_oracle(model, cfg, lp, dev_lp, headline):
+    """Logits and statuses of every precision against the CPU oracle port (fp32, the reference's arithmetic) on the
+    bench LP: max entry error relative to the row norm 10 that add_knowledge imposes, share of entries within the
+    north star's 16-bit bar 2e-2, status agreement with val.inference_gnn on the oracle's logits."""
+    port, ref, g = _port_setup(cfg, lp)
+    with torch.no_grad():
+        ec, ev = ref(torch.from_numpy(lp.c_feas), torch.from_numpy(lp.v_feas), port.TorchGraph(g))
+    exp = torch.cat((ec, ev)).numpy()
+    exp_status = port.inference_gnn_np(exp, lp.m)
+    h, (row, col, val, xs, xt) = dev_lp
+    res = {}
+    for p in ("fp32", "fp16", "bf16"):
+        model.set_precision(p)
+        st, lg = model.predict_basis_coo(row, col, val, h.m, h.n, xs, xt, is_sorted=True, want_logits=True)
+        d = np.abs(lg.cpu().numpy() - exp) / 10.0
+        res[p] = {"max_err": float(d.max()), "frac_within_2e-2": float(np.mean(d < 2e-2)),
+                  "status_agreement_vs_oracle": float(np.mean(st.cpu().numpy() == exp_status)),
+                  "bar": "max_err < 1e-4" if p == "fp32" else "max_err < 2e-2, status agreement >= 0.999"}
+        if p in KNOWN_DEVIATION:
+            res[p]["known_deviation"] = KNOWN_DEVIATION[p]
+    model.set_precision(headline)
+    res["oracle"] = "oracle/port.py (CPU, fp32; the reference's arch.py / val.py arithmetic) on ring LP 0, same weights"
+    return res
+
+
+def sweep_measure(args, rank, world, dev, lib, precision, steps, distinct, with_cpu):
+    """The batch basis-prediction sweep (scripts/pred_basis.py workload, BASELINE config C5) over a population of
     small/medium LPs (m log-uniform in [100, 20000], n = 2m, nnz = 5n).  A step = one LP.  The LPs are
     independent units: with N ranks the population is N times larger and dealt over the ranks (no collective)."""
-    import lpgnn_b200  # noqa: F401
-    from lpgnn_b200 import _lib, arch, synth
+    from lpgnn_b200 import arch, synth
     from lpgnn_b200.pipeline import BasisPipeline, PackedBasisPipeline, pack_lp, unpack_device
-    rank, world, local = dist_setup(args.gpus)
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    lib = _lib.load()
-    # weak scaling: `sweep_distinct` LPs PER RANK.  The population of world * sweep_distinct sizes is dealt in
-    # descending-nnz order, forwards then backwards over the ranks ("snake"), so every rank holds the same number
-    # of LPs and a near-equal share of the work -- a rank-dependent size mix would only measure the deal.
-    pop = synth.lp_population(args.sweep_distinct * world, seed=1239)
+    # weak scaling: `distinct` LPs PER RANK.  The population of world * distinct sizes is dealt in descending-nnz
+    # order, forwards then backwards over the ranks ("snake"), so every rank holds the same number of LPs and a
+    # near-equal share of the work -- a rank-dependent size mix would only measure the deal.
+    pop = synth.lp_population(distinct * world, seed=1239)
     if world > 1:
         from lpgnn_b200.io_utils import shard_indices
         mine = [pop[i] for i in shard_indices(len(pop), rank, world, weights=[p[2] for p in pop], equal_counts=True)]
@@ -376,27 +440,22 @@ def run_sweep(args):
     lps = [synth.processed_lp(m, n, z, seed=sd) for (m, n, z, sd) in mine]
     hosts = [pack_lp(lp.row, lp.col, lp.a_data, lp.c_feas, lp.v_feas, is_sorted=True) for lp in lps]
     torch.manual_seed(0)
-    model = arch.GCN_FC(8, 8, hids=args.sweep_hids, depth=3).to(dev).eval().set_precision(args.precision)
+    model = arch.GCN_FC(8, 8, hids=args.sweep_hids, depth=3).to(dev).eval().set_precision(precision)
     dev_lps = [(h, tuple(t.clone() for t in unpack_device(h.pack.to(dev), h))) for h in hosts]
 
     def one(i):
         h, (row, col, val, xs, xt) = dev_lps[i % len(dev_lps)]
         return model.predict_basis_coo(row, col, val, h.m, h.n, xs, xt, is_sorted=True)
 
-    steps = args.steps
     for i in range(max(args.warmup, 3)):
         one(i)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        sampler.mark()
     barrier(world)
     torch.cuda.synchronize()
     l0 = lib.lpgnn_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
-        st = one(i)
+        one(i)
     e1.record()
     torch.cuda.synchronize()
     launches = lib.lpgnn_launch_count() - l0
@@ -412,30 +471,54 @@ def run_sweep(args):
     n_done = sum(1 for _ in pipe.run(seq))
     torch.cuda.synchronize()
     t_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
-    clocks = sampler.stop() if rank == 0 else None
+    barrier(world)
     assert n_done == steps
     nnz_mean = float(np.mean([lp.nnz for lp in lps]))
     lps_s, lps_e2e = world * steps / (t_ms / 1e3), world * steps / (t_e2e / 1e3)
+    out = {
+        "value": lps_s, "unit": "LPs/s", "steps": steps, "ms_per_step": t_ms / steps, "scaling": "weak",
+        "workload": sweep_workload_string(len(mine), nnz_mean, args.sweep_hids),
+        "deal": "population of N x this many sizes dealt over the ranks in descending-nnz snake order (equal counts, "
+                "near-equal work), shuffled within the rank; no collective on the data path",
+        "precision": precision,
+        "e2e_api": "PackedBasisPipeline (block-diagonal packs, segmented basis decision)" if args.sweep_pack
+        else "BasisPipeline (one native call per LP)",
+        "mp_edges_per_sec": mp_edges(nnz_mean, 3) * lps_s,
+        "e2e": {"value": lps_e2e, "unit": "LPs/s", "h2d_bytes_per_step": float(np.mean([h.nbytes for h in hosts])),
+                "d2h_bytes_per_step": float(np.mean([h.m + h.n for h in hosts])), "ms_per_step": t_e2e / steps},
+        "gpu_launches": int(launches)}
+    if with_cpu and rank == 0 and world == 1:
+        out["cpu_baseline"] = cpu_sweep_baseline(lps, args.sweep_hids, sample_budget_s=args.cpu_seconds)
+    return out
+
+
+def run_sweep(args):
+    """--workload C5: the sweep as the headline line (see sweep_measure)."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import _lib
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.mark()
+    sw = sweep_measure(args, rank, world, dev, lib, args.precision, args.steps, args.sweep_distinct, not args.no_cpu)
+    clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         out = {
             "metric": "LPs/sec (basis prediction: graph build + GCN_FC forward + basis selection)",
-            "value": lps_s, "unit": "LPs/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": t_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "value": sw["value"], "unit": "LPs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": sw["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision if args.precision in ("bf16", "fp16") else "f32", "data": "synthetic",
-            "config": {"workload": f"C5: sweep over {len(pop)} distinct synthetic LPs (m log-uniform 100..20000, n=2m, "
-                                   f"nnz~5n, mean nnz {nnz_mean:.0f}), GCN_FC(8,8,hids={args.sweep_hids},depth=3), one LP per "
-                                   f"step; {len(mine)} LPs per rank, population dealt over ranks in descending-nnz snake order "
-                                   f"(equal counts, near-equal work)", "precision": args.precision,
-                       "l2": "small LPs: working set is L2-resident by nature of the workload",
-                       "e2e_api": "PackedBasisPipeline (block-diagonal packs, segmented basis decision)" if args.sweep_pack
-                       else "BasisPipeline (one native call per LP)"},
-            "mp_edges_per_sec": mp_edges(nnz_mean, 3) * lps_s,
-            "e2e": {"value": lps_e2e, "unit": "LPs/s", "h2d_bytes_per_step": float(np.mean([h.nbytes for h in hosts])),
-                    "d2h_bytes_per_step": float(np.mean([h.m + h.n for h in hosts])), "ms_per_step": t_e2e / steps},
-            "gpu_launches": int(launches), "clocks": clocks}
-        if world == 1 and not args.no_cpu:
-            out["cpu_baseline"] = cpu_sweep_baseline(lps, args.sweep_hids, sample_budget_s=args.cpu_seconds)
-        print(json.dumps(out))
+            "config": {"workload": sw["workload"], "deal": sw["deal"], "precision": args.precision,
+                       "l2": "small LPs: working set is L2-resident by nature of the workload", "e2e_api": sw["e2e_api"]},
+            "mp_edges_per_sec": sw["mp_edges_per_sec"], "e2e": sw["e2e"], "gpu_launches": sw["gpu_launches"],
+            "clocks": clocks}
+        if "cpu_baseline" in sw:
+            out["cpu_baseline"] = sw["cpu_baseline"]
+        print(json.dumps(out), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -538,7 +621,7 @@ def kernel_rooflines(model, lp, dev, peaks, bf16, args):
         left, _ = ops.conv_in_fused(csr, xt, xs, w(c1.right2left.lin_rel.weight), w(c1.right2left.lin_rel.bias),
                                     w(c1.right2left.lin_root.weight), dt, relu=True)
     if len(model.layers):
-        conv = model.layers[0]
+        conv = model.layers[-1]
         cast = conv._cache.get
         # SpMM pair of one hidden layer: compulsory bytes 2(m+n)Hs + 16z + 4(m+n+2)   
         t_s = time_kernel(lambda: ops.spmm(csr, right), reps, flush)
@@ -547,18 +630,48 @@ def kernel_rooflines(model, lp, dev, peaks, bf16, args):
         kernels[-1]["gather_model_bytes"] = 2 * z * H * s + (m + n) * H * s + 16 * z
         agg_t, agg_s = ops.spmm(csc, left), ops.spmm(csr, right)
         l2r, r2l = conv.left2right, conv.right2left
-        f_t = lambda: ops.node_transform(agg_t, cast(l2r.lin_rel.weight, dt), right, cast(l2r.lin_root.weight, dt),
-                                         w(l2r.lin_rel.bias), relu=True)
-        f_s = lambda: ops.node_transform(agg_s, cast(r2l.lin_rel.weight, dt), left, cast(r2l.lin_root.weight, dt),
-                                         w(r2l.lin_rel.bias), relu=True)
-        t_g = time_kernel(f_t, reps, flush) + time_kernel(f_s, reps, flush)
-        add("node_transform pair (tcgen05)" if bf16 else "node_transform pair (fp32 CUDA cores)", "tensor", t_g,
-            4 * (m + n) * H * H, 2)
-        right2 = f_t()
+        hl = (w(model.lin_left.weight), w(model.lin_left.bias), xs)
+        hr = (w(model.lin_right.weight), w(model.lin_right.bias), xt)
+        if bf16:
+            # the last hidden layer as the step runs it: basis-status head fused into the epilogue (the activation is
+            # never written) + head_finish (sum of the column-tile partials, bias, add_knowledge)
+            f_t = lambda: ops.node_transform_head(agg_t, cast(l2r.lin_rel.weight, dt), right, cast(l2r.lin_root.weight, dt),
+                                                  w(l2r.lin_rel.bias), *hr)
+            f_s = lambda: ops.node_transform_head(agg_s, cast(r2l.lin_rel.weight, dt), left, cast(r2l.lin_root.weight, dt),
+                                                  w(r2l.lin_rel.bias), *hl)
+            t_g = time_kernel(f_t, reps, flush) + time_kernel(f_s, reps, flush)
+            add("node_transform pair, head fused (tcgen05) + head_finish", "tensor", t_g, 4 * (m + n) * H * H, 4)
+        elif args.precision == "fp32":
+            from lpgnn_b200.autograd import x2_weights_cached
+            t_sp = (time_kernel(lambda: ops.split_x2(agg_t, right), reps, flush)
+                    + time_kernel(lambda: ops.split_x2(agg_s, left), reps, flush))
+            add("split_x2 pair (fp32 -> half hi / lo + row scale)", "hbm", t_sp, 2 * (m + n) * H * 8 + 4 * (m + n), 2)
+            at, xt2, st_ = ops.split_x2(agg_t, right)
+            as_, xs2, ss_ = ops.split_x2(agg_s, left)
+            wr_t, wo_t, cs_t = x2_weights_cached(conv._cache, l2r)
+            wr_s, wo_s, cs_s = x2_weights_cached(conv._cache, r2l)
+            f_t = lambda: ops.node_transform_x2(at, wr_t, xt2, wo_t, st_, cs_t, w(l2r.lin_rel.bias), relu=True, head=hr,
+                                                want_out=False)
+            f_s = lambda: ops.node_transform_x2(as_, wr_s, xs2, wo_s, ss_, cs_s, w(r2l.lin_rel.bias), relu=True, head=hl,
+                                                want_out=False)
+            t_g = time_kernel(f_t, reps, flush) + time_kernel(f_s, reps, flush)
+            # three half x half passes carry one fp32-accurate product: 3 x 4(m+n)H^2 tensor-core flops
+            add("node_transform_x2 pair, head fused (tcgen05, 3 half passes) + head_finish", "tensor", t_g,
+                3 * 4 * (m + n) * H * H, 4)
+            kernels[-1]["fp32_equivalent_flops"] = 4 * (m + n) * H * H
+        else:
+            f_t = lambda: ops.node_transform(agg_t, cast(l2r.lin_rel.weight, dt), right, cast(l2r.lin_root.weight, dt),
+                                             w(l2r.lin_rel.bias), relu=True)
+            f_s = lambda: ops.node_transform(agg_s, cast(r2l.lin_rel.weight, dt), left, cast(r2l.lin_root.weight, dt),
+                                             w(r2l.lin_rel.bias), relu=True)
+            t_g = time_kernel(f_t, reps, flush) + time_kernel(f_s, reps, flush)
+            add("node_transform pair (fp32 CUDA cores)", "tensor", t_g, 4 * (m + n) * H * H, 2)
+            right2 = f_t()
+            t_h = time_kernel(lambda: ops.head_mask(right2, w(model.lin_right.weight), w(model.lin_right.bias), xt), reps, flush)
+            add("head_mask (vars side)", "hbm", t_h, n * (H * s + 8 * 4 + 3 * 4), 1)
     else:
-        right2 = right
-    t_h = time_kernel(lambda: ops.head_mask(right2, w(model.lin_right.weight), w(model.lin_right.bias), xt), reps, flush)
-    add("head_mask (vars side)", "hbm", t_h, n * (H * s + 8 * 4 + 3 * 4), 1)
+        t_h = time_kernel(lambda: ops.head_mask(right, w(model.lin_right.weight), w(model.lin_right.bias), xt), reps, flush)
+        add("head_mask (vars side)", "hbm", t_h, n * (H * s + 8 * 4 + 3 * 4), 1)
     lc = torch.randn(m, 3, device=dev)
     lv = torch.randn(n, 3, device=dev)
     t_sel = time_kernel(lambda: ops.basis_select(lc, lv, int64=False), reps, flush)
@@ -571,14 +684,16 @@ def kernel_rooflines(model, lp, dev, peaks, bf16, args):
     t_b2 = time_kernel(lambda: BipartiteCSR.from_coo(h_row, h_col, h_val, m, n, is_sorted=False), reps, flush)
     add("graph_build (unsorted COO->CSR+CSC)", "hbm", t_b2, z * 12 * 2 * 3, -1)
     # measured DRAM traffic per launch from the committed ncu --set full capture (same workload / precision only)
-    for tname in ("r01d_traffic.json", "r01e_traffic.json"):
+    for tname in ("r01d_traffic.json", "r01e_traffic.json", "r02_traffic.json"):
         tpath = os.path.join(ROOT, "profiles", tname)
         if not os.path.isfile(tpath):
             continue
         tj = json.load(open(tpath))
         if tj.get("workload") == args.workload and tj.get("precision") == args.precision and args.structure == "staircase":
+            alias = {"node_transform pair, head fused (tcgen05) + head_finish": "node_transform pair (tcgen05)"}
             for k in kernels:
-                k["traffic"] = tj["bytes"].get(k["kernel"])
+                if k.get("traffic") is None:
+                    k["traffic"] = tj["bytes"].get(k["kernel"], tj["bytes"].get(alias.get(k["kernel"], "")))
     dom = max([k for k in kernels if "unsorted" not in k["kernel"]], key=lambda k: k["ms"])
     roof = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
             "frac": dom["frac"], "traffic": dom.get("traffic"), "kernel": dom["kernel"], "peak_source": peaks["source"] +
@@ -708,7 +823,7 @@ def cpu_sweep_baseline(lps, hids, sample_budget_s=15.0):
             "mp_edges_per_sec": mp_edges(nnz_mean, 3) / dt}
 
 
-def cpu_train_baseline(cfg, lp, sample_budget_s=8.0, max_steps=200):
+def cpu_train_baseline(cfg, lp, sample_budget_s=8.0, max_steps=200, warm=3):
     """configs[0] of BASELINE.json: the reference's CPU training step (train.py:117-129: forward, balanced loss,
     backward, Adam) on the oracle port, all host threads; a bounded sample of steps on the same LP."""
     import warnings
@@ -730,10 +845,10 @@ def cpu_train_baseline(cfg, lp, sample_budget_s=8.0, max_steps=200):
         loss.backward()
         opt.step()
 
-    for _ in range(3):
+    for _ in range(warm):
         step()
     t0, reps = time.perf_counter(), 0
-    while reps < max_steps and time.perf_counter() - t0 < sample_budget_s:
+    while reps < max_steps and (reps == 0 or time.perf_counter() - t0 < sample_budget_s):
         step()
         reps += 1
     dt = (time.perf_counter() - t0) / reps
@@ -758,15 +873,20 @@ def run_reference(args):
     if args.workload == "C5":
         # the sweep population of the GPU arm (rank 0's share at N=1): one LP per step, cycled in the same order
         cfg = dict(name="C5", hids=args.sweep_hids, depth=3)
-        pop = synth.lp_population(args.sweep_distinct, seed=1239)[:max(1, min(args.sweep_distinct, args.steps + 3))]
+        pop = synth.lp_population(args.sweep_distinct, seed=1239)
         lps_list = [synth.processed_lp(m, n, z, seed=sd) for (m, n, z, sd) in pop]
     else:
         cfg = workload_spec(args.workload)
-        lps_list = [synth.processed_lp(cfg["m"], cfg["n"], cfg["nnz"], seed=cfg["seed"], structure=args.structure)]
+        ring = max(1, args.distinct if cfg["nnz"] <= 2_000_000 else 1)       # rank 0's ring of the GPU arm
+        lps_list = [synth.processed_lp(cfg["m"], cfg["n"], cfg["nnz"], seed=cfg["seed"] + 17 * i, structure=args.structure)
+                    for i in range(ring)]
     lp = lps_list[0]
     port, model, _ = _port_setup(cfg, lp)
-    for i in range(max(1, min(args.warmup, 3))):
-        cpu_step(port, model, lps_list[i % len(lps_list)])
+    # the requested warm-up, bounded in time like the timed steps below (C2: ~0.6 s per CPU step)
+    warm_done, tw = 0, time.perf_counter()
+    while warm_done < max(args.warmup, 1) and (warm_done == 0 or time.perf_counter() - tw < args.cpu_cap_seconds / 3):
+        cpu_step(port, model, lps_list[warm_done % len(lps_list)])
+        warm_done += 1
     # bounded: a driver-chosen K sized for the GPU arm must not turn into tens of minutes of CPU work
     requested, done = args.steps, 0
     t0 = time.perf_counter()
@@ -778,20 +898,18 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     args.steps = done
     lps = args.steps / dt
-    nnz_mean = float(np.mean([x.nnz for x in lps_list[:max(1, min(done, len(lps_list)))]]))
+    nnz_mean = float(np.mean([x.nnz for x in lps_list]))
     print(json.dumps({
         "impl": "reference",
         "metric": "LPs/sec (basis prediction: graph build + GCN_FC forward + basis selection)",
         "value": lps, "unit": "LPs/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
-        "warmup": max(1, min(args.warmup, 3)), "warmup_requested": args.warmup,
+        "warmup": warm_done, "warmup_requested": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": (f"C5: sweep over {len(lps_list)} distinct synthetic LPs (m log-uniform 100..20000, n=2m, "
-                                f"nnz~5n, mean nnz {nnz_mean:.0f}), GCN_FC(8,8,hids={cfg['hids']},depth=3), one LP per step"
-                                if args.workload == "C5" else
-                                f"{cfg['name']}: GCN_FC(8,8,hids={cfg['hids']},depth={cfg['depth']}) inference, synthetic "
-                                f"{args.structure} LP {lp.m}x{lp.n}, nnz={lp.nnz}, one LP per step"),
-                   "precision": "fp32", "structure": args.structure},
+        "config": {"workload": (sweep_workload_string(len(lps_list), nnz_mean, cfg["hids"]) if args.workload == "C5" else
+                                workload_string(cfg["name"], cfg["hids"], cfg["depth"], args.structure, lp.m, lp.n, lp.nnz)),
+                   "precision": "fp32", "structure": args.structure,
+                   "note": "rank 0's first LP of the GPU arm's ring (same generator and seed); one host, all cores"},
         "mp_edges_per_sec": mp_edges(nnz_mean, cfg["depth"]) * lps,
         "cpu_baseline": {"value": lps, "unit": "LPs/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} LPs, one per step; oracle port of the reference CPU path "
@@ -799,7 +917,7 @@ def run_reference(args):
                                    f"installable here), torch threads={cores}"},
         "e2e": {"value": lps, "unit": "LPs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "steps_requested": requested,
-    }))
+    }), flush=True)
 
 
 def main():
@@ -814,8 +932,12 @@ def main():
     ap.add_argument("--sweep-pack", type=int, default=1, help="C5 e2e arm: pack LPs block-diagonally (1) or one call per LP (0)")
     # fp16 (IEEE half storage, fp32 accumulate) is the 16-bit mode that passes every parity gate of the north star
     # (>= 99.9 % status agreement); bf16 runs the same kernels at the same rate and is reported beside it
-    # (default: fp16; C4 is named "bf16 full-graph inference" in BASELINE.json and defaults to bf16)
-    ap.add_argument("--precision", default=None, choices=["bf16", "fp16", "fp32", "fp32_tc"])
+    # (default: fp16 for every workload; C4 -- "bf16 full-graph inference" in BASELINE.json -- headlines the gate-passing
+    # 16-bit mode too and carries the bf16 figure in the same line)
+    ap.add_argument("--precision", default=None, choices=["bf16", "fp16", "fp32", "fp32_simt"])
+    ap.add_argument("--distinct", type=int, default=4, help="distinct LPs per GPU cycled by the timed loops (C1-C3)")
+    ap.add_argument("--no-precisions", action="store_true", help="skip the fp32 / other 16-bit sub-measurements")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the C5 packed-sweep sub-measurement of the default run")
     ap.add_argument("--structure", default="staircase", choices=["staircase", "uniform"])
     ap.add_argument("--inflight", type=int, default=3, help="LPs in flight on alternating streams (both arms)")
     ap.add_argument("--kernel-reps", type=int, default=10)
@@ -827,7 +949,7 @@ def main():
     ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
     if args.precision is None:
-        args.precision = "bf16" if args.workload == "C4" else "fp16"
+        args.precision = "fp16"
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 3
         args.warmup = args.warmup if args.warmup is not None else 1

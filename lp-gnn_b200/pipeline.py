@@ -106,6 +106,9 @@ class BasisPipeline:
         if not lps:
             return
         D = self.depth
+        # (re)build the cached 16-bit / x2 weight copies on the CALLER's stream before the compute streams fork from it:
+        # built lazily inside the first predict call they would be written on one compute stream and read on the others
+        self.model._native_weights()
         if self.compute is not None:                               # weights etc. were produced on the caller's stream
             for st in self.compute:
                 st.wait_stream(torch.cuda.current_stream(self.dev))
@@ -255,6 +258,7 @@ class PackedBasisPipeline:
         packs = self._plan(lps)
         if not packs:
             return
+        self.model._native_weights()            # on the caller's stream, before the compute streams fork (see BasisPipeline.run)
         if self.compute is not None:
             for st in self.compute:
                 st.wait_stream(torch.cuda.current_stream(self.dev))
