@@ -499,6 +499,24 @@ LPGNN_API int lpgnn_balanced_ce(const float* logits_s, const int64_t* y_s, int32
                       const int64_t* y_t, int32_t n, int merge_lu, float* loss_out, float* dlogits_s,
                       float* dlogits_t, void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
 
+/* (f-3) The other two losses of the training loop, value and gradient in one kernel.  focal = 0: unbalanced()
+ * (reference train.py:30-37) = F.cross_entropy over the concatenation of both sides (plain mean over m+n rows);
+ * focal = 1: focal() (train.py:18-28, 49-53) = (1 - exp(-ce))^gamma * ce of that same mean CE (the reference applies
+ * the focal factor to the batch mean; gamma = 2).  loss_out, grad_scale_out: one float each (device); dlogits_*
+ * (optional, f32 [rows,3]) receive (softmax - onehot) / (m+n), and d loss / d logits = grad_scale_out * dlogits
+ * (the caller folds the scalar into its upstream gradient, no second pass over the rows).  Deterministic. */
+LPGNN_API size_t lpgnn_flat_ce_workspace_bytes(int32_t m, int32_t n);
+LPGNN_API int lpgnn_flat_ce(const float* logits_s, const int64_t* y_s, int32_t m, const float* logits_t,
+                  const int64_t* y_t, int32_t n, int focal, float gamma, float* loss_out, float* grad_scale_out,
+                  float* dlogits_s, float* dlogits_t, void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
+
+/* (f-3) Counters behind val.accuracy (reference val.py:199-237: per-side accuracy and sklearn precision / recall of
+ * class 1): counts_out (device int32[8]) = per side {#pred == gt, #pred == 1 and gt == 1, #pred == 1, #gt == 1},
+ * constraints then variables.  status [m+n] as written by lpgnn_basis_select (uint8 or int64), labels int64.
+ * One kernel; the caller reads eight integers instead of moving both vectors to the host. */
+LPGNN_API int lpgnn_basis_metrics(const void* status, int status_is_i64, const int64_t* y_s, int32_t m,
+                        const int64_t* y_t, int32_t n, int32_t* counts_out, lpgnn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (f-2) LP scaling + node features on the device.  Replaces dataset.scaling (reference dataset.py:23-76,
  * utils.py:323-332) and dataset.cvt_to_features (dataset.py:79-96, utils.py:335-383), float64 like the
@@ -543,6 +561,31 @@ LPGNN_API int lpgnn_induced_count(const int32_t* ptr, const int32_t* idx, const 
 LPGNN_API int lpgnn_induced_fill(const int32_t* ptr, const int32_t* idx, const float* val, const int32_t* rows,
                        int32_t n_rows, const int32_t* map_other, const int64_t* offsets, int32_t* out_row,
                        int32_t* out_col, float* out_val, lpgnn_stream_t stream);
+
+/* (f-4) One mini-batch with ONE host read.  lpgnn_sample_nodes builds the node sets of a sampled mini-batch entirely on
+ * the device: seeds (global unipartite ids, int64: constraints 0..m-1, variables m..m+n-1; dataset.py:258-260) are split by
+ * side in seed order, then `n_hops` hops of neighbour sampling (fanouts_host[h] neighbours per frontier node, < 0 = all;
+ * NeighborLoader num_neighbors, train.py:110 / val.py:23) append the newly reached nodes of each side in ascending id
+ * order -- the local numbering of MyToBipartite (dataset.py:288-294).  cons_nodes [m] / var_nodes [n]: local -> global id
+ * (filled up to the counts below); map_cons [m] / map_vars [n]: global -> local id or -1.  sizes: device int32
+ * [lpgnn_sample_sizes_len()]: [0] = sampled constraints, [1] = sampled variables, [2] / [3] = seed constraints / variables
+ * (s_bs, t_bs), [4 + 2h + side] = members after hop h.  lpgnn_induced_offsets then writes, for the sampled constraints,
+ * the start of every local row in the induced subgraph (offsets [rows_capacity + 1]) and its nnz into
+ * sizes[lpgnn_sample_sizes_len() - 2]; the caller reads `sizes` ONCE, allocates the COO and calls
+ * lpgnn_induced_fill_sorted, which emits the entries in canonical order (local row, ascending local column), i.e. ready
+ * for lpgnn_graph_build(LPGNN_COO_SORTED).  All ordered compactions are stable scans (decoupled look-back): deterministic. */
+LPGNN_API int32_t lpgnn_sample_sizes_len(void);
+LPGNN_API size_t lpgnn_sample_nodes_workspace_bytes(int32_t m, int32_t n, int32_t n_seeds);
+LPGNN_API int lpgnn_sample_nodes(const int32_t* rowptr, const int32_t* col, const int32_t* colptr, const int32_t* row_csc,
+                       int32_t m, int32_t n, const int64_t* seeds, int32_t n_seeds, const int32_t* fanouts_host,
+                       int32_t n_hops, uint64_t seed, int32_t* cons_nodes, int32_t* var_nodes, int32_t* map_cons,
+                       int32_t* map_vars, int32_t* sizes, void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
+LPGNN_API int lpgnn_induced_offsets(const int32_t* ptr, const int32_t* idx, const int32_t* rows, int32_t rows_capacity,
+                          const int32_t* map_other, int32_t* offsets, int32_t* sizes, void* workspace,
+                          size_t workspace_bytes, lpgnn_stream_t stream);
+LPGNN_API int lpgnn_induced_fill_sorted(const int32_t* ptr, const int32_t* idx, const float* val, const int32_t* rows,
+                              int32_t n_rows, const int32_t* map_other, const int32_t* offsets, int32_t* out_row,
+                              int32_t* out_col, float* out_val, lpgnn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -112,10 +112,18 @@ SIGNATURES = {
     "lpgnn_sample_mark": (_int, [_p, _p, _p, _i32, _i32, C.c_uint64, _p, _p]),
     "lpgnn_induced_count": (_int, [_p, _p, _p, _i32, _p, _p, _p]),
     "lpgnn_induced_fill": (_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),
+    "lpgnn_sample_sizes_len": (_i32, []),
+    "lpgnn_sample_nodes_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "lpgnn_sample_nodes": (_int, [_p, _p, _p, _p, _i32, _i32, _p, _i32, _p, _i32, C.c_uint64, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "lpgnn_induced_offsets": (_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _sz, _p]),
+    "lpgnn_induced_fill_sorted": (_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),
     "lpgnn_lp_features_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "lpgnn_lp_features": (_int, [_p] * 11 + [_i64, _i32, _i32] + [_p] * 10 + [_p, _sz, _p]),
     "lpgnn_balanced_ce_workspace_bytes": (_sz, [_i32, _i32]),
     "lpgnn_balanced_ce": (_int, [_p, _p, _i32, _p, _p, _i32, _int, _p, _p, _p, _p, _sz, _p]),
+    "lpgnn_flat_ce_workspace_bytes": (_sz, [_i32, _i32]),
+    "lpgnn_flat_ce": (_int, [_p, _p, _i32, _p, _p, _i32, _int, C.c_float, _p, _p, _p, _p, _p, _sz, _p]),
+    "lpgnn_basis_metrics": (_int, [_p, _int, _p, _i32, _p, _i32, _p, _p]),
     "lpgnn_basis_select_workspace_bytes": (_sz, [_i64]),
     "lpgnn_basis_select": (_int, [_p, _i32, _p, _i32, _i32, _p, _int, _p, _p, _sz, _p]),
 }

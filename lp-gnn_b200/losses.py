@@ -1,5 +1,6 @@
-"""Training losses of the reference (train.py:18-53, utils.py:286-299), kept in PyTorch as in the
-reference: they act on the [m,3] / [n,3] logits only and define what flows into the backward kernels."""
+"""Training losses of the reference (train.py:18-53, utils.py:286-299).  On CUDA fp32 logits with int64 labels all
+three (``balanced``, ``unbalanced``, ``focal``) are single native calls that return the loss and d(loss)/d(logits)
+(csrc/loss.cu); the framework spellings below them are what CPU tensors and the parity tests use."""
 from __future__ import annotations
 
 import torch
@@ -41,8 +42,14 @@ class FocalLoss(nn.modules.loss._WeightedLoss):
 cri_focal = FocalLoss()
 
 
-def unbalanced(logpr_cons, logpr_vars, y_s, y_t):
+def unbalanced_torch(logpr_cons, logpr_vars, y_s, y_t):
+    """train.py:30-37 with framework ops."""
     return F.cross_entropy(torch.cat((logpr_cons, logpr_vars), dim=0), torch.cat((y_s, y_t), dim=0))
+
+
+def focal_torch(logpr_cons, logpr_vars, y_s, y_t):
+    """train.py:49-53 with framework ops."""
+    return cri_focal(torch.cat((logpr_cons, logpr_vars), dim=0), torch.cat((y_s, y_t), dim=0))
 
 
 def balanced_torch(logpr_cons, logpr_vars, y_s, y_t):
@@ -92,8 +99,56 @@ def balanced(logpr_cons, logpr_vars, y_s, y_t):
     return balanced_torch(logpr_cons, logpr_vars, y_s, y_t)
 
 
+def _native_ok(logpr_cons, logpr_vars, y_s, y_t):
+    return (logpr_cons.is_cuda and logpr_vars.is_cuda and logpr_cons.dtype == torch.float32 and logpr_vars.dtype == torch.float32
+            and y_s.dtype == torch.int64 and y_t.dtype == torch.int64 and len(y_s) + len(y_t) > 0
+            and logpr_cons.shape[1] == 3 and logpr_vars.shape[1] == 3)
+
+
+class _FlatCE(torch.autograd.Function):
+    """``lpgnn_flat_ce``: unbalanced / focal loss and the un-scaled d(loss)/d(logits) from one kernel; the scalar
+    d(loss)/d(mean CE) stays on the device and is folded into the upstream gradient in backward."""
+
+    @staticmethod
+    def forward(ctx, logit_s, logit_t, y_s, y_t, focal_gamma):
+        from . import _lib
+        lib = _lib.load()
+        logit_s, logit_t = logit_s.contiguous(), logit_t.contiguous()
+        y_s, y_t = y_s.contiguous(), y_t.contiguous()
+        m, n = logit_s.shape[0], logit_t.shape[0]
+        dev = logit_s.device
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        d = torch.empty((m + n, 3), dtype=torch.float32, device=dev) if need else None
+        out = torch.empty(2, dtype=torch.float32, device=dev)               # [loss, d loss / d ce]
+        ws_bytes = lib.lpgnn_flat_ce_workspace_bytes(m, n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.lpgnn_flat_ce(logit_s.data_ptr(), y_s.data_ptr(), m, logit_t.data_ptr(), y_t.data_ptr(), n,
+                                   0 if focal_gamma is None else 1, 2.0 if focal_gamma is None else float(focal_gamma),
+                                   out.data_ptr(), out[1:].data_ptr(), _lib.ptr(d), d[m:].data_ptr() if need else None,
+                                   ws.data_ptr(), ws_bytes, _lib.stream_ptr())
+        _lib.check(rc, "lpgnn_flat_ce")
+        ctx.d, ctx.m, ctx.scale = d, m, out[1]
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        d = ctx.d * (g * ctx.scale)
+        return d[:ctx.m], d[ctx.m:], None, None, None
+
+
+def unbalanced(logpr_cons, logpr_vars, y_s, y_t):
+    """train.py:30-37.  CUDA fp32 logits with int64 labels take the fused kernel; anything else the framework ops."""
+    if _native_ok(logpr_cons, logpr_vars, y_s, y_t):
+        return _FlatCE.apply(logpr_cons, logpr_vars, y_s, y_t, None)
+    return unbalanced_torch(logpr_cons, logpr_vars, y_s, y_t)
+
+
 def focal(logpr_cons, logpr_vars, y_s, y_t):
-    return cri_focal(torch.cat((logpr_cons, logpr_vars), dim=0), torch.cat((y_s, y_t), dim=0))
+    """train.py:49-53 (gamma = 2, focal factor on the batch-mean CE as in the reference)."""
+    if _native_ok(logpr_cons, logpr_vars, y_s, y_t):
+        return _FlatCE.apply(logpr_cons, logpr_vars, y_s, y_t, cri_focal.gamma)
+    return focal_torch(logpr_cons, logpr_vars, y_s, y_t)
 
 
 LOSSES = {"balanced": balanced, "unbalanced": unbalanced, "focal": focal}

@@ -3,8 +3,9 @@
 The reference feeds such LPs to ``torch_geometric.loader.NeighborLoader`` on the unipartite graph and converts every
 sampled subgraph with ``MyToBipartite`` (train.py:103-116: ``num_neighbors=[6]*depth, shuffle=True, drop_last=True,
 directed=False``; val.py:14-36: ``num_neighbors=[-1]*depth, shuffle=False``).  Here the whole LP stays resident in HBM
-once (``ResidentLP``: the same CSR + CSC the full-graph path uses) and every mini-batch is cut out of it by three
-kernels (``lpgnn_sample_mark``, ``lpgnn_induced_count``, ``lpgnn_induced_fill``, ``csrc/sample.cu``):
+once (``ResidentLP``: the same CSR + CSC the full-graph path uses) and every mini-batch is cut out of it on the device
+(``lpgnn_sample_nodes``, ``lpgnn_induced_offsets``, ``lpgnn_induced_fill_sorted``, ``csrc/sample.cu``) with one host
+read of the resulting sizes:
 
 * seeds   = ``batch_size`` consecutive entries of the node order (a permutation when shuffling) over the unipartite
             ids -- constraints ``0..m-1`` first, variables ``m..m+n-1`` (dataset.py:258-260);
@@ -90,13 +91,35 @@ def induced_subgraph(lp: ResidentLP, cons_nodes, var_nodes) -> BipartiteCSR:
         return BipartiteCSR.from_coo(row, col, v, mc, nv, is_sorted=False)
 
 
+class _SamplerBuffers:
+    """Device buffers of the one-sync sampler, sized by the resident LP and reused by every mini-batch."""
+
+    def __init__(self, lp: ResidentLP, max_seeds: int):
+        lib = _lib.load()
+        dev = lp.device
+        i32 = lambda k: torch.empty(max(int(k), 1), dtype=torch.int32, device=dev)
+        self.cons_nodes, self.var_nodes, self.map_c, self.map_v = i32(lp.m), i32(lp.n), i32(lp.m), i32(lp.n)
+        self.offsets = i32(lp.m + 1)
+        self.sizes_len = int(lib.lpgnn_sample_sizes_len())
+        self.sizes = i32(self.sizes_len)
+        self.sizes_host = torch.empty(self.sizes_len, dtype=torch.int32).pin_memory()
+        self.max_seeds = int(max_seeds)
+        self.ws_bytes = int(lib.lpgnn_sample_nodes_workspace_bytes(lp.m, lp.n, max_seeds))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+
+
 class NeighborSubgraphLoader:
-    """Iterates seed batches of a ``ResidentLP`` and yields bipartite mini-batches (see the module docstring)."""
+    """Iterates seed batches of a ``ResidentLP`` and yields bipartite mini-batches (see the module docstring).
+
+    Every mini-batch is cut out by ``lpgnn_sample_nodes`` (seed split + all hops + ordered node lists, on the device),
+    ``lpgnn_induced_offsets``, ONE host read of the sizes (nodes per side, seeds per side, nnz), ``lpgnn_induced_fill_sorted``
+    and ``lpgnn_graph_build`` on its sorted path -- no ``nonzero`` / ``.item()`` per hop."""
 
     def __init__(self, lp: ResidentLP, num_neighbors, batch_size, shuffle=False, drop_last=False, seed=0):
         self.lp, self.num_neighbors = lp, [int(f) for f in num_neighbors]
         self.batch_size = int(min(batch_size, lp.num_nodes))
         self.shuffle, self.drop_last, self.seed, self.epoch = shuffle, drop_last, int(seed), 0
+        self._buf = None
 
     def __len__(self):
         full, rem = divmod(self.lp.num_nodes, self.batch_size)
@@ -114,39 +137,47 @@ class NeighborSubgraphLoader:
             yield self.sample(order[b * self.batch_size:(b + 1) * self.batch_size], salt=self.epoch * 1_000_003 + b)
 
     def sample(self, seeds, salt=0) -> Data:
+        import ctypes as C
         lp, dev = self.lp, self.lp.device
+        lib = _lib.load()
         g = lp.graph if not lp.graph._transposed else lp.graph.t()
-        csr, csc = g.views()
-        seeds = seeds.to(dev)
-        cons_seeds = seeds[seeds < lp.m].to(torch.int32)
-        var_seeds = (seeds[seeds >= lp.m] - lp.m).to(torch.int32)
-        in_c = torch.zeros(lp.m, dtype=torch.uint8, device=dev)
-        in_v = torch.zeros(lp.n, dtype=torch.uint8, device=dev)
-        in_c[cons_seeds.long()] = 1
-        in_v[var_seeds.long()] = 1
-        cons_parts, var_parts = [cons_seeds], [var_seeds]
-        front_c, front_v = cons_seeds, var_seeds
+        (rowptr, col, val, _), (colptr, row_csc, _, _) = g.views()
+        seeds = seeds.to(dev, torch.int64).contiguous()
+        ns = int(seeds.numel())
+        if self._buf is None or ns > self._buf.max_seeds:
+            self._buf = _SamplerBuffers(lp, max(ns, self.batch_size))
+        B = self._buf
+        hops = len(self.num_neighbors)
+        fan = (C.c_int32 * max(hops, 1))(*self.num_neighbors) if hops else None
+        s = (self.seed * 0x9E3779B1 + salt * 0x85EBCA77) & (2 ** 64 - 1)
         with torch.cuda.device(dev):
-            for hop, fan in enumerate(self.num_neighbors):
-                mark_v, mark_c = torch.zeros_like(in_v), torch.zeros_like(in_c)
-                s = (self.seed * 0x9E3779B1 + salt * 0x85EBCA77 + hop * 0xC2B2AE3D) & (2 ** 63 - 1)
-                _sample_mark(csr, front_c.contiguous(), fan, s, mark_v)
-                _sample_mark(csc, front_v.contiguous(), fan, s ^ 0x5555555555555555, mark_c)
-                front_v = torch.nonzero(mark_v & (1 - in_v)).flatten().to(torch.int32)     # new variables, ascending
-                front_c = torch.nonzero(mark_c & (1 - in_c)).flatten().to(torch.int32)
-                in_v |= mark_v
-                in_c |= mark_c
-                cons_parts.append(front_c)
-                var_parts.append(front_v)
-        cons_nodes = torch.cat(cons_parts).contiguous()
-        var_nodes = torch.cat(var_parts).contiguous()
-        sub = induced_subgraph(lp, cons_nodes, var_nodes)
+            st = _lib.stream_ptr()
+            _lib.check(lib.lpgnn_sample_nodes(rowptr.data_ptr(), col.data_ptr(), colptr.data_ptr(), row_csc.data_ptr(), lp.m, lp.n,
+                                              seeds.data_ptr(), ns, fan, hops, s, B.cons_nodes.data_ptr(), B.var_nodes.data_ptr(),
+                                              B.map_c.data_ptr(), B.map_v.data_ptr(), B.sizes.data_ptr(), B.ws.data_ptr(),
+                                              B.ws_bytes, st), "lpgnn_sample_nodes")
+            _lib.check(lib.lpgnn_induced_offsets(rowptr.data_ptr(), col.data_ptr(), B.cons_nodes.data_ptr(), lp.m,
+                                                 B.map_v.data_ptr(), B.offsets.data_ptr(), B.sizes.data_ptr(), B.ws.data_ptr(),
+                                                 B.ws_bytes, st), "lpgnn_induced_offsets")
+            B.sizes_host.copy_(B.sizes, non_blocking=True)
+            torch.cuda.current_stream().synchronize()             # the one host read of the mini-batch
+            sz = B.sizes_host.tolist()
+            mc, nv, s_bs, t_bs, z = sz[0], sz[1], sz[2], sz[3], sz[B.sizes_len - 2]
+            cons_nodes, var_nodes = B.cons_nodes[:mc].clone(), B.var_nodes[:nv].clone()
+            row = torch.empty(z, dtype=torch.int32, device=dev)
+            colo = torch.empty(z, dtype=torch.int32, device=dev)
+            v = torch.empty(z, dtype=torch.float32, device=dev)
+            if z:
+                _lib.check(lib.lpgnn_induced_fill_sorted(rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), cons_nodes.data_ptr(),
+                                                         mc, B.map_v.data_ptr(), B.offsets.data_ptr(), row.data_ptr(),
+                                                         colo.data_ptr(), v.data_ptr(), st), "lpgnn_induced_fill_sorted")
+            sub = BipartiteCSR.from_coo(row, colo, v, mc, nv, is_sorted=True)
         ci, vi = cons_nodes.long(), var_nodes.long()
         batch = Data(x_s=lp.x_s[ci], x_t=lp.x_t[vi], edge_index=sub, n_id_s=cons_nodes, n_id_t=var_nodes)
         if lp.y_s is not None:
             batch.y_s, batch.y_t = lp.y_s[ci], lp.y_t[vi]
-        batch.bs = batch.batch_size = int(seeds.numel())
-        batch.s_bs, batch.t_bs = int(cons_seeds.numel()), int(var_seeds.numel())
+        batch.bs = batch.batch_size = ns
+        batch.s_bs, batch.t_bs = s_bs, t_bs
         return batch
 
 

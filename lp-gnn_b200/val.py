@@ -126,29 +126,53 @@ def run(args):
 
 
 @torch.no_grad()
-def accuracy(logits, gt, num_cons, return_pr=False, dataset_name=""):
-    """Reference val.py:199-237: mean of constraint / variable accuracy, macro precision / recall of class 1."""
-    from sklearn import metrics
-    pred = inference_gnn(logits, num_cons)
-    pred_np, gt_np = pred.cpu().numpy(), gt.cpu().numpy()
-    if (pred_np[:num_cons] == 1).all():
+def accuracy_counts(logits, gt, num_cons):
+    """The integers behind ``accuracy`` without leaving the device: int32[12] = the 4 counts of ``lpgnn_basis_select``
+    (nodes with status 0 / 1 / 2, basic variables) followed by, per side, {#pred == gt, #pred == 1 and gt == 1, #pred == 1,
+    #gt == 1} (``lpgnn_basis_metrics``).  No host sync; a training loop reads it on the steps it logs."""
+    from . import _lib
+    lg = logits.float()
+    if not lg.is_cuda:
+        lg = lg.to(_device())
+    gt = gt.to(lg.device, torch.int64).contiguous()
+    m = int(num_cons)
+    n = lg.shape[0] - m
+    pred, sel = ops.basis_select(lg[:m], lg[m:], k_basic=m, int64=False, want_counts=True)
+    out = torch.empty(12, dtype=torch.int32, device=lg.device)
+    out[:4] = sel
+    with torch.cuda.device(lg.device):
+        rc = _lib.load().lpgnn_basis_metrics(pred.data_ptr(), 0, gt[:m].data_ptr(), m, gt[m:].data_ptr(), n, out[4:].data_ptr(),
+                                             _lib.stream_ptr())
+    _lib.check(rc, "lpgnn_basis_metrics")
+    return out
+
+
+def metrics_from_counts(c, m, n, return_pr=False, dataset_name=""):
+    """acc / precision / recall of reference val.py:199-237 from the 12 integers of ``accuracy_counts`` (sklearn's
+    ``precision_score`` / ``recall_score`` with ``labels=[1], average='macro'``: TP / #pred == 1 and TP / #gt == 1, 0 when
+    the denominator is empty)."""
+    c = [int(x) for x in c]
+    assert c[1] == m, (c, m)                              # #basic == number of rows (val.py:118-122)
+    if c[4 + 2] == m and m > 0:
         logging.warning("warning: may collapse, basis==all slacks")
-    acc1 = (gt_np[:num_cons] == pred_np[:num_cons]).mean()
-    acc2 = (gt_np[num_cons:] == pred_np[num_cons:]).mean()
-    stoch = bool(dataset_name) and "stoch" in dataset_name
-    if stoch:
-        acc1 = acc2
+    div = lambda a, b: a / b if b else 0.0
+    acc1, acc2 = div(c[4], m), div(c[8], n)
+    p1, p2 = div(c[5], c[6]), div(c[9], c[10])
+    r1, r2 = div(c[5], c[7]), div(c[9], c[11])
+    if bool(dataset_name) and "stoch" in dataset_name:    # stoch constraints are always labelled non-basic
+        acc1, p1, r1 = acc2, p2, r2
     acc = (acc1 + acc2) / 2.
-    if not return_pr:
-        return acc
-    kw = dict(labels=[1], average="macro", zero_division=0)
-    p1 = metrics.precision_score(gt_np[:num_cons], pred_np[:num_cons], **kw)
-    p2 = metrics.precision_score(gt_np[num_cons:], pred_np[num_cons:], **kw)
-    r1 = metrics.recall_score(gt_np[:num_cons], pred_np[:num_cons], **kw)
-    r2 = metrics.recall_score(gt_np[num_cons:], pred_np[num_cons:], **kw)
-    if stoch:
-        p1, r1 = p2, r2
-    return acc, (p1 + p2) / 2., (r1 + r2) / 2.
+    return (acc, (p1 + p2) / 2., (r1 + r2) / 2.) if return_pr else acc
+
+
+@torch.no_grad()
+def accuracy(logits, gt, num_cons, return_pr=False, dataset_name=""):
+    """Reference val.py:199-237: mean of constraint / variable accuracy, macro precision / recall of class 1.  The
+    basis decision and the confusion counts stay on the device; ONE read of twelve integers replaces the reference's
+    two vector copies + sklearn."""
+    m = int(num_cons)
+    c = accuracy_counts(logits, gt, m).tolist()
+    return metrics_from_counts(c, m, logits.shape[0] - m, return_pr, dataset_name)
 
 
 class InferenceManager:
