@@ -78,11 +78,17 @@ def write_sort_vars(fn, logits, m):
 
 
 @torch.no_grad()
-def predict_one(model, batch, dev, fp16=False):
-    """model -> logits -> (status uint8 [m+n], P(basic) [m+n]) on the host (pred_basis.py:70-85)."""
-    batch = batch_to(batch, dev, fp16)
-    lc, lv = model(batch)
-    lc, lv = lc[:batch.s_bs], lv[:batch.t_bs]
+def predict_one(model, batch, dev, fp16=False, args=None):
+    """model -> logits -> (status uint8 [m+n], P(basic) [m+n]) on the host (pred_basis.py:70-85).  LPs above
+    ``edge_num_thresh`` arrive unipartite (no ``x_s``) and go through ``val.model_inference_with_batch`` -- the sampled
+    full-neighbourhood path -- exactly as the reference routes EVERY batch (pred_basis.py:79)."""
+    if hasattr(batch, "x_s"):
+        batch = batch_to(batch, dev, fp16)
+        lc, lv = model(batch)
+        lc, lv = lc[:batch.s_bs], lv[:batch.t_bs]
+    else:
+        from .val import model_inference_with_batch
+        lc, lv = (t.to(dev).float() for t in model_inference_with_batch(model, batch, args))
     status = ops.basis_select(lc, lv, k_basic=lc.shape[0], int64=False)
     p1 = torch.softmax(torch.cat((lc, lv), 0), dim=-1)[:, 1]      # [m+n] values for the .sort file (tiny)
     return status.cpu().numpy(), p1.cpu().numpy(), lc.shape[0]
@@ -126,6 +132,11 @@ def run(args):
         loader = DataLoader(sub, batch_size=1, shuffle=False, num_workers=args.num_workers)
         names, hosts = [], []
         for batch in loader:
+            if not hasattr(batch, "x_s"):            # above edge_num_thresh: not packable, the per-LP sampled path takes it
+                fn = extract_fn(batch.processed_path[0])
+                status, _, m = predict_one(model, batch, dev, bool(args.fp16), args)
+                futures.append(pool.submit(write_bas_highs, f"{out_dir}/{fn}.bas", None, None, status[m:], status[:m]))
+                continue
             r, c, v = batch.edge_index._coo
             names.append(extract_fn(batch.processed_path[0]))
             hosts.append(pack_lp(r.numpy(), c.numpy(), v.numpy(), batch.x_s.numpy(), batch.x_t.numpy(),
@@ -137,18 +148,23 @@ def run(args):
         loader = DataLoader(sub, batch_size=1, shuffle=False, num_workers=args.num_workers)
         for batch in loader:
             fn = extract_fn(batch.processed_path[0])
-            status, p1, m = predict_one(model, batch, dev, bool(args.fp16))
+            status, p1, m = predict_one(model, batch, dev, bool(args.fp16), args)
             futures.append(pool.submit(write_bas_highs, f"{out_dir}/{fn}.bas", None, None, status[m:], status[:m]))
             futures.append(pool.submit(write_sort_vars, f"{out_dir}/{fn}.bas.sort", p1[m:], p1[:m]))
         # timing pass (pred_basis.py:157-178): model + basis decision per LP, inputs already on the device
         loader = DataLoader(sub, batch_size=1, shuffle=False, num_workers=args.num_workers)
         for batch in loader:
-            batch = batch_to(batch, dev, bool(args.fp16))
+            fn = extract_fn(batch.processed_path[0])
+            if hasattr(batch, "x_s"):
+                batch = batch_to(batch, dev, bool(args.fp16))
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            inference_only(model, batch)
+            if hasattr(batch, "x_s"):
+                inference_only(model, batch)
+            else:                                    # sampled path: sampling + forward per seed batch + basis decision
+                predict_one(model, batch, dev, bool(args.fp16), args)
             torch.cuda.synchronize()
-            times[extract_fn(batch.processed_path[0])] = time.perf_counter() - t0
+            times[fn] = time.perf_counter() - t0
     for f in futures:
         f.result()
     pool.shutdown()

@@ -64,31 +64,87 @@ def _shared_flat_view(grads):
     return torch.empty(0, dtype=g0.dtype, device=g0.device).set_(st, g0.storage_offset(), (end - g0.storage_offset(),))
 
 
+def _aligned_offsets(params):
+    """Offsets of the parameters in the flat gradient buffer of the native training step (16-byte aligned views)."""
+    offs = [0]
+    for p in params:
+        offs.append(offs[-1] + (p.numel() + 3) // 4 * 4)
+    return offs
+
+
 def allreduce_gradients(params, world):
     """Mean of the gradients over ranks with one collective.  NCCL over NVLink/NVSwitch on the GPU box; gloo in the
-    CPU tests.  Deterministic (fixed bucket layout).  Gradients of the native training step live in one flat buffer and
-    are reduced in place; otherwise flatten -> all_reduce(SUM) -> scale -> unflatten."""
+    CPU tests.  Deterministic (fixed bucket layout).  Every rank reduces a buffer of the SAME length whichever path
+    produced its gradients: the native step's flat buffer in place, anything else staged into that layout."""
     if world == 1:
         return
     from .training import consume_synced_backward
     if consume_synced_backward():              # reduced inside the native backward, overlapped with its second half
         return
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
+    params = [p for p in params if p.grad is not None]
+    if not params:
         return
+    grads = [p.grad for p in params]
     flat = _shared_flat_view(grads)
-    if flat is not None:                       # (alignment gaps of <= 3 floats between the views are reduced too: harmless)
+    offs = _aligned_offsets(params)
+    count = offs[-2] + params[-1].numel()
+    if flat is not None and flat.numel() == count:   # (alignment gaps of <= 3 floats between the views are reduced too: harmless)
         torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM)
         flat.mul_(1.0 / world)
         return
-    flat = torch.cat([g.reshape(-1) for g in grads])
+    flat = torch.zeros(count, dtype=grads[0].dtype, device=grads[0].device)
+    for g, o in zip(grads, offs):
+        flat[o:o + g.numel()].copy_(g.reshape(-1))
     torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM)
     flat.mul_(1.0 / world)
-    off = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
-        off += n
+    for g, o in zip(grads, offs):
+        g.copy_(flat[o:o + g.numel()].view_as(g))
+
+
+_host_group = [None]
+
+
+def host_group(world):
+    """gloo side group for host-side agreements between ranks (plain integers): going through the CPU keeps them off
+    the GPU stream, so an agreement never drains the launch queue the way a NCCL all-reduce + ``.item()`` would."""
+    if world == 1:
+        return None
+    if _host_group[0] is None:
+        dist = torch.distributed
+        _host_group[0] = dist.group.WORLD if dist.get_backend() == "gloo" else dist.new_group(backend="gloo")
+    return _host_group[0]
+
+
+def agreed_count(n_local, world):
+    """MAX over ranks of a per-rank step count: all ranks then take part in the same number of gradient collectives."""
+    if world == 1:
+        return int(n_local)
+    t = torch.tensor([int(n_local)], dtype=torch.int64)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=host_group(world))
+    return int(t[0])
+
+
+def idle_step(model, params, opt, world):
+    """A rank that has no k-th mini-batch where another rank has one (an empty graph, fewer sampled mini-batches for its
+    LP) joins the collective with ZERO gradients and applies the same averaged update: collective counts and replicas
+    stay identical, nothing hangs.  (The mean still divides by the world size.)"""
+    from . import training
+    offs = _aligned_offsets(params)
+    overlapped = training._gradient_sync[0] is not None and world > 1
+    flat = torch.zeros(offs[-1] if overlapped else offs[-2] + params[-1].numel(), dtype=params[0].dtype, device=params[0].device)
+    for p, o in zip(params, offs):
+        p.grad = flat[o:o + p.numel()].view_as(p)
+    if overlapped:     # the two collectives of an active rank's native backward (tail, then head), same cut
+        nh = len(getattr(model, "layers", []))
+        cut = offs[6 + 6 * (nh - 1)] if nh > 0 else offs[6]
+        handles = [training._gradient_sync[0](flat[cut:]), training._gradient_sync[0](flat[:cut])]
+        for h in handles:
+            if h is not None:
+                h.wait()
+        flat.mul_(training._gradient_sync[1])
+    else:
+        allreduce_gradients(params, world)
+    opt.step()
 
 
 def parse_args(argv=None, **defaults):
@@ -176,14 +232,22 @@ def run_exp(args):
                 break
             if hasattr(batch, "x_s"):                # already bipartite: one whole LP per step (train.py:103-104)
                 sub_loader = [batch]
+            elif batch.edge_index.shape[-1] == 0:    # train.py:106 skips empty graphs
+                sub_loader = []
             else:                                    # above edge_num_thresh: sampled mini-batches (train.py:105-116)
-                if batch.edge_index.shape[-1] == 0:
-                    continue
                 from .sampling import NeighborSubgraphLoader, ResidentLP, conv_depth
                 lp_res = ResidentLP.from_unipartite(batch, dev)
                 sub_loader = NeighborSubgraphLoader(lp_res, [6] * conv_depth(args.arch), min(args.batch_size, lp_res.num_nodes),
                                                     shuffle=True, drop_last=True, seed=args.seed + glstep)
-            for batch in sub_loader:
+            # data parallel: ranks whose LP yields fewer mini-batches (or none) than a peer's still join every gradient
+            # collective of this outer step (idle_step), so the collective count is rank-invariant
+            n_steps = agreed_count(len(sub_loader), world)
+            sub_iter = iter(sub_loader)
+            for _k in range(n_steps):
+                batch = next(sub_iter, None)
+                if batch is None:
+                    idle_step(model, params, opt, world)
+                    continue
                 batch.to(dev, non_blocking=True)
                 glstep += 1
                 logit_cons, logit_vars = model(batch)

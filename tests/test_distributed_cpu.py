@@ -69,3 +69,49 @@ def test_two_rank_gloo_broadcast_allreduce_and_sharding(tmp_path):
     for g0, gf0, gf1 in zip(r0["g"], r0["g_flat"], r1["g_flat"]):
         assert torch.equal(gf0, gf1) and torch.equal(gf0, g0)       # in-place flat path == flatten / unflatten path
     assert sorted(r0["shard"] + r1["shard"]) == list(range(11)) and not set(r0["shard"]) & set(r1["shard"])
+
+
+def _uneven_worker(rank, world, port, out_dir):
+    """Rank 0's LP yields 3 mini-batches, rank 1's only 1 (outer step 0); in outer step 1 rank 0 has an EMPTY graph
+    (0 mini-batches) and rank 1 has 2: the collective count must still be the same on both ranks (train.agreed_count /
+    train.idle_step), and the replicas must stay identical."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import arch, train
+    train.init_distributed(backend="gloo")
+    torch.manual_seed(0)
+    model = arch.GCN_FC(8, 8, hids=64, depth=3)
+    train.broadcast_parameters(model, world)
+    params = list(model.parameters())
+    opt = torch.optim.SGD(params, lr=0.1)
+    schedule = [[3, 1], [0, 2]]                                      # [outer step][rank] -> local mini-batches
+    gen = torch.Generator().manual_seed(50 + rank)
+    active = idle = 0
+    for counts in schedule:
+        n_steps = train.agreed_count(counts[rank], world)
+        assert n_steps == max(counts)
+        for k in range(n_steps):
+            if k < counts[rank]:
+                for p in params:                                     # a "backward pass": separate gradient tensors
+                    p.grad = torch.randn(p.shape, generator=gen)
+                train.allreduce_gradients(params, world)
+                opt.step()
+                active += 1
+            else:
+                train.idle_step(model, params, opt, world)
+                idle += 1
+    torch.save(dict(w=[p.detach().clone() for p in params], active=active, idle=idle), os.path.join(out_dir, f"u{rank}.pt"))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_gloo_uneven_minibatch_counts_do_not_hang_or_diverge(tmp_path):
+    world = 2
+    mp.spawn(_uneven_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = (torch.load(tmp_path / f"u{i}.pt") for i in range(world))
+    assert (r0["active"], r0["idle"]) == (3, 2) and (r1["active"], r1["idle"]) == (3, 2)
+    for a, b in zip(r0["w"], r1["w"]):
+        assert torch.equal(a, b)

@@ -92,6 +92,34 @@ def test_train_then_predict_basis_files(cuda, dataset_root, tmp_path):
         assert open(f"{log2}/pred-basis/{fn}.bas").read() == open(f"{log_dir}/pred-basis/{fn}.bas").read()
 
 
+def test_pred_basis_handles_lps_above_edge_num_thresh(cuda, dataset_root, tmp_path):
+    """LPs above ``edge_num_thresh`` stay unipartite in the loader (dataset.py:280-281); the reference routes every batch
+    through model_inference_with_batch (scripts/pred_basis.py:79), i.e. the sampled full-neighbourhood path.  Both modes
+    of ``pred_basis.run`` must write the same .bas files as with the threshold out of the way."""
+    from lpgnn_b200 import arch, pred_basis, train
+    torch.manual_seed(3)
+    model = arch.GCN_FC(8, 8, hids=64, depth=3)
+    ckpt = str(tmp_path / "mdl.pth")
+    model.save(ckpt)
+    outs = {}
+    for tag, extra in (("full", {}), ("above", dict(edge_num_thresh=100.0, batch_size=200)),
+                       ("above_packed", dict(edge_num_thresh=100.0, batch_size=200, packed=1))):
+        log_dir = str(tmp_path / tag) + "/"
+        args = train.parse_args([], arch="GCN_FC(8,8,hids=64,depth=3)", load_from=ckpt, dataset_processed_prefix=dataset_root,
+                                log_dir=log_dir, split="val", num_workers=0, **extra)
+        times = pred_basis.run(args)
+        files = sorted(f for f in os.listdir(log_dir + "pred-basis") if f.endswith(".bas"))
+        assert len(files) == 3
+        if not extra.get("packed"):
+            assert len(times) == 3 and all(t > 0 for t in times.values())
+        outs[tag] = {f: np.array(open(f"{log_dir}/pred-basis/{f}").read().splitlines()[3].split() +
+                                 open(f"{log_dir}/pred-basis/{f}").read().splitlines()[5].split(), dtype=np.int64) for f in files}
+    for f, full in outs["full"].items():
+        for tag in ("above", "above_packed"):
+            got = outs[tag][f]
+            assert got.shape == full.shape and np.mean(got == full) >= 0.995, (tag, f, np.mean(got == full))
+
+
 def test_val_inference_gnn_and_accuracy_accept_cpu_logits(cuda):
     """pred_basis.py:81-85 and train.py:132-137 hand CPU / detached logits to inference_gnn / accuracy."""
     import lpgnn_b200  # noqa: F401
