@@ -120,14 +120,14 @@ small_k_transform_kernel(const float* __restrict__ z, int32_t rows, const float*
                          OutT* __restrict__ out, int relu) {
   __shared__ __align__(16) float zs[kRows][KT];
   const int K = k_src + k_dst;
-  const int64_t row0 = (int64_t)blockIdx.y * kRows;
+  const int64_t row0 = (int64_t)blockIdx.x * kRows;      // row blocks on grid.x (2^31 - 1 blocks), column blocks on grid.y
   const int nrows = (int)min((int64_t)kRows, rows - row0);
   {
     const float4* src = reinterpret_cast<const float4*>(z + row0 * KT);
     float4* dst = reinterpret_cast<float4*>(&zs[0][0]);
     for (int i = threadIdx.x; i < nrows * KT / 4; i += kThreads) dst[i] = __ldg(src + i);
   }
-  const int c = blockIdx.x * kColsPerBlock + 2 * threadIdx.x;
+  const int c = blockIdx.y * kColsPerBlock + 2 * threadIdx.x;
   float2 w[KT];
   float2 bias = make_float2(0.f, 0.f);
   if (c < N) {
@@ -166,11 +166,11 @@ template <int KT>
 int launch(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const float* Xsrc, int k_src,
            const float* Xdst, int k_dst, const float* W_rel, const float* b_rel, const float* W_root, int N,
            void* out, int out_dtype, int relu, float* z, cudaStream_t st) {
-  LPGNN_REQUIRE(ceil_div(rows, kRows) <= 65535, "conv_in_fused: rows=%d exceeds the %d rows one launch covers", rows,
-                65535 * kRows);
+  LPGNN_REQUIRE(ceil_div(N, kColsPerBlock) <= 65535, "conv_in_fused: N=%d exceeds the %d columns one launch covers", N,
+                65535 * kColsPerBlock);
   gather_cat_kernel<KT, __nv_bfloat16><<<ceil_div((int64_t)rows * 8, kThreads), kThreads, 0, st>>>(
       ptr, idx, val, rows, Xsrc, k_src, Xdst, k_dst, z, nullptr);
-  dim3 grid(ceil_div(N, kColsPerBlock), ceil_div(rows, kRows));
+  dim3 grid(ceil_div(rows, kRows), ceil_div(N, kColsPerBlock));
   if (out_dtype == LPGNN_F32)
     small_k_transform_kernel<KT, float><<<grid, kThreads, 0, st>>>(z, rows, W_rel, k_src, W_root, k_dst, b_rel, N,
                                                                    reinterpret_cast<float*>(out), relu);

@@ -184,8 +184,12 @@ class MyToBipartite:
         src, dst = mapping[batch.edge_index[0]], mapping[batch.edge_index[1]]
         mask = src < ncons
         assert int(mask.sum()) * 2 == mask.shape[0]                               # dataset.py:297
-        batch.edge_index = BipartiteCSR.from_coo(src[mask], dst[mask] - ncons, batch.edge_attr[mask], ncons, nvars,
-                                                 is_sorted=bool(is_cons[:ncons].all()))
+        r, c = src[mask], dst[mask] - ncons
+        # canonical (row, col) order is CLAIMED to the device build only when it has been verified here: one pass over the
+        # composite keys (LPDataset.get always produces it; a hand-built graph with unsorted edges takes the sort path)
+        key = r * max(nvars, 1) + c
+        in_order = bool(is_cons[:ncons].all()) and (key.numel() < 2 or bool((key[1:] >= key[:-1]).all()))
+        batch.edge_index = BipartiteCSR.from_coo(r, c, batch.edge_attr[mask], ncons, nvars, is_sorted=in_order)
         del batch.edge_attr
         batch.x_s, batch.x_t = batch.x[is_cons, :], batch.x[is_vars, :]
         batch.y_s, batch.y_t = batch.y[is_cons], batch.y[is_vars]

@@ -316,3 +316,23 @@ def test_cta_pair_wgrad_is_bit_identical_to_single_cta(cuda):
     assert torch.equal(d0, d1)
     ref = dy.float().t() @ xx.float()
     assert float((d1 - ref).abs().max()) < 2e-3 * float(ref.abs().max())
+
+
+def test_conv_in_fused_above_the_old_grid_y_limit(cuda):
+    """fp32 input layer on more than 65535 * 64 rows (row blocks used to sit on gridDim.y): LPs below edge_num_thresh =
+    1.2e7 edges can have more nodes than that.  A diagonal-like graph keeps the expected values trivial."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    rows = 65535 * 64 + 70
+    ptr = torch.arange(rows + 1, dtype=torch.int32, device=cuda)            # one neighbour per row: node (i mod 1000)
+    idx = (torch.arange(rows, device=cuda) % 1000).to(torch.int32)
+    val = torch.full((rows,), 2.0, device=cuda)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x_src = torch.randn(1000, 8, device=cuda, generator=g)
+    x_dst = torch.randn(rows, 8, device=cuda, generator=g)
+    w_rel, w_root = torch.randn(64, 8, device=cuda, generator=g), torch.randn(64, 8, device=cuda, generator=g)
+    b = torch.randn(64, device=cuda, generator=g)
+    out, _ = ops.conv_in_fused((ptr, idx, val, rows), x_src, x_dst, w_rel, b, w_root, torch.float32, relu=True)
+    for r in (0, 1, 65535 * 64 - 1, 65535 * 64, rows - 1):
+        e = torch.relu((2.0 * x_src[r % 1000]) @ w_rel.T + b + x_dst[r] @ w_root.T)
+        assert torch.allclose(out[r], e, rtol=1e-5, atol=1e-5), r

@@ -174,3 +174,24 @@ def test_oracle_induced_subgraph_and_khop_expansion():
     assert list(cn) == [0, 2] and list(vn) == [0, 2]
     rowptr, col, val = port.induced_bipartite_subgraph(A, [2, 0], [2, 0])   # relabelled: rows (c2, c0), cols (v2, v0)
     assert list(rowptr) == [0, 1, 3] and list(col) == [0, 0, 1] and list(val) == [4., 2., 1.]
+
+
+def test_sorted_claim_is_only_made_for_verified_edge_order(pkg):
+    """MyToBipartite hands `is_sorted=True` to the device build only after checking the (row, col) order on the host: a
+    hand-built unipartite graph with constraint-first nodes but UNSORTED edges must take the sort path (a false claim
+    would leave rowptr entries unwritten, graph_build.cu prep_sorted_kernel)."""
+    from lpgnn_b200.dataset import MyToBipartite, UnipartiteData
+    m, n = 3, 4
+    row = np.array([0, 0, 1, 2, 2]); col = np.array([1, 3, 0, 2, 3]); val = np.arange(1, 6, dtype=np.float32)
+
+    def uni(order):
+        r, c, v = row[order], col[order] + m, val[order]
+        ei = torch.from_numpy(np.stack([np.concatenate([r, c]), np.concatenate([c, r])]))
+        ea = torch.from_numpy(np.concatenate([v, v]))
+        is_vars = torch.zeros(m + n, dtype=torch.long); is_vars[m:] = 1
+        return UnipartiteData(x=torch.zeros(m + n, 8), y=torch.zeros(m + n, dtype=torch.long), is_vars=is_vars,
+                              edge_index=ei, edge_attr=ea, num_nodes=m + n)
+
+    g_sorted = MyToBipartite()(uni(np.arange(5))).edge_index
+    g_unsorted = MyToBipartite()(uni(np.array([3, 0, 4, 2, 1]))).edge_index
+    assert g_sorted._sorted_hint is True and g_unsorted._sorted_hint is False
