@@ -29,10 +29,10 @@ def test_fused_losses_match_framework_ops(cuda, name, m, n, cs, ct):
     ref_fn = {"balanced": losses.balanced_torch, "unbalanced": losses.unbalanced_torch, "focal": losses.focal_torch}[name]
 
     def run(fn, dev, scale):
-        a, b = lc.to(dev).requires_grad_(), lv.to(dev).requires_grad_()
+        a, b = lc.detach().clone().to(dev).requires_grad_(), lv.detach().clone().to(dev).requires_grad_()
         loss = fn(a, b, ys.to(dev), yt.to(dev))
         (loss * scale).backward()                    # a non-trivial upstream gradient
-        return float(loss), a.grad.cpu(), b.grad.cpu()
+        return float(loss.detach()), a.grad.cpu(), b.grad.cpu()
 
     ref = run(ref_fn, "cpu", 0.7)
     got = run(losses.LOSSES[name], cuda, 0.7)
@@ -87,6 +87,6 @@ def test_accuracy_counters_match_sklearn_on_the_reference_formula(cuda, m, n, se
     if stoch:
         a1, p1, r1 = a2, p2, r2
     assert abs(acc - (a1 + a2) / 2) < 1e-12 and abs(prec - (p1 + p2) / 2) < 1e-12 and abs(recl - (r1 + r2) / 2) < 1e-12
-    assert val.accuracy(logits, gt, m) == acc                      # CPU-resident inputs, scalar form
+    assert val.accuracy(logits, gt, m, dataset_name=name) == acc                      # CPU-resident inputs, scalar form
     counts = val.accuracy_counts(logits.to(cuda), gt.to(cuda), m)
     assert counts.is_cuda and counts.dtype == torch.int32 and counts.shape == (12,)
