@@ -126,6 +126,9 @@ class NeighborSubgraphLoader:
         return full if (self.drop_last or rem == 0) else full + 1
 
     def __iter__(self):
+        """Mini-batch k+1's node sampling is ENQUEUED BEFORE mini-batch k is handed out: on the (in-order) stream it runs
+        ahead of the consumer's training step k, so when the consumer comes back for batch k+1 its sizes are already on
+        the host and the one host read never waits for an idle GPU."""
         lp = self.lp
         if self.shuffle:
             gen = torch.Generator(device="cpu").manual_seed(self.seed + 7919 * self.epoch)
@@ -133,15 +136,25 @@ class NeighborSubgraphLoader:
         else:
             order = torch.arange(lp.num_nodes, device=lp.device)
         self.epoch += 1
-        for b in range(len(self)):
-            yield self.sample(order[b * self.batch_size:(b + 1) * self.batch_size], salt=self.epoch * 1_000_003 + b)
+        nb = len(self)
+        seeds_of = lambda b: order[b * self.batch_size:(b + 1) * self.batch_size]
+        salt_of = lambda b: self.epoch * 1_000_003 + b
+        pending = self._stage_a(seeds_of(0), salt_of(0)) if nb else None
+        for b in range(nb):
+            batch = self._stage_b(pending)
+            pending = self._stage_a(seeds_of(b + 1), salt_of(b + 1)) if b + 1 < nb else None
+            yield batch
 
     def sample(self, seeds, salt=0) -> Data:
+        return self._stage_b(self._stage_a(seeds, salt))
+
+    def _stage_a(self, seeds, salt):
+        """Node sets + row offsets of the induced subgraph on the device, sizes on their way to the host."""
         import ctypes as C
         lp, dev = self.lp, self.lp.device
         lib = _lib.load()
         g = lp.graph if not lp.graph._transposed else lp.graph.t()
-        (rowptr, col, val, _), (colptr, row_csc, _, _) = g.views()
+        (rowptr, col, _, _), (colptr, row_csc, _, _) = g.views()
         seeds = seeds.to(dev, torch.int64).contiguous()
         ns = int(seeds.numel())
         if self._buf is None or ns > self._buf.max_seeds:
@@ -160,9 +173,22 @@ class NeighborSubgraphLoader:
                                                  B.map_v.data_ptr(), B.offsets.data_ptr(), B.sizes.data_ptr(), B.ws.data_ptr(),
                                                  B.ws_bytes, st), "lpgnn_induced_offsets")
             B.sizes_host.copy_(B.sizes, non_blocking=True)
-            torch.cuda.current_stream().synchronize()             # the one host read of the mini-batch
-            sz = B.sizes_host.tolist()
-            mc, nv, s_bs, t_bs, z = sz[0], sz[1], sz[2], sz[3], sz[B.sizes_len - 2]
+            ev = torch.cuda.Event()
+            ev.record()
+        return ns, ev, seeds                  # (seeds kept alive until the kernels that read them have been enqueued)
+
+    def _stage_b(self, pending) -> Data:
+        """The one host read (sizes), then the sorted induced COO, the graph build and the feature gathers."""
+        ns, ev, _ = pending
+        lp, dev, B = self.lp, self.lp.device, self._buf
+        lib = _lib.load()
+        g = lp.graph if not lp.graph._transposed else lp.graph.t()
+        (rowptr, col, val, _), _ = g.views()
+        ev.synchronize()
+        sz = B.sizes_host.tolist()
+        mc, nv, s_bs, t_bs, z = sz[0], sz[1], sz[2], sz[3], sz[B.sizes_len - 2]
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr()
             cons_nodes, var_nodes = B.cons_nodes[:mc].clone(), B.var_nodes[:nv].clone()
             row = torch.empty(z, dtype=torch.int32, device=dev)
             colo = torch.empty(z, dtype=torch.int32, device=dev)
