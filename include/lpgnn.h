@@ -294,6 +294,11 @@ LPGNN_API int lpgnn_basis_select(const float* logits_cons, int32_t m, const floa
                        int32_t k_basic, void* status, int status_is_i64, int32_t* counts_out,
                        void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
 
+/* Tuning knob (process-wide): lpgnn_basis_select runs as ONE cooperative launch (keys in registers, 3-digit radix select
+ * with grid-wide barriers) wherever the nodes fit the co-resident grid (default), or always as the 7-launch chain
+ * (enable = 0).  Same statuses either way.  Returns the previous setting. */
+LPGNN_API int lpgnn_set_select_fused(int enable);
+
 /* Segmented variant for a block-diagonal PACK of LPs: segment b owns constraints
  * [cons_ptr[b], cons_ptr[b+1]) of logits_cons and variables [vars_ptr[b], vars_ptr[b+1]) of logits_vars and
  * gets exactly (cons_ptr[b+1]-cons_ptr[b]) basic nodes (val.inference_gnn applied per LP).  One CTA per

@@ -124,6 +124,7 @@ SIGNATURES = {
     "lpgnn_flat_ce_workspace_bytes": (_sz, [_i32, _i32]),
     "lpgnn_flat_ce": (_int, [_p, _p, _i32, _p, _p, _i32, _int, C.c_float, _p, _p, _p, _p, _p, _sz, _p]),
     "lpgnn_basis_metrics": (_int, [_p, _int, _p, _i32, _p, _i32, _p, _p]),
+    "lpgnn_set_select_fused": (_int, [_int]),
     "lpgnn_basis_select_workspace_bytes": (_sz, [_i64]),
     "lpgnn_basis_select": (_int, [_p, _i32, _p, _i32, _i32, _p, _int, _p, _p, _sz, _p]),
 }

@@ -12,6 +12,8 @@
 //      ranks: deterministic; torch.topk leaves the tie order implementation-defined)
 //   4. status = 1 if selected else side.
 // HBM-bound integer/byte work: (m+n)*(12 + 4 + 1) bytes in pass 1, (m+n)*4 per select pass.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace lpgnn {
@@ -280,8 +282,183 @@ segmented_select_kernel(const float* __restrict__ lc, const float* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------ one-launch variant
+// The whole decision as ONE cooperative kernel: every thread keeps its nodes' keys in registers (contiguous nodes per
+// thread, so thread order == node order), the k-th largest key is found by a 3-digit MSB radix select (11 + 11 + 10
+// bits) with a grid-wide barrier after each histogram, every block re-derives the threshold from the global histogram,
+// and the ordered tie break (rare: only when the threshold key occurs more often than it is needed) costs one more
+// barrier.  Replaces the 7-launch chain above for everything that fits the co-resident grid (~4.8M nodes); at BASELINE
+// C2 size (150K nodes) the chain was pure launch latency (~50 us for 2.5 MB of traffic).
+namespace cg = cooperative_groups;
+constexpr int kSelThreads = 512;
+constexpr int kBins = 2048;
+
+struct Pick { uint32_t digit, above, at; };   // chosen digit, #keys with a larger digit, #keys in the chosen bin
+
+// exclusive prefix of v over the block in thread order (512 threads); *total = block sum
+__device__ __forceinline__ uint32_t sel_block_exclusive(uint32_t v, uint32_t* wsum /*[16]*/, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+  __syncthreads();                       // wsum may still be read from a previous call
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  uint32_t before = 0, all = 0;
+#pragma unroll
+  for (int w = 0; w < kSelThreads / 32; ++w) { const uint32_t x = wsum[w]; if (w < warp) before += x; all += x; }
+  *total = all;
+  return before + incl - v;
+}
+
+// Every block: the digit d with count(digit > d) < k_rem <= count(digit >= d) in the global histogram of this pass.
+__device__ __forceinline__ Pick block_pick(const uint32_t* __restrict__ ghist, uint32_t k_rem, uint32_t* wsum, Pick* pick_s) {
+  const int t = threadIdx.x;
+  uint32_t c[kBins / kSelThreads], s = 0;      // thread t owns bins 2047-4t .. 2044-4t (descending digits)
+#pragma unroll
+  for (int j = 0; j < kBins / kSelThreads; ++j) { c[j] = __ldcg(ghist + (kBins - 1 - (kBins / kSelThreads) * t - j)); s += c[j]; }
+  uint32_t total;
+  const uint32_t before = sel_block_exclusive(s, wsum, &total);
+  if (before < k_rem && k_rem <= before + s) {
+    uint32_t acc = before;
+    int j = 0;
+    for (; j < kBins / kSelThreads - 1; ++j) { if (acc + c[j] >= k_rem) break; acc += c[j]; }
+    pick_s->digit = (uint32_t)(kBins - 1 - (kBins / kSelThreads) * t - j);
+    pick_s->above = acc;
+    pick_s->at = c[j];
+  }
+  __syncthreads();
+  return *pick_s;
+}
+
+template <int MAXI, typename OutT>
+__global__ void __launch_bounds__(kSelThreads, 2)
+select_fused_kernel(const float* __restrict__ lc, int32_t m, const float* __restrict__ lv, int32_t n, uint32_t k, int ipt,
+                    uint32_t* __restrict__ hist /*[3][kBins], zeroed*/, uint32_t* __restrict__ tile_ties /*[grid]*/,
+                    OutT* __restrict__ status, int32_t* __restrict__ counts) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ uint32_t h[kBins];
+  __shared__ uint32_t wsum[kSelThreads / 32];
+  __shared__ Pick pick_s;
+  __shared__ int32_t c_s[4];
+  const int t = threadIdx.x;
+  const int64_t total = (int64_t)m + n;
+  const int64_t base = ((int64_t)blockIdx.x * kSelThreads + t) * ipt;
+  if (t < 4) c_s[t] = 0;
+  for (int i = t; i < kBins; i += kSelThreads) h[i] = 0;
+  __syncthreads();
+  // ---- softmax keys (bit pattern of p1; p1 >= 0 so unsigned order == float order) + the {0,2} side bit
+  uint32_t key[MAXI];
+  uint32_t side2 = 0;
+#pragma unroll
+  for (int j = 0; j < MAXI; ++j) {
+    key[j] = 0;
+    const int64_t i = base + j;
+    if (j < ipt && i < total) {
+      const float* p = (i < m) ? (lc + i * 3) : (lv + (i - m) * 3);
+      const float x0 = p[0], x1 = p[1], x2 = p[2];
+      const float mx = fmaxf(x0, fmaxf(x1, x2));
+      const float e0 = expf(x0 - mx), e1 = expf(x1 - mx), e2 = expf(x2 - mx);
+      const float sum = e0 + e1 + e2;
+      const float p0 = nan_to_zero(e0 / sum), p1 = nan_to_zero(e1 / sum), p2 = nan_to_zero(e2 / sum);
+      key[j] = __float_as_uint(p1);
+      if (!(p0 >= p2)) side2 |= 1u << j;
+      atomicAdd(&h[key[j] >> 21], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = t; i < kBins; i += kSelThreads) if (h[i]) atomicAdd(&hist[i], h[i]);
+  uint32_t thr = 0xffffffffu, k_rem = 0, n_ties = 0;
+  if (k > 0) {                                                 // (k == 0: threshold above every key, nothing selected)
+    grid.sync();
+    const Pick p0 = block_pick(hist, k, wsum, &pick_s);
+    k_rem = k - p0.above;
+    // ---- second digit (bits 10..20) over the keys that share the first
+#pragma unroll
+    for (int j = 0; j < MAXI; ++j)
+      if (j < ipt && base + j < total && (key[j] >> 21) == p0.digit) atomicAdd(&hist[kBins + ((key[j] >> 10) & 0x7ffu)], 1u);
+    grid.sync();
+    const Pick p1 = block_pick(hist + kBins, k_rem, wsum, &pick_s);
+    k_rem -= p1.above;
+    const uint32_t hi22 = (p0.digit << 11) | p1.digit;
+#pragma unroll
+    for (int j = 0; j < MAXI; ++j)
+      if (j < ipt && base + j < total && (key[j] >> 10) == hi22) atomicAdd(&hist[2 * kBins + (key[j] & 0x3ffu)], 1u);
+    grid.sync();
+    const Pick p2 = block_pick(hist + 2 * kBins, k_rem, wsum, &pick_s);
+    k_rem -= p2.above;
+    thr = (hi22 << 10) | p2.digit;
+    n_ties = p2.at;
+  }
+  // ---- ties at the threshold: all of them are taken unless the key occurs more often than needed; then the lowest
+  //      node indices win (block counts + grid barrier + in-block ranks: deterministic)
+  uint32_t before = 0;
+  const bool ordered = k_rem < n_ties;
+  if (ordered) {
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < MAXI; ++j) mine += (j < ipt && base + j < total && key[j] == thr);
+    uint32_t blk;
+    const uint32_t rank = sel_block_exclusive(mine, wsum, &blk);
+    if (t == 0) tile_ties[blockIdx.x] = blk;
+    grid.sync();
+    uint32_t part = 0;
+    for (int i = t; i < (int)blockIdx.x; i += kSelThreads) part += __ldcg(tile_ties + i);
+    uint32_t prev;
+    (void)sel_block_exclusive(part, wsum, &prev);
+    before = prev + rank;
+  }
+  int32_t n0 = 0, n1 = 0, n2 = 0, nbv = 0;
+#pragma unroll
+  for (int j = 0; j < MAXI; ++j) {
+    const int64_t i = base + j;
+    if (j < ipt && i < total) {
+      bool sel = key[j] > thr;
+      if (key[j] == thr) { sel = !ordered || before < k_rem; ++before; }
+      const int s = sel ? 1 : (int)((side2 >> j) & 1u) * 2;
+      status[i] = (OutT)s;
+      n0 += (s == 0); n1 += (s == 1); n2 += (s == 2); nbv += (s == 1 && i >= m);
+    }
+  }
+  if (counts) {
+    if (n0) atomicAdd(&c_s[0], n0);
+    if (n1) atomicAdd(&c_s[1], n1);
+    if (n2) atomicAdd(&c_s[2], n2);
+    if (nbv) atomicAdd(&c_s[3], nbv);
+    __syncthreads();
+    if (t < 4 && c_s[t]) atomicAdd(&counts[t], c_s[t]);
+  }
+}
+
+template <int MAXI, typename OutT>
+int launch_fused(const float* lc, int32_t m, const float* lv, int32_t n, uint32_t k, int ipt, int grid, uint32_t* hist,
+                 uint32_t* ties, void* status, int32_t* counts, cudaStream_t st) {
+  OutT* out = reinterpret_cast<OutT*>(status);
+  void* args[] = {(void*)&lc, (void*)&m, (void*)&lv, (void*)&n, (void*)&k, (void*)&ipt, (void*)&hist, (void*)&ties, (void*)&out,
+                  (void*)&counts};
+  LPGNN_CUDA_OK(cudaLaunchCooperativeKernel((const void*)select_fused_kernel<MAXI, OutT>, dim3(grid), dim3(kSelThreads), args, 0, st));
+  return LPGNN_OK;
+}
+
+// co-resident blocks of the fused kernel on this device (smallest over the instantiations that may be picked)
+int fused_capacity() {
+  static int cap = -1;
+  if (cap < 0) {
+    int per_sm = 0, coop = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, select_fused_kernel<16, int64_t>, kSelThreads, 0) != cudaSuccess)
+      per_sm = 0;
+    cudaGetLastError();
+    cap = per_sm * sm_count();
+  }
+  return cap;
+}
+
+int g_select_fused = 1;   // 0 forces the multi-launch chain (lpgnn_set_select_fused, for A/B measurements and tests)
+
 struct Layout {
-  size_t keys, side, hist, state, ties, total;
+  size_t keys, side, hist, state, ties, fhist, fties, total;
 };
 Layout layout(int64_t total_nodes) {
   Layout L;
@@ -292,6 +469,8 @@ Layout layout(int64_t total_nodes) {
   L.hist = off; off += 4 * 256 * 4;
   L.state = off; off += 256;
   L.ties = off; off += align_up(((t + kTile - 1) / kTile + 1) * 4, 256);
+  L.fhist = off; off += 3 * kBins * 4;                 // one-launch variant: three digit histograms ...
+  L.fties = off; off += 4096 * 4;                      // ... and per-block tie counts (grid <= 4096 blocks)
   L.total = off;
   return L;
 }
@@ -328,9 +507,32 @@ extern "C" int lpgnn_basis_select(const float* logits_cons, int32_t m, const flo
   void* state = w + L.state;
   uint32_t* ties = reinterpret_cast<uint32_t*>(w + L.ties);
 
+  const uint32_t k = (uint32_t)k_basic;
+  // ---- one cooperative launch when the nodes fit the co-resident grid with <= 16 keys per thread
+  const int cap = g_select_fused ? min(fused_capacity(), 4096) : 0;
+  if (cap > 0 && total <= (int64_t)cap * kSelThreads * 16) {
+    uint32_t* fhist = reinterpret_cast<uint32_t*>(w + L.fhist);
+    uint32_t* fties = reinterpret_cast<uint32_t*>(w + L.fties);
+    const int want = ceil_div(total, kSelThreads);
+    const int grid = want < cap ? want : cap;
+    const int ipt = ceil_div(total, (int64_t)grid * kSelThreads);
+    LPGNN_CUDA_OK(cudaMemsetAsync(fhist, 0, 3 * kBins * 4, st));
+    if (counts_out) LPGNN_CUDA_OK(cudaMemsetAsync(counts_out, 0, 4 * sizeof(int32_t), st));
+    int rc;
+    if (status_is_i64)
+      rc = ipt <= 1 ? launch_fused<1, int64_t>(logits_cons, m, logits_vars, n, k, ipt, grid, fhist, fties, status, counts_out, st)
+         : ipt <= 4 ? launch_fused<4, int64_t>(logits_cons, m, logits_vars, n, k, ipt, grid, fhist, fties, status, counts_out, st)
+                    : launch_fused<16, int64_t>(logits_cons, m, logits_vars, n, k, ipt, grid, fhist, fties, status, counts_out, st);
+    else
+      rc = ipt <= 1 ? launch_fused<1, uint8_t>(logits_cons, m, logits_vars, n, k, ipt, grid, fhist, fties, status, counts_out, st)
+         : ipt <= 4 ? launch_fused<4, uint8_t>(logits_cons, m, logits_vars, n, k, ipt, grid, fhist, fties, status, counts_out, st)
+                    : launch_fused<16, uint8_t>(logits_cons, m, logits_vars, n, k, ipt, grid, fhist, fties, status, counts_out, st);
+    if (rc) return rc;
+    count_launches(1);
+    return LPGNN_OK;
+  }
   const int grid_stride = min(ceil_div(total, kThreads), sm_count() * 8);
   const int ntiles = ceil_div(total, kTile);
-  const uint32_t k = (uint32_t)k_basic;
   (void)state;
   init_hist_kernel<<<1, 256, 0, st>>>(hist, counts_out);
   softmax_key_kernel<<<grid_stride, kThreads, 0, st>>>(logits_cons, m, logits_vars, n, keys, side, hist);
@@ -375,4 +577,12 @@ extern "C" int lpgnn_basis_select_segmented(const float* logits_cons, const floa
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;
+}
+
+// Tuning knob: 1 (default) = the one-launch cooperative kernel where it fits, 0 = always the multi-launch chain.  Both
+// produce the same statuses (same keys, same threshold, same ascending-index tie rule).  Returns the previous setting.
+extern "C" int lpgnn_set_select_fused(int enable) {
+  const int prev = lpgnn::g_select_fused;
+  lpgnn::g_select_fused = enable ? 1 : 0;
+  return prev;
 }

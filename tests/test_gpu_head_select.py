@@ -103,3 +103,37 @@ def test_basis_select_k_zero_and_all(cuda):
     lv = torch.from_numpy(rng.standard_normal((20, 3)).astype(np.float32)).to(cuda)
     assert int((ops.basis_select(lc, lv, k_basic=0) == 1).sum()) == 0
     assert int((ops.basis_select(lc, lv, k_basic=30) == 1).sum()) == 30
+
+
+@pytest.mark.parametrize("m,n,quant", [(1, 1, 0), (5, 7, 0), (1000, 2000, 0), (50_000, 100_000, 0), (50_000, 100_000, 8),
+                                        (300_000, 500_000, 64), (700_000, 1_500_000, 0), (2049, 4097, 2)])
+@pytest.mark.parametrize("int64", [False, True])
+def test_one_launch_select_equals_the_launch_chain(cuda, m, n, quant, int64):
+    """The cooperative one-launch kernel (keys in registers, 11+11+10-bit radix select with grid barriers) against the
+    7-launch chain: identical statuses and counts, including heavy ties at the threshold (quantised logits), k = 0 / all
+    and sizes above the fused path's capacity (where both calls take the chain)."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import _lib, ops
+    lib = _lib.load()
+    rng = np.random.default_rng(m + quant)
+    lc = (rng.standard_normal((m, 3)) * 4).astype(np.float32)
+    lv = (rng.standard_normal((n, 3)) * 4).astype(np.float32)
+    if quant:                                                # few distinct values -> many nodes share the threshold key
+        lc, lv = np.round(lc * quant / 16) / quant, np.round(lv * quant / 16) / quant
+    tc, tv = torch.from_numpy(lc.astype(np.float32)).to(cuda), torch.from_numpy(lv.astype(np.float32)).to(cuda)
+    for k in (None, 0, m + n, max(1, (m + n) // 3)):
+        prev = lib.lpgnn_set_select_fused(1)
+        try:
+            torch.cuda.synchronize()
+            before = lib.lpgnn_launch_count()
+            s1, c1 = ops.basis_select(tc, tv, k_basic=k, int64=int64, want_counts=True)
+            fused_launches = lib.lpgnn_launch_count() - before
+            lib.lpgnn_set_select_fused(0)
+            s0, c0 = ops.basis_select(tc, tv, k_basic=k, int64=int64, want_counts=True)
+        finally:
+            lib.lpgnn_set_select_fused(prev)
+        assert torch.equal(s1, s0) and torch.equal(c1, c0), (k, int((s1 != s0).sum()))
+        if m + n <= 1_000_000:
+            assert fused_launches == 1
+        kk = m if k is None else k
+        assert int((s1 == 1).sum()) == kk
