@@ -13,6 +13,8 @@
 // CSR  = sort by column digits, then by row digits (LSD over the composite key).
 // CSC  = stable sort of the CSR entries by column only (CSR order already breaks ties by row).
 // HBM-bound integer work; roofline = bytes moved per pass (12 B in + 12 B out per entry... see DESIGN.md).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace lpgnn {
@@ -51,12 +53,11 @@ __global__ void gather_entry_kernel(const uint32_t* __restrict__ col_src, const 
 // Sorted-COO fast path in ONE pass over the entries: verify the (row, col) order and the index range, emit the
 // CSR payload (col, val), fill rowptr from the row boundaries and set up the (key = col, payload = position)
 // pairs of the CSC sort.
-__global__ void prep_sorted_kernel(const uint32_t* __restrict__ row, const uint32_t* __restrict__ col,
-                                   const float* __restrict__ val, int64_t n, uint32_t m, uint32_t ncols,
-                                   uint32_t* __restrict__ col_out, float* __restrict__ val_out,
-                                   int32_t* __restrict__ rowptr, uint32_t* __restrict__ keys,
-                                   uint32_t* __restrict__ vals, uint32_t* __restrict__ status) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+__device__ __forceinline__ void prep_sorted_entry(int64_t e, const uint32_t* __restrict__ row, const uint32_t* __restrict__ col,
+                                                  const float* __restrict__ val, int64_t n, uint32_t m, uint32_t ncols,
+                                                  uint32_t* __restrict__ col_out, float* __restrict__ val_out,
+                                                  int32_t* __restrict__ rowptr, uint32_t* __restrict__ keys,
+                                                  uint32_t* __restrict__ vals, uint32_t* __restrict__ status) {
   if (e > n) return;
   const int64_t prev = (e == 0) ? -1 : (int64_t)row[e - 1];
   int64_t cur = (int64_t)m;
@@ -76,14 +77,22 @@ __global__ void prep_sorted_kernel(const uint32_t* __restrict__ row, const uint3
   for (int64_t q = prev + 1; q <= cur && q <= (int64_t)m; ++q) rowptr[q] = (int32_t)e;
 }
 
+__global__ void prep_sorted_kernel(const uint32_t* __restrict__ row, const uint32_t* __restrict__ col,
+                                   const float* __restrict__ val, int64_t n, uint32_t m, uint32_t ncols,
+                                   uint32_t* __restrict__ col_out, float* __restrict__ val_out,
+                                   int32_t* __restrict__ rowptr, uint32_t* __restrict__ keys,
+                                   uint32_t* __restrict__ vals, uint32_t* __restrict__ status) {
+  prep_sorted_entry(blockIdx.x * (int64_t)blockDim.x + threadIdx.x, row, col, val, n, m, ncols, col_out, val_out, rowptr, keys,
+                    vals, status);
+}
+
 // CSC payload + colptr in one pass: csr2csc[k] = perm[k], row_csc[k] = rows[perm[k]], val_csc[k] = val[perm[k]],
 // colptr from the boundaries of the sorted column keys.
-__global__ void finish_csc_kernel(const uint32_t* __restrict__ rows, const float* __restrict__ val,
-                                  const uint32_t* __restrict__ sorted_cols, const uint32_t* __restrict__ perm,
-                                  int64_t n, int32_t ncols, uint32_t* __restrict__ csr2csc,
-                                  uint32_t* __restrict__ row_csc, float* __restrict__ val_csc,
-                                  int32_t* __restrict__ colptr) {
-  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+__device__ __forceinline__ void finish_csc_entry(int64_t k, const uint32_t* __restrict__ rows, const float* __restrict__ val,
+                                                 const uint32_t* __restrict__ sorted_cols, const uint32_t* __restrict__ perm,
+                                                 int64_t n, int32_t ncols, uint32_t* __restrict__ csr2csc,
+                                                 uint32_t* __restrict__ row_csc, float* __restrict__ val_csc,
+                                                 int32_t* __restrict__ colptr) {
   if (k > n) return;
   const int64_t prev = (k == 0) ? -1 : (int64_t)sorted_cols[k - 1];
   int64_t cur = ncols;
@@ -95,6 +104,15 @@ __global__ void finish_csc_kernel(const uint32_t* __restrict__ rows, const float
     cur = min((int64_t)sorted_cols[k], (int64_t)ncols);
   }
   for (int64_t q = prev + 1; q <= cur; ++q) colptr[q] = (int32_t)k;
+}
+
+__global__ void finish_csc_kernel(const uint32_t* __restrict__ rows, const float* __restrict__ val,
+                                  const uint32_t* __restrict__ sorted_cols, const uint32_t* __restrict__ perm,
+                                  int64_t n, int32_t ncols, uint32_t* __restrict__ csr2csc,
+                                  uint32_t* __restrict__ row_csc, float* __restrict__ val_csc,
+                                  int32_t* __restrict__ colptr) {
+  finish_csc_entry(blockIdx.x * (int64_t)blockDim.x + threadIdx.x, rows, val, sorted_cols, perm, n, ncols, csr2csc, row_csc,
+                   val_csc, colptr);
 }
 
 // plain copy as a kernel (a cudaMemcpyAsync D2D costs ~10x a small kernel on the launch path)
@@ -116,14 +134,14 @@ __global__ void expand_check_range_kernel(const uint32_t* __restrict__ row, cons
   if (i < n && (row[i] >= m || col[i] >= ncols)) atomicOr(flag, 2u);
 }
 
-__global__ void __launch_bounds__(kSortThreads)
-radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int radix_bits,
-                  uint32_t* __restrict__ counts, int nblocks) {
+__device__ __forceinline__ void radix_hist_tile(int bid, const uint32_t* __restrict__ keys, int64_t n, int shift, int radix_bits,
+                                                uint32_t* __restrict__ counts, int nblocks) {
   __shared__ uint32_t h[kMaxRadix];
   const int radix = 1 << radix_bits;
+  __syncthreads();                       // (a previous tile of the same block may still be reading h)
   for (int d = threadIdx.x; d < radix; d += kSortThreads) h[d] = 0;
   __syncthreads();
-  const int64_t base = (int64_t)blockIdx.x * kSortTile;
+  const int64_t base = (int64_t)bid * kSortTile;
   uint32_t k[kSortRounds];
 #pragma unroll
   for (int r = 0; r < kSortRounds; ++r) {
@@ -136,17 +154,23 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int r
     if (i < n) atomicAdd(&h[(k[r] >> shift) & (radix - 1)], 1u);  // integer counts: order-free
   }
   __syncthreads();
-  for (int d = threadIdx.x; d < radix; d += kSortThreads) counts[(size_t)d * nblocks + blockIdx.x] = h[d];
+  for (int d = threadIdx.x; d < radix; d += kSortThreads) counts[(size_t)d * nblocks + bid] = h[d];
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int radix_bits,
+                  uint32_t* __restrict__ counts, int nblocks) {
+  radix_hist_tile(blockIdx.x, keys, n, shift, radix_bits, counts, nblocks);
 }
 
 // One block per digit d: exclusive scan of counts[d][0..nblocks) in place (coalesced) and the digit's
 // total into totals[d].  The scatter kernel turns the totals into digit bases itself.
-__global__ void __launch_bounds__(kSortThreads)
-scan_digit_rows_kernel(uint32_t* __restrict__ counts, int nblocks, uint32_t* __restrict__ totals) {
+__device__ __forceinline__ void scan_digit_row(int digit, uint32_t* __restrict__ counts, int nblocks, uint32_t* __restrict__ totals) {
   __shared__ uint32_t warp_sum[kSortThreads / 32];
   __shared__ uint32_t carry_s;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  uint32_t* row = counts + (size_t)blockIdx.x * nblocks;
+  uint32_t* row = counts + (size_t)digit * nblocks;
+  __syncthreads();
   if (t == 0) carry_s = 0;
   __syncthreads();
   for (int base = 0; base < nblocks; base += kSortThreads) {
@@ -167,7 +191,12 @@ scan_digit_rows_kernel(uint32_t* __restrict__ counts, int nblocks, uint32_t* __r
     if (t == kSortThreads - 1) carry_s = before + incl;
     __syncthreads();
   }
-  if (t == 0) totals[blockIdx.x] = carry_s;
+  if (t == 0) totals[digit] = carry_s;
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+scan_digit_rows_kernel(uint32_t* __restrict__ counts, int nblocks, uint32_t* __restrict__ totals) {
+  scan_digit_row(blockIdx.x, counts, nblocks, totals);
 }
 
 // Stable scatter.  Warp w owns the contiguous slice [base + w*256, base + (w+1)*256) of the tile and
@@ -175,17 +204,17 @@ scan_digit_rows_kernel(uint32_t* __restrict__ counts, int nblocks, uint32_t* __r
 // memory: the rank of an item inside its digit = (items of that digit in earlier rounds of the warp)
 // + (match-any rank inside the round).  One block-wide exclusive prefix over the 8 warp rows then
 // gives every item its global slot.  No atomics on ordered data -> deterministic and stable.
-__global__ void __launch_bounds__(kSortThreads)
-radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
-                     int radix_bits, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ totals,
-                     int nblocks) {
+__device__ __forceinline__ void radix_scatter_tile(int bid, const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n,
+                                                   int shift, int radix_bits, const uint32_t* __restrict__ offsets,
+                                                   const uint32_t* __restrict__ totals, int nblocks) {
   constexpr int kWarps = kSortThreads / 32;
   __shared__ uint32_t goff[kMaxRadix];          // global start of (digit, this block)
   __shared__ uint32_t dbase[kMaxRadix];         // exclusive scan of the digit totals
   __shared__ uint32_t wcnt[kWarps][kMaxRadix];  // per-warp digit counters -> exclusive prefix over warps
   const int radix = 1 << radix_bits;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  __syncthreads();                       // (a previous tile of the same block may still be reading the tables)
   for (int d = t; d < radix; d += kSortThreads) {
     dbase[d] = totals[d];
 #pragma unroll
@@ -209,8 +238,8 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     for (int j = 0; j < kPer; ++j) { const int d = lane * kPer + j; if (d < radix) dbase[d] = run; run += loc[j]; }
   }
   __syncthreads();
-  for (int d = t; d < radix; d += kSortThreads) goff[d] = dbase[d] + offsets[(size_t)d * nblocks + blockIdx.x];
-  const int64_t base = (int64_t)blockIdx.x * kSortTile + warp * (32 * kSortRounds);
+  for (int d = t; d < radix; d += kSortThreads) goff[d] = dbase[d] + offsets[(size_t)d * nblocks + bid];
+  const int64_t base = (int64_t)bid * kSortTile + warp * (32 * kSortRounds);
   uint32_t key[kSortRounds], val[kSortRounds], rank[kSortRounds];
 #pragma unroll
   for (int r = 0; r < kSortRounds; ++r) {
@@ -250,6 +279,47 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   }
 }
 
+__global__ void __launch_bounds__(kSortThreads)
+radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
+                     int radix_bits, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ totals,
+                     int nblocks) {
+  radix_scatter_tile(blockIdx.x, keys_in, vals_in, keys_out, vals_out, n, shift, radix_bits, offsets, totals, nblocks);
+}
+
+// ---- sorted-COO path as ONE cooperative launch: prep + the passes of the CSC radix sort + finish, with grid-wide barriers
+// where the chain had kernel boundaries (8 launches of ~7 us each for ~24 MB of traffic at BASELINE C2 size).  Block b
+// owns tile b of every pass (the grid covers all tiles: the caller checks the co-resident capacity); the digit rows of
+// the scan and the element-wise first / last phases are strided over the grid.  Same device functions as the chain, so
+// the results are bit-identical.
+__global__ void __launch_bounds__(kSortThreads)
+graph_sorted_fused_kernel(const uint32_t* __restrict__ row, const uint32_t* __restrict__ col, const float* __restrict__ val, int64_t z,
+                          uint32_t m, uint32_t ncols, uint32_t* __restrict__ col_out, float* __restrict__ val_out,
+                          int32_t* __restrict__ rowptr, uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1,
+                          uint32_t* counts, uint32_t* totals, int nblocks, int passes, int digit_bits, uint32_t* __restrict__ status,
+                          uint32_t* __restrict__ csr2csc, uint32_t* __restrict__ row_csc, float* __restrict__ val_csc,
+                          int32_t* __restrict__ colptr) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const int G = gridDim.x, b = blockIdx.x;
+  for (int64_t e = (int64_t)b * kSortThreads + threadIdx.x; e <= z; e += (int64_t)G * kSortThreads)
+    prep_sorted_entry(e, row, col, val, z, m, ncols, col_out, val_out, rowptr, k0, v0, status);
+  uint32_t *ki = k0, *vi = v0, *ko = k1, *vo = v1;
+  for (int p = 0; p < passes; ++p) {
+    const int shift = p * digit_bits;
+    grid.sync();
+    for (int tile = b; tile < nblocks; tile += G) radix_hist_tile(tile, ki, z, shift, digit_bits, counts, nblocks);
+    grid.sync();
+    for (int d = b; d < (1 << digit_bits); d += G) scan_digit_row(d, counts, nblocks, totals);
+    grid.sync();
+    for (int tile = b; tile < nblocks; tile += G) radix_scatter_tile(tile, ki, vi, ko, vo, z, shift, digit_bits, counts, totals, nblocks);
+    uint32_t* tk = ki; ki = ko; ko = tk;
+    uint32_t* tv = vi; vi = vo; vo = tv;
+  }
+  grid.sync();
+  for (int64_t k = (int64_t)b * kSortThreads + threadIdx.x; k <= z; k += (int64_t)G * kSortThreads)
+    finish_csc_entry(k, row, val_out, ki, vi, z, (int32_t)ncols, csr2csc, row_csc, val_csc, colptr);
+}
+
 // ptr[q] = first position e with sorted_keys[e] >= q, for q in [0, rows]; ptr[rows] = n.
 __global__ void fill_ptr_kernel(const uint32_t* __restrict__ sorted_keys, int64_t n, int32_t rows,
                                 int32_t* __restrict__ ptr) {
@@ -264,6 +334,23 @@ int bits_for(int64_t extent) {  // bits needed for values in [0, extent)
   int b = 1;
   while (b < 32 && ((int64_t)1 << b) < extent) ++b;
   return b;
+}
+
+int g_graph_fused = 1;   // 0 forces the launch chain on the sorted path (lpgnn_set_graph_fused)
+
+// co-resident blocks of the fused sorted-path kernel (0: cooperative launches unavailable)
+int fused_blocks() {
+  static int cap = -1;
+  if (cap < 0) {
+    int per_sm = 0, coop = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_sorted_fused_kernel, kSortThreads, 0) != cudaSuccess)
+      per_sm = 0;
+    cudaGetLastError();
+    cap = per_sm * sm_count();
+  }
+  return cap;
 }
 
 struct SortBufs {
@@ -362,6 +449,29 @@ extern "C" int lpgnn_graph_build(const void* coo_row, const void* coo_col, int i
   }
   uint32_t* u_col = reinterpret_cast<uint32_t*>(col);
   const uint32_t* csr_rows;  // row of every CSR entry
+  if ((flags & LPGNN_COO_SORTED) && !(flags & LPGNN_GRAPH_MEAN) && g_graph_fused && fused_blocks() > 0) {
+    // sorted COO, one cooperative launch (see graph_sorted_fused_kernel); the grid is capped at the co-resident capacity
+    // and strides over the tiles
+    const int nblocks = ceil_div(z, kSortTile);
+    const int bits = bits_for(n);
+    int passes = (bits + kMaxRadixBits - 1) / kMaxRadixBits;
+    int digit_bits = (bits + passes - 1) / passes;
+    const int cap = fused_blocks();
+    int grid = nblocks < cap ? (nblocks > 0 ? nblocks : 1) : cap;
+    const int64_t zz = z;
+    const uint32_t um = (uint32_t)m, un = (uint32_t)n;
+    uint32_t *k0 = b.k[0], *v0 = b.v[0], *k1 = b.k[1], *v1 = b.v[1], *cnt = b.counts, *tot = b.totals;
+    int nb = nblocks;
+    uint32_t* c2c = reinterpret_cast<uint32_t*>(csr2csc);
+    uint32_t* rcsc = reinterpret_cast<uint32_t*>(row_csc);
+    void* args[] = {(void*)&rsrc, (void*)&csrc, (void*)&coo_val, (void*)&zz, (void*)&um, (void*)&un, (void*)&u_col, (void*)&val,
+                    (void*)&rowptr, (void*)&k0, (void*)&v0, (void*)&k1, (void*)&v1, (void*)&cnt, (void*)&tot, (void*)&nb,
+                    (void*)&passes, (void*)&digit_bits, (void*)&u_status, (void*)&c2c, (void*)&rcsc, (void*)&val_csc,
+                    (void*)&colptr};
+    LPGNN_CUDA_OK(cudaLaunchCooperativeKernel((const void*)graph_sorted_fused_kernel, dim3(grid), dim3(kSortThreads), args, 0, st));
+    count_launches(launches + 1);
+    return LPGNN_OK;
+  }
   if (flags & LPGNN_COO_SORTED) {
     // Caller asserts row-major order (what the reference's pipeline produces, dataset.py:251-252): the CSR
     // arrays are the input; the claim and the index range are verified on the device and reported in *status.
@@ -434,4 +544,12 @@ extern "C" int lpgnn_pack_offsets(int32_t* row, int32_t* col, int64_t nnz, const
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;
+}
+
+// Tuning knob: 1 (default) = sorted COO inputs are built by ONE cooperative launch, 0 = always the launch chain.  Results
+// are bit-identical (same device functions).  Returns the previous setting.
+extern "C" int lpgnn_set_graph_fused(int enable) {
+  const int prev = lpgnn::g_graph_fused;
+  lpgnn::g_graph_fused = enable ? 1 : 0;
+  return prev;
 }
