@@ -13,6 +13,7 @@
 //   4. status = 1 if selected else side.
 // HBM-bound integer/byte work: (m+n)*(12 + 4 + 1) bytes in pass 1, (m+n)*4 per select pass.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -455,7 +456,8 @@ int fused_capacity() {
   return cap;
 }
 
-int g_select_fused = 1;   // 0 forces the multi-launch chain (lpgnn_set_select_fused, for A/B measurements and tests)
+// 0 forces the multi-launch chain (lpgnn_set_select_fused; environment LPGNN_SELECT_FUSED=0 for A/B runs)
+int g_select_fused = [] { const char* e = getenv("LPGNN_SELECT_FUSED"); return e ? atoi(e) != 0 : 1; }();
 
 struct Layout {
   size_t keys, side, hist, state, ties, fhist, fties, total;

@@ -14,6 +14,7 @@
 // CSC  = stable sort of the CSR entries by column only (CSR order already breaks ties by row).
 // HBM-bound integer work; roofline = bytes moved per pass (12 B in + 12 B out per entry... see DESIGN.md).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -336,7 +337,8 @@ int bits_for(int64_t extent) {  // bits needed for values in [0, extent)
   return b;
 }
 
-int g_graph_fused = 1;   // 0 forces the launch chain on the sorted path (lpgnn_set_graph_fused)
+// 0 forces the launch chain on the sorted path (lpgnn_set_graph_fused; environment LPGNN_GRAPH_FUSED=0 for A/B runs)
+int g_graph_fused = [] { const char* e = getenv("LPGNN_GRAPH_FUSED"); return e ? atoi(e) != 0 : 1; }();
 
 // co-resident blocks of the fused sorted-path kernel (0: cooperative launches unavailable)
 int fused_blocks() {
