@@ -50,6 +50,9 @@ extern "C" {
 /* lpgnn_graph_build flags */
 #define LPGNN_COO_SORTED 1
 #define LPGNN_GRAPH_MEAN 4   /* degree normalisation: val /= deg(row), val_csc /= deg(column) (mean aggregation) */
+/* lpgnn_predict_basis_packed only: statuses are written per LP, [constraints of LP b | variables of LP b] back to back
+ * (LP b starts at cons_ptr[b] + vars_ptr[b]), instead of [all constraints | all variables] */
+#define LPGNN_STATUS_LP_MAJOR 8
 
 #define LPGNN_EPI_NONE 0
 #define LPGNN_EPI_RELU 1
@@ -117,6 +120,16 @@ LPGNN_API int lpgnn_copy_many_h2d(const uint64_t* dst_ptrs, const uint64_t* src_
  * row-major sorted. */
 LPGNN_API int lpgnn_pack_offsets(int32_t* row, int32_t* col, int64_t nnz, const int32_t* edge_ptr,
                        const int32_t* cons_ptr, const int32_t* vars_ptr, int32_t n_segments,
+                       lpgnn_stream_t stream);
+
+/* Same job for LPs that were STAGED whole: `staged` holds, LP after LP, each LP's host pack [row | col | val | x_s | x_t]
+ * (4-byte words; LP b starts at word stage_off[b], stage_off [n_segments + 1]) exactly as one host -> device copy per LP
+ * left it; one kernel moves every word to its place in the pack layout (row / col / val [nnz], x_s [M,p], x_t [N,q]) and
+ * shifts the indices to the pack's numbering.  Replaces five copies per LP + lpgnn_pack_offsets (batch_to of the
+ * reference's sweep, utils.py:909-915: five tensor moves per LP). */
+LPGNN_API int lpgnn_pack_scatter(const int32_t* staged, const int32_t* stage_off, const int32_t* edge_ptr,
+                       const int32_t* cons_ptr, const int32_t* vars_ptr, int32_t n_segments, int32_t p, int32_t q,
+                       int64_t total_words, int32_t* row, int32_t* col, float* val, float* x_s, float* x_t,
                        lpgnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -313,6 +326,13 @@ LPGNN_API int lpgnn_basis_select_segmented(const float* logits_cons, const float
                                  const int32_t* cons_ptr, const int32_t* vars_ptr, int32_t n_segments,
                                  int32_t total_cons, int32_t total_vars, void* status, int status_is_i64,
                                  void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
+
+/* lp_major != 0: status position of local node i of segment b = cons_ptr[b] + vars_ptr[b] + i (each LP's statuses
+ * contiguous, constraints first) instead of the packed layout. */
+LPGNN_API int lpgnn_basis_select_segmented_ex(const float* logits_cons, const float* logits_vars,
+                                    const int32_t* cons_ptr, const int32_t* vars_ptr, int32_t n_segments,
+                                    int32_t total_cons, int32_t total_vars, void* status, int status_is_i64,
+                                    int lp_major, void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * One-call basis prediction: (a1) graph build -> (a2-a5) GCN_FC forward -> (a6) basis selection,

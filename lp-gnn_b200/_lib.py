@@ -20,6 +20,7 @@ F16 = 2      # IEEE half storage (the reference's --fp16 mode): inference entry 
 EPI_NONE, EPI_RELU = 0, 1
 COO_SORTED = 1
 GRAPH_MEAN = 4
+STATUS_LP_MAJOR = 8
 WS_X2 = 16
 
 _p = C.c_void_p
@@ -62,6 +63,7 @@ SIGNATURES = {
     "lpgnn_graph_build": (_int, [_p, _p, _int, _p, _i64, _i32, _i32, _int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "lpgnn_set_graph_fused": (_int, [_int]),
     "lpgnn_copy_many_h2d": (_int, [_p, _p, _p, _i32, _p]),
+    "lpgnn_pack_scatter": (_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i64, _p, _p, _p, _p, _p, _p]),
     "lpgnn_pack_offsets": (_int, [_p, _p, _i64, _p, _p, _p, _i32, _p]),
     "lpgnn_spmm": (_int, [_p, _p, _p, _i32, _p, _p, _i32, _int, _p]),
     "lpgnn_spmm_ex": (_int, [_p, _p, _p, _i32, _p, _p, _i32, _int, _int, _int, _p]),
@@ -86,6 +88,7 @@ SIGNATURES = {
     "lpgnn_predict_basis": (_int, [C.POINTER(GcnFcWeights), _p, _p, _p, _i64, _i32, _i32, _int, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "lpgnn_predict_basis_packed": (_int, [C.POINTER(GcnFcWeights), _p, _p, _p, _i64, _i32, _i32, _int, _p, _p, _p, _p, _i32, _p,
                                           _p, _p, _p, _sz, _p]),
+    "lpgnn_basis_select_segmented_ex": (_int, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _int, _int, _p, _sz, _p]),
     "lpgnn_basis_select_segmented": (_int, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _int, _p, _sz, _p]),
     "lpgnn_gemm_tn_splits": (_i32, [_i32, _i32, _i32]),
     "lpgnn_gemm_tn_workspace_bytes": (_sz, [_i32, _i32, _i32]),

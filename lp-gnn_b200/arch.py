@@ -255,10 +255,11 @@ class GCN_FC(GCNBase):
 
     @torch.no_grad()
     def predict_basis_packed(self, row, col, val, m, n, x_s, x_t, cons_ptr, vars_ptr, is_sorted=True, want_logits=False,
-                             buffers=None):
+                             buffers=None, lp_major=False):
         """Same for a block-diagonal pack of LPs (``row/col`` already in the pack's numbering, ``m/n`` the pack
         totals, ``cons_ptr/vars_ptr`` device int32 [B+1]): one forward pass over the pack, basis decision per LP.
-        Returns uint8 statuses [m+n] in the packed layout (all constraints, then all variables)."""
+        Returns uint8 statuses [m+n] in the packed layout (all constraints, then all variables), or with ``lp_major`` LP by
+        LP (constraints of LP b, then its variables, starting at ``cons_ptr[b] + vars_ptr[b]``)."""
         import ctypes as C
 
         from . import _lib
@@ -285,7 +286,8 @@ class GCN_FC(GCNBase):
         gstat = _status_slot(dev)
         with torch.cuda.device(dev):
             rc = lib.lpgnn_predict_basis_packed(C.byref(w), row.data_ptr(), col.data_ptr(), val.data_ptr(), z, m, n,
-                                                _lib.COO_SORTED if is_sorted else 0, x_s.data_ptr(), x_t.data_ptr(),
+                                                (_lib.COO_SORTED if is_sorted else 0) | (_lib.STATUS_LP_MAJOR if lp_major else 0),
+                                                x_s.data_ptr(), x_t.data_ptr(),
                                                 cons_ptr.data_ptr(), vars_ptr.data_ptr(), int(cons_ptr.shape[0]) - 1,
                                                 status.data_ptr(), _lib.ptr(logits), gstat.data_ptr(), ws.data_ptr(),
                                                 ws_bytes, _lib.stream_ptr())

@@ -221,7 +221,7 @@ template <typename OutT>
 __global__ void __launch_bounds__(kSegThreads)
 segmented_select_kernel(const float* __restrict__ lc, const float* __restrict__ lv, const int32_t* __restrict__ cptr,
                         const int32_t* __restrict__ vptr, int32_t total_cons, uint32_t* __restrict__ keys,
-                        uint8_t* __restrict__ side, OutT* __restrict__ status) {
+                        uint8_t* __restrict__ side, OutT* __restrict__ status, int lp_major) {
   __shared__ uint32_t hist[4 * 256];
   __shared__ Threshold ts;
   __shared__ uint32_t warp_ties[kSegThreads / 32];
@@ -275,7 +275,8 @@ segmented_select_kernel(const float* __restrict__ lc, const float* __restrict__ 
     if (i < tot) {
       const bool sel = key > thr || (tie && before < k_rem);
       const int64_t g = pos(i);
-      status[g] = (OutT)(sel ? 1 : (int)side[g]);
+      // output position: packed [all constraints | all variables], or per LP [cons of LP b | vars of LP b] back to back
+      status[lp_major ? (int64_t)c0 + v0 + i : g] = (OutT)(sel ? 1 : (int)side[g]);
     }
     __syncthreads();
     if (t == 0) { uint32_t s = 0; for (int w = 0; w < kSegThreads / 32; ++w) s += warp_ties[w]; run_s += s; }
@@ -556,6 +557,14 @@ extern "C" int lpgnn_basis_select_segmented(const float* logits_cons, const floa
                                             const int32_t* vars_ptr, int32_t n_segments, int32_t total_cons,
                                             int32_t total_vars, void* status, int status_is_i64, void* workspace,
                                             size_t workspace_bytes, lpgnn_stream_t stream) {
+  return lpgnn_basis_select_segmented_ex(logits_cons, logits_vars, cons_ptr, vars_ptr, n_segments, total_cons, total_vars, status,
+                                         status_is_i64, 0, workspace, workspace_bytes, stream);
+}
+
+extern "C" int lpgnn_basis_select_segmented_ex(const float* logits_cons, const float* logits_vars, const int32_t* cons_ptr,
+                                               const int32_t* vars_ptr, int32_t n_segments, int32_t total_cons,
+                                               int32_t total_vars, void* status, int status_is_i64, int lp_major,
+                                               void* workspace, size_t workspace_bytes, lpgnn_stream_t stream) {
   if (int rc = check_device()) return rc;
   LPGNN_REQUIRE(n_segments >= 0 && total_cons >= 0 && total_vars >= 0, "basis_select_segmented: negative size");
   if (n_segments == 0) return LPGNN_OK;
@@ -571,11 +580,11 @@ extern "C" int lpgnn_basis_select_segmented(const float* logits_cons, const floa
   if (status_is_i64)
     segmented_select_kernel<int64_t><<<n_segments, kSegThreads, 0, st>>>(logits_cons, logits_vars, cons_ptr, vars_ptr,
                                                                          total_cons, keys, side,
-                                                                         reinterpret_cast<int64_t*>(status));
+                                                                         reinterpret_cast<int64_t*>(status), lp_major);
   else
     segmented_select_kernel<uint8_t><<<n_segments, kSegThreads, 0, st>>>(logits_cons, logits_vars, cons_ptr, vars_ptr,
                                                                          total_cons, keys, side,
-                                                                         reinterpret_cast<uint8_t*>(status));
+                                                                         reinterpret_cast<uint8_t*>(status), lp_major);
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;

@@ -534,6 +534,55 @@ __global__ void pack_offsets_kernel(int32_t* __restrict__ row, int32_t* __restri
 }  // namespace
 }  // namespace lpgnn
 
+namespace lpgnn {
+namespace {
+// One pass from the STAGED LPs (each LP's host pack [row | col | val | x_s | x_t] copied verbatim, LP after LP) to the pack
+// layout [row Z | col Z | val Z | x_s M*p | x_t N*q], indices shifted to the pack's numbering (the job of
+// pack_offsets_kernel, fused).  One 4-byte word per thread; the LP of a word by binary search over the staging offsets.
+__global__ void pack_scatter_kernel(const int32_t* __restrict__ staged, const int32_t* __restrict__ stage_off,
+                                    const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ cons_ptr,
+                                    const int32_t* __restrict__ vars_ptr, int n_seg, int p, int q, int64_t total_words,
+                                    int32_t* __restrict__ row, int32_t* __restrict__ col, int32_t* __restrict__ val,
+                                    int32_t* __restrict__ x_s, int32_t* __restrict__ x_t) {
+  const int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (w >= total_words) return;
+  int lo = 0, hi = n_seg;                       // largest b with stage_off[b] <= w
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (stage_off[mid] <= w) lo = mid; else hi = mid; }
+  const int b = lo;
+  const int32_t e0 = edge_ptr[b], z = edge_ptr[b + 1] - e0;
+  const int32_t c0 = cons_ptr[b], mb = cons_ptr[b + 1] - c0;
+  const int32_t v0 = vars_ptr[b];
+  int64_t k = w - stage_off[b];
+  const int32_t x = staged[w];
+  if (k < z) { row[e0 + k] = x + c0; return; }
+  k -= z;
+  if (k < z) { col[e0 + k] = x + v0; return; }
+  k -= z;
+  if (k < z) { val[e0 + k] = x; return; }
+  k -= z;
+  if (k < (int64_t)mb * p) { x_s[(int64_t)c0 * p + k] = x; return; }
+  k -= (int64_t)mb * p;
+  x_t[(int64_t)v0 * q + k] = x;
+}
+}  // namespace
+}  // namespace lpgnn
+
+extern "C" int lpgnn_pack_scatter(const int32_t* staged, const int32_t* stage_off, const int32_t* edge_ptr,
+                                  const int32_t* cons_ptr, const int32_t* vars_ptr, int32_t n_segments, int32_t p, int32_t q,
+                                  int64_t total_words, int32_t* row, int32_t* col, float* val, float* x_s, float* x_t,
+                                  lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(total_words >= 0 && n_segments >= 1 && p > 0 && q > 0, "pack_scatter: bad arguments");
+  if (total_words == 0) return LPGNN_OK;
+  LPGNN_REQUIRE(staged && stage_off && edge_ptr && cons_ptr && vars_ptr && row && col && val && x_s && x_t, "pack_scatter: null pointer");
+  pack_scatter_kernel<<<ceil_div(total_words, 256), 256, 0, (cudaStream_t)stream>>>(
+      staged, stage_off, edge_ptr, cons_ptr, vars_ptr, n_segments, p, q, total_words, row, col, reinterpret_cast<int32_t*>(val),
+      reinterpret_cast<int32_t*>(x_s), reinterpret_cast<int32_t*>(x_t));
+  LPGNN_LAUNCH_OK();
+  count_launches(1);
+  return LPGNN_OK;
+}
+
 extern "C" int lpgnn_pack_offsets(int32_t* row, int32_t* col, int64_t nnz, const int32_t* edge_ptr,
                                   const int32_t* cons_ptr, const int32_t* vars_ptr, int32_t n_segments,
                                   lpgnn_stream_t stream) {

@@ -214,8 +214,8 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
   // ---- (a6) basis decision
   if (n_segments > 0) {
     LPGNN_REQUIRE(cons_ptr && vars_ptr, "predict_basis_packed: null segment pointers");
-    LPGNN_TRY(lpgnn_basis_select_segmented(B.logit_s, B.logit_t, cons_ptr, vars_ptr, n_segments, m, n, status_out, 0,
-                                           B.sel_ws, B.sel_ws_bytes, stream));
+    LPGNN_TRY(lpgnn_basis_select_segmented_ex(B.logit_s, B.logit_t, cons_ptr, vars_ptr, n_segments, m, n, status_out, 0,
+                                              (flags & LPGNN_STATUS_LP_MAJOR) ? 1 : 0, B.sel_ws, B.sel_ws_bytes, stream));
   } else {
     LPGNN_TRY(lpgnn_basis_select(B.logit_s, m, B.logit_t, n, m, status_out, 0, nullptr, B.sel_ws, B.sel_ws_bytes, stream));
   }

@@ -128,9 +128,9 @@ class BasisPipeline:
 
 class PackedBasisPipeline:
     """Sweep over many small/medium LPs (the reference's pred_basis workload, BASELINE config C5): consecutive LPs
-    are packed block-diagonally up to a node / nonzero budget, one pack = one H2D burst (each LP's pinned arrays
-    are copied straight to their offsets in the pack), ONE native forward over the pack and a per-LP (segmented)
-    basis decision, one D2H copy of the pack's statuses.  Packs are double-buffered like ``BasisPipeline``.
+    are packed block-diagonally up to a node / nonzero budget, one pack = one H2D burst (ONE copy per LP: its pinned
+    pack goes verbatim into a device staging area; ``lpgnn_pack_scatter`` builds the pack layout from it), ONE native
+    forward over the pack and a per-LP (segmented) basis decision, one D2H copy of the pack's statuses.  Packs are double-buffered like ``BasisPipeline``.
 
     ``for idx, status in pipe.run(host_lps)`` yields a fresh uint8 array [m+n] (constraints first) per LP, in order.
     """
@@ -144,7 +144,7 @@ class PackedBasisPipeline:
         # optional alternating compute streams as in BasisPipeline; off by default: packs already fill the GPU and
         # their varying workspace sizes defeat the per-stream allocator caches (measured 2.7x slower on C5)
         self.compute = [torch.cuda.Stream(self.dev) for _ in range(2)] if compute_streams > 1 else None
-        self.d_buf, self.h_status, self.h_ptr = [None, None], [None, None], [None, None]
+        self.d_buf, self.d_stage, self.h_status, self.h_ptr = [None, None], [None, None], [None, None], [None, None]
         self.bufs = [dict(), dict()]          # per slot: grow-only workspace / status buffers of the native call
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]
         self.done = [torch.cuda.Event(), torch.cuda.Event()]
@@ -164,58 +164,48 @@ class PackedBasisPipeline:
         return packs
 
     def _stage(self, slot, lps, ids, first_use):
-        """H2D of one pack on the copy stream.  Device layout (int32 words):
-        [row Z | col Z | val Z | x_s M*p | x_t N*q | edge_ptr B+1 | cons_ptr B+1 | vars_ptr B+1]."""
+        """H2D of one pack on the copy stream: ONE copy per LP (its pinned pack, verbatim, into a device staging area,
+        LP after LP) + one copy of the pack's offset tables.  Staging layout (int32 words): LP b at ``stage_off[b]``:
+        [row z_b | col z_b | val z_b | x_s m_b*p | x_t n_b*q]; tables: [stage_off | edge_ptr | cons_ptr | vars_ptr], B+1
+        words each.  ``lpgnn_pack_scatter`` (compute stream) turns that into the pack layout."""
         sub = [lps[i] for i in ids]
         B = len(sub)
-        zs = [lp.offs[1] - lp.offs[0] for lp in sub]
-        e_ptr = np.concatenate([[0], np.cumsum(zs)]).astype(np.int32)
-        c_ptr = np.concatenate([[0], np.cumsum([lp.m for lp in sub])]).astype(np.int32)
-        v_ptr = np.concatenate([[0], np.cumsum([lp.n for lp in sub])]).astype(np.int32)
-        Z, M, N = int(e_ptr[-1]), int(c_ptr[-1]), int(v_ptr[-1])
+        words = np.fromiter((lp.offs[5] for lp in sub), dtype=np.int64, count=B)
+        zs = np.fromiter((lp.offs[1] for lp in sub), dtype=np.int64, count=B)
+        ms = np.fromiter((lp.m for lp in sub), dtype=np.int64, count=B)
+        ns = np.fromiter((lp.n for lp in sub), dtype=np.int64, count=B)
+        tables = np.zeros((4, B + 1), dtype=np.int64)
+        np.cumsum(words, out=tables[0, 1:]); np.cumsum(zs, out=tables[1, 1:])
+        np.cumsum(ms, out=tables[2, 1:]); np.cumsum(ns, out=tables[3, 1:])
+        W, Z, M, N = (int(tables[k, -1]) for k in range(4))
         p, q = sub[0].p, sub[0].q
-        o_row, o_col, o_val = 0, Z, 2 * Z
-        o_xs, o_xt = 3 * Z, 3 * Z + M * p
-        o_ptr = o_xt + N * q
-        words = o_ptr + 3 * (B + 1)
-        if self.d_buf[slot] is None or self.d_buf[slot].numel() < words:
+        need = W + 4 * (B + 1)
+        if self.d_stage[slot] is None or self.d_stage[slot].numel() < need:
             if not first_use:
                 self.done[slot].synchronize()   # the slot's previous pack may still be computing on this buffer
-            self.d_buf[slot] = torch.empty(int(words * 1.25) + 64, dtype=torch.int32, device=self.dev)
-        if self.h_ptr[slot] is None or self.h_ptr[slot].numel() < 3 * (B + 1):
-            self.h_ptr[slot] = torch.empty(3 * (self.max_lps + 1), dtype=torch.int32).pin_memory()
-        hp = self.h_ptr[slot]
-        d = self.d_buf[slot]
+            self.d_stage[slot] = torch.empty(int(need * 1.25) + 64, dtype=torch.int32, device=self.dev)
+        if self.h_ptr[slot] is None:
+            self.h_ptr[slot] = torch.empty(4 * (self.max_lps + 1), dtype=torch.int32).pin_memory()
+        hp, d = self.h_ptr[slot], self.d_stage[slot]
         if not first_use:
-            self.ready[slot].synchronize()      # the slot's previous H2D has consumed the pinned pointer array
-        hp[:3 * (B + 1)] = torch.from_numpy(np.concatenate([e_ptr, c_ptr, v_ptr]))
-        # one native call enqueues all copies of the pack: 5 per LP (row, col, val, x_s, x_t straight to their
-        # offsets in the pack) + the segment pointer arrays
+            self.ready[slot].synchronize()      # the slot's previous H2D has consumed the pinned table buffer
+        hp.numpy()[:4 * (B + 1)] = tables.reshape(-1)
         base = d.data_ptr()
-        src0 = np.array([lp.pack.data_ptr() for lp in sub], dtype=np.uint64)
-        offs = np.array([lp.offs for lp in sub], dtype=np.uint64)                       # [B, 6] word offsets in the LP pack
-        ms, ns = np.array([lp.m for lp in sub], dtype=np.uint64), np.array([lp.n for lp in sub], dtype=np.uint64)
-        e0, c0, v0 = e_ptr[:-1].astype(np.uint64), c_ptr[:-1].astype(np.uint64), v_ptr[:-1].astype(np.uint64)
-        dst_w = np.stack([o_row + e0, o_col + e0, o_val + e0, o_xs + c0 * p, o_xt + v0 * q], axis=1)   # [B,5] words
-        src = (src0[:, None] + 4 * offs[:, :5]).reshape(-1)
-        dst = (np.uint64(base) + 4 * dst_w).reshape(-1)
-        nby = (4 * (offs[:, 1:6] - offs[:, 0:5])).reshape(-1)
-        src = np.concatenate([src, np.array([hp.data_ptr()], dtype=np.uint64)])
-        dst = np.concatenate([dst, np.array([base + 4 * o_ptr], dtype=np.uint64)])
-        nby = np.ascontiguousarray(np.concatenate([nby, np.array([12 * (B + 1)], dtype=np.uint64)]))
-        src, dst = np.ascontiguousarray(src), np.ascontiguousarray(dst)
+        src = np.empty(B + 1, dtype=np.uint64); dst = np.empty(B + 1, dtype=np.uint64); nby = np.empty(B + 1, dtype=np.uint64)
+        src[:B] = np.fromiter((lp.pack.data_ptr() for lp in sub), dtype=np.uint64, count=B)
+        dst[:B] = np.uint64(base) + (4 * tables[0, :B]).astype(np.uint64)
+        nby[:B] = (4 * words).astype(np.uint64)
+        src[B], dst[B], nby[B] = hp.data_ptr(), base + 4 * W, 16 * (B + 1)
         from . import _lib
         with torch.cuda.stream(self.copy_stream):
             if not first_use:
                 self.copy_stream.wait_event(self.done[slot])
             with torch.cuda.device(self.dev):
-                rc = _lib.load().lpgnn_copy_many_h2d(dst.ctypes.data, src.ctypes.data, nby.ctypes.data, int(src.shape[0]),
+                rc = _lib.load().lpgnn_copy_many_h2d(dst.ctypes.data, src.ctypes.data, nby.ctypes.data, B + 1,
                                                      self.copy_stream.cuda_stream)
             _lib.check(rc, "lpgnn_copy_many_h2d")
             self.ready[slot].record(self.copy_stream)
-        del ms, ns
-        return dict(B=B, Z=Z, M=M, N=N, p=p, q=q, offs=(o_row, o_col, o_val, o_xs, o_xt, o_ptr), c_ptr=c_ptr, v_ptr=v_ptr,
-                    sorted=all(lp.sorted for lp in sub))
+        return dict(B=B, W=W, Z=Z, M=M, N=N, p=p, q=q, c_ptr=tables[2], v_ptr=tables[3], sorted=all(lp.sorted for lp in sub))
 
     @torch.no_grad()
     def _compute(self, slot, meta):
@@ -226,32 +216,36 @@ class PackedBasisPipeline:
 
     def _compute_on(self, slot, meta, cur):
         from . import _lib
-        M, N, Z, B, p, q = meta["M"], meta["N"], meta["Z"], meta["B"], meta["p"], meta["q"]
+        M, N, Z, B, W, p, q = meta["M"], meta["N"], meta["Z"], meta["B"], meta["W"], meta["p"], meta["q"]
         if self.h_status[slot] is None or self.h_status[slot].numel() < M + N:
             self.h_status[slot] = torch.empty(int((M + N) * 1.25) + 64, dtype=torch.uint8).pin_memory()
+        words = 3 * Z + M * p + N * q
+        if self.d_buf[slot] is None or self.d_buf[slot].numel() < words:      # same stream as its previous users: safe to replace
+            self.d_buf[slot] = torch.empty(int(words * 1.25) + 64, dtype=torch.int32, device=self.dev)
         cur.wait_event(self.ready[slot])
-        d = self.d_buf[slot]
-        o_row, o_col, o_val, o_xs, o_xt, o_ptr = meta["offs"]
-        row, col = d[o_row:o_row + Z], d[o_col:o_col + Z]
-        val = d[o_val:o_val + Z].view(torch.float32)
-        x_s = d[o_xs:o_xs + M * p].view(torch.float32).view(M, p)
-        x_t = d[o_xt:o_xt + N * q].view(torch.float32).view(N, q)
-        e_ptr, c_ptr, v_ptr = (d[o_ptr + k * (B + 1):o_ptr + (k + 1) * (B + 1)] for k in range(3))
+        st, d = self.d_stage[slot], self.d_buf[slot]
+        row, col = d[0:Z], d[Z:2 * Z]
+        val = d[2 * Z:3 * Z].view(torch.float32)
+        x_s = d[3 * Z:3 * Z + M * p].view(torch.float32).view(M, p)
+        x_t = d[3 * Z + M * p:words].view(torch.float32).view(N, q)
+        s_off, e_ptr, c_ptr, v_ptr = (st[W + k * (B + 1):W + (k + 1) * (B + 1)] for k in range(4))
         with torch.cuda.device(self.dev):
-            rc = _lib.load().lpgnn_pack_offsets(row.data_ptr(), col.data_ptr(), Z, e_ptr.data_ptr(), c_ptr.data_ptr(),
-                                                v_ptr.data_ptr(), B, _lib.stream_ptr())
-        _lib.check(rc, "lpgnn_pack_offsets")
-        st = self.model.predict_basis_packed(row, col, val, M, N, x_s, x_t, c_ptr, v_ptr, is_sorted=meta["sorted"],
-                                             buffers=self.bufs[slot])
-        self.h_status[slot][:M + N].copy_(st, non_blocking=True)
+            rc = _lib.load().lpgnn_pack_scatter(st.data_ptr(), s_off.data_ptr(), e_ptr.data_ptr(), c_ptr.data_ptr(), v_ptr.data_ptr(),
+                                                B, p, q, W, row.data_ptr(), col.data_ptr(), val.data_ptr(), x_s.data_ptr(),
+                                                x_t.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "lpgnn_pack_scatter")
+        stt = self.model.predict_basis_packed(row, col, val, M, N, x_s, x_t, c_ptr, v_ptr, is_sorted=meta["sorted"],
+                                              buffers=self.bufs[slot], lp_major=True)
+        self.h_status[slot][:M + N].copy_(stt, non_blocking=True)
         self.done[slot].record(cur)
 
     def _emit(self, slot, meta, ids):
+        """Statuses arrive LP by LP (constraints, then variables of each LP): every yield is a copy of one slice."""
         self.done[slot].synchronize()
         h = self.h_status[slot].numpy()
-        M, c, v = meta["M"], meta["c_ptr"], meta["v_ptr"]
+        start = meta["c_ptr"] + meta["v_ptr"]
         for b, i in enumerate(ids):
-            yield i, np.concatenate([h[c[b]:c[b + 1]], h[M + v[b]:M + v[b + 1]]])
+            yield i, h[start[b]:start[b + 1]].copy()
 
     def run(self, host_lps):
         lps = list(host_lps)
