@@ -101,9 +101,9 @@ LPGNN_API int lpgnn_graph_build(const void* coo_row, const void* coo_col, int id
                       int32_t* csr2csc /*[nnz]*/, int32_t* status /*[1] device, optional*/,
                       void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
 
-/* Tuning knob (process-wide): a LPGNN_COO_SORTED build runs as ONE cooperative launch (prep, the radix passes of the CSC
- * sort and the finish, separated by grid-wide barriers; default) or as the chain of 8 launches (enable = 0).  Bit-identical
- * outputs.  Returns the previous setting. */
+/* Tuning knob (process-wide): a LPGNN_COO_SORTED build runs as the chain of 8 launches (default) or as ONE cooperative
+ * launch (enable = 1: prep, the radix passes of the CSC sort and the finish, separated by grid-wide barriers; measured no
+ * faster on B200, see csrc/graph_build.cu).  Bit-identical outputs.  Returns the previous setting. */
 LPGNN_API int lpgnn_set_graph_fused(int enable);
 
 /* `count` independent pinned-host -> device copies enqueued on `stream` by one native call (addresses and

@@ -337,8 +337,10 @@ int bits_for(int64_t extent) {  // bits needed for values in [0, extent)
   return b;
 }
 
-// 0 forces the launch chain on the sorted path (lpgnn_set_graph_fused; environment LPGNN_GRAPH_FUSED=0 for A/B runs)
-int g_graph_fused = [] { const char* e = getenv("LPGNN_GRAPH_FUSED"); return e ? atoi(e) != 0 : 1; }();
+// 1 builds sorted inputs with ONE cooperative launch (lpgnn_set_graph_fused; environment LPGNN_GRAPH_FUSED=1).  Off by
+// default: measured on B200 the grid barriers cost what the launches did (C2: 68 vs 62 us) and small LPs lose the
+// launch pipelining of the chain (C5, one call per LP: 4.7K vs 5.5K LPs/s); kept as an option and as a cross-check.
+int g_graph_fused = [] { const char* e = getenv("LPGNN_GRAPH_FUSED"); return e ? atoi(e) != 0 : 0; }();
 
 // co-resident blocks of the fused sorted-path kernel (0: cooperative launches unavailable)
 int fused_blocks() {
@@ -597,7 +599,7 @@ extern "C" int lpgnn_pack_offsets(int32_t* row, int32_t* col, int64_t nnz, const
   return LPGNN_OK;
 }
 
-// Tuning knob: 1 (default) = sorted COO inputs are built by ONE cooperative launch, 0 = always the launch chain.  Results
+// Tuning knob: 1 = sorted COO inputs are built by ONE cooperative launch, 0 (default) = the launch chain.  Results
 // are bit-identical (same device functions).  Returns the previous setting.
 extern "C" int lpgnn_set_graph_fused(int enable) {
   const int prev = lpgnn::g_graph_fused;
