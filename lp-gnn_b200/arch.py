@@ -174,7 +174,12 @@ class GCN_FC(GCNBase):
         """``lpgnn_gcn_fc_weights`` for the current parameters (rebuilt when a parameter changes)."""
         from . import _lib
         from .autograd import wcat_bf16
-        ver = tuple(p._version for p in self.parameters()) + (self.precision, str(self.lin_left.weight.device))
+        # (walking the module tree costs ~100 us per call: the Parameter objects are listed once, then only their
+        # version counters and storage addresses are compared)
+        plist = getattr(self, "_param_list", None)
+        if plist is None or len(plist) != 6 * (len(self.layers) + 1) + 4:
+            plist = self._param_list = list(self.parameters())
+        ver = tuple(p._version for p in plist) + (plist[0].data_ptr(), plist[-1].data_ptr(), self.precision)
         hit = getattr(self, "_native_cache", None)
         if hit is not None and hit[0] == ver:
             return hit[1]

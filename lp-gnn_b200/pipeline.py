@@ -135,7 +135,7 @@ class PackedBasisPipeline:
     ``for idx, status in pipe.run(host_lps)`` yields a fresh uint8 array [m+n] (constraints first) per LP, in order.
     """
 
-    def __init__(self, model, device, max_nodes=200_000, max_nnz=1_000_000, max_lps=64, compute_streams=1):
+    def __init__(self, model, device, max_nodes=600_000, max_nnz=3_000_000, max_lps=128, compute_streams=1):
         if not torch.cuda.is_available():
             raise RuntimeError("PackedBasisPipeline needs a CUDA device (no CPU fallback)")
         self.model, self.dev = model, torch.device(device)
