@@ -601,17 +601,16 @@ def kernel_rooflines(model, lp, dev, peaks, bf16, args):
     w = lambda p: p.detach()
     # input layer, variables side (rows = n): gather [A^T x_s | x_t] then the transform
     if bf16:
-        from lpgnn_b200.autograd import wcat_bf16
-        wc = wcat_bf16(c1._cache, c1.left2right, dt)
-        t_g = time_kernel(lambda: ops.gather_cat(csc, xs, xt, want_f32=False, want_bf16=True, dtype16=dt), reps, flush)
-        add("gather_cat (vars side)", "hbm", t_g, n * 64 * 2 + (m + n) * 8 * 4 + z * 8 + (n + 1) * 4, 1)
-        _, zb = ops.gather_cat(csc, xs, xt, want_f32=False, want_bf16=True, dtype16=dt)
-        f_in = lambda: ops.node_transform(zb, wc, bias=w(c1.left2right.lin_rel.bias), relu=True)
-        t = time_kernel(f_in, reps, flush)
-        add("input transform, one K block (tcgen05, vars side)", "hbm", t, n * H * s + n * 64 * 2, 1)
-        right = f_in()
-        _, zbs = ops.gather_cat(csr, xt, xs, want_f32=False, want_bf16=True, dtype16=dt)
-        left = ops.node_transform(zbs, wcat_bf16(c1._cache, c1.right2left, dt), bias=w(c1.right2left.lin_rel.bias), relu=True)
+        # input layer, one kernel per direction (aggregate + 16-wide MMA + bias + ReLU + 16-bit store); HBM-bound on the
+        # output write (a pure write stream of this size runs at ~5.8 TB/s on this part, scripts/bench_store.cu)
+        f_in = lambda: ops.conv_in_16(csc, xs, xt, w(c1.left2right.lin_rel.weight), w(c1.left2right.lin_rel.bias),
+                                      w(c1.left2right.lin_root.weight), dt, relu=True)[0]
+        f_in_s = lambda: ops.conv_in_16(csr, xt, xs, w(c1.right2left.lin_rel.weight), w(c1.right2left.lin_rel.bias),
+                                        w(c1.right2left.lin_root.weight), dt, relu=True)[0]
+        t = time_kernel(f_in, reps, flush) + time_kernel(f_in_s, reps, flush)
+        add("conv_in_16 pair (input layer: gather + MMA + ReLU + store, both sides)", "hbm", t,
+            (m + n) * H * s + 2 * (m + n) * 8 * 4 + 2 * z * 8 + (m + n + 2) * 4, 2)
+        right, left = f_in(), f_in_s()
     else:
         f_in = lambda: ops.conv_in_fused(csc, xs, xt, w(c1.left2right.lin_rel.weight), w(c1.left2right.lin_rel.bias),
                                          w(c1.left2right.lin_root.weight), dt, relu=True)

@@ -186,6 +186,18 @@ LPGNN_API int lpgnn_conv_in_fused(const int32_t* ptr, const int32_t* idx, const 
                         void* out, int out_dtype, int epilogue, float* z_cat,
                         lpgnn_stream_t stream);
 
+/* (a2+a3, input layer, 16-bit modes) conv1 of GCN_FC(8, 8, ...) in ONE kernel: out = epi( (A_view Xsrc) W_rel^T + b_rel +
+ * Xdst W_root^T ) with Xsrc [n_src,8], Xdst [rows,8], W_rel / W_root [N,8] f32 and out [rows,N] of out_dtype (LPGNN_BF16
+ * or LPGNN_F16; operands rounded to that type, fp32 accumulate).  The aggregate, the 16-wide product (one m16n8k16 MMA
+ * step per 16 x 8 outputs, accumulators in registers, bias as their initial value), ReLU and the 16-byte stores share a
+ * kernel whose only large traffic is the output write (csrc/conv_in_mma.cu).  z16 (optional, 16-bit [rows,64]) receives
+ * [aggregate | Xdst | 1 | 0 ...]: the operand lpgnn_wgrad needs for this layer's weight / bias gradient.  N % 32 == 0.
+ * Replaces GraphConv.forward + relu_ of the (p,q)->hids layer (reference arch.py:170, 75-80, 181-182). */
+LPGNN_API int lpgnn_conv_in_16(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,
+                     const float* Xsrc, const float* Xdst, const float* W_rel, const float* b_rel,
+                     const float* W_root, int32_t N, void* out, int out_dtype, int epilogue, void* z16,
+                     lpgnn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (a3) Dense node transform of a hidden GraphConv layer.  Replaces lin_rel(agg) + lin_root(x_dst)
  * (two torch Linear / cuBLAS sgemm calls + bias + add, PyG GraphConv.forward reached from

@@ -70,6 +70,7 @@ SIGNATURES = {
     "lpgnn_conv_in_zcat_width": (_i32, [_i32, _i32]),
     "lpgnn_gather_cat": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p]),
     "lpgnn_conv_in_fused": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p, _i32, _p, _int, _int, _p, _p]),
+    "lpgnn_conv_in_16": (_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _int, _int, _p, _p]),
     "lpgnn_node_transform": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _int, _int, _p]),
     "lpgnn_node_transform_ex": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, C.POINTER(EpilogueArgs), _p]),
     "lpgnn_split_bf16": (_int, [_p, _i64, _int, _p, _p]),

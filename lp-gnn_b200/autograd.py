@@ -121,6 +121,14 @@ def conv_in_bf16(conv, x_left, x_right, csr, csc, relu, want_f32=False, dtype=to
 def _conv_in_infer(conv, x_left, x_right, csr, csc, dt, relu):
     l2r, r2l = conv.left2right, conv.right2left
     k_tot = l2r.in_channels[0] + l2r.in_channels[1]
+    if dt in _HALF_TYPES and l2r.in_channels == (8, 8) and r2l.in_channels == (8, 8) and l2r.out_channels % 32 == 0 \
+            and l2r.out_channels <= 4096:
+        # the reference's shape: aggregate + transform + ReLU + 16-bit store in one kernel per direction
+        right_new, _ = ops.conv_in_16(csc, x_left, x_right, l2r.lin_rel.weight.detach(), l2r.lin_rel.bias.detach(),
+                                      l2r.lin_root.weight.detach(), dt, relu=relu)
+        left_new, _ = ops.conv_in_16(csr, x_right, x_left, r2l.lin_rel.weight.detach(), r2l.lin_rel.bias.detach(),
+                                     r2l.lin_root.weight.detach(), dt, relu=relu)
+        return left_new, right_new
     if dt in _HALF_TYPES and k_tot <= 64 and l2r.out_channels % 64 == 0:
         left_new, right_new, _, _ = conv_in_bf16(conv, x_left, x_right, csr, csc, relu, dtype=dt)
         return left_new, right_new

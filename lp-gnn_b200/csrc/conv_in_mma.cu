@@ -1,0 +1,190 @@
+// (a2+a3, input layer, 16-bit modes) conv1 of GCN_FC(8, 8, ...) in ONE kernel: aggregation of the 8-wide features,
+// the (8 + 8) -> hids transform, bias, ReLU and the 16-bit store.
+//
+// Replaces PyG GraphConv.forward for the (p,q)->hids layer and the relu_ after it (reference arch.py:170, 75-80,
+// 181-182).  The output write dominates ((m+n) * hids * 2 bytes: 307 MB at BASELINE C2, ~53 us at the measured
+// 5.8 TB/s of a pure write stream); the previous form -- gather kernel, then the tcgen05 transform over one padded
+// K block -- spent 155 us there because its TMEM -> register -> shared -> global epilogue was latency-bound and the
+// gather was a separate, launch-latency-sized kernel.  With a reduction length of 16 the product is a single
+// m16n8k16 MMA step per 16 x 8 outputs, so the accumulators can simply live in registers: every warp owns 16 rows,
+//   A fragments  the rows' [aggregate | own features] (16 values, 16-bit), built once per row tile in shared memory
+//   B fragments  [W_rel | W_root] as 16-bit, stored in shared memory in fragment order, one conflict-free 8-byte load
+//                per lane and MMA; the column order inside a 32-column chunk is permuted so that a lane ends up with 8
+//                CONSECUTIVE output features of a row and stores them as one 16-byte word (a warp store = 8 rows x 64 B)
+//   C = bias     the bias rides in as the accumulator's initial value
+// mma.sync (not tcgen05): TMEM accumulators would have to be drained to registers for the store anyway, which is
+// exactly what bounded the old kernel; there is no K loop to pipeline.  Persistent blocks (weights staged once),
+// 4 blocks per SM so the dependent gather chains of one block hide under the MMA / store phases of the others.
+#include "common.cuh"
+
+namespace lpgnn {
+namespace {
+
+constexpr int kMmaThreads = 256;
+constexpr int kMmaRows = 128;      // rows per block iteration: 8 warps x 16 rows
+
+template <typename T> struct Mma16816;
+template <> struct Mma16816<__nv_bfloat16> {
+  __device__ static __forceinline__ void run(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+};
+template <> struct Mma16816<__half> {
+  __device__ static __forceinline__ void run(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+};
+
+// Shared memory: wfrag [N/32][4][32] uint2 | bias [N] float | z tile [128][16] T
+template <typename T>
+__global__ void __launch_bounds__(kMmaThreads, 4)
+conv_in_mma_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ val, int32_t rows,
+                   const float* __restrict__ Xsrc, const float* __restrict__ Xdst, const float* __restrict__ W_rel,
+                   const float* __restrict__ b_rel, const float* __restrict__ W_root, int N, T* __restrict__ out, int relu,
+                   T* __restrict__ z16 /*[rows,64] or null*/) {
+  extern __shared__ __align__(16) uint8_t smem_m[];
+  uint2* wfrag = reinterpret_cast<uint2*>(smem_m);
+  float* bias_s = reinterpret_cast<float*>(smem_m + (size_t)N * 32);
+  uint32_t* zt = reinterpret_cast<uint32_t*>(smem_m + (size_t)N * 36);      // [128][8] words = 16 T per row
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  // ---- weights in fragment order: entry (chunk, j, lane) = B fragment of MMA j of the 32-column chunk.
+  //      fragment column n (= g) of MMA j is output feature chunk*32 + 8*(n/2) + 2*j + (n%2): lane (g,t) then owns the
+  //      accumulators of features chunk*32 + 8t + 2j, +1 -> over j = 0..3 the 8 consecutive features 8t .. 8t+7.
+  for (int i = tid; i < N * 4; i += kMmaThreads) {
+    const int l = i & 31, j = (i >> 5) & 3, chunk = i >> 7;
+    const int gg = l >> 2, tt = l & 3;
+    const int col = chunk * 32 + 8 * (gg >> 1) + 2 * j + (gg & 1);
+    const float2 wr = __ldg(reinterpret_cast<const float2*>(W_rel + (size_t)col * 8 + 2 * tt));    // k = 2t, 2t+1
+    const float2 wo = __ldg(reinterpret_cast<const float2*>(W_root + (size_t)col * 8 + 2 * tt));   // k = 2t+8, 2t+9
+    wfrag[i] = make_uint2(Half16<T>::pack(wr.x, wr.y), Half16<T>::pack(wo.x, wo.y));
+  }
+  for (int i = tid; i < N; i += kMmaThreads) bias_s[i] = b_rel ? __ldg(b_rel + i) : 0.f;
+  __syncthreads();
+
+  const int r = tid >> 1, h = tid & 1;               // gather role: row r of the tile, feature half h (4 of the 8)
+  const int nchunks = N >> 5;
+  for (int64_t row0 = (int64_t)blockIdx.x * kMmaRows; row0 < rows; row0 += (int64_t)gridDim.x * kMmaRows) {
+    // ---- z[row] = [ sum_e val[e] * Xsrc[idx[e], :] | Xdst[row, :] ]  (fp32 accumulate in CSR order, then 16-bit)
+    {
+      const int64_t row = row0 + r;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), xd = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < rows) {
+        const int32_t beg = __ldg(ptr + row), end = __ldg(ptr + row + 1);
+        int32_t e = beg;
+        for (; e + 2 <= end; e += 2) {
+          const int32_t i0 = __ldg(idx + e), i1 = __ldg(idx + e + 1);
+          const float w0 = __ldg(val + e), w1 = __ldg(val + e + 1);
+          const float4 x0 = __ldg(reinterpret_cast<const float4*>(Xsrc + (int64_t)i0 * 8 + 4 * h));
+          const float4 x1 = __ldg(reinterpret_cast<const float4*>(Xsrc + (int64_t)i1 * 8 + 4 * h));
+          a.x = fmaf(w0, x0.x, a.x); a.y = fmaf(w0, x0.y, a.y); a.z = fmaf(w0, x0.z, a.z); a.w = fmaf(w0, x0.w, a.w);
+          a.x = fmaf(w1, x1.x, a.x); a.y = fmaf(w1, x1.y, a.y); a.z = fmaf(w1, x1.z, a.z); a.w = fmaf(w1, x1.w, a.w);
+        }
+        if (e < end) {
+          const float w0 = __ldg(val + e);
+          const float4 x0 = __ldg(reinterpret_cast<const float4*>(Xsrc + (int64_t)__ldg(idx + e) * 8 + 4 * h));
+          a.x = fmaf(w0, x0.x, a.x); a.y = fmaf(w0, x0.y, a.y); a.z = fmaf(w0, x0.z, a.z); a.w = fmaf(w0, x0.w, a.w);
+        }
+        xd = __ldg(reinterpret_cast<const float4*>(Xdst + row * 8 + 4 * h));
+      }
+      uint32_t* zr = zt + r * 8;                     // words: [agg 0..7 | dst 0..7] as 16-bit pairs
+      *reinterpret_cast<uint2*>(zr + 2 * h) = make_uint2(Half16<T>::pack(a.x, a.y), Half16<T>::pack(a.z, a.w));
+      *reinterpret_cast<uint2*>(zr + 4 + 2 * h) = make_uint2(Half16<T>::pack(xd.x, xd.y), Half16<T>::pack(xd.z, xd.w));
+    }
+    __syncthreads();
+    if (z16) {   // the transform input as the operand of the layer's weight gradient: [z | 1 | 0 ...] 16-bit [rows,64]
+      const int64_t row = row0 + r;
+      if (row < rows) {
+        uint4* dst = reinterpret_cast<uint4*>(z16 + row * 64) + 4 * h;
+        if (h == 0) {
+          const uint4* src = reinterpret_cast<const uint4*>(zt + r * 8);
+          dst[0] = src[0]; dst[1] = src[1];
+          dst[2] = make_uint4(Half16<T>::pack(1.f, 0.f), 0u, 0u, 0u);
+          dst[3] = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+          dst[0] = dst[1] = dst[2] = dst[3] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    }
+    // ---- transform: warp `warp` owns rows 16*warp .. +15 of the tile
+    uint32_t a[4];
+    {
+      const uint32_t* z0 = zt + (16 * warp + g) * 8;
+      const uint32_t* z1 = z0 + 8 * 8;
+      a[0] = z0[t]; a[1] = z1[t]; a[2] = z0[4 + t]; a[3] = z1[4 + t];
+    }
+    const int64_t ra = row0 + 16 * warp + g, rb = ra + 8;
+    T* oa = out + ra * N + 8 * t;
+    T* ob = out + rb * N + 8 * t;
+    const bool va = ra < rows, vb = rb < rows;
+#pragma unroll 2
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t lo[4], hi[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint2 b = wfrag[(c * 4 + j) * 32 + lane];
+        const float2 bs = *reinterpret_cast<const float2*>(bias_s + c * 32 + 8 * t + 2 * j);
+        float d[4] = {bs.x, bs.y, bs.x, bs.y};
+        Mma16816<T>::run(d, a, b.x, b.y);
+        if (relu) { d[0] = fmaxf(d[0], 0.f); d[1] = fmaxf(d[1], 0.f); d[2] = fmaxf(d[2], 0.f); d[3] = fmaxf(d[3], 0.f); }
+        lo[j] = Half16<T>::pack(d[0], d[1]);
+        hi[j] = Half16<T>::pack(d[2], d[3]);
+      }
+      if (va) *reinterpret_cast<uint4*>(oa + c * 32) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      if (vb) *reinterpret_cast<uint4*>(ob + c * 32) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    }
+    __syncthreads();                                 // the z tile is rewritten by the next iteration
+  }
+}
+
+template <typename T>
+int launch_mma(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const float* Xsrc, const float* Xdst,
+               const float* W_rel, const float* b_rel, const float* W_root, int N, void* out, int relu, void* z16,
+               cudaStream_t st) {
+  static int blocks_per_sm = 0;
+  static int smem_set = 0;
+  const int smem = N * 36 + kMmaRows * 32;
+  auto kern = conv_in_mma_kernel<T>;
+  if (smem > smem_set) {
+    LPGNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    smem_set = smem;
+    blocks_per_sm = 0;
+  }
+  if (blocks_per_sm == 0) {
+    LPGNN_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kMmaThreads, smem));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+  }
+  const int tiles = ceil_div(rows, kMmaRows);
+  const int cap = sm_count() * blocks_per_sm;
+  kern<<<tiles < cap ? tiles : cap, kMmaThreads, smem, st>>>(ptr, idx, val, rows, Xsrc, Xdst, W_rel, b_rel, W_root, N,
+                                                             reinterpret_cast<T*>(out), relu, reinterpret_cast<T*>(z16));
+  LPGNN_LAUNCH_OK();
+  count_launches(1);
+  return LPGNN_OK;
+}
+
+}  // namespace
+}  // namespace lpgnn
+
+using namespace lpgnn;
+
+extern "C" int lpgnn_conv_in_16(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const float* Xsrc,
+                                const float* Xdst, const float* W_rel, const float* b_rel, const float* W_root, int32_t N,
+                                void* out, int out_dtype, int epilogue, void* z16, lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(rows >= 0 && N > 0 && N % 32 == 0 && N <= 4096, "conv_in_16: rows=%d, N=%d (N must be a multiple of 32, <= 4096)", rows, N);
+  LPGNN_REQUIRE(is_16bit(out_dtype), "conv_in_16: out dtype %d is not a 16-bit type", out_dtype);
+  if (rows == 0) return LPGNN_OK;
+  LPGNN_REQUIRE(ptr && idx && val && Xsrc && Xdst && W_rel && W_root && out, "conv_in_16: null pointer");
+  LPGNN_REQUIRE((uintptr_t)Xsrc % 16 == 0 && (uintptr_t)Xdst % 16 == 0 && (uintptr_t)W_rel % 8 == 0 && (uintptr_t)W_root % 8 == 0 &&
+                (uintptr_t)out % 16 == 0 && (uintptr_t)z16 % 16 == 0, "conv_in_16: misaligned pointer");
+  const int relu = (epilogue & LPGNN_EPI_RELU) ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == LPGNN_F16)
+    return launch_mma<__half>(ptr, idx, val, rows, Xsrc, Xdst, W_rel, b_rel, W_root, N, out, relu, z16, st);
+  return launch_mma<__nv_bfloat16>(ptr, idx, val, rows, Xsrc, Xdst, W_rel, b_rel, W_root, N, out, relu, z16, st);
+}

@@ -55,6 +55,27 @@ def conv_in_fused(view, x_src, x_dst, w_rel, b_rel, w_root, out_dtype, relu=True
     return out, z_cat
 
 
+def conv_in_16(view, x_src, x_dst, w_rel, b_rel, w_root, out_dtype, relu=True, want_z16=False):
+    """conv1 of GCN_FC(8, 8, ...) for one direction in the 16-bit modes, ONE kernel (``lpgnn_conv_in_16``: aggregate,
+    16-wide MMA with register accumulators, bias, ReLU, 16-bit store).  Returns ``(out[rows,N], z16[rows,64] | None)``."""
+    ptr_, idx, val, rows = view
+    require_cuda(ptr_, x_src, x_dst, w_rel, w_root, b_rel)
+    x_src, x_dst = _contig(x_src.float()), _contig(x_dst.float())
+    w_rel, w_root, b_rel = _contig(w_rel.float()), _contig(w_root.float()), _contig(b_rel.float())
+    if x_src.shape[1] != 8 or x_dst.shape[1] != 8:
+        raise ValueError("conv_in_16 covers the reference's 8 + 8 input features")
+    N = w_rel.shape[0]
+    out = torch.empty((rows, N), dtype=out_dtype, device=x_src.device)
+    z16 = torch.empty((rows, 64), dtype=out_dtype, device=x_src.device) if want_z16 else None
+    with torch.cuda.device(x_src.device):
+        rc = _lib.load().lpgnn_conv_in_16(ptr_.data_ptr(), idx.data_ptr(), val.data_ptr(), rows, x_src.data_ptr(),
+                                          x_dst.data_ptr(), w_rel.data_ptr(), b_rel.data_ptr(), w_root.data_ptr(), N,
+                                          out.data_ptr(), dtype_code(out_dtype), EPI_RELU if relu else EPI_NONE, ptr(z16),
+                                          stream_ptr())
+    check(rc, "lpgnn_conv_in_16")
+    return out, z16
+
+
 def gather_cat(view, x_src, x_dst, want_f32=True, want_bf16=False, dtype16=torch.bfloat16):
     """``z = [A_view @ x_src | x_dst | 0]``: fp32 ``[rows,KT]`` and/or 16-bit ``[rows,64]`` (``dtype16``: bf16 or
     half; input of the tensor-core transform in the 16-bit modes)."""

@@ -97,6 +97,48 @@ def test_conv_in_fused_vs_oracle(cuda, hids, out_dtype):
     np.testing.assert_allclose(out2.float().cpu().numpy(), e2, rtol=tol, atol=tol)
 
 
+@pytest.mark.parametrize("hids", [32, 96, 1024])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("m,n,z", [(700, 1300, 6000), (1, 3, 2), (129, 255, 0), (5000, 9000, 60_000)])
+def test_conv_in_16_one_kernel_input_layer(cuda, hids, dt, m, n, z):
+    """lpgnn_conv_in_16 (aggregate + 16-wide MMA + bias + ReLU + 16-bit store in one kernel) vs float64 on the operands
+    as the kernel rounds them (aggregate in fp32 CSR order -> 16-bit, weights -> 16-bit): only fp32 accumulation and the
+    output rounding remain.  Also the optional weight-gradient operand z16 and the two-kernel path it replaces."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    from lpgnn_b200.graph import BipartiteCSR
+    row, col, val = make_graph_arrays(m, n, z, 5)
+    g = BipartiteCSR.from_coo_arrays(row, col, val, m, n, cuda)
+    ref = port.graph_from_coo(row, col, val, m, n)
+    rng = np.random.default_rng(hids + m)
+    x_s = rng.standard_normal((m, 8)).astype(np.float32)
+    x_t = rng.standard_normal((n, 8)).astype(np.float32)
+    w_rel = (rng.standard_normal((hids, 8)) / 3).astype(np.float32)
+    w_root = (rng.standard_normal((hids, 8)) / 3).astype(np.float32)
+    b = rng.standard_normal(hids).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    rd = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dt).double().numpy()   # 16-bit rounding
+    csr, csc = g.views()
+    for view, xs, xd, ptr_, idx_, val_, relu in ((csc, x_s, x_t, ref.colptr, ref.row_csc, ref.val_csc, True),
+                                                 (csr, x_t, x_s, ref.rowptr, ref.col, ref.val, False)):
+        out, z16 = ops.conv_in_16(view, t(xs), t(xd), t(w_rel), t(b), t(w_root), dt, relu=relu, want_z16=True)
+        assert out.dtype == dt and out.shape == (xd.shape[0], hids)
+        agg = port.spmm_sequential(ptr_, idx_, val_, xs)
+        e = rd(agg) @ rd(w_rel).T + b.astype(np.float64) + rd(xd) @ rd(w_root).T
+        if relu:
+            e = np.maximum(e, 0)
+        eps = 2.0 ** -8 if dt == torch.bfloat16 else 2.0 ** -11
+        err = np.abs(out.double().cpu().numpy() - e)
+        assert float((err / (np.abs(e) + 1.0)).max()) < 1.5 * eps, float((err / (np.abs(e) + 1.0)).max())
+        zz = z16.float().cpu().numpy()
+        np.testing.assert_array_equal(zz[:, :8], rd(agg).astype(np.float32))
+        np.testing.assert_array_equal(zz[:, 8:16], rd(xd).astype(np.float32))
+        assert (zz[:, 16] == 1).all() and (zz[:, 17:] == 0).all()
+        if hids % 64 == 0:   # the gather + one-K-block tcgen05 path computes the same function
+            _, zb = ops.gather_cat(view, t(xs), t(xd), want_f32=False, want_bf16=True, dtype16=dt)
+            assert torch.equal(zb, z16)
+
+
 @pytest.mark.parametrize("M,N,K", [(1000, 1024, 1024), (129, 128, 128), (5000, 64, 64), (300, 512, 256)])
 @pytest.mark.parametrize("want_out", [False, True])
 def test_transform_with_fused_head(cuda, M, N, K, want_out):
