@@ -39,6 +39,13 @@ template <> struct Mma16816<__half> {
   }
 };
 
+// four consecutive floats; one 16-byte load when the caller's array is 16-byte aligned (feature matrices carved out of
+// a packed staging buffer are only 4-byte aligned)
+__device__ __forceinline__ float4 ld4(const float* p, bool vec) {
+  if (vec) return __ldg(reinterpret_cast<const float4*>(p));
+  return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+}
+
 // Shared memory: wfrag [N/32][4][32] uint2 | bias [N] float | z tile [128][16] T
 template <typename T>
 __global__ void __launch_bounds__(kMmaThreads, 4)
@@ -59,14 +66,15 @@ conv_in_mma_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ 
     const int l = i & 31, j = (i >> 5) & 3, chunk = i >> 7;
     const int gg = l >> 2, tt = l & 3;
     const int col = chunk * 32 + 8 * (gg >> 1) + 2 * j + (gg & 1);
-    const float2 wr = __ldg(reinterpret_cast<const float2*>(W_rel + (size_t)col * 8 + 2 * tt));    // k = 2t, 2t+1
-    const float2 wo = __ldg(reinterpret_cast<const float2*>(W_root + (size_t)col * 8 + 2 * tt));   // k = 2t+8, 2t+9
+    const float2 wr = make_float2(__ldg(W_rel + (size_t)col * 8 + 2 * tt), __ldg(W_rel + (size_t)col * 8 + 2 * tt + 1));    // k = 2t, 2t+1
+    const float2 wo = make_float2(__ldg(W_root + (size_t)col * 8 + 2 * tt), __ldg(W_root + (size_t)col * 8 + 2 * tt + 1));  // k = 2t+8, +9
     wfrag[i] = make_uint2(Half16<T>::pack(wr.x, wr.y), Half16<T>::pack(wo.x, wo.y));
   }
   for (int i = tid; i < N; i += kMmaThreads) bias_s[i] = b_rel ? __ldg(b_rel + i) : 0.f;
   __syncthreads();
 
   const int r = tid >> 1, h = tid & 1;               // gather role: row r of the tile, feature half h (4 of the 8)
+  const bool vsrc = (reinterpret_cast<uintptr_t>(Xsrc) & 15) == 0, vdst = (reinterpret_cast<uintptr_t>(Xdst) & 15) == 0;
   const int nchunks = N >> 5;
   for (int64_t row0 = (int64_t)blockIdx.x * kMmaRows; row0 < rows; row0 += (int64_t)gridDim.x * kMmaRows) {
     // ---- z[row] = [ sum_e val[e] * Xsrc[idx[e], :] | Xdst[row, :] ]  (fp32 accumulate in CSR order, then 16-bit)
@@ -79,17 +87,17 @@ conv_in_mma_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ 
         for (; e + 2 <= end; e += 2) {
           const int32_t i0 = __ldg(idx + e), i1 = __ldg(idx + e + 1);
           const float w0 = __ldg(val + e), w1 = __ldg(val + e + 1);
-          const float4 x0 = __ldg(reinterpret_cast<const float4*>(Xsrc + (int64_t)i0 * 8 + 4 * h));
-          const float4 x1 = __ldg(reinterpret_cast<const float4*>(Xsrc + (int64_t)i1 * 8 + 4 * h));
+          const float4 x0 = ld4(Xsrc + (int64_t)i0 * 8 + 4 * h, vsrc);
+          const float4 x1 = ld4(Xsrc + (int64_t)i1 * 8 + 4 * h, vsrc);
           a.x = fmaf(w0, x0.x, a.x); a.y = fmaf(w0, x0.y, a.y); a.z = fmaf(w0, x0.z, a.z); a.w = fmaf(w0, x0.w, a.w);
           a.x = fmaf(w1, x1.x, a.x); a.y = fmaf(w1, x1.y, a.y); a.z = fmaf(w1, x1.z, a.z); a.w = fmaf(w1, x1.w, a.w);
         }
         if (e < end) {
           const float w0 = __ldg(val + e);
-          const float4 x0 = __ldg(reinterpret_cast<const float4*>(Xsrc + (int64_t)__ldg(idx + e) * 8 + 4 * h));
+          const float4 x0 = ld4(Xsrc + (int64_t)__ldg(idx + e) * 8 + 4 * h, vsrc);
           a.x = fmaf(w0, x0.x, a.x); a.y = fmaf(w0, x0.y, a.y); a.z = fmaf(w0, x0.z, a.z); a.w = fmaf(w0, x0.w, a.w);
         }
-        xd = __ldg(reinterpret_cast<const float4*>(Xdst + row * 8 + 4 * h));
+        xd = ld4(Xdst + row * 8 + 4 * h, vdst);
       }
       uint32_t* zr = zt + r * 8;                     // words: [agg 0..7 | dst 0..7] as 16-bit pairs
       *reinterpret_cast<uint2*>(zr + 2 * h) = make_uint2(Half16<T>::pack(a.x, a.y), Half16<T>::pack(a.z, a.w));
@@ -180,8 +188,8 @@ extern "C" int lpgnn_conv_in_16(const int32_t* ptr, const int32_t* idx, const fl
   LPGNN_REQUIRE(is_16bit(out_dtype), "conv_in_16: out dtype %d is not a 16-bit type", out_dtype);
   if (rows == 0) return LPGNN_OK;
   LPGNN_REQUIRE(ptr && idx && val && Xsrc && Xdst && W_rel && W_root && out, "conv_in_16: null pointer");
-  LPGNN_REQUIRE((uintptr_t)Xsrc % 16 == 0 && (uintptr_t)Xdst % 16 == 0 && (uintptr_t)W_rel % 8 == 0 && (uintptr_t)W_root % 8 == 0 &&
-                (uintptr_t)out % 16 == 0 && (uintptr_t)z16 % 16 == 0, "conv_in_16: misaligned pointer");
+  LPGNN_REQUIRE((uintptr_t)Xsrc % 4 == 0 && (uintptr_t)Xdst % 4 == 0 && (uintptr_t)out % 16 == 0 && (uintptr_t)z16 % 16 == 0,
+                "conv_in_16: misaligned pointer (out / z16 need 16 bytes)");
   const int relu = (epilogue & LPGNN_EPI_RELU) ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (out_dtype == LPGNN_F16)

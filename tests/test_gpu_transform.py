@@ -125,13 +125,16 @@ def test_conv_in_16_one_kernel_input_layer(cuda, hids, dt, m, n, z):
         assert out.dtype == dt and out.shape == (xd.shape[0], hids)
         agg = port.spmm_sequential(ptr_, idx_, val_, xs)
         e = rd(agg) @ rd(w_rel).T + b.astype(np.float64) + rd(xd) @ rd(w_root).T
+        e_scale = np.abs(rd(agg)) @ np.abs(rd(w_rel)).T + np.abs(b).astype(np.float64) + np.abs(rd(xd)) @ np.abs(rd(w_root)).T
         if relu:
             e = np.maximum(e, 0)
         eps = 2.0 ** -8 if dt == torch.bfloat16 else 2.0 ** -11
         err = np.abs(out.double().cpu().numpy() - e)
-        assert float((err / (np.abs(e) + 1.0)).max()) < 1.5 * eps, float((err / (np.abs(e) + 1.0)).max())
+        # output rounding (eps of the value) + a one-ulp flip of an aggregate entry (eps of the terms' magnitude)
+        assert float((err / (e_scale + 1e-6)).max()) < 1.5 * eps, float((err / (e_scale + 1e-6)).max())
         zz = z16.float().cpu().numpy()
-        np.testing.assert_array_equal(zz[:, :8], rd(agg).astype(np.float32))
+        # (the kernel accumulates with fused multiply-adds, the oracle with separate roundings: at most one 16-bit ulp apart)
+        np.testing.assert_allclose(zz[:, :8], rd(agg).astype(np.float32), rtol=2 * eps, atol=1e-6)
         np.testing.assert_array_equal(zz[:, 8:16], rd(xd).astype(np.float32))
         assert (zz[:, 16] == 1).all() and (zz[:, 17:] == 0).all()
         if hids % 64 == 0:   # the gather + one-K-block tcgen05 path computes the same function
