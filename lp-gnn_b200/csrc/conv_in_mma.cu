@@ -187,7 +187,8 @@ extern "C" int lpgnn_conv_in_16(const int32_t* ptr, const int32_t* idx, const fl
   LPGNN_REQUIRE(rows >= 0 && N > 0 && N % 32 == 0 && N <= 4096, "conv_in_16: rows=%d, N=%d (N must be a multiple of 32, <= 4096)", rows, N);
   LPGNN_REQUIRE(is_16bit(out_dtype), "conv_in_16: out dtype %d is not a 16-bit type", out_dtype);
   if (rows == 0) return LPGNN_OK;
-  LPGNN_REQUIRE(ptr && idx && val && Xsrc && Xdst && W_rel && W_root && out, "conv_in_16: null pointer");
+  // (idx / val may be null for a graph without entries: they are only read inside non-empty rows)
+  LPGNN_REQUIRE(ptr && Xsrc && Xdst && W_rel && W_root && out, "conv_in_16: null pointer");
   LPGNN_REQUIRE((uintptr_t)Xsrc % 4 == 0 && (uintptr_t)Xdst % 4 == 0 && (uintptr_t)out % 16 == 0 && (uintptr_t)z16 % 16 == 0,
                 "conv_in_16: misaligned pointer (out / z16 need 16 bytes)");
   const int relu = (epilogue & LPGNN_EPI_RELU) ? 1 : 0;
