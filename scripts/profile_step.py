@@ -10,7 +10,7 @@ from lpgnn_b200 import arch, synth
 from lpgnn_b200.pipeline import pack_lp, unpack_device
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "predict"
-precision = sys.argv[2] if len(sys.argv) > 2 else "bf16"       # bf16 | fp16 (prediction only)
+precision = sys.argv[2] if len(sys.argv) > 2 else "bf16"       # bf16 | fp16 | fp32 (fp16: prediction only)
 dev = torch.device("cuda:0")
 cfg = synth.CONFIGS["C2"]
 lp = synth.processed_lp(cfg["m"], cfg["n"], cfg["nnz"], seed=cfg["seed"], structure="staircase")

@@ -24,8 +24,8 @@ for r in rows:
     a[0] += t; a[1] += 1
 tot = sum(a[0] for a in agg.values())
 with open(os.path.join(ROOT, "profiles", f"{tag}_step_shares.txt"), "w") as f:
-    what = sys.argv[4] if len(sys.argv) > 4 else "prediction step (lpgnn_predict_basis)"
-    f.write(f"# ncu launch list (gpu__time_duration.sum, --clock-control none) of ONE C2 bf16 {what} = {len(rows)} launches\n")
+    what = sys.argv[4] if len(sys.argv) > 4 else "bf16 prediction step (lpgnn_predict_basis)"
+    f.write(f"# ncu launch list (gpu__time_duration.sum, --clock-control none) of ONE C2 {what} = {len(rows)} launches\n")
     f.write("# (scripts/profile_step.py inside cudaProfilerStart/Stop).  Cold-cache, serialised: compare SHARES, not absolutes.\n\n")
     for k, (t, c) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         f.write(f"{t:9.1f} us  {100 * t / tot:5.1f} %  x{c:<2d} {k}\n")
@@ -64,7 +64,7 @@ for d in data:
     k = short(d[col["Kernel Name"]])
     traffic.setdefault(k, []).append(int(to_bytes(d, "dram__bytes_read.sum") + to_bytes(d, "dram__bytes_write.sum")))
 json.dump({"_comment": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum), ncu --set full --clock-control none, "
-                       "one C2 bf16 step (scripts/profile_step.py); launches in step order", "per_kernel": traffic},
+                       "one C2 step (scripts/profile_step.py; precision in the file name); launches in step order", "per_kernel": traffic},
           open(os.path.join(ROOT, "profiles", f"{tag}_traffic_raw.json"), "w"), indent=1)
 print(open(os.path.join(ROOT, "profiles", f"{tag}_step_shares.txt")).read())
 for k, v in traffic.items():
