@@ -21,7 +21,7 @@ namespace lpgnn {
 namespace {
 
 constexpr int kMmaThreads = 256;
-constexpr int kMmaRows = 128;      // rows per block iteration: 8 warps x 16 rows
+constexpr int kMmaRows = 128;      // rows a block covers per sweep of its warps: 8 warps x 16 rows
 
 template <typename T> struct Mma16816;
 template <> struct Mma16816<__nv_bfloat16> {
@@ -73,10 +73,15 @@ conv_in_mma_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ 
   for (int i = tid; i < N; i += kMmaThreads) bias_s[i] = b_rel ? __ldg(b_rel + i) : 0.f;
   __syncthreads();
 
-  const int r = tid >> 1, h = tid & 1;               // gather role: row r of the tile, feature half h (4 of the 8)
+  // ---- every WARP walks its own 16-row tiles (no block-level barrier after the weight staging: tiles are small, so the
+  //      150K rows of BASELINE C2 spread evenly over all resident warps and a warp's dependent gather chain hides under
+  //      the MMA / store phases of the others)
+  const int r = lane >> 1, h = lane & 1;             // gather role: row r of the tile, feature half h (4 of the 8)
   const bool vsrc = (reinterpret_cast<uintptr_t>(Xsrc) & 15) == 0, vdst = (reinterpret_cast<uintptr_t>(Xdst) & 15) == 0;
   const int nchunks = N >> 5;
-  for (int64_t row0 = (int64_t)blockIdx.x * kMmaRows; row0 < rows; row0 += (int64_t)gridDim.x * kMmaRows) {
+  uint32_t* zw = zt + warp * (16 * 8);               // this warp's z tile: [16][8] words = 16 T per row
+  const int64_t warps_total = (int64_t)gridDim.x * (kMmaThreads / 32);
+  for (int64_t row0 = ((int64_t)blockIdx.x * (kMmaThreads / 32) + warp) * 16; row0 < rows; row0 += warps_total * 16) {
     // ---- z[row] = [ sum_e val[e] * Xsrc[idx[e], :] | Xdst[row, :] ]  (fp32 accumulate in CSR order, then 16-bit)
     {
       const int64_t row = row0 + r;
@@ -99,17 +104,17 @@ conv_in_mma_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ 
         }
         xd = ld4(Xdst + row * 8 + 4 * h, vdst);
       }
-      uint32_t* zr = zt + r * 8;                     // words: [agg 0..7 | dst 0..7] as 16-bit pairs
+      uint32_t* zr = zw + r * 8;                     // words: [agg 0..7 | dst 0..7] as 16-bit pairs
       *reinterpret_cast<uint2*>(zr + 2 * h) = make_uint2(Half16<T>::pack(a.x, a.y), Half16<T>::pack(a.z, a.w));
       *reinterpret_cast<uint2*>(zr + 4 + 2 * h) = make_uint2(Half16<T>::pack(xd.x, xd.y), Half16<T>::pack(xd.z, xd.w));
     }
-    __syncthreads();
+    __syncwarp();
     if (z16) {   // the transform input as the operand of the layer's weight gradient: [z | 1 | 0 ...] 16-bit [rows,64]
       const int64_t row = row0 + r;
       if (row < rows) {
         uint4* dst = reinterpret_cast<uint4*>(z16 + row * 64) + 4 * h;
         if (h == 0) {
-          const uint4* src = reinterpret_cast<const uint4*>(zt + r * 8);
+          const uint4* src = reinterpret_cast<const uint4*>(zw + r * 8);
           dst[0] = src[0]; dst[1] = src[1];
           dst[2] = make_uint4(Half16<T>::pack(1.f, 0.f), 0u, 0u, 0u);
           dst[3] = make_uint4(0u, 0u, 0u, 0u);
@@ -118,14 +123,15 @@ conv_in_mma_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ 
         }
       }
     }
-    // ---- transform: warp `warp` owns rows 16*warp .. +15 of the tile
+    // ---- transform of the warp's 16 rows
     uint32_t a[4];
     {
-      const uint32_t* z0 = zt + (16 * warp + g) * 8;
+      const uint32_t* z0 = zw + g * 8;
       const uint32_t* z1 = z0 + 8 * 8;
       a[0] = z0[t]; a[1] = z1[t]; a[2] = z0[4 + t]; a[3] = z1[4 + t];
     }
-    const int64_t ra = row0 + 16 * warp + g, rb = ra + 8;
+    __syncwarp();                                    // the z tile may be rewritten (next tile's gather) from here on
+    const int64_t ra = row0 + g, rb = ra + 8;
     T* oa = out + ra * N + 8 * t;
     T* ob = out + rb * N + 8 * t;
     const bool va = ra < rows, vb = rb < rows;
@@ -145,7 +151,6 @@ conv_in_mma_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ 
       if (va) *reinterpret_cast<uint4*>(oa + c * 32) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       if (vb) *reinterpret_cast<uint4*>(ob + c * 32) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     }
-    __syncthreads();                                 // the z tile is rewritten by the next iteration
   }
 }
 
@@ -166,7 +171,7 @@ int launch_mma(const int32_t* ptr, const int32_t* idx, const float* val, int32_t
     LPGNN_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kMmaThreads, smem));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
   }
-  const int tiles = ceil_div(rows, kMmaRows);
+  const int tiles = ceil_div(rows, kMmaRows);       // blocks needed if every warp took one 16-row tile
   const int cap = sm_count() * blocks_per_sm;
   kern<<<tiles < cap ? tiles : cap, kMmaThreads, smem, st>>>(ptr, idx, val, rows, Xsrc, Xdst, W_rel, b_rel, W_root, N,
                                                              reinterpret_cast<T*>(out), relu, reinterpret_cast<T*>(z16));

@@ -53,7 +53,12 @@ class _GCNFCFunction(torch.autograd.Function):
         x_s, x_t = x_s.float().contiguous(), x_t.float().contiguous()
         # conv1 (p,q -> H), relu fused.  bf16 mode: gather -> tensor-core transform over one zero-padded K block
         # (same arithmetic as the inference path); fp32 mode: CUDA-core fused kernel.
-        if dt == torch.bfloat16 and x_s.shape[1] + x_t.shape[1] <= 64 and P[0].shape[0] % 64 == 0:
+        if dt == torch.bfloat16 and x_s.shape[1] == 8 and x_t.shape[1] == 8 and P[0].shape[0] % 64 == 0 and P[0].shape[0] <= 4096:
+            # the reference's 8 + 8 input features: one kernel per direction, which also emits the bf16 operand
+            # [z | 1 | 0] of the layer's tensor-core weight gradient
+            right, z_t = ops.conv_in_16(csc, x_s, x_t, P[0], P[1], P[2], dt, relu=True, want_z16=True)
+            left, z_s = ops.conv_in_16(csr, x_t, x_s, P[3], P[4], P[5], dt, relu=True, want_z16=True)
+        elif dt == torch.bfloat16 and x_s.shape[1] + x_t.shape[1] <= 64 and P[0].shape[0] % 64 == 0:
             def wcat(w_rel, w_root):
                 w = torch.zeros((w_rel.shape[0], 64), dtype=dt, device=w_rel.device)
                 w[:, :w_rel.shape[1]] = w_rel
