@@ -368,7 +368,8 @@ def run_gpu(args):
                 out["train_c1_fp32"]["cpu_baseline"] = cpu_train_baseline(c1, lp1)
                 out["train"]["cpu_baseline"] = cpu_train_baseline(cfg, lp, sample_budget_s=20.0, max_steps=3, warm=1)
     if not args.no_sweep and args.workload in ("C2", "C3"):
-        sw = sweep_measure(args, rank, world, dev, lib, args.precision, steps=max(200, min(10 * args.steps, 1000)),
+        # (at least 1000 LPs = ~20 packs per rank: a handful of packs would only time the pipeline's fill and drain)
+        sw = sweep_measure(args, rank, world, dev, lib, args.precision, steps=max(1000, min(10 * args.steps, 3000)),
                            distinct=args.sweep_distinct, with_cpu=False)
         if rank == 0:
             out["sweep"] = sw
