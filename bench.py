@@ -349,6 +349,7 @@ def run_gpu(args):
         c1 = workload_spec("C1")
         lp1 = synth.processed_lp(c1["m"], c1["n"], c1["nnz"], seed=c1["seed"] + 1000 * rank, structure=args.structure)
         tr1 = train_throughput(c1, lp1, dev, "fp32", max(10, min(args.steps, 100)), 3, world)
+        tr1p = train_packed_throughput(c1, dev, "fp32", 64, max(10, min(args.steps, 50)), world, rank, args.structure)
         ts = None
         if args.workload == "C3":
             try:
@@ -362,6 +363,7 @@ def run_gpu(args):
             out["train_ms_per_step"] = tr["ms_per_step"]
             out["train_lps_per_sec"] = tr["lps_per_sec"]
             out["train_c1_fp32"] = tr1
+            out["train_c1_fp32_packed"] = tr1p
             if ts is not None:
                 out["train_sampled"] = ts
             if world == 1 and not args.no_cpu:
@@ -570,6 +572,61 @@ def train_throughput(cfg, lp, dev, precision, steps, warmup, world):
                         f"(fwd + balanced loss + bwd + Adam{' + NCCL grad all-reduce' if world > 1 else ''}), dp={model.dp}",
             "precision": precision, "steps": steps, "ms_per_step": t_ms / steps, "lps_per_sec": sps,
             "mp_edges_per_sec_fwd_bwd": mp_edges(lp.nnz, cfg["depth"], fwd_bwd=True) * sps}
+
+
+def train_packed_throughput(cfg, dev, precision, n_lps, steps, world, rank, structure):
+    """Mini-batches of LP graphs (north star config 3; `train.py --pack`): ``n_lps`` distinct LPs of the workload's shape
+    packed block-diagonally, ONE native forward / backward over the pack, the per-LP balanced loss averaged over the pack
+    (losses.balanced_packed), gradient all-reduce (N > 1), Adam.  Reported per LP: the reference's loop (train.py:70,
+    117-129) takes one optimiser step per LP, here ``n_lps`` graphs share one."""
+    from lpgnn_b200 import arch, dataset, synth
+    from lpgnn_b200.data import Data
+    from lpgnn_b200.graph import BipartiteCSR
+    from lpgnn_b200.losses import balanced_packed
+    from lpgnn_b200.train import allreduce_gradients, broadcast_parameters
+    torch.manual_seed(0)
+    model = arch.GCN_FC(8, 8, hids=cfg["hids"], depth=cfg["depth"]).to(dev).train().set_precision(precision)
+    broadcast_parameters(model, world)
+    params = list(model.parameters())
+    opt = torch.optim.Adam(params, lr=1e-3, weight_decay=5e-4, fused=True)
+    items = []
+    for i in range(n_lps):
+        lp = synth.processed_lp(cfg["m"], cfg["n"], cfg["nnz"], seed=cfg["seed"] + 1000 * rank + 31 * i, structure=structure)
+        g = BipartiteCSR.from_coo(torch.from_numpy(lp.row), torch.from_numpy(lp.col), torch.from_numpy(lp.a_data.astype(np.float32)),
+                                  lp.m, lp.n, is_sorted=True)
+        items.append(Data(x_s=torch.from_numpy(lp.c_feas), x_t=torch.from_numpy(lp.v_feas), y_s=torch.from_numpy(lp.y_s),
+                          y_t=torch.from_numpy(lp.y_t), edge_index=g))
+    batch = dataset.pack_bipartite(items).to(dev)
+    nnz = batch.edge_index.nnz()
+
+    def step():
+        lc, lv = model(batch)
+        loss = balanced_packed(lc, lv, batch.y_s, batch.y_t, batch.cons_ptr, batch.vars_ptr)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        allreduce_gradients(params, world)
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        step()
+    barrier(world)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    t_ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    assert bool(torch.isfinite(loss))
+    lps = world * steps * n_lps / (t_ms / 1e3)
+    return {"workload": f"packs of {n_lps} {cfg['name']}-shaped LPs ({batch.x_s.shape[0]} x {batch.x_t.shape[0]}, nnz {nnz} per pack), "
+                        f"GCN_FC(8,8,hids={cfg['hids']},depth={cfg['depth']}): one training step per pack (fwd + per-LP balanced "
+                        f"loss + bwd + Adam{' + NCCL grad all-reduce' if world > 1 else ''})",
+            "precision": precision, "steps": steps, "ms_per_step": t_ms / steps, "ms_per_lp": t_ms / steps / n_lps,
+            "lps_per_sec": lps, "mp_edges_per_sec_fwd_bwd": mp_edges(nnz / n_lps, cfg["depth"], fwd_bwd=True) * lps}
 
 
 def kernel_rooflines(model, lp, dev, peaks, bf16, args):

@@ -541,6 +541,17 @@ LPGNN_API int lpgnn_balanced_ce(const float* logits_s, const int64_t* y_s, int32
                       const int64_t* y_t, int32_t n, int merge_lu, float* loss_out, float* dlogits_s,
                       float* dlogits_t, void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
 
+/* balanced() over a block-diagonal PACK of LPs (mini-batches of LP graphs; the reference trains one LP per step,
+ * train.py:70): LP b owns constraints [cons_ptr[b], cons_ptr[b+1]) of logits_s / y_s and variables [vars_ptr[b],
+ * vars_ptr[b+1]) of logits_t / y_t (device int32 [n_segments+1]), keeps its own class weights and (m_b+n_b)/m_b,
+ * (m_b+n_b)/n_b factors (train.py:39-46 per graph); loss_out = mean over the LPs, dlogits_* = its gradient (the average
+ * of the per-LP gradients).  One CTA per (LP, side); deterministic. */
+LPGNN_API size_t lpgnn_balanced_ce_segmented_workspace_bytes(int32_t n_segments);
+LPGNN_API int lpgnn_balanced_ce_segmented(const float* logits_s, const int64_t* y_s, const int32_t* cons_ptr,
+                                const float* logits_t, const int64_t* y_t, const int32_t* vars_ptr, int32_t n_segments,
+                                int merge_lu, float* loss_out, float* dlogits_s, float* dlogits_t, void* workspace,
+                                size_t workspace_bytes, lpgnn_stream_t stream);
+
 /* (f-3) The other two losses of the training loop, value and gradient in one kernel.  focal = 0: unbalanced()
  * (reference train.py:30-37) = F.cross_entropy over the concatenation of both sides (plain mean over m+n rows);
  * focal = 1: focal() (train.py:18-28, 49-53) = (1 - exp(-ce))^gamma * ce of that same mean CE (the reference applies

@@ -126,6 +126,8 @@ SIGNATURES = {
     "lpgnn_lp_features": (_int, [_p] * 11 + [_i64, _i32, _i32] + [_p] * 10 + [_p, _sz, _p]),
     "lpgnn_balanced_ce_workspace_bytes": (_sz, [_i32, _i32]),
     "lpgnn_balanced_ce": (_int, [_p, _p, _i32, _p, _p, _i32, _int, _p, _p, _p, _p, _sz, _p]),
+    "lpgnn_balanced_ce_segmented_workspace_bytes": (_sz, [_i32]),
+    "lpgnn_balanced_ce_segmented": (_int, [_p, _p, _p, _p, _p, _p, _i32, _int, _p, _p, _p, _p, _sz, _p]),
     "lpgnn_flat_ce_workspace_bytes": (_sz, [_i32, _i32]),
     "lpgnn_flat_ce": (_int, [_p, _p, _i32, _p, _p, _i32, _int, C.c_float, _p, _p, _p, _p, _p, _sz, _p]),
     "lpgnn_basis_metrics": (_int, [_p, _int, _p, _i32, _p, _i32, _p, _p]),

@@ -242,6 +242,86 @@ basis_metrics_kernel(const StatusT* __restrict__ status, const int64_t* __restri
   if (threadIdx.x < 8 && c[threadIdx.x]) atomicAdd(&counts[threadIdx.x], c[threadIdx.x]);
 }
 
+// ------------------------------------------------------------------------------------------------ packed mini-batches
+// balanced() for a block-diagonal PACK of LPs (north star: "mini-batches of LP graphs"; the reference trains one LP per
+// step, train.py:70): every LP b keeps its OWN class weights and (m_b+n_b)/m_b, (m_b+n_b)/n_b factors (train.py:39-46
+// applied per graph), the pack's loss is the mean over its LPs -- the gradient is the average of the per-LP gradients,
+// i.e. what one optimiser step over B graphs (or B data-parallel ranks) would apply.  One CTA per (LP, side): class
+// counts, weights, the weighted CE (fixed-order block reduction) and the logit gradients; the last CTA to finish adds
+// the per-(LP, side) terms in index order.  Deterministic.
+struct SegWs {
+  unsigned int done;
+  unsigned int pad[3];
+};
+
+__global__ void __launch_bounds__(kThreads)
+ce_segmented_kernel(const float* __restrict__ x_s, const int64_t* __restrict__ y_s, const int32_t* __restrict__ cptr,
+                    const float* __restrict__ x_t, const int64_t* __restrict__ y_t, const int32_t* __restrict__ vptr,
+                    int n_seg, int merge_lu, SegWs* ws, float* __restrict__ terms /*[n_seg][2]*/, float* __restrict__ d_s,
+                    float* __restrict__ d_t, float* __restrict__ loss_out) {
+  const int b = blockIdx.x >> 1, side = blockIdx.x & 1;
+  const int32_t c0 = cptr[b], mb = cptr[b + 1] - c0, v0 = vptr[b], nb = vptr[b + 1] - v0;
+  const float* x = side ? x_t + 3 * (int64_t)v0 : x_s + 3 * (int64_t)c0;
+  const int64_t* y = side ? y_t + v0 : y_s + c0;
+  float* d = side ? (d_t ? d_t + 3 * (int64_t)v0 : nullptr) : (d_s ? d_s + 3 * (int64_t)c0 : nullptr);
+  const int rows = side ? nb : mb;
+  __shared__ int cnt[4];
+  __shared__ float red[kThreads / 32];
+  __shared__ bool last;
+  if (threadIdx.x < 4) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  int c[3] = {0, 0, 0};
+  for (int i = threadIdx.x; i < rows; i += kThreads) { const int64_t l = y[i]; if (l >= 0 && l < 3) ++c[(int)l]; }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    int v = c[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&cnt[k], v);      // integer: order-free
+  }
+  __syncthreads();
+  float w[3], denom;
+  class_weights(cnt, merge_lu, w, &denom);
+  const float coef = rows > 0 ? (float)(mb + nb) / (float)rows : 0.f;
+  const float inv_b = 1.f / (float)n_seg;
+  float part = 0.f;
+  for (int i = threadIdx.x; i < rows; i += kThreads) {
+    const float a = x[3 * (int64_t)i], bb = x[3 * (int64_t)i + 1], cc = x[3 * (int64_t)i + 2];
+    const float mx = fmaxf(a, fmaxf(bb, cc));
+    const float ea = expf(a - mx), eb = expf(bb - mx), ec = expf(cc - mx);
+    const float se = ea + eb + ec;
+    const int64_t l = y[i];
+    const bool ok = l >= 0 && l < 3;
+    const float wi = ok ? w[(int)l] : 0.f;
+    part += ok ? wi * ((mx + logf(se)) - (l == 0 ? a : (l == 1 ? bb : cc))) : 0.f;
+    if (d) {
+      const float g = denom > 0.f ? inv_b * coef * wi / denom : 0.f, inv = 1.f / se;
+      d[3 * (int64_t)i] = g * (ea * inv - (l == 0 ? 1.f : 0.f));
+      d[3 * (int64_t)i + 1] = g * (eb * inv - (l == 1 ? 1.f : 0.f));
+      d[3 * (int64_t)i + 2] = g * (ec * inv - (l == 2 ? 1.f : 0.f));
+    }
+  }
+  // block sum in a fixed order (per-thread strided partials, then lanes, then warps)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; ++k) sum += red[k];
+    terms[blockIdx.x] = denom > 0.f ? coef * sum / denom : 0.f;
+    __threadfence();
+    last = atomicAdd(&ws->done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last || threadIdx.x != 0) return;
+  __threadfence();
+  double total = 0.0;
+  for (int k = 0; k < 2 * n_seg; ++k) total += (double)__ldcg(terms + k);
+  *loss_out = (float)(total / (double)n_seg);
+}
+
 }  // namespace
 }  // namespace lpgnn
 
@@ -317,6 +397,33 @@ extern "C" int lpgnn_basis_metrics(const void* status, int status_is_i64, const 
     basis_metrics_kernel<int64_t><<<grid, kThreads, 0, st>>>(reinterpret_cast<const int64_t*>(status), y_s, m, y_t, n, counts_out);
   else
     basis_metrics_kernel<uint8_t><<<grid, kThreads, 0, st>>>(reinterpret_cast<const uint8_t*>(status), y_s, m, y_t, n, counts_out);
+  LPGNN_LAUNCH_OK();
+  count_launches(1);
+  return LPGNN_OK;
+}
+
+extern "C" size_t lpgnn_balanced_ce_segmented_workspace_bytes(int32_t n_segments) {
+  return sizeof(SegWs) + (size_t)2 * (n_segments > 0 ? n_segments : 1) * sizeof(float);
+}
+
+extern "C" int lpgnn_balanced_ce_segmented(const float* logits_s, const int64_t* y_s, const int32_t* cons_ptr,
+                                           const float* logits_t, const int64_t* y_t, const int32_t* vars_ptr,
+                                           int32_t n_segments, int merge_lu, float* loss_out, float* dlogits_s, float* dlogits_t,
+                                           void* workspace, size_t workspace_bytes, lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(n_segments > 0, "balanced_ce_segmented: n_segments=%d must be positive", n_segments);
+  LPGNN_REQUIRE(logits_s && y_s && cons_ptr && logits_t && y_t && vars_ptr && loss_out && workspace, "balanced_ce_segmented: null pointer");
+  LPGNN_REQUIRE((dlogits_s == nullptr) == (dlogits_t == nullptr), "balanced_ce_segmented: pass both gradient outputs or neither");
+  LPGNN_REQUIRE((uintptr_t)workspace % 16 == 0, "balanced_ce_segmented: workspace must be 16-byte aligned");
+  if (workspace_bytes < lpgnn_balanced_ce_segmented_workspace_bytes(n_segments)) {
+    set_error("balanced_ce_segmented: workspace too small");
+    return LPGNN_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  SegWs* ws = reinterpret_cast<SegWs*>(workspace);
+  LPGNN_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(SegWs), st));
+  ce_segmented_kernel<<<2 * n_segments, kThreads, 0, st>>>(logits_s, y_s, cons_ptr, logits_t, y_t, vars_ptr, n_segments, merge_lu, ws,
+                                                          reinterpret_cast<float*>(ws + 1), dlogits_s, dlogits_t, loss_out);
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;

@@ -216,3 +216,36 @@ def write_synthetic_dataset(root, sizes, seed=0, structure="staircase"):
         msgpack_dump(dict(num_cons=lp.m, num_vars=lp.n, raw_path="", processed_path=fn,
                           con_nms=[f"c{j}" for j in range(lp.m)], var_nms=[f"x{j}" for j in range(lp.n)]), fn + ".meta")
     return pdir
+
+
+def pack_bipartite(batches):
+    """Block-diagonal pack of bipartite LP batches (``MyToBipartite`` output, host side): ONE graph (the direct sum of the LPs'
+    matrices, what a PyG ``DataLoader(batch_size > 1)`` would collate -- the reference runs ``batch_size=1``, train.py:70),
+    concatenated features / labels and the segment pointers ``cons_ptr`` / ``vars_ptr`` (int32 [B+1]) that
+    ``losses.balanced_packed`` and the segmented basis decision need.  Entries stay in canonical order when every LP's are."""
+    from .data import Data
+    ms = [int(b.x_s.shape[0]) for b in batches]
+    ns = [int(b.x_t.shape[0]) for b in batches]
+    c_ptr = np.concatenate([[0], np.cumsum(ms)]).astype(np.int64)
+    v_ptr = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
+    rows, cols, vals, in_order = [], [], [], True
+    for k, b in enumerate(batches):
+        g = b.edge_index
+        if g._coo is None:
+            raise ValueError("pack_bipartite packs host-side graphs (before .to(device))")
+        r, c, v = g._coo
+        rows.append(r.to(torch.int64) + int(c_ptr[k]))
+        cols.append(c.to(torch.int64) + int(v_ptr[k]))
+        vals.append(v)
+        in_order = in_order and bool(g._sorted_hint)
+    M, N = int(c_ptr[-1]), int(v_ptr[-1])
+    graph = BipartiteCSR.from_coo(torch.cat(rows), torch.cat(cols), torch.cat(vals), M, N, is_sorted=in_order)
+    out = Data(x_s=torch.cat([b.x_s for b in batches]), x_t=torch.cat([b.x_t for b in batches]), edge_index=graph,
+               cons_ptr=torch.from_numpy(c_ptr.astype(np.int32)), vars_ptr=torch.from_numpy(v_ptr.astype(np.int32)))
+    if all(hasattr(b, "y_s") for b in batches):
+        out.y_s, out.y_t = torch.cat([b.y_s for b in batches]), torch.cat([b.y_t for b in batches])
+    out.n_lps = len(batches)
+    out.lp_sizes = (ms, ns)                        # host-side sizes of the packed LPs (constraints, variables)
+    out.bs = out.batch_size = M + N
+    out.s_bs, out.t_bs = M, N
+    return out

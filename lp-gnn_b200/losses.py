@@ -99,6 +99,53 @@ def balanced(logpr_cons, logpr_vars, y_s, y_t):
     return balanced_torch(logpr_cons, logpr_vars, y_s, y_t)
 
 
+class _BalancedCEPacked(torch.autograd.Function):
+    """``lpgnn_balanced_ce_segmented``: mean over the LPs of a pack of the per-LP balanced loss, and its gradient."""
+
+    @staticmethod
+    def forward(ctx, logit_s, logit_t, y_s, y_t, cons_ptr, vars_ptr):
+        from . import _lib
+        lib = _lib.load()
+        logit_s, logit_t = logit_s.contiguous(), logit_t.contiguous()
+        y_s, y_t = y_s.contiguous(), y_t.contiguous()
+        m, n, B = logit_s.shape[0], logit_t.shape[0], int(cons_ptr.shape[0]) - 1
+        dev = logit_s.device
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        d = torch.empty((m + n, 3), dtype=torch.float32, device=dev) if need else None
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        ws_bytes = lib.lpgnn_balanced_ce_segmented_workspace_bytes(B)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.lpgnn_balanced_ce_segmented(logit_s.data_ptr(), y_s.data_ptr(), cons_ptr.data_ptr(), logit_t.data_ptr(),
+                                                 y_t.data_ptr(), vars_ptr.data_ptr(), B, 1, loss.data_ptr(), _lib.ptr(d),
+                                                 d[m:].data_ptr() if need else None, ws.data_ptr(), ws_bytes, _lib.stream_ptr())
+        _lib.check(rc, "lpgnn_balanced_ce_segmented")
+        ctx.d, ctx.m = d, m
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        d = ctx.d * g
+        return d[:ctx.m], d[ctx.m:], None, None, None, None
+
+
+def balanced_packed_torch(logpr_cons, logpr_vars, y_s, y_t, cons_ptr, vars_ptr):
+    """Mean over the LPs of a pack of ``balanced`` (train.py:39-46 applied per graph), framework ops."""
+    c, v = cons_ptr.tolist(), vars_ptr.tolist()
+    terms = [balanced_torch(logpr_cons[c[b]:c[b + 1]], logpr_vars[v[b]:v[b + 1]], y_s[c[b]:c[b + 1]], y_t[v[b]:v[b + 1]])
+             for b in range(len(c) - 1)]
+    return torch.stack(terms).mean()
+
+
+def balanced_packed(logpr_cons, logpr_vars, y_s, y_t, cons_ptr, vars_ptr):
+    """``balanced`` for a block-diagonal pack of LPs (``dataset.pack_bipartite``): every LP keeps its own class weights
+    and size factors; the pack's loss is the mean over its LPs, so its gradient is the average of the per-LP gradients."""
+    if _native_ok(logpr_cons, logpr_vars, y_s, y_t) and cons_ptr.is_cuda and vars_ptr.is_cuda \
+            and cons_ptr.dtype == torch.int32 and vars_ptr.dtype == torch.int32:
+        return _BalancedCEPacked.apply(logpr_cons, logpr_vars, y_s, y_t, cons_ptr.contiguous(), vars_ptr.contiguous())
+    return balanced_packed_torch(logpr_cons, logpr_vars, y_s, y_t, cons_ptr, vars_ptr)
+
+
 def _native_ok(logpr_cons, logpr_vars, y_s, y_t):
     return (logpr_cons.is_cuda and logpr_vars.is_cuda and logpr_cons.dtype == torch.float32 and logpr_vars.dtype == torch.float32
             and y_s.dtype == torch.int64 and y_t.dtype == torch.int64 and len(y_s) + len(y_t) > 0

@@ -24,9 +24,9 @@ from torch.optim.lr_scheduler import StepLR
 
 from .arch import *  # noqa: F401,F403  (``eval(args.arch)`` resolves GCN_FC(...) like the reference, train.py:79)
 from .data import DataLoader
-from .dataset import LPDataset, MyToBipartite
+from .dataset import LPDataset, MyToBipartite, pack_bipartite
 from .io_utils import shard_indices, split_train_val
-from .losses import LOSSES, FocalLoss, balanced, focal, unbalanced  # noqa: F401  (module-level names of train.py:18-53)
+from .losses import LOSSES, FocalLoss, balanced, balanced_packed, focal, unbalanced  # noqa: F401  (names of train.py:18-53)
 from .val import accuracy
 
 
@@ -173,6 +173,8 @@ def parse_args(argv=None, **defaults):
     ap.add_argument("--fp16", type=int, default=0)
     ap.add_argument("--log_every", type=int, default=9)
     ap.add_argument("--packed", type=int, default=0, help="pred_basis: pack LPs block-diagonally (sweep mode)")
+    ap.add_argument("--pack", type=int, default=1,
+                    help="train: LP graphs per optimiser step, packed block-diagonally (balanced loss; 1 = the reference's loop)")
     ap.add_argument("--dataset_processed_prefix", type=str, default=None)
     ap.add_argument("--log_dir", type=str, default=None)
     ap.set_defaults(**defaults)
@@ -225,11 +227,21 @@ def run_exp(args):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
         steps_per_epoch = int(t.item())
     t0 = time.time()
+    pack_k = max(int(getattr(args, "pack", 1)), 1)
+    if pack_k > 1 and args.loss != "balanced":
+        raise ValueError("--pack > 1 trains with the per-LP balanced loss (losses.balanced_packed)")
+    pending = []
     for epoch in range(args.epochs):
         model.train()
         for it, batch in enumerate(loader):
             if it >= steps_per_epoch:
                 break
+            if pack_k > 1 and hasattr(batch, "x_s"):
+                # mini-batches of LP graphs: `pack` consecutive LPs form one block-diagonal graph and ONE optimiser step
+                pending.append(batch)
+                if len(pending) < pack_k and it + 1 < steps_per_epoch:
+                    continue
+                batch, pending = pack_bipartite(pending), []
             if hasattr(batch, "x_s"):                # already bipartite: one whole LP per step (train.py:103-104)
                 sub_loader = [batch]
             elif batch.edge_index.shape[-1] == 0:    # train.py:106 skips empty graphs
@@ -253,7 +265,10 @@ def run_exp(args):
                 logit_cons, logit_vars = model(batch)
                 logit_cons, logit_vars = logit_cons[:batch.s_bs], logit_vars[:batch.t_bs]
                 y_s, y_t = batch.y_s[:batch.s_bs], batch.y_t[:batch.t_bs]
-                loss = loss_fn(logit_cons, logit_vars, y_s, y_t)
+                if hasattr(batch, "cons_ptr"):       # a pack: per-LP class weights, mean over the pack's LPs
+                    loss = balanced_packed(logit_cons, logit_vars, y_s, y_t, batch.cons_ptr, batch.vars_ptr)
+                else:
+                    loss = loss_fn(logit_cons, logit_vars, y_s, y_t)
                 opt.zero_grad()
                 loss.backward()
                 allreduce_gradients(params, world)
@@ -263,8 +278,10 @@ def run_exp(args):
                     assert not np.isnan(lv)              # train.py:126
                     # train.py:131-137 (acc_meter): the reference scores every step; here on the logged steps only,
                     # since accuracy() ends in a host read
-                    acc = float(accuracy(torch.cat((logit_cons, logit_vars), dim=0).detach(),
-                                         torch.cat((y_s, y_t), dim=0), logit_cons.shape[0]))
+                    m0, n0 = (batch.lp_sizes[0][0], batch.lp_sizes[1][0]) if hasattr(batch, "lp_sizes") else \
+                        (logit_cons.shape[0], logit_vars.shape[0])         # a pack is scored on its first LP
+                    acc = float(accuracy(torch.cat((logit_cons[:m0], logit_vars[:n0]), dim=0).detach(),
+                                         torch.cat((y_s[:m0], y_t[:n0]), dim=0), m0))
                     history.append(dict(epoch=epoch, step=glstep, loss=lv, acc=acc, lr=scheduler.get_last_lr()[0]))
                     if rank == 0:
                         logging.info(f"{epoch} {it}/{steps_per_epoch} step {glstep} loss {lv:.4f}")

@@ -120,6 +120,48 @@ def test_pred_basis_handles_lps_above_edge_num_thresh(cuda, dataset_root, tmp_pa
             assert got.shape == full.shape and np.mean(got == full) >= 0.995, (tag, f, np.mean(got == full))
 
 
+def test_packed_training_step_equals_the_average_of_per_lp_steps(cuda, dataset_root):
+    """Mini-batches of LP graphs (train.py --pack): the gradient of one packed step (block-diagonal graph, per-LP balanced
+    loss, mean over the pack) equals the average of the gradients of the single-LP steps, and train.run_exp trains with it."""
+    from lpgnn_b200 import arch, dataset, losses, train
+    ds = dataset.LPDataset(dataset_root, dataset.MyToBipartite())
+    batches = [ds[i] for i in range(4)]
+    torch.manual_seed(5)
+    model = arch.GCN_FC(8, 8, hids=64, depth=3, dp=0.0).to(cuda).train()
+    params = list(model.parameters())
+
+    def grads_of(loss):
+        for p in params:
+            p.grad = None
+        loss.backward()
+        return [p.grad.detach().clone() for p in params]
+
+    singles = []
+    for i in range(4):
+        b = ds[i].to(cuda)
+        lc, lv = model(b)
+        singles.append(grads_of(losses.balanced(lc, lv, b.y_s, b.y_t)))
+    pack = dataset.pack_bipartite(batches).to(cuda)
+    assert pack.n_lps == 4 and pack.cons_ptr.dtype == torch.int32 and int(pack.cons_ptr[-1]) == pack.x_s.shape[0]
+    pack.edge_index.check()
+    lc, lv = model(pack)
+    gp = grads_of(losses.balanced_packed(lc, lv, pack.y_s, pack.y_t, pack.cons_ptr, pack.vars_ptr))
+    for k, g in enumerate(gp):
+        mean = sum(s[k] for s in singles) / 4
+        assert float((g - mean).abs().max()) <= 2e-4 * max(1e-6, float(mean.abs().max())), k
+
+
+def test_train_entry_point_with_packs(cuda, dataset_root, tmp_path):
+    from lpgnn_b200 import train
+    log_dir = str(tmp_path / "run_pack") + "/"
+    args = train.parse_args([], arch="GCN_FC(8,8,hids=64,depth=3)", epochs=6, lr=2e-3, loss="balanced", pack=2,
+                            dataset_processed_prefix=dataset_root, log_dir=log_dir, num_workers=0, log_every=1)
+    model, history = train.run_exp(args)
+    assert os.path.exists(log_dir + "mdl.pth") and len(history) >= 12            # 5 training LPs -> 3 packs per epoch
+    assert all(np.isfinite(h["loss"]) and 0.0 <= h["acc"] <= 1.0 for h in history)
+    assert np.mean([h["loss"] for h in history[-4:]]) < np.mean([h["loss"] for h in history[:4]])
+
+
 def test_val_inference_gnn_and_accuracy_accept_cpu_logits(cuda):
     """pred_basis.py:81-85 and train.py:132-137 hand CPU / detached logits to inference_gnn / accuracy."""
     import lpgnn_b200  # noqa: F401

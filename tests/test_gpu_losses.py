@@ -90,3 +90,28 @@ def test_accuracy_counters_match_sklearn_on_the_reference_formula(cuda, m, n, se
     assert val.accuracy(logits, gt, m, dataset_name=name) == acc                      # CPU-resident inputs, scalar form
     counts = val.accuracy_counts(logits.to(cuda), gt.to(cuda), m)
     assert counts.is_cuda and counts.dtype == torch.int32 and counts.shape == (12,)
+
+
+@pytest.mark.parametrize("sizes", [[(7, 9)], [(300, 700), (1, 5), (257, 64)], [(1000, 2000)] * 5 + [(64, 3)]])
+def test_packed_balanced_loss_is_the_mean_of_the_per_lp_losses(cuda, sizes):
+    """losses.balanced_packed (one CTA per LP and side, per-LP class weights) vs the framework spelling: value, gradients,
+    bit-reproducibility."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import losses
+    parts = [_case(m, n, 10 * i + m, cuda, (0, 1, 2) if i % 2 else (1, 2), (0, 1, 2)) for i, (m, n) in enumerate(sizes)]
+    lc, lv = torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+    ys, yt = torch.cat([p[2] for p in parts]), torch.cat([p[3] for p in parts])
+    cptr = torch.tensor(np.concatenate([[0], np.cumsum([m for m, _ in sizes])]), dtype=torch.int32)
+    vptr = torch.tensor(np.concatenate([[0], np.cumsum([n for _, n in sizes])]), dtype=torch.int32)
+
+    def run(dev):
+        a, b = lc.clone().to(dev).requires_grad_(), lv.clone().to(dev).requires_grad_()
+        loss = losses.balanced_packed(a, b, ys.to(dev), yt.to(dev), cptr.to(dev), vptr.to(dev))
+        (loss * 1.3).backward()
+        return float(loss.detach()), a.grad.cpu(), b.grad.cpu()
+
+    ref, got, again = run("cpu"), run(cuda), run(cuda)
+    assert abs(ref[0] - got[0]) <= 2e-6 * max(1.0, abs(ref[0])), (ref[0], got[0])
+    for r, g in ((ref[1], got[1]), (ref[2], got[2])):
+        assert torch.allclose(r, g, rtol=2e-5, atol=1e-9 + 2e-6 * float(r.abs().max()))
+    assert got[0] == again[0] and torch.equal(got[1], again[1]) and torch.equal(got[2], again[2])
