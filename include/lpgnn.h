@@ -254,7 +254,8 @@ LPGNN_API int lpgnn_node_transform_split(int parts, const void* const* A1, int32
  * of x2 [rows,K2]; x2 may be NULL with K2 = 0) as two IEEE-half rows and a power-of-two scale:
  *     x[i,k] = scale[i] * ( hi[i,k] + 2^-11 * lo[i,k] )      (22 significant bits, no overflow for any fp32 row)
  * lpgnn_node_transform_x2 computes out = epi( A1 W1^T + A2 W2^T + bias ) from such operands (activations with row
- * scales `rowscale` [M], weights with output-feature scales `colscale` [N]; NULL = 1) as THREE half x half -> fp32
+ * scales `rowscale` [M] for A1 and `rowscale2` [M] for A2 -- NULL = the same array as A1's, for operands split together --,
+ * weights with output-feature scales `colscale` [N] shared by W1 and W2; NULL = 1) as THREE half x half -> fp32
  * tcgen05 passes (hi*hi + 2^-11 (hi*lo + lo*hi)); a TMEM accumulator only holds a short chunk of the reduction and
  * the chunks are summed in fp32 registers with round-to-nearest, so the tensor core's truncating accumulation does
  * not drift (csrc/gemm_x2.cu).  out: f32 [M,N] or NULL; head_w [3,N] / head_partial [nparts][M][3] (optional, as
@@ -264,9 +265,25 @@ LPGNN_API int lpgnn_split_x2(const float* x1, int32_t K1, const float* x2, int32
                    void* hi1, void* lo1, void* hi2, void* lo2, float* scale, lpgnn_stream_t stream);
 LPGNN_API int lpgnn_node_transform_x2(const void* A1_hi, const void* A1_lo, int32_t K1, const void* W1_hi, const void* W1_lo,
                             const void* A2_hi, const void* A2_lo, int32_t K2, const void* W2_hi, const void* W2_lo,
-                            const float* rowscale, const float* colscale, const float* bias, int32_t M, int32_t N,
-                            float* out, int epilogue, const float* head_w, float* head_partial,
+                            const float* rowscale, const float* rowscale2, const float* colscale, const float* bias,
+                            int32_t M, int32_t N, float* out, int epilogue, const float* head_w, float* head_partial,
                             lpgnn_stream_t stream);
+/* Producers that write x2 operands directly (no lpgnn_split_x2 pass over their fp32 output).  Both take their row scale
+ * from an A-PRIORI bound instead of the row maximum -- any power of two s with |x[r,:]| <= s * 2^13 keeps the 22 bits --:
+ *   lpgnn_conv_in_fused_x2   lpgnn_conv_in_fused (fp32 input layer, reference arch.py:170, 75-80, 181-182) that also emits
+ *                            hi / lo [rows,N] and scale [rows] with |out[r,:]| <= scale[r] * 2^12 (bound: sum_k |z[r,k]| *
+ *                            max_c |W[c,k]| + max |b|); wabs: float scratch [65]
+ *   lpgnn_spmm_x2            lpgnn_spmm over fp32 features whose result is ONLY written as hi / lo [rows,F] + scale [rows]
+ *                            (bound: sum_e |val[e]| * src_scale[idx[e]] * 2^12 with src_scale as written by the call
+ *                            above); shapes too small for the banded sweep go through lpgnn_spmm into `scratch`
+ *                            (fp32 [rows,F]) + lpgnn_split_x2 -- same outputs. */
+LPGNN_API int lpgnn_conv_in_fused_x2(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,
+                           const float* Xsrc, int32_t k_src, const float* Xdst, int32_t k_dst, const float* W_rel,
+                           const float* b_rel, const float* W_root, int32_t N, float* out, int epilogue, float* z_cat,
+                           void* hi, void* lo, float* scale, float* wabs, lpgnn_stream_t stream);
+LPGNN_API int lpgnn_spmm_x2(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const float* X,
+                  int32_t F, const float* src_scale, void* hi, void* lo, float* scale, float* scratch,
+                  lpgnn_stream_t stream);
 /* Tuning knob (process-wide): K-blocks of 64 accumulated inside TMEM before a chunk is added to the fp32 registers
  * (main passes; default 4; the 2^-11-weighted correction passes use 4x that, at least 16).  Returns the previous value. */
 LPGNN_API int lpgnn_set_x2_chunk(int kblocks);

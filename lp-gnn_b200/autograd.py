@@ -57,24 +57,32 @@ def use_x2(conv) -> bool:
         and not getattr(conv, "fp32_cuda_cores", False)
 
 
-def _conv_hidden_x2(conv, left, right, csr, csc, relu, heads=None):
+def _conv_hidden_x2(conv, left, right, csr, csc, relu, heads=None, pre=None):
     """One hidden layer in the fp32 tensor-core mode.  ``heads = ((w, b, feas)_left, (w, b, feas)_right)`` fuses the
-    basis-status heads (last layer): returns the logits instead of the activations."""
+    basis-status heads (last layer): returns the logits instead of the activations.  ``pre = ((parts, scale)_left,
+    (parts, scale)_right)``: the inputs already exist as x2 operands (written by the input layer), so the aggregation
+    writes x2 operands directly and no split pass runs."""
     l2r, r2l = conv.left2right, conv.right2left
-    agg_t = ops.spmm(csc, left)     # [n,H]  A^T . left
-    agg_s = ops.spmm(csr, right)    # [m,H]  A   . right
-    at, xt, st = ops.split_x2(agg_t, right)
-    as_, xs, ss = ops.split_x2(agg_s, left)
+    if pre is not None:
+        (xs, sxs), (xt, sxt) = pre
+        at, st = ops.spmm_x2(csc, left, sxs)      # [n,H]  A^T . left   (sources: constraint rows, scales sxs)
+        as_, ss = ops.spmm_x2(csr, right, sxt)    # [m,H]  A   . right
+    else:
+        agg_t = ops.spmm(csc, left)     # [n,H]  A^T . left
+        agg_s = ops.spmm(csr, right)    # [m,H]  A   . right
+        at, xt, st = ops.split_x2(agg_t, right)
+        as_, xs, ss = ops.split_x2(agg_s, left)
+        sxt = sxs = None                # operands split together share their row scale
     wrel_t, wroot_t, cs_t = x2_weights_cached(conv._cache, l2r)
     wrel_s, wroot_s, cs_s = x2_weights_cached(conv._cache, r2l)
     if heads is not None:
         _, logit_t = ops.node_transform_x2(at, wrel_t, xt, wroot_t, st, cs_t, l2r.lin_rel.bias.detach(), relu=relu,
-                                           head=heads[1], want_out=False)
+                                           head=heads[1], want_out=False, rowscale2=sxt)
         _, logit_s = ops.node_transform_x2(as_, wrel_s, xs, wroot_s, ss, cs_s, r2l.lin_rel.bias.detach(), relu=relu,
-                                           head=heads[0], want_out=False)
+                                           head=heads[0], want_out=False, rowscale2=sxs)
         return logit_s, logit_t
-    right_new = ops.node_transform_x2(at, wrel_t, xt, wroot_t, st, cs_t, l2r.lin_rel.bias.detach(), relu=relu)
-    left_new = ops.node_transform_x2(as_, wrel_s, xs, wroot_s, ss, cs_s, r2l.lin_rel.bias.detach(), relu=relu)
+    right_new = ops.node_transform_x2(at, wrel_t, xt, wroot_t, st, cs_t, l2r.lin_rel.bias.detach(), relu=relu, rowscale2=sxt)
+    left_new = ops.node_transform_x2(as_, wrel_s, xs, wroot_s, ss, cs_s, r2l.lin_rel.bias.detach(), relu=relu, rowscale2=sxs)
     return left_new, right_new
 
 
@@ -165,8 +173,19 @@ def gcn_fc_forward(model, x_s, x_t, graph):
         from .training import gcn_fc_train
         return gcn_fc_train(model, x_s, x_t, csr, csc)
     dt = _act_dtype(model)
-    left, right = _conv_in_infer(model.conv1, x_s, x_t, csr, csc, dt, relu=True)
     n_layers = len(model.layers)
+    pre = None
+    if dt == torch.float32 and n_layers and use_x2(model.layers[0]):
+        # fp32 on the tensor cores: the input layer writes its output as fp32 (gather source of the aggregation) AND as x2
+        # operands (lin_root side of the first hidden transform)
+        l2r, r2l = model.conv1.left2right, model.conv1.right2left
+        right, p_t, s_t = ops.conv_in_fused_x2(csc, x_s, x_t, l2r.lin_rel.weight.detach(), l2r.lin_rel.bias.detach(),
+                                               l2r.lin_root.weight.detach(), relu=True)
+        left, p_s, s_s = ops.conv_in_fused_x2(csr, x_t, x_s, r2l.lin_rel.weight.detach(), r2l.lin_rel.bias.detach(),
+                                              r2l.lin_root.weight.detach(), relu=True)
+        pre = ((p_s, s_s), (p_t, s_t))
+    else:
+        left, right = _conv_in_infer(model.conv1, x_s, x_t, csr, csc, dt, relu=True)
     for li, conv in enumerate(model.layers):
         # eval mode: dropout is the identity; relu is fused into the transform epilogue
         if li == n_layers - 1 and dt in _HALF_TYPES:
@@ -184,7 +203,10 @@ def gcn_fc_forward(model, x_s, x_t, graph):
         if li == n_layers - 1 and dt == torch.float32 and use_x2(conv):
             heads = ((model.lin_left.weight.detach(), model.lin_left.bias.detach(), x_s),
                      (model.lin_right.weight.detach(), model.lin_right.bias.detach(), x_t))
-            return _conv_hidden_x2(conv, left, right, csr, csc, True, heads=heads)
+            return _conv_hidden_x2(conv, left, right, csr, csc, True, heads=heads, pre=pre if li == 0 else None)
+        if li == 0 and pre is not None:
+            left, right = _conv_hidden_x2(conv, left, right, csr, csc, True, pre=pre)
+            continue
         left, right = _conv_hidden_infer(conv, left, right, csr, csc, relu=True)
     logit_s, _ = ops.head_mask(left, model.lin_left.weight.detach(), model.lin_left.bias.detach(), x_s)
     logit_t, _ = ops.head_mask(right, model.lin_right.weight.detach(), model.lin_right.bias.detach(), x_t)

@@ -162,6 +162,131 @@ small_k_transform_kernel(const float* __restrict__ z, int32_t rows, const float*
   }
 }
 
+// ---- fp32 input layer that ALSO emits its output in x2 form (operand of the fp32 tensor-core transform, gemm_x2.cu).
+// The row scale cannot wait for the row maximum (a row's columns are spread over blocks), and it does not have to: any
+// power of two s with |x[r,:]| <= s * 2^13 keeps the 22 significant bits (IEEE half has 2^-24 of absolute resolution
+// below that, i.e. 2^-37 of the bound), so an A-PRIORI bound serves:  |x[r,c]| <= sum_k |z[r,k]| * max_c |W[c,k]| + max_c |b|.
+// wabs_kernel: wabs[k] = max over output features of |Wcat[c][k]| (k < K), wabs[KT] = max |b|.
+template <int KT>
+__global__ void __launch_bounds__(kThreads)
+wabs_kernel(const float* __restrict__ W_rel, int k_src, const float* __restrict__ W_root, int k_dst, const float* __restrict__ b_rel,
+            int N, float* __restrict__ wabs) {
+  __shared__ float red[kThreads / 32][KT + 1];
+  float mx[KT + 1];
+#pragma unroll
+  for (int k = 0; k <= KT; ++k) mx[k] = 0.f;
+  for (int c = threadIdx.x; c < N; c += kThreads) {
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      float w = 0.f;
+      if (k < k_src) w = __ldg(W_rel + (int64_t)c * k_src + k);
+      else if (k < k_src + k_dst) w = __ldg(W_root + (int64_t)c * k_dst + (k - k_src));
+      mx[k] = fmaxf(mx[k], fabsf(w));
+    }
+    if (b_rel) mx[KT] = fmaxf(mx[KT], fabsf(__ldg(b_rel + c)));
+  }
+#pragma unroll
+  for (int k = 0; k <= KT; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = mx[k];
+  }
+  __syncthreads();
+  if (threadIdx.x <= KT) {
+    float v = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) v = fmaxf(v, red[w][threadIdx.x]);
+    wabs[threadIdx.x] = v;
+  }
+}
+
+// power-of-two scale s >= bound / 2^12 (one binade of margin over |x| <= s * 2^13 for the fp32 rounding of the bound)
+__device__ __forceinline__ float x2_scale_for_bound(float bound) {
+  int e = 12;
+  if (bound > 0.f && bound < __int_as_float(0x7f800000)) e = (int)((__float_as_uint(bound) >> 23) & 0xffu) - 127 + 1;
+  e = max(-100, min(e, 112));
+  return __int_as_float((uint32_t)(127 + e - 12) << 23);      // 2^(e-12): bound < 2^e  =>  |x| / s < 2^12
+}
+
+template <int KT>
+__global__ void __launch_bounds__(kThreads, KT <= 32 ? 2 : 1)
+small_k_transform_x2_kernel(const float* __restrict__ z, int32_t rows, const float* __restrict__ W_rel, int k_src,
+                            const float* __restrict__ W_root, int k_dst, const float* __restrict__ b_rel, int N,
+                            float* __restrict__ out, int relu, const float* __restrict__ wabs, __half* __restrict__ hi,
+                            __half* __restrict__ lo, float* __restrict__ scale) {
+  __shared__ __align__(16) float zs[kRows][KT];
+  __shared__ float down_s[kRows];
+  const int K = k_src + k_dst;
+  const int64_t row0 = (int64_t)blockIdx.x * kRows;
+  const int nrows = (int)min((int64_t)kRows, rows - row0);
+  {
+    const float4* src = reinterpret_cast<const float4*>(z + row0 * KT);
+    float4* dst = reinterpret_cast<float4*>(&zs[0][0]);
+    for (int i = threadIdx.x; i < nrows * KT / 4; i += kThreads) dst[i] = __ldg(src + i);
+  }
+  const int c = blockIdx.y * kColsPerBlock + 2 * threadIdx.x;
+  float2 w[KT];
+  float2 bias = make_float2(0.f, 0.f);
+  if (c < N) {
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      float a = 0.f, b = 0.f;
+      if (k < k_src) { a = __ldg(W_rel + (int64_t)c * k_src + k); b = __ldg(W_rel + (int64_t)(c + 1) * k_src + k); }
+      else if (k < K) { a = __ldg(W_root + (int64_t)c * k_dst + (k - k_src)); b = __ldg(W_root + (int64_t)(c + 1) * k_dst + (k - k_src)); }
+      w[k] = make_float2(a, b);
+    }
+    if (b_rel) bias = make_float2(__ldg(b_rel + c), __ldg(b_rel + c + 1));
+  }
+  __syncthreads();
+  if (threadIdx.x < nrows) {                 // the row's scale from the a-priori bound (every column block derives the same)
+    float bound = __ldg(wabs + KT);
+#pragma unroll
+    for (int k = 0; k < KT; ++k) bound = fmaf(fabsf(zs[threadIdx.x][k]), __ldg(wabs + k), bound);
+    const float s = x2_scale_for_bound(bound);
+    down_s[threadIdx.x] = 1.f / s;             // exact: a power of two
+    if (blockIdx.y == 0) scale[row0 + threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (c >= N) return;
+#pragma unroll 2
+  for (int r = 0; r < nrows; ++r) {
+    float2 acc = bias;
+#pragma unroll
+    for (int k4 = 0; k4 < KT; k4 += 4) {
+      const float4 zz = *reinterpret_cast<const float4*>(&zs[r][k4]);
+      acc = __ffma2_rn(make_float2(zz.x, zz.x), w[k4 + 0], acc);
+      acc = __ffma2_rn(make_float2(zz.y, zz.y), w[k4 + 1], acc);
+      acc = __ffma2_rn(make_float2(zz.z, zz.z), w[k4 + 2], acc);
+      acc = __ffma2_rn(make_float2(zz.w, zz.w), w[k4 + 3], acc);
+    }
+    if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); }
+    const int64_t o = (row0 + r) * N + c;
+    *reinterpret_cast<float2*>(out + o) = acc;
+    const float d = down_s[r];
+    const float sx = acc.x * d, sy = acc.y * d;
+    const __half hx = __float2half_rn(sx), hy = __float2half_rn(sy);
+    *reinterpret_cast<__half2*>(hi + o) = __halves2half2(hx, hy);
+    *reinterpret_cast<__half2*>(lo + o) = __halves2half2(__float2half_rn((sx - __half2float(hx)) * 2048.f),
+                                                        __float2half_rn((sy - __half2float(hy)) * 2048.f));
+  }
+}
+
+template <int KT>
+int launch_x2out(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const float* Xsrc, int k_src,
+                 const float* Xdst, int k_dst, const float* W_rel, const float* b_rel, const float* W_root, int N, float* out,
+                 int relu, float* z, void* hi, void* lo, float* scale, float* wabs, cudaStream_t st) {
+  LPGNN_REQUIRE(ceil_div(N, kColsPerBlock) <= 65535, "conv_in_fused_x2: N=%d exceeds the %d columns one launch covers", N,
+                65535 * kColsPerBlock);
+  wabs_kernel<KT><<<1, kThreads, 0, st>>>(W_rel, k_src, W_root, k_dst, b_rel, N, wabs);
+  gather_cat_kernel<KT, __nv_bfloat16><<<ceil_div((int64_t)rows * 8, kThreads), kThreads, 0, st>>>(
+      ptr, idx, val, rows, Xsrc, k_src, Xdst, k_dst, z, nullptr);
+  dim3 grid(ceil_div(rows, kRows), ceil_div(N, kColsPerBlock));
+  small_k_transform_x2_kernel<KT><<<grid, kThreads, 0, st>>>(z, rows, W_rel, k_src, W_root, k_dst, b_rel, N, out, relu, wabs,
+                                                           reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), scale);
+  LPGNN_LAUNCH_OK();
+  count_launches(3);
+  return LPGNN_OK;
+}
+
 template <int KT>
 int launch(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const float* Xsrc, int k_src,
            const float* Xdst, int k_dst, const float* W_rel, const float* b_rel, const float* W_root, int N,
@@ -244,4 +369,27 @@ extern "C" int lpgnn_conv_in_fused(const int32_t* ptr, const int32_t* idx, const
                       z_cat, st);
   return launch<64>(ptr, idx, val, rows, Xsrc, k_src, Xdst, k_dst, W_rel, b_rel, W_root, N, out, out_dtype, relu,
                     z_cat, st);
+}
+
+// conv_in_fused (fp32) that also writes its output as x2 operands: hi / lo IEEE-half [rows,N] and a power-of-two scale per row
+// with out[r,c] = scale[r] * (hi + 2^-11 lo) to 22 bits; scale comes from an a-priori bound (|out[r,:]| <= scale[r] * 2^12),
+// which is also what lpgnn_spmm_x2 needs to bound ITS rows.  wabs: float scratch [65].
+extern "C" int lpgnn_conv_in_fused_x2(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows,
+                                      const float* Xsrc, int32_t k_src, const float* Xdst, int32_t k_dst, const float* W_rel,
+                                      const float* b_rel, const float* W_root, int32_t N, float* out, int epilogue, float* z_cat,
+                                      void* hi, void* lo, float* scale, float* wabs, lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(rows >= 0 && N > 0 && N % 2 == 0, "conv_in_fused_x2: bad shape rows=%d N=%d (N must be even)", rows, N);
+  LPGNN_REQUIRE(k_src >= 1 && k_dst >= 0 && k_src + k_dst <= 64, "conv_in_fused_x2: k_src+k_dst=%d must be in [1,64]", k_src + k_dst);
+  if (rows == 0) return LPGNN_OK;
+  LPGNN_REQUIRE(ptr && Xsrc && W_rel && out && z_cat && hi && lo && scale && wabs && (k_dst == 0 || (Xdst && W_root)),
+                "conv_in_fused_x2: null pointer");
+  LPGNN_REQUIRE((uintptr_t)z_cat % 16 == 0 && (uintptr_t)out % 8 == 0 && (uintptr_t)hi % 4 == 0 && (uintptr_t)lo % 4 == 0,
+                "conv_in_fused_x2: misaligned pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int relu = (epilogue & LPGNN_EPI_RELU) ? 1 : 0;
+  const int KT = lpgnn_conv_in_zcat_width(k_src, k_dst);
+  if (KT == 16) return launch_x2out<16>(ptr, idx, val, rows, Xsrc, k_src, Xdst, k_dst, W_rel, b_rel, W_root, N, out, relu, z_cat, hi, lo, scale, wabs, st);
+  if (KT == 32) return launch_x2out<32>(ptr, idx, val, rows, Xsrc, k_src, Xdst, k_dst, W_rel, b_rel, W_root, N, out, relu, z_cat, hi, lo, scale, wabs, st);
+  return launch_x2out<64>(ptr, idx, val, rows, Xsrc, k_src, Xdst, k_dst, W_rel, b_rel, W_root, N, out, relu, z_cat, hi, lo, scale, wabs, st);
 }

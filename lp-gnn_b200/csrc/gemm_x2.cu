@@ -66,6 +66,7 @@ struct X2Segs {
   int kb_end[kMaxSegs];     // cumulative K-block count at the end of each segment
   int chunk_kb[kMaxSegs];   // K-blocks per TMEM chunk inside the segment
   float scale[kMaxSegs];    // weight of the segment's partial sums in the register accumulator (1 or 2^-11)
+  int rs_sel[kMaxSegs];     // which row-scale array the segment's A operand belongs to (0: rowscale, 1: rowscale2)
   int count;
 };
 
@@ -75,7 +76,7 @@ __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.
 template <int BN, int kCl, bool kHead>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_x2_kernel(const __grid_constant__ X2Segs segs, const float* __restrict__ bias, const float* __restrict__ rowscale,
-               const float* __restrict__ colscale, float* __restrict__ out, int M, int N, int relu,
+               const float* __restrict__ rowscale2, const float* __restrict__ colscale, float* __restrict__ out, int M, int N, int relu,
                const float* __restrict__ head_w /*[3,N]*/, float* __restrict__ head_partial /*[2N/BN][M][3]*/) {
   using C = Cfg<BN, kCl>;
   constexpr int NACC = BN / 2;                     // accumulator columns per epilogue thread
@@ -206,10 +207,15 @@ gemm_x2_kernel(const __grid_constant__ X2Segs segs, const float* __restrict__ bi
       float acc[NACC];
 #pragma unroll
       for (int j = 0; j < NACC; ++j) acc[j] = 0.f;
+      // this thread's row and the power-of-two scales of its two A operands (exact factors; rows past M contribute 0)
+      const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
+      const bool row_ok = row < M;
+      const float rs1 = row_ok ? (rowscale ? __ldg(rowscale + row) : 1.f) : 0.f;
+      const float rs2 = row_ok ? (rowscale2 ? __ldg(rowscale2 + row) : rs1) : 0.f;
       int seg_begin = 0;
       for (int sg = 0; sg < segs.count; ++sg) {
         const int seg_end = segs.kb_end[sg], ck = segs.chunk_kb[sg];
-        const float sc = segs.scale[sg];
+        const float sc = segs.scale[sg] * (segs.rs_sel[sg] ? rs2 : rs1);
         for (int cb = seg_begin; cb < seg_end; cb += ck, ++c) {
           const uint32_t buf = c & 1u;
           ptx::mbar_wait_quiet(&tmem_full[buf], (c >> 1) & 1u);
@@ -239,10 +245,7 @@ gemm_x2_kernel(const __grid_constant__ X2Segs segs, const float* __restrict__ bi
         seg_begin = seg_end;
       }
 
-      // out = epi( s_row * s_col * acc + bias ): the two scales are powers of two (exact)
-      const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
-      const bool row_ok = row < M;
-      const float rs = (row_ok && rowscale) ? __ldg(rowscale + row) : (row_ok ? 1.f : 0.f);
+      // out = epi( s_col * acc + bias ): the row scales rode in with the chunks, the column scale is a power of two (exact)
       const int col0 = hsel * NACC;
       float hd0 = 0.f, hd1 = 0.f, hd2 = 0.f;
       float* orow = out ? out + row * N + (int64_t)n_blk * BN + col0 : nullptr;
@@ -252,7 +255,7 @@ gemm_x2_kernel(const __grid_constant__ X2Segs segs, const float* __restrict__ bi
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int col = col0 + j4 + u;
-          float t = fmaf(acc[j4 + u] * rs, cs_s[col], bias_s[col]);
+          float t = fmaf(acc[j4 + u], cs_s[col], bias_s[col]);
           if (relu) t = fmaxf(t, 0.f);
           v[u] = t;
           if (kHead) {
@@ -281,8 +284,8 @@ gemm_x2_kernel(const __grid_constant__ X2Segs segs, const float* __restrict__ bi
 }
 
 template <int BN, int kCl, bool kHead>
-int launch_x2(const X2Segs& segs, const float* bias, const float* rowscale, const float* colscale, float* out, int M, int N,
-              int relu, const float* head_w, float* head_partial, cudaStream_t st) {
+int launch_x2(const X2Segs& segs, const float* bias, const float* rowscale, const float* rowscale2, const float* colscale, float* out,
+              int M, int N, int relu, const float* head_w, float* head_partial, cudaStream_t st) {
   using C = Cfg<BN, kCl>;
   auto kern = gemm_x2_kernel<BN, kCl, kHead>;
   static int max_clusters = -1;
@@ -309,7 +312,7 @@ int launch_x2(const X2Segs& segs, const float* bias, const float* rowscale, cons
   const int items = ceil_div(ceil_div(M, BM), kCl) * (N / BN);
   const int clusters = items < max_clusters ? items : max_clusters;
   cfg.gridDim = dim3(kCl * clusters);
-  LPGNN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, segs, bias, rowscale, colscale, out, M, N, relu, head_w, head_partial));
+  LPGNN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, segs, bias, rowscale, rowscale2, colscale, out, M, N, relu, head_w, head_partial));
   count_launches(1);
   return LPGNN_OK;
 }
@@ -389,8 +392,8 @@ extern "C" int lpgnn_split_x2(const float* x1, int32_t K1, const float* x2, int3
 
 extern "C" int lpgnn_node_transform_x2(const void* A1_hi, const void* A1_lo, int32_t K1, const void* W1_hi, const void* W1_lo,
                                        const void* A2_hi, const void* A2_lo, int32_t K2, const void* W2_hi, const void* W2_lo,
-                                       const float* rowscale, const float* colscale, const float* bias, int32_t M, int32_t N,
-                                       float* out, int epilogue, const float* head_w, float* head_partial,
+                                       const float* rowscale, const float* rowscale2, const float* colscale, const float* bias,
+                                       int32_t M, int32_t N, float* out, int epilogue, const float* head_w, float* head_partial,
                                        lpgnn_stream_t stream) {
   if (int rc = check_device()) return rc;
   LPGNN_REQUIRE(M >= 0 && N > 0 && N % 64 == 0 && K1 > 0 && K1 % BK == 0 && K2 >= 0 && K2 % BK == 0,
@@ -409,31 +412,31 @@ extern "C" int lpgnn_node_transform_x2(const void* A1_hi, const void* A1_lo, int
   // segment order: the correction passes (weight 2^-11) first, then the main passes
   X2Segs segs;
   int n = 0, kb = 0;
-  auto add = [&](const void* a, const void* w, int K, float scale, int chunk) -> int {
+  auto add = [&](const void* a, const void* w, int K, float scale, int chunk, int rs_sel) -> int {
     if (int rc = make_map_16bit(&segs.a[n], a, M, K, K, BM, true, "node_transform_x2")) return rc;
     if (int rc = make_map_16bit(&segs.w[n], w, N, K, K, pair ? BN / 2 : BN, true, "node_transform_x2")) return rc;
     kb += K / BK;
-    segs.kb_end[n] = kb; segs.chunk_kb[n] = chunk; segs.scale[n] = scale;
+    segs.kb_end[n] = kb; segs.chunk_kb[n] = chunk; segs.scale[n] = scale; segs.rs_sel[n] = rs_sel;
     ++n;
     return LPGNN_OK;
   };
   const float corr = 1.f / 2048.f;
   const int cm = g_x2_chunk_kb, cc = g_x2_corr_chunk_kb;
-  if (int rc = add(A1_hi, W1_lo, K1, corr, cc)) return rc;
-  if (int rc = add(A1_lo, W1_hi, K1, corr, cc)) return rc;
+  if (int rc = add(A1_hi, W1_lo, K1, corr, cc, 0)) return rc;
+  if (int rc = add(A1_lo, W1_hi, K1, corr, cc, 0)) return rc;
   if (K2) {
-    if (int rc = add(A2_hi, W2_lo, K2, corr, cc)) return rc;
-    if (int rc = add(A2_lo, W2_hi, K2, corr, cc)) return rc;
+    if (int rc = add(A2_hi, W2_lo, K2, corr, cc, 1)) return rc;
+    if (int rc = add(A2_lo, W2_hi, K2, corr, cc, 1)) return rc;
   }
-  if (int rc = add(A1_hi, W1_hi, K1, 1.f, cm)) return rc;
-  if (K2) if (int rc = add(A2_hi, W2_hi, K2, 1.f, cm)) return rc;
-  for (int i = n; i < kMaxSegs; ++i) { segs.a[i] = segs.a[0]; segs.w[i] = segs.w[0]; segs.kb_end[i] = kb; segs.chunk_kb[i] = 1; segs.scale[i] = 0.f; }
+  if (int rc = add(A1_hi, W1_hi, K1, 1.f, cm, 0)) return rc;
+  if (K2) if (int rc = add(A2_hi, W2_hi, K2, 1.f, cm, 1)) return rc;
+  for (int i = n; i < kMaxSegs; ++i) { segs.a[i] = segs.a[0]; segs.w[i] = segs.w[0]; segs.kb_end[i] = kb; segs.chunk_kb[i] = 1; segs.scale[i] = 0.f; segs.rs_sel[i] = 0; }
   segs.count = n;
   const int relu = (epilogue & LPGNN_EPI_RELU) ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
 #define LPGNN_X2_GO(BNV, CL)                                                                                          \
-  return head_w ? launch_x2<BNV, CL, true>(segs, bias, rowscale, colscale, out, M, N, relu, head_w, head_partial, st) \
-                : launch_x2<BNV, CL, false>(segs, bias, rowscale, colscale, out, M, N, relu, head_w, head_partial, st)
+  return head_w ? launch_x2<BNV, CL, true>(segs, bias, rowscale, rowscale2, colscale, out, M, N, relu, head_w, head_partial, st) \
+                : launch_x2<BNV, CL, false>(segs, bias, rowscale, rowscale2, colscale, out, M, N, relu, head_w, head_partial, st)
   if (pair) LPGNN_X2_GO(256, 2);
   if (BN == 256) LPGNN_X2_GO(256, 1);
   if (BN == 128) LPGNN_X2_GO(128, 1);

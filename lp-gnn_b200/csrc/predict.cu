@@ -39,7 +39,8 @@ struct Buffers {
   void *agg_s, *agg_t;       // [m,H], [n,H]
   // fp32 tensor-core mode: x2 operands (half hi / lo) of the aggregate and of the node's own features, row scales
   void *xa_hi[2], *xa_lo[2], *xx_hi[2], *xx_lo[2];   // [0] = constraint side [m,H], [1] = variable side [n,H]
-  float* xscale[2];
+  float *xscale[2], *xscale_x[2];                     // row scales of the aggregate (or of both, split together) / of x
+  float* wabs;
   float *part_s, *part_t;    // fused-head partials
   float *logit_s, *logit_t;  // [m,3], [n,3]
   void* sel_ws; size_t sel_ws_bytes;
@@ -83,7 +84,9 @@ size_t carve(Bump& b, Buffers& B, int64_t z, int32_t m, int32_t n, int32_t p, in
     B.xa_hi[i] = on ? b.take<char>(rows * H * 2) : nullptr; B.xa_lo[i] = on ? b.take<char>(rows * H * 2) : nullptr;
     B.xx_hi[i] = on ? b.take<char>(rows * H * 2) : nullptr; B.xx_lo[i] = on ? b.take<char>(rows * H * 2) : nullptr;
     B.xscale[i] = on ? b.take<float>(rows) : nullptr;
+    B.xscale_x[i] = on ? b.take<float>(rows) : nullptr;
   }
+  B.wabs = b.take<float>(2 * 80);
   const int nparts = lpgnn_node_transform_head_parts(H);
   B.part_s = b.take<float>((size_t)nparts * m * 3); B.part_t = b.take<float>((size_t)nparts * n * 3);
   B.logit_s = b.take<float>((size_t)m * 3); B.logit_t = b.take<float>((size_t)n * 3);
@@ -153,6 +156,13 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
                                    LPGNN_EPI_RELU, stream));
     LPGNN_TRY(lpgnn_node_transform(B.zb_s, 64, w->c1_r2l_wcat, nullptr, 0, nullptr, w->c1_r2l_b, m, H, left, dt, dt,
                                    LPGNN_EPI_RELU, stream));
+  } else if (x2) {   // fp32 input layer that also emits its output as x2 operands (lin_root side of the first hidden layer)
+    LPGNN_TRY(lpgnn_conv_in_fused_x2(B.colptr, B.row_csc, B.val_csc, n, x_s, p, x_t, q, w->c1_l2r_wrel, w->c1_l2r_b,
+                                     w->c1_l2r_wroot, H, (float*)right, LPGNN_EPI_RELU, B.z_t, B.xx_hi[1], B.xx_lo[1],
+                                     B.xscale_x[1], B.wabs, stream));
+    LPGNN_TRY(lpgnn_conv_in_fused_x2(B.rowptr, B.col, B.val, m, x_t, q, x_s, p, w->c1_r2l_wrel, w->c1_r2l_b,
+                                     w->c1_r2l_wroot, H, (float*)left, LPGNN_EPI_RELU, B.z_s, B.xx_hi[0], B.xx_lo[0],
+                                     B.xscale_x[0], B.wabs + 80, stream));
   } else {
     LPGNN_TRY(lpgnn_conv_in_fused(B.colptr, B.row_csc, B.val_csc, n, x_s, p, x_t, q, w->c1_l2r_wrel, w->c1_l2r_b,
                                   w->c1_l2r_wroot, H, right, dt, LPGNN_EPI_RELU, B.z_t, stream));
@@ -164,8 +174,16 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
   bool head_done = false;
   int cur = 0;
   for (int li = 0; li < n_hidden; ++li) {
-    LPGNN_TRY(lpgnn_spmm(B.colptr, B.row_csc, B.val_csc, n, left, B.agg_t, H, dt, stream));    // A^T . left
-    LPGNN_TRY(lpgnn_spmm(B.rowptr, B.col, B.val, m, right, B.agg_s, H, dt, stream));           // A   . right
+    const bool x2_direct = x2 && li == 0;    // first hidden layer: its inputs (conv1 outputs) already exist as x2 operands
+    if (x2_direct) {   // aggregate straight into x2 operands (scale from the sources' scales), no fp32 aggregate, no split pass
+      LPGNN_TRY(lpgnn_spmm_x2(B.colptr, B.row_csc, B.val_csc, n, (const float*)left, H, B.xscale_x[0], B.xa_hi[1], B.xa_lo[1],
+                              B.xscale[1], (float*)B.agg_t, stream));                          // A^T . left
+      LPGNN_TRY(lpgnn_spmm_x2(B.rowptr, B.col, B.val, m, (const float*)right, H, B.xscale_x[1], B.xa_hi[0], B.xa_lo[0],
+                              B.xscale[0], (float*)B.agg_s, stream));                          // A   . right
+    } else {
+      LPGNN_TRY(lpgnn_spmm(B.colptr, B.row_csc, B.val_csc, n, left, B.agg_t, H, dt, stream));    // A^T . left
+      LPGNN_TRY(lpgnn_spmm(B.rowptr, B.col, B.val, m, right, B.agg_s, H, dt, stream));           // A   . right
+    }
     const bool last = li == n_hidden - 1;
     if (last && bf16) {  // head fused into the epilogue; the last activation never reaches HBM
       LPGNN_TRY(lpgnn_node_transform_head_ex(B.agg_t, H, w->l2r_wrel[li], right, H, w->l2r_wroot[li], w->l2r_b[li], n, H,
@@ -177,17 +195,21 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
       LPGNN_TRY(lpgnn_head_finish(B.part_s, nparts, m, w->head_left_b, x_s, p, B.logit_s, stream));
       head_done = true;
     } else if (x2) {  // the reference's default precision on the tensor cores: three half x half passes over x2 operands
-      LPGNN_TRY(lpgnn_split_x2((const float*)B.agg_s, H, (const float*)left, H, m, B.xa_hi[0], B.xa_lo[0], B.xx_hi[0],
-                               B.xx_lo[0], B.xscale[0], stream));
-      LPGNN_TRY(lpgnn_split_x2((const float*)B.agg_t, H, (const float*)right, H, n, B.xa_hi[1], B.xa_lo[1], B.xx_hi[1],
-                               B.xx_lo[1], B.xscale[1], stream));
+      if (!x2_direct) {   // deeper layers: inputs are fp32 outputs of the previous transform -> split them (shared row scale)
+        LPGNN_TRY(lpgnn_split_x2((const float*)B.agg_s, H, (const float*)left, H, m, B.xa_hi[0], B.xa_lo[0], B.xx_hi[0],
+                                 B.xx_lo[0], B.xscale[0], stream));
+        LPGNN_TRY(lpgnn_split_x2((const float*)B.agg_t, H, (const float*)right, H, n, B.xa_hi[1], B.xa_lo[1], B.xx_hi[1],
+                                 B.xx_lo[1], B.xscale[1], stream));
+      }
+      const float* rsx_t = x2_direct ? B.xscale_x[1] : nullptr;   // row scales of the lin_root operand (null: shared)
+      const float* rsx_s = x2_direct ? B.xscale_x[0] : nullptr;
       void *nl = last ? nullptr : B.act[cur ^ 1][0], *nr = last ? nullptr : B.act[cur ^ 1][1];
       LPGNN_TRY(lpgnn_node_transform_x2(B.xa_hi[1], B.xa_lo[1], H, w->l2r_wrel_hi[li], w->l2r_wrel_lo[li], B.xx_hi[1],
-                                        B.xx_lo[1], H, w->l2r_wroot_hi[li], w->l2r_wroot_lo[li], B.xscale[1],
+                                        B.xx_lo[1], H, w->l2r_wroot_hi[li], w->l2r_wroot_lo[li], B.xscale[1], rsx_t,
                                         w->l2r_wscale[li], w->l2r_b[li], n, H, (float*)nr, LPGNN_EPI_RELU,
                                         last ? w->head_right_w : nullptr, last ? B.part_t : nullptr, stream));
       LPGNN_TRY(lpgnn_node_transform_x2(B.xa_hi[0], B.xa_lo[0], H, w->r2l_wrel_hi[li], w->r2l_wrel_lo[li], B.xx_hi[0],
-                                        B.xx_lo[0], H, w->r2l_wroot_hi[li], w->r2l_wroot_lo[li], B.xscale[0],
+                                        B.xx_lo[0], H, w->r2l_wroot_hi[li], w->r2l_wroot_lo[li], B.xscale[0], rsx_s,
                                         w->r2l_wscale[li], w->r2l_b[li], m, H, (float*)nl, LPGNN_EPI_RELU,
                                         last ? w->head_left_w : nullptr, last ? B.part_s : nullptr, stream));
       if (last) {

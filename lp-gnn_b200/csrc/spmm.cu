@@ -194,11 +194,29 @@ template <> struct PairAcc<float> {
 constexpr int kSweepThreads = 1024;
 
 // Each lane owns CH 16-byte chunks (chunk c at lane*16 + c*512 bytes of the slab); a warp owns one row at a time.
-template <typename T, int CH, int U>
+// kX2 (fp32 features only): the aggregate is written as x2 operands of the fp32 tensor-core transform (gemm_x2.cu) instead
+// of fp32 -- IEEE-half hi / lo rows and one power-of-two scale per row -- so no separate split pass reads it back.  The
+// scale comes from a bound that is known when the row is: |Y[i,:]| <= sum_e |val[e]| * s_src[idx[e]] * 2^12, where
+// |X[j,:]| <= s_src[j] * 2^12 is the guarantee the producer of X gave (lpgnn_conv_in_fused_x2).
+struct X2Out {
+  const float* src_scale;   // [n_src]
+  char* hi;                 // [rows, F] half
+  char* lo;
+  float* scale;             // [rows]
+};
+
+__device__ __forceinline__ float x2_scale_for_bound(float bound) {   // as in conv_in.cu: bound < 2^e -> scale 2^(e-12)
+  int e = 12;
+  if (bound > 0.f && bound < __int_as_float(0x7f800000)) e = (int)((__float_as_uint(bound) >> 23) & 0xffu) - 127 + 1;
+  e = max(-100, min(e, 112));
+  return __int_as_float((uint32_t)(127 + e - 12) << 23);
+}
+
+template <typename T, int CH, int U, bool kX2 = false>
 __global__ void __launch_bounds__(kSweepThreads, 1)
 spmm_sweep_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ val,
                   int32_t rows, const char* __restrict__ X, char* __restrict__ Y, uint32_t row_bytes,
-                  int32_t nslabs, int32_t rows_per_block) {
+                  int32_t nslabs, int32_t rows_per_block, const X2Out x2) {
   constexpr int P = PairAcc<T>::kPairs;
   constexpr int kWarps = kSweepThreads / 32;
   constexpr uint32_t kFull = 0xffffffffu;
@@ -215,11 +233,16 @@ spmm_sweep_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ i
   if (row < r_end) { beg = __ldg(ptr + row); end = __ldg(ptr + row + 1); }
   if (row + kWarps < r_end) { nbeg = __ldg(ptr + row + kWarps); nend = __ldg(ptr + row + kWarps + 1); }
   if (beg + lane < end) { my_idx = __ldg(idx + beg + lane); my_val = __ldg(val + beg + lane); }
+  float my_sb = 0.f;            // kX2: this lane's share of the row bound, sum |val| * s_src[idx]
+  if (kX2 && beg + lane < end) my_sb = fabsf(my_val) * __ldg(x2.src_scale + my_idx);
 
   for (; row < r_end; row += kWarps) {
-    int32_t nnbeg = 0, nnend = 0, n_idx = 0; float n_val = 0.f;
+    int32_t nnbeg = 0, nnend = 0, n_idx = 0; float n_val = 0.f, n_sb = 0.f;
     if (row + 2 * kWarps < r_end) { nnbeg = __ldg(ptr + row + 2 * kWarps); nnend = __ldg(ptr + row + 2 * kWarps + 1); }
-    if (nbeg + lane < nend) { n_idx = __ldg(idx + nbeg + lane); n_val = __ldg(val + nbeg + lane); }
+    if (nbeg + lane < nend) {
+      n_idx = __ldg(idx + nbeg + lane); n_val = __ldg(val + nbeg + lane);
+      if (kX2) n_sb = fabsf(n_val) * __ldg(x2.src_scale + n_idx);
+    }
 
     float2 acc[CH][P];
 #pragma unroll
@@ -230,7 +253,10 @@ spmm_sweep_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ i
     for (int32_t e0 = beg; e0 < end; e0 += 32) {
       if (e0 != beg) {
         my_idx = 0; my_val = 0.f;
-        if (e0 + lane < end) { my_idx = __ldg(idx + e0 + lane); my_val = __ldg(val + e0 + lane); }
+        if (e0 + lane < end) {
+          my_idx = __ldg(idx + e0 + lane); my_val = __ldg(val + e0 + lane);
+          if (kX2) my_sb += fabsf(my_val) * __ldg(x2.src_scale + my_idx);
+        }
       }
       const int cnt = min(32, end - e0);
       int j = 0;
@@ -258,17 +284,42 @@ spmm_sweep_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ i
       if (U > 2 && j + 2 <= cnt) batch(std::integral_constant<int, 2>{});
       if (j < cnt) batch(std::integral_constant<int, 1>{});
     }
-    uint4* dst = reinterpret_cast<uint4*>(Y + (uint64_t)(uint32_t)row * row_bytes + col0);
+    if constexpr (kX2) {
+      static_assert(!kX2 || sizeof(T) == 4, "x2 output is the fp32 path");
 #pragma unroll
-    for (int c = 0; c < CH; ++c) __stcs(dst + c * 32, PairAcc<T>::pack(acc[c]));
+      for (int o = 16; o > 0; o >>= 1) my_sb += __shfl_xor_sync(kFull, my_sb, o);
+      const float sc = x2_scale_for_bound(my_sb * 4096.f);
+      const float down = 1.f / sc;                            // exact: a power of two
+      if (slab == 0 && lane == 0) x2.scale[row] = sc;
+      const uint64_t off = ((uint64_t)(uint32_t)row * row_bytes + col0) >> 1;     // same elements, 2 bytes each
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        float v[4] = {acc[c][0].x, acc[c][0].y, acc[c][1].x, acc[c][1].y};
+        __half h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float sx = v[k] * down;
+          h[k] = __float2half_rn(sx);
+          l[k] = __float2half_rn((sx - __half2float(h[k])) * 2048.f);
+        }
+        const __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
+        const __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
+        *reinterpret_cast<uint2*>(x2.hi + off + c * 256) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        *reinterpret_cast<uint2*>(x2.lo + off + c * 256) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+      }
+    } else {
+      uint4* dst = reinterpret_cast<uint4*>(Y + (uint64_t)(uint32_t)row * row_bytes + col0);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) __stcs(dst + c * 32, PairAcc<T>::pack(acc[c]));
+    }
     beg = nbeg; end = nend; nbeg = nnbeg; nend = nnend;
-    my_idx = n_idx; my_val = n_val;
+    my_idx = n_idx; my_val = n_val; my_sb = n_sb;
   }
 }
 
-template <typename T, int CH, int U>
+template <typename T, int CH, int U, bool kX2 = false>
 int launch_sweep(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const void* X, void* Y,
-                 int32_t chunks, cudaStream_t st) {
+                 int32_t chunks, cudaStream_t st, const X2Out x2 = X2Out()) {
   const int nslabs = chunks / (32 * CH);
   constexpr int kWarps = kSweepThreads / 32;
   const int want_blocks = max(1, sm_count() / nslabs);          // one CTA per SM, all co-resident
@@ -276,12 +327,12 @@ int launch_sweep(const int32_t* ptr, const int32_t* idx, const float* val, int32
   const int nblocks = ceil_div(rows, rows_per_block);
   static bool carved = false;      // no shared memory is used: ask for the whole 228 KB as L1 (it holds the band)
   if (!carved) {
-    cudaFuncSetAttribute(spmm_sweep_kernel<T, CH, U>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(spmm_sweep_kernel<T, CH, U, kX2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     carved = true;
   }
-  spmm_sweep_kernel<T, CH, U><<<nblocks * nslabs, kSweepThreads, 0, st>>>(
+  spmm_sweep_kernel<T, CH, U, kX2><<<nblocks * nslabs, kSweepThreads, 0, st>>>(
       ptr, idx, val, rows, reinterpret_cast<const char*>(X), reinterpret_cast<char*>(Y), (uint32_t)chunks * 16u, nslabs,
-      rows_per_block);
+      rows_per_block, x2);
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;
@@ -364,4 +415,28 @@ extern "C" int lpgnn_spmm_ex(const int32_t* ptr, const int32_t* idx, const float
 extern "C" int lpgnn_spmm(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const void* X,
                           void* Y, int32_t F, int dtype, lpgnn_stream_t stream) {
   return lpgnn_spmm_ex(ptr, idx, val, rows, X, Y, F, dtype, 0, 0, stream);
+}
+
+// (a2, fp32 tensor-core mode) Aggregation of fp32 features straight into x2 operands: hi / lo IEEE-half [rows,F] + a
+// power-of-two scale per row (lpgnn_split_x2's format; Y = scale * (hi + 2^-11 lo) to 22 bits) -- the fp32 aggregate never
+// reaches HBM and no split pass reads it back.  src_scale [n_src]: |X[j,:]| <= src_scale[j] * 2^12 (as written by
+// lpgnn_conv_in_fused_x2).  Graphs too small for the banded sweep take lpgnn_spmm into `scratch` (fp32 [rows,F]) followed by
+// lpgnn_split_x2: the same outputs either way (the scale then comes from the row maximum instead of the bound).
+extern "C" int lpgnn_spmm_x2(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const float* X, int32_t F,
+                             const float* src_scale, void* hi, void* lo, float* scale, float* scratch, lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(rows >= 0 && F > 0 && F % 4 == 0, "spmm_x2: bad shape rows=%d F=%d", rows, F);
+  if (rows == 0) return LPGNN_OK;
+  LPGNN_REQUIRE(ptr && X && src_scale && hi && lo && scale, "spmm_x2: null pointer");
+  LPGNN_REQUIRE((uintptr_t)X % 16 == 0 && (uintptr_t)hi % 8 == 0 && (uintptr_t)lo % 8 == 0, "spmm_x2: misaligned pointer");
+  const int row_bytes = F * 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (row_bytes % 1024 == 0 && (int64_t)rows * (row_bytes / 1024) >= (int64_t)sm_count() * 64) {
+    X2Out x2;
+    x2.src_scale = src_scale; x2.hi = reinterpret_cast<char*>(hi); x2.lo = reinterpret_cast<char*>(lo); x2.scale = scale;
+    return launch_sweep<float, 2, 4, true>(ptr, idx, val, rows, X, nullptr, row_bytes / 16, st, x2);
+  }
+  LPGNN_REQUIRE(scratch, "spmm_x2: this shape takes the two-step path and needs the fp32 scratch [rows,F]");
+  if (int rc = lpgnn_spmm(ptr, idx, val, rows, X, scratch, F, LPGNN_F32, stream)) return rc;
+  return lpgnn_split_x2(scratch, F, nullptr, 0, rows, hi, lo, nullptr, nullptr, scale, stream);
 }

@@ -231,9 +231,10 @@ def split_x2(x1, x2=None):
 
 
 def node_transform_x2(a1, w1, a2=None, w2=None, rowscale=None, colscale=None, bias=None, relu=False, head=None,
-                      want_out=True):
+                      want_out=True, rowscale2=None):
     """fp32-accurate ``epi(a1 w1^T + a2 w2^T + bias)`` on the tensor cores from x2 operands (``split_x2`` pairs
-    ``(hi, lo)``; three half x half passes, chunked accumulation: csrc/gemm_x2.cu).  ``head=(head_w, head_b, feas)``
+    ``(hi, lo)``; three half x half passes, chunked accumulation: csrc/gemm_x2.cu).  ``rowscale`` belongs to ``a1``,
+    ``rowscale2`` to ``a2`` (default: the same array, operands split together).  ``head=(head_w, head_b, feas)``
     fuses the basis-status head + knowledge masking of the last layer and returns ``(out | None, logits[M,3])``."""
     require_cuda(*a1, *w1, rowscale, colscale, bias)
     M, K1 = a1[0].shape
@@ -256,7 +257,8 @@ def node_transform_x2(a1, w1, a2=None, w2=None, rowscale=None, colscale=None, bi
         rc = lib.lpgnn_node_transform_x2(a1[0].data_ptr(), a1[1].data_ptr(), K1, w1[0].data_ptr(), w1[1].data_ptr(),
                                          ptr(a2[0]) if a2 else None, ptr(a2[1]) if a2 else None, K2,
                                          ptr(w2[0]) if w2 else None, ptr(w2[1]) if w2 else None, ptr(rowscale),
-                                         ptr(colscale), ptr(bias), M, N, ptr(out), EPI_RELU if relu else EPI_NONE,
+                                         ptr(rowscale2), ptr(colscale), ptr(bias), M, N, ptr(out),
+                                         EPI_RELU if relu else EPI_NONE,
                                          ptr(head_w), ptr(partial), stream_ptr())
         check(rc, "lpgnn_node_transform_x2")
         if head is None:
@@ -266,6 +268,49 @@ def node_transform_x2(a1, w1, a2=None, w2=None, rowscale=None, colscale=None, bi
                                    logits.data_ptr(), stream_ptr())
     check(rc, "lpgnn_head_finish")
     return out, logits
+
+
+def conv_in_fused_x2(view, x_src, x_dst, w_rel, b_rel, w_root, relu=True):
+    """fp32 input layer (``conv_in_fused``) that also emits its output as x2 operands.  Returns ``(out[rows,N] f32,
+    (hi, lo), scale[rows])`` with ``|out[r,:]| <= scale[r] * 2^12`` (scale from an a-priori bound, ``lpgnn_conv_in_fused_x2``)."""
+    ptr_, idx, val, rows = view
+    require_cuda(ptr_, x_src, x_dst, w_rel, w_root)
+    x_src, x_dst = _contig(x_src.float()), _contig(x_dst.float())
+    w_rel, w_root, b_rel = _contig(w_rel.float()), _contig(w_root.float()), _contig(b_rel.float())
+    N = w_rel.shape[0]
+    lib = _lib.load()
+    dev = x_src.device
+    kt = lib.lpgnn_conv_in_zcat_width(x_src.shape[1], x_dst.shape[1])
+    out = torch.empty((rows, N), dtype=torch.float32, device=dev)
+    z_cat = torch.empty((rows, kt), dtype=torch.float32, device=dev)
+    hi, lo = (torch.empty((rows, N), dtype=torch.float16, device=dev) for _ in range(2))
+    scale = torch.empty(rows, dtype=torch.float32, device=dev)
+    wabs = torch.empty(80, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.lpgnn_conv_in_fused_x2(ptr_.data_ptr(), idx.data_ptr(), val.data_ptr(), rows, x_src.data_ptr(), x_src.shape[1],
+                                        x_dst.data_ptr(), x_dst.shape[1], w_rel.data_ptr(), b_rel.data_ptr(), w_root.data_ptr(),
+                                        N, out.data_ptr(), EPI_RELU if relu else EPI_NONE, z_cat.data_ptr(), hi.data_ptr(),
+                                        lo.data_ptr(), scale.data_ptr(), wabs.data_ptr(), stream_ptr())
+    check(rc, "lpgnn_conv_in_fused_x2")
+    return out, (hi, lo), scale
+
+
+def spmm_x2(view, x, src_scale):
+    """Aggregation of fp32 features straight into x2 operands (``lpgnn_spmm_x2``): ``((hi, lo), scale[rows])`` with
+    ``A_view @ x = scale * (hi + 2^-11 lo)`` to 22 bits; ``src_scale[j]`` bounds source row j as ``conv_in_fused_x2`` reports."""
+    ptr_, idx, val, rows = view
+    require_cuda(ptr_, x, src_scale)
+    x, src_scale = _contig(x.float()), _contig(src_scale.float())
+    F = x.shape[1]
+    dev = x.device
+    hi, lo = (torch.empty((rows, F), dtype=torch.float16, device=dev) for _ in range(2))
+    scale = torch.empty(rows, dtype=torch.float32, device=dev)
+    scratch = torch.empty((rows, F), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().lpgnn_spmm_x2(ptr_.data_ptr(), idx.data_ptr(), val.data_ptr(), rows, x.data_ptr(), F, src_scale.data_ptr(),
+                                       hi.data_ptr(), lo.data_ptr(), scale.data_ptr(), scratch.data_ptr(), stream_ptr())
+    check(rc, "lpgnn_spmm_x2")
+    return (hi, lo), scale
 
 
 def set_x2_chunk(kblocks: int) -> int:

@@ -381,3 +381,38 @@ def test_conv_in_fused_above_the_old_grid_y_limit(cuda):
     for r in (0, 1, 65535 * 64 - 1, 65535 * 64, rows - 1):
         e = torch.relu((2.0 * x_src[r % 1000]) @ w_rel.T + b + x_dst[r] @ w_root.T)
         assert torch.allclose(out[r], e, rtol=1e-5, atol=1e-5), r
+
+
+@pytest.mark.parametrize("m,n,z,H", [(700, 1300, 6000, 64), (20_000, 40_000, 200_000, 1024), (129, 255, 0, 128)])
+def test_x2_producers_write_the_operands_directly(cuda, m, n, z, H):
+    """lpgnn_conv_in_fused_x2 / lpgnn_spmm_x2: the fp32 input layer and the aggregation emit x2 operands themselves (row
+    scale from an a-priori bound instead of the row maximum).  scale * (hi + 2^-11 lo) must reproduce the fp32 results to
+    22 bits relative to the row's magnitude, the scales are powers of two that bound their rows, and the banded-sweep and
+    two-step forms of spmm_x2 agree with the plain fp32 aggregation."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    from lpgnn_b200.graph import BipartiteCSR
+    row, col, val = make_graph_arrays(m, n, z, 5, sort=True)
+    g = BipartiteCSR.from_coo_arrays(row, col, val, m, n, cuda, is_sorted=True)
+    csr, csc = g.views()
+    gen = torch.Generator(device="cuda").manual_seed(H + m)
+    x_s, x_t = torch.randn(m, 8, device=cuda, generator=gen), torch.randn(n, 8, device=cuda, generator=gen) * 5
+    w_rel, w_root = torch.randn(H, 8, device=cuda, generator=gen) / 3, torch.randn(H, 8, device=cuda, generator=gen) / 3
+    b = torch.randn(H, device=cuda, generator=gen)
+    out, (hi, lo), sc = ops.conv_in_fused_x2(csc, x_s, x_t, w_rel, b, w_root, relu=True)
+    ref, _ = ops.conv_in_fused(csc, x_s, x_t, w_rel, b, w_root, torch.float32, relu=True)
+    assert torch.equal(out, ref)
+    mant = torch.frexp(sc)[0]
+    assert torch.equal(mant, torch.full_like(mant, 0.5))
+    assert bool((out.abs().amax(1) <= sc * 4096).all())                       # the guarantee spmm_x2 builds on
+    rec = sc.double()[:, None] * (hi.double() + lo.double() / 2048)
+    rowmax = out.abs().amax(1, keepdim=True).double().clamp_min(1e-30)
+    assert float(((rec - out.double()).abs() / rowmax).max()) < 2.0 ** -21
+    # aggregation of that output (constraint side: A . right) straight into x2 operands
+    (ahi, alo), asc = ops.spmm_x2(csr, out, sc)
+    agg = ops.spmm(csr, out)
+    arec = asc.double()[:, None] * (ahi.double() + alo.double() / 2048)
+    amax = agg.abs().amax(1, keepdim=True).double().clamp_min(1e-30)
+    assert torch.isfinite(ahi.float()).all() and torch.isfinite(alo.float()).all()
+    assert float(((arec - agg.double()).abs() / amax).max()) < 2.0 ** -19      # bound-based scale: a few bits of head room spent
+    assert bool((agg.abs().amax(1) <= asc * 4096).all())
