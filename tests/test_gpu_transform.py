@@ -415,4 +415,4 @@ def test_x2_producers_write_the_operands_directly(cuda, m, n, z, H):
     amax = agg.abs().amax(1, keepdim=True).double().clamp_min(1e-30)
     assert torch.isfinite(ahi.float()).all() and torch.isfinite(alo.float()).all()
     assert float(((arec - agg.double()).abs() / amax).max()) < 2.0 ** -19      # bound-based scale: a few bits of head room spent
-    assert bool((agg.abs().amax(1) <= asc * 4096).all())
+    assert bool((agg.abs().amax(1) <= asc * 8192).all())        # (two-step form: scale from the row maximum, [2^12, 2^13))
