@@ -669,6 +669,17 @@ def kernel_rooflines(model, lp, dev, peaks, bf16, args):
         add("conv_in_16 pair (input layer: gather + MMA + ReLU + store, both sides)", "hbm", t,
             (m + n) * H * s + 2 * (m + n) * 8 * 4 + 2 * z * 8 + (m + n + 2) * 4, 2)
         right, left = f_in(), f_in_s()
+    elif args.precision == "fp32" and len(model.layers):
+        # fp32 on the tensor cores: the input layer writes fp32 (gather source of the aggregation) + x2 operands (hi / lo halves)
+        f_in = lambda: ops.conv_in_fused_x2(csc, xs, xt, w(c1.left2right.lin_rel.weight), w(c1.left2right.lin_rel.bias),
+                                            w(c1.left2right.lin_root.weight), relu=True)
+        f_in_s = lambda: ops.conv_in_fused_x2(csr, xt, xs, w(c1.right2left.lin_rel.weight), w(c1.right2left.lin_rel.bias),
+                                              w(c1.right2left.lin_root.weight), relu=True)
+        t = time_kernel(f_in, reps, flush) + time_kernel(f_in_s, reps, flush)
+        add("conv_in_fused_x2 pair (gather + CUDA-core transform, fp32 + x2 outputs, both sides)", "hbm", t,
+            (m + n) * H * 8 + 2 * (m + n) * 8 * 4 + 2 * z * 8 + (m + n + 2) * 4, 6)
+        right, x2_t, sx_t = f_in()
+        left, x2_s, sx_s = f_in_s()
     else:
         f_in = lambda: ops.conv_in_fused(csc, xs, xt, w(c1.left2right.lin_rel.weight), w(c1.left2right.lin_rel.bias),
                                          w(c1.left2right.lin_root.weight), dt, relu=True)
@@ -681,9 +692,15 @@ def kernel_rooflines(model, lp, dev, peaks, bf16, args):
         conv = model.layers[-1]
         cast = conv._cache.get
         # SpMM pair of one hidden layer: compulsory bytes 2(m+n)Hs + 16z + 4(m+n+2)   
-        t_s = time_kernel(lambda: ops.spmm(csr, right), reps, flush)
-        t_t = time_kernel(lambda: ops.spmm(csc, left), reps, flush)
-        add("spmm pair (A.R and A^T.L)", "hbm", t_s + t_t, 2 * (m + n) * H * s + 16 * z + 4 * (m + n + 2), 2)
+        if args.precision == "fp32":   # fp32 features in, x2 operands out (same bytes per element: 2 + 2)
+            t_s = time_kernel(lambda: ops.spmm_x2(csr, right, sx_t), reps, flush)
+            t_t = time_kernel(lambda: ops.spmm_x2(csc, left, sx_s), reps, flush)
+            add("spmm_x2 pair (A.R and A^T.L, fp32 in, x2 operands out)", "hbm", t_s + t_t,
+                2 * (m + n) * H * s + 16 * z + 4 * (m + n + 2) + 8 * (m + n), 2)
+        else:
+            t_s = time_kernel(lambda: ops.spmm(csr, right), reps, flush)
+            t_t = time_kernel(lambda: ops.spmm(csc, left), reps, flush)
+            add("spmm pair (A.R and A^T.L)", "hbm", t_s + t_t, 2 * (m + n) * H * s + 16 * z + 4 * (m + n + 2), 2)
         kernels[-1]["gather_model_bytes"] = 2 * z * H * s + (m + n) * H * s + 16 * z
         agg_t, agg_s = ops.spmm(csc, left), ops.spmm(csr, right)
         l2r, r2l = conv.left2right, conv.right2left
@@ -700,17 +717,14 @@ def kernel_rooflines(model, lp, dev, peaks, bf16, args):
             add("node_transform pair, head fused (tcgen05) + head_finish", "tensor", t_g, 4 * (m + n) * H * H, 4)
         elif args.precision == "fp32":
             from lpgnn_b200.autograd import x2_weights_cached
-            t_sp = (time_kernel(lambda: ops.split_x2(agg_t, right), reps, flush)
-                    + time_kernel(lambda: ops.split_x2(agg_s, left), reps, flush))
-            add("split_x2 pair (fp32 -> half hi / lo + row scale)", "hbm", t_sp, 2 * (m + n) * H * 8 + 4 * (m + n), 2)
-            at, xt2, st_ = ops.split_x2(agg_t, right)
-            as_, xs2, ss_ = ops.split_x2(agg_s, left)
+            (at, st_), (as_, ss_) = ops.spmm_x2(csc, left, sx_s), ops.spmm_x2(csr, right, sx_t)
+            xt2, xs2 = x2_t, x2_s
             wr_t, wo_t, cs_t = x2_weights_cached(conv._cache, l2r)
             wr_s, wo_s, cs_s = x2_weights_cached(conv._cache, r2l)
             f_t = lambda: ops.node_transform_x2(at, wr_t, xt2, wo_t, st_, cs_t, w(l2r.lin_rel.bias), relu=True, head=hr,
-                                                want_out=False)
+                                                want_out=False, rowscale2=sx_t)
             f_s = lambda: ops.node_transform_x2(as_, wr_s, xs2, wo_s, ss_, cs_s, w(r2l.lin_rel.bias), relu=True, head=hl,
-                                                want_out=False)
+                                                want_out=False, rowscale2=sx_s)
             t_g = time_kernel(f_t, reps, flush) + time_kernel(f_s, reps, flush)
             # three half x half passes carry one fp32-accurate product: 3 x 4(m+n)H^2 tensor-core flops
             add("node_transform_x2 pair, head fused (tcgen05, 3 half passes) + head_finish", "tensor", t_g,
