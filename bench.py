@@ -466,7 +466,7 @@ def sweep_measure(args, rank, world, dev, lib, precision, steps, distinct, with_
     t_ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
     pipe = PackedBasisPipeline(model, dev) if args.sweep_pack else BasisPipeline(model, dev)
     seq = [hosts[i % len(hosts)] for i in range(steps)]
-    for _ in pipe.run(seq[:8]):
+    for _ in pipe.run(seq[:min(len(seq), 3 * len(hosts))]):      # warm-up: full-size packs, so the grow-only buffers exist
         pass
     barrier(world)
     torch.cuda.synchronize()
