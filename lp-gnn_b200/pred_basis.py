@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import json
 import logging
+import os
 import os.path as osp
 import time
 from concurrent.futures import ThreadPoolExecutor
@@ -58,6 +59,46 @@ def write_bas(fn, var_nms, con_nms, pred_var, pred_con):
     lines.append("ENDATA")
     with open(fn, "w") as f:
         f.writelines(lines)
+
+
+def read_bas_highs(fn):
+    """HiGHS basis file -> ``(con_status, var_status)`` int arrays (reference scripts/cvt_to_pkl.py:166-178)."""
+    assert os.path.exists(fn), fn
+    with open(fn, "r") as f:
+        lines = f.readlines()
+    var_stas = con_stas = None
+    for i, line in enumerate(lines):
+        if "Columns" in line:
+            var_stas = np.array(lines[i + 1].split(), "int")
+        if "Rows" in line:
+            con_stas = np.array(lines[i + 1].split(), "int")
+    return con_stas, var_stas
+
+
+def read_bas(fn, con_nms=None, var_nms=None):
+    """Basis file -> ``(con_labels, var_labels)`` in {0: at lower, 1: basic, 2: at upper} (reference
+    scripts/cvt_to_pkl.py:180-209; the reader behind ``val.validation_wrt_converged``).  Named (MPS-style) files: ``XL`` /
+    ``XU`` pair a basic variable with a constraint at its lower / upper bound, ``LL`` / ``UL`` / ``BS`` set a variable;
+    unnamed constraints default to basic, unnamed variables to the lower bound.  HiGHS files are recognised by their first
+    line -- the reference tests for ``'HiGHS'`` while its own writer emits ``'HIGHS v1'``; both spellings are accepted."""
+    status_str_to_int = {"LL": 0, "BS": 1, "UL": 2, "XU": (1, 2), "XL": (1, 0)}
+    with open(fn, "r") as f:
+        lines = f.readlines()
+    if lines and ("HiGHS" in lines[0] or "HIGHS" in lines[0]):
+        return read_bas_highs(fn)
+    assert con_nms is not None
+    con_label, var_label = {}, {}
+    for line in lines:
+        parts = line.split()
+        if not parts or parts[0] not in status_str_to_int:
+            continue
+        st = status_str_to_int[parts[0]]
+        if parts[0] in ("XU", "XL"):
+            var_label[parts[1]], con_label[parts[2]] = st
+        else:
+            var_label[parts[1]] = st
+    return (np.array([con_label.get(nm, 1) for nm in con_nms], dtype=np.int64),
+            np.array([var_label.get(nm, 0) for nm in var_nms], dtype=np.int64))
 
 
 def write_sort_vars(fn, logits, m):

@@ -99,6 +99,41 @@ def validation(model, loader, dev, dump_info=None, args=None):
     return avg_loss, avg_acc
 
 
+@torch.no_grad()
+def validation_wrt_converged(model, loader, dev, dump_info=None, args=None):
+    """Reference val.py:71-104: accuracy of the predicted basis against the basis the solver CONVERGED to when started
+    from it (``{log_dir}/opt-from-pred-basis/{fn}.bas``, written by the solver harness, which is out of scope here); LPs
+    without such a file are skipped.  Returns ``(0, avg_acc)`` like the reference; ``dump_info`` names a JSON file that
+    receives ``{file name: {"cvg/acc", "cvg/prec", "cvg/recl"}}`` (the reference updates a pandas HDF file)."""
+    from .io_utils import extract_fn
+    from .pred_basis import read_bas
+    model.to(dev)
+    was_training = model.training
+    model.eval()
+    avg_acc, rows, n_lps = 0., {}, len(loader)
+    for idx, batch in enumerate(loader):
+        con_nms, var_nms = batch.con_nms[0], batch.var_nms[0]
+        fn = extract_fn(batch.processed_path[0])
+        logit_cons, logit_vars = model_inference_with_batch(model, batch, args)
+        tgt = f"{args.log_dir}/opt-from-pred-basis/{fn}.bas"
+        if not os.path.exists(tgt):
+            continue
+        con_lbls, var_lbls = read_bas(tgt, con_nms, var_nms)
+        acc, prec, recl = accuracy(torch.cat((logit_cons, logit_vars), dim=0),
+                                   torch.cat((torch.from_numpy(np.asarray(con_lbls)), torch.from_numpy(np.asarray(var_lbls))), dim=0),
+                                   logit_cons.shape[0], return_pr=True)
+        avg_acc += acc / n_lps
+        rows[fn] = {"cvg/acc": float(acc), "cvg/prec": float(prec), "cvg/recl": float(recl)}
+        if idx % 9 == 1:
+            logging.info(f"{idx} {fn} {n_lps} {acc} {prec} {recl}")
+    if was_training:
+        model.train()
+    if dump_info:
+        with open(dump_info, "w") as f:
+            json.dump(rows, f)
+    return 0, avg_acc
+
+
 def run(args):
     """Reference val.py:238-281: load the dataset, split, build ``eval(args.arch)``, load the checkpoint, optional
     ``model.half()`` and report the mean validation accuracy."""

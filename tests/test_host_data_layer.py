@@ -195,3 +195,30 @@ def test_sorted_claim_is_only_made_for_verified_edge_order(pkg):
     g_sorted = MyToBipartite()(uni(np.arange(5))).edge_index
     g_unsorted = MyToBipartite()(uni(np.array([3, 0, 4, 2, 1]))).edge_index
     assert g_sorted._sorted_hint is True and g_unsorted._sorted_hint is False
+
+
+def test_basis_file_readers_round_trip_the_writers(pkg, tmp_path):
+    """read_bas / read_bas_highs (reference scripts/cvt_to_pkl.py:166-209, the readers behind val.validation_wrt_converged)
+    against the writers of pred_basis.py: named (MPS-style) and HiGHS files give back the statuses that were written."""
+    pred = pkg["pred"]
+    rng = np.random.default_rng(4)
+    m, n = 7, 12
+    st = np.zeros(m + n, dtype=np.int64)
+    st[rng.permutation(m + n)[:m]] = 1                                # exactly m basic nodes
+    free = np.flatnonzero(st == 0)
+    st[free[rng.random(len(free)) < 0.5]] = 2
+    pc, pv = st[:m], st[m:]
+    con_nms, var_nms = [f"c{i}" for i in range(m)], [f"x{j}" for j in range(n)]
+    pred.write_bas(str(tmp_path / "named.bas"), var_nms, con_nms, pv, pc)
+    rc, rv = pred.read_bas(str(tmp_path / "named.bas"), con_nms, var_nms)
+    np.testing.assert_array_equal(rc, pc)
+    np.testing.assert_array_equal(rv, pv)
+    pred.write_bas_highs(str(tmp_path / "h.bas"), var_nms, con_nms, pv, pc)
+    for reader in (pred.read_bas, pred.read_bas_highs):
+        rc, rv = reader(str(tmp_path / "h.bas"))[:2] if reader is pred.read_bas_highs else reader(str(tmp_path / "h.bas"), con_nms, var_nms)
+        np.testing.assert_array_equal(rc, pc)
+        np.testing.assert_array_equal(rv, pv)
+    # a hand-written file in the solver's format: BS / LL lines and unnamed entries take the defaults
+    (tmp_path / "hand.bas").write_text("NAME x\n XU x1 c0 \n LL x2 \n BS x3 \n UL x4 \nENDATA\n")
+    rc, rv = pred.read_bas(str(tmp_path / "hand.bas"), ["c0", "c1"], ["x0", "x1", "x2", "x3", "x4"])
+    assert list(rc) == [2, 1] and list(rv) == [0, 1, 0, 1, 2]
