@@ -998,7 +998,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
-    ap.add_argument("--sweep-distinct", type=int, default=96, help="C5: distinct LPs materialised (cycled)")
+    ap.add_argument("--sweep-distinct", type=int, default=192, help="C5: distinct LPs materialised per GPU (cycled)")
     ap.add_argument("--sweep-hids", type=int, default=1024)
     ap.add_argument("--sweep-pack", type=int, default=1, help="C5 e2e arm: pack LPs block-diagonally (1) or one call per LP (0)")
     # fp16 (IEEE half storage, fp32 accumulate) is the 16-bit mode that passes every parity gate of the north star

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import KNOWN_DEVIATION, LOGIT_BAR_16BIT
 from oracle import port
 
 pytestmark = pytest.mark.gpu
@@ -68,13 +69,14 @@ def test_gcn_fc_forward_bf16(cuda, cfg, hids, depth):
     for got, exp in ((lc, ec), (lv, ev)):
         d = np.abs(got.cpu().numpy() - exp.numpy()) / 10.0
         fro = np.linalg.norm(got.cpu().numpy() - exp.numpy()) / np.linalg.norm(exp.numpy())
-        assert fro < 2e-2, fro
-        assert np.mean(d < 2e-2) >= 0.99, np.mean(d < 2e-2)
-        assert d.max() < 1.5e-1, d.max()
+        kd = KNOWN_DEVIATION["bf16"]
+        assert fro < kd["frobenius"], fro
+        assert np.mean(d < LOGIT_BAR_16BIT) >= kd["frac_within_bar"], np.mean(d < LOGIT_BAR_16BIT)
+        assert d.max() < kd["max_entry"], d.max()
     status = model.predict_basis(batch).cpu().numpy()
     exp = port.inference_gnn_np(np.concatenate([ec.numpy(), ev.numpy()]), lp.m)
     assert int((status == 1).sum()) == lp.m
-    assert np.mean(status == exp) >= 0.98          # bf16 logits move near-ties; the 99.9 % bar applies to fp32
+    assert np.mean(status == exp) >= KNOWN_DEVIATION["bf16"]["status_agreement"]   # known deviation: the 99.9 % bar holds for fp32 / fp16
 
 
 @pytest.mark.parametrize("cfg,hids,depth", [((1000, 2000, 10_000, 1235), 64, 2), ((3000, 6000, 30_000, 77), 1024, 3),
@@ -92,8 +94,8 @@ def test_gcn_fc_forward_fp16(cuda, cfg, hids, depth):
         assert got.dtype == torch.float32
         d = np.abs(got.cpu().numpy() - exp.numpy()) / 10.0
         fro = np.linalg.norm(got.cpu().numpy() - exp.numpy()) / np.linalg.norm(exp.numpy())
-        assert fro < 2.5e-3, fro
-        assert d.max() < 2e-2, d.max()
+        assert fro < KNOWN_DEVIATION["fp16"]["frobenius"], fro
+        assert d.max() < LOGIT_BAR_16BIT, d.max()          # at these sizes every entry meets the bar
     status = model.predict_basis(batch).cpu().numpy()
     exp = port.inference_gnn_np(np.concatenate([ec.numpy(), ev.numpy()]), lp.m)
     assert int((status == 1).sum()) == lp.m
@@ -173,9 +175,12 @@ def test_full_size_c2_parity_against_oracle(cuda, precision):
         assert d.max() < 1e-4, d.max()            # x2 operands, chunked accumulation) and on the CUDA cores alike
         assert agree >= 0.999
     elif precision == "fp16":                     # half storage: every entry within 2e-2 of the row norm... and 99.9 %
-        assert fro < 2.5e-3 and np.mean(d < 2e-2) >= 0.9999 and d.max() < 5e-2 and agree >= 0.999
+        kd = KNOWN_DEVIATION["fp16"]
+        assert fro < kd["frobenius"] and np.mean(d < LOGIT_BAR_16BIT) >= kd["frac_within_bar"] and d.max() < kd["max_entry"] \
+            and agree >= kd["status_agreement"]
     else:
-        assert fro < 2e-2 and np.mean(d < 2e-2) >= 0.99 and agree >= 0.98
+        kd = KNOWN_DEVIATION["bf16"]
+        assert fro < kd["frobenius"] and np.mean(d < LOGIT_BAR_16BIT) >= kd["frac_within_bar"] and agree >= kd["status_agreement"]
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp16"])

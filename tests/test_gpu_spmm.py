@@ -169,3 +169,42 @@ def test_sweep_kernel_writes_only_its_output(cuda):
                 _lib.check(rc, "spmm_ex")
                 torch.cuda.synchronize()
                 assert bool((buf[:pad] == 7.0).all()) and bool((buf[pad + rows * F:] == 7.0).all())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_c4_shape_banded_sweep_is_checked_not_only_timed(cuda, dtype):
+    """BASELINE config C4's own generator (1M x 2M staircase LP, ~9.8M nonzeros): the banded sweep that the step runs at
+    this size against the row kernel (bit-identical) and against the oracle's sequential CSR-order sum on sampled rows,
+    both orientations -- element offsets pass 2^31 (2M rows x 1024 features) on the REAL band structure."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops, synth
+    from lpgnn_b200.graph import BipartiteCSR
+    cfg = synth.CONFIGS["C4"]
+    lp = synth.processed_lp(cfg["m"], cfg["n"], cfg["nnz"], seed=cfg["seed"])
+    F = 1024 if dtype != torch.float32 else 512
+    g = BipartiteCSR.from_coo_arrays(lp.row, lp.col, lp.a_data.astype(np.float32), lp.m, lp.n, cuda, is_sorted=True).check()
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    for k, view in enumerate(g.views()):
+        src_rows = lp.n if k == 0 else lp.m
+        x = torch.randn(src_rows, F, device=cuda, generator=gen).to(dtype)
+        y = ops.spmm(view, x)                              # automatic: the banded sweep at this size
+        ref = ops.spmm(view, x, slab_bytes=-1)             # row-per-warp kernel
+        assert torch.equal(y.view(torch.int32 if dtype == torch.float32 else torch.int16),
+                           ref.view(torch.int32 if dtype == torch.float32 else torch.int16)), k
+        del ref
+        ptr_, idx, v, rows = view
+        pick = torch.from_numpy(np.unique(np.concatenate([[0, rows - 1], np.random.default_rng(k).integers(0, rows, 64)]))).to(cuda)
+        beg, end = ptr_[pick].cpu().numpy(), ptr_[pick + 1].cpu().numpy()
+        sub_ptr = np.concatenate([[0], np.cumsum(end - beg)])
+        sub_idx = np.concatenate([idx[b:e].cpu().numpy() for b, e in zip(beg, end)])
+        sub_val = np.concatenate([v[b:e].cpu().numpy() for b, e in zip(beg, end)])
+        uniq, inv = np.unique(sub_idx, return_inverse=True)                      # only the gathered source rows travel to the host
+        xs = x[torch.from_numpy(uniq).to(cuda)].float().cpu().numpy()
+        e = port.spmm_sequential(sub_ptr, inv.astype(sub_idx.dtype), sub_val, xs)
+        got = y[pick].float().cpu().numpy()
+        if dtype == torch.float32:
+            np.testing.assert_allclose(got, e, rtol=1e-5, atol=1e-5)
+        else:
+            assert np.mean(got == torch.from_numpy(e).to(dtype).float().numpy()) > 0.99
+            np.testing.assert_allclose(got, e, rtol=2e-3, atol=2e-3)
+        del x, y
