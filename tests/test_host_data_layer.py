@@ -34,6 +34,38 @@ def test_msgpack_numpy_roundtrip(pkg, tmp_path):
     assert set(raw[0].keys()) == {b"nd", b"type", b"kind", b"shape", b"data"} and raw[0][b"nd"] is True
 
 
+# The msgpack_numpy wire format (third-party, absent here; the reference pins no version -- 0.4.8 is the last release
+# and its encode() is what utils.py:193-200 patches in) assembled BY HAND from its published encode() and the msgpack
+# spec, so the reader/writer is checked against a vector this repo's encoder did not produce:
+#   ndarray  -> {b'nd': True, b'type': dtype.str, b'kind': b'', b'shape': shape, b'data': raw bytes}
+#   np scalar (not a Python float/int subclass) -> {b'nd': False, b'type': dtype.str, b'data': raw bytes}
+MSGPACK_NUMPY_GOLDEN = bytes.fromhex(
+    "93"                                                 # list of 3
+    "85"                                                 # map of 5: np.arange(3, dtype='<i4')
+    "c4026e64" "c3"                                      # b'nd': True
+    "c40474797065" "a33c6934"                            # b'type': '<i4'
+    "c4046b696e64" "c400"                                # b'kind': b''
+    "c4057368617065" "9103"                              # b'shape': [3]
+    "c40464617461" "c40c" "000000000100000002000000"     # b'data': 12 bytes, little endian
+    "83"                                                 # map of 3: np.float32(3.5)
+    "c4026e64" "c2"                                      # b'nd': False
+    "c40474797065" "a33c6634"                            # b'type': '<f4'
+    "c40464617461" "c404" "00006040"                     # b'data'
+    "a3783a31")                                          # the str 'x:1' (names are plain msgpack strings)
+
+
+def test_msgpack_numpy_wire_vector(pkg, tmp_path):
+    io = pkg["io"]
+    fn = tmp_path / "golden.pk"
+    fn.write_bytes(MSGPACK_NUMPY_GOLDEN)
+    arr, scalar, name = io.msgpack_load(fn)
+    np.testing.assert_array_equal(arr, np.arange(3, dtype=np.int32))
+    assert arr.dtype == np.dtype("<i4") and arr.flags.writeable            # copy=True of dataset.py:189
+    assert scalar.dtype == np.float32 and float(scalar) == 3.5 and name == "x:1"
+    io.msgpack_dump([np.arange(3, dtype="<i4"), np.float32(3.5), "x:1"], fn)
+    assert fn.read_bytes() == MSGPACK_NUMPY_GOLDEN
+
+
 def test_dataset_get_and_to_bipartite_match_oracle(pkg, tmp_path):
     ds_mod, synth = pkg["dataset"], pkg["synth"]
     root = str(tmp_path / "ds")
