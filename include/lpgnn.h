@@ -426,6 +426,13 @@ LPGNN_API int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const in
                                float* logits_out, int32_t* graph_status, void* workspace,
                                size_t workspace_bytes, lpgnn_stream_t stream);
 
+/* Tuning knob (process-wide): the two directions of a hidden layer are independent (reference arch.py:183-184), so
+ * lpgnn_predict_basis[_packed] enqueues the second direction's transform on a library-owned side stream, forked from
+ * and joined back into `stream` with events (default on; LPGNN_PREDICT_FORK=0 or enable = 0 keeps everything on
+ * `stream`).  Same results either way; everything the call enqueues is ordered before later work on `stream`.
+ * Returns the previous setting. */
+LPGNN_API int lpgnn_set_predict_fork(int enable);
+
 /* =============================================================================================
  * Backward pass (training step: reference train.py:121-129 calls loss.backward(), which runs the
  * autograd formulas of PyG GraphConv / torch_sparse spmm_sum / F.normalize / relu_ / dropout).

@@ -91,6 +91,7 @@ SIGNATURES = {
     "lpgnn_predict_basis": (_int, [C.POINTER(GcnFcWeights), _p, _p, _p, _i64, _i32, _i32, _int, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "lpgnn_predict_basis_packed": (_int, [C.POINTER(GcnFcWeights), _p, _p, _p, _i64, _i32, _i32, _int, _p, _p, _p, _p, _i32, _p,
                                           _p, _p, _p, _sz, _p]),
+    "lpgnn_set_predict_fork": (_int, [_int]),
     "lpgnn_basis_select_segmented_ex": (_int, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _int, _int, _p, _sz, _p]),
     "lpgnn_basis_select_segmented": (_int, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _int, _p, _sz, _p]),
     "lpgnn_gemm_tn_splits": (_i32, [_i32, _i32, _i32]),

@@ -62,12 +62,20 @@ conv_in_mma_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ 
   // ---- weights in fragment order: entry (chunk, j, lane) = B fragment of MMA j of the 32-column chunk.
   //      fragment column n (= g) of MMA j is output feature chunk*32 + 8*(n/2) + 2*j + (n%2): lane (g,t) then owns the
   //      accumulators of features chunk*32 + 8t + 2j, +1 -> over j = 0..3 the 8 consecutive features 8t .. 8t+7.
+  const bool wvec = ((reinterpret_cast<uintptr_t>(W_rel) | reinterpret_cast<uintptr_t>(W_root)) & 7) == 0;
+#pragma unroll 4
   for (int i = tid; i < N * 4; i += kMmaThreads) {
     const int l = i & 31, j = (i >> 5) & 3, chunk = i >> 7;
     const int gg = l >> 2, tt = l & 3;
     const int col = chunk * 32 + 8 * (gg >> 1) + 2 * j + (gg & 1);
-    const float2 wr = make_float2(__ldg(W_rel + (size_t)col * 8 + 2 * tt), __ldg(W_rel + (size_t)col * 8 + 2 * tt + 1));    // k = 2t, 2t+1
-    const float2 wo = make_float2(__ldg(W_root + (size_t)col * 8 + 2 * tt), __ldg(W_root + (size_t)col * 8 + 2 * tt + 1));  // k = 2t+8, +9
+    float2 wr, wo;
+    if (wvec) {
+      wr = __ldg(reinterpret_cast<const float2*>(W_rel + (size_t)col * 8 + 2 * tt));     // k = 2t, 2t+1
+      wo = __ldg(reinterpret_cast<const float2*>(W_root + (size_t)col * 8 + 2 * tt));    // k = 2t+8, +9
+    } else {
+      wr = make_float2(__ldg(W_rel + (size_t)col * 8 + 2 * tt), __ldg(W_rel + (size_t)col * 8 + 2 * tt + 1));
+      wo = make_float2(__ldg(W_root + (size_t)col * 8 + 2 * tt), __ldg(W_root + (size_t)col * 8 + 2 * tt + 1));
+    }
     wfrag[i] = make_uint2(Half16<T>::pack(wr.x, wr.y), Half16<T>::pack(wo.x, wo.y));
   }
   for (int i = tid; i < N; i += kMmaThreads) bias_s[i] = b_rel ? __ldg(b_rel + i) : 0.f;

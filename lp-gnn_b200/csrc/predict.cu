@@ -5,6 +5,12 @@
 // (dataset.py:299-304).  The host cost of a step is ~25 kernel launches from native code instead of ~25 Python
 // round trips, which is what bounds small LPs (BASELINE config C5: 10K small/medium LPs).
 // All device memory comes from ONE caller-provided workspace, carved with a bump allocator.
+#include <stdlib.h>
+
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 
 namespace lpgnn {
@@ -21,6 +27,32 @@ struct Bump {
     return r;
   }
 };
+
+// The two directions of a layer are independent (arch.py:183-184: `left, right = conv(left, right, edge_index)` computes both from the previous layer's features).
+// Their transforms are persistent kernels whose last wave leaves most SMs idle (C2: 21.1 and 10.6 waves of tile pairs),
+// so the second direction's transform is enqueued on a side stream: its CTA pairs start on the SMs the first kernel's
+// tail has already released, and for small LPs the two grids simply run side by side.  One side stream and event pair
+// per (device, caller stream), created on first use and kept for the life of the process.
+struct Side { cudaStream_t aux; cudaEvent_t fork, join; };
+int g_predict_fork = [] { const char* e = getenv("LPGNN_PREDICT_FORK"); return e ? atoi(e) != 0 : 1; }();
+
+int side_for(cudaStream_t st, Side* out) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, Side> sides;
+  int dev = 0;
+  LPGNN_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = sides.find({dev, st});
+  if (it == sides.end()) {
+    Side s;
+    LPGNN_CUDA_OK(cudaStreamCreateWithFlags(&s.aux, cudaStreamNonBlocking));
+    LPGNN_CUDA_OK(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    LPGNN_CUDA_OK(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+    it = sides.emplace(std::make_pair(dev, st), s).first;
+  }
+  *out = it->second;
+  return LPGNN_OK;
+}
 
 }  // namespace
 }  // namespace lpgnn
@@ -173,6 +205,13 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
   const int n_hidden = depth - 2;
   bool head_done = false;
   int cur = 0;
+  // second direction's transform on the side stream (see Side above); `st2` is the stream it is enqueued on
+  Side side{};
+  const bool fork = g_predict_fork && n_hidden > 0 && (bf16 || x2);
+  if (fork) LPGNN_TRY(side_for(st, &side));
+  lpgnn_stream_t st2 = fork ? (lpgnn_stream_t)side.aux : stream;
+#define LPGNN_FORK() do { if (fork) { LPGNN_CUDA_OK(cudaEventRecord(side.fork, st)); LPGNN_CUDA_OK(cudaStreamWaitEvent(side.aux, side.fork, 0)); } } while (0)
+#define LPGNN_JOIN() do { if (fork) { LPGNN_CUDA_OK(cudaEventRecord(side.join, side.aux)); LPGNN_CUDA_OK(cudaStreamWaitEvent(st, side.join, 0)); } } while (0)
   for (int li = 0; li < n_hidden; ++li) {
     const bool x2_direct = x2 && li == 0;    // first hidden layer: its inputs (conv1 outputs) already exist as x2 operands
     if (x2_direct) {   // aggregate straight into x2 operands (scale from the sources' scales), no fp32 aggregate, no split pass
@@ -186,13 +225,15 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
     }
     const bool last = li == n_hidden - 1;
     if (last && bf16) {  // head fused into the epilogue; the last activation never reaches HBM
+      const int nparts = lpgnn_node_transform_head_parts(H);
+      LPGNN_FORK();
       LPGNN_TRY(lpgnn_node_transform_head_ex(B.agg_t, H, w->l2r_wrel[li], right, H, w->l2r_wroot[li], w->l2r_b[li], n, H,
                                              nullptr, dt, LPGNN_EPI_RELU, w->head_right_w, B.part_t, stream));
       LPGNN_TRY(lpgnn_node_transform_head_ex(B.agg_s, H, w->r2l_wrel[li], left, H, w->r2l_wroot[li], w->r2l_b[li], m, H,
-                                             nullptr, dt, LPGNN_EPI_RELU, w->head_left_w, B.part_s, stream));
-      const int nparts = lpgnn_node_transform_head_parts(H);
+                                             nullptr, dt, LPGNN_EPI_RELU, w->head_left_w, B.part_s, st2));
+      LPGNN_TRY(lpgnn_head_finish(B.part_s, nparts, m, w->head_left_b, x_s, p, B.logit_s, st2));
+      LPGNN_JOIN();
       LPGNN_TRY(lpgnn_head_finish(B.part_t, nparts, n, w->head_right_b, x_t, q, B.logit_t, stream));
-      LPGNN_TRY(lpgnn_head_finish(B.part_s, nparts, m, w->head_left_b, x_s, p, B.logit_s, stream));
       head_done = true;
     } else if (x2) {  // the reference's default precision on the tensor cores: three half x half passes over x2 operands
       if (!x2_direct) {   // deeper layers: inputs are fp32 outputs of the previous transform -> split them (shared row scale)
@@ -204,6 +245,7 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
       const float* rsx_t = x2_direct ? B.xscale_x[1] : nullptr;   // row scales of the lin_root operand (null: shared)
       const float* rsx_s = x2_direct ? B.xscale_x[0] : nullptr;
       void *nl = last ? nullptr : B.act[cur ^ 1][0], *nr = last ? nullptr : B.act[cur ^ 1][1];
+      LPGNN_FORK();
       LPGNN_TRY(lpgnn_node_transform_x2(B.xa_hi[1], B.xa_lo[1], H, w->l2r_wrel_hi[li], w->l2r_wrel_lo[li], B.xx_hi[1],
                                         B.xx_lo[1], H, w->l2r_wroot_hi[li], w->l2r_wroot_lo[li], B.xscale[1], rsx_t,
                                         w->l2r_wscale[li], w->l2r_b[li], n, H, (float*)nr, LPGNN_EPI_RELU,
@@ -211,21 +253,24 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
       LPGNN_TRY(lpgnn_node_transform_x2(B.xa_hi[0], B.xa_lo[0], H, w->r2l_wrel_hi[li], w->r2l_wrel_lo[li], B.xx_hi[0],
                                         B.xx_lo[0], H, w->r2l_wroot_hi[li], w->r2l_wroot_lo[li], B.xscale[0], rsx_s,
                                         w->r2l_wscale[li], w->r2l_b[li], m, H, (float*)nl, LPGNN_EPI_RELU,
-                                        last ? w->head_left_w : nullptr, last ? B.part_s : nullptr, stream));
+                                        last ? w->head_left_w : nullptr, last ? B.part_s : nullptr, st2));
+      const int nparts = lpgnn_node_transform_head_parts(H);
+      if (last) LPGNN_TRY(lpgnn_head_finish(B.part_s, nparts, m, w->head_left_b, x_s, p, B.logit_s, st2));
+      LPGNN_JOIN();
       if (last) {
-        const int nparts = lpgnn_node_transform_head_parts(H);
         LPGNN_TRY(lpgnn_head_finish(B.part_t, nparts, n, w->head_right_b, x_t, q, B.logit_t, stream));
-        LPGNN_TRY(lpgnn_head_finish(B.part_s, nparts, m, w->head_left_b, x_s, p, B.logit_s, stream));
         head_done = true;
       } else {
         left = nl; right = nr; cur ^= 1;
       }
     } else {
       void *nl = B.act[cur ^ 1][0], *nr = B.act[cur ^ 1][1];
+      LPGNN_FORK();
       LPGNN_TRY(lpgnn_node_transform(B.agg_t, H, w->l2r_wrel[li], right, H, w->l2r_wroot[li], w->l2r_b[li], n, H, nr, dt,
                                      dt, LPGNN_EPI_RELU, stream));
       LPGNN_TRY(lpgnn_node_transform(B.agg_s, H, w->r2l_wrel[li], left, H, w->r2l_wroot[li], w->r2l_b[li], m, H, nl, dt,
-                                     dt, LPGNN_EPI_RELU, stream));
+                                     dt, LPGNN_EPI_RELU, st2));
+      LPGNN_JOIN();
       left = nl; right = nr; cur ^= 1;
     }
   }
@@ -247,5 +292,13 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
     LPGNN_TRY(lpgnn_basis_select(B.logit_s, m, B.logit_t, n, m, status_out, 0, nullptr, B.sel_ws, B.sel_ws_bytes, stream));
   }
 #undef LPGNN_TRY
+#undef LPGNN_FORK
+#undef LPGNN_JOIN
   return LPGNN_OK;
+}
+
+extern "C" int lpgnn_set_predict_fork(int enable) {
+  const int prev = lpgnn::g_predict_fork;
+  lpgnn::g_predict_fork = enable ? 1 : 0;
+  return prev;
 }

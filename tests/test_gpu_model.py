@@ -149,6 +149,41 @@ def test_native_one_call_prediction_matches_op_by_op_path(cuda, hids, depth, pre
     assert int(model.last_graph_status.item()) & 1
 
 
+@pytest.mark.parametrize("precision,hids,depth", [("fp16", 1024, 3), ("fp32", 128, 4), ("bf16", 64, 4)])
+def test_side_stream_fork_changes_nothing(cuda, precision, hids, depth):
+    """lpgnn_set_predict_fork: the second direction's transform on the library's side stream, on the default stream and on
+    two user streams back to back (each caller stream gets its own side stream), gives the bits of the one-stream order."""
+    from lpgnn_b200 import _lib
+    lib = _lib.load()
+    lp, model, ref, g_ref, batch = _setup((2500, 5200, 26000, 5), hids, depth, cuda)
+    model.set_precision(precision)
+    t = lambda a, dt: torch.from_numpy(a.astype(dt)).to(cuda)
+    coo = (t(lp.row, np.int32), t(lp.col, np.int32), t(lp.a_data, np.float32))
+
+    def run():
+        st, lg = model.predict_basis_coo(*coo, lp.m, lp.n, batch.x_s, batch.x_t, is_sorted=True, want_logits=True)
+        return st.clone(), lg.clone()
+
+    prev = lib.lpgnn_set_predict_fork(0)
+    try:
+        base = run()
+        assert lib.lpgnn_set_predict_fork(1) == 0
+        got = [run()]
+        torch.cuda.synchronize()
+        for _ in range(2):
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    got.append(run())
+            torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+    finally:
+        lib.lpgnn_set_predict_fork(prev)
+    for st, lg in got:
+        assert torch.equal(st, base[0]) and torch.equal(lg, base[1])
+
+
 @pytest.mark.parametrize("precision", ["fp32", "fp32_simt", "bf16", "fp16"])
 def test_full_size_c2_parity_against_oracle(cuda, precision):
     """BASELINE config C2 at full size (50K x 100K, ~491K nnz, hids 1024, depth 3): logits and statuses of the
