@@ -426,12 +426,13 @@ LPGNN_API int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const in
                                float* logits_out, int32_t* graph_status, void* workspace,
                                size_t workspace_bytes, lpgnn_stream_t stream);
 
-/* Tuning knob (process-wide): the two directions of a hidden layer are independent (reference arch.py:183-184), so
- * lpgnn_predict_basis[_packed] enqueues the second direction's transform on a library-owned side stream, forked from
- * and joined back into `stream` with events (default on; LPGNN_PREDICT_FORK=0 or enable = 0 keeps everything on
- * `stream`).  Same results either way; everything the call enqueues is ordered before later work on `stream`.
- * Returns the previous setting. */
-LPGNN_API int lpgnn_set_predict_fork(int enable);
+/* Tuning knob (process-wide): the two directions of a layer are independent (reference arch.py:183-184), so
+ * lpgnn_predict_basis[_packed] can enqueue the constraint side's kernels on a library-owned side stream, forked from
+ * and joined back into `stream` with events.  mode 0 = never, 1 = only LPs of up to 65536 nodes (default: larger LPs
+ * fill the GPU with either side alone and measured no gain), 2 = always; LPGNN_PREDICT_FORK sets the initial mode.
+ * Same results for every mode; everything the call enqueues is ordered before later work on `stream`.
+ * Returns the previous mode. */
+LPGNN_API int lpgnn_set_predict_fork(int mode);
 
 /* =============================================================================================
  * Backward pass (training step: reference train.py:121-129 calls loss.backward(), which runs the

@@ -28,13 +28,16 @@ struct Bump {
   }
 };
 
-// The two directions of a layer are independent (arch.py:183-184: `left, right = conv(left, right, edge_index)` computes both from the previous layer's features).
-// Their transforms are persistent kernels whose last wave leaves most SMs idle (C2: 21.1 and 10.6 waves of tile pairs),
-// so the second direction's transform is enqueued on a side stream: its CTA pairs start on the SMs the first kernel's
-// tail has already released, and for small LPs the two grids simply run side by side.  One side stream and event pair
-// per (device, caller stream), created on first use and kept for the life of the process.
+// The two directions of a layer are independent (arch.py:183-184: `left, right = conv(left, right, edge_index)` computes
+// both from the previous layer's features), so the constraint side's kernels can run on a side stream next to the
+// variable side's.  Measured on B200: LPs whose grids do not fill the GPU gain (C5, one call per LP: 5.9K -> 7.2K LPs/s);
+// at C2 size nothing is gained -- the transforms are power-bound, an idle tail lets the busy SMs clock higher -- and the
+// three-LP pipeline loses ~3 % to the extra interleaving.  Hence mode 1 (default) forks only LPs of up to kForkMaxNodes
+// nodes; 0 = never, 2 = always.  One side stream and event pair per (device, caller stream), created on first use and
+// kept for the life of the process.
+constexpr int64_t kForkMaxNodes = 65536;
 struct Side { cudaStream_t aux; cudaEvent_t fork, join; };
-int g_predict_fork = [] { const char* e = getenv("LPGNN_PREDICT_FORK"); return e ? atoi(e) != 0 : 1; }();
+int g_predict_fork = [] { const char* e = getenv("LPGNN_PREDICT_FORK"); const int v = e ? atoi(e) : 1; return v < 0 ? 0 : (v > 2 ? 2 : v); }();
 
 int side_for(cudaStream_t st, Side* out) {
   static std::mutex mu;
@@ -175,26 +178,37 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
                               B.val_csc, B.csr2csc, gstat, B.build_ws, B.build_ws_bytes, stream));
   const int dt = bf16 ? w->precision : LPGNN_F32;
   void *left = B.act[0][0], *right = B.act[0][1];
+  // The constraint side's chain (conv1 -> aggregate -> transform -> head) runs on the side stream (see Side above), the
+  // variable side's on `stream`; the chains meet where a layer reads the other side's features (LPGNN_CROSS).
+  Side side{};
+  const bool fork = depth > 2 && (bf16 || x2) && (g_predict_fork == 2 || (g_predict_fork == 1 && (int64_t)m + n <= kForkMaxNodes));
+  if (fork) LPGNN_TRY(side_for(st, &side));
+  lpgnn_stream_t st2 = fork ? (lpgnn_stream_t)side.aux : stream;
+#define LPGNN_FORK() do { if (fork) { LPGNN_CUDA_OK(cudaEventRecord(side.fork, st)); LPGNN_CUDA_OK(cudaStreamWaitEvent(side.aux, side.fork, 0)); } } while (0)
+#define LPGNN_JOIN() do { if (fork) { LPGNN_CUDA_OK(cudaEventRecord(side.join, side.aux)); LPGNN_CUDA_OK(cudaStreamWaitEvent(st, side.join, 0)); } } while (0)
+#define LPGNN_CROSS() do { if (fork) { LPGNN_CUDA_OK(cudaEventRecord(side.fork, st)); LPGNN_CUDA_OK(cudaEventRecord(side.join, side.aux)); \
+    LPGNN_CUDA_OK(cudaStreamWaitEvent(side.aux, side.fork, 0)); LPGNN_CUDA_OK(cudaStreamWaitEvent(st, side.join, 0)); } } while (0)
+  LPGNN_FORK();
   // ---- conv1 (+relu).  CSC view: dst = variables, src = constraints; CSR view: dst = constraints, src = variables
   if (bf16 && p == 8 && q == 8 && H % 32 == 0 && H <= 4096) {   // the reference's shape: one kernel per direction
     LPGNN_TRY(lpgnn_conv_in_16(B.colptr, B.row_csc, B.val_csc, n, x_s, x_t, w->c1_l2r_wrel, w->c1_l2r_b, w->c1_l2r_wroot, H,
                                right, dt, LPGNN_EPI_RELU, nullptr, stream));
     LPGNN_TRY(lpgnn_conv_in_16(B.rowptr, B.col, B.val, m, x_t, x_s, w->c1_r2l_wrel, w->c1_r2l_b, w->c1_r2l_wroot, H, left, dt,
-                               LPGNN_EPI_RELU, nullptr, stream));
+                               LPGNN_EPI_RELU, nullptr, st2));
   } else if (bf16) {
     LPGNN_TRY(lpgnn_gather_cat_ex(B.colptr, B.row_csc, B.val_csc, n, x_s, p, x_t, q, nullptr, B.zb_t, dt, stream));
-    LPGNN_TRY(lpgnn_gather_cat_ex(B.rowptr, B.col, B.val, m, x_t, q, x_s, p, nullptr, B.zb_s, dt, stream));
+    LPGNN_TRY(lpgnn_gather_cat_ex(B.rowptr, B.col, B.val, m, x_t, q, x_s, p, nullptr, B.zb_s, dt, st2));
     LPGNN_TRY(lpgnn_node_transform(B.zb_t, 64, w->c1_l2r_wcat, nullptr, 0, nullptr, w->c1_l2r_b, n, H, right, dt, dt,
                                    LPGNN_EPI_RELU, stream));
     LPGNN_TRY(lpgnn_node_transform(B.zb_s, 64, w->c1_r2l_wcat, nullptr, 0, nullptr, w->c1_r2l_b, m, H, left, dt, dt,
-                                   LPGNN_EPI_RELU, stream));
+                                   LPGNN_EPI_RELU, st2));
   } else if (x2) {   // fp32 input layer that also emits its output as x2 operands (lin_root side of the first hidden layer)
     LPGNN_TRY(lpgnn_conv_in_fused_x2(B.colptr, B.row_csc, B.val_csc, n, x_s, p, x_t, q, w->c1_l2r_wrel, w->c1_l2r_b,
                                      w->c1_l2r_wroot, H, (float*)right, LPGNN_EPI_RELU, B.z_t, B.xx_hi[1], B.xx_lo[1],
                                      B.xscale_x[1], B.wabs, stream));
     LPGNN_TRY(lpgnn_conv_in_fused_x2(B.rowptr, B.col, B.val, m, x_t, q, x_s, p, w->c1_r2l_wrel, w->c1_r2l_b,
                                      w->c1_r2l_wroot, H, (float*)left, LPGNN_EPI_RELU, B.z_s, B.xx_hi[0], B.xx_lo[0],
-                                     B.xscale_x[0], B.wabs + 80, stream));
+                                     B.xscale_x[0], B.wabs + 80, st2));
   } else {
     LPGNN_TRY(lpgnn_conv_in_fused(B.colptr, B.row_csc, B.val_csc, n, x_s, p, x_t, q, w->c1_l2r_wrel, w->c1_l2r_b,
                                   w->c1_l2r_wroot, H, right, dt, LPGNN_EPI_RELU, B.z_t, stream));
@@ -205,47 +219,38 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
   const int n_hidden = depth - 2;
   bool head_done = false;
   int cur = 0;
-  // second direction's transform on the side stream (see Side above); `st2` is the stream it is enqueued on
-  Side side{};
-  const bool fork = g_predict_fork && n_hidden > 0 && (bf16 || x2);
-  if (fork) LPGNN_TRY(side_for(st, &side));
-  lpgnn_stream_t st2 = fork ? (lpgnn_stream_t)side.aux : stream;
-#define LPGNN_FORK() do { if (fork) { LPGNN_CUDA_OK(cudaEventRecord(side.fork, st)); LPGNN_CUDA_OK(cudaStreamWaitEvent(side.aux, side.fork, 0)); } } while (0)
-#define LPGNN_JOIN() do { if (fork) { LPGNN_CUDA_OK(cudaEventRecord(side.join, side.aux)); LPGNN_CUDA_OK(cudaStreamWaitEvent(st, side.join, 0)); } } while (0)
   for (int li = 0; li < n_hidden; ++li) {
     const bool x2_direct = x2 && li == 0;    // first hidden layer: its inputs (conv1 outputs) already exist as x2 operands
+    LPGNN_CROSS();                           // both sides' features of the previous layer are complete (and were consumed)
     if (x2_direct) {   // aggregate straight into x2 operands (scale from the sources' scales), no fp32 aggregate, no split pass
       LPGNN_TRY(lpgnn_spmm_x2(B.colptr, B.row_csc, B.val_csc, n, (const float*)left, H, B.xscale_x[0], B.xa_hi[1], B.xa_lo[1],
                               B.xscale[1], (float*)B.agg_t, stream));                          // A^T . left
       LPGNN_TRY(lpgnn_spmm_x2(B.rowptr, B.col, B.val, m, (const float*)right, H, B.xscale_x[1], B.xa_hi[0], B.xa_lo[0],
-                              B.xscale[0], (float*)B.agg_s, stream));                          // A   . right
+                              B.xscale[0], (float*)B.agg_s, st2));                             // A   . right
     } else {
       LPGNN_TRY(lpgnn_spmm(B.colptr, B.row_csc, B.val_csc, n, left, B.agg_t, H, dt, stream));    // A^T . left
-      LPGNN_TRY(lpgnn_spmm(B.rowptr, B.col, B.val, m, right, B.agg_s, H, dt, stream));           // A   . right
+      LPGNN_TRY(lpgnn_spmm(B.rowptr, B.col, B.val, m, right, B.agg_s, H, dt, st2));              // A   . right
     }
     const bool last = li == n_hidden - 1;
     if (last && bf16) {  // head fused into the epilogue; the last activation never reaches HBM
       const int nparts = lpgnn_node_transform_head_parts(H);
-      LPGNN_FORK();
       LPGNN_TRY(lpgnn_node_transform_head_ex(B.agg_t, H, w->l2r_wrel[li], right, H, w->l2r_wroot[li], w->l2r_b[li], n, H,
                                              nullptr, dt, LPGNN_EPI_RELU, w->head_right_w, B.part_t, stream));
       LPGNN_TRY(lpgnn_node_transform_head_ex(B.agg_s, H, w->r2l_wrel[li], left, H, w->r2l_wroot[li], w->r2l_b[li], m, H,
                                              nullptr, dt, LPGNN_EPI_RELU, w->head_left_w, B.part_s, st2));
       LPGNN_TRY(lpgnn_head_finish(B.part_s, nparts, m, w->head_left_b, x_s, p, B.logit_s, st2));
-      LPGNN_JOIN();
       LPGNN_TRY(lpgnn_head_finish(B.part_t, nparts, n, w->head_right_b, x_t, q, B.logit_t, stream));
       head_done = true;
     } else if (x2) {  // the reference's default precision on the tensor cores: three half x half passes over x2 operands
       if (!x2_direct) {   // deeper layers: inputs are fp32 outputs of the previous transform -> split them (shared row scale)
         LPGNN_TRY(lpgnn_split_x2((const float*)B.agg_s, H, (const float*)left, H, m, B.xa_hi[0], B.xa_lo[0], B.xx_hi[0],
-                                 B.xx_lo[0], B.xscale[0], stream));
+                                 B.xx_lo[0], B.xscale[0], st2));
         LPGNN_TRY(lpgnn_split_x2((const float*)B.agg_t, H, (const float*)right, H, n, B.xa_hi[1], B.xa_lo[1], B.xx_hi[1],
                                  B.xx_lo[1], B.xscale[1], stream));
       }
       const float* rsx_t = x2_direct ? B.xscale_x[1] : nullptr;   // row scales of the lin_root operand (null: shared)
       const float* rsx_s = x2_direct ? B.xscale_x[0] : nullptr;
       void *nl = last ? nullptr : B.act[cur ^ 1][0], *nr = last ? nullptr : B.act[cur ^ 1][1];
-      LPGNN_FORK();
       LPGNN_TRY(lpgnn_node_transform_x2(B.xa_hi[1], B.xa_lo[1], H, w->l2r_wrel_hi[li], w->l2r_wrel_lo[li], B.xx_hi[1],
                                         B.xx_lo[1], H, w->l2r_wroot_hi[li], w->l2r_wroot_lo[li], B.xscale[1], rsx_t,
                                         w->l2r_wscale[li], w->l2r_b[li], n, H, (float*)nr, LPGNN_EPI_RELU,
@@ -255,9 +260,8 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
                                         w->r2l_wscale[li], w->r2l_b[li], m, H, (float*)nl, LPGNN_EPI_RELU,
                                         last ? w->head_left_w : nullptr, last ? B.part_s : nullptr, st2));
       const int nparts = lpgnn_node_transform_head_parts(H);
-      if (last) LPGNN_TRY(lpgnn_head_finish(B.part_s, nparts, m, w->head_left_b, x_s, p, B.logit_s, st2));
-      LPGNN_JOIN();
       if (last) {
+        LPGNN_TRY(lpgnn_head_finish(B.part_s, nparts, m, w->head_left_b, x_s, p, B.logit_s, st2));
         LPGNN_TRY(lpgnn_head_finish(B.part_t, nparts, n, w->head_right_b, x_t, q, B.logit_t, stream));
         head_done = true;
       } else {
@@ -265,19 +269,18 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
       }
     } else {
       void *nl = B.act[cur ^ 1][0], *nr = B.act[cur ^ 1][1];
-      LPGNN_FORK();
       LPGNN_TRY(lpgnn_node_transform(B.agg_t, H, w->l2r_wrel[li], right, H, w->l2r_wroot[li], w->l2r_b[li], n, H, nr, dt,
                                      dt, LPGNN_EPI_RELU, stream));
       LPGNN_TRY(lpgnn_node_transform(B.agg_s, H, w->r2l_wrel[li], left, H, w->r2l_wroot[li], w->r2l_b[li], m, H, nl, dt,
                                      dt, LPGNN_EPI_RELU, st2));
-      LPGNN_JOIN();
       left = nl; right = nr; cur ^= 1;
     }
   }
   if (!head_done) {
-    LPGNN_TRY(lpgnn_head_mask(left, dt, m, H, w->head_left_w, w->head_left_b, x_s, p, B.logit_s, nullptr, stream));
+    LPGNN_TRY(lpgnn_head_mask(left, dt, m, H, w->head_left_w, w->head_left_b, x_s, p, B.logit_s, nullptr, st2));
     LPGNN_TRY(lpgnn_head_mask(right, dt, n, H, w->head_right_w, w->head_right_b, x_t, q, B.logit_t, nullptr, stream));
   }
+  LPGNN_JOIN();
   if (logits_out) {
     LPGNN_CUDA_OK(cudaMemcpyAsync(logits_out, B.logit_s, sizeof(float) * 3 * (size_t)m, cudaMemcpyDeviceToDevice, st));
     LPGNN_CUDA_OK(cudaMemcpyAsync(logits_out + 3 * (size_t)m, B.logit_t, sizeof(float) * 3 * (size_t)n,
@@ -294,11 +297,12 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
 #undef LPGNN_TRY
 #undef LPGNN_FORK
 #undef LPGNN_JOIN
+#undef LPGNN_CROSS
   return LPGNN_OK;
 }
 
-extern "C" int lpgnn_set_predict_fork(int enable) {
+extern "C" int lpgnn_set_predict_fork(int mode) {
   const int prev = lpgnn::g_predict_fork;
-  lpgnn::g_predict_fork = enable ? 1 : 0;
+  lpgnn::g_predict_fork = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
   return prev;
 }

@@ -151,8 +151,9 @@ def test_native_one_call_prediction_matches_op_by_op_path(cuda, hids, depth, pre
 
 @pytest.mark.parametrize("precision,hids,depth", [("fp16", 1024, 3), ("fp32", 128, 4), ("bf16", 64, 4)])
 def test_side_stream_fork_changes_nothing(cuda, precision, hids, depth):
-    """lpgnn_set_predict_fork: the second direction's transform on the library's side stream, on the default stream and on
-    two user streams back to back (each caller stream gets its own side stream), gives the bits of the one-stream order."""
+    """lpgnn_set_predict_fork: the constraint side's kernels on the library's side stream (mode 2 = always), on the default
+    stream and on two user streams back to back (each caller stream gets its own side stream), give the bits of the
+    one-stream order (mode 0)."""
     from lpgnn_b200 import _lib
     lib = _lib.load()
     lp, model, ref, g_ref, batch = _setup((2500, 5200, 26000, 5), hids, depth, cuda)
@@ -167,7 +168,7 @@ def test_side_stream_fork_changes_nothing(cuda, precision, hids, depth):
     prev = lib.lpgnn_set_predict_fork(0)
     try:
         base = run()
-        assert lib.lpgnn_set_predict_fork(1) == 0
+        assert lib.lpgnn_set_predict_fork(2) == 0
         got = [run()]
         torch.cuda.synchronize()
         for _ in range(2):
