@@ -851,7 +851,7 @@ def train_sampled_throughput(cfg, lp, dev, precision, steps, world, seeds_per_ba
                     break
         return loss
 
-    run(3)
+    run(10)          # mini-batches differ in size: let the caching allocator see the range before the timed region
     barrier(world)
     torch.cuda.synchronize()
     del sizes[:]
