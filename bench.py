@@ -373,6 +373,7 @@ def run_gpu(args):
         # (at least 1000 LPs = ~20 packs per rank: a handful of packs would only time the pipeline's fill and drain)
         sw = sweep_measure(args, rank, world, dev, lib, args.precision, steps=max(1000, min(10 * args.steps, 3000)),
                            distinct=args.sweep_distinct, with_cpu=False)
+        sw.pop("_model"), sw.pop("_largest")
         if rank == 0:
             out["sweep"] = sw
             out["sweep_lps_per_sec"] = sw["value"]
@@ -492,6 +493,7 @@ def sweep_measure(args, rank, world, dev, lib, precision, steps, distinct, with_
         "gpu_launches": int(launches)}
     if with_cpu and rank == 0 and world == 1:
         out["cpu_baseline"] = cpu_sweep_baseline(lps, args.sweep_hids, sample_budget_s=args.cpu_seconds)
+    out["_model"], out["_largest"] = model, max(lps, key=lambda lp: lp.nnz)      # for the caller's kernel table; popped there
     return out
 
 
@@ -509,6 +511,13 @@ def run_sweep(args):
         sampler.mark()
     sw = sweep_measure(args, rank, world, dev, lib, args.precision, args.steps, args.sweep_distinct, not args.no_cpu)
     clocks = sampler.stop() if rank == 0 else None
+    model, largest = sw.pop("_model"), sw.pop("_largest")
+    roof = None
+    if rank == 0 and not args.no_kernels:
+        # per-kernel table on the LARGEST LP of this rank's share (every kernel timed alone, L2 flushed): the sweep has no
+        # single launch shape, and its packs (600K nodes) run the same kernels at C2-like sizes
+        roof = kernel_rooflines(model, largest, dev, load_peaks(), args.precision in ("bf16", "fp16"), args)
+        roof["roofline"]["workload"] = f"largest LP of the population ({largest.m} x {largest.n}, nnz {largest.nnz}), one LP per launch"
     if rank == 0:
         out = {
             "metric": "LPs/sec (basis prediction: graph build + GCN_FC forward + basis selection)",
@@ -521,6 +530,8 @@ def run_sweep(args):
             "clocks": clocks}
         if "cpu_baseline" in sw:
             out["cpu_baseline"] = sw["cpu_baseline"]
+        if roof is not None:
+            out.update(roof)
         print(json.dumps(out), flush=True)
     if world > 1:
         import torch.distributed as dist
@@ -746,7 +757,7 @@ def kernel_rooflines(model, lp, dev, peaks, bf16, args):
     lc = torch.randn(m, 3, device=dev)
     lv = torch.randn(n, 3, device=dev)
     t_sel = time_kernel(lambda: ops.basis_select(lc, lv, int64=False), reps, flush)
-    add("basis_select (7 launches)", "hbm", t_sel, (m + n) * (12 + 4 + 1 + 4 * 4 + 4 + 1), 7)
+    add("basis_select (one cooperative launch)", "hbm", t_sel, (m + n) * (12 + 1), 1)
     h_row = torch.from_numpy(lp.row.astype(np.int32)).to(dev)
     h_col = torch.from_numpy(lp.col.astype(np.int32)).to(dev)
     h_val = torch.from_numpy(lp.a_data.astype(np.float32)).to(dev)

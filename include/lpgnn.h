@@ -197,6 +197,17 @@ LPGNN_API int lpgnn_conv_in_16(const int32_t* ptr, const int32_t* idx, const flo
                      const float* Xsrc, const float* Xdst, const float* W_rel, const float* b_rel,
                      const float* W_root, int32_t N, void* out, int out_dtype, int epilogue, void* z16,
                      lpgnn_stream_t stream);
+/* Both directions of that layer in ONE launch (arch.py:181: `left, right = self.conv1(x_left, x_right, edge_index)`):
+ * out_t [n,N] = variables side (CSC view: colptr / row_csc / val_csc, sources x_s, own features x_t, l2r weights),
+ * out_s [m,N] = constraints side (CSR view, sources x_t, own features x_s, r2l weights).  The launch's blocks are split
+ * between the sides in proportion to their rows, so the second direction's weight staging and first gathers hide under
+ * the first one's stores; results are bit-identical to two lpgnn_conv_in_16 calls.  z16_s / z16_t optional as above. */
+LPGNN_API int lpgnn_conv_in_16_pair(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* colptr,
+                          const int32_t* row_csc, const float* val_csc, int32_t m, int32_t n, const float* x_s,
+                          const float* x_t, const float* l2r_wrel, const float* l2r_b, const float* l2r_wroot,
+                          const float* r2l_wrel, const float* r2l_b, const float* r2l_wroot, int32_t N,
+                          void* out_s, void* out_t, int out_dtype, int epilogue, void* z16_s, void* z16_t,
+                          lpgnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a3) Dense node transform of a hidden GraphConv layer.  Replaces lin_rel(agg) + lin_root(x_dst)

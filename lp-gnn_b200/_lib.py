@@ -71,6 +71,8 @@ SIGNATURES = {
     "lpgnn_gather_cat": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p]),
     "lpgnn_conv_in_fused": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p, _i32, _p, _int, _int, _p, _p]),
     "lpgnn_conv_in_16": (_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _int, _int, _p, _p]),
+    "lpgnn_conv_in_16_pair": (_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _int, _int,
+                                     _p, _p, _p]),
     "lpgnn_node_transform": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _int, _int, _p]),
     "lpgnn_node_transform_ex": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, C.POINTER(EpilogueArgs), _p]),
     "lpgnn_split_bf16": (_int, [_p, _i64, _int, _p, _p]),

@@ -46,13 +46,32 @@ __device__ __forceinline__ float4 ld4(const float* p, bool vec) {
   return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
 }
 
+// One direction of the layer: destination rows of one side, sources on the other.
+struct ConvInSide {
+  const int32_t* ptr; const int32_t* idx; const float* val; int32_t rows;
+  const float* Xsrc; const float* Xdst; const float* W_rel; const float* b_rel; const float* W_root;
+  void* out; void* z16;   // z16: [rows,64] or null
+};
+
 // Shared memory: wfrag [N/32][4][32] uint2 | bias [N] float | z tile [128][16] T
+// Blocks [0, blocks_a) work on side `sa`, the rest on side `sb` (both directions of the layer in ONE launch: the second
+// direction's weight staging and first gathers hide under the first one's stores instead of following its tail).
+// (the side's fields are read straight from the kernel parameter bank: selecting them into registers per block costs ~14
+// registers of the 64 available at four blocks per SM, so each side gets its own copy of the body instead)
 template <typename T>
-__global__ void __launch_bounds__(kMmaThreads, 4)
-conv_in_mma_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ val, int32_t rows,
-                   const float* __restrict__ Xsrc, const float* __restrict__ Xdst, const float* __restrict__ W_rel,
-                   const float* __restrict__ b_rel, const float* __restrict__ W_root, int N, T* __restrict__ out, int relu,
-                   T* __restrict__ z16 /*[rows,64] or null*/) {
+__device__ __forceinline__ void conv_in_side(const ConvInSide& S, const int side_block, const int side_blocks, const int N,
+                                             const int relu) {
+  const int32_t* __restrict__ ptr = S.ptr;
+  const int32_t* __restrict__ idx = S.idx;
+  const float* __restrict__ val = S.val;
+  const int32_t rows = S.rows;
+  const float* __restrict__ Xsrc = S.Xsrc;
+  const float* __restrict__ Xdst = S.Xdst;
+  const float* __restrict__ W_rel = S.W_rel;
+  const float* __restrict__ b_rel = S.b_rel;
+  const float* __restrict__ W_root = S.W_root;
+  T* __restrict__ out = reinterpret_cast<T*>(S.out);
+  T* __restrict__ z16 = reinterpret_cast<T*>(S.z16);
   extern __shared__ __align__(16) uint8_t smem_m[];
   uint2* wfrag = reinterpret_cast<uint2*>(smem_m);
   float* bias_s = reinterpret_cast<float*>(smem_m + (size_t)N * 32);
@@ -88,8 +107,8 @@ conv_in_mma_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ 
   const bool vsrc = (reinterpret_cast<uintptr_t>(Xsrc) & 15) == 0, vdst = (reinterpret_cast<uintptr_t>(Xdst) & 15) == 0;
   const int nchunks = N >> 5;
   uint32_t* zw = zt + warp * (16 * 8);               // this warp's z tile: [16][8] words = 16 T per row
-  const int64_t warps_total = (int64_t)gridDim.x * (kMmaThreads / 32);
-  for (int64_t row0 = ((int64_t)blockIdx.x * (kMmaThreads / 32) + warp) * 16; row0 < rows; row0 += warps_total * 16) {
+  const int64_t warps_total = (int64_t)side_blocks * (kMmaThreads / 32);
+  for (int64_t row0 = ((int64_t)side_block * (kMmaThreads / 32) + warp) * 16; row0 < rows; row0 += warps_total * 16) {
     // ---- z[row] = [ sum_e val[e] * Xsrc[idx[e], :] | Xdst[row, :] ]  (fp32 accumulate in CSR order, then 16-bit)
     {
       const int64_t row = row0 + r;
@@ -163,9 +182,14 @@ conv_in_mma_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ 
 }
 
 template <typename T>
-int launch_mma(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const float* Xsrc, const float* Xdst,
-               const float* W_rel, const float* b_rel, const float* W_root, int N, void* out, int relu, void* z16,
-               cudaStream_t st) {
+__global__ void __launch_bounds__(kMmaThreads, 4)
+conv_in_mma_kernel(const __grid_constant__ ConvInSide sa, const __grid_constant__ ConvInSide sb, int blocks_a, int N, int relu) {
+  if ((int)blockIdx.x < blocks_a) conv_in_side<T>(sa, (int)blockIdx.x, blocks_a, N, relu);
+  else conv_in_side<T>(sb, (int)blockIdx.x - blocks_a, (int)gridDim.x - blocks_a, N, relu);
+}
+
+template <typename T>
+int launch_mma(const ConvInSide& a, const ConvInSide& b, int N, int relu, cudaStream_t st) {
   static int blocks_per_sm = 0;
   static int smem_set = 0;
   const int smem = N * 36 + kMmaRows * 32;
@@ -179,12 +203,31 @@ int launch_mma(const int32_t* ptr, const int32_t* idx, const float* val, int32_t
     LPGNN_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kMmaThreads, smem));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
   }
-  const int tiles = ceil_div(rows, kMmaRows);       // blocks needed if every warp took one 16-row tile
+  // blocks needed if every warp took one 16-row tile, capped by the co-resident grid; a pair shares the cap in
+  // proportion to the sides' rows (every warp of either side then walks the same number of tiles)
   const int cap = sm_count() * blocks_per_sm;
-  kern<<<tiles < cap ? tiles : cap, kMmaThreads, smem, st>>>(ptr, idx, val, rows, Xsrc, Xdst, W_rel, b_rel, W_root, N,
-                                                             reinterpret_cast<T*>(out), relu, reinterpret_cast<T*>(z16));
+  int ta = ceil_div(a.rows, kMmaRows), tb = ceil_div(b.rows, kMmaRows);
+  if (ta + tb > cap) {
+    const int64_t total = (int64_t)a.rows + b.rows;
+    int ca = tb == 0 ? cap : (int)((int64_t)cap * a.rows / total);
+    if (ta > 0 && ca < 1) ca = 1;
+    if (tb > 0 && ca > cap - 1) ca = cap - 1;
+    const int cb = cap - ca;
+    ta = ta < ca ? ta : ca;
+    tb = tb < cb ? tb : cb;
+  }
+  if (ta + tb == 0) return LPGNN_OK;
+  kern<<<ta + tb, kMmaThreads, smem, st>>>(a, b, ta, N, relu);
   LPGNN_LAUNCH_OK();
   count_launches(1);
+  return LPGNN_OK;
+}
+
+int check_side(const ConvInSide& s, const char* who) {
+  // (idx / val may be null for a graph without entries: they are only read inside non-empty rows)
+  LPGNN_REQUIRE(s.ptr && s.Xsrc && s.Xdst && s.W_rel && s.W_root && s.out, "%s: null pointer", who);
+  LPGNN_REQUIRE((uintptr_t)s.Xsrc % 4 == 0 && (uintptr_t)s.Xdst % 4 == 0 && (uintptr_t)s.out % 16 == 0 && (uintptr_t)s.z16 % 16 == 0,
+                "%s: misaligned pointer (out / z16 need 16 bytes)", who);
   return LPGNN_OK;
 }
 
@@ -200,13 +243,32 @@ extern "C" int lpgnn_conv_in_16(const int32_t* ptr, const int32_t* idx, const fl
   LPGNN_REQUIRE(rows >= 0 && N > 0 && N % 32 == 0 && N <= 4096, "conv_in_16: rows=%d, N=%d (N must be a multiple of 32, <= 4096)", rows, N);
   LPGNN_REQUIRE(is_16bit(out_dtype), "conv_in_16: out dtype %d is not a 16-bit type", out_dtype);
   if (rows == 0) return LPGNN_OK;
-  // (idx / val may be null for a graph without entries: they are only read inside non-empty rows)
-  LPGNN_REQUIRE(ptr && Xsrc && Xdst && W_rel && W_root && out, "conv_in_16: null pointer");
-  LPGNN_REQUIRE((uintptr_t)Xsrc % 4 == 0 && (uintptr_t)Xdst % 4 == 0 && (uintptr_t)out % 16 == 0 && (uintptr_t)z16 % 16 == 0,
-                "conv_in_16: misaligned pointer (out / z16 need 16 bytes)");
+  const ConvInSide a{ptr, idx, val, rows, Xsrc, Xdst, W_rel, b_rel, W_root, out, z16};
+  if (int rc = check_side(a, "conv_in_16")) return rc;
+  const ConvInSide none{};
   const int relu = (epilogue & LPGNN_EPI_RELU) ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (out_dtype == LPGNN_F16)
-    return launch_mma<__half>(ptr, idx, val, rows, Xsrc, Xdst, W_rel, b_rel, W_root, N, out, relu, z16, st);
-  return launch_mma<__nv_bfloat16>(ptr, idx, val, rows, Xsrc, Xdst, W_rel, b_rel, W_root, N, out, relu, z16, st);
+  if (out_dtype == LPGNN_F16) return launch_mma<__half>(a, none, N, relu, st);
+  return launch_mma<__nv_bfloat16>(a, none, N, relu, st);
+}
+
+extern "C" int lpgnn_conv_in_16_pair(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* colptr,
+                                     const int32_t* row_csc, const float* val_csc, int32_t m, int32_t n, const float* x_s,
+                                     const float* x_t, const float* l2r_wrel, const float* l2r_b, const float* l2r_wroot,
+                                     const float* r2l_wrel, const float* r2l_b, const float* r2l_wroot, int32_t N,
+                                     void* out_s, void* out_t, int out_dtype, int epilogue, void* z16_s, void* z16_t,
+                                     lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(m >= 0 && n >= 0 && N > 0 && N % 32 == 0 && N <= 4096,
+                "conv_in_16_pair: m=%d, n=%d, N=%d (N must be a multiple of 32, <= 4096)", m, n, N);
+  LPGNN_REQUIRE(is_16bit(out_dtype), "conv_in_16_pair: out dtype %d is not a 16-bit type", out_dtype);
+  // variables side: destination = variables (CSC view), sources = constraints; constraints side: the CSR view
+  ConvInSide t{colptr, row_csc, val_csc, n, x_s, x_t, l2r_wrel, l2r_b, l2r_wroot, out_t, z16_t};
+  ConvInSide s{rowptr, col, val, m, x_t, x_s, r2l_wrel, r2l_b, r2l_wroot, out_s, z16_s};
+  if (n > 0) { if (int rc = check_side(t, "conv_in_16_pair")) return rc; } else { t = ConvInSide{}; }
+  if (m > 0) { if (int rc = check_side(s, "conv_in_16_pair")) return rc; } else { s = ConvInSide{}; }
+  const int relu = (epilogue & LPGNN_EPI_RELU) ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == LPGNN_F16) return launch_mma<__half>(t, s, N, relu, st);
+  return launch_mma<__nv_bfloat16>(t, s, N, relu, st);
 }

@@ -191,10 +191,16 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
   LPGNN_FORK();
   // ---- conv1 (+relu).  CSC view: dst = variables, src = constraints; CSR view: dst = constraints, src = variables
   if (bf16 && p == 8 && q == 8 && H % 32 == 0 && H <= 4096) {   // the reference's shape: one kernel per direction
-    LPGNN_TRY(lpgnn_conv_in_16(B.colptr, B.row_csc, B.val_csc, n, x_s, x_t, w->c1_l2r_wrel, w->c1_l2r_b, w->c1_l2r_wroot, H,
-                               right, dt, LPGNN_EPI_RELU, nullptr, stream));
-    LPGNN_TRY(lpgnn_conv_in_16(B.rowptr, B.col, B.val, m, x_t, x_s, w->c1_r2l_wrel, w->c1_r2l_b, w->c1_r2l_wroot, H, left, dt,
-                               LPGNN_EPI_RELU, nullptr, st2));
+    if (fork) {   // small LPs: the sides run next to each other on two streams
+      LPGNN_TRY(lpgnn_conv_in_16(B.colptr, B.row_csc, B.val_csc, n, x_s, x_t, w->c1_l2r_wrel, w->c1_l2r_b, w->c1_l2r_wroot, H,
+                                 right, dt, LPGNN_EPI_RELU, nullptr, stream));
+      LPGNN_TRY(lpgnn_conv_in_16(B.rowptr, B.col, B.val, m, x_t, x_s, w->c1_r2l_wrel, w->c1_r2l_b, w->c1_r2l_wroot, H, left, dt,
+                                 LPGNN_EPI_RELU, nullptr, st2));
+    } else {      // one launch for both directions
+      LPGNN_TRY(lpgnn_conv_in_16_pair(B.rowptr, B.col, B.val, B.colptr, B.row_csc, B.val_csc, m, n, x_s, x_t, w->c1_l2r_wrel,
+                                      w->c1_l2r_b, w->c1_l2r_wroot, w->c1_r2l_wrel, w->c1_r2l_b, w->c1_r2l_wroot, H, left, right,
+                                      dt, LPGNN_EPI_RELU, nullptr, nullptr, stream));
+    }
   } else if (bf16) {
     LPGNN_TRY(lpgnn_gather_cat_ex(B.colptr, B.row_csc, B.val_csc, n, x_s, p, x_t, q, nullptr, B.zb_t, dt, stream));
     LPGNN_TRY(lpgnn_gather_cat_ex(B.rowptr, B.col, B.val, m, x_t, q, x_s, p, nullptr, B.zb_s, dt, st2));

@@ -226,12 +226,11 @@ extern "C" int lpgnn_train_forward(const lpgnn_gcn_fc_weights* w, const int32_t*
   }
   // conv1 (+relu)
   if (bf16 && p == 8 && q == 8 && H % 32 == 0 && H <= 4096) {
-    // the reference's shape: aggregate + transform + ReLU + store in one kernel per direction; zb = [z | 1 | 0] bf16 is the
+    // the reference's shape: aggregate + transform + ReLU + store of both directions in one kernel; zb = [z | 1 | 0] bf16 is the
     // operand of the layer's weight gradient (lpgnn_wgrad below)
-    LPGNN_TRY(lpgnn_conv_in_16(colptr, row_csc, val_csc, n, x_s, x_t, w->c1_l2r_wrel, w->c1_l2r_b, w->c1_l2r_wroot, H, B.right[0],
-                               dt, LPGNN_EPI_RELU, B.zb_t, stream));
-    LPGNN_TRY(lpgnn_conv_in_16(rowptr, col, val, m, x_t, x_s, w->c1_r2l_wrel, w->c1_r2l_b, w->c1_r2l_wroot, H, B.left[0], dt,
-                               LPGNN_EPI_RELU, B.zb_s, stream));
+    LPGNN_TRY(lpgnn_conv_in_16_pair(rowptr, col, val, colptr, row_csc, val_csc, m, n, x_s, x_t, w->c1_l2r_wrel, w->c1_l2r_b,
+                                    w->c1_l2r_wroot, w->c1_r2l_wrel, w->c1_r2l_b, w->c1_r2l_wroot, H, B.left[0], B.right[0], dt,
+                                    LPGNN_EPI_RELU, B.zb_s, B.zb_t, stream));
   } else if (bf16) {
     LPGNN_REQUIRE(p + q <= 64, "train_forward: bf16 input layer needs p + q <= 64");
     wcat_kernel<<<dim3((H * 64 + 255) / 256, 2), 256, 0, st>>>(

@@ -76,6 +76,35 @@ def conv_in_16(view, x_src, x_dst, w_rel, b_rel, w_root, out_dtype, relu=True, w
     return out, z16
 
 
+def conv_in_16_pair(csr, csc, x_s, x_t, l2r, r2l, out_dtype, relu=True, want_z16=False):
+    """Both directions of conv1 in ONE launch (``lpgnn_conv_in_16_pair``).  ``csr`` / ``csc`` = the two views of the
+    graph, ``l2r`` / ``r2l`` = ``(w_rel, b_rel, w_root)`` of the two GraphConvs.  Returns
+    ``(left[m,N], right[n,N], z16_s | None, z16_t | None)``, bit-identical to two ``conv_in_16`` calls."""
+    rowptr, col, val, m = csr
+    colptr, row_csc, val_csc, n = csc
+    require_cuda(rowptr, colptr, x_s, x_t, *l2r, *r2l)
+    x_s, x_t = _contig(x_s.float()), _contig(x_t.float())
+    l2r = [_contig(t.float()) for t in l2r]
+    r2l = [_contig(t.float()) for t in r2l]
+    if x_s.shape[1] != 8 or x_t.shape[1] != 8:
+        raise ValueError("conv_in_16_pair covers the reference's 8 + 8 input features")
+    N = l2r[0].shape[0]
+    dev = x_s.device
+    left = torch.empty((m, N), dtype=out_dtype, device=dev)
+    right = torch.empty((n, N), dtype=out_dtype, device=dev)
+    z_s = torch.empty((m, 64), dtype=out_dtype, device=dev) if want_z16 else None
+    z_t = torch.empty((n, 64), dtype=out_dtype, device=dev) if want_z16 else None
+    with torch.cuda.device(dev):
+        rc = _lib.load().lpgnn_conv_in_16_pair(rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), colptr.data_ptr(),
+                                               row_csc.data_ptr(), val_csc.data_ptr(), m, n, x_s.data_ptr(), x_t.data_ptr(),
+                                               l2r[0].data_ptr(), l2r[1].data_ptr(), l2r[2].data_ptr(), r2l[0].data_ptr(),
+                                               r2l[1].data_ptr(), r2l[2].data_ptr(), N, left.data_ptr(), right.data_ptr(),
+                                               dtype_code(out_dtype), EPI_RELU if relu else EPI_NONE, ptr(z_s), ptr(z_t),
+                                               stream_ptr())
+    check(rc, "lpgnn_conv_in_16_pair")
+    return left, right, z_s, z_t
+
+
 def gather_cat(view, x_src, x_dst, want_f32=True, want_bf16=False, dtype16=torch.bfloat16):
     """``z = [A_view @ x_src | x_dst | 0]``: fp32 ``[rows,KT]`` and/or 16-bit ``[rows,64]`` (``dtype16``: bf16 or
     half; input of the tensor-core transform in the 16-bit modes)."""

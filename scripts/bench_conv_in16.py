@@ -1,4 +1,4 @@
-"""Input layer in the 16-bit modes (lpgnn_conv_in_16) on a C2-shaped LP: both directions, time and fraction of the write roofline."""
+"""Input layer in the 16-bit modes (lpgnn_conv_in_16 / lpgnn_conv_in_16_pair) on a C2-shaped LP: both directions, time and fraction of the write roofline."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -27,7 +27,11 @@ w = lambda p: p.detach()
 for dt in (torch.float16, torch.bfloat16):
     ft = lambda: ops.conv_in_16(csc, xs, xt, w(c1.left2right.lin_rel.weight), w(c1.left2right.lin_rel.bias), w(c1.left2right.lin_root.weight), dt)
     fs = lambda: ops.conv_in_16(csr, xt, xs, w(c1.right2left.lin_rel.weight), w(c1.right2left.lin_rel.bias), w(c1.right2left.lin_root.weight), dt)
-    tt, ts_ = timeit(ft), timeit(fs)
+    l2r = (w(c1.left2right.lin_rel.weight), w(c1.left2right.lin_rel.bias), w(c1.left2right.lin_root.weight))
+    r2l = (w(c1.right2left.lin_rel.weight), w(c1.right2left.lin_rel.bias), w(c1.right2left.lin_root.weight))
+    fp = lambda: ops.conv_in_16_pair(csr, csc, xs, xt, l2r, r2l, dt)
+    tt, ts_, tp = timeit(ft), timeit(fs), timeit(fp)
     by = (lp.m + lp.n) * 1024 * 2
+    print(f"{dt}: both directions in ONE launch {tp*1e3:.1f} us = {by/tp/1e6:.0f} GB/s written ({by/tp/1e6/6538.9:.2f})", flush=True)
     print(f"{dt}: vars side {tt*1e3:.1f} us, cons side {ts_*1e3:.1f} us, pair {1e3*(tt+ts_):.1f} us = {by/(tt+ts_)/1e6:.0f} GB/s written "
           f"({by/(tt+ts_)/1e6/6538.9:.2f} of the measured copy bandwidth)", flush=True)

@@ -16,6 +16,37 @@ __global__ void store_kernel(uint4* out, size_t n16) {
   }
 }
 
+// The input layer's store patterns: a warp owns 16-row tiles of a [rows, 1024] 16-bit matrix (2 KB per row).
+//   HALF = true : per 32-column chunk two stores of 8 rows x 64 B (lane (g,t): row g / g+8, bytes 64c + 16t) -- every
+//                 128-byte line is written by two different instructions (what mma.sync's accumulator layout gives)
+//   HALF = false: per 64-column chunk four stores of 4 rows x 128 B (full lines per instruction)
+template <bool HALF>
+__global__ void tile_store_kernel(uint8_t* out, int rows) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const uint4 v = make_uint4(threadIdx.x, blockIdx.x, 3u, 4u);
+  const long warps = (long)gridDim.x * (blockDim.x >> 5);
+  for (long row0 = ((long)blockIdx.x * (blockDim.x >> 5) + warp) * 16; row0 < rows; row0 += warps * 16) {
+    if (HALF) {
+      uint8_t* ra = out + (row0 + g) * 2048 + 16 * t;
+      uint8_t* rb = ra + 8 * 2048;
+#pragma unroll 2
+      for (int c = 0; c < 32; ++c) {
+        if (row0 + g < rows) *reinterpret_cast<uint4*>(ra + 64 * c) = v;
+        if (row0 + g + 8 < rows) *reinterpret_cast<uint4*>(rb + 64 * c) = v;
+      }
+    } else {
+      uint8_t* r0 = out + (row0 + (lane >> 3)) * 2048 + 16 * (lane & 7);
+#pragma unroll 2
+      for (int c = 0; c < 16; ++c) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (row0 + (lane >> 3) + 4 * k < rows) *reinterpret_cast<uint4*>(r0 + (long)k * 4 * 2048 + 128 * c) = v;
+      }
+    }
+  }
+}
+
 // each CTA fills a 16 KB shared tile once, then streams it to consecutive 16 KB chunks of the output with bulk stores
 __global__ void tma_store_kernel(uint8_t* out, size_t bytes) {
   extern __shared__ __align__(128) uint8_t tile[];
@@ -42,7 +73,7 @@ int main() {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   cudaFuncSetAttribute(tma_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384);
-  for (int mode = 0; mode < 5; ++mode) {
+  for (int mode = 0; mode < 7; ++mode) {
     for (int grid_mult : {2, 8, 32}) {
       float best = 1e9f;
       for (int rep = 0; rep < 6; ++rep) {
@@ -54,13 +85,16 @@ int main() {
         if (mode == 2) store_kernel<2><<<grid, 256>>>((uint4*)buf, bytes / 16);
         if (mode == 3) tma_store_kernel<<<grid, 128, 16384>>>(buf, bytes);
         if (mode == 4) cudaMemsetAsync(buf, 7, bytes);
+        if (mode == 5) tile_store_kernel<true><<<sms * 4, 256>>>(buf, 100000);
+        if (mode == 6) tile_store_kernel<false><<<sms * 4, 256>>>(buf, 100000);
         cudaEventRecord(b); cudaEventSynchronize(b);
         float ms; cudaEventElapsedTime(&ms, a, b);
         if (rep > 0 && ms < best) best = ms;
       }
-      const char* names[] = {"st.global.v4", "st.global.cs.v4", "st.global.L1::no_allocate.v4", "TMA bulk store 16 KB", "cudaMemsetAsync"};
+      const char* names[] = {"st.global.v4", "st.global.cs.v4", "st.global.L1::no_allocate.v4", "TMA bulk store 16 KB", "cudaMemsetAsync",
+                             "16-row tiles, 8 rows x 64 B", "16-row tiles, 4 rows x 128 B"};
       printf("%-30s grid %4d x SMs: %7.1f us  %6.0f GB/s\n", names[mode], grid_mult, best * 1e3f, bytes / best / 1e6f);
-      if (mode == 4) break;
+      if (mode >= 4) break;
     }
   }
   cudaError_t e = cudaDeviceSynchronize();

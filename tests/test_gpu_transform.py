@@ -142,6 +142,31 @@ def test_conv_in_16_one_kernel_input_layer(cuda, hids, dt, m, n, z):
             assert torch.equal(zb, z16)
 
 
+@pytest.mark.parametrize("hids", [32, 1024])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("m,n,z", [(700, 1300, 6000), (1, 3, 2), (129, 255, 0), (3, 40_000, 90_000), (60_000, 110_000, 500_000)])
+def test_conv_in_16_pair_equals_two_single_launches(cuda, hids, dt, m, n, z):
+    """lpgnn_conv_in_16_pair (both directions in one launch, blocks split between the sides) == two lpgnn_conv_in_16
+    launches, bit for bit, outputs and weight-gradient operands; sizes below and above the co-resident grid, lopsided sides."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    from lpgnn_b200.graph import BipartiteCSR
+    row, col, val = make_graph_arrays(m, n, z, 11)
+    g = BipartiteCSR.from_coo_arrays(row, col, val, m, n, cuda)
+    rng = np.random.default_rng(hids + n)
+    t = lambda *shape: torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).to(cuda)
+    x_s, x_t = t(m, 8), t(n, 8)
+    l2r, r2l = (t(hids, 8), t(hids), t(hids, 8)), (t(hids, 8), t(hids), t(hids, 8))
+    csr, csc = g.views()
+    for want_z in (False, True):
+        right, z_t = ops.conv_in_16(csc, x_s, x_t, *l2r, dt, relu=True, want_z16=want_z)
+        left, z_s = ops.conv_in_16(csr, x_t, x_s, *r2l, dt, relu=True, want_z16=want_z)
+        pl, pr, pz_s, pz_t = ops.conv_in_16_pair(csr, csc, x_s, x_t, l2r, r2l, dt, relu=True, want_z16=want_z)
+        assert torch.equal(pl, left) and torch.equal(pr, right)
+        if want_z:
+            assert torch.equal(pz_s, z_s) and torch.equal(pz_t, z_t)
+
+
 @pytest.mark.parametrize("M,N,K", [(1000, 1024, 1024), (129, 128, 128), (5000, 64, 64), (300, 512, 256)])
 @pytest.mark.parametrize("want_out", [False, True])
 def test_transform_with_fused_head(cuda, M, N, K, want_out):
