@@ -670,16 +670,15 @@ def kernel_rooflines(model, lp, dev, peaks, bf16, args):
     w = lambda p: p.detach()
     # input layer, variables side (rows = n): gather [A^T x_s | x_t] then the transform
     if bf16:
-        # input layer, one kernel per direction (aggregate + 16-wide MMA + bias + ReLU + 16-bit store); HBM-bound on the
-        # output write (a pure write stream of this size runs at ~5.8 TB/s on this part, scripts/bench_store.cu)
-        f_in = lambda: ops.conv_in_16(csc, xs, xt, w(c1.left2right.lin_rel.weight), w(c1.left2right.lin_rel.bias),
-                                      w(c1.left2right.lin_root.weight), dt, relu=True)[0]
-        f_in_s = lambda: ops.conv_in_16(csr, xt, xs, w(c1.right2left.lin_rel.weight), w(c1.right2left.lin_rel.bias),
-                                        w(c1.right2left.lin_root.weight), dt, relu=True)[0]
-        t = time_kernel(f_in, reps, flush) + time_kernel(f_in_s, reps, flush)
-        add("conv_in_16 pair (input layer: gather + MMA + ReLU + store, both sides)", "hbm", t,
-            (m + n) * H * s + 2 * (m + n) * 8 * 4 + 2 * z * 8 + (m + n + 2) * 4, 2)
-        right, left = f_in(), f_in_s()
+        # input layer, ONE kernel for both directions (aggregate + 16-wide MMA + bias + ReLU + 16-bit store); HBM-bound on
+        # the output write (a pure write stream of this size runs at ~5.8 TB/s on this part, scripts/bench_store.cu)
+        l2r_w = (w(c1.left2right.lin_rel.weight), w(c1.left2right.lin_rel.bias), w(c1.left2right.lin_root.weight))
+        r2l_w = (w(c1.right2left.lin_rel.weight), w(c1.right2left.lin_rel.bias), w(c1.right2left.lin_root.weight))
+        f_pair = lambda: ops.conv_in_16_pair(csr, csc, xs, xt, l2r_w, r2l_w, dt, relu=True)
+        t = time_kernel(f_pair, reps, flush)
+        add("conv_in_16_pair (input layer: gather + MMA + ReLU + store, both sides, one launch)", "hbm", t,
+            (m + n) * H * s + 2 * (m + n) * 8 * 4 + 2 * z * 8 + (m + n + 2) * 4, 1)
+        left, right = f_pair()[:2]
     elif args.precision == "fp32" and len(model.layers):
         # fp32 on the tensor cores: the input layer writes fp32 (gather source of the aggregation) + x2 operands (hi / lo halves)
         f_in = lambda: ops.conv_in_fused_x2(csc, xs, xt, w(c1.left2right.lin_rel.weight), w(c1.left2right.lin_rel.bias),
