@@ -208,6 +208,10 @@ LPGNN_API int lpgnn_conv_in_16_pair(const int32_t* rowptr, const int32_t* col, c
                           const float* r2l_wrel, const float* r2l_b, const float* r2l_wroot, int32_t N,
                           void* out_s, void* out_t, int out_dtype, int epilogue, void* z16_s, void* z16_t,
                           lpgnn_stream_t stream);
+/* Tuning knob (process-wide): inputs of at least 2 x SM-count batches of 128 rows with N in {256, 512, 768, 1024} take a
+ * warp-specialised form of the kernel (B fragments in registers, producer warps gathering the next batch) -- default on;
+ * enable = 0 keeps every size on the shared-memory-B kernel.  Bit-identical results.  Returns the previous setting. */
+LPGNN_API int lpgnn_set_conv_in_regb(int enable);
 
 /* ---------------------------------------------------------------------------------------------
  * (a3) Dense node transform of a hidden GraphConv layer.  Replaces lin_rel(agg) + lin_root(x_dst)

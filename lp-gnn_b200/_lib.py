@@ -71,6 +71,7 @@ SIGNATURES = {
     "lpgnn_gather_cat": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p]),
     "lpgnn_conv_in_fused": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p, _i32, _p, _int, _int, _p, _p]),
     "lpgnn_conv_in_16": (_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _int, _int, _p, _p]),
+    "lpgnn_set_conv_in_regb": (_int, [_int]),
     "lpgnn_conv_in_16_pair": (_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _int, _int,
                                      _p, _p, _p]),
     "lpgnn_node_transform": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _int, _int, _p]),

@@ -142,9 +142,10 @@ def test_conv_in_16_one_kernel_input_layer(cuda, hids, dt, m, n, z):
             assert torch.equal(zb, z16)
 
 
-@pytest.mark.parametrize("hids", [32, 1024])
+@pytest.mark.parametrize("hids", [32, 256, 768, 1024])
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("m,n,z", [(700, 1300, 6000), (1, 3, 2), (129, 255, 0), (3, 40_000, 90_000), (60_000, 110_000, 500_000)])
+@pytest.mark.parametrize("m,n,z", [(700, 1300, 6000), (1, 3, 2), (129, 255, 0), (3, 40_000, 90_000), (60_000, 110_000, 500_000),
+                                   (37_999, 5, 40_000)])
 def test_conv_in_16_pair_equals_two_single_launches(cuda, hids, dt, m, n, z):
     """lpgnn_conv_in_16_pair (both directions in one launch, blocks split between the sides) == two lpgnn_conv_in_16
     launches, bit for bit, outputs and weight-gradient operands; sizes below and above the co-resident grid, lopsided sides."""
@@ -165,6 +166,16 @@ def test_conv_in_16_pair_equals_two_single_launches(cuda, hids, dt, m, n, z):
         assert torch.equal(pl, left) and torch.equal(pr, right)
         if want_z:
             assert torch.equal(pz_s, z_s) and torch.equal(pz_t, z_t)
+        # large inputs with N in {256, ..., 1024} take the warp-specialised register-B kernel: same bits as the other one
+        from lpgnn_b200 import _lib
+        prev = _lib.load().lpgnn_set_conv_in_regb(0)
+        try:
+            ql, qr, qz_s, qz_t = ops.conv_in_16_pair(csr, csc, x_s, x_t, l2r, r2l, dt, relu=True, want_z16=want_z)
+        finally:
+            _lib.load().lpgnn_set_conv_in_regb(prev)
+        assert torch.equal(ql, pl) and torch.equal(qr, pr)
+        if want_z:
+            assert torch.equal(qz_s, pz_s) and torch.equal(qz_t, pz_t)
 
 
 @pytest.mark.parametrize("M,N,K", [(1000, 1024, 1024), (129, 128, 128), (5000, 64, 64), (300, 512, 256)])
