@@ -101,7 +101,14 @@ LPGNN_API int lpgnn_graph_build(const void* coo_row, const void* coo_col, int id
                       int32_t* csr2csc /*[nnz]*/, int32_t* status /*[1] device, optional*/,
                       void* workspace, size_t workspace_bytes, lpgnn_stream_t stream);
 
-/* Tuning knob (process-wide): a LPGNN_COO_SORTED build runs as the chain of 8 launches (default) or as ONE cooperative
+/* Tuning knob (process-wide): a LPGNN_COO_SORTED build runs as the plain chain (default: 2 + 3 launches per radix pass of
+ * the CSC sort -- 8 at BASELINE C2) or, with enable = 1, as the compact chain (1 + 2 per pass: the preparation kernel
+ * also counts the first digit and the columns, every scatter counts the next pass's digits, the last scatter writes the
+ * CSC payload and colptr; measured no faster on B200, see csrc/graph_build.cu).  Bit-identical outputs.  Returns the
+ * previous setting. */
+LPGNN_API int lpgnn_set_graph_compact(int enable);
+
+/* Tuning knob (process-wide): a LPGNN_COO_SORTED build runs as a chain of launches (default) or as ONE cooperative
  * launch (enable = 1: prep, the radix passes of the CSC sort and the finish, separated by grid-wide barriers; measured no
  * faster on B200, see csrc/graph_build.cu).  Bit-identical outputs.  Returns the previous setting. */
 LPGNN_API int lpgnn_set_graph_fused(int enable);

@@ -62,6 +62,7 @@ SIGNATURES = {
     "lpgnn_graph_build_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "lpgnn_graph_build": (_int, [_p, _p, _int, _p, _i64, _i32, _i32, _int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "lpgnn_set_graph_fused": (_int, [_int]),
+    "lpgnn_set_graph_compact": (_int, [_int]),
     "lpgnn_copy_many_h2d": (_int, [_p, _p, _p, _i32, _p]),
     "lpgnn_pack_scatter": (_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i64, _p, _p, _p, _p, _p, _p]),
     "lpgnn_pack_offsets": (_int, [_p, _p, _i64, _p, _p, _p, _i32, _p]),

@@ -288,6 +288,165 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   radix_scatter_tile(blockIdx.x, keys_in, vals_in, keys_out, vals_out, n, shift, radix_bits, offsets, totals, nblocks);
 }
 
+// ---- sorted-COO path in 1 + 2 * passes launches (was 2 + 3 * passes): the histogram of pass 0 and the per-column counts
+// ride in the preparation kernel, the histogram of pass p + 1 is accumulated by the scatter of pass p (integer atomics on
+// (digit, destination tile) counters: order-free), and the last scatter writes the CSC payload itself while extra blocks
+// of the same launch turn the column counts into colptr (bucket base of the last digit + a block scan inside the bucket).
+// Same ranks as the chain above, so the result is bit-identical (tests/test_gpu_graph_build.py).
+__global__ void __launch_bounds__(kSortThreads)
+prep_hist_kernel(const uint32_t* __restrict__ row, const uint32_t* __restrict__ col, const float* __restrict__ val, int64_t n,
+                 uint32_t m, uint32_t ncols, uint32_t* __restrict__ col_out, float* __restrict__ val_out,
+                 int32_t* __restrict__ rowptr, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                 uint32_t* __restrict__ status, int radix_bits, uint32_t* __restrict__ counts, int nblocks,
+                 uint32_t* __restrict__ colcount) {
+  __shared__ uint32_t h[kMaxRadix];
+  const int radix = 1 << radix_bits;
+  for (int d = threadIdx.x; d < radix; d += kSortThreads) h[d] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * kSortTile;
+#pragma unroll
+  for (int r = 0; r < kSortRounds; ++r) {
+    const int64_t e = base + r * kSortThreads + threadIdx.x;
+    prep_sorted_entry(e, row, col, val, n, m, ncols, col_out, val_out, rowptr, keys, vals, status);
+    if (e < n) {
+      const uint32_t c = col[e];
+      atomicAdd(&h[c & (radix - 1)], 1u);
+      if (c < ncols) atomicAdd(&colcount[c], 1u);
+    }
+  }
+  __syncthreads();
+  if ((int)blockIdx.x < nblocks)
+    for (int d = threadIdx.x; d < radix; d += kSortThreads) counts[(size_t)d * nblocks + blockIdx.x] = h[d];
+}
+
+// scan of the digit rows (as scan_digit_rows_kernel) that also clears the counter table the NEXT scatter accumulates into
+__global__ void __launch_bounds__(kSortThreads)
+scan_digit_rows_zero_kernel(uint32_t* __restrict__ counts, int nblocks, uint32_t* __restrict__ totals,
+                            uint32_t* __restrict__ zero, int64_t zero_words) {
+  for (int64_t i = (int64_t)blockIdx.x * kSortThreads + threadIdx.x; i < zero_words; i += (int64_t)gridDim.x * kSortThreads) zero[i] = 0;
+  scan_digit_row(blockIdx.x, counts, nblocks, totals);
+}
+
+// Stable scatter of one pass (ranks exactly as radix_scatter_tile).  kLast = false: writes the permuted pairs and counts
+// the NEXT pass's digits per destination tile.  kLast = true: blocks [0, nblocks) write the CSC payload of their items,
+// blocks [nblocks, nblocks + radix) write colptr of the columns whose last digit is blockIdx.x - nblocks.
+template <bool kLast>
+__global__ void __launch_bounds__(kSortThreads)
+radix_scatter_fused_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
+                           uint32_t* __restrict__ vals_out, int64_t n, int shift, int radix_bits, const uint32_t* __restrict__ offsets,
+                           const uint32_t* __restrict__ totals, int nblocks, uint32_t* __restrict__ next_counts, int next_bits,
+                           const uint32_t* __restrict__ rows, const float* __restrict__ val, uint32_t* __restrict__ csr2csc,
+                           uint32_t* __restrict__ row_csc, float* __restrict__ val_csc, const uint32_t* __restrict__ colcount,
+                           int32_t* __restrict__ colptr, uint32_t ncols) {
+  constexpr int kWarps = kSortThreads / 32;
+  __shared__ uint32_t goff[kMaxRadix];
+  __shared__ uint32_t dbase[kMaxRadix];
+  __shared__ uint32_t wcnt[kWarps][kMaxRadix];
+  const int radix = 1 << radix_bits;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int bid = blockIdx.x;
+  for (int d = t; d < radix; d += kSortThreads) {
+    dbase[d] = totals[d];
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) wcnt[w][d] = 0;
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of <= 512 totals by one warp, 16 per lane
+    constexpr int kPer = kMaxRadix / 32;
+    uint32_t loc[kPer];
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) { const int d = lane * kPer + j; loc[j] = (d < radix) ? dbase[d] : 0u; s += loc[j]; }
+    uint32_t incl = s;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    uint32_t run = incl - s;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) { const int d = lane * kPer + j; if (d < radix) dbase[d] = run; run += loc[j]; }
+  }
+  __syncthreads();
+  if (kLast && bid >= nblocks) {
+    // ---- colptr of the bucket of last-pass digit g: columns [g << shift, (g + 1) << shift)
+    const uint32_t g = (uint32_t)(bid - nblocks);
+    const uint64_t cbeg = (uint64_t)g << shift, cend = min((uint64_t)(g + 1) << shift, (uint64_t)ncols);
+    if (g == 0 && t == 0) colptr[ncols] = (int32_t)n;
+    uint32_t* wsum = &wcnt[0][0];        // reuse: [kWarps] warp sums + carry
+    uint32_t running = dbase[g];
+    for (uint64_t c0 = cbeg; c0 < cend; c0 += kSortThreads) {
+      const uint64_t c = c0 + t;
+      const uint32_t cnt = (c < cend) ? colcount[c] : 0u;
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
+      }
+      __syncthreads();                   // (previous iteration's readers of wsum are done)
+      if (lane == 31) wsum[warp] = incl;
+      __syncthreads();
+      uint32_t before = running;
+      for (int w = 0; w < warp; ++w) before += wsum[w];
+      if (c < cend) colptr[c] = (int32_t)(before + incl - cnt);
+      uint32_t tot = 0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) tot += wsum[w];
+      running += tot;
+    }
+    return;
+  }
+  for (int d = t; d < radix; d += kSortThreads) goff[d] = dbase[d] + offsets[(size_t)d * nblocks + bid];
+  const int64_t base = (int64_t)bid * kSortTile + warp * (32 * kSortRounds);
+  uint32_t key[kSortRounds], pay[kSortRounds], rank[kSortRounds];
+#pragma unroll
+  for (int r = 0; r < kSortRounds; ++r) {
+    const int64_t i = base + r * 32 + lane;
+    key[r] = 0; pay[r] = 0;
+    if (i < n) { key[r] = keys_in[i]; pay[r] = vals_in[i]; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kSortRounds; ++r) {
+    const bool valid = base + r * 32 + lane < n;
+    const uint32_t digit = valid ? ((key[r] >> shift) & (radix - 1)) : (uint32_t)radix;  // invalid lanes: own class
+    const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+    const uint32_t in_round = __popc(peers & ((1u << lane) - 1));
+    uint32_t before = 0;
+    if (valid) before = wcnt[warp][digit];
+    __syncwarp();
+    if (valid && in_round == 0) wcnt[warp][digit] = before + __popc(peers);
+    __syncwarp();
+    rank[r] = before + in_round;
+  }
+  __syncthreads();
+  for (int d = t; d < radix; d += kSortThreads) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) { const uint32_t c = wcnt[w][d]; wcnt[w][d] = acc; acc += c; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kSortRounds; ++r) {
+    if (base + r * 32 + lane < n) {
+      const uint32_t digit = (key[r] >> shift) & (radix - 1);
+      const uint32_t pos = goff[digit] + wcnt[warp][digit] + rank[r];
+      if (kLast) {
+        const uint32_t p = pay[r];
+        csr2csc[pos] = p;
+        row_csc[pos] = rows[p];
+        val_csc[pos] = val[p];
+      } else {
+        keys_out[pos] = key[r];
+        vals_out[pos] = pay[r];
+        const uint32_t nd = (key[r] >> (shift + radix_bits)) & ((1u << next_bits) - 1);
+        atomicAdd(&next_counts[(size_t)nd * nblocks + pos / kSortTile], 1u);
+      }
+    }
+  }
+}
+
 // ---- sorted-COO path as ONE cooperative launch: prep + the passes of the CSC radix sort + finish, with grid-wide barriers
 // where the chain had kernel boundaries (8 launches of ~7 us each for ~24 MB of traffic at BASELINE C2 size).  Block b
 // owns tile b of every pass (the grid covers all tiles: the caller checks the co-resident capacity); the digit rows of
@@ -357,6 +516,13 @@ int fused_blocks() {
   return cap;
 }
 
+// 1 runs the sorted path in 1 + 2 * passes launches (lpgnn_set_graph_compact; environment LPGNN_GRAPH_COMPACT=1).  Off by
+// default: measured on B200 (ncu launch list of one C2 step) the fused kernels take exactly what their parts took --
+// prep + histogram 12.6 us (6.7 + 4.2), scatter + next histogram 18.0 (13.2 + 4.2), last scatter + payload + colptr 20.5
+// (13.2 + 7.0) -- and with the stream fed ahead the three saved launches hide nothing: C2 1 325 vs 1 334 LPs/s, C5 one call
+// per LP 7.1K vs 7.3K.  Kept as an option (13.6 instead of 16.4 launches per LP) and as a cross-check.
+int g_graph_compact = [] { const char* e = getenv("LPGNN_GRAPH_COMPACT"); return e ? atoi(e) != 0 : 0; }();
+
 struct SortBufs {
   uint32_t *k[2], *v[2];
   uint32_t* counts;
@@ -398,12 +564,13 @@ __global__ void mean_normalize_kernel(const int32_t* __restrict__ ptr, float* __
 using namespace lpgnn;
 
 extern "C" size_t lpgnn_graph_build_workspace_bytes(int64_t nnz, int32_t m, int32_t n) {
-  (void)m; (void)n;
+  (void)m;
   const size_t z = (size_t)(nnz > 0 ? nnz : 1);
   const size_t words = align_up(z, 64);
   const size_t nblocks = (z + kSortTile - 1) / kSortTile;
-  // k0,k1,v0,v1,r32,c32,rows_sorted + counts + digit totals
-  return (7 * words + align_up(kMaxRadix * nblocks, 64) + kMaxRadix + 64) * sizeof(uint32_t) + 256;
+  // k0,k1,v0,v1,r32,c32,rows_sorted + counts + digit totals + [second counter table | per-column counts] (compact sorted path)
+  return (7 * words + 2 * align_up(kMaxRadix * nblocks, 64) + kMaxRadix + 64 + align_up((size_t)(n > 0 ? n : 0) + 2, 64)) *
+             sizeof(uint32_t) + 256;
 }
 
 extern "C" int lpgnn_graph_build(const void* coo_row, const void* coo_col, int idx_is_i64, const float* coo_val,
@@ -474,6 +641,53 @@ extern "C" int lpgnn_graph_build(const void* coo_row, const void* coo_col, int i
                     (void*)&colptr};
     LPGNN_CUDA_OK(cudaLaunchCooperativeKernel((const void*)graph_sorted_fused_kernel, dim3(grid), dim3(kSortThreads), args, 0, st));
     count_launches(launches + 1);
+    return LPGNN_OK;
+  }
+  if ((flags & LPGNN_COO_SORTED) && g_graph_compact) {
+    // Caller asserts row-major order (dataset.py:251-252); CSR arrays = the input, CSC by a stable sort on the column, in
+    // 1 + 2 * passes launches (see prep_hist_kernel / radix_scatter_fused_kernel)
+    const int nblocks = ceil_div(z, kSortTile);
+    const int bits = bits_for(n);
+    const int passes = (bits + kMaxRadixBits - 1) / kMaxRadixBits;
+    const int digit_bits = (bits + passes - 1) / passes;  // <= 9
+    const size_t table = align_up((size_t)kMaxRadix * nblocks, 64);
+    uint32_t* counts2 = b.totals + kMaxRadix + 64;         // second counter table, then the per-column counts
+    uint32_t* colcount = counts2 + table;
+    uint32_t* tab[2] = {b.counts, counts2};
+    LPGNN_CUDA_OK(cudaMemsetAsync(counts2, 0, (table + (size_t)n + 2) * sizeof(uint32_t), st));
+    prep_hist_kernel<<<ceil_div(z + 1, kSortTile), kSortThreads, 0, st>>>(rsrc, csrc, coo_val, z, (uint32_t)m, (uint32_t)n, u_col, val,
+                                                                          rowptr, b.k[0], b.v[0], u_status, digit_bits, tab[0],
+                                                                          nblocks, colcount);
+    launches += 1;
+    int cur = 0;
+    for (int p = 0; p < passes; ++p) {
+      const int shift = p * digit_bits;
+      const bool last = p == passes - 1;
+      // pass p reads table p % 2; the scatter of pass p fills table (p + 1) % 2, cleared by the memset (p = 0) or by the scan of
+      // pass p (it held the counts of pass p - 1, fully consumed by then)
+      if (p >= 1 && !last)
+        scan_digit_rows_zero_kernel<<<1 << digit_bits, kSortThreads, 0, st>>>(tab[p & 1], nblocks, b.totals, tab[(p + 1) & 1],
+                                                                              (int64_t)table);
+      else
+        scan_digit_rows_kernel<<<1 << digit_bits, kSortThreads, 0, st>>>(tab[p & 1], nblocks, b.totals);
+      if (last)
+        radix_scatter_fused_kernel<true><<<nblocks + (1 << digit_bits), kSortThreads, 0, st>>>(
+            b.k[cur], b.v[cur], nullptr, nullptr, z, shift, digit_bits, tab[p & 1], b.totals, nblocks, nullptr, 0, rsrc, coo_val,
+            reinterpret_cast<uint32_t*>(csr2csc), reinterpret_cast<uint32_t*>(row_csc), val_csc, colcount, colptr, (uint32_t)n);
+      else
+        radix_scatter_fused_kernel<false><<<nblocks, kSortThreads, 0, st>>>(
+            b.k[cur], b.v[cur], b.k[cur ^ 1], b.v[cur ^ 1], z, shift, digit_bits, tab[p & 1], b.totals, nblocks, tab[(p + 1) & 1],
+            digit_bits, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0u);
+      cur ^= 1;
+      launches += 2;
+    }
+    if (flags & LPGNN_GRAPH_MEAN) {
+      mean_normalize_kernel<<<ceil_div(m, 256), 256, 0, st>>>(rowptr, val, m);
+      mean_normalize_kernel<<<ceil_div(n, 256), 256, 0, st>>>(colptr, val_csc, n);
+      launches += 2;
+    }
+    LPGNN_LAUNCH_OK();
+    count_launches(launches);
     return LPGNN_OK;
   }
   if (flags & LPGNN_COO_SORTED) {
@@ -601,6 +815,12 @@ extern "C" int lpgnn_pack_offsets(int32_t* row, int32_t* col, int64_t nnz, const
 
 // Tuning knob: 1 = sorted COO inputs are built by ONE cooperative launch, 0 (default) = the launch chain.  Results
 // are bit-identical (same device functions).  Returns the previous setting.
+extern "C" int lpgnn_set_graph_compact(int enable) {
+  const int prev = lpgnn::g_graph_compact;
+  lpgnn::g_graph_compact = enable ? 1 : 0;
+  return prev;
+}
+
 extern "C" int lpgnn_set_graph_fused(int enable) {
   const int prev = lpgnn::g_graph_fused;
   lpgnn::g_graph_fused = enable ? 1 : 0;

@@ -177,27 +177,31 @@ def test_mean_normalised_build_matches_oracle_and_feeds_the_model(cuda):
 @pytest.mark.parametrize("m,n,z,seed", [(5, 7, 12, 0), (1, 1, 1, 1), (3000, 7000, 30_000, 12), (50_000, 100_000, 500_000, 5),
                                          (300, 70_000, 40_000, 3), (70_000, 300, 40_000, 4), (400_000, 900_000, 3_000_000, 8)])
 def test_one_launch_sorted_build_equals_the_launch_chain(cuda, m, n, z, seed):
-    """Sorted COO -> CSR + CSC as one cooperative launch (grid barriers between the radix phases) vs the 8-launch chain:
-    bit-identical outputs, one launch, the same verification of a false sorted claim / out-of-range indices; sizes above
-    the co-resident tile capacity stride over the tiles."""
+    """Sorted COO -> CSR + CSC in its three forms -- the plain chain (default: 2 + 3 launches per radix pass), the compact
+    chain (1 + 2 per pass: histograms and the CSC payload ride in the scatters) and one cooperative launch (grid barriers
+    between the radix phases): bit-identical outputs, the same verification of a false sorted claim / out-of-range
+    indices; sizes above the co-resident tile capacity stride over the tiles."""
     import lpgnn_b200  # noqa: F401
     from lpgnn_b200 import _lib
     from lpgnn_b200.graph import BipartiteCSR
     lib = _lib.load()
     row, col, val = make_graph_arrays(m, n, z, seed, sort=True)
     outs = []
-    for mode in (1, 0):
-        prev = lib.lpgnn_set_graph_fused(mode)
+    for fused, compact, allowed in ((1, 1, (1,)), (0, 0, (5, 8, 11)), (0, 1, (3, 5, 7))):
+        prev_f, prev_c = lib.lpgnn_set_graph_fused(fused), lib.lpgnn_set_graph_compact(compact)
         try:
             torch.cuda.synchronize()
             before = lib.lpgnn_launch_count()
             g = BipartiteCSR.from_coo_arrays(row, col, val, m, n, cuda, is_sorted=True).check()
             launches = lib.lpgnn_launch_count() - before
         finally:
-            lib.lpgnn_set_graph_fused(prev)
+            lib.lpgnn_set_graph_fused(prev_f)
+            lib.lpgnn_set_graph_compact(prev_c)
         outs.append(g)
-        assert launches == 1 if mode else launches in (5, 8, 11), (mode, launches)      # chain: 2 + 3 per radix pass
-    a, b = outs
+        assert launches in allowed, (fused, compact, launches)
+    a, b, c = outs
+    for name in ("rowptr", "col", "val", "colptr", "row_csc", "val_csc", "csr2csc"):
+        assert torch.equal(getattr(c, name), getattr(b, name)), name
     for name in ("rowptr", "col", "val", "colptr", "row_csc", "val_csc", "csr2csc"):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
     _assert_equal(a, port.graph_from_coo(row, col, val, m, n))
