@@ -9,13 +9,16 @@
 // m16n8k16 MMA step per 16 x 8 outputs, so the accumulators can simply live in registers: every warp owns 16 rows,
 //   A fragments  the rows' [aggregate | own features] (16 values, 16-bit), built once per row tile in shared memory
 //   B fragments  [W_rel | W_root] as 16-bit, stored in shared memory in fragment order, one conflict-free 16-byte load
-//                per lane and PAIR of MMAs (the per-chunk shared-memory reads are what the MIO queue throttles on); the
-//                column order inside a 32-column chunk is permuted so that a lane ends up with 8
-//                CONSECUTIVE output features of a row and stores them as one 16-byte word (a warp store = 8 rows x 64 B)
+//                per lane and PAIR of MMAs; the column order inside a 32-column chunk is permuted so that a lane ends
+//                up with 8 CONSECUTIVE output features of a row and stores them as one 16-byte word (a warp store =
+//                8 rows x 64 B)
 //   C = bias     the bias rides in as the accumulator's initial value
 // mma.sync (not tcgen05): TMEM accumulators would have to be drained to registers for the store anyway, which is
-// exactly what bounded the old kernel; there is no K loop to pipeline.  Persistent blocks (weights staged once),
-// 4 blocks per SM so the dependent gather chains of one block hide under the MMA / store phases of the others.
+// exactly what bounded the old kernel; there is no K loop to pipeline.
+// Two kernels: conv_in_mma_kernel (every warp walks its own 16-row tiles, B fragments re-read from shared memory per
+// chunk; persistent blocks, 4 per SM: small inputs and any N % 32 == 0) and conv_in_mma_regb_kernel further down
+// (large inputs, N = 256 .. 1024: B fragments in registers, producer warps gathering ahead).  Same arithmetic in the same
+// order, so their results are bit-identical.
 #include <stdlib.h>
 
 #include "common.cuh"

@@ -142,7 +142,7 @@ def test_conv_in_16_one_kernel_input_layer(cuda, hids, dt, m, n, z):
             assert torch.equal(zb, z16)
 
 
-@pytest.mark.parametrize("hids", [32, 256, 768, 1024])
+@pytest.mark.parametrize("hids", [32, 256, 512, 768, 1024])
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("m,n,z", [(700, 1300, 6000), (1, 3, 2), (129, 255, 0), (3, 40_000, 90_000), (60_000, 110_000, 500_000),
                                    (37_999, 5, 40_000)])
