@@ -345,7 +345,7 @@ def run_gpu(args):
     # ---- the workloads that shard: C3 data-parallel training step, C5 packed sweep (every N, same line)
     if not args.no_train:
         tp = "bf16" if args.precision == "fp16" else ("fp32" if args.precision.startswith("fp32") else args.precision)
-        tr = train_throughput(cfg, lp, dev, tp, max(10, min(args.steps, 50)), 3, world)
+        tr = train_throughput(cfg, lp, dev, tp, args.train_steps or max(10, min(args.steps, 50)), 3, world)
         c1 = workload_spec("C1")
         lp1 = synth.processed_lp(c1["m"], c1["n"], c1["nnz"], seed=c1["seed"] + 1000 * rank, structure=args.structure)
         tr1 = train_throughput(c1, lp1, dev, "fp32", max(10, min(args.steps, 100)), 3, world)
@@ -1008,6 +1008,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--train-steps", type=int, default=0, help="timed steps of the training sub-arm (default: min(steps, 50))")
     ap.add_argument("--sweep-distinct", type=int, default=192, help="C5: distinct LPs materialised per GPU (cycled)")
     ap.add_argument("--sweep-hids", type=int, default=1024)
     ap.add_argument("--sweep-pack", type=int, default=1, help="C5 e2e arm: pack LPs block-diagonally (1) or one call per LP (0)")
