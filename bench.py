@@ -841,7 +841,7 @@ def train_sampled_throughput(cfg, lp, dev, precision, steps, world, seeds_per_ba
                      torch.from_numpy(lp.y_s).to(dev), torch.from_numpy(lp.y_t).to(dev))
     hops = max(cfg["depth"] - 1, 1)          # train.py:108-110: depth - 1 hops for GCN_FC (the last layer is the FC head)
     loader = NeighborSubgraphLoader(res, [fanout] * hops, seeds_per_batch, shuffle=True, drop_last=True, seed=1)
-    sizes = []
+    sizes, stamps = [], []
 
     def run(count):
         done, loss = 0, None
@@ -856,6 +856,7 @@ def train_sampled_throughput(cfg, lp, dev, precision, steps, world, seeds_per_ba
                 allreduce_gradients(params, world)
                 opt.step()
                 sizes.append((batch.x_s.shape[0] + batch.x_t.shape[0], batch.edge_index.nnz()))
+                stamps.append(time.perf_counter())
                 done += 1
                 if done >= count:
                     break
@@ -866,10 +867,15 @@ def train_sampled_throughput(cfg, lp, dev, precision, steps, world, seeds_per_ba
     torch.cuda.synchronize()
     del sizes[:]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    allocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
+    reserved0 = torch.cuda.memory_reserved(dev)
+    del stamps[:]
+    stamps.append(time.perf_counter())
     e0.record()
     loss = run(steps)
     e1.record()
     torch.cuda.synchronize()
+    device_allocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - allocs0
     barrier(world)
     t_ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
     assert bool(torch.isfinite(loss))
@@ -880,6 +886,9 @@ def train_sampled_throughput(cfg, lp, dev, precision, steps, world, seeds_per_ba
                         f"{' + NCCL grad all-reduce' if world > 1 else ''}",
             "precision": precision, "steps": steps, "ms_per_step": t_ms / steps, "minibatches_per_sec": sps,
             "seed_nodes_per_sec": sps * loader.batch_size, "mean_sampled_nodes": nodes, "mean_sampled_nnz": nnz,
+            "cudaMalloc_calls_in_timed_region": int(device_allocs),
+            "reserved_bytes_growth_in_timed_region": int(torch.cuda.memory_reserved(dev) - reserved0),
+            "host_ms_per_step_median_max": [float(np.median(np.diff(stamps)) * 1e3), float(np.max(np.diff(stamps)) * 1e3)],
             "mp_edges_per_sec_fwd_bwd": mp_edges(nnz, cfg["depth"], fwd_bwd=True) * sps}
 
 

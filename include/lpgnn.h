@@ -686,6 +686,14 @@ LPGNN_API int lpgnn_induced_offsets(const int32_t* ptr, const int32_t* idx, cons
 LPGNN_API int lpgnn_induced_fill_sorted(const int32_t* ptr, const int32_t* idx, const float* val, const int32_t* rows,
                               int32_t n_rows, const int32_t* map_other, const int32_t* offsets, int32_t* out_row,
                               int32_t* out_col, float* out_val, lpgnn_stream_t stream);
+/* Node data of the sampled mini-batch in ONE launch (what NeighborLoader's n_id slicing yields, train.py:117-123):
+ * out_xs [mc,p] = x_s[cons_nodes], out_xt [nv,q] = x_t[var_nodes], out_ys / out_yt = int64 labels of those nodes
+ * (y_s, y_t, out_ys, out_yt may all be null), ids_s / ids_t = copies of the node lists (cons_nodes / var_nodes live in
+ * the sampler's reused buffers). */
+LPGNN_API int lpgnn_sample_gather(const float* x_s, const float* x_t, const int64_t* y_s, const int64_t* y_t,
+                        const int32_t* cons_nodes, int32_t mc, const int32_t* var_nodes, int32_t nv, int32_t p,
+                        int32_t q, float* out_xs, float* out_xt, int64_t* out_ys, int64_t* out_yt, int32_t* ids_s,
+                        int32_t* ids_t, lpgnn_stream_t stream);
 
 #ifdef __cplusplus
 }

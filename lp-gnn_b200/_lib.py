@@ -129,6 +129,7 @@ SIGNATURES = {
     "lpgnn_sample_nodes": (_int, [_p, _p, _p, _p, _i32, _i32, _p, _i32, _p, _i32, C.c_uint64, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "lpgnn_induced_offsets": (_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _sz, _p]),
     "lpgnn_induced_fill_sorted": (_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),
+    "lpgnn_sample_gather": (_int, [_p, _p, _p, _p, _p, _i32, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "lpgnn_lp_features_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "lpgnn_lp_features": (_int, [_p] * 11 + [_i64, _i32, _i32] + [_p] * 10 + [_p, _sz, _p]),
     "lpgnn_balanced_ce_workspace_bytes": (_sz, [_i32, _i32]),

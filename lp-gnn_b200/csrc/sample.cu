@@ -415,3 +415,56 @@ extern "C" int lpgnn_induced_fill_sorted(const int32_t* ptr, const int32_t* idx,
   count_launches(1);
   return LPGNN_OK;
 }
+
+// ---- node data of a sampled mini-batch in one launch: feature rows, labels and ids of the sampled constraints and variables
+// (train.py:117-123 reads batch.x_s / x_t / y_s / y_t; PyG's NeighborLoader slices them with n_id)
+namespace lpgnn {
+namespace {
+__global__ void sample_gather_kernel(const float* __restrict__ x_s, const float* __restrict__ x_t, const int64_t* __restrict__ y_s,
+                                     const int64_t* __restrict__ y_t, const int32_t* __restrict__ cons_nodes, int32_t mc,
+                                     const int32_t* __restrict__ var_nodes, int32_t nv, int32_t p, int32_t q,
+                                     float* __restrict__ out_xs, float* __restrict__ out_xt, int64_t* __restrict__ out_ys,
+                                     int64_t* __restrict__ out_yt, int32_t* __restrict__ ids_s, int32_t* __restrict__ ids_t) {
+  const int64_t a = (int64_t)mc * p, b = a + (int64_t)nv * q;
+  const int64_t total = b + mc + nv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < a) {
+      const int32_t r = (int32_t)(i / p), c = (int32_t)(i % p);
+      out_xs[i] = __ldg(x_s + (int64_t)__ldg(cons_nodes + r) * p + c);
+    } else if (i < b) {
+      const int64_t k = i - a;
+      const int32_t r = (int32_t)(k / q), c = (int32_t)(k % q);
+      out_xt[k] = __ldg(x_t + (int64_t)__ldg(var_nodes + r) * q + c);
+    } else if (i < b + mc) {
+      const int32_t r = (int32_t)(i - b);
+      const int32_t node = __ldg(cons_nodes + r);
+      ids_s[r] = node;
+      if (y_s) out_ys[r] = __ldg(y_s + node);
+    } else {
+      const int32_t r = (int32_t)(i - b - mc);
+      const int32_t node = __ldg(var_nodes + r);
+      ids_t[r] = node;
+      if (y_t) out_yt[r] = __ldg(y_t + node);
+    }
+  }
+}
+}  // namespace
+}  // namespace lpgnn
+
+extern "C" int lpgnn_sample_gather(const float* x_s, const float* x_t, const int64_t* y_s, const int64_t* y_t,
+                                   const int32_t* cons_nodes, int32_t mc, const int32_t* var_nodes, int32_t nv, int32_t p,
+                                   int32_t q, float* out_xs, float* out_xt, int64_t* out_ys, int64_t* out_yt, int32_t* ids_s,
+                                   int32_t* ids_t, lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(mc >= 0 && nv >= 0 && p > 0 && q > 0, "sample_gather: bad sizes mc=%d nv=%d p=%d q=%d", mc, nv, p, q);
+  if (mc + nv == 0) return LPGNN_OK;
+  LPGNN_REQUIRE(x_s && x_t && cons_nodes && var_nodes && out_xs && out_xt && ids_s && ids_t, "sample_gather: null pointer");
+  LPGNN_REQUIRE((y_s == nullptr) == (out_ys == nullptr) && (y_t == nullptr) == (out_yt == nullptr), "sample_gather: label pointers must come in pairs");
+  const int64_t total = (int64_t)mc * p + (int64_t)nv * q + mc + nv;
+  const int64_t want = (total + 255) / 256, cap = (int64_t)sm_count() * 16;
+  lpgnn::sample_gather_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+      x_s, x_t, y_s, y_t, cons_nodes, mc, var_nodes, nv, p, q, out_xs, out_xt, out_ys, out_yt, ids_s, ids_t);
+  LPGNN_LAUNCH_OK();
+  count_launches(1);
+  return LPGNN_OK;
+}

@@ -189,19 +189,38 @@ class NeighborSubgraphLoader:
         mc, nv, s_bs, t_bs, z = sz[0], sz[1], sz[2], sz[3], sz[B.sizes_len - 2]
         with torch.cuda.device(dev):
             st = _lib.stream_ptr()
-            cons_nodes, var_nodes = B.cons_nodes[:mc].clone(), B.var_nodes[:nv].clone()
             row = torch.empty(z, dtype=torch.int32, device=dev)
             colo = torch.empty(z, dtype=torch.int32, device=dev)
             v = torch.empty(z, dtype=torch.float32, device=dev)
             if z:
-                _lib.check(lib.lpgnn_induced_fill_sorted(rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), cons_nodes.data_ptr(),
+                _lib.check(lib.lpgnn_induced_fill_sorted(rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), B.cons_nodes.data_ptr(),
                                                          mc, B.map_v.data_ptr(), B.offsets.data_ptr(), row.data_ptr(),
                                                          colo.data_ptr(), v.data_ptr(), st), "lpgnn_induced_fill_sorted")
             sub = BipartiteCSR.from_coo(row, colo, v, mc, nv, is_sorted=True)
-        ci, vi = cons_nodes.long(), var_nodes.long()
-        batch = Data(x_s=lp.x_s[ci], x_t=lp.x_t[vi], edge_index=sub, n_id_s=cons_nodes, n_id_t=var_nodes)
+            # features, labels and node ids of the sampled nodes: one launch (the node lists live in reused buffers)
+            native = (lp.x_s.dtype == torch.float32 and lp.x_t.dtype == torch.float32 and lp.x_s.is_contiguous()
+                      and lp.x_t.is_contiguous() and (lp.y_s is None or (lp.y_s.dtype == torch.int64 and lp.y_t.dtype == torch.int64
+                                                                          and lp.y_s.is_contiguous() and lp.y_t.is_contiguous())))
+            if native:
+                p_, q_ = lp.x_s.shape[1], lp.x_t.shape[1]
+                x_s = torch.empty((mc, p_), dtype=torch.float32, device=dev)
+                x_t = torch.empty((nv, q_), dtype=torch.float32, device=dev)
+                cons_nodes = torch.empty(mc, dtype=torch.int32, device=dev)
+                var_nodes = torch.empty(nv, dtype=torch.int32, device=dev)
+                y_s = torch.empty(mc, dtype=torch.int64, device=dev) if lp.y_s is not None else None
+                y_t = torch.empty(nv, dtype=torch.int64, device=dev) if lp.y_s is not None else None
+                _lib.check(lib.lpgnn_sample_gather(lp.x_s.data_ptr(), lp.x_t.data_ptr(), _lib.ptr(lp.y_s), _lib.ptr(lp.y_t),
+                                                   B.cons_nodes.data_ptr(), mc, B.var_nodes.data_ptr(), nv, p_, q_, x_s.data_ptr(),
+                                                   x_t.data_ptr(), _lib.ptr(y_s), _lib.ptr(y_t), cons_nodes.data_ptr(),
+                                                   var_nodes.data_ptr(), st), "lpgnn_sample_gather")
+            else:
+                cons_nodes, var_nodes = B.cons_nodes[:mc].clone(), B.var_nodes[:nv].clone()
+                ci, vi = cons_nodes.long(), var_nodes.long()
+                x_s, x_t = lp.x_s[ci], lp.x_t[vi]
+                y_s, y_t = (lp.y_s[ci], lp.y_t[vi]) if lp.y_s is not None else (None, None)
+        batch = Data(x_s=x_s, x_t=x_t, edge_index=sub, n_id_s=cons_nodes, n_id_t=var_nodes)
         if lp.y_s is not None:
-            batch.y_s, batch.y_t = lp.y_s[ci], lp.y_t[vi]
+            batch.y_s, batch.y_t = y_s, y_t
         batch.bs = batch.batch_size = ns
         batch.s_bs, batch.t_bs = s_bs, t_bs
         return batch

@@ -178,6 +178,9 @@ class _GCNFCFunction(torch.autograd.Function):
         return (None, None, None, None, None, *grads)
 
 
+_ws_high_water = {}          # device -> bytes requested for the native step's workspace (see _NativeTrainFunction.forward)
+
+
 class _NativeTrainFunction(torch.autograd.Function):
     """The same step through ``lpgnn_train_forward`` / ``lpgnn_train_backward``: two C calls enqueue every
     kernel; activations live in one workspace tensor that the autograd node keeps alive; the parameter
@@ -194,6 +197,13 @@ class _NativeTrainFunction(torch.autograd.Function):
         x_s, x_t = x_s.float().contiguous(), x_t.float().contiguous()
         m, n = x_s.shape[0], x_t.shape[0]
         ws_bytes = lib.lpgnn_train_workspace_bytes(m, n, w.p, w.q, w.hids, w.depth, w.precision)
+        # Sampled mini-batches differ by a few per cent in size: ask the caching allocator for the SAME size every step (a
+        # high-water mark with 6 % headroom when it has to grow), so that a batch slightly larger than all before it reuses
+        # the cached block instead of triggering a multi-GB cudaMalloc in the middle of training.
+        high = _ws_high_water.get(dev, 0)
+        if ws_bytes > high or ws_bytes < high // 2:
+            high = _ws_high_water[dev] = ws_bytes + ws_bytes // 16 if ws_bytes > high else ws_bytes
+        ws_bytes = max(ws_bytes, high)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         logits = torch.empty((m + n, 3), dtype=torch.float32, device=dev)
         dp = cfg["dp"] if cfg["training"] else 0.0
