@@ -765,7 +765,7 @@ def kernel_rooflines(model, lp, dev, peaks, bf16, args):
     t_b2 = time_kernel(lambda: BipartiteCSR.from_coo(h_row, h_col, h_val, m, n, is_sorted=False), reps, flush)
     add("graph_build (unsorted COO->CSR+CSC)", "hbm", t_b2, z * 12 * 2 * 3, -1)
     # measured DRAM traffic per launch from the committed ncu --set full capture (same workload / precision only)
-    for tname in ("r01d_traffic.json", "r01e_traffic.json", "r02_traffic.json"):
+    for tname in ("r02e_traffic.json", "r01d_traffic.json", "r01e_traffic.json"):     # newest capture first
         tpath = os.path.join(ROOT, "profiles", tname)
         if not os.path.isfile(tpath):
             continue
