@@ -329,6 +329,16 @@ LPGNN_API int lpgnn_node_transform_head_ex(const void* A1, int32_t K1, const voi
 /* logits = add_knowledge(sum_p head_partial[p] + b): finishes the fused head (arch.py:190-191). */
 LPGNN_API int lpgnn_head_finish(const float* head_partial, int32_t nparts, int32_t rows, const float* b,
                       const float* feas, int32_t q, float* logits, lpgnn_stream_t stream);
+/* Same, also writing the un-normalised logits (raw_out [rows,3], may be null): what lpgnn_head_mask_bwd needs. */
+LPGNN_API int lpgnn_head_finish_ex(const float* partial, int32_t nparts, int32_t rows, const float* b, const float* feas,
+                         int32_t q, float* logits, float* raw_out, lpgnn_stream_t stream);
+/* Training forward of the LAST hidden layer (bf16): lpgnn_node_transform_ex (ReLU + dropout + 16-bit store) with the head
+ * of lpgnn_node_transform_head accumulated in the same epilogue on the values that are stored, i.e. after dropout
+ * (reference arch.py:186-190: dropout, relu_, lin_left / lin_right).  head_partial as for lpgnn_node_transform_head. */
+LPGNN_API int lpgnn_node_transform_head_train(const void* A1, int32_t K1, const void* W1, const void* A2, int32_t K2,
+                                    const void* W2, const float* bias, int32_t M, int32_t N, void* out,
+                                    const lpgnn_epilogue_args* epi, const float* head_w, float* head_partial,
+                                    lpgnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a4+a5) Basis-status head + knowledge masking.  Replaces torch.nn.Linear(H,3) (reference

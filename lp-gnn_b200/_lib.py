@@ -89,6 +89,8 @@ SIGNATURES = {
     "lpgnn_node_transform_head_parts": (_i32, [_i32]),
     "lpgnn_node_transform_head": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _p, _p, _p]),
     "lpgnn_head_finish": (_int, [_p, _i32, _i32, _p, _p, _i32, _p, _p]),
+    "lpgnn_head_finish_ex": (_int, [_p, _i32, _i32, _p, _p, _i32, _p, _p, _p]),
+    "lpgnn_node_transform_head_train": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, C.POINTER(EpilogueArgs), _p, _p, _p]),
     "lpgnn_head_mask": (_int, [_p, _int, _i32, _i32, _p, _p, _p, _i32, _p, _p, _p]),
     "lpgnn_add_knowledge": (_int, [_p, _i32, _p, _i32, _p, _p]),
     "lpgnn_predict_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32, _i32, _i32, _int]),

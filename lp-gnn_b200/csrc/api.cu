@@ -193,6 +193,31 @@ extern "C" int lpgnn_node_transform_ex(const void* A1, int32_t K1, const void* W
                              nullptr, 1, (cudaStream_t)stream, epx);
 }
 
+// Training forward of the LAST hidden layer: transform + ReLU + dropout + 16-bit store as lpgnn_node_transform_ex, with the
+// basis-status head accumulated in the same epilogue on the values that are stored (after dropout).
+extern "C" int lpgnn_node_transform_head_train(const void* A1, int32_t K1, const void* W1, const void* A2, int32_t K2,
+                                               const void* W2, const float* bias, int32_t M, int32_t N, void* out,
+                                               const lpgnn_epilogue_args* epi, const float* head_w, float* head_partial,
+                                               lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(epi, "node_transform_head_train: null epilogue arguments");
+  LPGNN_REQUIRE(epi->dropout_p >= 0.f && epi->dropout_p < 1.f, "node_transform_head_train: dropout_p=%f outside [0,1)", epi->dropout_p);
+  LPGNN_REQUIRE(M >= 0 && N > 0 && K1 > 0 && K2 >= 0, "node_transform_head_train: bad shape M=%d N=%d K1=%d K2=%d", M, N, K1, K2);
+  if (M == 0) return LPGNN_OK;
+  LPGNN_REQUIRE(A1 && W1 && out && head_w && head_partial, "node_transform_head_train: null pointer");
+  LPGNN_REQUIRE(K2 == 0 || (A2 && W2), "node_transform_head_train: K2=%d but A2/W2 is null", K2);
+  LPGNN_REQUIRE(!epi->mask_act, "node_transform_head_train: the keep-mask epilogue belongs to the backward pass");
+  if (K2 == 0) { A2 = nullptr; W2 = nullptr; }
+  EpiX epx;
+  if (epi->dropout_p > 0.f) {
+    epx.drop_threshold = (uint32_t)((double)epi->dropout_p * 4294967296.0);
+    epx.drop_seed = epi->dropout_seed;
+    epx.out_scale = 1.f / (1.f - epi->dropout_p);
+  }
+  return node_transform_bf16(A1, K1, W1, A2, K2, W2, bias, M, N, out, 0, (epi->epilogue & LPGNN_EPI_RELU) ? 1 : 0, head_w,
+                             head_partial, 1, (cudaStream_t)stream, epx);
+}
+
 // two partial slices per column tile (the tile's columns are drained by two warps per row)
 extern "C" int32_t lpgnn_node_transform_head_parts(int32_t N) { return 2 * (N % 256 == 0 ? N / 256 : (N % 128 == 0 ? N / 128 : N / 64)); }
 

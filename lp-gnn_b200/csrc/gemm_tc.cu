@@ -295,12 +295,27 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
         uint4* srow = reinterpret_cast<uint4*>(my_stage + lane * C::kRowBytes);
         if constexpr (sizeof(OutT) == 2) {
           uint32_t packed[16];
+          // dropout keep bits of this lane's 32 consecutive elements (8 hash quads), applied BEFORE the values are packed
+          // or enter the fused head, so the head sees exactly the activations that are stored
+          uint32_t keep = 0xffffffffu;
+          if constexpr (kEpx) {
+            if (epx.drop_threshold) {
+              const uint64_t q0 = (uint64_t)((row_base + lane) * N + (int64_t)n_blk * BN + pc * 32) >> 2;
+              keep = 0u;
+#pragma unroll
+              for (int qd = 0; qd < 8; ++qd) keep |= (dropout_keep4(epx.drop_seed, q0 + qd, epx.drop_threshold) & 15u) << (4 * qd);
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float v0 = __uint_as_float(r[2 * j]) + bias_s[pc * 32 + 2 * j];
             float v1 = __uint_as_float(r[2 * j + 1]) + bias_s[pc * 32 + 2 * j + 1];
             if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-            if constexpr (kEpx) { v0 *= epx.out_scale; v1 *= epx.out_scale; }
+            if constexpr (kEpx) {
+              v0 *= epx.out_scale; v1 *= epx.out_scale;
+              if (!((keep >> (2 * j)) & 1u)) v0 = 0.f;
+              if (!((keep >> (2 * j + 1)) & 1u)) v1 = 0.f;
+            }
             packed[j] = Half16<OutT>::pack(v0, v1);
             if (kHead && head_w) {
               const int col = pc * 32 + 2 * j;
@@ -341,13 +356,6 @@ gemm_tc_kernel(const __grid_constant__ Segs segs, const float* __restrict__ bias
                 const uint4 a = am[i];
                 v.x &= bf16x2_pos_mask(a.x); v.y &= bf16x2_pos_mask(a.y);
                 v.z &= bf16x2_pos_mask(a.z); v.w &= bf16x2_pos_mask(a.w);
-              }
-              if (kEpx && epx.drop_threshold) {
-                const uint64_t q0 = (uint64_t)(e0 + piece * 8) >> 2;       // this thread's 8 elements = 2 hash quads
-                const uint32_t k0 = dropout_keep4(epx.drop_seed, q0, epx.drop_threshold);
-                const uint32_t k1 = dropout_keep4(epx.drop_seed, q0 + 1, epx.drop_threshold);
-                auto lanes = [](uint32_t two) -> uint32_t { return ((two & 1u) ? 0x0000ffffu : 0u) | ((two & 2u) ? 0xffff0000u : 0u); };
-                v.x &= lanes(k0); v.y &= lanes(k0 >> 2); v.z &= lanes(k1); v.w &= lanes(k1 >> 2);
               }
             }
             uint8_t* dst = reinterpret_cast<uint8_t*>(out_t + e0);

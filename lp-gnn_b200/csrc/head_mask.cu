@@ -194,7 +194,7 @@ __global__ void add_knowledge_kernel(const float* __restrict__ in, int32_t rows,
 
 __global__ void head_finish_kernel(const float* __restrict__ partial, int nparts, int32_t rows,
                                    const float* __restrict__ b, const float* __restrict__ feas, int q,
-                                   float* __restrict__ logits) {
+                                   float* __restrict__ logits, float* __restrict__ raw_out) {
   const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (row >= rows) return;
   float r0 = __ldg(b), r1 = __ldg(b + 1), r2 = __ldg(b + 2);
@@ -202,6 +202,7 @@ __global__ void head_finish_kernel(const float* __restrict__ partial, int nparts
     const float* pp = partial + ((int64_t)p * rows + row) * 3;
     r0 += pp[0]; r1 += pp[1]; r2 += pp[2];
   }
+  if (raw_out) { raw_out[row * 3] = r0; raw_out[row * 3 + 1] = r1; raw_out[row * 3 + 2] = r2; }
   finish_row(r0, r1, r2, feas, q, row, logits);
 }
 
@@ -210,16 +211,21 @@ __global__ void head_finish_kernel(const float* __restrict__ partial, int nparts
 
 using namespace lpgnn;
 
-extern "C" int lpgnn_head_finish(const float* partial, int32_t nparts, int32_t rows, const float* b, const float* feas,
-                                 int32_t q, float* logits, lpgnn_stream_t stream) {
+extern "C" int lpgnn_head_finish_ex(const float* partial, int32_t nparts, int32_t rows, const float* b, const float* feas,
+                                    int32_t q, float* logits, float* raw_out, lpgnn_stream_t stream) {
   if (int rc = check_device()) return rc;
   LPGNN_REQUIRE(rows >= 0 && nparts >= 1 && q >= 3, "head_finish: bad shape rows=%d nparts=%d q=%d", rows, nparts, q);
   if (rows == 0) return LPGNN_OK;
   LPGNN_REQUIRE(partial && b && feas && logits, "head_finish: null pointer");
-  head_finish_kernel<<<ceil_div(rows, 256), 256, 0, (cudaStream_t)stream>>>(partial, nparts, rows, b, feas, q, logits);
+  head_finish_kernel<<<ceil_div(rows, 256), 256, 0, (cudaStream_t)stream>>>(partial, nparts, rows, b, feas, q, logits, raw_out);
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;
+}
+
+extern "C" int lpgnn_head_finish(const float* partial, int32_t nparts, int32_t rows, const float* b, const float* feas,
+                                 int32_t q, float* logits, lpgnn_stream_t stream) {
+  return lpgnn_head_finish_ex(partial, nparts, rows, b, feas, q, logits, nullptr, stream);
 }
 
 extern "C" int lpgnn_head_mask(const void* H, int h_dtype, int32_t rows, int32_t Hdim, const float* W, const float* b,

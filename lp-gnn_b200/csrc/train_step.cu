@@ -256,6 +256,22 @@ extern "C" int lpgnn_train_forward(const lpgnn_gcn_fc_weights* w, const int32_t*
     // reference order is dropout then relu_ (arch.py:186-188); the two commute and both sit in the epilogue
     lpgnn_epilogue_args ea;
     ea.epilogue = LPGNN_EPI_RELU; ea.dropout_p = dropout_p; ea.mask_act = nullptr; ea.mask_scale = 1.f;
+    if (bf16 && li == nh - 1) {
+      // last hidden layer: the basis-status head rides in the transform's epilogue (on the values that are stored, after
+      // dropout), so the stored activation is not read back for it; the partial dot products live in the gradient
+      // buffers of the backward pass (dpre_*: unused until then, >= 12 * nparts bytes per row)
+      const int nparts = lpgnn_node_transform_head_parts(H);
+      float *part_t = reinterpret_cast<float*>(B.dpre_t), *part_s = reinterpret_cast<float*>(B.dpre_s);
+      ea.dropout_seed = seed + 2 * li;
+      LPGNN_TRY(lpgnn_node_transform_head_train(B.agg_t[li], H, wl2r_rel[li], B.right[li], H, wl2r_root[li], w->l2r_b[li], n, H,
+                                                B.right[li + 1], &ea, w->head_right_w, part_t, stream));
+      ea.dropout_seed = seed + 2 * li + 1;
+      LPGNN_TRY(lpgnn_node_transform_head_train(B.agg_s[li], H, wr2l_rel[li], B.left[li], H, wr2l_root[li], w->r2l_b[li], m, H,
+                                                B.left[li + 1], &ea, w->head_left_w, part_s, stream));
+      LPGNN_TRY(lpgnn_head_finish_ex(part_s, nparts, m, w->head_left_b, x_s, p, logits_s, B.raw_s, stream));
+      LPGNN_TRY(lpgnn_head_finish_ex(part_t, nparts, n, w->head_right_b, x_t, q, logits_t, B.raw_t, stream));
+      return LPGNN_OK;
+    }
     ea.dropout_seed = seed + 2 * li;
     LPGNN_TRY(lpgnn_node_transform_ex(B.agg_t[li], H, wl2r_rel[li], B.right[li], H, wl2r_root[li], w->l2r_b[li], n, H,
                                       B.right[li + 1], dt, &ea, stream));

@@ -197,6 +197,39 @@ def node_transform_head(a1, w1, a2, w2, bias, head_w, head_b, feas, relu=True, w
     return logits, out
 
 
+def node_transform_head_train(a1, w1, a2, w2, bias, head_w, head_b, feas, relu=True, dropout=None):
+    """Training forward of the last hidden layer (bf16): ``out = dropout(relu(a1 w1^T + a2 w2^T + bias))`` stored in 16 bits,
+    with the basis-status head accumulated in the same epilogue on the stored (post-dropout) values.  ``dropout=(p, seed)``
+    or None.  Returns ``(out[M,N], logits[M,3], raw[M,3])`` -- ``raw`` = un-normalised logits for ``head_mask_bwd``."""
+    import ctypes as C
+    require_cuda(a1, w1, a2, w2, bias, head_w, head_b, feas)
+    a1, w1, a2, w2 = _contig(a1), _contig(w1), _contig(a2), _contig(w2)
+    bias, head_w, head_b, feas = _contig(bias.float()), _contig(head_w.float()), _contig(head_b.float()), _contig(feas.float())
+    if a1.dtype != torch.bfloat16:
+        raise TypeError("node_transform_head_train: bf16 operands (training mode of the tensor-core path)")
+    M, K1 = a1.shape
+    N, K2 = w1.shape[0], a2.shape[1]
+    lib = _lib.load()
+    nparts = lib.lpgnn_node_transform_head_parts(N)
+    partial = torch.empty((nparts, M, 3), dtype=torch.float32, device=a1.device)
+    out = torch.empty((M, N), dtype=a1.dtype, device=a1.device)
+    logits = torch.empty((M, 3), dtype=torch.float32, device=a1.device)
+    raw = torch.empty((M, 3), dtype=torch.float32, device=a1.device)
+    epi = _lib.EpilogueArgs()
+    epi.epilogue = EPI_RELU if relu else EPI_NONE
+    epi.dropout_p, epi.dropout_seed = (float(dropout[0]), int(dropout[1]) & (2 ** 64 - 1)) if dropout else (0.0, 0)
+    epi.mask_act, epi.mask_scale = None, 1.0
+    with torch.cuda.device(a1.device):
+        rc = lib.lpgnn_node_transform_head_train(a1.data_ptr(), K1, w1.data_ptr(), a2.data_ptr(), K2, w2.data_ptr(),
+                                                 bias.data_ptr(), M, N, out.data_ptr(), C.byref(epi), head_w.data_ptr(),
+                                                 partial.data_ptr(), stream_ptr())
+        check(rc, "lpgnn_node_transform_head_train")
+        rc = lib.lpgnn_head_finish_ex(partial.data_ptr(), nparts, M, head_b.data_ptr(), feas.data_ptr(), feas.shape[1],
+                                      logits.data_ptr(), raw.data_ptr(), stream_ptr())
+    check(rc, "lpgnn_head_finish_ex")
+    return out, logits, raw
+
+
 def _ptr_array(tensors):
     import ctypes as C
     return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])

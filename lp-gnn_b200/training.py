@@ -74,23 +74,34 @@ class _GCNFCFunction(torch.autograd.Function):
             left, z_s = ops.conv_in_fused(csr, x_t, x_s, P[3], P[4], P[5], dt, relu=True)
         saved = [z_s, z_t, left, right]
         scale = 1.0
+        head_done = False
         for i in range(n_layers):
             w = P[6 + 6 * i: 12 + 6 * i]
             agg_t, agg_s = ops.spmm(csc, left), ops.spmm(csr, right)
             # reference order is dropout then relu_ (arch.py:186-188); relu(drop(x)) == drop(relu(x)), and both are
             # fused into the transform's epilogue
             drop = training and dp > 0
-            right_new = ops.node_transform(agg_t, cast(w[0]), right, cast(w[2]), w[1], relu=True,
-                                           dropout=(dp, seed + 2 * i) if drop else None)
-            left_new = ops.node_transform(agg_s, cast(w[3]), left, cast(w[5]), w[4], relu=True,
-                                          dropout=(dp, seed + 2 * i + 1) if drop else None)
+            if dt == torch.bfloat16 and i == n_layers - 1:
+                # last hidden layer, bf16: the head rides in the transform's epilogue (as in the native step)
+                hw = P[6 + 6 * n_layers:]
+                right_new, logit_t, raw_t = ops.node_transform_head_train(agg_t, cast(w[0]), right, cast(w[2]), w[1], hw[2], hw[3],
+                                                                          x_t, relu=True, dropout=(dp, seed + 2 * i) if drop else None)
+                left_new, logit_s, raw_s = ops.node_transform_head_train(agg_s, cast(w[3]), left, cast(w[5]), w[4], hw[0], hw[1],
+                                                                         x_s, relu=True, dropout=(dp, seed + 2 * i + 1) if drop else None)
+                head_done = True
+            else:
+                right_new = ops.node_transform(agg_t, cast(w[0]), right, cast(w[2]), w[1], relu=True,
+                                               dropout=(dp, seed + 2 * i) if drop else None)
+                left_new = ops.node_transform(agg_s, cast(w[3]), left, cast(w[5]), w[4], relu=True,
+                                              dropout=(dp, seed + 2 * i + 1) if drop else None)
             if drop:
                 scale = 1.0 / (1.0 - dp)
             saved += [agg_s, agg_t, left_new, right_new]
             left, right = left_new, right_new
-        hw = P[6 + 6 * n_layers:]
-        logit_s, raw_s = ops.head_mask(left, hw[0], hw[1], x_s, want_raw=True)
-        logit_t, raw_t = ops.head_mask(right, hw[2], hw[3], x_t, want_raw=True)
+        if not head_done:
+            hw = P[6 + 6 * n_layers:]
+            logit_s, raw_s = ops.head_mask(left, hw[0], hw[1], x_s, want_raw=True)
+            logit_t, raw_t = ops.head_mask(right, hw[2], hw[3], x_t, want_raw=True)
         ctx.csr, ctx.csc, ctx.cfg = csr, csc, cfg
         ctx.scale = scale if (training and dp > 0) else 1.0
         ctx.save_for_backward(x_s, x_t, raw_s, raw_t, *saved, *P)
