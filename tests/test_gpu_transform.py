@@ -209,6 +209,42 @@ def test_transform_with_fused_head(cuda, M, N, K, want_out):
         assert torch.equal(out, ref)
 
 
+@pytest.mark.parametrize("M,N,K", [(3000, 1024, 1024), (129, 128, 128), (5000, 64, 64), (40_000, 256, 256)])
+@pytest.mark.parametrize("dp", [0.0, 0.3])
+def test_training_transform_with_fused_head_sees_the_stored_activation(cuda, M, N, K, dp):
+    """Training forward of the last hidden layer: ReLU + dropout + bf16 store with the head accumulated in the same
+    epilogue.  The stored activation is bit-identical to the transform without the head (same keep decisions), the
+    un-normalised logits are the head of exactly that activation (up to its bf16 rounding: the epilogue feeds the fp32
+    values), the final logits are add_knowledge of them, and the drop rate is the requested one."""
+    import lpgnn_b200  # noqa: F401
+    from lpgnn_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    bf = torch.bfloat16
+    a1 = torch.randn(M, K, device=cuda, generator=g).to(bf)
+    a2 = torch.randn(M, K, device=cuda, generator=g).to(bf)
+    w1 = (torch.randn(N, K, device=cuda, generator=g) / K ** 0.5).to(bf)
+    w2 = (torch.randn(N, K, device=cuda, generator=g) / K ** 0.5).to(bf)
+    b = torch.randn(N, device=cuda, generator=g)
+    hw = torch.randn(3, N, device=cuda, generator=g) / N ** 0.5
+    hb = torch.randn(3, device=cuda, generator=g)
+    feas = torch.randint(-1, 2, (M, 8), device=cuda, generator=g).float()
+    drop = (dp, 1234) if dp > 0 else None
+    out, logits, raw = ops.node_transform_head_train(a1, w1, a2, w2, b, hw, hb, feas, relu=True, dropout=drop)
+    ref = ops.node_transform(a1, w1, a2, w2, b, relu=True, dropout=drop)
+    assert torch.equal(out, ref)
+    if dp > 0:
+        pre = ops.node_transform(a1, w1, a2, w2, b, relu=True)
+        kept = (out != 0).sum().item() / max((pre != 0).sum().item(), 1)
+        assert abs(kept - (1 - dp)) < 0.01, kept
+    exp_raw = out.double() @ hw.double().T + hb.double()
+    scale = (out.double().abs() @ hw.double().abs().T + hb.double().abs())
+    assert float(((raw.double() - exp_raw).abs() / scale).max()) < 2.0 ** -8        # bf16 rounding of the stored values
+    exp = torch.nn.functional.normalize(raw.double()) * 10
+    exp[:, 0] -= 10 * (feas[:, 5] != 0)
+    exp[:, 2] -= 10 * (feas[:, 7] != 0)
+    assert float((logits.double() - exp).abs().max()) < 1e-4
+
+
 @pytest.mark.parametrize("M,N,K1,K2", [(1000, 1024, 1024, 1024), (129, 64, 64, 64), (5000, 128, 128, 0), (333, 512, 192, 64)])
 @pytest.mark.parametrize("parts,tol", [(2, 4e-5), (3, 2e-5)])
 def test_transform_fp32_via_split_bf16_tensor_core_passes(cuda, M, N, K1, K2, parts, tol):
