@@ -185,6 +185,37 @@ def test_side_stream_fork_changes_nothing(cuda, precision, hids, depth):
         assert torch.equal(st, base[0]) and torch.equal(lg, base[1])
 
 
+@pytest.mark.parametrize("fork_mode", [0, 2])
+def test_prediction_call_is_cuda_graph_capturable(cuda, fork_mode):
+    """The one-call prediction (graph build + forward + selection, with or without the library's side stream) can be
+    captured into a CUDA graph and replayed: the fork / join events keep the side stream inside the capture."""
+    from lpgnn_b200 import _lib
+    lib = _lib.load()
+    lp, model, ref, g_ref, batch = _setup((2000, 4100, 21000, 9), 256, 3, cuda)
+    model.set_precision("fp16")
+    t = lambda a, dt: torch.from_numpy(a.astype(dt)).to(cuda)
+    coo = (t(lp.row, np.int32), t(lp.col, np.int32), t(lp.a_data, np.float32))
+    prev = lib.lpgnn_set_predict_fork(fork_mode)
+    try:
+        with torch.no_grad():
+            want = model.predict_basis_coo(*coo, lp.m, lp.n, batch.x_s, batch.x_t, is_sorted=True).clone()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):                       # warm-up on a side stream, as torch.cuda.graph asks for
+                model.predict_basis_coo(*coo, lp.m, lp.n, batch.x_s, batch.x_t, is_sorted=True)
+            torch.cuda.current_stream().wait_stream(s)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = model.predict_basis_coo(*coo, lp.m, lp.n, batch.x_s, batch.x_t, is_sorted=True)
+            for _ in range(3):
+                out.zero_()
+                graph.replay()
+                torch.cuda.synchronize()
+                assert torch.equal(out, want)
+    finally:
+        lib.lpgnn_set_predict_fork(prev)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "fp32_simt", "bf16", "fp16"])
 def test_full_size_c2_parity_against_oracle(cuda, precision):
     """BASELINE config C2 at full size (50K x 100K, ~491K nnz, hids 1024, depth 3): logits and statuses of the
