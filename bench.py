@@ -706,14 +706,12 @@ def kernel_rooflines(model, lp, dev, peaks, bf16, args):
         cast = conv._cache.get
         # SpMM pair of one hidden layer: compulsory bytes 2(m+n)Hs + 16z + 4(m+n+2)   
         if args.precision == "fp32":   # fp32 features in, x2 operands out (same bytes per element: 2 + 2)
-            t_s = time_kernel(lambda: ops.spmm_x2(csr, right, sx_t), reps, flush)
-            t_t = time_kernel(lambda: ops.spmm_x2(csc, left, sx_s), reps, flush)
-            add("spmm_x2 pair (A.R and A^T.L, fp32 in, x2 operands out)", "hbm", t_s + t_t,
-                2 * (m + n) * H * s + 16 * z + 4 * (m + n + 2) + 8 * (m + n), 2)
-        else:
-            t_s = time_kernel(lambda: ops.spmm(csr, right), reps, flush)
-            t_t = time_kernel(lambda: ops.spmm(csc, left), reps, flush)
-            add("spmm pair (A.R and A^T.L)", "hbm", t_s + t_t, 2 * (m + n) * H * s + 16 * z + 4 * (m + n + 2), 2)
+            t_p = time_kernel(lambda: ops.spmm_x2_pair(csr, csc, left, right, sx_s, sx_t, nnz=z), reps, flush)
+            add("spmm_x2 pair (A.R and A^T.L, fp32 in, x2 operands out)", "hbm", t_p,
+                2 * (m + n) * H * s + 16 * z + 4 * (m + n + 2) + 8 * (m + n), 1)
+        else:   # both aggregations in one launch (as the step runs them)
+            t_p = time_kernel(lambda: ops.spmm_pair(csr, csc, left, right, nnz=z), reps, flush)
+            add("spmm pair (A.R and A^T.L)", "hbm", t_p, 2 * (m + n) * H * s + 16 * z + 4 * (m + n + 2), 1)
         kernels[-1]["gather_model_bytes"] = 2 * z * H * s + (m + n) * H * s + 16 * z
         agg_t, agg_s = ops.spmm(csc, left), ops.spmm(csr, right)
         l2r, r2l = conv.left2right, conv.right2left

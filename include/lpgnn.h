@@ -306,6 +306,22 @@ LPGNN_API int lpgnn_conv_in_fused_x2(const int32_t* ptr, const int32_t* idx, con
 LPGNN_API int lpgnn_spmm_x2(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const float* X,
                   int32_t F, const float* src_scale, void* hi, void* lo, float* scale, float* scratch,
                   lpgnn_stream_t stream);
+/* Both aggregations of a layer in ONE launch where both take the banded sweep (reference arch.py:71-80: the two
+ * GraphConvs of a GraphConvTwoDirection read the same features): agg_t [n,F] = A^T L over the CSC view, agg_s [m,F] = A R
+ * over the CSR view; each side gets the SMs its work (nnz + rows) asks for (nnz < 0: unknown to the caller, an LP-typical
+ * density is assumed -- it only steers the split).  Other shapes: two lpgnn_spmm calls.  Same
+ * bits either way.  lpgnn_spmm_x2_pair: the same for lpgnn_spmm_x2 (scale_L / scale_R = the sources' row-scale bounds). */
+LPGNN_API int lpgnn_spmm_pair(const int32_t* rowptr, const int32_t* col, const float* val, int32_t m, const int32_t* colptr,
+                    const int32_t* row_csc, const float* val_csc, int32_t n, int64_t nnz, const void* L,
+                    const void* R, void* agg_s, void* agg_t, int32_t F, int dtype, lpgnn_stream_t stream);
+LPGNN_API int lpgnn_spmm_x2_pair(const int32_t* rowptr, const int32_t* col, const float* val, int32_t m,
+                       const int32_t* colptr, const int32_t* row_csc, const float* val_csc, int32_t n, int64_t nnz,
+                       const float* L, const float* R, int32_t F, const float* scale_L, const float* scale_R,
+                       void* hi_s, void* lo_s, float* scale_s, void* hi_t, void* lo_t, float* scale_t,
+                       float* scratch_s, float* scratch_t, lpgnn_stream_t stream);
+/* Tuning knob (process-wide): enable = 0 makes the two pair entry points above always run as two launches (A/B runs);
+ * returns the previous setting. */
+LPGNN_API int lpgnn_set_spmm_pair(int enable);
 /* Tuning knob (process-wide): K-blocks of 64 accumulated inside TMEM before a chunk is added to the fp32 registers
  * (main passes; default 4; the 2^-11-weighted correction passes use 4x that, at least 16).  Returns the previous value. */
 LPGNN_API int lpgnn_set_x2_chunk(int kblocks);

@@ -86,6 +86,9 @@ SIGNATURES = {
     "lpgnn_set_x2_chunk": (_int, [_int]),
     "lpgnn_conv_in_fused_x2": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p, _i32, _p, _int, _p, _p, _p, _p, _p, _p]),
     "lpgnn_spmm_x2": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _p, _p, _p, _p, _p]),
+    "lpgnn_set_spmm_pair": (_int, [_int]),
+    "lpgnn_spmm_pair": (_int, [_p, _p, _p, _i32, _p, _p, _p, _i32, _i64, _p, _p, _p, _p, _i32, _int, _p]),
+    "lpgnn_spmm_x2_pair": (_int, [_p, _p, _p, _i32, _p, _p, _p, _i32, _i64, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "lpgnn_node_transform_head_parts": (_i32, [_i32]),
     "lpgnn_node_transform_head": (_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _int, _p, _p, _p]),
     "lpgnn_head_finish": (_int, [_p, _i32, _i32, _p, _p, _i32, _p, _p]),

@@ -228,11 +228,18 @@ extern "C" int lpgnn_predict_basis_packed(const lpgnn_gcn_fc_weights* w, const i
   for (int li = 0; li < n_hidden; ++li) {
     const bool x2_direct = x2 && li == 0;    // first hidden layer: its inputs (conv1 outputs) already exist as x2 operands
     LPGNN_CROSS();                           // both sides' features of the previous layer are complete (and were consumed)
-    if (x2_direct) {   // aggregate straight into x2 operands (scale from the sources' scales), no fp32 aggregate, no split pass
+    if (x2_direct && !fork) {   // both aggregations in one launch, straight into x2 operands (see below)
+      LPGNN_TRY(lpgnn_spmm_x2_pair(B.rowptr, B.col, B.val, m, B.colptr, B.row_csc, B.val_csc, n, nnz, (const float*)left,
+                                   (const float*)right, H, B.xscale_x[0], B.xscale_x[1], B.xa_hi[0], B.xa_lo[0], B.xscale[0],
+                                   B.xa_hi[1], B.xa_lo[1], B.xscale[1], (float*)B.agg_s, (float*)B.agg_t, stream));
+    } else if (x2_direct) {   // aggregate straight into x2 operands (scale from the sources' scales), no fp32 aggregate, no split pass
       LPGNN_TRY(lpgnn_spmm_x2(B.colptr, B.row_csc, B.val_csc, n, (const float*)left, H, B.xscale_x[0], B.xa_hi[1], B.xa_lo[1],
                               B.xscale[1], (float*)B.agg_t, stream));                          // A^T . left
       LPGNN_TRY(lpgnn_spmm_x2(B.rowptr, B.col, B.val, m, (const float*)right, H, B.xscale_x[1], B.xa_hi[0], B.xa_lo[0],
                               B.xscale[0], (float*)B.agg_s, st2));                             // A   . right
+    } else if (!fork) {       // A^T . left and A . right in one launch where both take the banded sweep
+      LPGNN_TRY(lpgnn_spmm_pair(B.rowptr, B.col, B.val, m, B.colptr, B.row_csc, B.val_csc, n, nnz, left, right, B.agg_s, B.agg_t,
+                                H, dt, stream));
     } else {
       LPGNN_TRY(lpgnn_spmm(B.colptr, B.row_csc, B.val_csc, n, left, B.agg_t, H, dt, stream));    // A^T . left
       LPGNN_TRY(lpgnn_spmm(B.rowptr, B.col, B.val, m, right, B.agg_s, H, dt, st2));              // A   . right

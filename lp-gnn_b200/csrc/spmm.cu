@@ -10,6 +10,8 @@
 // reference CPU kernel), and writes the row once.  (idx,val) pairs are fetched G at a time with
 // one coalesced load and broadcast with shuffles; feature rows are gathered with 128-bit loads,
 // UNROLL neighbours in flight per lane.  HBM/L2-bound: see DESIGN.md for the byte model.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #include <type_traits>
@@ -212,17 +214,30 @@ __device__ __forceinline__ float x2_scale_for_bound(float bound) {   // as in co
   return __int_as_float((uint32_t)(127 + e - 12) << 23);
 }
 
-template <typename T, int CH, int U, bool kX2 = false>
-__global__ void __launch_bounds__(kSweepThreads, 1)
-spmm_sweep_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ val,
-                  int32_t rows, const char* __restrict__ X, char* __restrict__ Y, uint32_t row_bytes,
-                  int32_t nslabs, int32_t rows_per_block, const X2Out x2) {
+// One aggregation: Y[rows, F] = A_view X.  (Both directions of a layer are independent and equally long at LP shapes, so
+// a launch can carry two of them: half of the SMs each, one ramp and one tail instead of two.)
+struct SweepSide {
+  const int32_t* ptr; const int32_t* idx; const float* val; int32_t rows;
+  const char* X; char* Y; int32_t rows_per_block;
+  X2Out x2;
+};
+
+template <typename T, int CH, int U, bool kX2>
+__device__ __forceinline__ void sweep_side(const SweepSide& S, const int side_block, const uint32_t row_bytes, const int32_t nslabs) {
+  const int32_t* __restrict__ ptr = S.ptr;
+  const int32_t* __restrict__ idx = S.idx;
+  const float* __restrict__ val = S.val;
+  const int32_t rows = S.rows;
+  const char* __restrict__ X = S.X;
+  char* __restrict__ Y = S.Y;
+  const int32_t rows_per_block = S.rows_per_block;
+  const X2Out& x2 = S.x2;
   constexpr int P = PairAcc<T>::kPairs;
   constexpr int kWarps = kSweepThreads / 32;
   constexpr uint32_t kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int slab = blockIdx.x % nslabs;
-  const int32_t r_begin = (blockIdx.x / nslabs) * rows_per_block;
+  const int slab = side_block % nslabs;
+  const int32_t r_begin = (side_block / nslabs) * rows_per_block;
   const int32_t r_end = min(rows, r_begin + rows_per_block);
   const uint32_t col0 = (uint32_t)(slab * 32 * CH + lane) * 16u;    // byte column of this lane's first chunk
   const uint64_t xbase = reinterpret_cast<uint64_t>(X) + col0;      // (row_bytes is a multiple of the slab: no bounds tests)
@@ -318,24 +333,51 @@ spmm_sweep_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ i
 }
 
 template <typename T, int CH, int U, bool kX2 = false>
-int launch_sweep(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const void* X, void* Y,
-                 int32_t chunks, cudaStream_t st, const X2Out x2 = X2Out()) {
-  const int nslabs = chunks / (32 * CH);
+__global__ void __launch_bounds__(kSweepThreads, 1)
+spmm_sweep_kernel(const __grid_constant__ SweepSide sa, const __grid_constant__ SweepSide sb, int blocks_a, uint32_t row_bytes,
+                  int32_t nslabs) {
+  if ((int)blockIdx.x < blocks_a) sweep_side<T, CH, U, kX2>(sa, (int)blockIdx.x, row_bytes, nslabs);
+  else sweep_side<T, CH, U, kX2>(sb, (int)blockIdx.x - blocks_a, row_bytes, nslabs);
+}
+
+// `share` of the co-resident CTAs (one per SM) this side may use: row ranges x slabs
+inline int plan_side(SweepSide& s, int nslabs, int share) {
   constexpr int kWarps = kSweepThreads / 32;
-  const int want_blocks = max(1, sm_count() / nslabs);          // one CTA per SM, all co-resident
-  const int rows_per_block = max(ceil_div(rows, want_blocks), kWarps);   // even split: every SM gets the same share
-  const int nblocks = ceil_div(rows, rows_per_block);
+  if (s.rows <= 0) { s.rows_per_block = kWarps; return 0; }
+  const int want_blocks = max(1, share / nslabs);                // row ranges of this side
+  s.rows_per_block = max(ceil_div(s.rows, want_blocks), kWarps);  // even split: every SM gets the same share
+  return ceil_div(s.rows, s.rows_per_block) * nslabs;
+}
+
+template <typename T, int CH, int U, bool kX2 = false>
+int launch_sweep_sides(SweepSide a, SweepSide b, int32_t chunks, int64_t nnz, cudaStream_t st) {
+  const int nslabs = chunks / (32 * CH);
   static bool carved = false;      // no shared memory is used: ask for the whole 228 KB as L1 (it holds the band)
   if (!carved) {
     cudaFuncSetAttribute(spmm_sweep_kernel<T, CH, U, kX2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     carved = true;
   }
-  spmm_sweep_kernel<T, CH, U, kX2><<<nblocks * nslabs, kSweepThreads, 0, st>>>(
-      ptr, idx, val, rows, reinterpret_cast<const char*>(X), reinterpret_cast<char*>(Y), (uint32_t)chunks * 16u, nslabs,
-      rows_per_block, x2);
+  // SMs in proportion to the sides' work: every nonzero gathers one slab row, every output row writes one
+  int share_a = sm_count();
+  if (b.rows > 0) {
+    const double wa = (double)nnz + a.rows, wb = (double)nnz + b.rows;
+    share_a = (int)(sm_count() * wa / (wa + wb) + 0.5);
+    share_a = max(nslabs, min(sm_count() - nslabs, share_a / nslabs * nslabs));
+  }
+  const int blocks_a = plan_side(a, nslabs, share_a);
+  const int blocks_b = plan_side(b, nslabs, sm_count() - share_a);
+  spmm_sweep_kernel<T, CH, U, kX2><<<blocks_a + blocks_b, kSweepThreads, 0, st>>>(a, b, blocks_a, (uint32_t)chunks * 16u, nslabs);
   LPGNN_LAUNCH_OK();
   count_launches(1);
   return LPGNN_OK;
+}
+
+template <typename T, int CH, int U, bool kX2 = false>
+int launch_sweep(const int32_t* ptr, const int32_t* idx, const float* val, int32_t rows, const void* X, void* Y,
+                 int32_t chunks, cudaStream_t st, const X2Out x2 = X2Out()) {
+  SweepSide a{ptr, idx, val, rows, reinterpret_cast<const char*>(X), reinterpret_cast<char*>(Y), 0, x2};
+  SweepSide none{};
+  return launch_sweep_sides<T, CH, U, kX2>(a, none, chunks, 0, st);
 }
 
 template <typename T>
@@ -417,6 +459,48 @@ extern "C" int lpgnn_spmm(const int32_t* ptr, const int32_t* idx, const float* v
   return lpgnn_spmm_ex(ptr, idx, val, rows, X, Y, F, dtype, 0, 0, stream);
 }
 
+// 0: lpgnn_spmm_pair / lpgnn_spmm_x2_pair always run as two launches (environment LPGNN_SPMM_PAIR=0, lpgnn_set_spmm_pair: A/B)
+static int g_spmm_pair = [] { const char* e = getenv("LPGNN_SPMM_PAIR"); return e ? atoi(e) != 0 : 1; }();
+
+extern "C" int lpgnn_set_spmm_pair(int enable) {
+  const int prev = g_spmm_pair;
+  g_spmm_pair = enable ? 1 : 0;
+  return prev;
+}
+
+// Both aggregations of a layer in ONE launch where both take the banded sweep (agg_t [n,F] = A^T L over the CSC view,
+// agg_s [m,F] = A R over the CSR view): each side gets the SMs its work asks for, the launch has one ramp and one tail.
+// Anything else (small graphs, rows that are no multiple of the slab) is two lpgnn_spmm calls.  Same bits either way.
+extern "C" int lpgnn_spmm_pair(const int32_t* rowptr, const int32_t* col, const float* val, int32_t m, const int32_t* colptr,
+                               const int32_t* row_csc, const float* val_csc, int32_t n, int64_t nnz, const void* L,
+                               const void* R, void* agg_s, void* agg_t, int32_t F, int dtype, lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(m >= 0 && n >= 0 && F > 0, "spmm_pair: bad shape m=%d n=%d F=%d", m, n, F);
+  if (nnz < 0) nnz = 4 * (int64_t)(m > n ? m : n);     // unknown on the host: LP-typical density, only steers the SM split
+  LPGNN_REQUIRE(dtype_ok(dtype), "spmm_pair: bad dtype %d", dtype);
+  const int esz = dtype == LPGNN_F32 ? 4 : 2;
+  const int row_bytes = F * esz;
+  const int slab = row_bytes % 1024 == 0 ? 1024 : (row_bytes % 512 == 0 ? 512 : -1);
+  const bool sweep = g_spmm_pair && slab > 0 && (int64_t)m * (row_bytes / slab) >= (int64_t)sm_count() * 64 &&
+                     (int64_t)n * (row_bytes / slab) >= (int64_t)sm_count() * 64;
+  if (!sweep) {
+    if (int rc = lpgnn_spmm(colptr, row_csc, val_csc, n, L, agg_t, F, dtype, stream)) return rc;
+    return lpgnn_spmm(rowptr, col, val, m, R, agg_s, F, dtype, stream);
+  }
+  LPGNN_REQUIRE(rowptr && colptr && L && R && agg_s && agg_t, "spmm_pair: null pointer");
+  LPGNN_REQUIRE(((uintptr_t)L | (uintptr_t)R | (uintptr_t)agg_s | (uintptr_t)agg_t) % 16 == 0, "spmm_pair: X/Y must be 16-byte aligned");
+  SweepSide t{colptr, row_csc, val_csc, n, reinterpret_cast<const char*>(L), reinterpret_cast<char*>(agg_t), 0, X2Out()};
+  SweepSide sd{rowptr, col, val, m, reinterpret_cast<const char*>(R), reinterpret_cast<char*>(agg_s), 0, X2Out()};
+  const int32_t chunks = row_bytes / 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LPGNN_F32)
+    return slab == 1024 ? launch_sweep_sides<float, 2, 4>(t, sd, chunks, nnz, st) : launch_sweep_sides<float, 1, 4>(t, sd, chunks, nnz, st);
+  if (dtype == LPGNN_F16)
+    return slab == 1024 ? launch_sweep_sides<__half, 2, 2>(t, sd, chunks, nnz, st) : launch_sweep_sides<__half, 1, 2>(t, sd, chunks, nnz, st);
+  return slab == 1024 ? launch_sweep_sides<__nv_bfloat16, 2, 2>(t, sd, chunks, nnz, st)
+                      : launch_sweep_sides<__nv_bfloat16, 1, 2>(t, sd, chunks, nnz, st);
+}
+
 // (a2, fp32 tensor-core mode) Aggregation of fp32 features straight into x2 operands: hi / lo IEEE-half [rows,F] + a
 // power-of-two scale per row (lpgnn_split_x2's format; Y = scale * (hi + 2^-11 lo) to 22 bits) -- the fp32 aggregate never
 // reaches HBM and no split pass reads it back.  src_scale [n_src]: |X[j,:]| <= src_scale[j] * 2^12 (as written by
@@ -439,4 +523,33 @@ extern "C" int lpgnn_spmm_x2(const int32_t* ptr, const int32_t* idx, const float
   LPGNN_REQUIRE(scratch, "spmm_x2: this shape takes the two-step path and needs the fp32 scratch [rows,F]");
   if (int rc = lpgnn_spmm(ptr, idx, val, rows, X, scratch, F, LPGNN_F32, stream)) return rc;
   return lpgnn_split_x2(scratch, F, nullptr, 0, rows, hi, lo, nullptr, nullptr, scale, stream);
+}
+
+// The two aggregations of the first hidden layer in the fp32 tensor-core mode, one launch (see lpgnn_spmm_pair /
+// lpgnn_spmm_x2): side t = A^T L -> (hi_t, lo_t, scale_t), side s = A R -> (hi_s, lo_s, scale_s).
+extern "C" int lpgnn_spmm_x2_pair(const int32_t* rowptr, const int32_t* col, const float* val, int32_t m, const int32_t* colptr,
+                                  const int32_t* row_csc, const float* val_csc, int32_t n, int64_t nnz, const float* L,
+                                  const float* R, int32_t F, const float* scale_L, const float* scale_R, void* hi_s, void* lo_s,
+                                  float* scale_s, void* hi_t, void* lo_t, float* scale_t, float* scratch_s, float* scratch_t,
+                                  lpgnn_stream_t stream) {
+  if (int rc = check_device()) return rc;
+  LPGNN_REQUIRE(m >= 0 && n >= 0 && F > 0 && F % 4 == 0, "spmm_x2_pair: bad shape m=%d n=%d F=%d", m, n, F);
+  if (nnz < 0) nnz = 4 * (int64_t)(m > n ? m : n);
+  const int row_bytes = F * 4;
+  const bool sweep = g_spmm_pair && row_bytes % 1024 == 0 && (int64_t)m * (row_bytes / 1024) >= (int64_t)sm_count() * 64 &&
+                     (int64_t)n * (row_bytes / 1024) >= (int64_t)sm_count() * 64;
+  if (!sweep) {
+    if (int rc = lpgnn_spmm_x2(colptr, row_csc, val_csc, n, L, F, scale_L, hi_t, lo_t, scale_t, scratch_t, stream)) return rc;
+    return lpgnn_spmm_x2(rowptr, col, val, m, R, F, scale_R, hi_s, lo_s, scale_s, scratch_s, stream);
+  }
+  LPGNN_REQUIRE(rowptr && colptr && L && R && scale_L && scale_R && hi_s && lo_s && scale_s && hi_t && lo_t && scale_t,
+                "spmm_x2_pair: null pointer");
+  LPGNN_REQUIRE(((uintptr_t)L | (uintptr_t)R) % 16 == 0 && ((uintptr_t)hi_s | (uintptr_t)lo_s | (uintptr_t)hi_t | (uintptr_t)lo_t) % 8 == 0,
+                "spmm_x2_pair: misaligned pointer");
+  X2Out xt, xs;
+  xt.src_scale = scale_L; xt.hi = reinterpret_cast<char*>(hi_t); xt.lo = reinterpret_cast<char*>(lo_t); xt.scale = scale_t;
+  xs.src_scale = scale_R; xs.hi = reinterpret_cast<char*>(hi_s); xs.lo = reinterpret_cast<char*>(lo_s); xs.scale = scale_s;
+  SweepSide t{colptr, row_csc, val_csc, n, reinterpret_cast<const char*>(L), nullptr, 0, xt};
+  SweepSide sd{rowptr, col, val, m, reinterpret_cast<const char*>(R), nullptr, 0, xs};
+  return launch_sweep_sides<float, 2, 4, true>(t, sd, row_bytes / 16, nnz, (cudaStream_t)stream);
 }

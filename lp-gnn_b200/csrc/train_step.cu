@@ -251,8 +251,9 @@ extern "C" int lpgnn_train_forward(const lpgnn_gcn_fc_weights* w, const int32_t*
                                   B.left[0], dt, LPGNN_EPI_RELU, B.z_s, stream));
   }
   for (int li = 0; li < nh; ++li) {
-    LPGNN_TRY(lpgnn_spmm(colptr, row_csc, val_csc, n, B.left[li], B.agg_t[li], H, dt, stream));
-    LPGNN_TRY(lpgnn_spmm(rowptr, col, val, m, B.right[li], B.agg_s[li], H, dt, stream));
+    // A^T . left and A . right in one launch where both take the banded sweep (nnz is not known on the host here: -1)
+    LPGNN_TRY(lpgnn_spmm_pair(rowptr, col, val, m, colptr, row_csc, val_csc, n, -1, B.left[li], B.right[li], B.agg_s[li],
+                              B.agg_t[li], H, dt, stream));
     // reference order is dropout then relu_ (arch.py:186-188); the two commute and both sit in the epilogue
     lpgnn_epilogue_args ea;
     ea.epilogue = LPGNN_EPI_RELU; ea.dropout_p = dropout_p; ea.mask_act = nullptr; ea.mask_scale = 1.f;
@@ -381,8 +382,8 @@ extern "C" int lpgnn_train_backward_ex(const lpgnn_gcn_fc_weights* w, const int3
     // data gradients.  dL = A (dPre_t W_rel^{l2r}) + dPre_s W_root^{r2l} = [A dPre_t | dPre_s] [W_rel^{l2r} ; W_root^{r2l}]:
     // aggregate first, then ONE two-operand transform per side (transposed weights prepared by the forward call)
     // whose epilogue applies the ReLU / dropout mask of the layer input.
-    LPGNN_TRY(lpgnn_spmm(rowptr, col, val, m, dpt, B.dlagg, H, dt, stream));          // A   dPre_t  [m,H]
-    LPGNN_TRY(lpgnn_spmm(colptr, row_csc, val_csc, n, dps, B.dragg, H, dt, stream));  // A^T dPre_s  [n,H]
+    // A dPre_t [m,H] and A^T dPre_s [n,H]: the same pair launch on the gradients
+    LPGNN_TRY(lpgnn_spmm_pair(rowptr, col, val, m, colptr, row_csc, val_csc, n, -1, dps, dpt, B.dlagg, B.dragg, H, dt, stream));
     lpgnn_epilogue_args ea;
     ea.epilogue = LPGNN_EPI_NONE; ea.dropout_p = 0.f; ea.dropout_seed = 0;
     ea.mask_scale = li > 0 ? scale : 1.f;   // conv1's output has no dropout

@@ -33,6 +33,27 @@ def spmm(view, x: torch.Tensor, slab_bytes: int = 0, unroll: int = 0) -> torch.T
     return y
 
 
+def spmm_pair(csr, csc, left, right, nnz=-1):
+    """Both aggregations of a layer in one launch where both take the banded sweep (``lpgnn_spmm_pair``):
+    ``agg_s[m,F] = A @ right`` (CSR view), ``agg_t[n,F] = A^T @ left`` (CSC view).  Returns ``(agg_s, agg_t)``, the bits of
+    two ``spmm`` calls.  ``nnz`` only steers how the SMs are split between the two sides (-1: unknown)."""
+    rowptr, col, val, m = csr
+    colptr, row_csc, val_csc, n = csc
+    require_cuda(rowptr, colptr, left, right)
+    left, right = _contig(left), _contig(right)
+    if left.dtype != right.dtype or left.shape[1] != right.shape[1]:
+        raise TypeError("spmm_pair: both feature matrices must share dtype and width")
+    F = left.shape[1]
+    agg_s = torch.empty((m, F), dtype=left.dtype, device=left.device)
+    agg_t = torch.empty((n, F), dtype=left.dtype, device=left.device)
+    with torch.cuda.device(left.device):
+        rc = _lib.load().lpgnn_spmm_pair(rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), m, colptr.data_ptr(), row_csc.data_ptr(),
+                                         val_csc.data_ptr(), n, int(nnz), left.data_ptr(), right.data_ptr(), agg_s.data_ptr(),
+                                         agg_t.data_ptr(), F, dtype_code(left.dtype), stream_ptr())
+    check(rc, "lpgnn_spmm_pair")
+    return agg_s, agg_t
+
+
 def conv_in_fused(view, x_src, x_dst, w_rel, b_rel, w_root, out_dtype, relu=True):
     """conv1 of GCN_FC for one direction: ``relu(lin_rel(A_view @ x_src) + lin_root(x_dst))`` (reference
     arch.py:75-80, 181-182).  Returns ``(out[rows,N], z_cat[rows,KT])`` where ``z_cat = [A_view@x_src | x_dst | 0]``
@@ -373,6 +394,29 @@ def spmm_x2(view, x, src_scale):
                                        hi.data_ptr(), lo.data_ptr(), scale.data_ptr(), scratch.data_ptr(), stream_ptr())
     check(rc, "lpgnn_spmm_x2")
     return (hi, lo), scale
+
+
+def spmm_x2_pair(csr, csc, left, right, scale_left, scale_right, nnz=-1):
+    """``spmm_x2`` for both directions in one launch (``lpgnn_spmm_x2_pair``).  Returns
+    ``(((hi_s, lo_s), scale_s), ((hi_t, lo_t), scale_t))`` for ``A @ right`` and ``A^T @ left``."""
+    rowptr, col, val, m = csr
+    colptr, row_csc, val_csc, n = csc
+    require_cuda(rowptr, colptr, left, right, scale_left, scale_right)
+    left, right = _contig(left.float()), _contig(right.float())
+    scale_left, scale_right = _contig(scale_left.float()), _contig(scale_right.float())
+    F = left.shape[1]
+    dev = left.device
+    mk = lambda rows: (torch.empty((rows, F), dtype=torch.float16, device=dev), torch.empty((rows, F), dtype=torch.float16, device=dev),
+                       torch.empty(rows, dtype=torch.float32, device=dev), torch.empty((rows, F), dtype=torch.float32, device=dev))
+    hi_s, lo_s, sc_s, tmp_s = mk(m)
+    hi_t, lo_t, sc_t, tmp_t = mk(n)
+    with torch.cuda.device(dev):
+        rc = _lib.load().lpgnn_spmm_x2_pair(rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), m, colptr.data_ptr(), row_csc.data_ptr(),
+                                            val_csc.data_ptr(), n, int(nnz), left.data_ptr(), right.data_ptr(), F, scale_left.data_ptr(),
+                                            scale_right.data_ptr(), hi_s.data_ptr(), lo_s.data_ptr(), sc_s.data_ptr(), hi_t.data_ptr(),
+                                            lo_t.data_ptr(), sc_t.data_ptr(), tmp_s.data_ptr(), tmp_t.data_ptr(), stream_ptr())
+    check(rc, "lpgnn_spmm_x2_pair")
+    return ((hi_s, lo_s), sc_s), ((hi_t, lo_t), sc_t)
 
 
 def set_x2_chunk(kblocks: int) -> int:

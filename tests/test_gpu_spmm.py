@@ -208,3 +208,39 @@ def test_c4_shape_banded_sweep_is_checked_not_only_timed(cuda, dtype):
             assert np.mean(got == torch.from_numpy(e).to(dtype).float().numpy()) > 0.99
             np.testing.assert_allclose(got, e, rtol=2e-3, atol=2e-3)
         del x, y
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("m,n,z,F", [(50_000, 100_000, 500_000, 1024), (30_000, 9_000, 200_000, 256), (9_000, 30_000, 100_000, 512),
+                                     (700, 1300, 6000, 64), (5, 40_000, 60_000, 1024), (20_000, 41_000, 0, 1024)])
+def test_pair_launch_equals_two_aggregations(cuda, dtype, m, n, z, F):
+    """lpgnn_spmm_pair (A R and A^T L in one launch where both take the banded sweep, the SMs split by work; two plain
+    launches otherwise) returns the bits of two lpgnn_spmm calls, with and without the nonzero count as a hint."""
+    from lpgnn_b200 import ops
+    g, _ = _graph(m, n, z, 3, cuda)
+    csr, csc = g.views()
+    gen = torch.Generator(device="cuda").manual_seed(m + F)
+    left = torch.randn(m, F, device=cuda, generator=gen).to(dtype)
+    right = torch.randn(n, F, device=cuda, generator=gen).to(dtype)
+    agg_s, agg_t = ops.spmm(csr, right), ops.spmm(csc, left)
+    for hint in (g.nnz(), -1):
+        ps, pt = ops.spmm_pair(csr, csc, left, right, nnz=hint)
+        assert torch.equal(ps, agg_s) and torch.equal(pt, agg_t)
+
+
+@pytest.mark.parametrize("m,n,z,F", [(50_000, 100_000, 500_000, 1024), (700, 1300, 6000, 128), (30_000, 70_000, 300_000, 256)])
+def test_x2_pair_launch_equals_two_aggregations(cuda, m, n, z, F):
+    """lpgnn_spmm_x2_pair == two lpgnn_spmm_x2 calls (hi / lo operands and row scales), sweep and two-step shapes."""
+    from lpgnn_b200 import ops
+    g, _ = _graph(m, n, z, 4, cuda)
+    csr, csc = g.views()
+    gen = torch.Generator(device="cuda").manual_seed(n + F)
+    left = torch.randn(m, F, device=cuda, generator=gen)
+    right = torch.randn(n, F, device=cuda, generator=gen)
+    # row-scale bounds as the producer of the features reports them: |X[j,:]| <= scale[j] * 2^12
+    sl = (left.abs().amax(1) / 4096).clamp_min(1e-30)
+    sr = (right.abs().amax(1) / 4096).clamp_min(1e-30)
+    (s_ops, s_sc), (t_ops, t_sc) = ops.spmm_x2(csr, right, sr), ops.spmm_x2(csc, left, sl)
+    ((hs, ls), ss), ((ht, lt), st) = ops.spmm_x2_pair(csr, csc, left, right, sl, sr, nnz=g.nnz())
+    assert torch.equal(hs, s_ops[0]) and torch.equal(ls, s_ops[1]) and torch.equal(ss, s_sc)
+    assert torch.equal(ht, t_ops[0]) and torch.equal(lt, t_ops[1]) and torch.equal(st, t_sc)
